@@ -1,0 +1,115 @@
+/* lnr_b200.h -- C ABI of the B200-native approximate-map path of `linear filter` (xp3i4/linear).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Every entry point names the reference interface it replaces (paths relative to the reference tree).
+ * INTEGRATION.md shows the shim a maintainer adds on the reference side (SeqAn String <-> these buffers).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative LNR_E_* code otherwise; lnr_last_error() gives text.
+ *     The reference's functions on this path always return 0 and never throw (pmpfinder.cpp:2709).
+ *   - sequences are the reference's Dna5 ordinals, one byte per base: A,C,G,T,N = 0..4 (base.h:106-116).
+ *   - `threads_sem` is the reference's -t. It is a SEMANTIC parameter of the index and of the genome
+ *     feature builder (chunk seams: index_util.cpp:1654-1670, pmpfinder.cpp:603-650), not a degree of
+ *     parallelism here.
+ *   - cords / anchors / hits are the reference's 64-bit encodings (include/cords.h:23-39).
+ *   - there is no CPU fallback: without a CUDA device every call fails with LNR_E_CUDA.
+ */
+#ifndef LNR_B200_H
+#define LNR_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNR_OK 0
+#define LNR_E_CUDA (-1)      /* CUDA runtime error or no device */
+#define LNR_E_ARG (-2)       /* invalid argument */
+#define LNR_E_CAPACITY (-3)  /* caller buffer too small; *needed outputs say how much */
+#define LNR_E_UNSUPPORTED (-4)
+#define LNR_E_LIMIT (-5)     /* input outside the reference's own limits (contig >= 2^30, > 1024 contigs, read >= 2^20) */
+
+typedef struct lnr_ctx lnr_ctx;
+typedef struct lnr_genome lnr_genome;
+typedef struct lnr_feats lnr_feats;
+typedef struct lnr_index lnr_index;
+
+/* ---- context -------------------------------------------------------------------------------------*/
+int lnr_ctx_create(int device, lnr_ctx ** out);
+void lnr_ctx_destroy(lnr_ctx *);
+const char * lnr_last_error(const lnr_ctx *);
+/* record a CUDA-event pair around every kernel launched through this context (bench/roofline) */
+int lnr_ctx_set_profiling(lnr_ctx *, int on);
+/* kernels launched since the last reset: n names/ms/counts copied (up to cap); returns total distinct */
+int lnr_ctx_kernel_times(lnr_ctx *, int cap, const char ** names, float * total_ms, uint64_t * launches);
+int lnr_ctx_reset_kernel_times(lnr_ctx *);
+
+/* ---- genome: replaces Mapper::loadGenomes' in-memory StringSet<String<Dna5>> (mapper.cpp:389) --------*/
+int lnr_genome_upload(lnr_ctx *, uint32_t n_contigs, const uint8_t * const * dna5, const uint64_t * len,
+                      lnr_genome ** out);
+/* same, but the bases are already in device memory, contigs back to back in one buffer (bench "value" leg) */
+int lnr_genome_from_device(lnr_ctx *, uint32_t n_contigs, const uint8_t * dev_concat, const uint64_t * len,
+                           lnr_genome ** out);
+void lnr_genome_destroy(lnr_genome *);
+
+/* ---- genome features: createFeatures(StringSet<String<Dna5>>&, StringSet<FeaturesDynamic>&, int, unsigned)
+ *      pmpfinder.cpp:775 -> createFeatures2_48 (parallel builder) :589.  feature_type 2 = 2-mer/48 (-f 2) */
+int lnr_features_build(lnr_ctx *, const lnr_genome *, int feature_type, unsigned threads_sem, lnr_feats ** out);
+int lnr_features_count(const lnr_feats *, uint32_t contig, uint64_t * n_entries);
+/* dst: int32[3*n] (int96 entries) for feature_type 2 */
+int lnr_features_download(const lnr_feats *, uint32_t contig, void * dst, uint64_t cap_entries, uint64_t * n_entries);
+void lnr_features_destroy(lnr_feats *);
+
+/* ---- index: createIndexDynamic(..., threads, efficient) index_util.cpp:2478 -> createDIndex :1628 -------
+ *      index_type 1 = DIndex (-i 1, the default), 2 = HIndex (-i 2) */
+int lnr_index_build(lnr_ctx *, const lnr_genome *, int index_type, unsigned threads_sem, lnr_index ** out);
+/* DIndex contents: dir = int32[2^26+1], hs = uint64[n_hs] (include/index_util.h:99-120).
+ * Pass NULL for dir/hs to query n_hs only. */
+int lnr_index_export_dindex(const lnr_index *, int32_t * dir, uint64_t * hs, uint64_t hs_cap, uint64_t * n_hs);
+void lnr_index_destroy(lnr_index *);
+
+/* ---- per-read approximate mapping -------------------------------------------------------------------
+ * Replaces, for every read j of a block (Mapper::p_calRecords mapper.cpp:438-447, map_ :825-849):
+ *     _compltRvseStr(read, comStr); createFeatures(read) ; createFeatures(comStr);      base.cpp:335, pmpfinder.cpp:724
+ *     apxMap(index, read, anchors, crhit, f1, f2, apx_gaps, cords_str, cords_end, cords_info,
+ *            f_chain=1, pm_g, pm_pmp);                                                   pmpfinder.cpp:2709
+ * Reads with length <= 200 get an empty cord list (mapper.cpp:440). cords_end[i] = cords_str[i] +
+ * ((W<<20)|W), W = lnr_params.window (96 for -f 2), is reconstructed by the caller (pmpfinder.cpp:2801). */
+typedef struct lnr_params
+{
+    int preset;       /* -p: 0 => thd_stop_chain_len_ratio 0.7, 1/2 => 0 (mapper.cpp:174-197); code default 1 */
+    int feature_type; /* -f: 2 */
+    int reserved[6];
+} lnr_params;
+
+/* optional stage checkpoints; any pointer may be NULL. Offsets arrays hold n_reads+1 entries. */
+typedef struct lnr_debug_out
+{
+    uint64_t * raw_anchors; uint64_t raw_anchors_cap; uint64_t * raw_anchors_off;   /* getDIndexMatchAll, primary call, without the anchors[0] sentinel */
+    uint64_t * hits;        uint64_t hits_cap;        uint64_t * hits_off;          /* hits after getAnchorHitsChains (primary call) */
+    uint64_t * cords1;      uint64_t cords1_cap;      uint64_t * cords1_off;        /* cords after the first apxMap_ */
+} lnr_debug_out;
+
+/* host buffers in, host buffers out (the drop-in call; copies are part of the call) */
+int lnr_apxmap_batch(lnr_ctx *, const lnr_index *, const lnr_feats * f2, const lnr_params *,
+                     uint32_t n_reads, const uint8_t * dna5_concat, const uint64_t * read_off /* n+1 */,
+                     uint64_t * cords_str_concat, uint64_t * cords_off /* n+1 */, uint64_t cords_capacity,
+                     lnr_debug_out * dbg /* may be NULL */);
+/* device buffers in, device buffers out (inputs already resident in HBM; bench "value" leg).
+ * n_cords_total (host) receives the number of cords written. */
+int lnr_apxmap_batch_device(lnr_ctx *, const lnr_index *, const lnr_feats * f2, const lnr_params *,
+                            uint32_t n_reads, const uint8_t * dev_dna5_concat, const uint64_t * host_read_off,
+                            uint64_t * dev_cords, uint64_t * dev_cords_off, uint64_t cords_capacity,
+                            uint64_t * n_cords_total);
+/* algorithmic-byte counters of the last batch: S seeds, H bucket records scanned, A raw anchors,
+ * Hits, W window candidates evaluated, C cords */
+int lnr_last_batch_counters(lnr_ctx *, uint64_t counters[8]);
+
+/* read features of one read (both strands), for the host gap stage and for parity tests:
+ * createFeatures(begin(read), end(read), f1[s]) pmpfinder.cpp:724 -> createFeatures2_48 (serial) :556 */
+int lnr_read_features(lnr_ctx *, const uint8_t * dna5, uint64_t len, int feature_type,
+                      void * dst_fwd, void * dst_rev, uint64_t cap_entries, uint64_t * n_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1147 @@
+// Per-read approximate-map pipeline: everything apxMap (pmpfinder.cpp:2709) does after seeding.
+//
+// One warp owns one read. Data-parallel pieces (binning, radix sorts, the chaining DP's predecessor scan,
+// traceback maxima, hit window filtering) are spread over the 32 lanes; the small data-dependent
+// sequential pieces (run filter, traceback bookkeeping, block cutting, window extension, block chaining)
+// run on lane 0 over the warp's private scratch arena. All comparator-tie behaviour of the reference's
+// std::sort call sites is reproduced with lnr::gnu_sort (lnr_sortlib.h).
+//
+// The file is plain C++ when compiled without nvcc (single-lane warp, tests/host_emu) so the logic can be
+// verified against the oracle on a CPU-only machine. Reference citations: file:line in the reference tree.
+#pragma once
+#include "lnr_defs.h"
+#include "lnr_sortlib.h"
+#include "lnr_warp.h"
+
+namespace lnr {
+
+// ----------------------------------------------------------------------------------------------------
+// small types
+// ----------------------------------------------------------------------------------------------------
+struct ChainRec { i32 score, score2, len, p2anchor, root_ptr, f_leaf; };   // cluster_util.h:38-48
+struct Blk { u32 first, second; };                                         // UPair of pointers [first, second)
+struct YPair { u64 first, second; };                                       // UPair of cords
+
+struct PipeIn
+{
+    const u8 * read;            // forward read bases (unused after seeding, kept for debugging)
+    u32 L;                      // read length
+    const F96 * f1[2];          // read features, strand 0 / 1           (createFeatures2_48 serial)
+    u32 nf1;                    // entries per strand
+    const F96 * const * f2;     // genome features per contig            (createFeatures2_48 parallel)
+    const u32 * nf2;            // entries per contig
+    float stop_ratio;           // ChainAnchorsHitsParms::thd_stop_chain_len_ratio (0.7 or 0, mapper.cpp:184)
+};
+
+struct PipeCounters { u64 hits, windows; };
+
+static const int kNumBins = (1 << 30) / 30000 + 2;   // binningFilter bins over a 30-bit x (pmpfinder.cpp:1984)
+
+// ----------------------------------------------------------------------------------------------------
+// window distance (pmpfinder.cpp:493-535)
+// ----------------------------------------------------------------------------------------------------
+LNR_HD int script_dist(i32 s1, i32 s2)   // __scriptDist63_31: packed 6-bit fields, bias 31, borrows kept
+{
+    const i32 mxu31 = (31 << 24) + (31 << 18) + (31 << 12) + (31 << 6) + 31;
+    i32 d = (i32)((u32)s1 + (u32)mxu31 - (u32)s2);
+    i32 a = ((d >> 24) & 63) - 31, b = ((d >> 18) & 63) - 31, c = ((d >> 12) & 63) - 31, e = ((d >> 6) & 63) - 31,
+        f = (d & 63) - 31;
+    return (a < 0 ? -a : a) + (b < 0 ? -b : b) + (c < 0 ? -c : c) + (e < 0 ? -e : e) + (f < 0 ? -f : f);
+}
+LNR_HD u32 window_dist48(const F96 * a, const F96 * b)   // _windowDist2_48: scripts at offsets {0,3}
+{
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i += 3)
+        s += script_dist(a[i].v[0], b[i].v[0]) + script_dist(a[i].v[1], b[i].v[1]) + script_dist(a[i].v[2], b[i].v[2]);
+    return (u32)s;
+}
+// __windowDist (pmpfinder.cpp:655). The reference does not bounds-check here; for in-spec inputs the
+// indices are in range, the guard only keeps the device from faulting on out-of-spec data.
+LNR_HD u32 wdist(const PipeIn & in, u32 strand, u32 id, u64 y, u64 x, PipeCounters & cnt)
+{
+    cnt.windows++;
+    if (y + 3 >= in.nf1 || x + 3 >= in.nf2[id]) return 1000;
+    return window_dist48(in.f1[strand] + y, in.f2[id] + x);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// stable LSD radix sort of 64-bit keys by an extracted sub-key, 8 bits per pass, warp-cooperative.
+// `src` is never written; passes ping-pong between t0 and t1; returns the buffer holding the result.
+// Passes whose digit is identical for all keys are skipped. hist: 256 u32 of warp-private scratch.
+// ----------------------------------------------------------------------------------------------------
+struct KeyAsc { LNR_HD u64 operator()(u64 v) const { return v; } };
+struct KeyXDesc { LNR_HD u64 operator()(u64 v) const { return (u64)0x3fffffffULL - anchor_x(v); } };
+
+template <class KeyFn>
+LNR_PIPE u64 * radix_sort(const Warp & w, u32 * hist, u64 * src, u64 * t0, u64 * t1, int n, int key_bits, KeyFn key)
+{
+    // which bits vary at all
+    u64 vor = 0, vand = ~0ULL;
+    for (int i = w.lane; i < n; i += w.nl) { u64 k = key(src[i]); vor |= k; vand &= k; }
+    vor = wor64(w, vor);
+    vand = ~wor64(w, ~vand);
+    u64 diff = vor ^ vand;
+    u64 * in = src;
+    u64 * out = t0;
+    for (int shift = 0; shift < key_bits; shift += 8)
+    {
+        if (((diff >> shift) & 0xff) == 0) continue;
+        for (int b = w.lane; b < 256; b += w.nl) hist[b] = 0;
+        wsync(w);
+        for (int i = w.lane; i < n; i += w.nl)
+        {
+            u32 d = (u32)(key(in[i]) >> shift) & 0xff;
+#ifdef __CUDA_ARCH__
+            atomicAdd(&hist[d], 1u);
+#else
+            hist[d]++;
+#endif
+        }
+        wsync(w);
+        // exclusive scan of the 256 bins
+        {
+            int per = 256 / w.nl;
+            int b0 = w.lane * per, s = 0;
+            for (int b = 0; b < per; b++) s += (int)hist[b0 + b];
+            int total;
+            int base = wscan_excl(w, s, total);
+            for (int b = 0; b < per; b++) { int c = (int)hist[b0 + b]; hist[b0 + b] = (u32)base; base += c; }
+        }
+        wsync(w);
+        // stable scatter, 32 keys at a time in index order
+        for (int c = 0; c < n; c += w.nl)
+        {
+            int i = c + w.lane;
+            bool valid = i < n;
+            u64 v = valid ? in[i] : 0;
+            u32 d = valid ? ((u32)(key(v) >> shift) & 0xff) : 0x100u + (u32)w.lane;
+            u32 peers = wmatch(w, d);
+            int rank = popc_below(w, peers);
+            u32 base = valid ? hist[d] : 0;
+            wsync(w);
+            if (valid)
+            {
+                out[base + rank] = v;
+                if (rank == popc32(peers) - 1) hist[d] = base + rank + 1;   // highest lane of the group
+            }
+            wsync(w);
+        }
+        in = out;
+        out = (out == t0) ? t1 : t0;
+    }
+    wsync(w);
+    return in;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// anchor filters (pmpfinder.cpp:1979-2183)
+// ----------------------------------------------------------------------------------------------------
+LNR_HD u32 anchor_bin(u64 a) { return (u32)(cord_x(a) / 30000); }
+
+// binningFilter (:1979). A[0..n) -> survivors in B (or A unchanged when nothing survives). Returns the
+// buffer that holds the result and its length through n_out. `bins` is the warp's zeroed histogram and is
+// returned zeroed.
+LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u64 * A, u64 * B, int n, int & n_out)
+{
+    for (int i = w.lane; i < n; i += w.nl)
+    {
+#ifdef __CUDA_ARCH__
+        atomicAdd(&bins[anchor_bin(A[i])], 1u);
+#else
+        bins[anchor_bin(A[i])]++;
+#endif
+    }
+    wsync(w);
+    int ii = 0;
+    for (int c = 0; c < n; c += w.nl)
+    {
+        int i = c + w.lane;
+        u64 a = i < n ? A[i] : 0;
+        bool keep = i < n && bins[anchor_bin(a)] > 10;
+        int total;
+        int pos = wscan_excl(w, keep ? 1 : 0, total);
+        if (keep) B[ii + pos] = a;
+        ii += total;
+    }
+    wsync(w);
+    for (int i = w.lane; i < n; i += w.nl) bins[anchor_bin(A[i])] = 0;
+    wsync(w);
+    if (ii != 0) { n_out = ii; return B; }
+    n_out = n;
+    return A;
+}
+
+// filterAnchorsList (:2019) on ascending-sorted anchors a[0..n), a[0] == 0. Writes accepted ranges and
+// returns their number. Sequential (running median).
+LNR_HD int filter_anchor_runs(const u64 * a, int n, Blk * ranges)
+{
+    int nr = 0;
+    u64 ak2 = a[1];
+    u64 block_str = 1, count = 0, min_y = ~0ULL, max_y = 0;
+    for (int i = 1; i < n; i++)
+    {
+        u64 y = cord_y(a[i]);
+        u64 dy2 = (u64)iabs64((i64)(y - cord_y(ak2)));
+        bool cont = cord_x40(a[i] - ak2) < (dy2 >> 2);
+        if (cont)
+        {
+            if (min_y > y) min_y = y;
+            if (max_y < y) max_y = y;
+            ak2 = a[(block_str + (u64)i) >> 1];
+            ++count;
+        }
+        if (!cont || i == n - 1)
+        {
+            u64 thd = umax64((max_y - min_y) >> 10, 2);
+            if (count > thd) { ranges[nr].first = (u32)block_str; ranges[nr].second = (u32)i; nr++; }
+            block_str = (u64)i;
+            ak2 = a[i];
+            min_y = y;
+            max_y = y;
+            count = 1;
+        }
+    }
+    return nr;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// chain scores (cluster_util.cpp:337-443, :586-860)
+// ----------------------------------------------------------------------------------------------------
+LNR_HD int score_anchor(u64 a1, u64 a2)   // getApxChainScore :387
+{
+    i64 dy = (i64)(cord_y(a1) - cord_y(a2));
+    if (dy < 10) return -10000;
+    i64 dx = (i64)(anchor_x(a1) - anchor_x(a2));
+    i64 da = iabs64(dx - dy);
+    i64 derr = (100 * da) / imax64(imax64(iabs64(dy), iabs64(dx)), 50);
+    int sderr;
+    if (derr < 5) sderr = (int)(4 * derr);
+    else if (derr < 10) sderr = (int)(6 * derr - 10);
+    else if (derr < 100) sderr = (int)(derr * derr - 5 * derr);
+    else return -1000;
+    int sdy;
+    dy /= 15;
+    if (dy < 150) sdy = (int)(dy / 5);
+    else if (dy < 100) sdy = (int)(dy - 30);
+    else if (dy < 10000) sdy = (int)(dy * dy / 200 + 20);
+    else sdy = 10000;
+    return da < 10 ? 100 - sdy : 100 - sdy - sderr;
+}
+LNR_HD int score_anchor0(u64 a1, u64 a2)   // getApxChainScore0 :337
+{
+    i64 dy = (i64)(cord_y(a1) - cord_y(a2));
+    if (dy < 5) return -10000;
+    i64 dx = (i64)(anchor_x(a1) - anchor_x(a2));
+    i64 da = iabs64(dx - dy);
+    i64 derr = (100 * da) / imax64(imax64(iabs64(dy), iabs64(dx)), 50);
+    if (derr >= 100) return -1000;
+    int sdy = (int)dy, sderr = (int)da;
+    return da < 30 ? 100 - sdy : 100 - sdy - sderr;
+}
+LNR_HD int score_blocks_hits(u64 c11, u64 c22)   // getApxChainScore2 :586
+{
+    i64 dy = (i64)(cord_y(c11) - cord_y(c22));
+    i64 dx = (i64)(cord_x(c11) - cord_x(c22));
+    if (dx < 0 || dy < 0 || cord_strand(c11 ^ c22) || dx > 20000 || dy > 20000) return (int)0x80000000;
+    i64 da = iabs64(dx - dy);
+    i64 derr = (100 * da) / imax64(imax64(iabs64(dy), 100), iabs64(dx));
+    if (da > 100 || derr > 50)
+    {
+        if (dx < dy) return (int)(100 - 30 - dy / 1000 - dx / 100);
+        return (int)(100 - 30 - dy / 100 - dx / 1000);
+    }
+    return (int)(100 - dy / 95);
+}
+LNR_HD int score_blocks_cords(u64 c11, u64 c12, u64 c21, u64 c22, u64 L, int strand)   // getApxChainScore3 :811
+{
+    i64 dx, dy;
+    // getChainBlockDxDy :774
+    if (cord_strand(c11) != (u64)strand)
+    {
+        if (cord_strand(c22) != (u64)strand) { dy = (i64)(cord_y(c21) - cord_y(c12)); dx = (i64)(cord_x(c21) - cord_x(c12)); }
+        else { dy = (i64)(L - cord_y(c12) - 1 - cord_y(c22)); dx = (i64)(cord_x(c11) - cord_x(c22)); }
+    }
+    else
+    {
+        if (cord_strand(c22) != (u64)strand) { dy = (i64)(cord_y(c11) - L + 1 + cord_y(c21)); dx = (i64)(cord_x(c11) - cord_x(c22)); }
+        else { dy = (i64)(cord_y(c11) - cord_y(c22)); dx = (i64)(cord_x(c11) - cord_x(c22)); }
+    }
+    int f_type = (int)cord_strand(c11 ^ c22);
+    i64 min_dy = -80, min_dx = -(i64)L;
+    i64 max_dy = (i64)((float)L * 1.0f);
+    i64 max_dx = 15000, dup_trigger = -50;
+    i64 dx_ = iabs64(dx), dy_ = iabs64(dy), da = dx - dy;
+    int score = 0;
+    if (dy < min_dy || dy > max_dy || dx < min_dx || dx_ > max_dx) score = (int)0x80000000;
+    else
+    {
+        i64 sdy = dy_ > 2000 ? imin64(dy_ / 25 - 50, 70) : dy_ / 40;
+        i64 sdx = dx_ > 2000 ? imin64(dx_ / 25 - 50, 70) : dx_ / 40;
+        if (f_type == 1) { if (dx > min_dx) score = (int)(75 - sdy); }
+        else if (da < -imax64(dx_ / 4, 50))
+        {
+            if (dx > dup_trigger) score = (int)(80 - sdx);
+            else score = (int)(80 - sdy);
+        }
+        else if (da > imax64(dy / 4, 50)) score = (int)(80 - sdy);
+        else score = (int)(100 - sdy);
+    }
+    return score;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// getBestChains (cluster_util.cpp:53): for each i the best predecessor among the previous 20 or any with
+// x_j - x_i < 300. The reference scans j downward and overwrites on `>=`, so among equal best sums the
+// smallest j wins. Lanes evaluate 32 predecessors at a time; the recurrence over i stays sequential.
+// ----------------------------------------------------------------------------------------------------
+LNR_PIPE void best_chains(const Warp & w, const u64 * a, ChainRec * ch, int n, int score_type)
+{
+    const int depth = 20;
+    const u64 dx_depth = 300;
+    for (int i = 0; i < n; i++)
+    {
+        u64 ai = a[i];
+        u64 xi = anchor_x(ai);
+        int j_str = i - depth > 0 ? i - depth : 0;
+        i64 best = -1;                 // packed (sum << 32) | (0x7fffffff - j); -1 = none
+        for (int jb = i - 1; jb >= 0; jb -= w.nl)
+        {
+            int j = jb - w.lane;
+            bool ok = j >= 0;
+            u64 aj = ok ? a[j] : 0;
+            ok = ok && (j >= j_str || anchor_x(aj) - xi < dx_depth);
+            if (ok)
+            {
+                int s = score_type == 0 ? score_anchor(aj, ai) : score_anchor0(aj, ai);
+                if (s > 0)
+                {
+                    i64 sum = (i64)s + (i64)ch[j].score;
+                    if (sum >= -1)
+                    {
+                        i64 key = (sum << 32) | (i64)(0x7fffffff - j);
+                        if (key > best) best = key;
+                    }
+                }
+            }
+            // the reference's loop stops at the first j that fails the range test; x is sorted
+            // descending, so the test is monotone in j and a failing lane ends the scan
+            if (wballot(w, !ok) != 0) break;
+        }
+        best = wmax_i64(w, best);
+        if (w.lane == 0)
+        {
+            int new_max = best < 0 ? -1 : (int)(best >> 32);
+            int max_j = best < 0 ? i : 0x7fffffff - (int)(best & 0x7fffffff);
+            if (new_max > 0)
+            {
+                ch[i].p2anchor = max_j; ch[i].score = new_max; ch[i].len = ch[max_j].len + 1; ch[i].score2 = new_max;
+                ch[i].root_ptr = ch[max_j].root_ptr; ch[i].f_leaf = 1; ch[max_j].f_leaf = 0;
+            }
+            else
+            {
+                ch[i].p2anchor = -1; ch[i].score = 0; ch[i].len = 1; ch[i].score2 = 0; ch[i].root_ptr = i; ch[i].f_leaf = 1;
+            }
+        }
+        wsync(w);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// traceback (cluster_util.cpp:122-332). Chains are written back to back into out_el / out_score;
+// chain_off[c] .. chain_off[c+1] delimit chain c. Sequential. Returns the number of chains.
+// ----------------------------------------------------------------------------------------------------
+template <class E>
+LNR_HD int traceback0(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
+                      int min_len, int abort_score, int bestn, float stop_ratio)
+{   // traceBackChains0 :122
+    const int delete_score = -1000;
+    int n_chains = 0, pos = 0;
+    chain_off[0] = 0;
+    int search_times = bestn < 50 ? bestn : 50;
+    for (int it = 0; it < search_times; it++)
+    {
+        bool f_done = true;
+        int max_2nd = -1, max_score = -1, max_str = -1, max_len = 0;
+        for (int j = 0; j < n; j++)
+            if (rec[j].score > max_score)
+            {
+                max_2nd = max_score; max_str = j; max_score = rec[j].score; max_len = rec[j].len; f_done = false;
+            }
+        if (n_chains > 0)
+            if ((float)max_len > (float)(u64)(chain_off[1] - chain_off[0]) * stop_ratio) f_done = false;
+        if (f_done || max_score == 0) break;
+        if (max_len > min_len && max_score / (max_len - 1) > abort_score)
+        {
+            int cur = pos;   // tentative chain [pos, cur)
+            for (int j = max_str; j != -1; j = rec[j].p2anchor)
+            {
+                if (rec[j].score != delete_score)
+                {
+                    out_el[cur] = el[j];
+                    out_score[cur] = rec[j].score2;
+                    cur++;
+                    rec[j].score = delete_score;
+                }
+                else
+                {
+                    int infix = rec[j].score2;
+                    if (max_score - infix < max_2nd)
+                    {
+                        for (int k = max_str; k != j; k = rec[k].p2anchor) rec[k].score = rec[k].score2 - infix;
+                        cur = pos;
+                    }
+                    break;
+                }
+            }
+            if (cur != pos && n_chains < max_chains)
+            {
+                pos = cur;
+                n_chains++;
+                chain_off[n_chains] = pos;
+            }
+        }
+        if (max_str != -1) rec[max_str].score = delete_score;
+    }
+    return n_chains;
+}
+
+template <class E>
+LNR_HD int traceback1(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
+                      int min_len, int abort_score, int bestn, float stop_ratio)
+{   // traceBackChains1 :214 -- called only when there are <= 50 trees
+    int root[64], lscore[64], llen[64], lidx[64];
+    int nt = 0;
+    for (int j = 0; j < n; j++)
+        if (rec[j].f_leaf)
+        {
+            int f_new = 1;
+            for (int k = 0; k < nt; k++)
+                if (root[k] == rec[j].root_ptr)
+                {
+                    if (rec[j].score > lscore[k]) { lscore[k] = rec[j].score; llen[k] = rec[j].len; lidx[k] = j; }
+                    f_new = 0;
+                }
+            if (f_new && nt < 64) { root[nt] = rec[j].root_ptr; lscore[nt] = rec[j].score; llen[nt] = rec[j].len; lidx[nt] = j; nt++; }
+        }
+    struct Rank { int first, second; };
+    Rank ranks[64];
+    for (int i = 0; i < nt; i++) { ranks[i].first = i; ranks[i].second = lscore[i]; }
+    gnu_sort(ranks, nt, [](const Rank & a, const Rank & b) { return a.second > b.second; });
+    int n_chains = 0, pos = 0, f_stop = 0;
+    int stale = 0;   // the reference keeps appending to an uncleared `chain` once f_stop is set (dead data)
+    chain_off[0] = 0;
+    int lim = bestn < nt ? bestn : nt;
+    for (int i = 0; i < lim; i++)
+    {
+        int t = ranks[i].first;
+        int max_score = lscore[t], max_len = llen[t], max_str = lidx[t];
+        int mean = max_len > 1 ? max_score / (max_len - 1) : abort_score + 1;
+        if (max_len > min_len && mean > abort_score)
+        {
+            int cur = pos;
+            for (int j = max_str; j != -1; j = rec[j].p2anchor) { out_el[cur] = el[j]; out_score[cur] = rec[j].score2; cur++; }
+            if (cur != pos)
+            {
+                if (n_chains > 0)
+                    if ((float)(u64)(cur - pos + stale) / (float)(u64)(chain_off[1] - chain_off[0]) < stop_ratio) f_stop = 1;
+                if (!f_stop && n_chains < max_chains)
+                {
+                    pos = cur;
+                    n_chains++;
+                    chain_off[n_chains] = pos;
+                }
+                else if (f_stop) stale += cur - pos;
+            }
+        }
+    }
+    return n_chains;
+}
+
+template <class E>
+LNR_HD int traceback(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
+                     int min_len, int abort_score, int bestn, float stop_ratio)
+{   // traceBackChains :307 -- number of distinct roots = records that start a tree
+    int roots = 0;
+    for (int i = 0; i < n; i++) roots += rec[i].p2anchor == -1;
+    if (roots > 50) return traceback0(el, rec, n, out_el, out_score, chain_off, max_chains, min_len, abort_score, bestn, stop_ratio);
+    return traceback1(el, rec, n, out_el, out_score, chain_off, max_chains, min_len, abort_score, bestn, stop_ratio);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// blocks of hits / cords
+// ----------------------------------------------------------------------------------------------------
+// gather_blocks_ (pmpfinder.cpp:1484). Appends to sep[n_sep..]; when str_ends != null also records the
+// shifted start/end cords. Returns the new n_sep.
+LNR_HD int gather_blocks(u64 * cords, int n, YPair * str_ends, int & n_str_ends, Blk * sep, int n_sep, u32 str_, u32 end_,
+                         u64 L, u64 large_gap, u64 cord_size, int f_set_end)
+{
+    n_str_ends = 0;
+    if (n < 2) return n_sep;
+    u64 dmax = cord_size / 2, d;
+    u32 p_str = str_;
+    for (u32 i = str_ + 1; i < end_; i++)
+        if (is_end(cords[i - 1]) || !cords_consecutive(cords[i - 1], cords[i], large_gap))
+        {
+            if (str_ends)
+            {
+                d = umin64(L - cord_y(cords[p_str]) - 1, dmax);
+                str_ends[n_str_ends].first = shift_cord(cords[p_str], (i64)d, (i64)d);
+                d = umin64(L - cord_y(cords[i - 1]) - 1, dmax);
+                str_ends[n_str_ends].second = shift_cord(cords[i - 1], (i64)d, (i64)d);
+            }
+            n_str_ends++;
+            sep[n_sep].first = p_str; sep[n_sep].second = i; n_sep++;
+            if (f_set_end) cords[i - 1] |= kFlagEnd;
+            p_str = i;
+        }
+    if (str_ends)
+    {
+        d = umin64(L - cord_y(cords[n - 1]) - 1, dmax);
+        str_ends[n_str_ends].first = shift_cord(cords[p_str], (i64)d, (i64)d);
+        str_ends[n_str_ends].second = shift_cord(cords[n - 1], (i64)d, (i64)d);
+    }
+    n_str_ends++;
+    sep[n_sep].first = p_str; sep[n_sep].second = (u32)n; n_sep++;
+    return n_sep;
+}
+
+// preFilterChains2 (pmpfinder.cpp:2366) with getCordXY = get_cord_y. sep (nb blocks) is replaced by the
+// y-disjoint pieces (tmp: scratch of capacity cap); cuts: 2*nb u64; strs: nb u64. Returns the new count,
+// or -1 when the piece buffer would overflow.
+LNR_HD int prefilter_chains2(u64 * hits, int n_hits, Blk * sep, int nb, Blk * tmp, int cap, u64 * cuts, u64 * strs)
+{
+    const u64 mask = 1ULL << 62;
+    for (int i = 0; i < nb; i++)
+    {
+        cuts[2 * i] = sep[i].first;
+        cuts[2 * i + 1] = (u64)(sep[i].second - 1) | mask;
+        strs[i] = sep[i].first;
+    }
+    gnu_sort(cuts, 2 * nb, [hits, mask](const u64 & a, const u64 & b) { return cord_y(hits[a & ~mask]) < cord_y(hits[b & ~mask]); });
+    int nt = 0;
+    for (int i = 0; i < 2 * nb; i++)
+    {
+        u64 cuty = cord_y(hits[cuts[i] & ~mask]);
+        for (int j = 0; j < nb && strs[j] < (u64)n_hits; j++)
+        {
+            if (cuty < cord_y(hits[strs[j]])) continue;
+            for (u64 k = strs[j]; k < sep[j].second; k++)
+            {
+                u64 yk = cord_y(hits[k]);
+                u64 up;
+                if (cuts[i] & mask)
+                {
+                    if (yk == cuty) up = k + 1;
+                    else if (yk > cuty) up = k;
+                    else continue;
+                }
+                else
+                {
+                    if (yk >= cuty) up = k;
+                    else continue;
+                }
+                if (strs[j] != up)
+                {
+                    if (nt >= cap) return -1;
+                    tmp[nt].first = (u32)strs[j]; tmp[nt].second = (u32)up; nt++;
+                    strs[j] = up;
+                }
+                break;
+            }
+        }
+    }
+    for (int i = 0; i < nt; i++) sep[i] = tmp[i];
+    gnu_sort(sep, nt, [](const Blk & a, const Blk & b) { return a.second < b.second; });
+    for (int i = 0; i < nt; i++) hits[sep[i].second - 1] |= kFlagEnd;
+    return nt;
+}
+
+// getBestChains2 (cluster_util.cpp:469); mode 0 = hits blocks (getApxChainScore2), 1 = cord blocks
+// (getApxChainScore3 on `strand`)
+LNR_HD void best_chains2(const u64 * recs, const Blk * sep, const i32 * sep_score, ChainRec * ch, int nb, u64 L, int mode, int strand)
+{
+    const int depth = 20;
+    for (int i = 0; i < nb; i++)
+    {
+        int j_str = i - depth > 0 ? i - depth : 0;
+        int max_j = i, new_max = -1;
+        for (int j = j_str; j < i; j++)
+        {
+            int s = mode == 0 ? score_blocks_hits(recs[sep[j].first], recs[sep[i].second - 1])
+                              : score_blocks_cords(recs[sep[j].first], recs[sep[j].second - 1], recs[sep[i].first],
+                                                   recs[sep[i].second - 1], L, strand);
+            if (s > 0 && s + ch[j].score + sep_score[i] >= new_max)
+            {
+                max_j = j;
+                new_max = s + ch[j].score + sep_score[i];
+            }
+        }
+        if (new_max > 0)
+        {
+            ch[i].p2anchor = max_j; ch[i].score = new_max;
+            ch[i].len = (i32)(sep[i].second - sep[i].first) + ch[max_j].len;
+            ch[i].score2 = ch[i].score; ch[i].root_ptr = ch[max_j].root_ptr; ch[i].f_leaf = 1; ch[max_j].f_leaf = 0;
+        }
+        else
+        {
+            ch[i].p2anchor = -1; ch[i].score = sep_score[i]; ch[i].len = (i32)(sep[i].second - sep[i].first);
+            ch[i].score2 = ch[i].score; ch[i].root_ptr = i; ch[i].f_leaf = 1;
+        }
+    }
+}
+
+// scratch needed by chain_blocks_base for nb blocks
+struct BlockScratch
+{
+    u32 * ptr; Blk * sep_tmp; i32 * score_tmp; ChainRec * rec; Blk * out_el; i32 * out_score; int * chain_off;
+};
+template <class AllocT> LNR_PIPE_INL bool block_scratch_alloc(AllocT & ar, BlockScratch & s, int nb)
+{
+    s.ptr = arena_alloc<u32>(ar, nb);
+    s.sep_tmp = arena_alloc<Blk>(ar, nb);
+    s.score_tmp = arena_alloc<i32>(ar, nb);
+    s.rec = arena_alloc<ChainRec>(ar, nb);
+    s.out_el = arena_alloc<Blk>(ar, nb);
+    s.out_score = arena_alloc<i32>(ar, nb);
+    s.chain_off = arena_alloc<int>(ar, 8);
+    return !ar.failed;
+}
+
+// chainBlocksBase (cluster_util.cpp:533). Returns the number of chains (<= 3, bestn), elements in s.out_el.
+LNR_HD int chain_blocks_base(const u64 * recs, const Blk * sep, const i32 * sep_score, int nb, BlockScratch & s, u64 L,
+                             int mode, int strand, int f_sort)
+{
+    if (nb < 2) return 0;
+    for (int i = 0; i < nb; i++) s.ptr[i] = (u32)i;
+    if (f_sort)
+        gnu_sort(s.ptr, nb, [recs, sep](const u32 & a, const u32 & b) { return cord_x40(recs[sep[a].first]) > cord_x40(recs[sep[b].first]); });
+    for (int i = 0; i < nb; i++) { s.sep_tmp[i] = sep[s.ptr[i]]; s.score_tmp[i] = sep_score[s.ptr[i]]; }
+    best_chains2(recs, s.sep_tmp, s.score_tmp, s.rec, nb, L, mode, strand);
+    return traceback<Blk>(s.sep_tmp, s.rec, nb, s.out_el, s.out_score, s.chain_off, 6, 1, 0, 3, 0.7f);
+}
+
+// _filterBlocksHits (cluster_util.cpp:633): major chain + up to 4 optional chains > 0.8 * len.
+// Writes the new hit list (without header) into out; returns its length.
+LNR_HD int filter_blocks_hits(const Blk * el, const int * chain_off, int n_chains, const u64 * hits, u64 * out)
+{
+    int no = 0;
+    u64 len_cur = 0;
+    for (int i = chain_off[0]; i < chain_off[1]; i++)
+    {
+        for (u32 j = el[i].first; j < el[i].second; j++) out[no++] = hits[j] & ~kFlagEnd;
+        len_cur += el[i].second - el[i].first;
+    }
+    out[no - 1] |= kFlagEnd;
+    float major_bound = (float)(0.8 * (double)len_cur);
+    u32 major_limit = 5, major_n = 1;
+    for (int c = 1; c < n_chains; c++)
+    {
+        len_cur = 0;
+        for (int i = chain_off[c]; i < chain_off[c + 1]; i++) len_cur += el[i].second - el[i].first;
+        // (the reference's third branch needs len_cur == 0, impossible for non-empty blocks)
+        if (major_n < major_limit && (float)len_cur > major_bound)
+        {
+            ++major_n;
+            for (int i = chain_off[c]; i < chain_off[c + 1]; i++)
+                for (u32 k = el[i].first; k < el[i].second; k++) out[no++] = hits[k] & ~kFlagEnd;
+            out[no - 1] |= kFlagEnd;
+        }
+        out[no - 1] |= kFlagEnd;
+    }
+    return no;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// window extension (pmpfinder.cpp:883-1176)
+// ----------------------------------------------------------------------------------------------------
+LNR_HD u64 previous_window(const PipeIn & in, u64 cord, PipeCounters & cnt)   // previousWindow :883
+{
+    u64 id = cord_id(cord), strand = cord_strand(cord), x_suf = cord_x(cord) >> 4, y_suf = cord_y(cord) >> 4;
+    if (y_suf < (u64)kMed || x_suf < (u64)kSup) return 0;
+    u64 y = y_suf - kMed, x_min = 0;
+    u32 mn = ~0u;
+    for (u64 x = x_suf - kSup; x < x_suf - kInf; x++)
+    {
+        u32 t = wdist(in, (u32)strand, (u32)id, y, x, cnt);
+        if (t < mn) { mn = t; x_min = x; }
+    }
+    if (mn > (u32)kWinThr) return 0;
+    if (x_suf - x_min > (u64)kMed)
+        return (((id << 30) + ((x_suf - kMed) << 4)) << 20) + ((x_suf - x_min - kMed + y) << 4) + (strand << 61);
+    return (((id << 30) + (x_min << 4)) << 20) + (y << 4) + (strand << 61);
+}
+LNR_HD u64 next_window(const PipeIn & in, u64 cord, PipeCounters & cnt)   // nextWindow :1079
+{
+    u64 id = cord_id(cord), strand = cord_strand(cord), x_pre = cord_x(cord) >> 4, y_pre = cord_y(cord) >> 4;
+    if (y_pre + 2 * kSup > (u64)in.nf1 || x_pre + 2 * kSup > (u64)in.nf2[id]) return 0;
+    u64 y = y_pre + kMed, x_min = 0;
+    u32 mn = ~0u;
+    for (u64 x = x_pre + kInf; x < x_pre + kSup; x++)
+    {
+        u32 t = wdist(in, (u32)strand, (u32)id, y, x, cnt);
+        if (t < mn) { mn = t; x_min = x; }
+    }
+    if (mn > (u32)kWinThr) return 0;
+    if (x_min - x_pre > (u64)kMed)
+        return (((id << 30) + ((x_pre + kMed) << 4)) << 20) + ((x_pre + kMed - x_min + y) << 4) + (strand << 61);
+    return (((id << 30) + (x_min << 4)) << 20) + (y << 4) + (strand << 61);
+}
+// extendWindow :1152; returns false when the cord buffer is full
+LNR_HD bool extend_window(const PipeIn & in, u64 * cords, int & n, int cap, u64 ystr, u64 yend, PipeCounters & cnt)
+{
+    int p_str = n - 1;
+    u64 nc;
+    while ((nc = previous_window(in, cords[n - 1], cnt)) && cord_y(nc) >= ystr)
+    {
+        if (n >= cap) return false;
+        cords[n++] = nc;
+    }
+    int p_end = n;
+    for (int k = p_str; k < (p_str + p_end) / 2; k++)
+    {
+        u64 t = cords[k]; cords[k] = cords[n - k + p_str - 1]; cords[n - k + p_str - 1] = t;
+    }
+    while ((nc = next_window(in, cords[n - 1], cnt)) && cord_y(nc) + kWin < yend)
+    {
+        if (n >= cap) return false;
+        cords[n++] = nc;
+    }
+    return true;
+}
+
+// path_dst_2 (pmpfinder.cpp:1309), iterators restated as indices (hitBegin = 1). Returns false on overflow.
+LNR_HD bool path_dst_2(const PipeIn & in, const u64 * H, int nh, u64 * cords, int & nc, int cap, u64 read_str, u64 read_end,
+                       PipeCounters & cnt)
+{
+    const u64 L = in.L, cs = kWin;
+    int hb = 1, he = nh;
+    if (hb + 1 >= he) return true;
+    if (nc == 0) { if (cap < 1) return false; cords[nc++] = kFlagEnd; }   // initCords
+    u64 ready_str, ready_end, cordy_str = 0, cordy_end = 0;
+    bool f_sp_l = false, f_sp_r = false, f_block_end = false, f_append = false;
+    int nx = hb + 1, first = hb;
+    for (int it = hb; it < he; it = nx++)
+    {
+        ready_str = cord_strand(H[it]) ? L - read_end : read_str;
+        ready_end = cord_strand(H[it]) ? L - read_str + 1 : read_end;
+        bool it_first = is_end(H[it - 1]);
+        i64 da_l = it_first ? 0 : iabs64((i64)(cord_x(H[it]) - cord_x(H[it - 1]) - cord_y(H[it]) + cord_y(H[it - 1])));
+        f_sp_l = (da_l > 80) || cord_strand(H[it] ^ H[it - 1]);
+        while (1)
+        {
+            if (nx >= he || is_end(H[nx - 1])) { f_block_end = true; first = nx; break; }
+            i64 da_r = iabs64((i64)(cord_x(H[nx]) - cord_x(H[nx - 1]) - cord_y(H[nx]) + cord_y(H[nx - 1])));
+            f_sp_r = (da_r > 80) || cord_strand(H[nx] ^ H[nx - 1]);
+            if ((cord_y(H[it]) + cs < cord_y(H[nx]) && cord_x(H[it]) + cs < cord_x(H[nx])) || f_sp_r) break;
+            nx++;
+        }
+        if (!f_sp_r && !f_block_end)
+        {
+            // sic: the whole hit value, not its y, when f_sp_l (pmpfinder.cpp:1360)
+            cordy_str = f_sp_l ? H[it] : (it_first ? ready_str : cord_y(cords[nc - 1]));
+            cordy_end = cord_y(H[nx]);
+            if (nc >= cap) return false;
+            cords[nc++] = H[it] & ~kFlagEnd;
+            f_append = true;
+        }
+        else
+        {
+            if (!f_sp_l && cord_y(H[nx - 1]) >= cs && cord_x(H[nx - 1]) >= cs)
+            {
+                u64 ncord = shift_cord(H[nx - 1], -(i64)cs, -(i64)cs);
+                cordy_str = it_first ? read_str : cord_y(ncord);
+                cordy_end = cord_y(H[nx - 1]);
+                if (nc >= cap) return false;
+                cords[nc++] = ncord & ~kFlagEnd;
+                f_append = true;
+            }
+            else f_append = false;
+        }
+        if (is_end(H[it]) || f_block_end) { f_block_end = true; cordy_end = ready_end; }
+        if (f_append)
+            if (!extend_window(in, cords, nc, cap, cordy_str, cordy_end, cnt)) return false;
+        if (f_block_end) cords[nc - 1] |= kFlagEnd;
+        nx = f_block_end ? first : nx;
+        f_sp_l = f_sp_r = f_block_end = f_append = false;
+    }
+    return true;
+}
+
+// clean_blocks_ (pmpfinder.cpp:1537); returns the new length
+LNR_HD int clean_blocks(u64 * cords, int n, u64 drop_len, i64 map_err)
+{
+    if (n == 0) return 0;
+    u64 ptr = 1, len = 0;
+    for (int i = 1; i < n; i++)
+    {
+        len++;
+        if (!is_end(cords[i - 1]))
+        {
+            i64 dx = (i64)(cord_x(cords[i]) - cord_x(cords[ptr - 1]));
+            i64 dy = (i64)(cord_y(cords[i]) - cord_y(cords[ptr - 1]));
+            if (dx < 0 || dy < 0)
+            {
+                if (iabs64(dx) < map_err && iabs64(dy) < map_err) { --len; --ptr; }
+                else cords[ptr] = cords[i];
+            }
+            else cords[ptr] = cords[i];
+        }
+        else cords[ptr] = cords[i];
+        if (is_end(cords[i]))
+        {
+            ptr = len < drop_len ? ptr - len : ptr;
+            len = 0;
+            cords[ptr] |= kFlagEnd;
+        }
+        ptr++;
+    }
+    return (int)ptr;
+}
+
+LNR_HD void forward_y(YPair se, u64 L, u64 & a, u64 & b)   // getUPForwardy cords.cpp:469
+{
+    if (cord_strand(se.first)) { a = L - cord_y(se.second) - 1; b = L - cord_y(se.first) - 1; }
+    else { a = cord_y(se.first); b = cord_y(se.second); }
+}
+LNR_HD int push_gap(YPair * gaps, int & ng, int cap, u64 a, u64 b, u64 L)
+{
+    if (ng >= cap) return 0;
+    gaps[ng].first = a; gaps[ng].second = b;
+    u64 ga, gb;
+    forward_y(gaps[ng], L, ga, gb);
+    ng++;
+    return (int)(gb - ga);
+}
+// gather_gaps_y_ (pmpfinder.cpp:1592). Returns the summed gap length; gaps appended to gaps[0..ng)
+LNR_HD int gather_gaps_y(YPair * str_ends, int ns, YPair * gaps, int & ng, int cap, u64 L, u64 gap_size)
+{
+    u64 cord_frt = 0, cord_end = L - 1;
+    int sum = 0;
+    ng = 0;
+    if (ns == 0) return push_gap(gaps, ng, cap, cord_frt, cord_end, L);
+    gnu_sort(str_ends, ns, [L](const YPair & i, const YPair & j) {
+        u64 y1 = cord_strand(i.first) ? L - cord_y(i.second) - 1 : cord_y(i.first);
+        u64 y2 = cord_strand(j.first) ? L - cord_y(j.second) - 1 : cord_y(j.first);
+        return y1 < y2;
+    });
+    u64 f_cover = 0, cordy1 = 0, cordy2 = 0, y1a, y1b, y2a, y2b;
+    forward_y(str_ends[0], L, y1a, y1b);
+    y2a = y1a; y2b = y1b;
+    if (y1a > gap_size)
+    {
+        cordy2 = cord_y(y1a);
+        sum += push_gap(gaps, ng, cap, cord_frt, cordy2, L);
+    }
+    for (int i = 1; i < ns; i++)
+    {
+        if (!f_cover) { forward_y(str_ends[i - 1], L, y1a, y1b); cordy1 = cord_y(y1b); }
+        forward_y(str_ends[i], L, y2a, y2b);
+        cordy2 = cord_y(y2a);
+        if (y1b > y2b) f_cover = 1;
+        else
+        {
+            if (y2a > y1b && y2a - y1b > gap_size) sum += push_gap(gaps, ng, cap, cordy1, cordy2, L);
+            f_cover = 0;
+        }
+    }
+    u64 max_y_end = f_cover ? y1b : y2b;
+    if (L - max_y_end > gap_size) sum += push_gap(gaps, ng, cap, max_y_end, cord_end, L);
+    return sum;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// cord-block chaining (cluster_util.cpp:936-1103)
+// ----------------------------------------------------------------------------------------------------
+LNR_HD void revert_chain_block_strand(Blk * el, int * chain_off, int n_chains, const u64 * cords, int strand)
+{   // revertChainBlockStrand :1023 (the reference appends a (0,0) terminator; restated with an index bound)
+    u64 f_strand = strand ? 1 : 0;
+    for (int c = 0; c < n_chains; c++)
+    {
+        Blk * ch = el + chain_off[c];
+        int len = chain_off[c + 1] - chain_off[c];
+        u64 pre = 0, cur = 0;
+        int swap_str = 0;
+        for (int j = 0; j <= len; j++)
+        {
+            if (j == len || cord_strand(cords[ch[j].first]) == f_strand) cur = 0;
+            else cur = 1;
+            if (cur && !pre) swap_str = j;
+            if (!cur && pre)
+                for (int k = swap_str; k < (swap_str + j) / 2; k++)
+                {
+                    Blk t = ch[k]; ch[k] = ch[swap_str + j - 1 - k]; ch[swap_str + j - 1 - k] = t;
+                }
+            pre = cur;
+        }
+    }
+}
+// _filterBlocksCords :865 (f_header = 1, <= major_limit chains). Returns the new length written to out.
+LNR_HD int filter_blocks_cords(const Blk * el, const int * chain_off, int n_chains, const u64 * cords, u64 * out, u32 major_limit)
+{
+    int no = 0;
+    out[no++] = cords[0];
+    u64 len_cur = 0;
+    for (int i = chain_off[0]; i < chain_off[1]; i++)
+    {
+        for (u32 j = el[i].first; j < el[i].second; j++) out[no++] = cords[j] & ~kFlagEnd;
+        len_cur += el[i].second - el[i].first;
+    }
+    out[no - 1] |= kFlagEnd;
+    float major_bound = (float)(0.8 * (double)len_cur);
+    u32 major_n = 1;
+    for (int c = 1; c < n_chains && major_n < major_limit; c++)
+    {
+        len_cur = 0;
+        for (int i = chain_off[c]; i < chain_off[c + 1]; i++) len_cur += el[i].second - el[i].first;
+        if ((float)len_cur > major_bound)
+        {
+            ++major_n;
+            for (int i = chain_off[c]; i < chain_off[c + 1]; i++)
+                for (u32 k = el[i].first; k < el[i].second; k++) out[no++] = cords[k] & ~kFlagEnd;
+            out[no - 1] |= kFlagEnd;
+        }
+    }
+    return no;
+}
+
+LNR_HD u64 block_key_y(const u64 * cords, Blk a, u64 L, int strand)
+{
+    bool flip = strand ? !cord_strand(cords[a.first]) : (cord_strand(cords[a.first]) != 0);
+    return flip ? L - 1 - cord_y(cords[a.second - 1]) : cord_y(cords[a.first]);
+}
+// chainBlocksSingleStrand :936
+LNR_HD int chain_blocks_single_strand(const u64 * cords, Blk * sep, int nb, BlockScratch & s, i32 * sep_score, int strand, u64 L,
+                                      u32 init_score)
+{
+    gnu_sort(sep, nb, [cords, L, strand](const Blk & a, const Blk & b) { return block_key_y(cords, a, L, strand) > block_key_y(cords, b, L, strand); });
+    for (int i = 0; i < nb; i++) sep_score[i] = (i32)((sep[i].second - sep[i].first) * init_score);
+    return chain_blocks_base(cords, sep, sep_score, nb, s, L, 1, strand, 0);
+}
+LNR_HD int best_strand_of(const Blk * e1, const int * o1, int n1, const Blk * e2, const int * o2, int n2)
+{   // getChainBlocksBestStrand :979
+    int l1 = 0, l2 = 0;
+    int m = n1 < n2 ? n1 : n2;
+    for (int i = 0; i < m; i++)
+    {
+        for (int j = o1[i]; j < o1[i + 1]; j++) l1 += (int)(e1[j].second - e1[j].first);
+        for (int j = o2[i]; j < o2[i + 1]; j++) l2 += (int)(e2[j].second - e2[j].first);
+        if (l1 < l2) return 1;
+        else if (l1 > l2) return 0;
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Phase 1: one apxMap_ call after seeding (pmpfinder.cpp:2632): filter -> chain -> hits -> blocks ->
+// window extension. A[0..n): raw anchors with A[0] the sentinel slot; B: second buffer of n entries.
+// Appends to cords. dbg_hits (optional): hits after getAnchorHitsChains.
+// Return: 0 ok, 1 scratch/cord capacity exhausted.
+// ----------------------------------------------------------------------------------------------------
+LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, const PipeIn & in, u64 * A, u64 * B, int n,
+                       u64 read_str, u64 read_end, int score_type, u64 * cords, int & n_cords, int cords_cap,
+                       u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt)
+{
+    arena_reset(ar);
+    if (dbg_nhits && w.lane == 0) *dbg_nhits = 1;
+    if (dbg_hits && w.lane == 0 && dbg_hits_cap > 0) dbg_hits[0] = kFlagEnd;
+    if (w.lane == 0) A[0] = 0;               // Anchors::init(1) base.cpp:272
+    wsync(w);
+    // ---- filterAnchors (:2159): binningFilter + filterAnchors1
+    int m;
+    u64 * S = binning_filter(w, bins, A, B, n, m);
+    if (m <= 1) return 0;                    // no chains, hits stay empty (path_dst :1457)
+    u64 * O = (S == A) ? B : A;              // the other buffer
+    if (w.lane == 0) S[0] = 0;               // filterAnchorsList :2030 overwrites whatever is first
+    wsync(w);
+    u64 * C = arena_alloc<u64>(ar, (u64)m);
+    Blk * ranges = arena_alloc<Blk>(ar, (u64)m / 2 + 2);
+    if (ar.failed) return 1;
+    u64 * sorted = radix_sort(w, hist256, S, O, C, m, 62, KeyAsc());
+    int nr = 0;
+    if (w.lane == 0) nr = filter_anchor_runs(sorted, m, ranges);
+    nr = wbcast(w, nr, 0);
+    wsync(w);
+    // compact the accepted runs (anchors[0] is dropped, filterAnchors1 :2073)
+    u64 * F = (sorted == O) ? C : O;         // a buffer that is neither `sorted` nor S
+    if (F == S) F = (sorted == C) ? O : C;
+    int n2 = 0;
+    for (int r = 0; r < nr; r++)
+    {
+        int b = (int)ranges[r].first, e = (int)ranges[r].second;
+        for (int j = b + w.lane; j < e; j += w.nl) F[n2 + (j - b)] = sorted[j];
+        n2 += e - b;
+    }
+    wsync(w);
+    // ---- chainAnchorsHits (:2448): sort by AnchorX descending with std::sort's tie order
+    u64 * hits = arena_alloc<u64>(ar, (u64)n2 + 2);
+    u64 * hits2 = arena_alloc<u64>(ar, (u64)n2 + 2);
+    i32 * hits_score = arena_alloc<i32>(ar, (u64)n2 + 2);
+    int * chain_off = arena_alloc<int>(ar, 64);
+    if (ar.failed) return 1;
+    int n_hits = 1;
+    if (w.lane == 0) { hits[0] = kFlagEnd; hits_score[0] = 0; }
+    if (n2 >= 2)
+    {
+        // free buffers: the two of {A,B,C} that are not F
+        u64 * T0 = (F == A) ? B : A;
+        u64 * T1 = (F == C) ? B : C;
+        if (T1 == T0) T1 = C;
+        u64 * X = radix_sort(w, hist256, F, T0, T1, n2, 30, KeyXDesc());
+        int tie = 0;
+        for (int i = 1 + w.lane; i < n2; i += w.nl) tie |= anchor_x(X[i]) == anchor_x(X[i - 1]);
+        tie = wballot(w, tie != 0) != 0;
+        if (tie)
+        {
+            // comparator ties: only libstdc++'s own permutation is right
+            if (w.lane == 0) gnu_sort(F, n2, [](const u64 & a, const u64 & b) { return anchor_x(a) > anchor_x(b); });
+            wsync(w);
+            X = F;
+        }
+        ChainRec * rec = arena_alloc<ChainRec>(ar, (u64)n2);
+        u64 * ch_el = arena_alloc<u64>(ar, (u64)n2);
+        if (ar.failed) return 1;
+        best_chains(w, X, rec, n2, score_type);
+        if (w.lane == 0)
+        {
+            int nch = traceback<u64>(X, rec, n2, ch_el, hits_score + 1, chain_off, 60, 1, 45, 50, in.stop_ratio);
+            for (int c = 0; c < nch; c++)
+            {
+                for (int j = chain_off[c]; j < chain_off[c + 1]; j++) hits[1 + j] = hit2cord_dstr(ch_el[j]);
+                hits[chain_off[c + 1]] |= kFlagEnd;
+            }
+            n_hits = 1 + chain_off[nch];
+        }
+    }
+    else if (w.lane == 0 && n2 == 1)
+    {
+        // a single anchor: sorted trivially, chainAnchorsBase returns without chains (cluster_util.cpp:450)
+    }
+    n_hits = wbcast(w, n_hits, 0);
+    wsync(w);
+    // ---- blocks of hits: gather_blocks_ (:1484) -> preFilterChains2 (:2366) -> chainBlocksHits
+    Blk * sep = arena_alloc<Blk>(ar, (u64)n_hits + 1);
+    Blk * sep_tmp = arena_alloc<Blk>(ar, (u64)n_hits + 1);
+    u64 * cuts = arena_alloc<u64>(ar, 2 * (u64)n_hits + 2);
+    u64 * strs = arena_alloc<u64>(ar, (u64)n_hits + 1);
+    i32 * sep_score = arena_alloc<i32>(ar, (u64)n_hits + 1);
+    BlockScratch bs;
+    block_scratch_alloc(ar, bs, n_hits + 1);
+    u8 * keep = arena_alloc<u8>(ar, (u64)n_hits + 1);
+    if (ar.failed) return 1;
+    u64 * H = hits;
+    int err = 0;
+    if (w.lane == 0)
+    {
+        int dummy = 0;
+        int nb = gather_blocks(hits, n_hits, (YPair *)0, dummy, sep, 0, 1, (u32)n_hits, in.L, 600, 0, 0);
+        nb = prefilter_chains2(hits, n_hits, sep, nb, sep_tmp, n_hits + 1, cuts, strs);
+        if (nb < 0) err = 1;
+        else
+        {
+            for (int i = 0; i < nb; i++) sep_score[i] = hits_score[sep[i].first] - hits_score[sep[i].second - 1];
+            int nch = chain_blocks_base(hits, sep, sep_score, nb, bs, in.L, 0, 0, 1);
+            if (nch > 0) { n_hits = filter_blocks_hits(bs.out_el, bs.chain_off, nch, hits, hits2); H = hits2; }
+        }
+        if (dbg_hits && !err)
+        {
+            u32 k = (u32)n_hits < dbg_hits_cap ? (u32)n_hits : dbg_hits_cap;
+            for (u32 i = 0; i < k; i++) dbg_hits[i] = H[i];
+            *dbg_nhits = (u32)n_hits;
+        }
+    }
+    err = wbcast(w, err, 0);
+    if (err) return 1;
+    n_hits = wbcast(w, n_hits, 0);
+    H = (u64 *)wbcast64(w, (u64)H, 0);
+    wsync(w);
+    if (n_hits < 2) return 0;                // path_dst :1457
+    // ---- _filterHits (:1417): drop hits whose own window distance >= reject (50)
+    for (int it = 1 + w.lane; it < n_hits; it += w.nl)
+    {
+        u64 h = H[it];
+        u32 strand = (u32)cord_strand(h), id = (u32)cord_id(h);
+        u64 x1 = cord_y(h) >> 4, x2 = cord_x(h) >> 4;
+        u32 dist = (x1 + 4 < in.nf1 && x2 + 4 < in.nf2[id]) ? window_dist48(in.f1[strand] + x1, in.f2[id] + x2) : 1000u;   // _windowDist :676
+        keep[it] = dist < (u32)kWinReject;
+    }
+    wsync(w);
+    int ok = 1;
+    if (w.lane == 0)
+    {
+        cnt.hits += (u64)(n_hits - 1);
+        int mv = 0;
+        for (int it = 1; it < n_hits; it++)
+        {
+            u64 h = H[it];
+            if (keep[it]) H[it - mv] = h;
+            else mv++;
+            if (is_end(h)) H[it - mv] |= kFlagEnd;
+        }
+        n_hits -= mv;
+        ok = path_dst_2(in, H, n_hits, cords, n_cords, cords_cap, read_str, read_end, cnt) ? 1 : 0;
+    }
+    ok = wbcast(w, ok, 0);
+    n_cords = wbcast(w, n_cords, 0);
+    wsync(w);
+    return ok ? 0 : 1;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Phase 2 (lane 0): clean_blocks_, gather_blocks_, gather_gaps_y_ and the re-map decision
+// (pmpfinder.cpp:2744-2749). gaps: forward-strand [y1, y2) intervals to re-map. Returns 1 if re-map is
+// needed, 0 if not, -1 on capacity failure.
+// ----------------------------------------------------------------------------------------------------
+LNR_HD int phase_mid(u64 L, u64 * cords, int & n_cords, YPair * str_ends, Blk * sep, int & n_sep, YPair * gaps, int & n_gaps, int gaps_cap)
+{
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    n_cords = clean_blocks(cords, n_cords, (u64)drop_len, 50);
+    int ns = 0;
+    n_sep = gather_blocks(cords, n_cords, str_ends, ns, sep, 0, 1, (u32)n_cords, L, 1000, kWin, 1);
+    if (n_cords < 2) ns = 0;
+    int gap_sum = gather_gaps_y(str_ends, ns, gaps, n_gaps, gaps_cap, L, 1000);
+    if (n_gaps >= gaps_cap) return -1;
+    for (int i = 0; i < n_gaps; i++)   // getUPForwardy of every gap (:2753)
+    {
+        u64 a, b;
+        forward_y(gaps[i], L, a, b);
+        gaps[i].first = a; gaps[i].second = b;
+    }
+    return ((float)gap_sum / (float)L >= 0.7f) ? 1 : 0;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Phase 3 (lane 0): chainApxCordsBlocks -> chainBlocksCords (:1747, cluster_util.cpp:1068), clean_blocks_,
+// final flags (:2788-2801). sep/n_sep: blocks from the last gather_blocks_. tmp: cord scratch of cords_cap.
+// ----------------------------------------------------------------------------------------------------
+LNR_HD int phase_finish(u64 L, u64 * cords, int & n_cords, Blk * sep, int n_sep, Blk * sep2, i32 * score1, i32 * score2,
+                        BlockScratch & s1, BlockScratch & s2, u64 * tmp)
+{
+    for (int i = 0; i < n_sep; i++) sep2[i] = sep[i];
+    int n1 = chain_blocks_single_strand(cords, sep, n_sep, s1, score1, 0, L, 16);
+    int n2 = chain_blocks_single_strand(cords, sep2, n_sep, s2, score2, 1, L, 16);
+    int best = best_strand_of(s1.out_el, s1.chain_off, n1, s2.out_el, s2.chain_off, n2);
+    BlockScratch & sb = best == 0 ? s1 : s2;
+    int nb = best == 0 ? n1 : n2;
+    if (nb > 0)
+    {
+        revert_chain_block_strand(sb.out_el, sb.chain_off, nb, cords, best);
+        int no = filter_blocks_cords(sb.out_el, sb.chain_off, nb, cords, tmp, 2);
+        for (int i = 0; i < no; i++) cords[i] = tmp[i];
+        n_cords = no;
+    }
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    n_cords = clean_blocks(cords, n_cords, (u64)drop_len, 50);
+    int seg = 0;
+    for (int i = 0; i < n_cords; i++)
+    {
+        u64 c = cords[i];
+        if (seg) c |= kFlagRecd; else c &= ~kFlagRecd;
+        c |= kFlagMain;
+        if (is_end(c)) seg = 1 - seg;
+        cords[i] = c;
+    }
+    return 0;
+}
+
+}  // namespace lnr

@@ -167,3 +167,24 @@ class RefImpl(_Checker):
             raise FileNotFoundError(REF_SO + " missing: run `make -C oracle ref` where /root/reference exists")
         with _quiet_stderr():
             super().__init__(REF_SO, contigs, **kw)
+
+
+EMU_SO = os.path.join(ROOT, "tests", "host_emu", "libemu.so")
+
+
+def build_emu() -> str:
+    src = os.path.join(ROOT, "tests", "host_emu", "emu.cpp")
+    hdrs = [os.path.join(ROOT, "linear_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "linear_b200", "csrc"))
+            if f.endswith(".h")]
+    newest = max(os.path.getmtime(p) for p in [src] + hdrs)
+    if not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", src, "-o", EMU_SO])
+    return EMU_SO
+
+
+class HostEmu(_Checker):
+    """Product headers (linear_b200/csrc/lnr_*.h) compiled for the host with a single-lane warp."""
+    prefix = "emu_"
+
+    def __init__(self, contigs, **kw):
+        super().__init__(build_emu(), contigs, **kw)
