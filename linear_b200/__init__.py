@@ -1,0 +1,8 @@
+"""linear_b200 -- B200-native approximate-map path of `linear filter` (xp3i4/linear) behind a C ABI.
+
+Only what the hot path needs lives here: csrc/ (sm_100a kernels + the C ABI of include/lnr_b200.h),
+api.py (ctypes mirror of the reference's operator interface for the path) and datagen.py (synthetic inputs).
+"""
+from . import datagen  # noqa: F401
+from .api import (Context, Features, Genome, Index, LnrError, apx_map_batch, cords_end, create_features,  # noqa: F401
+                  create_index, load_library, read_features)

@@ -1,0 +1,288 @@
+"""Host-side Python binding of the C ABI in include/lnr_b200.h (ctypes; used by tests/ and bench.py).
+
+The names follow the reference interface each call replaces:
+  Genome            <- Mapper::loadGenomes / StringSet<String<Dna5>>                    (mapper.cpp:389)
+  create_features   <- createFeatures(genomes, f2, feature_type, threads)               (pmpfinder.cpp:775)
+  create_index      <- createIndexDynamic(genomes, index, 0, n, threads, false)         (index_util.cpp:2478)
+  apx_map_batch     <- per read: _compltRvseStr + 2x createFeatures + apxMap            (mapper.cpp:438-447)
+
+There is no CPU fallback: if the CUDA library is missing or no device is present every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblnr_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+
+LNR_OK, LNR_E_CUDA, LNR_E_ARG, LNR_E_CAPACITY, LNR_E_UNSUPPORTED, LNR_E_LIMIT = 0, -1, -2, -3, -4, -5
+
+EXPORTS = [
+    "lnr_ctx_create", "lnr_ctx_destroy", "lnr_last_error", "lnr_ctx_set_profiling", "lnr_ctx_kernel_times",
+    "lnr_ctx_reset_kernel_times", "lnr_genome_upload", "lnr_genome_from_device", "lnr_genome_destroy",
+    "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
+    "lnr_index_build", "lnr_index_export_dindex", "lnr_index_destroy", "lnr_apxmap_batch",
+    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_read_features",
+]
+
+
+class LnrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lnr_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("preset", C.c_int), ("feature_type", C.c_int), ("reserved", C.c_int * 6)]
+
+
+class DebugOut(C.Structure):
+    _fields_ = [("raw_anchors", u64p), ("raw_anchors_cap", C.c_uint64), ("raw_anchors_off", u64p),
+                ("hits", u64p), ("hits_cap", C.c_uint64), ("hits_off", u64p),
+                ("cords1", u64p), ("cords1_cap", C.c_uint64), ("cords1_off", u64p)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load liblnr_b200.so (built in-tree by __graft_entry__.build()). Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.lnr_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.lnr_ctx_destroy.argtypes = [vp]
+    lib.lnr_ctx_destroy.restype = None
+    lib.lnr_last_error.argtypes = [vp]
+    lib.lnr_last_error.restype = C.c_char_p
+    lib.lnr_ctx_set_profiling.argtypes = [vp, C.c_int]
+    lib.lnr_ctx_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), u64p]
+    lib.lnr_ctx_reset_kernel_times.argtypes = [vp]
+    lib.lnr_genome_upload.argtypes = [vp, C.c_uint32, C.POINTER(u8p), u64p, C.POINTER(vp)]
+    lib.lnr_genome_from_device.argtypes = [vp, C.c_uint32, vp, u64p, C.POINTER(vp)]
+    lib.lnr_genome_destroy.argtypes = [vp]
+    lib.lnr_genome_destroy.restype = None
+    lib.lnr_features_build.argtypes = [vp, vp, C.c_int, C.c_uint, C.POINTER(vp)]
+    lib.lnr_features_count.argtypes = [vp, C.c_uint32, u64p]
+    lib.lnr_features_download.argtypes = [vp, C.c_uint32, vp, C.c_uint64, u64p]
+    lib.lnr_features_destroy.argtypes = [vp]
+    lib.lnr_features_destroy.restype = None
+    lib.lnr_index_build.argtypes = [vp, vp, C.c_int, C.c_uint, C.POINTER(vp)]
+    lib.lnr_index_export_dindex.argtypes = [vp, i32p, u64p, C.c_uint64, u64p]
+    lib.lnr_index_destroy.argtypes = [vp]
+    lib.lnr_index_destroy.restype = None
+    lib.lnr_apxmap_batch.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, u64p, C.c_uint64,
+                                     C.POINTER(DebugOut)]
+    lib.lnr_apxmap_batch_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, vp, C.c_uint64, u64p]
+    lib.lnr_last_batch_counters.argtypes = [vp, u64p]
+    lib.lnr_read_features.argtypes = [vp, u8p, C.c_uint64, C.c_int, vp, vp, C.c_uint64, u64p]
+    _lib = lib
+    return lib
+
+
+COUNTER_NAMES = ("S_seeds", "H_records_scanned", "A_raw_anchors", "Hits", "W_windows", "C_cords", "bases", "remap_tasks")
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.lnr_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise LnrError(rc, "lnr_ctx_create failed (no CUDA device?)")
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise LnrError(rc, (self.lib.lnr_last_error(self.h) or b"").decode())
+
+    def set_profiling(self, on: bool):
+        self.check(self.lib.lnr_ctx_set_profiling(self.h, int(on)))
+
+    def reset_kernel_times(self):
+        self.check(self.lib.lnr_ctx_reset_kernel_times(self.h))
+
+    def kernel_times(self):
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = (C.c_uint64 * cap)()
+        k = self.lib.lnr_ctx_kernel_times(self.h, cap, names, ms, n)
+        return {names[i].decode(): (float(ms[i]), int(n[i])) for i in range(min(k, cap))}
+
+    def counters(self):
+        c = (C.c_uint64 * 8)()
+        self.check(self.lib.lnr_last_batch_counters(self.h, c))
+        return dict(zip(COUNTER_NAMES, [int(v) for v in c]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lnr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Genome:
+    """Device-resident genome (StringSet<String<Dna5>> of the reference)."""
+
+    def __init__(self, ctx: Context, contigs: Optional[Sequence[np.ndarray]] = None, device_ptr: int = 0,
+                 lens: Optional[Sequence[int]] = None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if contigs is not None:
+            self._keep = [np.ascontiguousarray(c, dtype=np.uint8) for c in contigs]
+            n = len(self._keep)
+            ptrs = (u8p * n)(*[c.ctypes.data_as(u8p) for c in self._keep])
+            ln = np.array([len(c) for c in self._keep], dtype=np.uint64)
+            ctx.check(ctx.lib.lnr_genome_upload(ctx.h, n, ptrs, ln.ctypes.data_as(u64p), C.byref(h)))
+            self.lens = [int(v) for v in ln]
+        else:
+            ln = np.array(list(lens), dtype=np.uint64)
+            ctx.check(ctx.lib.lnr_genome_from_device(ctx.h, len(ln), C.c_void_p(device_ptr), ln.ctypes.data_as(u64p), C.byref(h)))
+            self.lens = [int(v) for v in ln]
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lnr_genome_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Features:
+    def __init__(self, ctx: Context, genome: Genome, feature_type: int = 2, threads: int = 4):
+        self.ctx, self.genome, self.feature_type = ctx, genome, feature_type
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lnr_features_build(ctx.h, genome.h, feature_type, threads, C.byref(h)))
+        self.h = h
+
+    def download(self, contig: int) -> np.ndarray:
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.lnr_features_count(self.h, contig, C.byref(n)))
+        out = np.zeros((n.value, 3), dtype=np.int32)
+        self.ctx.check(self.ctx.lib.lnr_features_download(self.h, contig, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lnr_features_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Index:
+    def __init__(self, ctx: Context, genome: Genome, index_type: int = 1, threads: int = 4):
+        self.ctx, self.genome, self.index_type = ctx, genome, index_type
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lnr_index_build(ctx.h, genome.h, index_type, threads, C.byref(h)))
+        self.h = h
+
+    @property
+    def n_hs(self) -> int:
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.lnr_index_export_dindex(self.h, None, None, 0, C.byref(n)))
+        return int(n.value)
+
+    def export_dindex(self) -> Tuple[np.ndarray, np.ndarray]:
+        n = self.n_hs
+        dir_ = np.zeros((1 << 26) + 1, dtype=np.int32)
+        hs = np.zeros(n, dtype=np.uint64)
+        nn = C.c_uint64()
+        self.ctx.check(self.ctx.lib.lnr_index_export_dindex(self.h, dir_.ctypes.data_as(i32p), hs.ctypes.data_as(u64p), n, C.byref(nn)))
+        return dir_, hs
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lnr_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def create_features(ctx, genome, feature_type=2, threads=4) -> Features:
+    return Features(ctx, genome, feature_type, threads)
+
+
+def create_index(ctx, genome, index_type=1, threads=4) -> Index:
+    return Index(ctx, genome, index_type, threads)
+
+
+def read_features(ctx: Context, read: np.ndarray, feature_type: int = 2):
+    read = np.ascontiguousarray(read, dtype=np.uint8)
+    n = C.c_uint64()
+    ctx.check(ctx.lib.lnr_read_features(ctx.h, read.ctypes.data_as(u8p), len(read), feature_type, None, None, 0, C.byref(n)))
+    f = np.zeros((n.value, 3), np.int32)
+    r = np.zeros((n.value, 3), np.int32)
+    if n.value:
+        ctx.check(ctx.lib.lnr_read_features(ctx.h, read.ctypes.data_as(u8p), len(read), feature_type,
+                                            f.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+    return f, r
+
+
+def apx_map_batch(ctx: Context, index: Index, feats: Features, bases, offsets, preset: int = 1, debug: bool = False,
+                  cords_out: Optional[np.ndarray] = None, cords_off_out: Optional[np.ndarray] = None):
+    """bases: uint8 host buffer (numpy array; pass the numpy view of a pinned torch tensor for full PCIe speed),
+    offsets: uint64[n+1]. Returns (cords uint64[], cords_off uint64[n+1][, debug dict])."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    cap = int(len(bases) // 16 + 64 * n + 1024) if cords_out is None else len(cords_out)
+    cords = np.empty(cap, dtype=np.uint64) if cords_out is None else cords_out
+    coff = np.zeros(n + 1, dtype=np.uint64) if cords_off_out is None else cords_off_out
+    prm = Params(preset=preset, feature_type=feats.feature_type)
+    dbg = None
+    keep = {}
+    if debug:
+        dbg = DebugOut()
+        ra_cap = int(len(bases) * 4 + 1024)
+        keep["ra"] = np.zeros(ra_cap, np.uint64); keep["ra_off"] = np.zeros(n + 1, np.uint64)
+        keep["h"] = np.zeros(int(len(bases) // 8 + 64 * n), np.uint64); keep["h_off"] = np.zeros(n + 1, np.uint64)
+        keep["c1"] = np.zeros(int(len(bases) // 4 + 16 * n + 8), np.uint64); keep["c1_off"] = np.zeros(n + 1, np.uint64)
+        dbg.raw_anchors = keep["ra"].ctypes.data_as(u64p); dbg.raw_anchors_cap = ra_cap; dbg.raw_anchors_off = keep["ra_off"].ctypes.data_as(u64p)
+        dbg.hits = keep["h"].ctypes.data_as(u64p); dbg.hits_cap = len(keep["h"]); dbg.hits_off = keep["h_off"].ctypes.data_as(u64p)
+        dbg.cords1 = keep["c1"].ctypes.data_as(u64p); dbg.cords1_cap = len(keep["c1"]); dbg.cords1_off = keep["c1_off"].ctypes.data_as(u64p)
+    rc = ctx.lib.lnr_apxmap_batch(ctx.h, index.h, feats.h, C.byref(prm), n, bases.ctypes.data_as(C.c_void_p),
+                                  offsets.ctypes.data_as(u64p), cords.ctypes.data_as(C.c_void_p), coff.ctypes.data_as(u64p), cap,
+                                  C.byref(dbg) if dbg is not None else None)
+    ctx.check(rc)
+    res = cords[: int(coff[-1])]
+    if debug:
+        return res, coff, keep
+    return res, coff
+
+
+def cords_end(cords_str: np.ndarray, window: int = 96) -> np.ndarray:
+    """cords_end[i] = cords_str[i] + ((W << 20) | W) (pmpfinder.cpp:2790-2801)."""
+    return cords_str + np.uint64((window << 20) | window)

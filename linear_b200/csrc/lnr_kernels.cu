@@ -1,0 +1,1515 @@
+// sm_100a kernels + C ABI (include/lnr_b200.h) of the approximate-map path of `linear filter`.
+//
+// Data layout in HBM
+//   genome    1 byte/base as delivered (Dna5 ordinals), contigs back to back at 256-byte aligned offsets with
+//             >= 256 zero bytes after each contig
+//   DIndex    dir: int32[2^26+1] bucket offsets; hs: uint64[n_hs] records, ascending inside a bucket
+//   features  F96 (3 x int32) per 16 bases; per contig for the genome, per (read, strand) for a batch
+//   batch     read bases back to back, anchors / scratch per read, cords per read at host-computed offsets
+//
+// Kernels (all HBM / latency bound integer work, no tensor-core shaped math on this path)
+//   k_feat_genome / k_feat_reads      2-mer/48 features: one thread per 16-base cell, 3-cell sums through smem
+//   k_idx_prep, k_idx_pass<FILL>      DIndex samples: genome tile staged in smem, one thread per 4 samples,
+//                                     emit rule by block max-scan, histogram / scatter with global atomics
+//   k_scan_*                          device-wide exclusive scan (reduce / spine / apply), fused bucket omission
+//   k_idx_sort_buckets                ascending order inside each bucket
+//   k_seed_prep / k_seed_count / k_seed_fill   per-read seeding, one thread per sample, exact-size output
+//   k_map_primary / k_map_remap       warp-per-read pipeline (lnr_pipeline.h), persistent warps + atomic queue
+//   k_gather_cords                    per-read cords -> caller's concatenated layout
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lnr_b200.h"
+#include "lnr_core.h"
+#include "lnr_pipeline.h"
+
+using namespace lnr;
+
+// =====================================================================================================
+// host-side context
+// =====================================================================================================
+struct KernelStat { double ms; uint64_t launches; };
+
+struct DevBuf
+{
+    void * p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T * as() const { return (T *)p; }
+};
+
+struct lnr_ctx
+{
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool profiling = false;
+    uint64_t launches_total = 0;
+    std::map<std::string, KernelStat> stats;
+    std::vector<std::string> stat_order;
+    struct Pending { std::string name; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;
+    // batch workspace
+    DevBuf bases, read_off, tasks, sample_info, sample_cnt, scan_tmp, anchorsA, anchorsB, feats, foff, ftile,
+        cords, cords_base, ncords, slots, bins, arena, tasks2, misc, out_cords, out_off, dbg_hits, dbg_hoff, dbg_nhits,
+        dbg_c1, dbg_nc1, read_meta;
+    uint64_t counters[8] = {0};
+    const void * bins_zeroed = nullptr;
+    size_t bins_zeroed_cap = 0;
+    DevBuf remap_list;
+    int map_warps_per_cta = 4;
+    int map_ctas_per_sm = 4;
+    size_t arena_bytes_per_warp = 2u << 20;
+};
+
+struct lnr_genome
+{
+    lnr_ctx * ctx;
+    uint32_t n_contigs;
+    std::vector<uint64_t> len, off;
+    uint64_t total_padded;
+    u8 * d_bases;   // owned
+};
+struct lnr_feats
+{
+    lnr_ctx * ctx;
+    int feature_type;
+    uint32_t n_contigs;
+    std::vector<uint32_t> n;        // entries per contig
+    std::vector<uint64_t> off;      // entry offset per contig
+    F96 * d_f;                      // owned, all contigs back to back
+    const F96 ** d_ptrs;            // device table of per-contig pointers
+    u32 * d_n;                      // device table of counts
+};
+struct lnr_index
+{
+    lnr_ctx * ctx;
+    int index_type;
+    i32 * d_dir;
+    u64 * d_hs;
+    uint64_t n_hs;
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            char b_[512];                                                                               \
+            snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            ctx->err = b_;                                                                              \
+            return LNR_E_CUDA;                                                                          \
+        }                                                                                               \
+    } while (0)
+
+static int fail(lnr_ctx * ctx, int code, const char * msg) { if (ctx) ctx->err = msg; return code; }
+
+// kernel launch with optional event bracketing (bench: per-kernel device time on the launching stream)
+struct LaunchScope
+{
+    lnr_ctx * ctx; bool on; lnr_ctx::Pending p;
+    LaunchScope(lnr_ctx * c, const char * name, int n_launches = 1) : ctx(c), on(c->profiling)
+    {
+        c->launches_total += (uint64_t)n_launches;
+        if (!on) return;
+        p.name = name;
+        for (cudaEvent_t * e : {&p.a, &p.b})
+        {
+            if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(p.a, ctx->stream);
+    }
+    ~LaunchScope()
+    {
+        if (!on) return;
+        cudaEventRecord(p.b, ctx->stream);
+        ctx->pending.push_back(p);
+    }
+};
+static void harvest_stats(lnr_ctx * ctx)
+{
+    for (auto & p : ctx->pending)
+    {
+        cudaEventSynchronize(p.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        auto it = ctx->stats.find(p.name);
+        if (it == ctx->stats.end()) { ctx->stats[p.name] = KernelStat{0, 0}; ctx->stat_order.push_back(p.name); it = ctx->stats.find(p.name); }
+        it->second.ms += ms;
+        it->second.launches += 1;
+        ctx->event_pool.push_back(p.a);
+        ctx->event_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+// =====================================================================================================
+// device helpers
+// =====================================================================================================
+struct GAcc   // bounds-checked byte view of one sequence in global memory; out of range reads as 0
+{
+    const u8 * s; i64 len;
+    __device__ __forceinline__ int operator()(i64 p) const { return (p >= 0 && p < len) ? (int)__ldg(s + p) : 0; }
+};
+struct GRcAcc   // reverse-complement view (_compltRvseStr base.cpp:335)
+{
+    const u8 * s; i64 len;
+    __device__ __forceinline__ int operator()(i64 p) const
+    {
+        if (p < 0 || p >= len) return 0;
+        int c = (int)__ldg(s + (len - 1 - p));
+        return c < 4 ? 3 - c : 4;
+    }
+};
+
+// =====================================================================================================
+// features
+// =====================================================================================================
+static const int FT = 256;           // threads per CTA = cells per CTA
+static const int FE = FT - 2;        // entries per CTA
+
+template <class Acc>
+__device__ __forceinline__ void feat_tile(Acc acc, u32 e0, u32 n_entries, F96 * out, u64 * s_lo, u32 * s_hi)
+{
+    u32 c = e0 + threadIdx.x;        // cell index
+    u64 lo = 0; u32 hi = 0;
+    if (c < n_entries + 2) feat_cell(acc, 16 * (i64)c, lo, hi);
+    s_lo[threadIdx.x] = lo;
+    s_hi[threadIdx.x] = hi;
+    __syncthreads();
+    if (threadIdx.x < FE && c < n_entries)
+    {
+        F96 f = feat_entry(lo + s_lo[threadIdx.x + 1] + s_lo[threadIdx.x + 2], hi + s_hi[threadIdx.x + 1] + s_hi[threadIdx.x + 2]);
+        i32 * o = (i32 *)(out + c);
+        o[0] = f.v[0]; o[1] = f.v[1]; o[2] = f.v[2];
+    }
+}
+
+// genome: aligned 16-byte loads for interior cells
+struct GAcc16
+{
+    const u8 * s; i64 len;
+    __device__ __forceinline__ int operator()(i64 p) const { return (p >= 0 && p < len) ? (int)__ldg(s + p) : 0; }
+};
+
+__global__ void __launch_bounds__(FT) k_feat_genome(const u8 * __restrict__ g, i64 len, u32 n_entries, F96 * __restrict__ out)
+{
+    __shared__ u64 s_lo[FT];
+    __shared__ u32 s_hi[FT];
+    u32 e0 = blockIdx.x * FE;
+    u32 c = e0 + threadIdx.x;
+    u64 lo = 0; u32 hi = 0;
+    i64 p0 = 16 * (i64)c;
+    if (c < n_entries + 2)
+    {
+        if (p0 + 17 <= len)
+        {
+            // one aligned 16-byte load + the first byte of the next cell
+            uint4 v = __ldg((const uint4 *)(g + p0));
+            u32 wds[4] = {v.x, v.y, v.z, v.w};
+            int a = (int)(wds[0] & 0xff);
+#pragma unroll
+            for (int i = 1; i <= 16; i++)
+            {
+                int b = i < 16 ? (int)((wds[i >> 2] >> (8 * (i & 3))) & 0xff) : (int)__ldg(g + p0 + 16);
+                if (a < 4 && b < 4)
+                {
+                    int id = 4 * a + b;
+                    if (id < 10) lo += 1ULL << (6 * id);
+                    else if (id < 15) hi += 1u << (6 * (id - 10));
+                }
+                a = b;
+            }
+        }
+        else
+        {
+            GAcc acc = {g, len};
+            feat_cell(acc, p0, lo, hi);
+        }
+    }
+    s_lo[threadIdx.x] = lo;
+    s_hi[threadIdx.x] = hi;
+    __syncthreads();
+    if (threadIdx.x < FE && c < n_entries)
+    {
+        F96 f = feat_entry(lo + s_lo[threadIdx.x + 1] + s_lo[threadIdx.x + 2], hi + s_hi[threadIdx.x + 1] + s_hi[threadIdx.x + 2]);
+        i32 * o = (i32 *)(out + c);
+        o[0] = f.v[0]; o[1] = f.v[1]; o[2] = f.v[2];
+    }
+}
+
+// reads: tile table gives (read, strand, first entry); ftile[i] = first tile of read i (2 strands per read)
+__global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
+                                                   const u64 * __restrict__ foff, const u32 * __restrict__ ftile, u32 n_reads,
+                                                   F96 * __restrict__ out)
+{
+    __shared__ u64 s_lo[FT];
+    __shared__ u32 s_hi[FT];
+    u32 tile = blockIdx.x;
+    u32 lo_i = 0, hi_i = n_reads;   // largest r with ftile[r] <= tile
+    while (hi_i - lo_i > 1) { u32 mid = (lo_i + hi_i) >> 1; if (ftile[mid] <= tile) lo_i = mid; else hi_i = mid; }
+    u32 r = lo_i;
+    u64 L = read_off[r + 1] - read_off[r];
+    u32 nf = feat_count_read(L);
+    u32 tps = (nf + FE - 1) / FE;               // tiles per strand
+    u32 t = tile - ftile[r];
+    u32 strand = t >= tps ? 1u : 0u;
+    u32 e0 = (t - strand * tps) * FE;
+    F96 * o = out + foff[r] + (u64)strand * nf;
+    const u8 * s = bases + read_off[r];
+    if (!strand) { GAcc acc = {s, (i64)L}; feat_tile(acc, e0, nf, o, s_lo, s_hi); }
+    else { GRcAcc acc = {s, (i64)L}; feat_tile(acc, e0, nf, o, s_lo, s_hi); }
+}
+
+// =====================================================================================================
+// DIndex build
+// =====================================================================================================
+static const int IT = 256;           // threads per CTA
+static const int IS = 4;             // samples per thread
+static const int ITILE = IT * IS;    // samples per CTA
+static const int ISM = ITILE * 9 + 64 + 32;
+
+__global__ void k_idx_prep(const u8 * __restrict__ g, IdxChunk * chunks, u32 n_chunks)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunks) return;
+    IdxChunk ch = chunks[i];
+    GAcc acc = {g + ch.base_off, ch.len};
+    ch.kskip = hash_init_skip<kSpanD>(acc, ch.t_str, ch.len);
+    ch.bias = ch.kskip ? selector_bias<kSpanD>(acc, ch.t_str + ch.kskip, ch.t_str) : 0;
+    chunks[i] = ch;
+}
+
+struct TileAcc   // smem-staged tile with global fallback
+{
+    const u8 * sm; i64 p0, p1; const u8 * g; i64 len;
+    __device__ __forceinline__ int operator()(i64 p) const
+    {
+        if (p >= p0 && p < p1) return (int)sm[p - p0];
+        return (p >= 0 && p < len) ? (int)__ldg(g + p) : 0;
+    }
+};
+
+// FILL = false: histogram of emitted samples (createDIndex pass 1, index_util.cpp:1661-1699)
+// FILL = true : scatter records of non-omitted buckets (pass 2, :1737-1781)
+template <bool FILL>
+__global__ void __launch_bounds__(IT) k_idx_pass(const u8 * __restrict__ g, const IdxChunk * __restrict__ chunks,
+                                                 const u32 * __restrict__ tile0, u32 n_chunks, u32 * __restrict__ cnt,
+                                                 const i32 * __restrict__ dir, u32 * __restrict__ fillc, u64 * __restrict__ hs)
+{
+    __shared__ __align__(16) u8 s_b[ISM];
+    __shared__ i32 s_warp[IT / 32];
+    __shared__ i32 s_back;
+    // chunk of this tile
+    u32 tile = blockIdx.x;
+    u32 lo = 0, hi = n_chunks;
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tile0[mid] <= tile) lo = mid; else hi = mid; }
+    const IdxChunk ch = chunks[lo];
+    const u8 * gs = g + ch.base_off;
+    i64 m0 = (i64)(tile - tile0[lo]) * ITILE;
+    i64 nm = ch.n_samples - m0 < ITILE ? ch.n_samples - m0 : ITILE;
+    // stage bases [j0 - 8, j0 + 9*nm + 32) ; j0 = first sample position of the tile
+    i64 j0 = ch.t_str + kIdxMinStep + 9 * m0;
+    i64 p0 = (j0 - 8) & ~15LL;
+    if (p0 < 0) p0 = 0;
+    i64 p1 = j0 + 9 * nm + 32;
+    if (p1 > ch.len) p1 = ch.len;
+    {
+        i64 nb = p1 - p0;
+        i64 nv = nb >> 4;
+        const uint4 * src = (const uint4 *)(gs + p0);
+        uint4 * dst = (uint4 *)s_b;
+        for (i64 i = threadIdx.x; i < nv; i += IT) dst[i] = __ldg(src + i);
+        for (i64 i = (nv << 4) + threadIdx.x; i < nb; i += IT) s_b[i] = __ldg(gs + p0 + i);
+    }
+    __syncthreads();
+    TileAcc acc = {s_b, p0, p1, gs, ch.len};
+    // each thread: IS consecutive samples
+    u32 X[IS]; u64 rec[IS];
+    i64 mt = m0 + (i64)threadIdx.x * IS;
+#pragma unroll
+    for (int q = 0; q < IS; q++)
+    {
+        X[q] = 0xffffffffu; rec[q] = 0;
+        if (mt + q < ch.n_samples && (i64)threadIdx.x * IS + q < nm) idx_sample(acc, ch, mt + q, X[q], rec[q]);
+    }
+    // X of the sample just before this thread's first one
+    u32 xprev = __shfl_up_sync(0xffffffffu, X[IS - 1], 1);
+    __shared__ u32 s_last[IT / 32];
+    if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = X[IS - 1];
+    // look-back of the tile's first sample: number of consecutive earlier samples with the same X
+    if (threadIdx.x < 32)
+    {
+        i32 back = 0;
+        if (m0 > 0)
+        {
+            u32 X0 = __shfl_sync(0xffffffffu, X[0], 0);
+            GAcc ga = {gs, ch.len};
+            i64 m = m0 - 1;
+            while (true)
+            {
+                i64 mm = m - threadIdx.x;
+                bool same = false;
+                if (mm >= 0) { u32 Xm; u64 r; idx_sample(ga, ch, mm, Xm, r); same = Xm == X0; }
+                u32 neq = __ballot_sync(0xffffffffu, !same);
+                if (neq) { back += __ffs((int)neq) - 1; break; }
+                back += 32; m -= 32;
+            }
+        }
+        if (threadIdx.x == 0) s_back = back;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) xprev = threadIdx.x == 0 ? 0xfffffffeu : s_last[(threadIdx.x >> 5) - 1];
+    // run start (tile-relative sample index; negative = before the tile) by max-scan
+    i32 local_i = (i32)threadIdx.x * IS;
+    i32 rs[IS];
+    i32 run = -0x40000000;   // "unknown, inherited"
+    {
+        u32 xp = xprev;
+#pragma unroll
+        for (int q = 0; q < IS; q++)
+        {
+            bool brk = X[q] != xp;
+            if (threadIdx.x == 0 && q == 0) brk = false;   // resolved through s_back
+            if (brk) run = local_i + q;
+            rs[q] = run;
+            xp = X[q];
+        }
+    }
+    // inclusive max-scan of `run` across threads
+    i32 v = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { i32 t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v = max(v, t); }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    i32 carry = -0x40000000;
+    for (int wq = 0; wq < (int)(threadIdx.x >> 5); wq++) carry = max(carry, s_warp[wq]);
+    i32 excl = __shfl_up_sync(0xffffffffu, v, 1);
+    if ((threadIdx.x & 31) == 0) excl = -0x40000000;
+    excl = max(excl, carry);
+    i32 tile_start_run = -s_back;   // run start of sample 0 (<= 0)
+#pragma unroll
+    for (int q = 0; q < IS; q++)
+    {
+        i32 r = rs[q] > -0x40000000 ? rs[q] : (excl > -0x40000000 ? excl : tile_start_run);
+        i32 idx = local_i + q;
+        bool valid = idx < nm;
+        bool emit = valid && (((idx - r) & 1) == 0);
+        if (emit)
+        {
+            if (!FILL) atomicAdd(&cnt[X[q]], 1u);
+            else
+            {
+                i32 b = dir[X[q]], e = dir[X[q] + 1];
+                if (e - b > 0)
+                {
+                    u32 slot = atomicAdd(&fillc[X[q]], 1u);
+                    hs[(u64)b + slot] = rec[q];
+                }
+            }
+        }
+    }
+}
+
+// ---- device-wide exclusive scan of u32 (reduce / spine / apply), 4096 items per CTA --------------------
+static const int ST = 256, SI = 16, STILE = ST * SI;
+// transform applied to the input: cap > 0 -> values > cap become 0 and are written back (bucket omission)
+__global__ void __launch_bounds__(ST) k_scan_reduce(u32 * __restrict__ in, u64 n, u32 cap, u64 * __restrict__ partial)
+{
+    __shared__ u64 s[ST / 32];
+    u64 base = (u64)blockIdx.x * STILE;
+    u64 sum = 0;
+    for (int i = 0; i < SI; i++)
+    {
+        u64 idx = base + (u64)i * ST + threadIdx.x;
+        if (idx < n)
+        {
+            u32 v = in[idx];
+            if (cap && v > cap) { v = 0; in[idx] = 0; }
+            sum += v;
+        }
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { u64 t = 0; for (int i = 0; i < ST / 32; i++) t += s[i]; partial[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_scan_spine(u64 * __restrict__ partial, u32 n_blocks, u64 * __restrict__ total)
+{
+    __shared__ u64 s[32];
+    __shared__ u64 s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < n_blocks; base += 1024)
+    {
+        u32 i = base + threadIdx.x;
+        u64 v = i < n_blocks ? partial[i] : 0;
+        u64 x = v;
+        for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += t; }
+        if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            u64 y = s[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, y, o); if (threadIdx.x >= o) y += t; }
+            s[threadIdx.x] = y;
+        }
+        __syncthreads();
+        u64 wbase = (threadIdx.x >> 5) ? s[(threadIdx.x >> 5) - 1] : 0;
+        u64 incl = x + wbase + s_carry;
+        if (i < n_blocks) partial[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+// OutT = i32 (dir) or u32 / u64 offsets
+template <class OutT>
+__global__ void __launch_bounds__(ST) k_scan_apply(const u32 * __restrict__ in, u64 n, const u64 * __restrict__ partial, OutT * __restrict__ out)
+{
+    __shared__ u64 s[ST / 32];
+    u64 base = (u64)blockIdx.x * STILE + (u64)threadIdx.x * SI;
+    u32 v[SI];
+    u64 sum = 0;
+#pragma unroll
+    for (int i = 0; i < SI; i++) { u64 idx = base + i; v[i] = idx < n ? in[idx] : 0; sum += v[i]; }
+    u64 x = sum;
+    for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += t; }
+    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+    __syncthreads();
+    u64 wbase = 0;
+    for (int i = 0; i < (int)(threadIdx.x >> 5); i++) wbase += s[i];
+    u64 run = partial[blockIdx.x] + wbase + x - sum;
+#pragma unroll
+    for (int i = 0; i < SI; i++) { u64 idx = base + i; if (idx < n) out[idx] = (OutT)run; run += v[i]; }
+}
+
+// ascending order inside each bucket (index_util.cpp:1788-1796); one thread per bucket, buckets <= 400
+__global__ void k_idx_sort_buckets(const i32 * __restrict__ dir, u64 * __restrict__ hs, u32 n_buckets)
+{
+    u32 X = blockIdx.x * blockDim.x + threadIdx.x;
+    if (X >= n_buckets) return;
+    i32 b = dir[X], e = dir[X + 1];
+    int n = e - b;
+    if (n < 2) return;
+    u64 * a = hs + b;
+    for (int i = 1; i < n; i++)
+    {
+        u64 v = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+        a[j + 1] = v;
+    }
+}
+
+// =====================================================================================================
+// seeding (getDIndexMatchAll, pmpfinder.cpp:1856)
+// =====================================================================================================
+__global__ void k_seed_prep(const u8 * __restrict__ bases, const u64 * __restrict__ read_off, SeedTask * tasks, u32 n_tasks)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tasks) return;
+    SeedTask t = tasks[i];
+    u64 L = read_off[t.read + 1] - read_off[t.read];
+    GAcc acc = {bases + read_off[t.read], (i64)L};
+    t.kskip = (u32)hash_init_skip<kSpanD>(acc, 0, (i64)L);
+    t.bias = selector_bias<kSpanD>(acc, (i64)t.kskip, (i64)t.str + kSpanD);
+    tasks[i] = t;
+}
+
+// per sample: packed info = bucket start (32) | bucket size (16) | Y (8) | strand (1) | k (is recomputed) ;
+// count = records passing the Y-key rule. A sample whose X equals the previous sample's X is skipped
+// (xpre rule, :1882; xpre starts at 0).
+__device__ __forceinline__ u32 find_task(const SeedTask * tasks, u32 n_tasks, u64 s)
+{
+    u32 lo = 0, hi = n_tasks;
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tasks[mid].sample0 <= s) lo = mid; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
+                                                    const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
+                                                    const i32 * __restrict__ dir, const u64 * __restrict__ hs,
+                                                    u64 * __restrict__ info, u32 * __restrict__ count, unsigned long long * counters)
+{
+    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 c = 0, scanned = 0;
+    if (s < n_samples)
+    {
+        u32 ti = find_task(tasks, n_tasks, s);
+        SeedTask t = tasks[ti];
+        u32 m = (u32)(s - t.sample0) + 1;
+        u64 L = read_off[t.read + 1] - read_off[t.read];
+        GAcc acc = {bases + read_off[t.read], (i64)L};
+        SeedVal sv; u32 k;
+        seed_sample(acc, t, m, sv, k);
+        u32 xprev = 0;
+        if (m > 1) { SeedVal pv; u32 kp; seed_sample(acc, t, m - 1, pv, kp); xprev = pv.X; }
+        u64 inf = 0;
+        if (sv.X != xprev)
+        {
+            i32 b = __ldg(dir + sv.X), e = __ldg(dir + sv.X + 1);
+            for (i32 i = b; i < e; i++) c += ykey_match((u32)(__ldg(hs + i) & kMaskY), sv.Y) ? 1u : 0u;
+            scanned = (u32)(e - b);
+            inf = (u64)(u32)b | ((u64)(u32)(e - b) << 32) | ((u64)sv.Y << 48) | ((u64)sv.strand << 56);
+        }
+        info[s] = inf;
+        count[s] = c;
+    }
+    // counters: H (records scanned), A (anchors)
+    u32 tot_c = c, tot_s = scanned;
+    for (int o = 16; o; o >>= 1) { tot_c += __shfl_xor_sync(0xffffffffu, tot_c, o); tot_s += __shfl_xor_sync(0xffffffffu, tot_s, o); }
+    if ((threadIdx.x & 31) == 0 && (tot_c | tot_s)) { atomicAdd(&counters[1], (unsigned long long)tot_s); atomicAdd(&counters[2], (unsigned long long)tot_c); }
+}
+// anchors of task ti start at aoff[sample0] + ti (slot 0 of the region is the sentinel)
+__global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read_off, const SeedTask * __restrict__ tasks, u32 n_tasks,
+                                                   u64 n_samples, const u64 * __restrict__ hs, const u64 * __restrict__ info,
+                                                   const u64 * __restrict__ aoff, u64 * __restrict__ anchors)
+{
+    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_samples) return;
+    u64 inf = info[s];
+    u32 nrec = (u32)(inf >> 32) & 0xffff;
+    if (!nrec) return;
+    u32 ti = find_task(tasks, n_tasks, s);
+    SeedTask t = tasks[ti];
+    u32 m = (u32)(s - t.sample0) + 1;
+    u64 k = (u64)t.str + kSpanD + (u64)t.alpha * m - 1;
+    u64 L = read_off[t.read + 1] - read_off[t.read];
+    u32 b = (u32)inf, Y = (u32)(inf >> 48) & 0xff, strand = (u32)(inf >> 56) & 1;
+    u64 * out = anchors + aoff[s] + ti + 1;
+    for (u32 i = 0; i < nrec; i++)
+    {
+        u64 h = __ldg(hs + b + i);
+        if (ykey_match((u32)(h & kMaskY), Y)) *out++ = val2anchor(h, k, L, strand);
+    }
+}
+
+// =====================================================================================================
+// warp-per-read pipeline kernels
+// =====================================================================================================
+struct ReadSlot
+{
+    u32 n_cords;     // cords so far / final
+    u32 status;      // 0 done, 1 waiting for re-map, 2 capacity failure
+    u32 task0, n_tasks;   // re-map tasks
+};
+struct MapArgs
+{
+    const u64 * read_off; const u8 * bases; u32 n_reads;
+    const F96 * feats; const u64 * foff;               // read features
+    const F96 * const * f2; const u32 * nf2;           // genome features
+    const SeedTask * tasks; u32 n_tasks;               // seeding tasks of this pass
+    const u64 * aoff;                                  // anchor offsets per sample (+ n_samples sentinel entry)
+    u64 * A; u64 * B;
+    u64 * cords; const u64 * cords_base;               // per-read cord regions
+    ReadSlot * slots;
+    SeedTask * tasks2; u32 tasks2_cap; u32 * n_tasks2; // re-map tasks produced by the primary pass
+    u32 * bins; u8 * arena; u64 arena_per_warp;
+    u32 * queue;                                       // atomic work counter
+    float stop_ratio;
+    unsigned long long * counters;
+    // optional debug
+    u64 * dbg_hits; const u64 * dbg_hoff; u32 * dbg_nhits; u64 * dbg_c1; u32 * dbg_nc1;
+};
+
+__device__ __forceinline__ void fill_pipe_in(const MapArgs & a, u32 r, PipeIn & in)
+{
+    u64 L = a.read_off[r + 1] - a.read_off[r];
+    in.read = a.bases + a.read_off[r];
+    in.L = (u32)L;
+    in.nf1 = feat_count_read(L);
+    in.f1[0] = a.feats + a.foff[r];
+    in.f1[1] = in.f1[0] + in.nf1;
+    in.f2 = a.f2; in.nf2 = a.nf2;
+    in.stop_ratio = a.stop_ratio;
+}
+
+// finish a read (lane 0 inside, all lanes call): gather (if re-mapped) + phase_finish
+__device__ __noinline__ int finish_read(const Warp & w, Arena & ar, u64 L, u64 * cords, int & nc, int cap, Blk * sep_in, int n_sep_in, bool regather)
+{
+    if (regather) arena_reset(ar);   // otherwise sep_in lives in the arena and must stay valid
+    int n_sep_cap = nc + 2;
+    Blk * sp1 = arena_alloc<Blk>(ar, n_sep_cap);
+    Blk * sp2 = arena_alloc<Blk>(ar, n_sep_cap);
+    i32 * sc1 = arena_alloc<i32>(ar, n_sep_cap);
+    i32 * sc2 = arena_alloc<i32>(ar, n_sep_cap);
+    BlockScratch s1, s2;
+    block_scratch_alloc(ar, s1, n_sep_cap);
+    block_scratch_alloc(ar, s2, n_sep_cap);
+    u64 * tmp = arena_alloc<u64>(ar, (u64)cap);
+    if (ar.failed) return 1;
+    if (w.lane == 0)
+    {
+        int n_sep;
+        if (regather)
+        {
+            int dummy = 0;
+            n_sep = gather_blocks(cords, nc, (YPair *)0, dummy, sp1, 0, 1, (u32)nc, L, 1000, kWin, 1);
+        }
+        else
+        {
+            n_sep = n_sep_in;
+            for (int i = 0; i < n_sep; i++) sp1[i] = sep_in[i];
+        }
+        phase_finish(L, cords, nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp);
+    }
+    nc = __shfl_sync(0xffffffffu, nc, 0);
+    __syncwarp();
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
+{
+    __shared__ u32 s_hist[4][256];
+    Warp w = {(int)(threadIdx.x & 31), 32};
+    u32 wid = threadIdx.x >> 5;
+    u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
+    Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
+    u32 * bins = a.bins + (u64)gw * kNumBins;
+    PipeCounters cnt = {0, 0};
+    u64 c_cords = 0;
+    while (true)
+    {
+        u32 r = 0;
+        if (w.lane == 0) r = atomicAdd(a.queue, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n_reads) break;
+        u64 L = a.read_off[r + 1] - a.read_off[r];
+        ReadSlot slot = {0, 0, 0, 0};
+        if (L > (u64)kMinReadLen)                        // mapper.cpp:440
+        {
+            PipeIn in;
+            fill_pipe_in(a, r, in);
+            // primary task of read r is task r
+            const SeedTask t = a.tasks[r];
+            u64 s0 = t.sample0, s1 = s0 + t.n_samples;
+            u64 base = a.aoff[s0] + r;
+            int n = (int)(a.aoff[s1] - a.aoff[s0]) + 1;
+            u64 * cords = a.cords + a.cords_base[r];
+            int cap = (int)(a.cords_base[r + 1] - a.cords_base[r]);
+            int nc = 0;
+            u64 * dh = a.dbg_hits ? a.dbg_hits + a.dbg_hoff[r] : (u64 *)0;
+            u32 dcap = a.dbg_hits ? (u32)(a.dbg_hoff[r + 1] - a.dbg_hoff[r]) : 0;
+            int rc = phase_map(w, ar, s_hist[wid], bins, in, a.A + base, a.B + base, n, 0, L & kMaskY, 0, cords, nc, cap,
+                               dh, a.dbg_nhits ? a.dbg_nhits + r : (u32 *)0, dcap, cnt);
+            if (a.dbg_c1 && !rc)
+            {
+                for (int i = w.lane; i < nc; i += 32) a.dbg_c1[a.cords_base[r] + i] = cords[i];
+                if (w.lane == 0) a.dbg_nc1[r] = (u32)nc;
+            }
+            int remap = 0, n_sep = 0, n_gaps = 0;
+            Blk * sep = 0;
+            u32 task0 = 0;
+            if (!rc)
+            {
+                arena_reset(ar);
+                YPair * str_ends = arena_alloc<YPair>(ar, (u64)nc + 2);
+                sep = arena_alloc<Blk>(ar, (u64)nc + 2);
+                int gcap = (int)(L / 1000 + 4);
+                YPair * gaps = arena_alloc<YPair>(ar, (u64)gcap);
+                if (ar.failed) rc = 1;
+                else
+                {
+                    if (w.lane == 0)
+                    {
+                        remap = phase_mid(L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
+                        if (remap == 1)
+                        {
+                            task0 = atomicAdd(a.n_tasks2, (u32)n_gaps);
+                            if (task0 + (u32)n_gaps > a.tasks2_cap) remap = -1;
+                            else
+                                for (int i = 0; i < n_gaps; i++)
+                                {
+                                    SeedTask t2;
+                                    t2.read = r; t2.str = (u32)(gaps[i].first & kMaskY); t2.end = (u32)gaps[i].second; t2.alpha = 7;
+                                    t2.n_samples = seed_task_samples(t2.str, t2.end, 7);
+                                    t2.bias = 0; t2.kskip = 0; t2.pad = 0; t2.sample0 = 0;
+                                    a.tasks2[task0 + i] = t2;
+                                }
+                        }
+                    }
+                    remap = __shfl_sync(0xffffffffu, remap, 0);
+                    nc = __shfl_sync(0xffffffffu, nc, 0);
+                    n_sep = __shfl_sync(0xffffffffu, n_sep, 0);
+                    n_gaps = __shfl_sync(0xffffffffu, n_gaps, 0);
+                    task0 = __shfl_sync(0xffffffffu, task0, 0);
+                    __syncwarp();
+                    if (remap < 0) rc = 1;
+                }
+            }
+            if (!rc && remap == 0) rc = finish_read(w, ar, L, cords, nc, cap, sep, n_sep, false);
+            slot.n_cords = rc ? 0 : (u32)nc;
+            slot.status = rc ? 2u : (remap == 1 ? 1u : 0u);
+            slot.task0 = task0; slot.n_tasks = remap == 1 ? (u32)n_gaps : 0;
+            if (!rc && remap == 0) c_cords += (u64)nc;
+        }
+        if (w.lane == 0) a.slots[r] = slot;
+    }
+    if (w.lane == 0)
+    {
+        if (cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)cnt.hits);
+        if (cnt.windows) atomicAdd(&a.counters[4], (unsigned long long)cnt.windows);
+        if (c_cords) atomicAdd(&a.counters[5], (unsigned long long)c_cords);
+    }
+}
+
+// re-map pass (pmpfinder.cpp:2749-2767): reads with status 1; `remap_reads` lists them
+__global__ void __launch_bounds__(128) k_map_remap(MapArgs a, const u32 * __restrict__ remap_reads, u32 n_remap)
+{
+    __shared__ u32 s_hist[4][256];
+    Warp w = {(int)(threadIdx.x & 31), 32};
+    u32 wid = threadIdx.x >> 5;
+    u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
+    Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
+    u32 * bins = a.bins + (u64)gw * kNumBins;
+    PipeCounters cnt = {0, 0};
+    u64 c_cords = 0;
+    while (true)
+    {
+        u32 q = 0;
+        if (w.lane == 0) q = atomicAdd(a.queue, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= n_remap) break;
+        u32 r = remap_reads[q];
+        ReadSlot slot = a.slots[r];
+        u64 L = a.read_off[r + 1] - a.read_off[r];
+        PipeIn in;
+        fill_pipe_in(a, r, in);
+        u64 * cords = a.cords + a.cords_base[r];
+        int cap = (int)(a.cords_base[r + 1] - a.cords_base[r]);
+        int nc = (int)slot.n_cords;
+        int rc = 0;
+        for (u32 g = 0; g < slot.n_tasks && !rc; g++)
+        {
+            u32 ti = slot.task0 + g;
+            const SeedTask t = a.tasks[ti];
+            u64 s0 = t.sample0, s1 = s0 + t.n_samples;
+            u64 base = a.aoff[s0] + ti;
+            int n = (int)(a.aoff[s1] - a.aoff[s0]) + 1;
+            rc = phase_map(w, ar, s_hist[wid], bins, in, a.A + base, a.B + base, n, (u64)t.str, (u64)t.end & kMaskY, 1, cords, nc, cap,
+                           (u64 *)0, (u32 *)0, 0, cnt);
+        }
+        if (!rc) rc = finish_read(w, ar, L, cords, nc, cap, (Blk *)0, 0, true);
+        slot.n_cords = rc ? 0 : (u32)nc;
+        slot.status = rc ? 2u : 0u;
+        if (!rc) c_cords += (u64)nc;
+        if (w.lane == 0) a.slots[r] = slot;
+    }
+    if (w.lane == 0)
+    {
+        if (cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)cnt.hits);
+        if (cnt.windows) atomicAdd(&a.counters[4], (unsigned long long)cnt.windows);
+        if (c_cords) atomicAdd(&a.counters[5], (unsigned long long)c_cords);
+    }
+}
+
+__global__ void k_slot_counts(const ReadSlot * __restrict__ slots, u32 n, u32 * __restrict__ cnt, u32 * __restrict__ n_fail)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cnt[i] = slots[i].n_cords;
+    if (slots[i].status == 2) atomicAdd(n_fail, 1u);
+}
+// one warp per read copies its cords to the concatenated output
+__global__ void k_gather_cords(const u64 * __restrict__ cords, const u64 * __restrict__ cords_base, const u32 * __restrict__ ncords,
+                               const u64 * __restrict__ out_off, u32 n_reads, u64 * __restrict__ out, u64 out_cap)
+{
+    u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    u64 o = out_off[r];
+    const u64 * src = cords + cords_base[r];
+    u32 n = ncords[r];
+    for (u32 i = lane; i < n; i += 32)
+        if (o + i < out_cap) out[o + i] = src[i];
+}
+
+// ---- scan helper ------------------------------------------------------------------------------------------
+// out[i] = exclusive prefix of in[0..n) (after optional capping); *d_total (device u64) receives the sum
+template <class OutT>
+static int device_scan(lnr_ctx * ctx, u32 * d_in, u64 n, u32 cap, OutT * d_out, u64 * d_total, const char * tag)
+{
+    u32 nb = (u32)((n + STILE - 1) / STILE);
+    CK(ctx->scan_tmp.reserve(((size_t)nb + 2) * sizeof(u64)));
+    u64 * part = ctx->scan_tmp.as<u64>();
+    {
+        LaunchScope ls(ctx, tag, 3);
+        k_scan_reduce<<<nb, ST, 0, ctx->stream>>>(d_in, n, cap, part);
+        k_scan_spine<<<1, 1024, 0, ctx->stream>>>(part, nb, d_total);
+        k_scan_apply<OutT><<<nb, ST, 0, ctx->stream>>>(d_in, n, part, d_out);
+    }
+    CK(cudaGetLastError());
+    return LNR_OK;
+}
+
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int lnr_ctx_create(int device, lnr_ctx ** out)
+{
+    if (!out) return LNR_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return LNR_E_CUDA;
+    lnr_ctx * ctx = new lnr_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LNR_E_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LNR_E_CUDA; }
+    *out = ctx;
+    return LNR_OK;
+}
+void lnr_ctx_destroy(lnr_ctx * ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    harvest_stats(ctx);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
+                       &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
+                       &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list})
+        b->release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char * lnr_last_error(const lnr_ctx * ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int lnr_ctx_set_profiling(lnr_ctx * ctx, int on) { if (!ctx) return LNR_E_ARG; ctx->profiling = on != 0; return LNR_OK; }
+int lnr_ctx_reset_kernel_times(lnr_ctx * ctx)
+{
+    if (!ctx) return LNR_E_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    harvest_stats(ctx);
+    ctx->stats.clear();
+    ctx->stat_order.clear();
+    return LNR_OK;
+}
+int lnr_ctx_kernel_times(lnr_ctx * ctx, int cap, const char ** names, float * total_ms, uint64_t * launches)
+{
+    if (!ctx) return LNR_E_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    harvest_stats(ctx);
+    int i = 0;
+    for (auto & nm : ctx->stat_order)
+    {
+        if (i < cap)
+        {
+            auto it = ctx->stats.find(nm);
+            names[i] = it->first.c_str();
+            total_ms[i] = (float)it->second.ms;
+            launches[i] = it->second.launches;
+        }
+        i++;
+    }
+    return i;
+}
+
+// ---- genome -------------------------------------------------------------------------------------------
+static int genome_layout(lnr_ctx * ctx, uint32_t n_contigs, const uint64_t * len, lnr_genome * g)
+{
+    if (n_contigs == 0 || n_contigs > 1024) return fail(ctx, LNR_E_LIMIT, "1..1024 contigs (linear.cpp:107)");
+    uint64_t off = 0;
+    for (uint32_t i = 0; i < n_contigs; i++)
+    {
+        if (len[i] >= (1ULL << 30) - (1ULL << 20)) return fail(ctx, LNR_E_LIMIT, "contig length must be < 2^30 - 2^20 (cords.cpp:13-15)");
+        g->len.push_back(len[i]);
+        g->off.push_back(off);
+        off += (len[i] + 256 + 255) & ~255ULL;
+    }
+    g->total_padded = off + 256;
+    return LNR_OK;
+}
+int lnr_genome_upload(lnr_ctx * ctx, uint32_t n_contigs, const uint8_t * const * dna5, const uint64_t * len, lnr_genome ** out)
+{
+    if (!ctx || !dna5 || !len || !out) return LNR_E_ARG;
+    cudaSetDevice(ctx->device);
+    lnr_genome * g = new lnr_genome();
+    g->ctx = ctx; g->n_contigs = n_contigs; g->d_bases = nullptr;
+    int rc = genome_layout(ctx, n_contigs, len, g);
+    if (rc) { delete g; return rc; }
+    cudaError_t e = cudaMalloc(&g->d_bases, g->total_padded);
+    if (e != cudaSuccess) { delete g; return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)); }
+    cudaMemsetAsync(g->d_bases, 0, g->total_padded, ctx->stream);
+    for (uint32_t i = 0; i < n_contigs; i++)
+        cudaMemcpyAsync(g->d_bases + g->off[i], dna5[i], len[i], cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(g->d_bases); delete g; return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)); }
+    *out = g;
+    return LNR_OK;
+}
+int lnr_genome_from_device(lnr_ctx * ctx, uint32_t n_contigs, const uint8_t * dev_concat, const uint64_t * len, lnr_genome ** out)
+{
+    if (!ctx || !dev_concat || !len || !out) return LNR_E_ARG;
+    cudaSetDevice(ctx->device);
+    lnr_genome * g = new lnr_genome();
+    g->ctx = ctx; g->n_contigs = n_contigs; g->d_bases = nullptr;
+    int rc = genome_layout(ctx, n_contigs, len, g);
+    if (rc) { delete g; return rc; }
+    cudaError_t e = cudaMalloc(&g->d_bases, g->total_padded);
+    if (e != cudaSuccess) { delete g; return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)); }
+    cudaMemsetAsync(g->d_bases, 0, g->total_padded, ctx->stream);
+    uint64_t src = 0;
+    for (uint32_t i = 0; i < n_contigs; i++)
+    {
+        cudaMemcpyAsync(g->d_bases + g->off[i], dev_concat + src, len[i], cudaMemcpyDeviceToDevice, ctx->stream);
+        src += len[i];
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(g->d_bases); delete g; return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)); }
+    *out = g;
+    return LNR_OK;
+}
+void lnr_genome_destroy(lnr_genome * g)
+{
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    if (g->d_bases) cudaFree(g->d_bases);
+    delete g;
+}
+
+// ---- genome features ------------------------------------------------------------------------------------
+int lnr_features_build(lnr_ctx * ctx, const lnr_genome * g, int feature_type, unsigned threads_sem, lnr_feats ** out)
+{
+    if (!ctx || !g || !out || threads_sem == 0) return LNR_E_ARG;
+    if (feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "only feature_type 2 (2-mer/48, -f 2) is implemented");
+    cudaSetDevice(ctx->device);
+    lnr_feats * f = new lnr_feats();
+    f->ctx = ctx; f->feature_type = feature_type; f->n_contigs = g->n_contigs; f->d_f = nullptr; f->d_ptrs = nullptr; f->d_n = nullptr;
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < g->n_contigs; i++)
+    {
+        uint32_t n = feat_count_genome(g->len[i], threads_sem);
+        f->n.push_back(n);
+        f->off.push_back(tot);
+        tot += n + 8;   // a little slack between contigs
+    }
+    CK(cudaMalloc(&f->d_f, (tot + 8) * sizeof(F96)));
+    CK(cudaMemsetAsync(f->d_f, 0, (tot + 8) * sizeof(F96), ctx->stream));
+    CK(cudaMalloc(&f->d_ptrs, g->n_contigs * sizeof(F96 *)));
+    CK(cudaMalloc(&f->d_n, g->n_contigs * sizeof(u32)));
+    std::vector<const F96 *> ptrs;
+    for (uint32_t i = 0; i < g->n_contigs; i++) ptrs.push_back(f->d_f + f->off[i]);
+    CK(cudaMemcpyAsync(f->d_ptrs, ptrs.data(), ptrs.size() * sizeof(F96 *), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f->d_n, f->n.data(), f->n.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t i = 0; i < g->n_contigs; i++)
+    {
+        if (!f->n[i]) continue;
+        LaunchScope ls(ctx, "k_feat_genome");
+        u32 grid = (f->n[i] + FE - 1) / FE;
+        k_feat_genome<<<grid, FT, 0, ctx->stream>>>(g->d_bases + g->off[i], (i64)g->len[i], f->n[i], f->d_f + f->off[i]);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = f;
+    return LNR_OK;
+}
+int lnr_features_count(const lnr_feats * f, uint32_t contig, uint64_t * n)
+{
+    if (!f || !n || contig >= f->n_contigs) return LNR_E_ARG;
+    *n = f->n[contig];
+    return LNR_OK;
+}
+int lnr_features_download(const lnr_feats * f, uint32_t contig, void * dst, uint64_t cap_entries, uint64_t * n_entries)
+{
+    if (!f || contig >= f->n_contigs) return LNR_E_ARG;
+    lnr_ctx * ctx = f->ctx;
+    cudaSetDevice(ctx->device);
+    if (n_entries) *n_entries = f->n[contig];
+    if (!dst) return LNR_OK;
+    if (cap_entries < f->n[contig]) return fail(ctx, LNR_E_CAPACITY, "feature buffer too small");
+    CK(cudaMemcpy(dst, f->d_f + f->off[contig], (size_t)f->n[contig] * sizeof(F96), cudaMemcpyDeviceToHost));
+    return LNR_OK;
+}
+void lnr_features_destroy(lnr_feats * f)
+{
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    if (f->d_f) cudaFree(f->d_f);
+    if (f->d_ptrs) cudaFree((void *)f->d_ptrs);
+    if (f->d_n) cudaFree(f->d_n);
+    delete f;
+}
+
+// ---- index ---------------------------------------------------------------------------------------------------
+int lnr_index_build(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, lnr_index ** out)
+{
+    if (!ctx || !g || !out || threads_sem == 0) return LNR_E_ARG;
+    if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "only index_type 1 (DIndex, -i 1) is implemented");
+    cudaSetDevice(ctx->device);
+    // chunk table (createDIndex :1654-1670)
+    std::vector<IdxChunk> chunks;
+    std::vector<u32> tile0;
+    u64 n_samples = 0;
+    u32 n_tiles = 0;
+    for (uint32_t ci = 0; ci < g->n_contigs; ci++)
+        for (unsigned c = 0; c < threads_sem; c++)
+        {
+            IdxChunk ch;
+            memset(&ch, 0, sizeof ch);
+            ch.base_off = g->off[ci]; ch.len = (i64)g->len[ci]; ch.contig = ci;
+            idx_chunk_range(ch.len, threads_sem, c, ch.t_str, ch.n_samples);
+            if (ch.n_samples <= 0) continue;
+            ch.sample0 = n_samples;
+            n_samples += (u64)ch.n_samples;
+            tile0.push_back(n_tiles);
+            n_tiles += (u32)((ch.n_samples + ITILE - 1) / ITILE);
+            chunks.push_back(ch);
+        }
+    lnr_index * ix = new lnr_index();
+    ix->ctx = ctx; ix->index_type = 1; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = 0;
+    u32 * d_cnt = nullptr; IdxChunk * d_chunks = nullptr; u32 * d_tile0 = nullptr; u64 * d_total = nullptr;
+    auto cleanup = [&]() { if (d_cnt) cudaFree(d_cnt); if (d_chunks) cudaFree(d_chunks); if (d_tile0) cudaFree(d_tile0); if (d_total) cudaFree(d_total); };
+#define CKI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); lnr_index_destroy(ix); return LNR_E_CUDA; } } while (0)
+    CKI(cudaMalloc(&ix->d_dir, (size_t)kDirSize * sizeof(i32)));
+    CKI(cudaMalloc(&d_cnt, ((size_t)kDirSize + 16) * sizeof(u32)));
+    CKI(cudaMalloc(&d_total, sizeof(u64)));
+    CKI(cudaMemsetAsync(d_cnt, 0, ((size_t)kDirSize + 16) * sizeof(u32), ctx->stream));
+    u32 n_chunks = (u32)chunks.size();
+    if (n_chunks)
+    {
+        CKI(cudaMalloc(&d_chunks, chunks.size() * sizeof(IdxChunk)));
+        CKI(cudaMalloc(&d_tile0, tile0.size() * sizeof(u32)));
+        CKI(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(IdxChunk), cudaMemcpyHostToDevice, ctx->stream));
+        CKI(cudaMemcpyAsync(d_tile0, tile0.data(), tile0.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_idx_prep");
+            k_idx_prep<<<(n_chunks + 127) / 128, 128, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks);
+        }
+        {
+            LaunchScope ls(ctx, "k_idx_count");
+            k_idx_pass<false><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, d_cnt, nullptr, nullptr, nullptr);
+        }
+        CKI(cudaGetLastError());
+    }
+    // omit buckets > 400, exclusive prefix sum over 2^26+1 entries (:1702-1721)
+    {
+        int rc = device_scan<i32>(ctx, d_cnt, kDirSize, kIdxOmit, ix->d_dir, d_total, "k_scan_dir");
+        if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
+    }
+    u64 total = 0;
+    CKI(cudaMemcpyAsync(&total, d_total, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CKI(cudaStreamSynchronize(ctx->stream));
+    if (total >= (1ULL << 31)) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_LIMIT, "hs exceeds int32 bucket offsets (index_util.h:101)"); }
+    ix->n_hs = total;
+    CKI(cudaMalloc(&ix->d_hs, (size_t)(total + 8) * sizeof(u64)));
+    if (n_chunks && total)
+    {
+        CKI(cudaMemsetAsync(d_cnt, 0, ((size_t)kDirSize + 16) * sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_idx_fill");
+            k_idx_pass<true><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, nullptr, ix->d_dir, d_cnt, ix->d_hs);
+        }
+        {
+            LaunchScope ls(ctx, "k_idx_sort_buckets");
+            k_idx_sort_buckets<<<((kDirSize - 1) + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, ix->d_hs, kDirSize - 1);
+        }
+        CKI(cudaGetLastError());
+    }
+    CKI(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+#undef CKI
+    *out = ix;
+    return LNR_OK;
+}
+int lnr_index_export_dindex(const lnr_index * ix, int32_t * dir, uint64_t * hs, uint64_t hs_cap, uint64_t * n_hs)
+{
+    if (!ix) return LNR_E_ARG;
+    lnr_ctx * ctx = ix->ctx;
+    cudaSetDevice(ctx->device);
+    if (n_hs) *n_hs = ix->n_hs;
+    if (dir) CK(cudaMemcpy(dir, ix->d_dir, (size_t)kDirSize * sizeof(i32), cudaMemcpyDeviceToHost));
+    if (hs)
+    {
+        if (hs_cap < ix->n_hs) return fail(ctx, LNR_E_CAPACITY, "hs buffer too small");
+        CK(cudaMemcpy(hs, ix->d_hs, (size_t)ix->n_hs * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    return LNR_OK;
+}
+void lnr_index_destroy(lnr_index * ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->ctx->device);
+    if (ix->d_dir) cudaFree(ix->d_dir);
+    if (ix->d_hs) cudaFree(ix->d_hs);
+    delete ix;
+}
+
+// ---- seeding pass (count / scan / fill) -----------------------------------------------------------------------
+// tasks: host copy (sample0/n_samples filled); d_tasks: device copy. On return anchorsA holds the anchors,
+// *d_aoff the per-sample offsets (n_samples + 1 entries, in sample_info's tail buffer), total anchors in *total.
+static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases, const u64 * d_read_off, SeedTask * d_tasks,
+                        u32 n_tasks, u64 n_samples, DevBuf & aoff_buf, u64 * total_out, const char * tag)
+{
+    CK(ctx->sample_info.reserve((size_t)(n_samples + 1) * sizeof(u64)));
+    CK(ctx->sample_cnt.reserve((size_t)(n_samples + STILE + 1) * sizeof(u32)));
+    CK(aoff_buf.reserve((size_t)(n_samples + STILE + 1) * sizeof(u64)));
+    CK(ctx->misc.reserve(256));
+    u64 * d_total = ctx->misc.as<u64>();
+    unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
+    {
+        LaunchScope ls(ctx, "k_seed_prep");
+        k_seed_prep<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks);
+    }
+    // one extra zero count so that aoff[n_samples] = total
+    CK(cudaMemsetAsync(ctx->sample_cnt.as<u32>() + n_samples, 0, sizeof(u32), ctx->stream));
+    if (n_samples)
+    {
+        LaunchScope ls(ctx, tag);
+        k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dir,
+                                                                              ix->d_hs, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
+    }
+    CK(cudaGetLastError());
+    int rc = device_scan<u64>(ctx, ctx->sample_cnt.as<u32>(), n_samples + 1, 0, aoff_buf.as<u64>(), d_total, "k_scan_seeds");
+    if (rc) return rc;
+    u64 total = 0;
+    CK(cudaMemcpyAsync(&total, d_total, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *total_out = total;
+    size_t need = (size_t)(total + n_tasks + 8) * sizeof(u64);
+    CK(ctx->anchorsA.reserve(need));
+    CK(ctx->anchorsB.reserve(need));
+    if (n_samples)
+    {
+        LaunchScope ls(ctx, "k_seed_fill");
+        k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs,
+                                                                             ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>());
+    }
+    CK(cudaGetLastError());
+    return LNR_OK;
+}
+
+// ---- the batch ---------------------------------------------------------------------------------------------------
+static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, const lnr_params * prm, uint32_t n_reads,
+                       const u8 * d_bases, const uint64_t * h_read_off, u64 * d_out, u64 * d_out_off, uint64_t out_cap,
+                       uint64_t * n_cords_total, lnr_debug_out * dbg)
+{
+    if (n_reads == 0) { if (n_cords_total) *n_cords_total = 0; return LNR_OK; }
+    const float stop_ratio = prm && prm->preset == 0 ? 0.7f : 0.0f;
+    // ---- host-side layout from the read lengths
+    std::vector<SeedTask> tasks(n_reads);
+    std::vector<u64> foff(n_reads + 1), cbase(n_reads + 1), hoff(n_reads + 1);
+    std::vector<u32> ftile(n_reads + 1);
+    u64 n_samples = 0, nf_tot = 0, c_tot = 0;
+    u32 n_ftiles = 0;
+    for (uint32_t r = 0; r < n_reads; r++)
+    {
+        u64 L = h_read_off[r + 1] - h_read_off[r];
+        if (L >= (1ULL << 20)) return fail(ctx, LNR_E_LIMIT, "read length must be < 2^20 (cords.h:25)");
+        SeedTask & t = tasks[r];
+        memset(&t, 0, sizeof t);
+        t.read = r; t.str = 0; t.end = (u32)L; t.alpha = 15;
+        t.n_samples = L > (u64)kMinReadLen ? seed_task_samples(0, (u32)L, 15) : 0;
+        t.sample0 = n_samples;
+        n_samples += t.n_samples;
+        u32 nf = L > (u64)kMinReadLen ? feat_count_read(L) : 0;
+        foff[r] = nf_tot;
+        nf_tot += 2ull * nf;
+        ftile[r] = n_ftiles;
+        n_ftiles += 2 * ((nf + FE - 1) / FE);
+        cbase[r] = c_tot;
+        c_tot += L > (u64)kMinReadLen ? 16 + L / 4 : 0;
+    }
+    foff[n_reads] = nf_tot; ftile[n_reads] = n_ftiles; cbase[n_reads] = c_tot;
+    const u64 total_bases = h_read_off[n_reads];
+    // ---- uploads
+    CK(ctx->read_off.reserve((n_reads + 1) * sizeof(u64)));
+    CK(ctx->tasks.reserve(n_reads * sizeof(SeedTask)));
+    CK(ctx->foff.reserve((n_reads + 1) * sizeof(u64)));
+    CK(ctx->ftile.reserve((n_reads + 1) * sizeof(u32)));
+    CK(ctx->cords_base.reserve((n_reads + 1) * sizeof(u64)));
+    CK(ctx->feats.reserve((size_t)(nf_tot + 8) * sizeof(F96)));
+    CK(ctx->cords.reserve((size_t)(c_tot + 8) * sizeof(u64)));
+    CK(ctx->slots.reserve((size_t)n_reads * sizeof(ReadSlot)));
+    CK(ctx->ncords.reserve((size_t)(n_reads + STILE + 1) * sizeof(u32)));
+    CK(ctx->out_off.reserve((size_t)(n_reads + STILE + 1) * sizeof(u64)));
+    CK(ctx->misc.reserve(256));
+    CK(cudaMemcpyAsync(ctx->read_off.p, h_read_off, (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), n_reads * sizeof(SeedTask), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->foff.p, foff.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ftile.p, ftile.data(), (n_reads + 1) * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->cords_base.p, cbase.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+    const u64 * d_read_off = ctx->read_off.as<u64>();
+    unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
+    u32 * d_queue = (u32 *)(ctx->misc.as<u64>() + 20);
+    u32 * d_ntasks2 = d_queue + 1;
+    u32 * d_nfail = d_queue + 2;
+    // ---- read features (both strands)
+    if (n_ftiles)
+    {
+        LaunchScope ls(ctx, "k_feat_reads");
+        k_feat_reads<<<n_ftiles, FT, 0, ctx->stream>>>(d_bases, d_read_off, ctx->foff.as<u64>(), ctx->ftile.as<u32>(), n_reads, ctx->feats.as<F96>());
+    }
+    CK(cudaGetLastError());
+    // ---- primary seeding
+    DevBuf & aoff = ctx->read_meta;   // reused as the per-sample anchor offset buffer
+    u64 total_anchors = 0;
+    int rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks.as<SeedTask>(), n_reads, n_samples, aoff, &total_anchors, "k_seed_count");
+    if (rc) return rc;
+    if (dbg && dbg->raw_anchors_off)
+    {
+        // per-read raw anchors without the sentinel: copy region by region (debug path, not timed)
+        std::vector<u64> h_aoff(n_samples + 1);
+        CK(cudaMemcpyAsync(h_aoff.data(), aoff.p, (n_samples + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        u64 o = 0;
+        dbg->raw_anchors_off[0] = 0;
+        for (uint32_t r = 0; r < n_reads; r++)
+        {
+            u64 a0 = h_aoff[tasks[r].sample0], a1 = h_aoff[tasks[r].sample0 + tasks[r].n_samples];
+            u64 n = a1 - a0;
+            if (dbg->raw_anchors && o + n <= dbg->raw_anchors_cap && n)
+                CK(cudaMemcpyAsync(dbg->raw_anchors + o, ctx->anchorsA.as<u64>() + a0 + r + 1, n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+            o += n;
+            dbg->raw_anchors_off[r + 1] = o;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    // ---- workspace of the pipeline kernels
+    const int wpc = 4;
+    const int n_ctas = ctx->n_sm * ctx->map_ctas_per_sm;
+    const u64 n_warps = (u64)n_ctas * wpc;
+    CK(ctx->bins.reserve((size_t)n_warps * kNumBins * sizeof(u32)));
+    CK(ctx->arena.reserve((size_t)n_warps * ctx->arena_bytes_per_warp));
+    if (ctx->bins_zeroed != ctx->bins.p || ctx->bins_zeroed_cap != ctx->bins.cap)   // the kernels return the histograms zeroed
+    {
+        ctx->bins_zeroed_cap = ctx->bins.cap;
+        CK(cudaMemsetAsync(ctx->bins.p, 0, (size_t)n_warps * kNumBins * sizeof(u32), ctx->stream));
+        ctx->bins_zeroed = ctx->bins.p;
+    }
+    u32 tasks2_cap = n_reads * 4 + 1024;
+    CK(ctx->tasks2.reserve((size_t)tasks2_cap * sizeof(SeedTask)));
+    if (dbg && dbg->hits_off)
+    {
+        u64 o = 0;
+        for (uint32_t r = 0; r < n_reads; r++) { hoff[r] = o; o += (h_read_off[r + 1] - h_read_off[r]) / 8 + 64; }
+        hoff[n_reads] = o;
+        CK(ctx->dbg_hits.reserve((size_t)o * sizeof(u64)));
+        CK(ctx->dbg_hoff.reserve((n_reads + 1) * sizeof(u64)));
+        CK(ctx->dbg_nhits.reserve(n_reads * sizeof(u32)));
+        CK(cudaMemsetAsync(ctx->dbg_nhits.p, 0, n_reads * sizeof(u32), ctx->stream));
+        CK(cudaMemcpyAsync(ctx->dbg_hoff.p, hoff.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (dbg && dbg->cords1_off)
+    {
+        CK(ctx->dbg_c1.reserve((size_t)(c_tot + 8) * sizeof(u64)));
+        CK(ctx->dbg_nc1.reserve(n_reads * sizeof(u32)));
+        CK(cudaMemsetAsync(ctx->dbg_nc1.p, 0, n_reads * sizeof(u32), ctx->stream));
+    }
+    MapArgs a;
+    memset(&a, 0, sizeof a);
+    a.read_off = d_read_off; a.bases = d_bases; a.n_reads = n_reads;
+    a.feats = ctx->feats.as<F96>(); a.foff = ctx->foff.as<u64>();
+    a.f2 = f2->d_ptrs; a.nf2 = f2->d_n;
+    a.tasks = ctx->tasks.as<SeedTask>(); a.n_tasks = n_reads;
+    a.aoff = aoff.as<u64>();
+    a.A = ctx->anchorsA.as<u64>(); a.B = ctx->anchorsB.as<u64>();
+    a.cords = ctx->cords.as<u64>(); a.cords_base = ctx->cords_base.as<u64>();
+    a.slots = ctx->slots.as<ReadSlot>();
+    a.tasks2 = ctx->tasks2.as<SeedTask>(); a.tasks2_cap = tasks2_cap; a.n_tasks2 = d_ntasks2;
+    a.bins = ctx->bins.as<u32>(); a.arena = ctx->arena.as<u8>(); a.arena_per_warp = ctx->arena_bytes_per_warp;
+    a.queue = d_queue;
+    a.stop_ratio = stop_ratio;
+    a.counters = d_counters;
+    if (dbg && dbg->hits_off) { a.dbg_hits = ctx->dbg_hits.as<u64>(); a.dbg_hoff = ctx->dbg_hoff.as<u64>(); a.dbg_nhits = ctx->dbg_nhits.as<u32>(); }
+    if (dbg && dbg->cords1_off) { a.dbg_c1 = ctx->dbg_c1.as<u64>(); a.dbg_nc1 = ctx->dbg_nc1.as<u32>(); }
+    {
+        LaunchScope ls(ctx, "k_map_primary");
+        k_map_primary<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    // ---- re-map pass
+    u32 n_tasks2 = 0;
+    CK(cudaMemcpyAsync(&n_tasks2, d_ntasks2, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_tasks2 > tasks2_cap) return fail(ctx, LNR_E_CAPACITY, "re-map task buffer exhausted");
+    if (n_tasks2)
+    {
+        std::vector<SeedTask> t2(n_tasks2);
+        std::vector<ReadSlot> slots(n_reads);
+        CK(cudaMemcpyAsync(t2.data(), ctx->tasks2.p, n_tasks2 * sizeof(SeedTask), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(slots.data(), ctx->slots.p, n_reads * sizeof(ReadSlot), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        u64 ns2 = 0;
+        for (u32 i = 0; i < n_tasks2; i++) { t2[i].sample0 = ns2; ns2 += t2[i].n_samples; }
+        std::vector<u32> remap_reads;
+        for (uint32_t r = 0; r < n_reads; r++) if (slots[r].status == 1) remap_reads.push_back(r);
+        CK(cudaMemcpyAsync(ctx->tasks2.p, t2.data(), n_tasks2 * sizeof(SeedTask), cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx->remap_list.reserve(std::max<size_t>(remap_reads.size(), 1) * sizeof(u32)));
+        u32 * d_remap = ctx->remap_list.as<u32>();
+        CK(cudaMemcpyAsync(d_remap, remap_reads.data(), remap_reads.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        u64 total2 = 0;
+        rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_remap");
+        if (rc) return rc;
+        a.tasks = ctx->tasks2.as<SeedTask>(); a.n_tasks = n_tasks2;
+        a.aoff = aoff.as<u64>();
+        a.A = ctx->anchorsA.as<u64>(); a.B = ctx->anchorsB.as<u64>();
+        a.dbg_hits = nullptr; a.dbg_c1 = nullptr; a.dbg_nhits = nullptr; a.dbg_nc1 = nullptr;
+        CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_map_remap");
+            k_map_remap<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size());
+        }
+        CK(cudaGetLastError());
+    }
+    // ---- compaction into the caller's layout
+    {
+        LaunchScope ls(ctx, "k_slot_counts");
+        k_slot_counts<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(ctx->slots.as<ReadSlot>(), n_reads, ctx->ncords.as<u32>(), d_nfail);
+    }
+    CK(cudaMemsetAsync(ctx->ncords.as<u32>() + n_reads, 0, sizeof(u32), ctx->stream));
+    u64 * d_total = ctx->misc.as<u64>();
+    rc = device_scan<u64>(ctx, ctx->ncords.as<u32>(), (u64)n_reads + 1, 0, d_out_off ? d_out_off : ctx->out_off.as<u64>(), d_total, "k_scan_cords");
+    if (rc) return rc;
+    const u64 * d_off = d_out_off ? d_out_off : ctx->out_off.as<u64>();
+    {
+        LaunchScope ls(ctx, "k_gather_cords");
+        k_gather_cords<<<(u32)(((u64)n_reads * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->cords.as<u64>(), ctx->cords_base.as<u64>(),
+                                                                                       ctx->ncords.as<u32>(), d_off, n_reads, d_out, out_cap);
+    }
+    CK(cudaGetLastError());
+    u64 h_misc[32];
+    CK(cudaMemcpyAsync(h_misc, ctx->misc.p, sizeof h_misc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u64 total_cords = h_misc[0];
+    u32 n_fail = ((u32 *)(h_misc + 20))[2];
+    ctx->counters[0] = n_samples;                 // S
+    ctx->counters[1] = h_misc[8 + 1];             // H
+    ctx->counters[2] = h_misc[8 + 2];             // A
+    ctx->counters[3] = h_misc[8 + 3];             // Hits
+    ctx->counters[4] = h_misc[8 + 4];             // W
+    ctx->counters[5] = total_cords;               // C
+    ctx->counters[6] = total_bases;
+    ctx->counters[7] = n_tasks2;
+    if (n_cords_total) *n_cords_total = total_cords;
+    if (dbg && dbg->hits_off)
+    {
+        std::vector<u32> nh(n_reads);
+        CK(cudaMemcpy(nh.data(), ctx->dbg_nhits.p, n_reads * sizeof(u32), cudaMemcpyDeviceToHost));
+        u64 o = 0;
+        dbg->hits_off[0] = 0;
+        for (uint32_t r = 0; r < n_reads; r++)
+        {
+            u64 n = std::min<u64>(nh[r], hoff[r + 1] - hoff[r]);
+            if (dbg->hits && o + n <= dbg->hits_cap && n)
+                CK(cudaMemcpy(dbg->hits + o, ctx->dbg_hits.as<u64>() + hoff[r], n * sizeof(u64), cudaMemcpyDeviceToHost));
+            o += n;
+            dbg->hits_off[r + 1] = o;
+        }
+    }
+    if (dbg && dbg->cords1_off)
+    {
+        std::vector<u32> nc1(n_reads);
+        CK(cudaMemcpy(nc1.data(), ctx->dbg_nc1.p, n_reads * sizeof(u32), cudaMemcpyDeviceToHost));
+        u64 o = 0;
+        dbg->cords1_off[0] = 0;
+        for (uint32_t r = 0; r < n_reads; r++)
+        {
+            u64 n = nc1[r];
+            if (dbg->cords1 && o + n <= dbg->cords1_cap && n)
+                CK(cudaMemcpy(dbg->cords1 + o, ctx->dbg_c1.as<u64>() + cbase[r], n * sizeof(u64), cudaMemcpyDeviceToHost));
+            o += n;
+            dbg->cords1_off[r + 1] = o;
+        }
+    }
+    if (n_fail) return fail(ctx, LNR_E_CAPACITY, "per-read scratch exhausted for some reads (raise arena_bytes_per_warp)");
+    if (total_cords > out_cap) return fail(ctx, LNR_E_CAPACITY, "cords_capacity too small");
+    return LNR_OK;
+}
+
+int lnr_apxmap_batch_device(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, const lnr_params * prm, uint32_t n_reads,
+                            const uint8_t * dev_bases, const uint64_t * host_read_off, uint64_t * dev_cords, uint64_t * dev_cords_off,
+                            uint64_t cords_capacity, uint64_t * n_cords_total)
+{
+    if (!ctx || !ix || !f2 || !host_read_off || !dev_bases || !dev_cords) return LNR_E_ARG;
+    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
+    cudaSetDevice(ctx->device);
+    return apxmap_core(ctx, ix, f2, prm, n_reads, dev_bases, host_read_off, dev_cords, dev_cords_off, cords_capacity, n_cords_total, nullptr);
+}
+
+int lnr_apxmap_batch(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, const lnr_params * prm, uint32_t n_reads,
+                     const uint8_t * bases, const uint64_t * read_off, uint64_t * cords, uint64_t * cords_off, uint64_t cords_capacity,
+                     lnr_debug_out * dbg)
+{
+    if (!ctx || !ix || !f2 || !read_off || (!bases && n_reads) || !cords || !cords_off) return LNR_E_ARG;
+    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
+    cudaSetDevice(ctx->device);
+    if (n_reads == 0) { cords_off[0] = 0; return LNR_OK; }
+    u64 total_bases = read_off[n_reads];
+    CK(ctx->bases.reserve((size_t)total_bases + 256));
+    CK(cudaMemcpyAsync(ctx->bases.p, bases, total_bases, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->bases.as<u8>() + total_bases, 0, 256, ctx->stream));
+    CK(ctx->out_cords.reserve((size_t)(cords_capacity + 8) * sizeof(u64)));
+    u64 total = 0;
+    int rc = apxmap_core(ctx, ix, f2, prm, n_reads, ctx->bases.as<u8>(), read_off, ctx->out_cords.as<u64>(), nullptr, cords_capacity, &total, dbg);
+    if (rc && rc != LNR_E_CAPACITY) return rc;
+    if (rc == LNR_E_CAPACITY && total > cords_capacity) return rc;
+    CK(cudaMemcpyAsync(cords_off, ctx->out_off.p, (n_reads + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cords, ctx->out_cords.p, (size_t)total * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int lnr_last_batch_counters(lnr_ctx * ctx, uint64_t counters[8])
+{
+    if (!ctx || !counters) return LNR_E_ARG;
+    for (int i = 0; i < 8; i++) counters[i] = ctx->counters[i];
+    return LNR_OK;
+}
+
+int lnr_read_features(lnr_ctx * ctx, const uint8_t * dna5, uint64_t len, int feature_type, void * dst_fwd, void * dst_rev,
+                      uint64_t cap_entries, uint64_t * n_entries)
+{
+    if (!ctx || !dna5) return LNR_E_ARG;
+    if (feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
+    cudaSetDevice(ctx->device);
+    u32 nf = feat_count_read(len);
+    if (n_entries) *n_entries = nf;
+    if (!nf) return LNR_OK;
+    if (cap_entries < nf) return fail(ctx, LNR_E_CAPACITY, "feature buffer too small");
+    CK(ctx->bases.reserve((size_t)len + 256));
+    CK(ctx->feats.reserve((size_t)(2 * nf + 8) * sizeof(F96)));
+    CK(ctx->read_off.reserve(2 * sizeof(u64)));
+    CK(ctx->foff.reserve(2 * sizeof(u64)));
+    CK(ctx->ftile.reserve(2 * sizeof(u32)));
+    u64 ro[2] = {0, len}, fo[2] = {0, 2ull * nf};
+    u32 ft[2] = {0, 2 * ((nf + FE - 1) / FE)};
+    CK(cudaMemcpyAsync(ctx->bases.p, dna5, len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->read_off.p, ro, sizeof ro, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->foff.p, fo, sizeof fo, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ftile.p, ft, sizeof ft, cudaMemcpyHostToDevice, ctx->stream));
+    k_feat_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(), 1, ctx->feats.as<F96>());
+    CK(cudaGetLastError());
+    if (dst_fwd) CK(cudaMemcpyAsync(dst_fwd, ctx->feats.p, (size_t)nf * sizeof(F96), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst_rev) CK(cudaMemcpyAsync(dst_rev, ctx->feats.as<F96>() + nf, (size_t)nf * sizeof(F96), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LNR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+"""Generates tests/golden/golden.json from the UNMODIFIED reference (oracle/_ref/libref_harness.so, built from
+/root/reference by oracle/build_ref.sh). Run in the build container only:  python tests/golden/make_golden.py
+The reference ships no golden vectors of its own; these digests pin the oracle
+restatement and the CUDA path to the reference's own outputs on the seeded cases of tests/cases.py."""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+from cases import CASES, digest, make_case  # noqa: E402
+from cpu_checkers import RefImpl  # noqa: E402
+
+out = {}
+for name in CASES:
+    g, reads, bases, offs, T, preset = make_case(name)
+    R = RefImpl(g, threads=T, preset=preset)
+    d, hs = R.dindex()
+    nz = np.flatnonzero(np.diff(d))
+    e = {"threads": T, "preset": preset, "n_hs": int(len(hs)), "hs": digest(hs),
+         "dir_nonzero": digest(nz.astype(np.int64)), "dir_counts": digest(np.diff(d)[nz].astype(np.int32)),
+         "genome_features": [digest(R.genome_features(i)[:-1]) for i in range(len(g))]}
+    # two passes of the reference over every read; reads whose output is not reproducible are excluded
+    # (the reference reads unowned bytes in rare cases)
+    empty = np.zeros(0, np.uint64)   # reads <= 200 bases are never mapped (mapper.cpp:440)
+    cords_a = [R.cords(r) if len(r) > 200 else empty for r in reads]
+    cords_b = [R.cords(r) if len(r) > 200 else empty for r in reads]
+    stable = [bool(np.array_equal(a, b)) for a, b in zip(cords_a, cords_b)]
+    e["stable"] = stable
+    e["n_cords"] = [int(len(c)) for c in cords_a]
+    e["cords"] = [digest(c) for c in cords_a]
+    e["raw_anchors"] = [digest(R.stage(r, 1)[1:]) if len(r) > 200 else digest(np.zeros(0, np.uint64)) for r in reads]
+    e["hits"] = [digest(R.stage(r, 3)) if len(r) > 200 else "" for r in reads]
+    out[name] = e
+    print(name, "reads", len(reads), "unstable", stable.count(False), "cords", sum(e["n_cords"]))
+json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=0)

@@ -290,3 +290,23 @@ int emu_map_batch(void * h, uint32_t n_reads, const uint8_t * bases, const uint6
 }
 
 }  // extern "C"
+
+// gnu_sort must reproduce std::sort's permutation, ties included. Sorts `n` (key, payload) records with a
+// key-only comparator by both and returns the number of positions that differ.
+extern "C" int emu_gnu_sort_check(uint64_t * keys_payload, int n, int descending)
+{
+    std::vector<uint64_t> a(keys_payload, keys_payload + n), b(a);
+    if (descending)
+    {
+        std::sort(a.begin(), a.end(), [](uint64_t & x, uint64_t & y) { return (x >> 32) > (y >> 32); });
+        lnr::gnu_sort(b.data(), n, [](const uint64_t & x, const uint64_t & y) { return (x >> 32) > (y >> 32); });
+    }
+    else
+    {
+        std::sort(a.begin(), a.end(), [](uint64_t & x, uint64_t & y) { return (x >> 32) < (y >> 32); });
+        lnr::gnu_sort(b.data(), n, [](const uint64_t & x, const uint64_t & y) { return (x >> 32) < (y >> 32); });
+    }
+    int bad = 0;
+    for (int i = 0; i < n; i++) bad += a[i] != b[i];
+    return bad;
+}

@@ -1,0 +1,155 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle (and, where oracle/_ref travelled
+with the snapshot, the unmodified reference) and against the committed golden digests. Bit-exact everywhere."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, digest, make_case
+from cpu_checkers import Oracle, RefImpl, have_ref
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import linear_b200
+    linear_b200.load_library()   # fails loudly if the CUDA extension is missing
+    return linear_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(lb):
+    return lb.Context(0)
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, lb, ctx):
+    g, reads, bases, offs, T, preset = make_case(request.param)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    O = Oracle(g, threads=T, preset=preset)
+    return dict(name=request.param, g=g, reads=reads, bases=bases, offs=offs, T=T, preset=preset, gen=gen, feats=feats,
+                index=index, O=O)
+
+
+def test_dindex_bit_exact(case):
+    d0, h0 = case["O"].dindex()
+    d1, h1 = case["index"].export_dindex()
+    assert d1.shape == d0.shape and np.array_equal(d0, d1)
+    assert np.array_equal(h0, h1)
+    gd = GOLDEN[case["name"]]
+    assert len(h1) == gd["n_hs"] and digest(h1) == gd["hs"]
+
+
+def test_index_properties(case):
+    """size-independent properties: buckets ascending, <= 400 entries, every record decodes to a sampled position"""
+    d, hs = case["index"].export_dindex()
+    cnt = np.diff(d)
+    assert cnt.min() >= 0 and cnt.max() <= 400 and d[-1] == len(hs)
+    same_bucket = np.ones(len(hs) - 1, dtype=bool)
+    same_bucket[d[1:-1][(d[1:-1] > 0) & (d[1:-1] < len(hs))] - 1] = False
+    assert np.all(hs[1:][same_bucket] > hs[:-1][same_bucket])
+    x = (hs >> np.uint64(20)) & np.uint64((1 << 30) - 1)
+    cid = (hs >> np.uint64(50)) & np.uint64(1023)
+    lens = np.array([len(c) for c in case["g"]], dtype=np.uint64)
+    assert np.all(cid < len(lens)) and np.all(x - np.uint64(1 << 20) < lens[cid.astype(np.int64)])
+
+
+def test_genome_features_bit_exact(case):
+    for i in range(len(case["g"])):
+        assert np.array_equal(case["O"].genome_features(i), case["feats"].download(i))
+        assert digest(case["feats"].download(i)[:-1]) == GOLDEN[case["name"]]["genome_features"][i]
+
+
+def test_read_features_bit_exact(case, lb, ctx):
+    for r in case["reads"][:12]:
+        if len(r) <= 200:
+            continue
+        f, rc = lb.read_features(ctx, r)
+        assert np.array_equal(f, case["O"].read_features(r, 0))
+        assert np.array_equal(rc, case["O"].read_features(r, 1))
+
+
+def test_apxmap_stages_and_cords_bit_exact(case, lb, ctx):
+    O, reads = case["O"], case["reads"]
+    cords, coff, dbg = lb.apx_map_batch(ctx, case["index"], case["feats"], case["bases"], case["offs"], preset=case["preset"], debug=True)
+    gd = GOLDEN[case["name"]]
+    bad = []
+    for i, r in enumerate(reads):
+        mine = cords[int(coff[i]):int(coff[i + 1])]
+        if len(r) <= 200:
+            assert len(mine) == 0
+            continue
+        ra = dbg["ra"][int(dbg["ra_off"][i]):int(dbg["ra_off"][i + 1])]
+        assert np.array_equal(ra, O.stage(r, 1)[1:]), f"raw anchors, read {i}"
+        h = dbg["h"][int(dbg["h_off"][i]):int(dbg["h_off"][i + 1])]
+        assert np.array_equal(h, O.stage(r, 3)), f"hits, read {i}"
+        c1 = dbg["c1"][int(dbg["c1_off"][i]):int(dbg["c1_off"][i + 1])]
+        assert np.array_equal(c1, O.stage(r, 4)), f"cords after first apxMap_, read {i}"
+        if not np.array_equal(mine, O.cords(r)):
+            bad.append(i)
+        if gd["stable"][i]:
+            assert digest(mine) == gd["cords"][i], f"golden cords, read {i}"
+    assert not bad, f"cords differ for reads {bad}"
+    # cords_end reconstruction (pmpfinder.cpp:2790-2801)
+    assert np.array_equal(lb.cords_end(cords), cords + np.uint64((96 << 20) | 96))
+
+
+def test_batch_without_debug_and_repeatability(case, lb, ctx):
+    a, ao = lb.apx_map_batch(ctx, case["index"], case["feats"], case["bases"], case["offs"], preset=case["preset"])
+    b, bo = lb.apx_map_batch(ctx, case["index"], case["feats"], case["bases"], case["offs"], preset=case["preset"])
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    oc, oo = case["O"].map_batch(case["bases"], case["offs"], map_threads=4)
+    assert np.array_equal(oo, ao) and np.array_equal(oc, a)
+
+
+def test_empty_and_tiny_batches(case, lb, ctx):
+    c, off = lb.apx_map_batch(ctx, case["index"], case["feats"], np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(c) == 0 and list(off) == [0]
+    r = case["reads"][0]
+    c, off = lb.apx_map_batch(ctx, case["index"], case["feats"], r, np.array([0, len(r)], np.uint64), preset=case["preset"])
+    assert np.array_equal(c, case["O"].cords(r))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref did not travel")
+def test_against_unmodified_reference(lb, ctx):
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    R = RefImpl(g, threads=T, preset=preset)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    d0, h0 = R.dindex()
+    d1, h1 = index.export_dindex()
+    assert np.array_equal(d0, d1) and np.array_equal(h0, h1)
+    cords, coff = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset)
+    rc, ro = R.map_batch(bases, offs, map_threads=4)
+    assert np.array_equal(ro, coff) and np.array_equal(rc, cords)
+
+
+def test_genome_with_N_runs(lb, ctx):
+    """N arithmetic of the rolling hash (shape_extend.cpp:176-180) and of the features, closed-form on the GPU"""
+    from linear_b200 import datagen
+    lens = datagen.contig_lengths(600_000, 2, seed=4)
+    g = datagen.make_genome(21, lens, n_families=1, copies=30, n_tandem=4, n_runs=40)
+    rs = datagen.simulate_reads(5, g, 30, mean_len=5000, sd_len=1000, err=0.03)
+    O = Oracle(g, threads=4)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, 4)
+    index = lb.create_index(ctx, gen, 1, 4)
+    d0, h0 = O.dindex()
+    d1, h1 = index.export_dindex()
+    assert np.array_equal(d0, d1) and np.array_equal(h0, h1)
+    for i in range(len(g)):
+        assert np.array_equal(O.genome_features(i), feats.download(i))
+    cords, coff = lb.apx_map_batch(ctx, index, feats, rs.bases, rs.offsets)
+    oc, oo = O.map_batch(rs.bases, rs.offsets, map_threads=4)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+
+
+def test_limits_are_rejected(lb, ctx):
+    with pytest.raises(lb.LnrError):
+        lb.Genome(ctx, [np.zeros(10, np.uint8)] * 1025)
