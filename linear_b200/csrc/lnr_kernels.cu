@@ -1491,7 +1491,7 @@ int lnr_read_features(lnr_ctx * ctx, const uint8_t * dna5, uint64_t len, int fea
     cudaSetDevice(ctx->device);
     u32 nf = feat_count_read(len);
     if (n_entries) *n_entries = nf;
-    if (!nf) return LNR_OK;
+    if (!nf || (!dst_fwd && !dst_rev)) return LNR_OK;   // count query
     if (cap_entries < nf) return fail(ctx, LNR_E_CAPACITY, "feature buffer too small");
     CK(ctx->bases.reserve((size_t)len + 256));
     CK(ctx->feats.reserve((size_t)(2 * nf + 8) * sizeof(F96)));
