@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- reads/sec of apx-map + chain (and index-build seconds) of the B200 path of `linear filter`.
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): a synthetic 3.1-Gbase, 24-contig genome
+with planted repeats, ONT-like simulated reads (lognormal mean 20 kb, ~10 % error 4:3:3 sub:ins:del, 20 % of
+reads with one planted ins/del/inv/dup SV, 50 % reverse strand). One "step" = one batch of reads through the
+whole hot path: reverse complement + 2x read features + seeding + anchor filter/sort + chaining + window
+extension + block chaining = cords (what Mapper::p_calRecords does per read before mapGaps).
+
+  value  reads/s, whole job, inputs already resident in HBM           (lnr_apxmap_batch_device)
+  e2e    reads/s through the drop-in C-ABI call with pinned HOST buffers, H2D of bases and D2H of cords inside
+         the timed region                                             (lnr_apxmap_batch)
+  roofline      dominant kernel of the step: algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the reference's own CPU code (oracle/_ref, or the oracle port) on a bounded sample of the batch
+  --impl reference   times that CPU implementation alone, same config / metric
+
+N > 1 (torchrun): reads shard across ranks with no data-path collective (weak scaling, fixed reads per GPU); the
+index is replicated. Timing: barrier + cuda sync both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GENOME_BASES = int(os.environ.get("LNR_BENCH_GENOME", 3_100_000_000))
+N_CONTIGS = 24
+THREADS_SEM = 16          # the reference's code default -t (base.cpp:26-54); semantic for the index
+METRIC = "reads/sec apx-map+chain (3.1-Gbase synth); index build sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 16384)))
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("LNR_BENCH_CPU_SAMPLE", 2048)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def contig_lengths():
+    from linear_b200 import datagen
+    return datagen.contig_lengths(GENOME_BASES, N_CONTIGS, seed=31)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic inputs, generated on the GPU (torch is plumbing here: device memory + RNG)
+# ---------------------------------------------------------------------------------------------------------
+def gen_genome(torch, dev, lens, seed=1234):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    total = int(sum(lens))
+    genome = torch.empty(total, dtype=torch.uint8, device=dev)
+    step = 1 << 28
+    for s in range(0, total, step):   # chunked: randint materialises int64 internally
+        n = min(step, total - s)
+        genome[s:s + n] = torch.randint(0, 4, (n,), generator=g, device=dev, dtype=torch.uint8)
+    # planted interspersed repeat families: 8 families x 2000 copies x 300 bp, ~12 % divergence, and 2000 tandem arrays
+    for fam in range(8):
+        base = torch.randint(0, 4, (300,), generator=g, device=dev, dtype=torch.uint8)
+        pos = torch.randint(0, total - 400, (2000,), generator=g, device=dev)
+        idx = (pos[:, None] + torch.arange(300, device=dev)[None, :]).reshape(-1)
+        copies = base.repeat(2000)
+        mut = torch.rand(copies.shape, generator=g, device=dev) < 0.12
+        copies = torch.where(mut, torch.randint(0, 4, copies.shape, generator=g, device=dev, dtype=torch.uint8), copies)
+        genome[idx] = copies
+    unit_len = 40
+    pos = torch.randint(0, total - 2000, (2000,), generator=g, device=dev)
+    units = torch.randint(0, 4, (2000, unit_len), generator=g, device=dev, dtype=torch.uint8)
+    arr = units.repeat(1, 20)
+    idx = (pos[:, None] + torch.arange(unit_len * 20, device=dev)[None, :]).reshape(-1)
+    genome[idx] = arr.reshape(-1)
+    return genome
+
+
+def gen_reads(torch, dev, genome, lens, n_reads, seed, mean=20000, sigma=0.5, err=0.10, mix=(4, 3, 3), sv_frac=0.2):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    mu = float(np.log(mean) - sigma * sigma / 2)
+    L = torch.exp(torch.randn(n_reads, generator=g, device=dev) * sigma + mu).long().clamp_(2000, 150000)
+    off = torch.zeros(n_reads + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(L, 0)
+    total = int(off[-1].item())
+    rid = torch.repeat_interleave(torch.arange(n_reads, device=dev), L)
+    pos = torch.arange(total, device=dev) - off[rid]
+    tot = float(sum(mix))
+    p_sub, p_ins, p_del = (err * m / tot for m in mix)
+    u = torch.rand(total, generator=g, device=dev)
+    is_ins = u < p_ins
+    is_del = (u >= p_ins) & (u < p_ins + p_del)
+    is_sub = (u >= p_ins + p_del) & (u < err)
+    step = torch.ones(total, dtype=torch.int64, device=dev)
+    step[is_ins] = 0
+    step[is_del] = 2
+    # one planted SV in sv_frac of the reads
+    has_sv = (torch.rand(n_reads, generator=g, device=dev) < sv_frac) & (L > 9000)
+    kind = torch.randint(0, 4, (n_reads,), generator=g, device=dev)           # 0 ins, 1 del, 2 inv, 3 dup
+    p = (2000 + torch.rand(n_reads, generator=g, device=dev) * (L - 7000).clamp_min(1)).long()
+    r01 = torch.rand(n_reads, generator=g, device=dev)
+    lo = torch.tensor([100, 100, 500, 300], device=dev)[kind]
+    hi = torch.tensor([2000, 3000, 3000, 2000], device=dev)[kind]
+    m = (lo + r01 * (hi - lo)).long()
+    sv_r, p_r, m_r, k_r = has_sv[rid], p[rid], m[rid], kind[rid]
+    in_sv = sv_r & (pos >= p_r) & (pos < p_r + m_r)
+    ins_reg = in_sv & (k_r == 0)
+    inv_reg = in_sv & (k_r == 2)
+    is_ins = is_ins | ins_reg
+    step[ins_reg] = 0
+    step[inv_reg] = 1
+    at_p = sv_r & (pos == p_r)
+    step = torch.where(at_p & (k_r == 1), step + m_r, step)
+    step = torch.where(at_p & (k_r == 3), step - m_r, step)
+    step[pos == 0] = 0
+    cs = torch.cumsum(step, 0)
+    rel = cs - cs[off[:-1]][rid]
+    # template start: uniform over the genome, kept inside one contig
+    coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    coff_t = torch.tensor(coff, device=dev)
+    gpos = (torch.rand(n_reads, generator=g, device=dev, dtype=torch.float64) * float(coff[-1])).long()
+    ci = (torch.searchsorted(coff_t, gpos, right=True) - 1).clamp_(0, len(lens) - 1)
+    span = (L.double() * 1.35).long() + 8000
+    cstart, cend = coff_t[ci], coff_t[ci + 1]
+    start = torch.minimum(gpos, cend - span).clamp_min(0)
+    start = torch.maximum(start, cstart + 3000)
+    tpos = start[rid] + rel
+    t_at_p = tpos[(off[:-1] + p).clamp_max(total - 1)]
+    tpos = torch.where(inv_reg, 2 * t_at_p[rid] + m_r - 1 - tpos, tpos)
+    tpos = torch.minimum(torch.maximum(tpos, cstart[rid]), cend[rid] - 1)
+    b = genome[tpos]
+    b = torch.where(inv_reg, 3 - b, b)
+    rnd = torch.randint(0, 4, (total,), generator=g, device=dev, dtype=torch.uint8)
+    b = torch.where(is_sub & ~inv_reg, (b + 1 + rnd % 3) % 4, b)
+    b = torch.where(is_ins, rnd, b)
+    rev = torch.rand(n_reads, generator=g, device=dev) < 0.5
+    src = torch.where(rev[rid], off[rid] + (L[rid] - 1 - pos), off[rid] + pos)
+    out = b[src]
+    out = torch.where(rev[rid], 3 - out, out).to(torch.uint8).contiguous()
+    return out, off.cpu().numpy().astype(np.uint64)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.stop_flag, self.rows = gpu_index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference(contigs_host, bases, offs, n_sample, cores):
+    """The reference's own CPU path on a bounded sample: oracle/_ref (kind 'reference') if it travelled, else the
+    oracle port. Returns dict(value reads/s, index_build_s, kind, cores, sample)."""
+    from cpu_checkers import Oracle, RefImpl, have_ref
+    kind = "reference" if have_ref() else "port"
+    cls = RefImpl if have_ref() else Oracle
+    t0 = time.time()
+    chk = cls(contigs_host, threads=THREADS_SEM, preset=1)
+    t_index = time.time() - t0
+    n = min(n_sample, len(offs) - 1)
+    sb = bases[: int(offs[n])]
+    so = offs[: n + 1].copy()
+    t0 = time.time()
+    chk.map_batch(sb, so, map_threads=cores)
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "reads/s", "cores": cores, "kind": kind, "index_build_s": round(t_index, 2),
+            "index_threads": THREADS_SEM,
+            "sample": f"first {n} reads of the rank-0 batch ({int(so[-1])} bases) through apxMap with {cores} OpenMP threads; "
+                      f"genome features + DIndex built by the same code at -t {THREADS_SEM} in {t_index:.1f} s"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    import torch
+    lens = contig_lengths()
+    cores = os.cpu_count() or 1
+    config = {"workload": f"{GENOME_BASES / 1e9:.2f}-Gbase synthetic genome ({N_CONTIGS} contigs, planted repeats) + ONT-like reads "
+                          f"(lognormal mean 20 kb, 10% error, 20% planted SV), {args.batch_reads} reads per step per GPU",
+              "index": "DIndex (-i 1)", "features": "2-mer/48 (-f 2)", "threads_sem": THREADS_SEM, "preset": 1,
+              "batch_reads_per_gpu": args.batch_reads, "parallelism": f"reads sharded x{world}, index replicated",
+              "l2_policy": "inputs larger than L2 (batch bases + index >> 126 MB)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if not torch.cuda.is_available():
+            # no GPU needed for this arm, but the synthetic genome recipe is the GPU one; fall back to numpy
+            rng = np.random.default_rng(1234)
+            contigs = [rng.integers(0, 4, size=l, dtype=np.uint8) for l in lens]
+            from linear_b200 import datagen
+            rs = datagen.simulate_reads(77, contigs, args.cpu_sample, mean_len=20000, err=0.10, mix=(4, 3, 3), sv_frac=0.2, lognormal=True)
+            bases, offs = rs.bases, rs.offsets
+        else:
+            dev = torch.device("cuda", local_rank)
+            genome = gen_genome(torch, dev, lens)
+            bases_t, offs = gen_reads(torch, dev, genome, lens, max(args.cpu_sample, 64), seed=1000)
+            bases = bases_t.cpu().numpy()
+            gh = genome.cpu().numpy()
+            coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            contigs = [gh[coff[i]:coff[i + 1]] for i in range(len(lens))]
+            del genome, bases_t
+            torch.cuda.empty_cache()
+        from cpu_checkers import Oracle, RefImpl, have_ref
+        cls = RefImpl if have_ref() else Oracle
+        t0 = time.time()
+        chk = cls(contigs, threads=THREADS_SEM, preset=1)
+        t_index = time.time() - t0
+        n = min(args.cpu_sample, len(offs) - 1)
+        per = max(n // max(args.steps + args.warmup, 1), 16)
+        times = []
+        for s in range(args.warmup + args.steps):
+            a = (s * per) % max(n - per, 1)
+            so = (offs[a:a + per + 1] - offs[a]).astype(np.uint64)
+            sb = bases[int(offs[a]):int(offs[a + per])]
+            t0 = time.time()
+            chk.map_batch(sb, so, map_threads=cores)
+            if s >= args.warmup:
+                times.append(time.time() - t0)
+        tot = sum(times)
+        val = per * len(times) / tot
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": dict(config, reads_per_step=per),
+                "index_build_s": round(t_index, 2),
+                "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": "reference" if have_ref() else "port",
+                                 "sample": f"{per} reads per step through the reference's apxMap with {cores} OpenMP threads "
+                                           f"(index + features built at -t {THREADS_SEM} in {t_index:.1f} s)"},
+                "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------------- B200 arm
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import linear_b200 as lb
+    lb.load_library()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    genome = gen_genome(torch, dev, lens)
+    ctx = lb.Context(local_rank)
+    lens64 = [int(x) for x in lens]
+    # ---- index build, inputs resident in HBM (genome features + DIndex = createFeatures + createIndexDynamic)
+    ctx.set_profiling(True)
+    barrier()
+    t0 = time.time()
+    gen = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=lens64)
+    feats = lb.create_features(ctx, gen, 2, THREADS_SEM)
+    index = lb.create_index(ctx, gen, 1, THREADS_SEM)
+    torch.cuda.synchronize()
+    t_index = max_over_ranks(time.time() - t0)
+    idx_kernels = ctx.kernel_times()
+    n_hs = index.n_hs
+    ctx.reset_kernel_times()
+    # ---- index build end to end from host memory (rank 0, N = 1 only): upload + features + index
+    t_index_e2e = None
+    contigs_host = None
+    if world == 1:
+        gh = torch.empty(genome.shape, dtype=torch.uint8, pin_memory=True)
+        gh.copy_(genome)
+        ghn = gh.numpy()
+        coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        contigs_host = [ghn[coff[i]:coff[i + 1]] for i in range(len(lens))]
+        index.close(); feats.close(); gen.close()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        gen = lb.Genome(ctx, contigs_host)
+        feats = lb.create_features(ctx, gen, 2, THREADS_SEM)
+        index = lb.create_index(ctx, gen, 1, THREADS_SEM)
+        torch.cuda.synchronize()
+        t_index_e2e = time.time() - t0
+        ctx.reset_kernel_times()
+    # ---- reads of this rank
+    bases_t, offs = gen_reads(torch, dev, genome, lens, args.batch_reads, seed=1000 + rank)
+    del genome
+    torch.cuda.empty_cache()
+    n_reads = len(offs) - 1
+    total_bases = int(offs[-1])
+    cap = total_bases // 16 + 64 * n_reads + 1024
+    cords_dev = torch.empty(cap, dtype=torch.int64, device=dev)
+    coff_dev = torch.empty(n_reads + 4200, dtype=torch.int64, device=dev)
+    import ctypes as C
+    from linear_b200.api import Params, u64p
+    prm = Params(preset=1, feature_type=2)
+    offs_c = offs.ctypes.data_as(u64p)
+    ntot = C.c_uint64()
+
+    def step_device():
+        ctx.check(ctx.lib.lnr_apxmap_batch_device(ctx.h, index.h, feats.h, C.byref(prm), n_reads, C.c_void_p(bases_t.data_ptr()), offs_c,
+                                                  C.c_void_p(cords_dev.data_ptr()), C.c_void_p(coff_dev.data_ptr()), cap, C.byref(ntot)))
+
+    bases_pin = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)
+    bases_pin.copy_(bases_t)
+    bases_np = bases_pin.numpy()
+    cords_pin = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+    cords_np = cords_pin.numpy().view(np.uint64)
+    coff_np = np.zeros(n_reads + 1, dtype=np.uint64)
+
+    def step_host():
+        return lb.apx_map_batch(ctx, index, feats, bases_np, offs, preset=1, cords_out=cords_np, cords_off_out=coff_np)
+
+    # ---- timed region: device-resident inputs
+    ctx.set_profiling(False)
+    for _ in range(args.warmup):
+        step_device()
+    ctx.set_profiling(True)
+    ctx.reset_kernel_times()
+    launches0 = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    for _ in range(args.steps):
+        step_device()
+    torch.cuda.synchronize()
+    barrier()
+    dt = max_over_ranks(time.time() - t0)
+    sampler.stop_flag = True
+    kt = ctx.kernel_times()
+    counters = ctx.counters()
+    n_cords = int(ntot.value)
+    value = world * n_reads * args.steps / dt
+    # ---- end to end through the host-buffer call
+    ctx.set_profiling(False)
+    step_host()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        c_host, _ = step_host()
+    torch.cuda.synchronize()
+    barrier()
+    dt_e2e = max_over_ranks(time.time() - t0)
+    e2e_value = world * n_reads * args.steps / dt_e2e
+    d2h = int(len(c_host) * 8 + (n_reads + 1) * 8)
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (SURVEY 8d per-unit bytes x units of one launch)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    S, H, A, Hits, W, Cc = (counters[k] for k in ("S_seeds", "H_records_scanned", "A_raw_anchors", "Hits", "W_windows", "C_cords"))
+    nf_bytes = 2 * 12 * (total_bases // 16)
+    alg = {  # algorithmic bytes per launch of each kernel (one launch = one batch)
+        "k_feat_reads": total_bases + nf_bytes,
+        "k_seed_count": total_bases + 8 * S + 8 * H,
+        "k_seed_fill": 8 * S + 8 * H + 8 * A,
+        "k_map_primary": 8 * A + 48 * Hits + 144 * W + 16 * Cc,
+    }
+    per_kernel = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1]} for k, v in kt.items()}
+    step_ms_kernels = sum(v[0] for v in kt.values()) / args.steps
+    dom = max(kt.items(), key=lambda kv: kv[1][0])[0] if kt else None
+    roof = None
+    if dom:
+        ms = kt[dom][0] / max(kt[dom][1], 1)
+        ab = alg.get(dom, 0)
+        ach = ab / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ab, "ms_per_launch": ms,
+                "share_of_step": (kt[dom][0] / args.steps) / step_ms_kernels if step_ms_kernels else None,
+                "whole_step": {"algorithmic_bytes": sum(alg.values()),
+                               "achieved_GBps": sum(alg.values()) / (dt / args.steps) / 1e9}}
+    idx_alg = GENOME_BASES + 8 * n_hs + 4 * ((1 << 26) + 1) + GENOME_BASES + 12 * (GENOME_BASES // 16)
+    index_info = {"seconds": round(t_index, 4), "seconds_e2e_from_host": None if t_index_e2e is None else round(t_index_e2e, 4),
+                  "n_hs": n_hs, "algorithmic_bytes": idx_alg, "achieved_GBps": idx_alg / t_index / 1e9,
+                  "frac_of_hbm_peak": idx_alg / t_index / 1e9 / peak,
+                  "kernels_ms": {k: round(v[0], 3) for k, v in idx_kernels.items()}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and contigs_host is not None:
+        try:
+            cpu = cpu_reference(contigs_host, bases_np, offs, args.cpu_sample, cores)
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
+    launches = sum(v[1] for v in kt.values())
+    line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": total_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000 * dt_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "index_build": index_info,
+            "clocks": sampler.summary(), "kernels": per_kernel, "counters": counters, "cords_per_step": n_cords,
+            "bases_per_step": total_bases}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
