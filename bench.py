@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 16384)))
+    ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 32768)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("LNR_BENCH_CPU_SAMPLE", 2048)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -365,6 +365,7 @@ def main():
     sampler.stop_flag = True
     kt = ctx.kernel_times()
     counters = ctx.counters()
+    stage_cycles = ctx.stage_cycles()
     n_cords = int(ntot.value)
     value = world * n_reads * args.steps / dt
     # ---- end to end through the host-buffer call
@@ -432,7 +433,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": total_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * dt_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "index_build": index_info,
-            "clocks": sampler.summary(), "kernels": per_kernel, "counters": counters, "cords_per_step": n_cords,
+            "clocks": sampler.summary(), "kernels": per_kernel, "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
             "bases_per_step": total_bases}
     print(json.dumps(line))
     if world > 1:

@@ -103,6 +103,10 @@ int lnr_apxmap_batch_device(lnr_ctx *, const lnr_index *, const lnr_feats * f2, 
 /* algorithmic-byte counters of the last batch: S seeds, H bucket records scanned, A raw anchors,
  * Hits, W window candidates evaluated, C cords */
 int lnr_last_batch_counters(lnr_ctx *, uint64_t counters[8]);
+/* profiling aid: SM cycles spent per stage of the warp-per-read pipeline in the last batch (lane 0, summed over warps):
+ * 0 binning, 1 ascending sort, 2 run filter, 3 x sort, 4 chaining DP, 5 traceback, 6 hit blocks, 7 hit window filter,
+ * 8 window extension, 9 clean/gaps, 10 cord block chaining, 11 reads needing the sequential tie-order sort, 12 reads */
+int lnr_last_batch_stage_cycles(lnr_ctx *, uint64_t cycles[16]);
 
 /* read features of one read (both strands), for the host gap stage and for parity tests:
  * createFeatures(begin(read), end(read), f1[s]) pmpfinder.cpp:724 -> createFeatures2_48 (serial) :556 */

@@ -30,7 +30,7 @@ EXPORTS = [
     "lnr_ctx_reset_kernel_times", "lnr_genome_upload", "lnr_genome_from_device", "lnr_genome_destroy",
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
     "lnr_index_build", "lnr_index_export_dindex", "lnr_index_destroy", "lnr_apxmap_batch",
-    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_read_features",
+    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_stage_cycles", "lnr_read_features",
 ]
 
 
@@ -87,11 +87,14 @@ def load_library() -> C.CDLL:
                                      C.POINTER(DebugOut)]
     lib.lnr_apxmap_batch_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, vp, C.c_uint64, u64p]
     lib.lnr_last_batch_counters.argtypes = [vp, u64p]
+    lib.lnr_last_batch_stage_cycles.argtypes = [vp, u64p]
     lib.lnr_read_features.argtypes = [vp, u8p, C.c_uint64, C.c_int, vp, vp, C.c_uint64, u64p]
     _lib = lib
     return lib
 
 
+STAGE_NAMES = ("binning", "sort_asc", "run_filter", "sort_x", "chain_dp", "traceback", "hit_blocks", "hit_window_filter",
+               "window_extension", "clean_gaps", "cord_block_chaining", "n_tie_fallback", "n_reads", "max_read_cycles", "sum_read_cycles", "r15")
 COUNTER_NAMES = ("S_seeds", "H_records_scanned", "A_raw_anchors", "Hits", "W_windows", "C_cords", "bases", "remap_tasks")
 
 
@@ -127,6 +130,11 @@ class Context:
         c = (C.c_uint64 * 8)()
         self.check(self.lib.lnr_last_batch_counters(self.h, c))
         return dict(zip(COUNTER_NAMES, [int(v) for v in c]))
+
+    def stage_cycles(self):
+        c = (C.c_uint64 * 16)()
+        self.check(self.lib.lnr_last_batch_stage_cycles(self.h, c))
+        return dict(zip(STAGE_NAMES, [int(v) for v in c]))
 
     def close(self):
         if getattr(self, "h", None):

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -73,11 +74,12 @@ struct lnr_ctx
         cords, cords_base, ncords, slots, bins, arena, tasks2, misc, out_cords, out_off, dbg_hits, dbg_hoff, dbg_nhits,
         dbg_c1, dbg_nc1, read_meta;
     uint64_t counters[8] = {0};
+    uint64_t stage_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list;
+    DevBuf remap_list, order;
     int map_warps_per_cta = 4;
-    int map_ctas_per_sm = 4;
+    int map_ctas_per_sm = 6;
     size_t arena_bytes_per_warp = 2u << 20;
 };
 
@@ -626,6 +628,7 @@ struct MapArgs
     SeedTask * tasks2; u32 tasks2_cap; u32 * n_tasks2; // re-map tasks produced by the primary pass
     u32 * bins; u8 * arena; u64 arena_per_warp;
     u32 * queue;                                       // atomic work counter
+    const u32 * order;                                 // reads sorted by length, longest first (tail latency)
     float stop_ratio;
     unsigned long long * counters;
     // optional debug
@@ -686,7 +689,8 @@ __global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
     u32 * bins = a.bins + (u64)gw * kNumBins;
-    PipeCounters cnt = {0, 0};
+    PipeCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
     u64 c_cords = 0;
     while (true)
     {
@@ -694,8 +698,10 @@ __global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
         if (w.lane == 0) r = atomicAdd(a.queue, 1u);
         r = __shfl_sync(0xffffffffu, r, 0);
         if (r >= a.n_reads) break;
+        r = a.order[r];
         u64 L = a.read_off[r + 1] - a.read_off[r];
         ReadSlot slot = {0, 0, 0, 0};
+        long long t_read = LNR_CLOCK();
         if (L > (u64)kMinReadLen)                        // mapper.cpp:440
         {
             PipeIn in;
@@ -720,6 +726,8 @@ __global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
             int remap = 0, n_sep = 0, n_gaps = 0;
             Blk * sep = 0;
             u32 task0 = 0;
+            long long tl = LNR_CLOCK();
+            cnt.t[12]++;
             if (!rc)
             {
                 arena_reset(ar);
@@ -757,19 +765,32 @@ __global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
                     if (remap < 0) rc = 1;
                 }
             }
+            LNR_LAP(cnt, 9, tl);
             if (!rc && remap == 0) rc = finish_read(w, ar, L, cords, nc, cap, sep, n_sep, false);
+            LNR_LAP(cnt, 10, tl);
             slot.n_cords = rc ? 0 : (u32)nc;
             slot.status = rc ? 2u : (remap == 1 ? 1u : 0u);
             slot.task0 = task0; slot.n_tasks = remap == 1 ? (u32)n_gaps : 0;
             if (!rc && remap == 0) c_cords += (u64)nc;
         }
         if (w.lane == 0) a.slots[r] = slot;
+        {
+            u64 dt = (u64)(LNR_CLOCK() - t_read);
+            cnt.t[14] += dt;
+            if (dt > cnt.t[13]) cnt.t[13] = dt;
+        }
     }
     if (w.lane == 0)
     {
         if (cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)cnt.hits);
         if (cnt.windows) atomicAdd(&a.counters[4], (unsigned long long)cnt.windows);
         if (c_cords) atomicAdd(&a.counters[5], (unsigned long long)c_cords);
+        for (int i = 0; i < 16; i++)
+            if (cnt.t[i])
+            {
+                if (i == 13) atomicMax(&a.counters[24 + i], (unsigned long long)cnt.t[i]);
+                else atomicAdd(&a.counters[24 + i], (unsigned long long)cnt.t[i]);
+            }
     }
 }
 
@@ -782,7 +803,8 @@ __global__ void __launch_bounds__(128) k_map_remap(MapArgs a, const u32 * __rest
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
     u32 * bins = a.bins + (u64)gw * kNumBins;
-    PipeCounters cnt = {0, 0};
+    PipeCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
     u64 c_cords = 0;
     while (true)
     {
@@ -820,6 +842,7 @@ __global__ void __launch_bounds__(128) k_map_remap(MapArgs a, const u32 * __rest
         if (cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)cnt.hits);
         if (cnt.windows) atomicAdd(&a.counters[4], (unsigned long long)cnt.windows);
         if (c_cords) atomicAdd(&a.counters[5], (unsigned long long)c_cords);
+        for (int i = 0; i < 16; i++) if (cnt.t[i]) atomicAdd(&a.counters[24 + i], (unsigned long long)cnt.t[i]);
     }
 }
 
@@ -880,6 +903,8 @@ int lnr_ctx_create(int device, lnr_ctx ** out)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->n_sm = prop.multiProcessorCount;
+    if (const char * e = getenv("LNR_MAP_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->map_ctas_per_sm = v; }
+    if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LNR_E_CUDA; }
     *out = ctx;
     return LNR_OK;
@@ -894,7 +919,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order})
         b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1169,7 +1194,7 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     CK(ctx->sample_info.reserve((size_t)(n_samples + 1) * sizeof(u64)));
     CK(ctx->sample_cnt.reserve((size_t)(n_samples + STILE + 1) * sizeof(u32)));
     CK(aoff_buf.reserve((size_t)(n_samples + STILE + 1) * sizeof(u64)));
-    CK(ctx->misc.reserve(256));
+    CK(ctx->misc.reserve(512));
     u64 * d_total = ctx->misc.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
     {
@@ -1214,7 +1239,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     // ---- host-side layout from the read lengths
     std::vector<SeedTask> tasks(n_reads);
     std::vector<u64> foff(n_reads + 1), cbase(n_reads + 1), hoff(n_reads + 1);
-    std::vector<u32> ftile(n_reads + 1);
+    std::vector<u32> ftile(n_reads + 1), order(n_reads);
     u64 n_samples = 0, nf_tot = 0, c_tot = 0;
     u32 n_ftiles = 0;
     for (uint32_t r = 0; r < n_reads; r++)
@@ -1236,6 +1261,8 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         c_tot += L > (u64)kMinReadLen ? 16 + L / 4 : 0;
     }
     foff[n_reads] = nf_tot; ftile[n_reads] = n_ftiles; cbase[n_reads] = c_tot;
+    for (uint32_t r = 0; r < n_reads; r++) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](u32 x, u32 y) { return h_read_off[x + 1] - h_read_off[x] > h_read_off[y + 1] - h_read_off[y]; });
     const u64 total_bases = h_read_off[n_reads];
     // ---- uploads
     CK(ctx->read_off.reserve((n_reads + 1) * sizeof(u64)));
@@ -1243,18 +1270,20 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(ctx->foff.reserve((n_reads + 1) * sizeof(u64)));
     CK(ctx->ftile.reserve((n_reads + 1) * sizeof(u32)));
     CK(ctx->cords_base.reserve((n_reads + 1) * sizeof(u64)));
+    CK(ctx->order.reserve((size_t)n_reads * sizeof(u32)));
     CK(ctx->feats.reserve((size_t)(nf_tot + 8) * sizeof(F96)));
     CK(ctx->cords.reserve((size_t)(c_tot + 8) * sizeof(u64)));
     CK(ctx->slots.reserve((size_t)n_reads * sizeof(ReadSlot)));
     CK(ctx->ncords.reserve((size_t)(n_reads + STILE + 1) * sizeof(u32)));
     CK(ctx->out_off.reserve((size_t)(n_reads + STILE + 1) * sizeof(u64)));
-    CK(ctx->misc.reserve(256));
+    CK(ctx->misc.reserve(512));
     CK(cudaMemcpyAsync(ctx->read_off.p, h_read_off, (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), n_reads * sizeof(SeedTask), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->foff.p, foff.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->ftile.p, ftile.data(), (n_reads + 1) * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->cords_base.p, cbase.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+    CK(cudaMemsetAsync(ctx->misc.p, 0, 512, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->order.p, order.data(), (size_t)n_reads * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     const u64 * d_read_off = ctx->read_off.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
     u32 * d_queue = (u32 *)(ctx->misc.as<u64>() + 20);
@@ -1335,6 +1364,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     a.tasks2 = ctx->tasks2.as<SeedTask>(); a.tasks2_cap = tasks2_cap; a.n_tasks2 = d_ntasks2;
     a.bins = ctx->bins.as<u32>(); a.arena = ctx->arena.as<u8>(); a.arena_per_warp = ctx->arena_bytes_per_warp;
     a.queue = d_queue;
+    a.order = ctx->order.as<u32>();
     a.stop_ratio = stop_ratio;
     a.counters = d_counters;
     if (dbg && dbg->hits_off) { a.dbg_hits = ctx->dbg_hits.as<u64>(); a.dbg_hoff = ctx->dbg_hoff.as<u64>(); a.dbg_nhits = ctx->dbg_nhits.as<u32>(); }
@@ -1394,7 +1424,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
                                                                                        ctx->ncords.as<u32>(), d_off, n_reads, d_out, out_cap);
     }
     CK(cudaGetLastError());
-    u64 h_misc[32];
+    u64 h_misc[64];
     CK(cudaMemcpyAsync(h_misc, ctx->misc.p, sizeof h_misc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     u64 total_cords = h_misc[0];
@@ -1407,6 +1437,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     ctx->counters[5] = total_cords;               // C
     ctx->counters[6] = total_bases;
     ctx->counters[7] = n_tasks2;
+    for (int i = 0; i < 16; i++) ctx->stage_cycles[i] = h_misc[8 + 24 + i];
     if (n_cords_total) *n_cords_total = total_cords;
     if (dbg && dbg->hits_off)
     {
@@ -1480,6 +1511,13 @@ int lnr_last_batch_counters(lnr_ctx * ctx, uint64_t counters[8])
 {
     if (!ctx || !counters) return LNR_E_ARG;
     for (int i = 0; i < 8; i++) counters[i] = ctx->counters[i];
+    return LNR_OK;
+}
+
+int lnr_last_batch_stage_cycles(lnr_ctx * ctx, uint64_t cycles[16])
+{
+    if (!ctx || !cycles) return LNR_E_ARG;
+    for (int i = 0; i < 16; i++) cycles[i] = ctx->stage_cycles[i];
     return LNR_OK;
 }
 

@@ -33,7 +33,17 @@ struct PipeIn
     float stop_ratio;           // ChainAnchorsHitsParms::thd_stop_chain_len_ratio (0.7 or 0, mapper.cpp:184)
 };
 
-struct PipeCounters { u64 hits, windows; };
+// per-warp counters; t[] = clock64 cycles spent per pipeline stage on lane 0 (profiling aid, see kStageNames)
+struct PipeCounters { u64 hits, windows; u64 t[16]; };
+#ifdef __CUDA_ARCH__
+#define LNR_CLOCK() clock64()
+#else
+#define LNR_CLOCK() 0LL
+#endif
+#define LNR_LAP(cnt, id, t0) do { long long t1_ = LNR_CLOCK(); (cnt).t[id] += (u64)(t1_ - (t0)); (t0) = t1_; } while (0)
+// 0 binning, 1 sort ascending, 2 run filter, 3 sort by x (+ tie fallback), 4 chaining DP, 5 traceback, 6 hit blocks,
+// 7 hit window filter, 8 path / window extension, 9 mid (clean, gaps), 10 finish (cord block chaining),
+// 11 reads that needed the sequential tie-order sort, 12 reads
 
 static const int kNumBins = (1 << 30) / 30000 + 2;   // binningFilter bins over a 30-bit x (pmpfinder.cpp:1984)
 
@@ -653,118 +663,175 @@ LNR_HD int filter_blocks_hits(const Blk * el, const int * chain_off, int n_chain
 }
 
 // ----------------------------------------------------------------------------------------------------
-// window extension (pmpfinder.cpp:883-1176)
+// window extension (pmpfinder.cpp:883-1176). Warp-uniform: every lane follows the same control flow and
+// holds the same scalars; the 3 candidate windows x 2 scripts x 3 ints of one step are spread over 18
+// lanes, cords are written by lane 0 and the most recent cord is kept in a register (`last`).
 // ----------------------------------------------------------------------------------------------------
-LNR_HD u64 previous_window(const PipeIn & in, u64 cord, PipeCounters & cnt)   // previousWindow :883
+// distances of the read window at feature row y against genome windows x0, x0+1, x0+2 (__windowDist :655;
+// the reference does not bounds-check, the guard only protects the device on out-of-spec data)
+LNR_PIPE_INL void wdist3(const Warp & w, const PipeIn & in, u32 strand, u32 id, u64 y, u64 x0, u32 d[3], PipeCounters & cnt)
+{
+    cnt.windows += 3;
+    const u32 nf2 = in.nf2[id];
+    const bool yok = y + 3 < in.nf1;
+    const F96 * fa = in.f1[strand] + y;
+    const F96 * fb = in.f2[id] + x0;
+    int s0 = 0, s1 = 0, s2 = 0;
+    for (int t = w.lane; t < 18; t += w.nl)
+    {
+        int c = t / 6, part = t - 6 * c, i = part >= 3 ? 3 : 0, k = part - i;
+        if (yok && x0 + c + 3 < nf2)
+        {
+            int v = script_dist(fa[i].v[k], fb[c + i].v[k]);
+            if (c == 0) s0 += v; else if (c == 1) s1 += v; else s2 += v;
+        }
+    }
+    s0 = wsum(w, s0); s1 = wsum(w, s1); s2 = wsum(w, s2);
+    d[0] = (yok && x0 + 3 < nf2) ? (u32)s0 : 1000u;
+    d[1] = (yok && x0 + 4 < nf2) ? (u32)s1 : 1000u;
+    d[2] = (yok && x0 + 5 < nf2) ? (u32)s2 : 1000u;
+}
+LNR_PIPE_INL u64 previous_window(const Warp & w, const PipeIn & in, u64 cord, PipeCounters & cnt)   // previousWindow :883
 {
     u64 id = cord_id(cord), strand = cord_strand(cord), x_suf = cord_x(cord) >> 4, y_suf = cord_y(cord) >> 4;
     if (y_suf < (u64)kMed || x_suf < (u64)kSup) return 0;
-    u64 y = y_suf - kMed, x_min = 0;
-    u32 mn = ~0u;
-    for (u64 x = x_suf - kSup; x < x_suf - kInf; x++)
-    {
-        u32 t = wdist(in, (u32)strand, (u32)id, y, x, cnt);
-        if (t < mn) { mn = t; x_min = x; }
-    }
+    u64 y = y_suf - kMed, x0 = x_suf - kSup;       // candidates x_suf-6 .. x_suf-4
+    u32 d[3];
+    wdist3(w, in, (u32)strand, (u32)id, y, x0, d, cnt);
+    u32 mn = d[0]; u64 x_min = x0;                  // first strict minimum in ascending x
+    if (d[1] < mn) { mn = d[1]; x_min = x0 + 1; }
+    if (d[2] < mn) { mn = d[2]; x_min = x0 + 2; }
     if (mn > (u32)kWinThr) return 0;
     if (x_suf - x_min > (u64)kMed)
         return (((id << 30) + ((x_suf - kMed) << 4)) << 20) + ((x_suf - x_min - kMed + y) << 4) + (strand << 61);
     return (((id << 30) + (x_min << 4)) << 20) + (y << 4) + (strand << 61);
 }
-LNR_HD u64 next_window(const PipeIn & in, u64 cord, PipeCounters & cnt)   // nextWindow :1079
+LNR_PIPE_INL u64 next_window(const Warp & w, const PipeIn & in, u64 cord, PipeCounters & cnt)   // nextWindow :1079
 {
     u64 id = cord_id(cord), strand = cord_strand(cord), x_pre = cord_x(cord) >> 4, y_pre = cord_y(cord) >> 4;
     if (y_pre + 2 * kSup > (u64)in.nf1 || x_pre + 2 * kSup > (u64)in.nf2[id]) return 0;
-    u64 y = y_pre + kMed, x_min = 0;
-    u32 mn = ~0u;
-    for (u64 x = x_pre + kInf; x < x_pre + kSup; x++)
-    {
-        u32 t = wdist(in, (u32)strand, (u32)id, y, x, cnt);
-        if (t < mn) { mn = t; x_min = x; }
-    }
+    u64 y = y_pre + kMed, x0 = x_pre + kInf;        // candidates x_pre+3 .. x_pre+5
+    u32 d[3];
+    wdist3(w, in, (u32)strand, (u32)id, y, x0, d, cnt);
+    u32 mn = d[0]; u64 x_min = x0;
+    if (d[1] < mn) { mn = d[1]; x_min = x0 + 1; }
+    if (d[2] < mn) { mn = d[2]; x_min = x0 + 2; }
     if (mn > (u32)kWinThr) return 0;
     if (x_min - x_pre > (u64)kMed)
         return (((id << 30) + ((x_pre + kMed) << 4)) << 20) + ((x_pre + kMed - x_min + y) << 4) + (strand << 61);
     return (((id << 30) + (x_min << 4)) << 20) + (y << 4) + (strand << 61);
 }
-// extendWindow :1152; returns false when the cord buffer is full
-LNR_HD bool extend_window(const PipeIn & in, u64 * cords, int & n, int cap, u64 ystr, u64 yend, PipeCounters & cnt)
+// extendWindow :1152; returns false when the cord buffer is full. `last` == cords[n-1] on entry and exit.
+LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, int & n, int cap, u64 & last, u64 ystr, u64 yend,
+                                PipeCounters & cnt)
 {
     int p_str = n - 1;
+    const u64 first = last;
     u64 nc;
-    while ((nc = previous_window(in, cords[n - 1], cnt)) && cord_y(nc) >= ystr)
+    while ((nc = previous_window(w, in, last, cnt)) && cord_y(nc) >= ystr)
     {
         if (n >= cap) return false;
-        cords[n++] = nc;
+        if (w.lane == 0) cords[n] = nc;
+        n++;
+        last = nc;
     }
-    int p_end = n;
-    for (int k = p_str; k < (p_str + p_end) / 2; k++)
+    if (n - p_str > 1)
     {
-        u64 t = cords[k]; cords[k] = cords[n - k + p_str - 1]; cords[n - k + p_str - 1] = t;
+        wsync(w);
+        for (int k = p_str + w.lane; k < (p_str + n) / 2; k += w.nl)
+        {
+            u64 t = cords[k]; cords[k] = cords[n - k + p_str - 1]; cords[n - k + p_str - 1] = t;
+        }
+        wsync(w);
     }
-    while ((nc = next_window(in, cords[n - 1], cnt)) && cord_y(nc) + kWin < yend)
+    last = first;                                   // after the reversal the seeding cord is last again
+    while ((nc = next_window(w, in, last, cnt)) && cord_y(nc) + kWin < yend)
     {
         if (n >= cap) return false;
-        cords[n++] = nc;
+        if (w.lane == 0) cords[n] = nc;
+        n++;
+        last = nc;
     }
     return true;
 }
 
-// path_dst_2 (pmpfinder.cpp:1309), iterators restated as indices (hitBegin = 1). Returns false on overflow.
-LNR_HD bool path_dst_2(const PipeIn & in, const u64 * H, int nh, u64 * cords, int & nc, int cap, u64 read_str, u64 read_end,
-                       PipeCounters & cnt)
+// path_dst_2 (pmpfinder.cpp:1309), iterators restated as indices (hitBegin = 1). Warp-uniform.
+// Returns false on overflow.
+LNR_PIPE bool path_dst_2(const Warp & w, const PipeIn & in, const u64 * H, int nh, u64 * cords, int & nc, int cap, u64 read_str,
+                         u64 read_end, PipeCounters & cnt)
 {
     const u64 L = in.L, cs = kWin;
     int hb = 1, he = nh;
     if (hb + 1 >= he) return true;
-    if (nc == 0) { if (cap < 1) return false; cords[nc++] = kFlagEnd; }   // initCords
+    u64 last;
+    if (nc == 0)                                    // initCords
+    {
+        if (cap < 1) return false;
+        if (w.lane == 0) cords[0] = kFlagEnd;
+        nc = 1;
+        last = kFlagEnd;
+    }
+    else last = cords[nc - 1];
     u64 ready_str, ready_end, cordy_str = 0, cordy_end = 0;
     bool f_sp_l = false, f_sp_r = false, f_block_end = false, f_append = false;
     int nx = hb + 1, first = hb;
     for (int it = hb; it < he; it = nx++)
     {
-        ready_str = cord_strand(H[it]) ? L - read_end : read_str;
-        ready_end = cord_strand(H[it]) ? L - read_str + 1 : read_end;
-        bool it_first = is_end(H[it - 1]);
-        i64 da_l = it_first ? 0 : iabs64((i64)(cord_x(H[it]) - cord_x(H[it - 1]) - cord_y(H[it]) + cord_y(H[it - 1])));
-        f_sp_l = (da_l > 80) || cord_strand(H[it] ^ H[it - 1]);
+        const u64 Hit = H[it], Hprev = H[it - 1];
+        ready_str = cord_strand(Hit) ? L - read_end : read_str;
+        ready_end = cord_strand(Hit) ? L - read_str + 1 : read_end;
+        bool it_first = is_end(Hprev);
+        i64 da_l = it_first ? 0 : iabs64((i64)(cord_x(Hit) - cord_x(Hprev) - cord_y(Hit) + cord_y(Hprev)));
+        f_sp_l = (da_l > 80) || cord_strand(Hit ^ Hprev);
+        u64 Hn1 = Hit;                              // H[nx - 1]
         while (1)
         {
-            if (nx >= he || is_end(H[nx - 1])) { f_block_end = true; first = nx; break; }
-            i64 da_r = iabs64((i64)(cord_x(H[nx]) - cord_x(H[nx - 1]) - cord_y(H[nx]) + cord_y(H[nx - 1])));
-            f_sp_r = (da_r > 80) || cord_strand(H[nx] ^ H[nx - 1]);
-            if ((cord_y(H[it]) + cs < cord_y(H[nx]) && cord_x(H[it]) + cs < cord_x(H[nx])) || f_sp_r) break;
+            if (nx >= he || is_end(Hn1)) { f_block_end = true; first = nx; break; }
+            u64 Hn = H[nx];
+            i64 da_r = iabs64((i64)(cord_x(Hn) - cord_x(Hn1) - cord_y(Hn) + cord_y(Hn1)));
+            f_sp_r = (da_r > 80) || cord_strand(Hn ^ Hn1);
+            if ((cord_y(Hit) + cs < cord_y(Hn) && cord_x(Hit) + cs < cord_x(Hn)) || f_sp_r) break;
             nx++;
+            Hn1 = Hn;
         }
         if (!f_sp_r && !f_block_end)
         {
             // sic: the whole hit value, not its y, when f_sp_l (pmpfinder.cpp:1360)
-            cordy_str = f_sp_l ? H[it] : (it_first ? ready_str : cord_y(cords[nc - 1]));
+            cordy_str = f_sp_l ? Hit : (it_first ? ready_str : cord_y(last));
             cordy_end = cord_y(H[nx]);
             if (nc >= cap) return false;
-            cords[nc++] = H[it] & ~kFlagEnd;
+            last = Hit & ~kFlagEnd;
+            if (w.lane == 0) cords[nc] = last;
+            nc++;
             f_append = true;
         }
         else
         {
-            if (!f_sp_l && cord_y(H[nx - 1]) >= cs && cord_x(H[nx - 1]) >= cs)
+            if (!f_sp_l && cord_y(Hn1) >= cs && cord_x(Hn1) >= cs)
             {
-                u64 ncord = shift_cord(H[nx - 1], -(i64)cs, -(i64)cs);
+                u64 ncord = shift_cord(Hn1, -(i64)cs, -(i64)cs);
                 cordy_str = it_first ? read_str : cord_y(ncord);
-                cordy_end = cord_y(H[nx - 1]);
+                cordy_end = cord_y(Hn1);
                 if (nc >= cap) return false;
-                cords[nc++] = ncord & ~kFlagEnd;
+                last = ncord & ~kFlagEnd;
+                if (w.lane == 0) cords[nc] = last;
+                nc++;
                 f_append = true;
             }
             else f_append = false;
         }
-        if (is_end(H[it]) || f_block_end) { f_block_end = true; cordy_end = ready_end; }
+        if (is_end(Hit) || f_block_end) { f_block_end = true; cordy_end = ready_end; }
         if (f_append)
-            if (!extend_window(in, cords, nc, cap, cordy_str, cordy_end, cnt)) return false;
-        if (f_block_end) cords[nc - 1] |= kFlagEnd;
+            if (!extend_window(w, in, cords, nc, cap, last, cordy_str, cordy_end, cnt)) return false;
+        if (f_block_end)
+        {
+            last |= kFlagEnd;
+            if (w.lane == 0) cords[nc - 1] = last;
+        }
         nx = f_block_end ? first : nx;
         f_sp_l = f_sp_r = f_block_end = f_append = false;
     }
+    wsync(w);
     return true;
 }
 
@@ -943,6 +1010,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
                        u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt)
 {
     arena_reset(ar);
+    long long tl = LNR_CLOCK();
     if (dbg_nhits && w.lane == 0) *dbg_nhits = 1;
     if (dbg_hits && w.lane == 0 && dbg_hits_cap > 0) dbg_hits[0] = kFlagEnd;
     if (w.lane == 0) A[0] = 0;               // Anchors::init(1) base.cpp:272
@@ -950,6 +1018,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     // ---- filterAnchors (:2159): binningFilter + filterAnchors1
     int m;
     u64 * S = binning_filter(w, bins, A, B, n, m);
+    LNR_LAP(cnt, 0, tl);
     if (m <= 1) return 0;                    // no chains, hits stay empty (path_dst :1457)
     u64 * O = (S == A) ? B : A;              // the other buffer
     if (w.lane == 0) S[0] = 0;               // filterAnchorsList :2030 overwrites whatever is first
@@ -958,6 +1027,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     Blk * ranges = arena_alloc<Blk>(ar, (u64)m / 2 + 2);
     if (ar.failed) return 1;
     u64 * sorted = radix_sort(w, hist256, S, O, C, m, 62, KeyAsc());
+    LNR_LAP(cnt, 1, tl);
     int nr = 0;
     if (w.lane == 0) nr = filter_anchor_runs(sorted, m, ranges);
     nr = wbcast(w, nr, 0);
@@ -973,6 +1043,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
         n2 += e - b;
     }
     wsync(w);
+    LNR_LAP(cnt, 2, tl);
     // ---- chainAnchorsHits (:2448): sort by AnchorX descending with std::sort's tie order
     u64 * hits = arena_alloc<u64>(ar, (u64)n2 + 2);
     u64 * hits2 = arena_alloc<u64>(ar, (u64)n2 + 2);
@@ -997,11 +1068,14 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
             if (w.lane == 0) gnu_sort(F, n2, [](const u64 & a, const u64 & b) { return anchor_x(a) > anchor_x(b); });
             wsync(w);
             X = F;
+            cnt.t[11]++;
         }
+        LNR_LAP(cnt, 3, tl);
         ChainRec * rec = arena_alloc<ChainRec>(ar, (u64)n2);
         u64 * ch_el = arena_alloc<u64>(ar, (u64)n2);
         if (ar.failed) return 1;
         best_chains(w, X, rec, n2, score_type);
+        LNR_LAP(cnt, 4, tl);
         if (w.lane == 0)
         {
             int nch = traceback<u64>(X, rec, n2, ch_el, hits_score + 1, chain_off, 60, 1, 45, 50, in.stop_ratio);
@@ -1019,6 +1093,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     }
     n_hits = wbcast(w, n_hits, 0);
     wsync(w);
+    LNR_LAP(cnt, 5, tl);
     // ---- blocks of hits: gather_blocks_ (:1484) -> preFilterChains2 (:2366) -> chainBlocksHits
     Blk * sep = arena_alloc<Blk>(ar, (u64)n_hits + 1);
     Blk * sep_tmp = arena_alloc<Blk>(ar, (u64)n_hits + 1);
@@ -1055,6 +1130,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     n_hits = wbcast(w, n_hits, 0);
     H = (u64 *)wbcast64(w, (u64)H, 0);
     wsync(w);
+    LNR_LAP(cnt, 6, tl);
     if (n_hits < 2) return 0;                // path_dst :1457
     // ---- _filterHits (:1417): drop hits whose own window distance >= reject (50)
     for (int it = 1 + w.lane; it < n_hits; it += w.nl)
@@ -1066,7 +1142,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
         keep[it] = dist < (u32)kWinReject;
     }
     wsync(w);
-    int ok = 1;
+    LNR_LAP(cnt, 7, tl);
     if (w.lane == 0)
     {
         cnt.hits += (u64)(n_hits - 1);
@@ -1079,11 +1155,11 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
             if (is_end(h)) H[it - mv] |= kFlagEnd;
         }
         n_hits -= mv;
-        ok = path_dst_2(in, H, n_hits, cords, n_cords, cords_cap, read_str, read_end, cnt) ? 1 : 0;
     }
-    ok = wbcast(w, ok, 0);
-    n_cords = wbcast(w, n_cords, 0);
+    n_hits = wbcast(w, n_hits, 0);
     wsync(w);
+    int ok = path_dst_2(w, in, H, n_hits, cords, n_cords, cords_cap, read_str, read_end, cnt) ? 1 : 0;
+    LNR_LAP(cnt, 8, tl);
     return ok ? 0 : 1;
 }
 

@@ -1,0 +1,74 @@
+"""CPU, world_size 2 over gloo: the N > 1 host path (shard reads by bases -> map each shard independently ->
+concatenate in input order) gives exactly the unsharded result. The per-shard map is done by the CPU oracle here
+(no GPU in this container); on the GPU box bench.py runs the same sharding with the CUDA path per rank."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from cases import make_case
+    from cpu_checkers import Oracle
+    from linear_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g, reads, bases, offs, T, preset = make_case("clean_hifi")
+    O = Oracle(g, threads=T, preset=preset)           # index replicated on every rank
+    lo, hi = sharding.shard_ranges(offs, world)[rank]
+    sb, so = sharding.take_shard(bases, offs, lo, hi)
+    part = O.map_batch(sb, so, map_threads=1)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (part[0], part[1], lo, hi))
+    dist.barrier()
+    if rank == 0:
+        cords, coff = sharding.merge_cords([(c, o) for c, o, _, _ in gathered])
+        full_c, full_o = O.map_batch(bases, offs, map_threads=2)
+        ranges = [(a, b) for _, _, a, b in gathered]
+        q.put((bool(np.array_equal(cords, full_c) and np.array_equal(coff, full_o)), ranges, len(offs) - 1))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_unsharded():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, ranges, n = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
+    assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == n
+
+
+def test_shard_ranges_cover_and_balance():
+    from linear_b200 import sharding
+    rng = np.random.default_rng(0)
+    lens = rng.integers(1, 50000, size=1000)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    for world in (1, 2, 3, 8):
+        rs = sharding.shard_ranges(offs, world)
+        assert rs[0][0] == 0 and rs[-1][1] == 1000
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+        per = [int(offs[b] - offs[a]) for a, b in rs]
+        assert max(per) - min(per) <= 2 * 50000
+    assert sharding.shard_ranges(np.zeros(1, np.uint64), 4) == [(0, 0)] * 4
