@@ -303,58 +303,92 @@ LNR_HD int score_blocks_cords(u64 c11, u64 c12, u64 c21, u64 c22, u64 L, int str
 // ----------------------------------------------------------------------------------------------------
 // getBestChains (cluster_util.cpp:53): for each i the best predecessor among the previous 20 or any with
 // x_j - x_i < 300. The reference scans j downward and overwrites on `>=`, so among equal best sums the
-// smallest j wins. Lanes evaluate 32 predecessors at a time; the recurrence over i stays sequential.
+// smallest j wins; the scan stops at the first j that fails the range test.
+//
+// The recurrence over i is sequential. Lane l keeps predecessor j = i-1-l (anchor, chain score, chain
+// length, root) in registers and the window slides by one shuffle per step, so the inner loop has no
+// dependent global loads; predecessors older than the register window (dense repeats only) come from
+// global memory. The winner is found with one 32-bit warp max over (sum << 5 | lane).
 // ----------------------------------------------------------------------------------------------------
+LNR_HD int score_pair(u64 aj, u64 ai, int score_type) { return score_type == 0 ? score_anchor(aj, ai) : score_anchor0(aj, ai); }
+
 LNR_PIPE void best_chains(const Warp & w, const u64 * a, ChainRec * ch, int n, int score_type)
 {
     const int depth = 20;
     const u64 dx_depth = 300;
+    u64 aj = 0;                       // anchor of predecessor i-1-lane
+    i32 sj = 0, lenj = 0, rootj = 0;  // its chain score / length / root
+    u64 a_next = n > 0 ? a[0] : 0;
     for (int i = 0; i < n; i++)
     {
-        u64 ai = a[i];
-        u64 xi = anchor_x(ai);
-        int j_str = i - depth > 0 ? i - depth : 0;
-        i64 best = -1;                 // packed (sum << 32) | (0x7fffffff - j); -1 = none
-        for (int jb = i - 1; jb >= 0; jb -= w.nl)
+        const u64 ai = a_next;
+        if (i + 1 < n) a_next = a[i + 1];
+        const u64 xi = anchor_x(ai);
+        const int j = i - 1 - w.lane;
+        bool ok = j >= 0 && (w.lane < depth || anchor_x(aj) - xi < dx_depth);
+        u32 okmask = wballot(w, ok);
+        u32 full = w.nl == 32 ? 0xffffffffu : ((1u << w.nl) - 1);
+        int first_fail = okmask == full ? w.nl : ffs32(~okmask & full);
+        u32 key = 0;                  // (sum << 5) | lane ; 0 = none
+        if (ok && w.lane < first_fail)
         {
-            int j = jb - w.lane;
-            bool ok = j >= 0;
-            u64 aj = ok ? a[j] : 0;
-            ok = ok && (j >= j_str || anchor_x(aj) - xi < dx_depth);
-            if (ok)
+            int s = score_pair(aj, ai, score_type);
+            if (s > 0) key = ((u32)(s + sj) << 5) | (u32)w.lane;
+        }
+        key = wmax_u32(w, key);
+        int new_max = key ? (int)(key >> 5) : -1;
+        int max_j = key ? i - 1 - (int)(key & 31) : i;
+        i32 p_len = 0, p_root = 0;
+        if (key) { p_len = wbcast(w, lenj, (int)(key & 31)); p_root = wbcast(w, rootj, (int)(key & 31)); }
+        // predecessors beyond the register window: only when every window lane passed the range test
+        if (first_fail == w.nl && i - 1 - w.nl >= 0)
+        {
+            i64 best = key ? (((i64)new_max << 32) | (i64)(0x7fffffff - max_j)) : -1;
+            bool from_mem = false;
+            for (int jb = i - 1 - w.nl; jb >= 0; jb -= w.nl)
             {
-                int s = score_type == 0 ? score_anchor(aj, ai) : score_anchor0(aj, ai);
-                if (s > 0)
+                int jj = jb - w.lane;
+                bool ok2 = jj >= 0;
+                u64 a2 = ok2 ? a[jj] : 0;
+                ok2 = ok2 && (jj >= i - depth || anchor_x(a2) - xi < dx_depth);
+                u32 m2 = wballot(w, ok2);
+                int ff = m2 == full ? w.nl : ffs32(~m2 & full);
+                if (ok2 && w.lane < ff)
                 {
-                    i64 sum = (i64)s + (i64)ch[j].score;
-                    if (sum >= -1)
+                    int s = score_pair(a2, ai, score_type);
+                    if (s > 0)
                     {
-                        i64 key = (sum << 32) | (i64)(0x7fffffff - j);
-                        if (key > best) best = key;
+                        i64 k2 = (((i64)s + (i64)ch[jj].score) << 32) | (i64)(0x7fffffff - jj);
+                        if (k2 > best) best = k2;
                     }
                 }
+                if (ff != w.nl) break;
             }
-            // the reference's loop stops at the first j that fails the range test; x is sorted
-            // descending, so the test is monotone in j and a failing lane ends the scan
-            if (wballot(w, !ok) != 0) break;
+            i64 bmax = wmax_i64(w, best);
+            if (bmax >= 0)
+            {
+                int mj = 0x7fffffff - (int)(bmax & 0x7fffffff);
+                from_mem = mj != max_j || !key;
+                new_max = (int)(bmax >> 32);
+                max_j = mj;
+            }
+            if (from_mem) { p_len = ch[max_j].len; p_root = ch[max_j].root_ptr; }
         }
-        best = wmax_i64(w, best);
+        i32 c_score, c_len, c_root;
+        if (new_max > 0) { c_score = new_max; c_len = p_len + 1; c_root = p_root; }
+        else { c_score = 0; c_len = 1; c_root = i; max_j = -1; }
         if (w.lane == 0)
         {
-            int new_max = best < 0 ? -1 : (int)(best >> 32);
-            int max_j = best < 0 ? i : 0x7fffffff - (int)(best & 0x7fffffff);
-            if (new_max > 0)
-            {
-                ch[i].p2anchor = max_j; ch[i].score = new_max; ch[i].len = ch[max_j].len + 1; ch[i].score2 = new_max;
-                ch[i].root_ptr = ch[max_j].root_ptr; ch[i].f_leaf = 1; ch[max_j].f_leaf = 0;
-            }
-            else
-            {
-                ch[i].p2anchor = -1; ch[i].score = 0; ch[i].len = 1; ch[i].score2 = 0; ch[i].root_ptr = i; ch[i].f_leaf = 1;
-            }
+            ChainRec r;
+            r.p2anchor = max_j; r.score = c_score; r.score2 = c_score; r.len = c_len; r.root_ptr = c_root; r.f_leaf = 1;
+            ch[i] = r;
+            if (max_j >= 0) ch[max_j].f_leaf = 0;
         }
-        wsync(w);
+        // slide the window: lane l takes lane l-1, lane 0 takes element i
+        aj = wshift_up64(w, aj); sj = (i32)wshift_up32(w, (u32)sj); lenj = (i32)wshift_up32(w, (u32)lenj); rootj = (i32)wshift_up32(w, (u32)rootj);
+        if (w.lane == 0) { aj = ai; sj = c_score; lenj = c_len; rootj = c_root; }
     }
+    wsync(w);
 }
 
 // ----------------------------------------------------------------------------------------------------

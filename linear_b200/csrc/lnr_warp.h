@@ -67,7 +67,14 @@ LNR_PIPE_INL int wscan_excl(const Warp & w, int v, int & total)
     total = __shfl_sync(kFull, s, 31);
     return s - v;
 }
+LNR_PIPE_INL u32 wmax_u32(const Warp &, u32 v) { return __reduce_max_sync(kFull, v); }
 LNR_PIPE_INL u32 wmatch(const Warp &, u32 key) { return __match_any_sync(kFull, key); }
+LNR_PIPE_INL u32 wshift_up32(const Warp &, u32 v) { return __shfl_up_sync(kFull, v, 1); }   // lane l gets lane l-1 (lane 0 keeps its own)
+LNR_PIPE_INL u64 wshift_up64(const Warp &, u64 v)
+{
+    u32 lo = __shfl_up_sync(kFull, (u32)v, 1), hi = __shfl_up_sync(kFull, (u32)(v >> 32), 1);
+    return ((u64)hi << 32) | lo;
+}
 LNR_PIPE_INL int popc_below(const Warp & w, u32 mask) { return __popc(mask & ((1u << w.lane) - 1)); }
 LNR_PIPE_INL int popc32(u32 m) { return __popc(m); }
 LNR_PIPE_INL int ffs32(u32 m) { return __ffs((int)m) - 1; }
@@ -80,7 +87,10 @@ LNR_PIPE_INL int wsum(const Warp &, int v) { return v; }
 LNR_PIPE_INL u64 wor64(const Warp &, u64 v) { return v; }
 LNR_PIPE_INL i64 wmax_i64(const Warp &, i64 v) { return v; }
 LNR_PIPE_INL int wscan_excl(const Warp &, int v, int & total) { total = v; return 0; }
+LNR_PIPE_INL u32 wmax_u32(const Warp &, u32 v) { return v; }
 LNR_PIPE_INL u32 wmatch(const Warp &, u32) { return 1u; }
+LNR_PIPE_INL u32 wshift_up32(const Warp &, u32 v) { return v; }
+LNR_PIPE_INL u64 wshift_up64(const Warp &, u64 v) { return v; }
 LNR_PIPE_INL int popc_below(const Warp &, u32) { return 0; }
 LNR_PIPE_INL int popc32(u32 m) { return __builtin_popcount(m); }
 LNR_PIPE_INL int ffs32(u32 m) { return __builtin_ffs((int)m) - 1; }
