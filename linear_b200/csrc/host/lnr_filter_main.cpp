@@ -1,0 +1,178 @@
+// `linear_b200_filter filter reads.fa genome.fa [-t N] [-p N] [-i 1] [-f 2] [-ot 1] [-g 0]`
+//
+// Host-side mirror of the reference's CLI surface for the apx-map path (src/args_parser.cpp:118,
+// src/linear.cpp:8-21 process1, src/mapper.cpp:883 map): load genome -> features + index on the GPU through the
+// C ABI -> stream reads in blocks of 50 000 (mapper.cpp:892) -> lnr_apxmap_batch -> APF text identical to
+// print_cords_apf (src/f_io.cpp:100-207). It exists to diff whole-program output against
+// `linear filter reads.fa genome.fa -ot 1 -b 0 -g 0 -t T`; gap mapping and SAM/BAM stay the reference's host code.
+// Output: <reads-file-stem>.apf in the working directory (mapper.cpp:904-906).
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "../../../include/lnr_b200.h"
+
+struct Rec { std::string id; std::vector<uint8_t> seq; };
+
+static inline uint8_t ord5(char c)   // seqan Dna5: every non-ACGTU byte is N (alphabet_residue_tabs.h:113-140)
+{
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2;
+                 case 'T': case 't': case 'U': case 'u': return 3; default: return 4; }
+}
+
+// FASTA / FASTQ reader; `n` records at most (0 = all). Returns false at end of file.
+struct SeqReader
+{
+    std::ifstream in; std::string line; bool have = false;
+    bool open(const std::string & p) { in.open(p); return in.good(); }
+    bool next_line() { if (have) { have = false; return true; } return (bool)std::getline(in, line); }
+    bool read(std::vector<Rec> & out, size_t n, bool cut_id_at_space)
+    {
+        out.clear();
+        while (n == 0 || out.size() < n)
+        {
+            if (!next_line()) break;
+            if (line.empty()) continue;
+            if (line[0] == '>')
+            {
+                Rec r; r.id = line.substr(1);
+                if (!r.id.empty() && r.id.back() == '\r') r.id.pop_back();
+                if (cut_id_at_space) r.id = r.id.substr(0, r.id.find(' '));   // loadRecords base.cpp:154
+                while (std::getline(in, line))
+                {
+                    if (!line.empty() && (line[0] == '>' || line[0] == '@')) { have = true; break; }
+                    for (char c : line) if (c != '\r' && c != ' ') r.seq.push_back(ord5(c));
+                }
+                out.push_back(std::move(r));
+            }
+            else if (line[0] == '@')
+            {
+                Rec r; r.id = line.substr(1);
+                if (cut_id_at_space) r.id = r.id.substr(0, r.id.find(' '));
+                std::string s, plus, q;
+                std::getline(in, s); std::getline(in, plus); std::getline(in, q);
+                for (char c : s) if (c != '\r') r.seq.push_back(ord5(c));
+                out.push_back(std::move(r));
+            }
+        }
+        return !out.empty();
+    }
+};
+
+static const uint64_t kEnd = 1ULL << 60;
+static inline uint64_t cx(uint64_t v) { return (v >> 20) & ((1ULL << 30) - 1); }
+static inline uint64_t cy(uint64_t v) { return v & 0xfffff; }
+static inline uint64_t cs(uint64_t v) { return (v >> 61) & 1; }
+static inline uint64_t cid(uint64_t v) { return (v >> 50) & 1023; }
+
+// print_cords_apf (f_io.cpp:100-207) for one block of reads
+static void write_apf(std::ostream & of, const std::vector<Rec> & reads, const std::vector<Rec> & genome, const uint64_t * cords,
+                      const uint64_t * coff, char & main_icon, uint64_t window)
+{
+    std::ostringstream st;
+    int fflag = 0;
+    for (size_t k = 0; k < reads.size(); k++)
+    {
+        const uint64_t * c = cords + coff[k];
+        size_t n = (size_t)(coff[k + 1] - coff[k]);
+        for (size_t j = 1; j < n; j++)
+        {
+            if (c[j - 1] & kEnd)
+            {
+                size_t m = j; int mcount = 0, blen = 0;
+                while (m < n && !(c[m] & kEnd)) { if (cs(c[m])) mcount++; blen++; m++; }
+                if (mcount > blen / 2) main_icon = '-';
+                else if (mcount == blen / 2) main_icon = cs(c[j]) ? '-' : '+';
+                else main_icon = '+';
+                uint64_t rend = 0, gend = 0;
+                for (size_t i = j;; i++)
+                    if ((c[i] & kEnd) || i == n - 1) { rend = cy(c[i]) + window; gend = cx(c[i]) + window; break; }
+                if (k > 0) st << "\n";
+                st << "@ " << reads[k].id << " " << reads[k].seq.size() << " " << cy(c[j]) << " "
+                   << std::min<uint64_t>(rend, reads[k].seq.size()) << " " << main_icon << " " << genome[cid(c[j])].id << " "
+                   << genome[cid(c[j])].seq.size() << " " << cx(c[j]) << " " << gend << "\n";
+                fflag = 1;
+            }
+            char icon = cs(c[j]) ? '-' : '+';
+            int64_t d1 = 0, d2 = 0;
+            if (!fflag) { d1 = (int64_t)(cx(c[j]) - cx(c[j - 1])); d2 = (int64_t)(cy(c[j]) - cy(c[j - 1])); }
+            st << "| " << cy(c[j]) << " " << cx(c[j]) << " " << d2 << " " << d1 << " " << icon << "\n";
+            fflag = 0;
+        }
+    }
+    of << st.str();
+}
+
+int main(int argc, char ** argv)
+{
+    std::vector<std::string> pos;
+    int threads = 16, preset = 1, index_t = 1, feature_t = 2, ot = 2, device = 0;   // defaults: base.cpp:26-54
+    for (int i = 1; i < argc; i++)
+    {
+        std::string a = argv[i];
+        auto val = [&](int & dst) { if (i + 1 < argc) dst = atoi(argv[++i]); };
+        if (a == "-t" || a == "--thread") val(threads);
+        else if (a == "-p" || a == "--preset") val(preset);
+        else if (a == "-i" || a == "--index_type") val(index_t);
+        else if (a == "-f" || a == "--feature_type") val(feature_t);
+        else if (a == "-ot" || a == "--output_type") val(ot);
+        else if (a == "--device") val(device);
+        else if (a == "-g" || a == "-b" || a == "-o" || a == "-c" || a == "-s" || a == "-a") { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }
+        else if (!a.empty() && a[0] == '-') { /* other reference options do not affect this path */ }
+        else pos.push_back(a);
+    }
+    if (pos.size() < 3 || pos[0] != "filter")
+    {
+        fprintf(stderr, "usage: %s filter reads.fa genome.fa [-t N] [-p N] [-i 1] [-f 2] [-ot 1]\n", argv[0]);
+        return 1;
+    }
+    const std::string rpath = pos[1], gpath = pos[2];
+    SeqReader gr;
+    if (!gr.open(gpath)) { fprintf(stderr, "E[06]:Can't open file %s\n", gpath.c_str()); return 1; }
+    std::vector<Rec> genome;
+    gr.read(genome, 0, true);
+    if (genome.size() >= 1024) { fprintf(stderr, "too many contigs (linear.cpp:107)\n"); return 1; }
+    lnr_ctx * ctx = nullptr; lnr_genome * g = nullptr; lnr_feats * f2 = nullptr; lnr_index * ix = nullptr;
+    auto die = [&](const char * what, int rc) { fprintf(stderr, "lnr_b200: %s failed (%d): %s\n", what, rc, ctx ? lnr_last_error(ctx) : "no CUDA device"); return 2; };
+    int rc;
+    if ((rc = lnr_ctx_create(device, &ctx))) return die("lnr_ctx_create", rc);
+    std::vector<const uint8_t *> ptr; std::vector<uint64_t> len;
+    for (auto & r : genome) { ptr.push_back(r.seq.data()); len.push_back(r.seq.size()); }
+    if ((rc = lnr_genome_upload(ctx, (uint32_t)genome.size(), ptr.data(), len.data(), &g))) return die("lnr_genome_upload", rc);
+    if ((rc = lnr_features_build(ctx, g, feature_t, (unsigned)threads, &f2))) return die("lnr_features_build", rc);
+    if ((rc = lnr_index_build(ctx, g, index_t, (unsigned)threads, &ix))) return die("lnr_index_build", rc);
+    // output prefix = read file stem (mapper.cpp:904-906)
+    std::string stem = rpath.substr(rpath.find_last_of('/') == std::string::npos ? 0 : rpath.find_last_of('/') + 1);
+    stem = stem.substr(0, stem.find('.'));
+    std::ofstream of;
+    if (ot & 1) of.open(stem + ".apf");
+    SeqReader rr;
+    if (!rr.open(rpath)) { fprintf(stderr, "E[07]:Can't open read file %s\n", rpath.c_str()); return 1; }
+    std::vector<Rec> reads;
+    lnr_params prm; memset(&prm, 0, sizeof prm); prm.preset = preset; prm.feature_type = feature_t;
+    char main_icon = '+';
+    uint64_t n_reads_total = 0, n_cords_total = 0;
+    while (rr.read(reads, 50000, false))   // blockSize, mapper.cpp:892
+    {
+        std::vector<uint64_t> off(reads.size() + 1, 0);
+        for (size_t j = 0; j < reads.size(); j++) off[j + 1] = off[j] + reads[j].seq.size();
+        std::vector<uint8_t> bases(off.back());
+        for (size_t j = 0; j < reads.size(); j++) if (!reads[j].seq.empty()) memcpy(&bases[off[j]], reads[j].seq.data(), reads[j].seq.size());
+        std::vector<uint64_t> cords(off.back() / 16 + 64 * reads.size() + 1024), coff(reads.size() + 1);
+        if ((rc = lnr_apxmap_batch(ctx, ix, f2, &prm, (uint32_t)reads.size(), bases.data(), off.data(), cords.data(), coff.data(), cords.size(), nullptr)))
+            return die("lnr_apxmap_batch", rc);
+        main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
+        if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, 96);
+        n_reads_total += reads.size();
+        n_cords_total += coff.back();
+    }
+    fprintf(stderr, "lnr_b200 filter: %llu reads, %llu cords -> %s.apf\n", (unsigned long long)n_reads_total, (unsigned long long)n_cords_total, stem.c_str());
+    lnr_index_destroy(ix); lnr_features_destroy(f2); lnr_genome_destroy(g); lnr_ctx_destroy(ctx);
+    return 0;
+}

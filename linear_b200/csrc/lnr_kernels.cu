@@ -661,21 +661,19 @@ __device__ __noinline__ int finish_read(const Warp & w, Arena & ar, u64 L, u64 *
     block_scratch_alloc(ar, s2, n_sep_cap);
     u64 * tmp = arena_alloc<u64>(ar, (u64)cap);
     if (ar.failed) return 1;
-    if (w.lane == 0)
+    int n_sep;
+    if (regather)
     {
-        int n_sep;
-        if (regather)
-        {
-            int dummy = 0;
-            n_sep = gather_blocks(cords, nc, (YPair *)0, dummy, sp1, 0, 1, (u32)nc, L, 1000, kWin, 1);
-        }
-        else
-        {
-            n_sep = n_sep_in;
-            for (int i = 0; i < n_sep; i++) sp1[i] = sep_in[i];
-        }
-        phase_finish(L, cords, nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp);
+        int dummy = 0;
+        n_sep = gather_blocks_w(w, cords, nc, (YPair *)0, dummy, sp1, L, 1000, kWin, 1);
     }
+    else
+    {
+        n_sep = n_sep_in;
+        for (int i = w.lane; i < n_sep; i += 32) sp1[i] = sep_in[i];
+        __syncwarp();
+    }
+    phase_finish_w(w, L, cords, nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp);
     nc = __shfl_sync(0xffffffffu, nc, 0);
     __syncwarp();
     return 0;
@@ -738,9 +736,9 @@ __global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
                 if (ar.failed) rc = 1;
                 else
                 {
+                    remap = phase_mid_w(w, L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
                     if (w.lane == 0)
                     {
-                        remap = phase_mid(L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
                         if (remap == 1)
                         {
                             task0 = atomicAdd(a.n_tasks2, (u32)n_gaps);

@@ -710,17 +710,15 @@ LNR_PIPE_INL void wdist3(const Warp & w, const PipeIn & in, u32 strand, u32 id, 
     const bool yok = y + 3 < in.nf1;
     const F96 * fa = in.f1[strand] + y;
     const F96 * fb = in.f2[id] + x0;
-    int s0 = 0, s1 = 0, s2 = 0;
+    // every script distance is <= 5*32, a window sums 6 of them: 10 bits per candidate, one warp add
+    int packed = 0;
     for (int t = w.lane; t < 18; t += w.nl)
     {
         int c = t / 6, part = t - 6 * c, i = part >= 3 ? 3 : 0, k = part - i;
-        if (yok && x0 + c + 3 < nf2)
-        {
-            int v = script_dist(fa[i].v[k], fb[c + i].v[k]);
-            if (c == 0) s0 += v; else if (c == 1) s1 += v; else s2 += v;
-        }
+        if (yok && x0 + c + 3 < nf2) packed += script_dist(fa[i].v[k], fb[c + i].v[k]) << (10 * c);
     }
-    s0 = wsum(w, s0); s1 = wsum(w, s1); s2 = wsum(w, s2);
+    packed = wsum(w, packed);
+    int s0 = packed & 1023, s1 = (packed >> 10) & 1023, s2 = (packed >> 20) & 1023;
     d[0] = (yok && x0 + 3 < nf2) ? (u32)s0 : 1000u;
     d[1] = (yok && x0 + 4 < nf2) ? (u32)s1 : 1000u;
     d[2] = (yok && x0 + 5 < nf2) ? (u32)s2 : 1000u;
@@ -1034,6 +1032,97 @@ LNR_HD int best_strand_of(const Blk * e1, const int * o1, int n1, const Blk * e2
 }
 
 // ----------------------------------------------------------------------------------------------------
+// warp-parallel versions of the two linear passes over the cord list
+// ----------------------------------------------------------------------------------------------------
+// clean_blocks_ is the identity when no cord steps back inside a block and no block is shorter than
+// drop_len; that is the common case and is checked by all lanes. Otherwise lane 0 runs clean_blocks.
+LNR_PIPE int clean_blocks_w(const Warp & w, u64 * cords, int n, u64 drop_len, i64 map_err)
+{
+    if (n == 0) return 0;
+    wsync(w);
+    bool bad = false;
+    for (int i = 1 + w.lane; i < n; i += w.nl)
+    {
+        u64 p = cords[i - 1], c = cords[i];
+        if (!is_end(p))
+        {
+            i64 dx = (i64)(cord_x(c) - cord_x(p)), dy = (i64)(cord_y(c) - cord_y(p));
+            if (dx < 0 || dy < 0) bad = true;
+        }
+        // a block [s, i] shorter than drop_len (<= 2): its end cord directly or one step after another end
+        if (is_end(c) && drop_len > 0)
+        {
+            if (is_end(p) && 1 < drop_len) bad = true;
+            if (i >= 2 && !is_end(p) && is_end(cords[i - 2]) && 2 < drop_len) bad = true;
+        }
+    }
+    if (wballot(w, bad) == 0) return n;
+    int out = n;
+    if (w.lane == 0) out = clean_blocks(cords, n, drop_len, map_err);
+    out = wbcast(w, out, 0);
+    wsync(w);
+    return out;
+}
+
+// gather_blocks_ (pmpfinder.cpp:1484), all lanes: block boundaries are found 32 cords at a time and appended in
+// order. Same outputs as gather_blocks (str_ = 1, end_ = n).
+LNR_PIPE int gather_blocks_w(const Warp & w, u64 * cords, int n, YPair * str_ends, int & n_str_ends, Blk * sep, u64 L, u64 large_gap,
+                             u64 cord_size, int f_set_end)
+{
+    n_str_ends = 0;
+    if (n < 2) return 0;
+    wsync(w);
+    const u64 dmax = cord_size / 2;
+    int nb = 0;
+    u32 p_str = 1;
+    for (int c0 = 2; c0 < n; c0 += w.nl)
+    {
+        int i = c0 + w.lane;
+        bool brk = false;
+        u64 prev = 0;
+        if (i < n)
+        {
+            prev = cords[i - 1];
+            brk = is_end(prev) || !cords_consecutive(prev, cords[i], large_gap);
+        }
+        u32 m = wballot(w, brk);
+        int rank = popc_below(w, m);
+        // start of this lane's block = previous boundary (in this chunk or carried)
+        u32 below = w.nl == 32 ? (m & ((1u << w.lane) - 1)) : 0;
+        u32 start = below ? (u32)(c0 + (hibit32(below))) : p_str;
+        if (brk)
+        {
+            if (str_ends)
+            {
+                u64 sc = cords[start];
+                u64 d = umin64(L - cord_y(sc) - 1, dmax);
+                str_ends[nb + rank].first = shift_cord(sc, (i64)d, (i64)d);
+                d = umin64(L - cord_y(prev) - 1, dmax);
+                str_ends[nb + rank].second = shift_cord(prev, (i64)d, (i64)d);
+            }
+            sep[nb + rank].first = start; sep[nb + rank].second = (u32)i;
+            if (f_set_end) cords[i - 1] = prev | kFlagEnd;
+        }
+        if (m) p_str = (u32)(c0 + (hibit32(m)));
+        nb += popc32(m);
+    }
+    if (w.lane == 0)
+    {
+        if (str_ends)
+        {
+            u64 d = umin64(L - cord_y(cords[n - 1]) - 1, dmax);
+            str_ends[nb].first = shift_cord(cords[p_str], (i64)d, (i64)d);
+            str_ends[nb].second = shift_cord(cords[n - 1], (i64)d, (i64)d);
+        }
+        sep[nb].first = p_str; sep[nb].second = (u32)n;
+    }
+    nb++;
+    n_str_ends = nb;
+    wsync(w);
+    return nb;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // Phase 1: one apxMap_ call after seeding (pmpfinder.cpp:2632): filter -> chain -> hits -> blocks ->
 // window extension. A[0..n): raw anchors with A[0] the sentinel slot; B: second buffer of n entries.
 // Appends to cords. dbg_hits (optional): hits after getAnchorHitsChains.
@@ -1252,6 +1341,77 @@ LNR_HD int phase_finish(u64 L, u64 * cords, int & n_cords, Blk * sep, int n_sep,
         cords[i] = c;
     }
     return 0;
+}
+
+// warp versions of phase 2 / phase 3: the linear passes run on all lanes, the small block-chaining logic on lane 0
+LNR_PIPE int phase_mid_w(const Warp & w, u64 L, u64 * cords, int & n_cords, YPair * str_ends, Blk * sep, int & n_sep, YPair * gaps,
+                         int & n_gaps, int gaps_cap)
+{
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    n_cords = clean_blocks_w(w, cords, n_cords, (u64)drop_len, 50);
+    int ns = 0;
+    n_sep = gather_blocks_w(w, cords, n_cords, str_ends, ns, sep, L, 1000, kWin, 1);
+    int res = 0;
+    if (w.lane == 0)
+    {
+        int gap_sum = gather_gaps_y(str_ends, ns, gaps, n_gaps, gaps_cap, L, 1000);
+        if (n_gaps >= gaps_cap) res = -1;
+        else
+        {
+            for (int i = 0; i < n_gaps; i++)
+            {
+                u64 a, b;
+                forward_y(gaps[i], L, a, b);
+                gaps[i].first = a; gaps[i].second = b;
+            }
+            res = ((float)gap_sum / (float)L >= 0.7f) ? 1 : 0;
+        }
+    }
+    res = wbcast(w, res, 0);
+    n_gaps = wbcast(w, n_gaps, 0);
+    wsync(w);
+    return res;
+}
+
+LNR_PIPE void phase_finish_w(const Warp & w, u64 L, u64 * cords, int & n_cords, Blk * sep, int n_sep, Blk * sep2, i32 * score1, i32 * score2,
+                             BlockScratch & s1, BlockScratch & s2, u64 * tmp)
+{
+    if (w.lane == 0)
+    {
+        for (int i = 0; i < n_sep; i++) sep2[i] = sep[i];
+        int n1 = chain_blocks_single_strand(cords, sep, n_sep, s1, score1, 0, L, 16);
+        int n2 = chain_blocks_single_strand(cords, sep2, n_sep, s2, score2, 1, L, 16);
+        int best = best_strand_of(s1.out_el, s1.chain_off, n1, s2.out_el, s2.chain_off, n2);
+        BlockScratch & sb = best == 0 ? s1 : s2;
+        int nb = best == 0 ? n1 : n2;
+        if (nb > 0)
+        {
+            revert_chain_block_strand(sb.out_el, sb.chain_off, nb, cords, best);
+            int no = filter_blocks_cords(sb.out_el, sb.chain_off, nb, cords, tmp, 2);
+            for (int i = 0; i < no; i++) cords[i] = tmp[i];
+            n_cords = no;
+        }
+    }
+    n_cords = wbcast(w, n_cords, 0);
+    wsync(w);
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    n_cords = clean_blocks_w(w, cords, n_cords, (u64)drop_len, 50);
+    // main / record flags (pmpfinder.cpp:2788-2801): the record bit alternates after every block end
+    int ends_before = 0;
+    for (int c0 = 0; c0 < n_cords; c0 += w.nl)
+    {
+        int i = c0 + w.lane;
+        u64 c = i < n_cords ? cords[i] : 0;
+        u32 m = wballot(w, i < n_cords && is_end(c));
+        int seg = (ends_before + popc_below(w, m)) & 1;
+        if (i < n_cords)
+        {
+            if (seg) c |= kFlagRecd; else c &= ~kFlagRecd;
+            cords[i] = c | kFlagMain;
+        }
+        ends_before += popc32(m);
+    }
+    wsync(w);
 }
 
 }  // namespace lnr

@@ -31,11 +31,7 @@ LNR_PIPE_INL u64 wbcast64(const Warp &, u64 v, int src)
     u32 lo = __shfl_sync(kFull, (u32)v, src), hi = __shfl_sync(kFull, (u32)(v >> 32), src);
     return ((u64)hi << 32) | lo;
 }
-LNR_PIPE_INL int wsum(const Warp &, int v)
-{
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-}
+LNR_PIPE_INL int wsum(const Warp &, int v) { return __reduce_add_sync(kFull, v); }
 LNR_PIPE_INL u64 wor64(const Warp &, u64 v)
 {
     for (int o = 16; o; o >>= 1)
@@ -78,6 +74,7 @@ LNR_PIPE_INL u64 wshift_up64(const Warp &, u64 v)
 LNR_PIPE_INL int popc_below(const Warp & w, u32 mask) { return __popc(mask & ((1u << w.lane) - 1)); }
 LNR_PIPE_INL int popc32(u32 m) { return __popc(m); }
 LNR_PIPE_INL int ffs32(u32 m) { return __ffs((int)m) - 1; }
+LNR_PIPE_INL int hibit32(u32 m) { return 31 - __clz((int)m); }
 #else
 LNR_PIPE_INL void wsync(const Warp &) {}
 LNR_PIPE_INL u32 wballot(const Warp &, bool p) { return p ? 1u : 0u; }
@@ -94,6 +91,7 @@ LNR_PIPE_INL u64 wshift_up64(const Warp &, u64 v) { return v; }
 LNR_PIPE_INL int popc_below(const Warp &, u32) { return 0; }
 LNR_PIPE_INL int popc32(u32 m) { return __builtin_popcount(m); }
 LNR_PIPE_INL int ffs32(u32 m) { return __builtin_ffs((int)m) - 1; }
+LNR_PIPE_INL int hibit32(u32 m) { return 31 - __builtin_clz(m); }
 #endif
 
 // Bump allocator over the warp's private scratch region (reset for every read). Allocation failure is

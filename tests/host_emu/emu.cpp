@@ -169,7 +169,7 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
     Blk * sep = arena_alloc<Blk>(ar, nc + 2);
     YPair * gaps = arena_alloc<YPair>(ar, L / 1000 + 4);
     int n_sep = 0, n_gaps = 0;
-    int remap = phase_mid(L, R.cords.data(), nc, str_ends, sep, n_sep, gaps, n_gaps, (int)(L / 1000 + 4));
+    int remap = phase_mid_w(w, L, R.cords.data(), nc, str_ends, sep, n_sep, gaps, n_gaps, (int)(L / 1000 + 4));
     if (remap < 0) return 1;
     std::vector<YPair> gv(gaps, gaps + n_gaps);
     std::vector<Blk> sepv(sep, sep + n_sep);
@@ -186,7 +186,7 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
         }
         sepv.assign(nc + 2, Blk());
         int dummy = 0;
-        n_sep = gather_blocks(R.cords.data(), nc, (YPair *)0, dummy, sepv.data(), 0, 1, (u32)nc, L, 1000, kWin, 1);
+        n_sep = gather_blocks_w(w, R.cords.data(), nc, (YPair *)0, dummy, sepv.data(), L, 1000, kWin, 1);
     }
     arena_reset(ar);
     Blk * sp1 = arena_alloc<Blk>(ar, n_sep + 1);
@@ -199,7 +199,7 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
     u64 * tmp = arena_alloc<u64>(ar, cap);
     if (ar.failed) return 1;
     for (int i = 0; i < n_sep; i++) sp1[i] = sepv[i];
-    phase_finish(L, R.cords.data(), nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp);
+    phase_finish_w(w, L, R.cords.data(), nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp);
     cords_out.assign(R.cords.begin(), R.cords.begin() + nc);
     return 0;
 }
