@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 32768)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("LNR_BENCH_CPU_SAMPLE", 2048)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("LNR_BENCH_STREAMS", 2)),
+                    help="concurrent host threads, each with its own lnr_ctx (the reference calls p_calRecords from -t threads)")
     return ap.parse_args()
 
 
@@ -211,7 +213,8 @@ def main():
                           f"(lognormal mean 20 kb, 10% error, 20% planted SV), {args.batch_reads} reads per step per GPU",
               "index": "DIndex (-i 1)", "features": "2-mer/48 (-f 2)", "threads_sem": THREADS_SEM, "preset": 1,
               "batch_reads_per_gpu": args.batch_reads, "parallelism": f"reads sharded x{world}, index replicated",
-              "l2_policy": "inputs larger than L2 (batch bases + index >> 126 MB)"}
+              "l2_policy": "inputs larger than L2 (batch bases + index >> 126 MB)",
+              "host_threads": args.streams}
 
     if args.impl == "reference":
         if rank != 0:
@@ -323,62 +326,87 @@ def main():
     n_reads = len(offs) - 1
     total_bases = int(offs[-1])
     cap = total_bases // 16 + 64 * n_reads + 1024
-    cords_dev = torch.empty(cap, dtype=torch.int64, device=dev)
-    coff_dev = torch.empty(n_reads + 4200, dtype=torch.int64, device=dev)
     import ctypes as C
     from linear_b200.api import Params, u64p
     prm = Params(preset=1, feature_type=2)
     offs_c = offs.ctypes.data_as(u64p)
-    ntot = C.c_uint64()
-
-    def step_device():
-        ctx.check(ctx.lib.lnr_apxmap_batch_device(ctx.h, index.h, feats.h, C.byref(prm), n_reads, C.c_void_p(bases_t.data_ptr()), offs_c,
-                                                  C.c_void_p(cords_dev.data_ptr()), C.c_void_p(coff_dev.data_ptr()), cap, C.byref(ntot)))
-
     bases_pin = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)
     bases_pin.copy_(bases_t)
     bases_np = bases_pin.numpy()
-    cords_pin = torch.empty(cap, dtype=torch.int64, pin_memory=True)
-    cords_np = cords_pin.numpy().view(np.uint64)
-    coff_np = np.zeros(n_reads + 1, dtype=np.uint64)
+    n_str = max(1, args.streams)
+    ctxs = [ctx] + [lb.Context(local_rank) for _ in range(n_str - 1)]
 
-    def step_host():
-        return lb.apx_map_batch(ctx, index, feats, bases_np, offs, preset=1, cords_out=cords_np, cords_off_out=coff_np)
+    class Stream:
+        """one host thread's resources: its own lnr_ctx (CUDA stream + workspace) and output buffers"""
+        def __init__(self, c):
+            self.ctx = c
+            self.cords_dev = torch.empty(cap, dtype=torch.int64, device=dev)
+            self.coff_dev = torch.empty(n_reads + 4200, dtype=torch.int64, device=dev)
+            self.ntot = C.c_uint64()
+            self.cords_pin = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+            self.cords_np = self.cords_pin.numpy().view(np.uint64)
+            self.coff_np = np.zeros(n_reads + 1, dtype=np.uint64)
+            self.last = None
+
+        def step_device(self):
+            c = self.ctx
+            c.check(c.lib.lnr_apxmap_batch_device(c.h, index.h, feats.h, C.byref(prm), n_reads, C.c_void_p(bases_t.data_ptr()), offs_c,
+                                                  C.c_void_p(self.cords_dev.data_ptr()), C.c_void_p(self.coff_dev.data_ptr()), cap,
+                                                  C.byref(self.ntot)))
+
+        def step_host(self):
+            self.last = lb.apx_map_batch(self.ctx, index, feats, bases_np, offs, preset=1, cords_out=self.cords_np, cords_off_out=self.coff_np)
+
+    streams = [Stream(c) for c in ctxs]
+
+    def run_steps(kind, k):
+        """k steps in total, dealt round-robin to the host threads; returns wall seconds (barrier + sync both sides)"""
+        per = [k // n_str + (1 if i < k % n_str else 0) for i in range(n_str)]
+
+        def work(st, n):
+            for _ in range(n):
+                getattr(st, kind)()
+        barrier()
+        t0 = time.time()
+        if n_str == 1:
+            work(streams[0], per[0])
+        else:
+            th = [threading.Thread(target=work, args=(streams[i], per[i])) for i in range(n_str) if per[i]]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        torch.cuda.synchronize()
+        barrier()
+        return time.time() - t0
 
     # ---- timed region: device-resident inputs
-    ctx.set_profiling(False)
-    for _ in range(args.warmup):
-        step_device()
-    ctx.set_profiling(True)
-    ctx.reset_kernel_times()
-    launches0 = 0
+    for c in ctxs:
+        c.set_profiling(False)
+    run_steps("step_device", args.warmup * n_str)
+    for c in ctxs:
+        c.set_profiling(True)
+        c.reset_kernel_times()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    for _ in range(args.steps):
-        step_device()
-    torch.cuda.synchronize()
-    barrier()
-    dt = max_over_ranks(time.time() - t0)
+    dt = max_over_ranks(run_steps("step_device", args.steps))
     sampler.stop_flag = True
-    kt = ctx.kernel_times()
+    kt = {}
+    for c in ctxs:
+        for k, v in c.kernel_times().items():
+            a = kt.get(k, (0.0, 0))
+            kt[k] = (a[0] + v[0], a[1] + v[1])
     counters = ctx.counters()
     stage_cycles = ctx.stage_cycles()
-    n_cords = int(ntot.value)
+    n_cords = int(streams[0].ntot.value)
     value = world * n_reads * args.steps / dt
     # ---- end to end through the host-buffer call
-    ctx.set_profiling(False)
-    step_host()
-    barrier()
-    t0 = time.time()
-    for _ in range(args.steps):
-        c_host, _ = step_host()
-    torch.cuda.synchronize()
-    barrier()
-    dt_e2e = max_over_ranks(time.time() - t0)
+    for c in ctxs:
+        c.set_profiling(False)
+    run_steps("step_host", n_str)
+    dt_e2e = max_over_ranks(run_steps("step_host", args.steps))
     e2e_value = world * n_reads * args.steps / dt_e2e
+    c_host = streams[0].last[0]
     d2h = int(len(c_host) * 8 + (n_reads + 1) * 8)
     sampler.join(timeout=2)
 

@@ -14,7 +14,10 @@
 //   k_scan_*                          device-wide exclusive scan (reduce / spine / apply), fused bucket omission
 //   k_idx_sort_buckets                ascending order inside each bucket
 //   k_seed_prep / k_seed_count / k_seed_fill   per-read seeding, one thread per sample, exact-size output
-//   k_map_primary / k_map_remap       warp-per-read pipeline (lnr_pipeline.h), persistent warps + atomic queue
+//   k_map_hits                        warp per seeding task (lnr_pipeline.h: filter, sorts, chaining DP, traceback, hit blocks),
+//                                     persistent warps + atomic queue, longest reads first
+//   k_map_extend                      window extension, one THREAD per read (32 reads in lockstep per warp)
+//   k_map_finish                      warp per read: clean / gaps / re-map decision / cord-block chaining
 //   k_gather_cords                    per-read cords -> caller's concatenated layout
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -77,9 +80,10 @@ struct lnr_ctx
     uint64_t stage_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order;
+    DevBuf remap_list, order, task_nhits;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
+    int extend_group = 32;
     size_t arena_bytes_per_warp = 2u << 20;
 };
 
@@ -629,6 +633,7 @@ struct MapArgs
     u32 * bins; u8 * arena; u64 arena_per_warp;
     u32 * queue;                                       // atomic work counter
     const u32 * order;                                 // reads sorted by length, longest first (tail latency)
+    u32 * task_nhits;                                  // hits per task after stage 1 (0xffffffff = scratch exhausted)
     float stop_ratio;
     unsigned long long * counters;
     // optional debug
@@ -679,110 +684,51 @@ __device__ __noinline__ int finish_read(const Warp & w, Arena & ar, u64 L, u64 *
     return 0;
 }
 
-__global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
+// ---- stage 1: hits. One warp per seeding task (primary pass: task r = read r; re-map pass: one task per gap).
+// Everything of apxMap_ up to and including _filterHits; the hits replace the task's anchors in A.
+__global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass)
 {
     __shared__ u32 s_hist[4][256];
-    Warp w = {(int)(threadIdx.x & 31), 32};
+    Warp w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
     u32 wid = threadIdx.x >> 5;
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
     u32 * bins = a.bins + (u64)gw * kNumBins;
     PipeCounters cnt;
     memset(&cnt, 0, sizeof cnt);
-    u64 c_cords = 0;
     while (true)
     {
-        u32 r = 0;
-        if (w.lane == 0) r = atomicAdd(a.queue, 1u);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= a.n_reads) break;
-        r = a.order[r];
+        u32 q = 0;
+        if (w.lane == 0) q = atomicAdd(a.queue, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= a.n_tasks) break;
+        u32 ti = remap_pass ? q : a.order[q];          // primary: longest reads first
+        const SeedTask t = a.tasks[ti];
+        u32 r = t.read;
         u64 L = a.read_off[r + 1] - a.read_off[r];
-        ReadSlot slot = {0, 0, 0, 0};
+        if (w.lane == 0) a.task_nhits[ti] = 0;
+        if (L <= (u64)kMinReadLen) continue;            // mapper.cpp:440
         long long t_read = LNR_CLOCK();
-        if (L > (u64)kMinReadLen)                        // mapper.cpp:440
-        {
-            PipeIn in;
-            fill_pipe_in(a, r, in);
-            // primary task of read r is task r
-            const SeedTask t = a.tasks[r];
-            u64 s0 = t.sample0, s1 = s0 + t.n_samples;
-            u64 base = a.aoff[s0] + r;
-            int n = (int)(a.aoff[s1] - a.aoff[s0]) + 1;
-            u64 * cords = a.cords + a.cords_base[r];
-            int cap = (int)(a.cords_base[r + 1] - a.cords_base[r]);
-            int nc = 0;
-            u64 * dh = a.dbg_hits ? a.dbg_hits + a.dbg_hoff[r] : (u64 *)0;
-            u32 dcap = a.dbg_hits ? (u32)(a.dbg_hoff[r + 1] - a.dbg_hoff[r]) : 0;
-            int rc = phase_map(w, ar, s_hist[wid], bins, in, a.A + base, a.B + base, n, 0, L & kMaskY, 0, cords, nc, cap,
-                               dh, a.dbg_nhits ? a.dbg_nhits + r : (u32 *)0, dcap, cnt);
-            if (a.dbg_c1 && !rc)
-            {
-                for (int i = w.lane; i < nc; i += 32) a.dbg_c1[a.cords_base[r] + i] = cords[i];
-                if (w.lane == 0) a.dbg_nc1[r] = (u32)nc;
-            }
-            int remap = 0, n_sep = 0, n_gaps = 0;
-            Blk * sep = 0;
-            u32 task0 = 0;
-            long long tl = LNR_CLOCK();
-            cnt.t[12]++;
-            if (!rc)
-            {
-                arena_reset(ar);
-                YPair * str_ends = arena_alloc<YPair>(ar, (u64)nc + 2);
-                sep = arena_alloc<Blk>(ar, (u64)nc + 2);
-                int gcap = (int)(L / 1000 + 4);
-                YPair * gaps = arena_alloc<YPair>(ar, (u64)gcap);
-                if (ar.failed) rc = 1;
-                else
-                {
-                    remap = phase_mid_w(w, L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
-                    if (w.lane == 0)
-                    {
-                        if (remap == 1)
-                        {
-                            task0 = atomicAdd(a.n_tasks2, (u32)n_gaps);
-                            if (task0 + (u32)n_gaps > a.tasks2_cap) remap = -1;
-                            else
-                                for (int i = 0; i < n_gaps; i++)
-                                {
-                                    SeedTask t2;
-                                    t2.read = r; t2.str = (u32)(gaps[i].first & kMaskY); t2.end = (u32)gaps[i].second; t2.alpha = 7;
-                                    t2.n_samples = seed_task_samples(t2.str, t2.end, 7);
-                                    t2.bias = 0; t2.kskip = 0; t2.pad = 0; t2.sample0 = 0;
-                                    a.tasks2[task0 + i] = t2;
-                                }
-                        }
-                    }
-                    remap = __shfl_sync(0xffffffffu, remap, 0);
-                    nc = __shfl_sync(0xffffffffu, nc, 0);
-                    n_sep = __shfl_sync(0xffffffffu, n_sep, 0);
-                    n_gaps = __shfl_sync(0xffffffffu, n_gaps, 0);
-                    task0 = __shfl_sync(0xffffffffu, task0, 0);
-                    __syncwarp();
-                    if (remap < 0) rc = 1;
-                }
-            }
-            LNR_LAP(cnt, 9, tl);
-            if (!rc && remap == 0) rc = finish_read(w, ar, L, cords, nc, cap, sep, n_sep, false);
-            LNR_LAP(cnt, 10, tl);
-            slot.n_cords = rc ? 0 : (u32)nc;
-            slot.status = rc ? 2u : (remap == 1 ? 1u : 0u);
-            slot.task0 = task0; slot.n_tasks = remap == 1 ? (u32)n_gaps : 0;
-            if (!rc && remap == 0) c_cords += (u64)nc;
-        }
-        if (w.lane == 0) a.slots[r] = slot;
-        {
-            u64 dt = (u64)(LNR_CLOCK() - t_read);
-            cnt.t[14] += dt;
-            if (dt > cnt.t[13]) cnt.t[13] = dt;
-        }
+        PipeIn in;
+        fill_pipe_in(a, r, in);
+        u64 s0 = t.sample0, s1 = s0 + t.n_samples;
+        u64 base = a.aoff[s0] + ti;
+        int n = (int)(a.aoff[s1] - a.aoff[s0]) + 1;
+        int nc_dummy = 0;
+        u64 * dh = (!remap_pass && a.dbg_hits) ? a.dbg_hits + a.dbg_hoff[r] : (u64 *)0;
+        u32 dcap = dh ? (u32)(a.dbg_hoff[r + 1] - a.dbg_hoff[r]) : 0;
+        int rc = phase_map(w, ar, s_hist[wid], bins, in, a.A + base, a.B + base, n, (u64)t.str, remap_pass ? ((u64)t.end & kMaskY) : (L & kMaskY),
+                           remap_pass ? 1 : 0, (u64 *)0, nc_dummy, 0, dh, dh ? a.dbg_nhits + r : (u32 *)0, dcap, cnt, a.A + base,
+                           a.task_nhits + ti);
+        if (rc && w.lane == 0) a.task_nhits[ti] = 0xffffffffu;   // scratch exhausted
+        if (!remap_pass) cnt.t[12]++;
+        u64 dt = (u64)(LNR_CLOCK() - t_read);
+        cnt.t[14] += dt;
+        if (dt > cnt.t[13]) cnt.t[13] = dt;
     }
     if (w.lane == 0)
     {
         if (cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)cnt.hits);
-        if (cnt.windows) atomicAdd(&a.counters[4], (unsigned long long)cnt.windows);
-        if (c_cords) atomicAdd(&a.counters[5], (unsigned long long)c_cords);
         for (int i = 0; i < 16; i++)
             if (cnt.t[i])
             {
@@ -792,15 +738,69 @@ __global__ void __launch_bounds__(128) k_map_primary(MapArgs a)
     }
 }
 
-// re-map pass (pmpfinder.cpp:2749-2767): reads with status 1; `remap_reads` lists them
-__global__ void __launch_bounds__(128) k_map_remap(MapArgs a, const u32 * __restrict__ remap_reads, u32 n_remap)
+// ---- stage 2: window extension (path_dst_2 + extendWindow), ONE THREAD PER READ. The per-step work (3 candidate
+// windows x 2 scripts x 3 ints) and the control flow are the same for every read, so 32 reads advance in lockstep
+// in one warp; reads are taken in length order so that the lanes of a warp have similar trip counts.
+__global__ void __launch_bounds__(128) k_map_extend(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int group)
 {
-    __shared__ u32 s_hist[4][256];
-    Warp w = {(int)(threadIdx.x & 31), 32};
+    // `group` lanes (power of two <= 32) cooperate on one read: they share the 18 script distances of a window step
+    u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 q = tid / (u32)group;
+    int gl = (int)(tid % (u32)group);
+    unsigned lane32 = threadIdx.x & 31;
+    unsigned gmask = group == 32 ? 0xffffffffu : (((1u << group) - 1u) << (lane32 - (unsigned)gl));
+    PipeCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    long long t0 = LNR_CLOCK();
+    if (q < n_list)
+    {
+        u32 r = read_list[q];
+        u64 L = a.read_off[r + 1] - a.read_off[r];
+        if (L > (u64)kMinReadLen)
+        {
+            Warp w1 = {gl, group, gmask};
+            PipeIn in;
+            fill_pipe_in(a, r, in);
+            ReadSlot slot = a.slots[r];
+            u64 * cords = a.cords + a.cords_base[r];
+            int cap = (int)(a.cords_base[r + 1] - a.cords_base[r]);
+            int nc = remap_pass ? (int)slot.n_cords : 0;
+            u32 t_first = remap_pass ? slot.task0 : r, t_cnt = remap_pass ? slot.n_tasks : 1;
+            bool ok = remap_pass ? slot.status == 1 : true;
+            for (u32 g = 0; g < t_cnt && ok; g++)
+            {
+                u32 ti = t_first + g;
+                const SeedTask t = a.tasks[ti];
+                u32 nh = a.task_nhits[ti];
+                if (nh == 0xffffffffu) { ok = false; break; }
+                u64 base = a.aoff[t.sample0] + ti;
+                ok = path_dst_2(w1, in, a.A + base, (int)nh, cords, nc, cap, (u64)t.str, remap_pass ? ((u64)t.end & kMaskY) : (L & kMaskY), cnt);
+            }
+            if (gl == 0)
+            {
+                slot.n_cords = ok ? (u32)nc : 0;
+                if (!ok) slot.status = 2;
+                a.slots[r] = slot;
+            }
+        }
+    }
+    cnt.t[8] = (u64)(LNR_CLOCK() - t0);
+    u64 wn = gl == 0 ? cnt.windows : 0, tc = cnt.t[8];
+    for (int o = 16; o; o >>= 1) { wn += __shfl_xor_sync(0xffffffffu, wn, o); tc = max(tc, __shfl_xor_sync(0xffffffffu, tc, o)); }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (wn) atomicAdd(&a.counters[4], (unsigned long long)wn);
+        atomicAdd(&a.counters[24 + 8], (unsigned long long)tc);
+    }
+}
+
+// ---- stage 3: clean / gaps / re-map decision / cord-block chaining, one warp per read
+__global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass)
+{
+    Warp w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
     u32 wid = threadIdx.x >> 5;
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
-    u32 * bins = a.bins + (u64)gw * kNumBins;
     PipeCounters cnt;
     memset(&cnt, 0, sizeof cnt);
     u64 c_cords = 0;
@@ -809,36 +809,74 @@ __global__ void __launch_bounds__(128) k_map_remap(MapArgs a, const u32 * __rest
         u32 q = 0;
         if (w.lane == 0) q = atomicAdd(a.queue, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= n_remap) break;
-        u32 r = remap_reads[q];
-        ReadSlot slot = a.slots[r];
+        if (q >= n_list) break;
+        u32 r = read_list[q];
         u64 L = a.read_off[r + 1] - a.read_off[r];
-        PipeIn in;
-        fill_pipe_in(a, r, in);
+        ReadSlot slot = a.slots[r];
+        if (L <= (u64)kMinReadLen) { slot.n_cords = 0; slot.status = 0; slot.task0 = 0; slot.n_tasks = 0; if (w.lane == 0) a.slots[r] = slot; continue; }
+        if (slot.status == 2) continue;
         u64 * cords = a.cords + a.cords_base[r];
         int cap = (int)(a.cords_base[r + 1] - a.cords_base[r]);
         int nc = (int)slot.n_cords;
         int rc = 0;
-        for (u32 g = 0; g < slot.n_tasks && !rc; g++)
+        long long tl = LNR_CLOCK();
+        if (!remap_pass)
         {
-            u32 ti = slot.task0 + g;
-            const SeedTask t = a.tasks[ti];
-            u64 s0 = t.sample0, s1 = s0 + t.n_samples;
-            u64 base = a.aoff[s0] + ti;
-            int n = (int)(a.aoff[s1] - a.aoff[s0]) + 1;
-            rc = phase_map(w, ar, s_hist[wid], bins, in, a.A + base, a.B + base, n, (u64)t.str, (u64)t.end & kMaskY, 1, cords, nc, cap,
-                           (u64 *)0, (u32 *)0, 0, cnt);
+            if (a.dbg_c1)
+            {
+                for (int i = w.lane; i < nc; i += 32) a.dbg_c1[a.cords_base[r] + i] = cords[i];
+                if (w.lane == 0) a.dbg_nc1[r] = (u32)nc;
+            }
+            int remap = 0, n_sep = 0, n_gaps = 0;
+            u32 task0 = 0;
+            arena_reset(ar);
+            YPair * str_ends = arena_alloc<YPair>(ar, (u64)nc + 2);
+            Blk * sep = arena_alloc<Blk>(ar, (u64)nc + 2);
+            int gcap = (int)(L / 1000 + 4);
+            YPair * gaps = arena_alloc<YPair>(ar, (u64)gcap);
+            if (ar.failed) rc = 1;
+            else
+            {
+                remap = phase_mid_w(w, L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
+                if (w.lane == 0 && remap == 1)
+                {
+                    task0 = atomicAdd(a.n_tasks2, (u32)n_gaps);
+                    if (task0 + (u32)n_gaps > a.tasks2_cap) remap = -1;
+                    else
+                        for (int i = 0; i < n_gaps; i++)
+                        {
+                            SeedTask t2;
+                            t2.read = r; t2.str = (u32)(gaps[i].first & kMaskY); t2.end = (u32)gaps[i].second; t2.alpha = 7;
+                            t2.n_samples = seed_task_samples(t2.str, t2.end, 7);
+                            t2.bias = 0; t2.kskip = 0; t2.pad = 0; t2.sample0 = 0;
+                            a.tasks2[task0 + i] = t2;
+                        }
+                }
+                remap = __shfl_sync(0xffffffffu, remap, 0);
+                task0 = __shfl_sync(0xffffffffu, task0, 0);
+                __syncwarp();
+                if (remap < 0) rc = 1;
+            }
+            LNR_LAP(cnt, 9, tl);
+            if (!rc && remap == 0) rc = finish_read(w, ar, L, cords, nc, cap, sep, n_sep, false);
+            LNR_LAP(cnt, 10, tl);
+            slot.n_cords = rc ? 0 : (u32)nc;
+            slot.status = rc ? 2u : (remap == 1 ? 1u : 0u);
+            slot.task0 = task0; slot.n_tasks = remap == 1 ? (u32)n_gaps : 0;
+            if (!rc && remap == 0) c_cords += (u64)nc;
         }
-        if (!rc) rc = finish_read(w, ar, L, cords, nc, cap, (Blk *)0, 0, true);
-        slot.n_cords = rc ? 0 : (u32)nc;
-        slot.status = rc ? 2u : 0u;
-        if (!rc) c_cords += (u64)nc;
+        else
+        {
+            rc = finish_read(w, ar, L, cords, nc, cap, (Blk *)0, 0, true);
+            LNR_LAP(cnt, 10, tl);
+            slot.n_cords = rc ? 0 : (u32)nc;
+            slot.status = rc ? 2u : 0u;
+            if (!rc) c_cords += (u64)nc;
+        }
         if (w.lane == 0) a.slots[r] = slot;
     }
     if (w.lane == 0)
     {
-        if (cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)cnt.hits);
-        if (cnt.windows) atomicAdd(&a.counters[4], (unsigned long long)cnt.windows);
         if (c_cords) atomicAdd(&a.counters[5], (unsigned long long)c_cords);
         for (int i = 0; i < 16; i++) if (cnt.t[i]) atomicAdd(&a.counters[24 + i], (unsigned long long)cnt.t[i]);
     }
@@ -902,6 +940,7 @@ int lnr_ctx_create(int device, lnr_ctx ** out)
     cudaGetDeviceProperties(&prop, device);
     ctx->n_sm = prop.multiProcessorCount;
     if (const char * e = getenv("LNR_MAP_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->map_ctas_per_sm = v; }
+    if (const char * e = getenv("LNR_EXTEND_GROUP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->extend_group = v; }
     if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LNR_E_CUDA; }
     *out = ctx;
@@ -917,7 +956,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits})
         b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1367,9 +1406,21 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     a.counters = d_counters;
     if (dbg && dbg->hits_off) { a.dbg_hits = ctx->dbg_hits.as<u64>(); a.dbg_hoff = ctx->dbg_hoff.as<u64>(); a.dbg_nhits = ctx->dbg_nhits.as<u32>(); }
     if (dbg && dbg->cords1_off) { a.dbg_c1 = ctx->dbg_c1.as<u64>(); a.dbg_nc1 = ctx->dbg_nc1.as<u32>(); }
+    CK(ctx->task_nhits.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
+    a.task_nhits = ctx->task_nhits.as<u32>();
+    CK(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_reads * sizeof(ReadSlot), ctx->stream));
     {
-        LaunchScope ls(ctx, "k_map_primary");
-        k_map_primary<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a);
+        LaunchScope ls(ctx, "k_map_hits");
+        k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 0);
+    }
+    {
+        LaunchScope ls(ctx, "k_map_extend");
+        k_map_extend<<<(u32)(((u64)n_reads * ctx->extend_group + 127) / 128), 128, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0, ctx->extend_group);
+    }
+    CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_map_finish");
+        k_map_finish<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0);
     }
     CK(cudaGetLastError());
     // ---- re-map pass
@@ -1401,8 +1452,17 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         a.dbg_hits = nullptr; a.dbg_c1 = nullptr; a.dbg_nhits = nullptr; a.dbg_nc1 = nullptr;
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
         {
-            LaunchScope ls(ctx, "k_map_remap");
-            k_map_remap<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size());
+            LaunchScope ls(ctx, "k_map_hits_remap");
+            k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 1);
+        }
+        {
+            LaunchScope ls(ctx, "k_map_extend_remap");
+            k_map_extend<<<(u32)(((u64)remap_reads.size() * ctx->extend_group + 127) / 128), 128, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size(), 1, ctx->extend_group);
+        }
+        CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_map_finish_remap");
+            k_map_finish<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size(), 1);
         }
         CK(cudaGetLastError());
     }

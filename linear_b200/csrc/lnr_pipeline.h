@@ -563,35 +563,31 @@ LNR_HD int prefilter_chains2(u64 * hits, int n_hits, Blk * sep, int nb, Blk * tm
         strs[i] = sep[i].first;
     }
     gnu_sort(cuts, 2 * nb, [hits, mask](const u64 & a, const u64 & b) { return cord_y(hits[a & ~mask]) < cord_y(hits[b & ~mask]); });
+    // The reference scans every block linearly for every cut (pmpfinder.cpp:2398-2437). y is strictly ascending
+    // inside a block (chains need dy >= 5), so the first k with y >= cuty is found by binary search, and a block
+    // that ends below the cut cannot produce a piece -- same pieces, same order, without the quadratic rescans.
     int nt = 0;
     for (int i = 0; i < 2 * nb; i++)
     {
+        const bool is_last = (cuts[i] & mask) != 0;
         u64 cuty = cord_y(hits[cuts[i] & ~mask]);
         for (int j = 0; j < nb && strs[j] < (u64)n_hits; j++)
         {
+            if (strs[j] >= sep[j].second) continue;                       // block used up: the k loop is empty
             if (cuty < cord_y(hits[strs[j]])) continue;
-            for (u64 k = strs[j]; k < sep[j].second; k++)
+            if (cord_y(hits[sep[j].second - 1]) < cuty) continue;          // no k with y >= cuty
+            u64 lo = strs[j], hi = sep[j].second - 1;                     // first k in [lo, hi] with y >= cuty
+            while (lo < hi)
             {
-                u64 yk = cord_y(hits[k]);
-                u64 up;
-                if (cuts[i] & mask)
-                {
-                    if (yk == cuty) up = k + 1;
-                    else if (yk > cuty) up = k;
-                    else continue;
-                }
-                else
-                {
-                    if (yk >= cuty) up = k;
-                    else continue;
-                }
-                if (strs[j] != up)
-                {
-                    if (nt >= cap) return -1;
-                    tmp[nt].first = (u32)strs[j]; tmp[nt].second = (u32)up; nt++;
-                    strs[j] = up;
-                }
-                break;
+                u64 mid = (lo + hi) >> 1;
+                if (cord_y(hits[mid]) >= cuty) hi = mid; else lo = mid + 1;
+            }
+            u64 up = (is_last && cord_y(hits[lo]) == cuty) ? lo + 1 : lo;
+            if (strs[j] != up)
+            {
+                if (nt >= cap) return -1;
+                tmp[nt].first = (u32)strs[j]; tmp[nt].second = (u32)up; nt++;
+                strs[j] = up;
             }
         }
     }
@@ -1130,10 +1126,14 @@ LNR_PIPE int gather_blocks_w(const Warp & w, u64 * cords, int n, YPair * str_end
 // ----------------------------------------------------------------------------------------------------
 LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, const PipeIn & in, u64 * A, u64 * B, int n,
                        u64 read_str, u64 read_end, int score_type, u64 * cords, int & n_cords, int cords_cap,
-                       u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt)
+                       u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt,
+                       u64 * hits_out = (u64 *)0, u32 * n_hits_out = (u32 *)0)
 {
+    // hits_out != null: stop after _filterHits and hand the hits over (it may alias A; capacity n) -- the window
+    // extension then runs in its own thread-per-read kernel. hits_out == null: run path_dst_2 here.
     arena_reset(ar);
     long long tl = LNR_CLOCK();
+    if (n_hits_out && w.lane == 0) *n_hits_out = 0;
     if (dbg_nhits && w.lane == 0) *dbg_nhits = 1;
     if (dbg_hits && w.lane == 0 && dbg_hits_cap > 0) dbg_hits[0] = kFlagEnd;
     if (w.lane == 0) A[0] = 0;               // Anchors::init(1) base.cpp:272
@@ -1229,11 +1229,14 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     if (ar.failed) return 1;
     u64 * H = hits;
     int err = 0;
-    if (w.lane == 0)
+    int nb0;
     {
         int dummy = 0;
-        int nb = gather_blocks(hits, n_hits, (YPair *)0, dummy, sep, 0, 1, (u32)n_hits, in.L, 600, 0, 0);
-        nb = prefilter_chains2(hits, n_hits, sep, nb, sep_tmp, n_hits + 1, cuts, strs);
+        nb0 = gather_blocks_w(w, hits, n_hits, (YPair *)0, dummy, sep, in.L, 600, 0, 0);
+    }
+    if (w.lane == 0)
+    {
+        int nb = prefilter_chains2(hits, n_hits, sep, nb0, sep_tmp, n_hits + 1, cuts, strs);
         if (nb < 0) err = 1;
         else
         {
@@ -1281,6 +1284,14 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     }
     n_hits = wbcast(w, n_hits, 0);
     wsync(w);
+    if (hits_out)
+    {
+        for (int i = w.lane; i < n_hits; i += w.nl) hits_out[i] = H[i];
+        if (w.lane == 0) *n_hits_out = (u32)n_hits;
+        wsync(w);
+        LNR_LAP(cnt, 7, tl);
+        return 0;
+    }
     int ok = path_dst_2(w, in, H, n_hits, cords, n_cords, cords_cap, read_str, read_end, cnt) ? 1 : 0;
     LNR_LAP(cnt, 8, tl);
     return ok ? 0 : 1;

@@ -17,13 +17,15 @@ namespace lnr {
 
 struct Warp
 {
-    int lane;   // 0..nl-1
-    int nl;     // 32 on the device, 1 on the host
+    int lane;        // 0..nl-1
+    int nl;          // lanes that cooperate on one read: 32 (a warp), a power-of-two sub-warp group, or 1
+    unsigned mask;   // member mask of the group inside its hardware warp (device only)
 };
 
 #ifdef __CUDACC__
 static const unsigned kFull = 0xffffffffu;
-LNR_PIPE_INL void wsync(const Warp &) { __syncwarp(); }
+// a Warp with nl == 1 is a single thread running the warp-uniform code on its own (thread-per-read kernels)
+LNR_PIPE_INL void wsync(const Warp & w) { if (w.nl != 1) __syncwarp(w.mask); }
 LNR_PIPE_INL u32 wballot(const Warp &, bool p) { return __ballot_sync(kFull, p); }
 template <class T> LNR_PIPE_INL T wbcast(const Warp &, T v, int src) { return __shfl_sync(kFull, v, src); }
 LNR_PIPE_INL u64 wbcast64(const Warp &, u64 v, int src)
@@ -31,7 +33,12 @@ LNR_PIPE_INL u64 wbcast64(const Warp &, u64 v, int src)
     u32 lo = __shfl_sync(kFull, (u32)v, src), hi = __shfl_sync(kFull, (u32)(v >> 32), src);
     return ((u64)hi << 32) | lo;
 }
-LNR_PIPE_INL int wsum(const Warp &, int v) { return __reduce_add_sync(kFull, v); }
+LNR_PIPE_INL int wsum(const Warp & w, int v)
+{
+    if (w.nl == 32) return __reduce_add_sync(kFull, v);
+    for (int o = w.nl >> 1; o; o >>= 1) v += __shfl_xor_sync(w.mask, v, o);   // sub-warp group (xor stays inside an aligned group)
+    return v;
+}
 LNR_PIPE_INL u64 wor64(const Warp &, u64 v)
 {
     for (int o = 16; o; o >>= 1)

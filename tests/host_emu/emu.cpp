@@ -137,7 +137,7 @@ struct ReadRun
 // the per-read orchestration of kernels A and B (apxMap, pmpfinder.cpp:2709)
 int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std::vector<u64> * hits_out, int stop_after_first)
 {
-    Warp w = {0, 1};
+    Warp w = {0, 1, 1u};
     SeqAcc acc = {read, (i64)L};
     RcAcc rc = {read, (i64)L};
     ReadRun R;
@@ -159,9 +159,12 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
     R.B.assign(R.A.size(), 0);
     std::vector<u64> dbg(R.A.size() + 2);
     u32 ndbg = 0;
+    // stage 1 (k_map_hits) hands the hits over in A, stage 2 (k_map_extend) runs the window extension
+    u32 nh = 0;
     if (phase_map(w, ar, R.hist, E.bins.data(), in, R.A.data(), R.B.data(), (int)R.A.size(), 0, L & kMaskY, 0,
-                  R.cords.data(), nc, cap, dbg.data(), &ndbg, (u32)dbg.size(), cnt))
+                  R.cords.data(), nc, cap, dbg.data(), &ndbg, (u32)dbg.size(), cnt, R.A.data(), &nh))
         return 1;
+    if (!path_dst_2(w, in, R.A.data(), (int)nh, R.cords.data(), nc, cap, 0, L & kMaskY, cnt)) return 1;
     if (hits_out) hits_out->assign(dbg.begin(), dbg.begin() + ndbg);
     if (stop_after_first) { cords_out.assign(R.cords.begin(), R.cords.begin() + nc); return 0; }
     arena_reset(ar);
@@ -181,8 +184,9 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
             seed(E, acc, t2, R.A);
             R.B.assign(R.A.size(), 0);
             if (phase_map(w, ar, R.hist, E.bins.data(), in, R.A.data(), R.B.data(), (int)R.A.size(), gv[i].first & kMaskY,
-                          gv[i].second & kMaskY, 1, R.cords.data(), nc, cap, 0, 0, 0, cnt))
+                          gv[i].second & kMaskY, 1, R.cords.data(), nc, cap, 0, 0, 0, cnt, R.A.data(), &nh))
                 return 1;
+            if (!path_dst_2(w, in, R.A.data(), (int)nh, R.cords.data(), nc, cap, gv[i].first & kMaskY, gv[i].second & kMaskY, cnt)) return 1;
         }
         sepv.assign(nc + 2, Blk());
         int dummy = 0;
