@@ -78,6 +78,7 @@ struct lnr_ctx
         dbg_c1, dbg_nc1, read_meta;
     uint64_t counters[8] = {0};
     uint64_t stage_cycles[16] = {0};
+    uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
     DevBuf remap_list, order, task_nhits;
@@ -684,6 +685,33 @@ __device__ __noinline__ int finish_read(const Warp & w, Arena & ar, u64 L, u64 *
     return 0;
 }
 
+// Processing order of the primary pass: tasks with the most raw anchors first (their hits stage is the longest, so
+// they must not start last). Counting sort into 132 quarter-octave buckets, one CTA.
+__global__ void __launch_bounds__(1024) k_order_tasks(const SeedTask * __restrict__ tasks, u32 n_tasks, const u64 * __restrict__ aoff,
+                                                      u32 * __restrict__ order)
+{
+    __shared__ u32 s_cnt[136];
+    for (int i = threadIdx.x; i < 136; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    auto bucket = [&](u32 t) -> int {
+        u64 n = aoff[tasks[t].sample0 + tasks[t].n_samples] - aoff[tasks[t].sample0];
+        if (n == 0) return 0;
+        int lg = 63 - __clzll((long long)n);
+        int frac = lg >= 2 ? (int)((n >> (lg - 2)) & 3) : 0;
+        int b = lg * 4 + frac + 1;
+        return b > 135 ? 135 : b;
+    };
+    for (u32 t = threadIdx.x; t < n_tasks; t += blockDim.x) atomicAdd(&s_cnt[bucket(t)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        u32 run = 0;
+        for (int b = 135; b >= 0; b--) { u32 c = s_cnt[b]; s_cnt[b] = run; run += c; }
+    }
+    __syncthreads();
+    for (u32 t = threadIdx.x; t < n_tasks; t += blockDim.x) order[atomicAdd(&s_cnt[bucket(t)], 1u)] = t;
+}
+
 // ---- stage 1: hits. One warp per seeding task (primary pass: task r = read r; re-map pass: one task per gap).
 // Everything of apxMap_ up to and including _filterHits; the hits replace the task's anchors in A.
 __global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass)
@@ -709,6 +737,7 @@ __global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass)
         if (w.lane == 0) a.task_nhits[ti] = 0;
         if (L <= (u64)kMinReadLen) continue;            // mapper.cpp:440
         long long t_read = LNR_CLOCK();
+        PipeCounters before = cnt;
         PipeIn in;
         fill_pipe_in(a, r, in);
         u64 s0 = t.sample0, s1 = s0 + t.n_samples;
@@ -722,6 +751,8 @@ __global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass)
                            a.task_nhits + ti);
         if (rc && w.lane == 0) a.task_nhits[ti] = 0xffffffffu;   // scratch exhausted
         if (!remap_pass) cnt.t[12]++;
+        if (!remap_pass && q == 0 && w.lane == 0)   // the longest read: its own stage profile (tail analysis)
+            for (int i = 0; i < 12; i++) a.counters[56 + i] = (unsigned long long)(cnt.t[i] - before.t[i]);
         u64 dt = (u64)(LNR_CLOCK() - t_read);
         cnt.t[14] += dt;
         if (dt > cnt.t[13]) cnt.t[13] = dt;
@@ -1231,7 +1262,7 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     CK(ctx->sample_info.reserve((size_t)(n_samples + 1) * sizeof(u64)));
     CK(ctx->sample_cnt.reserve((size_t)(n_samples + STILE + 1) * sizeof(u32)));
     CK(aoff_buf.reserve((size_t)(n_samples + STILE + 1) * sizeof(u64)));
-    CK(ctx->misc.reserve(512));
+    CK(ctx->misc.reserve(1024));
     u64 * d_total = ctx->misc.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
     {
@@ -1276,7 +1307,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     // ---- host-side layout from the read lengths
     std::vector<SeedTask> tasks(n_reads);
     std::vector<u64> foff(n_reads + 1), cbase(n_reads + 1), hoff(n_reads + 1);
-    std::vector<u32> ftile(n_reads + 1), order(n_reads);
+    std::vector<u32> ftile(n_reads + 1);
     u64 n_samples = 0, nf_tot = 0, c_tot = 0;
     u32 n_ftiles = 0;
     for (uint32_t r = 0; r < n_reads; r++)
@@ -1298,8 +1329,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         c_tot += L > (u64)kMinReadLen ? 16 + L / 4 : 0;
     }
     foff[n_reads] = nf_tot; ftile[n_reads] = n_ftiles; cbase[n_reads] = c_tot;
-    for (uint32_t r = 0; r < n_reads; r++) order[r] = r;
-    std::stable_sort(order.begin(), order.end(), [&](u32 x, u32 y) { return h_read_off[x + 1] - h_read_off[x] > h_read_off[y + 1] - h_read_off[y]; });
+
     const u64 total_bases = h_read_off[n_reads];
     // ---- uploads
     CK(ctx->read_off.reserve((n_reads + 1) * sizeof(u64)));
@@ -1313,14 +1343,14 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(ctx->slots.reserve((size_t)n_reads * sizeof(ReadSlot)));
     CK(ctx->ncords.reserve((size_t)(n_reads + STILE + 1) * sizeof(u32)));
     CK(ctx->out_off.reserve((size_t)(n_reads + STILE + 1) * sizeof(u64)));
-    CK(ctx->misc.reserve(512));
+    CK(ctx->misc.reserve(1024));
     CK(cudaMemcpyAsync(ctx->read_off.p, h_read_off, (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), n_reads * sizeof(SeedTask), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->foff.p, foff.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->ftile.p, ftile.data(), (n_reads + 1) * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->cords_base.p, cbase.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->misc.p, 0, 512, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->order.p, order.data(), (size_t)n_reads * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->misc.p, 0, 1024, ctx->stream));
+
     const u64 * d_read_off = ctx->read_off.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
     u32 * d_queue = (u32 *)(ctx->misc.as<u64>() + 20);
@@ -1406,6 +1436,10 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     a.counters = d_counters;
     if (dbg && dbg->hits_off) { a.dbg_hits = ctx->dbg_hits.as<u64>(); a.dbg_hoff = ctx->dbg_hoff.as<u64>(); a.dbg_nhits = ctx->dbg_nhits.as<u32>(); }
     if (dbg && dbg->cords1_off) { a.dbg_c1 = ctx->dbg_c1.as<u64>(); a.dbg_nc1 = ctx->dbg_nc1.as<u32>(); }
+    {
+        LaunchScope ls(ctx, "k_order_tasks");
+        k_order_tasks<<<1, 1024, 0, ctx->stream>>>(ctx->tasks.as<SeedTask>(), n_reads, aoff.as<u64>(), ctx->order.as<u32>());
+    }
     CK(ctx->task_nhits.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
     a.task_nhits = ctx->task_nhits.as<u32>();
     CK(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_reads * sizeof(ReadSlot), ctx->stream));
@@ -1482,7 +1516,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
                                                                                        ctx->ncords.as<u32>(), d_off, n_reads, d_out, out_cap);
     }
     CK(cudaGetLastError());
-    u64 h_misc[64];
+    u64 h_misc[128];
     CK(cudaMemcpyAsync(h_misc, ctx->misc.p, sizeof h_misc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     u64 total_cords = h_misc[0];
@@ -1496,6 +1530,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     ctx->counters[6] = total_bases;
     ctx->counters[7] = n_tasks2;
     for (int i = 0; i < 16; i++) ctx->stage_cycles[i] = h_misc[8 + 24 + i];
+    for (int i = 0; i < 12; i++) ctx->longest_cycles[i] = h_misc[8 + 56 + i];
     if (n_cords_total) *n_cords_total = total_cords;
     if (dbg && dbg->hits_off)
     {
@@ -1576,6 +1611,7 @@ int lnr_last_batch_stage_cycles(lnr_ctx * ctx, uint64_t cycles[16])
 {
     if (!ctx || !cycles) return LNR_E_ARG;
     for (int i = 0; i < 16; i++) cycles[i] = ctx->stage_cycles[i];
+    if (getenv("LNR_LONGEST_PROFILE")) for (int i = 0; i < 12; i++) cycles[i] = ctx->longest_cycles[i];
     return LNR_OK;
 }
 

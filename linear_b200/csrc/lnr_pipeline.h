@@ -662,17 +662,14 @@ LNR_HD int chain_blocks_base(const u64 * recs, const Blk * sep, const i32 * sep_
 }
 
 // _filterBlocksHits (cluster_util.cpp:633): major chain + up to 4 optional chains > 0.8 * len.
-// Writes the new hit list (without header) into out; returns its length.
-LNR_HD int filter_blocks_hits(const Blk * el, const int * chain_off, int n_chains, const u64 * hits, u64 * out)
+// Plans the new hit list (without header): which chains survive. keep_chain[c] = 1 for the chains copied, in order.
+// Returns the number of hits that will be written.
+LNR_HD int filter_blocks_hits_plan(const Blk * el, const int * chain_off, int n_chains, u8 * keep_chain)
 {
-    int no = 0;
     u64 len_cur = 0;
-    for (int i = chain_off[0]; i < chain_off[1]; i++)
-    {
-        for (u32 j = el[i].first; j < el[i].second; j++) out[no++] = hits[j] & ~kFlagEnd;
-        len_cur += el[i].second - el[i].first;
-    }
-    out[no - 1] |= kFlagEnd;
+    for (int i = chain_off[0]; i < chain_off[1]; i++) len_cur += el[i].second - el[i].first;
+    int no = (int)len_cur;
+    keep_chain[0] = 1;
     float major_bound = (float)(0.8 * (double)len_cur);
     u32 major_limit = 5, major_n = 1;
     for (int c = 1; c < n_chains; c++)
@@ -680,16 +677,33 @@ LNR_HD int filter_blocks_hits(const Blk * el, const int * chain_off, int n_chain
         len_cur = 0;
         for (int i = chain_off[c]; i < chain_off[c + 1]; i++) len_cur += el[i].second - el[i].first;
         // (the reference's third branch needs len_cur == 0, impossible for non-empty blocks)
-        if (major_n < major_limit && (float)len_cur > major_bound)
-        {
-            ++major_n;
-            for (int i = chain_off[c]; i < chain_off[c + 1]; i++)
-                for (u32 k = el[i].first; k < el[i].second; k++) out[no++] = hits[k] & ~kFlagEnd;
-            out[no - 1] |= kFlagEnd;
-        }
-        out[no - 1] |= kFlagEnd;
+        keep_chain[c] = 0;
+        if (major_n < major_limit && (float)len_cur > major_bound) { ++major_n; keep_chain[c] = 1; no += (int)len_cur; }
     }
     return no;
+}
+// copies the planned chains: every hit loses its end flag except the last of each chain. All lanes.
+LNR_PIPE void filter_blocks_hits_copy(const Warp & w, const Blk * el, const int * chain_off, int n_chains, const u8 * keep_chain,
+                                      const u64 * hits, u64 * out)
+{
+    int no = 0;
+    for (int c = 0; c < n_chains; c++)
+    {
+        if (!keep_chain[c]) continue;
+        for (int i = chain_off[c]; i < chain_off[c + 1]; i++)
+        {
+            int b = (int)el[i].first, e = (int)el[i].second;
+            bool last_piece = i == chain_off[c + 1] - 1;
+            for (int j = b + w.lane; j < e; j += w.nl)
+            {
+                u64 h = hits[j] & ~kFlagEnd;
+                if (last_piece && j == e - 1) h |= kFlagEnd;
+                out[no + (j - b)] = h;
+            }
+            no += e - b;
+        }
+    }
+    wsync(w);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -1234,6 +1248,8 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
         int dummy = 0;
         nb0 = gather_blocks_w(w, hits, n_hits, (YPair *)0, dummy, sep, in.L, 600, 0, 0);
     }
+    u8 * keep_chain = keep;            // reuse: `keep` is only needed later by the hit window filter
+    int nch = 0;
     if (w.lane == 0)
     {
         int nb = prefilter_chains2(hits, n_hits, sep, nb0, sep_tmp, n_hits + 1, cuts, strs);
@@ -1241,20 +1257,26 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
         else
         {
             for (int i = 0; i < nb; i++) sep_score[i] = hits_score[sep[i].first] - hits_score[sep[i].second - 1];
-            int nch = chain_blocks_base(hits, sep, sep_score, nb, bs, in.L, 0, 0, 1);
-            if (nch > 0) { n_hits = filter_blocks_hits(bs.out_el, bs.chain_off, nch, hits, hits2); H = hits2; }
-        }
-        if (dbg_hits && !err)
-        {
-            u32 k = (u32)n_hits < dbg_hits_cap ? (u32)n_hits : dbg_hits_cap;
-            for (u32 i = 0; i < k; i++) dbg_hits[i] = H[i];
-            *dbg_nhits = (u32)n_hits;
+            nch = chain_blocks_base(hits, sep, sep_score, nb, bs, in.L, 0, 0, 1);
+            if (nch > 0) n_hits = filter_blocks_hits_plan(bs.out_el, bs.chain_off, nch, keep_chain);
         }
     }
     err = wbcast(w, err, 0);
     if (err) return 1;
+    nch = wbcast(w, nch, 0);
     n_hits = wbcast(w, n_hits, 0);
-    H = (u64 *)wbcast64(w, (u64)H, 0);
+    wsync(w);
+    if (nch > 0)
+    {
+        filter_blocks_hits_copy(w, bs.out_el, bs.chain_off, nch, keep_chain, hits, hits2);
+        H = hits2;
+    }
+    if (dbg_hits)
+    {
+        u32 k = (u32)n_hits < dbg_hits_cap ? (u32)n_hits : dbg_hits_cap;
+        for (u32 i = (u32)w.lane; i < k; i += (u32)w.nl) dbg_hits[i] = H[i];
+        if (w.lane == 0) *dbg_nhits = (u32)n_hits;
+    }
     wsync(w);
     LNR_LAP(cnt, 6, tl);
     if (n_hits < 2) return 0;                // path_dst :1457
