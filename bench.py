@@ -212,7 +212,7 @@ def main():
     config = {"workload": f"{GENOME_BASES / 1e9:.2f}-Gbase synthetic genome ({N_CONTIGS} contigs, planted repeats) + ONT-like reads "
                           f"(lognormal mean 20 kb, 10% error, 20% planted SV), {args.batch_reads} reads per step per GPU",
               "index": "DIndex (-i 1)", "features": "2-mer/48 (-f 2)", "threads_sem": THREADS_SEM, "preset": 1,
-              "batch_reads_per_gpu": args.batch_reads, "parallelism": f"reads sharded x{world}, index replicated",
+              "batch_reads_per_gpu": args.batch_reads, "parallelism": f"reads sharded x{world} (no collective); index built by minimizer range x{world} + one NCCL all-gather",
               "l2_policy": "inputs larger than L2 (batch bases + index >> 126 MB)",
               "host_threads": args.streams}
 
@@ -262,7 +262,7 @@ def main():
                                  "sample": f"{per} reads per step through the reference's apxMap with {cores} OpenMP threads "
                                            f"(index + features built at -t {THREADS_SEM} in {t_index:.1f} s)"},
                 "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return
 
     # ------------------------------------------------------------------------------------------------- B200 arm
@@ -295,7 +295,12 @@ def main():
     t0 = time.time()
     gen = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=lens64)
     feats = lb.create_features(ctx, gen, 2, THREADS_SEM)
-    index = lb.create_index(ctx, gen, 1, THREADS_SEM)
+    if world == 1:
+        index = lb.create_index(ctx, gen, 1, THREADS_SEM)
+    else:
+        # hash-range sharded build: every rank builds 2^26/N buckets, one all-gather step over NVLink assembles them
+        from linear_b200 import sharding
+        index = sharding.build_index_sharded(lb, ctx, gen, THREADS_SEM, rank, world, torch, dist, dev)
     torch.cuda.synchronize()
     t_index = max_over_ranks(time.time() - t0)
     idx_kernels = ctx.kernel_times()
@@ -383,14 +388,13 @@ def main():
     # ---- timed region: device-resident inputs
     for c in ctxs:
         c.set_profiling(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     run_steps("step_device", args.warmup * n_str)
     for c in ctxs:
         c.set_profiling(True)
         c.reset_kernel_times()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     dt = max_over_ranks(run_steps("step_device", args.steps))
-    sampler.stop_flag = True
     kt = {}
     for c in ctxs:
         for k, v in c.kernel_times().items():
@@ -408,6 +412,7 @@ def main():
     e2e_value = world * n_reads * args.steps / dt_e2e
     c_host = streams[0].last[0]
     d2h = int(len(c_host) * 8 + (n_reads + 1) * 8)
+    sampler.stop_flag = True
     sampler.join(timeout=2)
 
     if rank != 0:
@@ -428,7 +433,9 @@ def main():
         "k_feat_reads": total_bases + nf_bytes,
         "k_seed_count": total_bases + 8 * S + 8 * H,
         "k_seed_fill": 8 * S + 8 * H + 8 * A,
-        "k_map_primary": 8 * A + 48 * Hits + 144 * W + 16 * Cc,
+        "k_map_hits": 8 * A + 48 * Hits,
+        "k_map_extend": 144 * W + 8 * Cc,
+        "k_map_finish": 16 * Cc,
     }
     per_kernel = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1]} for k, v in kt.items()}
     step_ms_kernels = sum(v[0] for v in kt.values()) / args.steps
@@ -463,7 +470,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "index_build": index_info,
             "clocks": sampler.summary(), "kernels": per_kernel, "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
             "bases_per_step": total_bases}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

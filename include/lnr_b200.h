@@ -65,6 +65,17 @@ int lnr_index_build(lnr_ctx *, const lnr_genome *, int index_type, unsigned thre
 /* DIndex contents: dir = int32[2^26+1], hs = uint64[n_hs] (include/index_util.h:99-120).
  * Pass NULL for dir/hs to query n_hs only. */
 int lnr_index_export_dindex(const lnr_index *, int32_t * dir, uint64_t * hs, uint64_t hs_cap, uint64_t * n_hs);
+/* Multi-GPU build: shard s of n keeps only the minimizers X in [s*2^26/n, (s+1)*2^26/n). The result is a
+ * DIndex whose dir counts only those buckets and whose hs holds only their records; the > 400 omission rule and the
+ * order inside a bucket are bucket-local, so concatenating the shards' hs in shard order and rebasing each shard's dir
+ * slice by the records of the shards before it gives exactly the index lnr_index_build produces. The exchange
+ * (one all-gather of counts, hs slices and dir slices) is done by the caller over NCCL on the device buffers below. */
+int lnr_index_build_shard(lnr_ctx *, const lnr_genome *, int index_type, unsigned threads_sem, unsigned shard, unsigned n_shards,
+                          lnr_index ** out);
+/* device-to-device copies of the index arrays (dev_dir: int32[2^26+1], dev_hs: uint64[>= n_hs]; either may be NULL) */
+int lnr_index_export_dindex_device(const lnr_index *, int32_t * dev_dir, uint64_t * dev_hs, uint64_t hs_cap);
+/* wraps assembled device arrays into an index (copies them) */
+int lnr_index_from_device(lnr_ctx *, const int32_t * dev_dir, const uint64_t * dev_hs, uint64_t n_hs, lnr_index ** out);
 void lnr_index_destroy(lnr_index *);
 
 /* ---- per-read approximate mapping -------------------------------------------------------------------

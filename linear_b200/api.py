@@ -29,7 +29,8 @@ EXPORTS = [
     "lnr_ctx_create", "lnr_ctx_destroy", "lnr_last_error", "lnr_ctx_set_profiling", "lnr_ctx_kernel_times",
     "lnr_ctx_reset_kernel_times", "lnr_genome_upload", "lnr_genome_from_device", "lnr_genome_destroy",
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
-    "lnr_index_build", "lnr_index_export_dindex", "lnr_index_destroy", "lnr_apxmap_batch",
+    "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_dindex_device",
+    "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch",
     "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_stage_cycles", "lnr_read_features",
 ]
 
@@ -81,6 +82,9 @@ def load_library() -> C.CDLL:
     lib.lnr_features_destroy.restype = None
     lib.lnr_index_build.argtypes = [vp, vp, C.c_int, C.c_uint, C.POINTER(vp)]
     lib.lnr_index_export_dindex.argtypes = [vp, i32p, u64p, C.c_uint64, u64p]
+    lib.lnr_index_build_shard.argtypes = [vp, vp, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.POINTER(vp)]
+    lib.lnr_index_export_dindex_device.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.lnr_index_from_device.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(vp)]
     lib.lnr_index_destroy.argtypes = [vp]
     lib.lnr_index_destroy.restype = None
     lib.lnr_apxmap_batch.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, u64p, C.c_uint64,
@@ -207,11 +211,32 @@ class Features:
 
 
 class Index:
-    def __init__(self, ctx: Context, genome: Genome, index_type: int = 1, threads: int = 4):
+    def __init__(self, ctx: Context, genome: Optional[Genome] = None, index_type: int = 1, threads: int = 4, shard: int = 0,
+                 n_shards: int = 1, handle=None):
         self.ctx, self.genome, self.index_type = ctx, genome, index_type
+        if handle is not None:
+            self.h = handle
+            return
         h = C.c_void_p()
-        ctx.check(ctx.lib.lnr_index_build(ctx.h, genome.h, index_type, threads, C.byref(h)))
+        if n_shards == 1:
+            ctx.check(ctx.lib.lnr_index_build(ctx.h, genome.h, index_type, threads, C.byref(h)))
+        else:
+            ctx.check(ctx.lib.lnr_index_build_shard(ctx.h, genome.h, index_type, threads, shard, n_shards, C.byref(h)))
         self.h = h
+
+    def export_device(self, torch, device):
+        """(dir int32[2^26+1], hs int64[n_hs]) as torch device tensors (device-to-device copy)"""
+        n = self.n_hs
+        d = torch.empty((1 << 26) + 1, dtype=torch.int32, device=device)
+        hs = torch.empty(max(n, 1), dtype=torch.int64, device=device)
+        self.ctx.check(self.ctx.lib.lnr_index_export_dindex_device(self.h, C.c_void_p(d.data_ptr()), C.c_void_p(hs.data_ptr()), max(n, 1)))
+        return d, hs[:n]
+
+    @staticmethod
+    def from_device(ctx: Context, dir_t, hs_t) -> "Index":
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lnr_index_from_device(ctx.h, C.c_void_p(dir_t.data_ptr()), C.c_void_p(hs_t.data_ptr()), int(hs_t.numel()), C.byref(h)))
+        return Index(ctx, None, handle=h)
 
     @property
     def n_hs(self) -> int:

@@ -321,8 +321,10 @@ struct TileAcc   // smem-staged tile with global fallback
 template <bool FILL>
 __global__ void __launch_bounds__(IT) k_idx_pass(const u8 * __restrict__ g, const IdxChunk * __restrict__ chunks,
                                                  const u32 * __restrict__ tile0, u32 n_chunks, u32 * __restrict__ cnt,
-                                                 const i32 * __restrict__ dir, u32 * __restrict__ fillc, u64 * __restrict__ hs)
+                                                 const i32 * __restrict__ dir, u32 * __restrict__ fillc, u64 * __restrict__ hs,
+                                                 u32 x_lo, u32 x_hi)
 {
+    // [x_lo, x_hi): minimizer range owned by this shard (multi-GPU build partitions the 2^26 buckets)
     __shared__ __align__(16) u8 s_b[ISM];
     __shared__ i32 s_warp[IT / 32];
     __shared__ i32 s_back;
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(IT) k_idx_pass(const u8 * __restrict__ g, cons
         i32 r = rs[q] > -0x40000000 ? rs[q] : (excl > -0x40000000 ? excl : tile_start_run);
         i32 idx = local_i + q;
         bool valid = idx < nm;
-        bool emit = valid && (((idx - r) & 1) == 0);
+        bool emit = valid && (((idx - r) & 1) == 0) && X[q] >= x_lo && X[q] < x_hi;
         if (emit)
         {
             if (!FILL) atomicAdd(&cnt[X[q]], 1u);
@@ -1150,7 +1152,52 @@ void lnr_features_destroy(lnr_feats * f)
 }
 
 // ---- index ---------------------------------------------------------------------------------------------------
+static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_index ** out);
+
 int lnr_index_build(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, lnr_index ** out)
+{
+    return index_build_range(ctx, g, index_type, threads_sem, 0u, 1u << kDirBits, out);
+}
+int lnr_index_build_shard(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, unsigned shard, unsigned n_shards,
+                          lnr_index ** out)
+{
+    if (n_shards == 0 || shard >= n_shards || ((1u << kDirBits) % n_shards) != 0) return fail(ctx, LNR_E_ARG, "n_shards must divide 2^26");
+    u32 per = (1u << kDirBits) / n_shards;
+    return index_build_range(ctx, g, index_type, threads_sem, shard * per, (shard + 1) * per, out);
+}
+int lnr_index_export_dindex_device(const lnr_index * ix, int32_t * dev_dir, uint64_t * dev_hs, uint64_t hs_cap)
+{
+    if (!ix) return LNR_E_ARG;
+    lnr_ctx * ctx = ix->ctx;
+    cudaSetDevice(ctx->device);
+    if (dev_dir) CK(cudaMemcpyAsync(dev_dir, ix->d_dir, (size_t)kDirSize * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dev_hs)
+    {
+        if (hs_cap < ix->n_hs) return fail(ctx, LNR_E_CAPACITY, "hs buffer too small");
+        CK(cudaMemcpyAsync(dev_hs, ix->d_hs, (size_t)ix->n_hs * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LNR_OK;
+}
+int lnr_index_from_device(lnr_ctx * ctx, const int32_t * dev_dir, const uint64_t * dev_hs, uint64_t n_hs, lnr_index ** out)
+{
+    if (!ctx || !dev_dir || !out || (n_hs && !dev_hs)) return LNR_E_ARG;
+    cudaSetDevice(ctx->device);
+    lnr_index * ix = new lnr_index();
+    ix->ctx = ctx; ix->index_type = 1; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = n_hs;
+    if (cudaMalloc(&ix->d_dir, (size_t)kDirSize * sizeof(i32)) != cudaSuccess || cudaMalloc(&ix->d_hs, (size_t)(n_hs + 8) * sizeof(u64)) != cudaSuccess)
+    {
+        lnr_index_destroy(ix);
+        return fail(ctx, LNR_E_CUDA, "cudaMalloc failed in lnr_index_from_device");
+    }
+    cudaMemcpyAsync(ix->d_dir, dev_dir, (size_t)kDirSize * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (n_hs) cudaMemcpyAsync(ix->d_hs, dev_hs, (size_t)n_hs * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)); }
+    *out = ix;
+    return LNR_OK;
+}
+static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_index ** out)
 {
     if (!ctx || !g || !out || threads_sem == 0) return LNR_E_ARG;
     if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "only index_type 1 (DIndex, -i 1) is implemented");
@@ -1196,7 +1243,7 @@ int lnr_index_build(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigne
         }
         {
             LaunchScope ls(ctx, "k_idx_count");
-            k_idx_pass<false><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, d_cnt, nullptr, nullptr, nullptr);
+            k_idx_pass<false><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, d_cnt, nullptr, nullptr, nullptr, x_lo, x_hi);
         }
         CKI(cudaGetLastError());
     }
@@ -1216,7 +1263,7 @@ int lnr_index_build(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigne
         CKI(cudaMemsetAsync(d_cnt, 0, ((size_t)kDirSize + 16) * sizeof(u32), ctx->stream));
         {
             LaunchScope ls(ctx, "k_idx_fill");
-            k_idx_pass<true><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, nullptr, ix->d_dir, d_cnt, ix->d_hs);
+            k_idx_pass<true><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, nullptr, ix->d_dir, d_cnt, ix->d_hs, x_lo, x_hi);
         }
         {
             LaunchScope ls(ctx, "k_idx_sort_buckets");

@@ -39,3 +39,53 @@ def merge_cords(parts: Sequence[Tuple[np.ndarray, np.ndarray]]):
         offs.append(np.asarray(o[1:], dtype=np.uint64) + base)
         base = base + np.uint64(len(c))
     return cords.astype(np.uint64), np.concatenate(offs)
+
+
+# ---- hash-range sharded DIndex build ---------------------------------------------------------------------
+N_BUCKETS = 1 << 26
+
+
+def assemble_dindex(parts, xp=np):
+    """parts[s] = (dir_s, hs_s) of shard s (lnr_index_build_shard): dir_s is the full 2^26+1 exclusive prefix over the
+    shard's own records, hs_s its records. Returns the (dir, hs) of the whole index. `xp` is numpy or torch: with torch
+    device tensors this is the local assembly step after the all-gather."""
+    n = len(parts)
+    per = N_BUCKETS // n
+    counts = [int(p[1].shape[0]) for p in parts]
+    base = 0
+    slices = []
+    for s, (d, _) in enumerate(parts):
+        slices.append(d[s * per:(s + 1) * per] + base)
+        base += counts[s]
+    if xp is np:
+        dir_ = np.concatenate(slices + [np.array([base], dtype=slices[0].dtype)])
+        hs = np.concatenate([p[1] for p in parts])
+    else:
+        dir_ = xp.cat(slices + [xp.tensor([base], dtype=slices[0].dtype, device=slices[0].device)])
+        hs = xp.cat([p[1] for p in parts])
+    return dir_, hs
+
+
+def build_index_sharded(lb, ctx, genome, threads, rank, world, torch, dist, device):
+    """Every rank builds the buckets of its minimizer range, then ONE exchange step over NCCL: all-gather of the record
+    counts, of the (padded) hs slices and of the rebased dir slices. Returns an Index holding the whole DIndex."""
+    part = lb.Index(ctx, genome, 1, threads, shard=rank, n_shards=world)
+    d_loc, hs_loc = part.export_device(torch, device)
+    part.close()
+    n_loc = torch.tensor([hs_loc.numel()], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n_loc) for _ in range(world)]
+    dist.all_gather(counts, n_loc)
+    counts = [int(c.item()) for c in counts]
+    n_max = max(counts)
+    pad = torch.zeros(n_max, dtype=torch.int64, device=device)
+    pad[: hs_loc.numel()] = hs_loc
+    hs_all = torch.empty(world * n_max, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(hs_all, pad)
+    per = N_BUCKETS // world
+    base = sum(counts[:rank])
+    my_slice = (d_loc[rank * per:(rank + 1) * per] + base).contiguous()
+    dir_all = torch.empty(N_BUCKETS + 1, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(dir_all[:N_BUCKETS], my_slice)
+    dir_all[N_BUCKETS] = sum(counts)
+    hs = torch.cat([hs_all[r * n_max: r * n_max + counts[r]] for r in range(world)])
+    return lb.Index.from_device(ctx, dir_all, hs)

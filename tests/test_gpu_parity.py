@@ -153,3 +153,30 @@ def test_genome_with_N_runs(lb, ctx):
 def test_limits_are_rejected(lb, ctx):
     with pytest.raises(lb.LnrError):
         lb.Genome(ctx, [np.zeros(10, np.uint8)] * 1025)
+
+
+@pytest.mark.parametrize("n_shards", [2, 8])
+def test_hash_range_sharded_index_build(lb, ctx, n_shards):
+    """multi-GPU index build, emulated on one GPU: every shard builds the buckets of its minimizer range; concatenating
+    the shards in order and rebasing dir reproduces the whole DIndex bit for bit (the NCCL all-gather only moves these
+    arrays between ranks; bench.py --gpus N runs it for real)"""
+    from linear_b200 import sharding
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    gen = lb.Genome(ctx, g)
+    full = lb.create_index(ctx, gen, 1, T)
+    d0, h0 = full.export_dindex()
+    parts = []
+    for s in range(n_shards):
+        p = lb.Index(ctx, gen, 1, T, shard=s, n_shards=n_shards)
+        parts.append(p.export_dindex())
+        p.close()
+    assert sum(len(p[1]) for p in parts) == len(h0)
+    d1, h1 = sharding.assemble_dindex(parts)
+    assert np.array_equal(d0, d1) and np.array_equal(h0, h1)
+    # device-side round trip used by the NCCL path
+    import torch
+    dev = torch.device("cuda", 0)
+    dt, ht = full.export_device(torch, dev)
+    again = lb.Index.from_device(ctx, dt, ht)
+    d2, h2 = again.export_dindex()
+    assert np.array_equal(d0, d2) and np.array_equal(h0, h2)

@@ -72,3 +72,25 @@ def test_shard_ranges_cover_and_balance():
         per = [int(offs[b] - offs[a]) for a, b in rs]
         assert max(per) - min(per) <= 2 * 50000
     assert sharding.shard_ranges(np.zeros(1, np.uint64), 4) == [(0, 0)] * 4
+
+
+def test_assemble_dindex_from_hash_range_shards():
+    """host logic of the multi-GPU index assembly: split a full DIndex by minimizer range the way lnr_index_build_shard
+    does, reassemble, compare"""
+    from cases import make_case
+    from cpu_checkers import Oracle
+    from linear_b200 import sharding
+    g, reads, bases, offs, T, preset = make_case("clean_hifi")
+    d, hs = Oracle(g, threads=T, preset=preset).dindex()
+    cnt = np.diff(d).astype(np.int64)
+    NB = sharding.N_BUCKETS
+    for n in (1, 2, 4, 8):
+        per = NB // n
+        parts = []
+        for s in range(n):
+            c = np.zeros(NB, dtype=np.int64)
+            c[s * per:(s + 1) * per] = cnt[s * per:(s + 1) * per]
+            ds = np.concatenate([[0], np.cumsum(c)]).astype(np.int32)
+            parts.append((ds, hs[d[s * per]:d[(s + 1) * per]]))
+        d2, h2 = sharding.assemble_dindex(parts)
+        assert np.array_equal(d2, d) and np.array_equal(h2, hs)
