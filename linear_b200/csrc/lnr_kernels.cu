@@ -561,18 +561,34 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
                                                     u64 * __restrict__ info, u32 * __restrict__ count, unsigned long long * counters)
 {
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
     u32 c = 0, scanned = 0;
+    u32 X = 0xffffffffu, ti = 0xffffffffu, m = 0;
+    SeedTask t;
+    memset(&t, 0, sizeof t);
+    GAcc acc = {nullptr, 0};
+    SeedVal sv = {0, 0, 0};
     if (s < n_samples)
     {
-        u32 ti = find_task(tasks, n_tasks, s);
-        SeedTask t = tasks[ti];
-        u32 m = (u32)(s - t.sample0) + 1;
+        ti = find_task(tasks, n_tasks, s);
+        t = tasks[ti];
+        m = (u32)(s - t.sample0) + 1;
         u64 L = read_off[t.read + 1] - read_off[t.read];
-        GAcc acc = {bases + read_off[t.read], (i64)L};
-        SeedVal sv; u32 k;
+        acc.s = bases + read_off[t.read]; acc.len = (i64)L;
+        u32 k;
         seed_sample(acc, t, m, sv, k);
+        X = sv.X;
+    }
+    // X of the previous sample of the same task: the lane below usually holds it, otherwise it is recomputed
+    u32 xl = __shfl_up_sync(0xffffffffu, X, 1), til = __shfl_up_sync(0xffffffffu, ti, 1), ml = __shfl_up_sync(0xffffffffu, m, 1);
+    if (s < n_samples)
+    {
         u32 xprev = 0;
-        if (m > 1) { SeedVal pv; u32 kp; seed_sample(acc, t, m - 1, pv, kp); xprev = pv.X; }
+        if (m > 1)
+        {
+            if (lane > 0 && til == ti && ml == m - 1) xprev = xl;
+            else { SeedVal pv; u32 kp; seed_sample(acc, t, m - 1, pv, kp); xprev = pv.X; }
+        }
         u64 inf = 0;
         if (sv.X != xprev)
         {
