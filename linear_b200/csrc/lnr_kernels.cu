@@ -81,11 +81,12 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order, task_nhits;
+    DevBuf remap_list, order, task_nhits, big_arena, big_list;
+    size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
     int extend_group = 32;
-    size_t arena_bytes_per_warp = 2u << 20;
+    size_t arena_bytes_per_warp = 4u << 20;
 };
 
 struct lnr_genome
@@ -653,6 +654,8 @@ struct MapArgs
     u32 * queue;                                       // atomic work counter
     const u32 * order;                                 // reads sorted by length, longest first (tail latency)
     u32 * task_nhits;                                  // hits per task after stage 1 (0xffffffff = scratch exhausted)
+    u32 * big_list; u32 * n_big;                       // tasks whose scratch did not fit the per-warp arena: re-run with the big arena
+    u8 * big_arena; u64 big_arena_per_warp;
     float stop_ratio;
     unsigned long long * counters;
     // optional debug
@@ -671,36 +674,38 @@ __device__ __forceinline__ void fill_pipe_in(const MapArgs & a, u32 r, PipeIn & 
     in.stop_ratio = a.stop_ratio;
 }
 
-// finish a read (lane 0 inside, all lanes call): gather (if re-mapped) + phase_finish
-__device__ __noinline__ int finish_read(const Warp & w, Arena & ar, u64 L, u64 * cords, int & nc, int cap, Blk * sep_in, int n_sep_in, bool regather)
+// scratch of the cord-block chaining stage for a read with n cords
+struct FinishBufs { Blk * sp1; Blk * sp2; i32 * sc1; i32 * sc2; BlockScratch s1, s2; u64 * tmp; };
+__device__ __forceinline__ bool alloc_finish(Arena & ar, FinishBufs & f, int n)
 {
-    if (regather) arena_reset(ar);   // otherwise sep_in lives in the arena and must stay valid
-    int n_sep_cap = nc + 2;
-    Blk * sp1 = arena_alloc<Blk>(ar, n_sep_cap);
-    Blk * sp2 = arena_alloc<Blk>(ar, n_sep_cap);
-    i32 * sc1 = arena_alloc<i32>(ar, n_sep_cap);
-    i32 * sc2 = arena_alloc<i32>(ar, n_sep_cap);
-    BlockScratch s1, s2;
-    block_scratch_alloc(ar, s1, n_sep_cap);
-    block_scratch_alloc(ar, s2, n_sep_cap);
-    u64 * tmp = arena_alloc<u64>(ar, (u64)cap);
-    if (ar.failed) return 1;
+    int cap = n + 2;
+    f.sp1 = arena_alloc<Blk>(ar, cap);
+    f.sp2 = arena_alloc<Blk>(ar, cap);
+    f.sc1 = arena_alloc<i32>(ar, cap);
+    f.sc2 = arena_alloc<i32>(ar, cap);
+    block_scratch_alloc(ar, f.s1, cap);
+    block_scratch_alloc(ar, f.s2, cap);
+    f.tmp = arena_alloc<u64>(ar, (u64)cap);
+    return !ar.failed;
+}
+// finish a read (all lanes): gather blocks again if it was re-mapped, then chainBlocksCords + flags
+__device__ __noinline__ void finish_read(const Warp & w, FinishBufs & f, u64 L, u64 * cords, int & nc, Blk * sep_in, int n_sep_in, bool regather)
+{
     int n_sep;
     if (regather)
     {
         int dummy = 0;
-        n_sep = gather_blocks_w(w, cords, nc, (YPair *)0, dummy, sp1, L, 1000, kWin, 1);
+        n_sep = gather_blocks_w(w, cords, nc, (YPair *)0, dummy, f.sp1, L, 1000, kWin, 1);
     }
     else
     {
         n_sep = n_sep_in;
-        for (int i = w.lane; i < n_sep; i += 32) sp1[i] = sep_in[i];
+        for (int i = w.lane; i < n_sep; i += 32) f.sp1[i] = sep_in[i];
         __syncwarp();
     }
-    phase_finish_w(w, L, cords, nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp);
+    phase_finish_w(w, L, cords, nc, f.sp1, n_sep, f.sp2, f.sc1, f.sc2, f.s1, f.s2, f.tmp);
     nc = __shfl_sync(0xffffffffu, nc, 0);
     __syncwarp();
-    return 0;
 }
 
 // Processing order of the primary pass: tasks with the most raw anchors first (their hits stage is the longest, so
@@ -732,13 +737,17 @@ __global__ void __launch_bounds__(1024) k_order_tasks(const SeedTask * __restric
 
 // ---- stage 1: hits. One warp per seeding task (primary pass: task r = read r; re-map pass: one task per gap).
 // Everything of apxMap_ up to and including _filterHits; the hits replace the task's anchors in A.
-__global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass)
+__global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass, int big_pass)
 {
+    // big_pass: second, tiny launch over the tasks that exhausted the 2 MB per-warp arena (reads with very many
+    // anchors), a few warps with a large arena each
     __shared__ u32 s_hist[4][256];
     Warp w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
     u32 wid = threadIdx.x >> 5;
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
+    if (big_pass) { ar.base = a.big_arena + (u64)gw * a.big_arena_per_warp; ar.cap = a.big_arena_per_warp; }
+    const u32 n_units = big_pass ? *a.n_big : a.n_tasks;
     u32 * bins = a.bins + (u64)gw * kNumBins;
     PipeCounters cnt;
     memset(&cnt, 0, sizeof cnt);
@@ -747,8 +756,8 @@ __global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass)
         u32 q = 0;
         if (w.lane == 0) q = atomicAdd(a.queue, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= a.n_tasks) break;
-        u32 ti = remap_pass ? q : a.order[q];          // primary: longest reads first
+        if (q >= n_units) break;
+        u32 ti = big_pass ? a.big_list[q] : (remap_pass ? q : a.order[q]);   // primary: heaviest reads first
         const SeedTask t = a.tasks[ti];
         u32 r = t.read;
         u64 L = a.read_off[r + 1] - a.read_off[r];
@@ -766,10 +775,14 @@ __global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass)
         u32 dcap = dh ? (u32)(a.dbg_hoff[r + 1] - a.dbg_hoff[r]) : 0;
         int rc = phase_map(w, ar, s_hist[wid], bins, in, a.A + base, a.B + base, n, (u64)t.str, remap_pass ? ((u64)t.end & kMaskY) : (L & kMaskY),
                            remap_pass ? 1 : 0, (u64 *)0, nc_dummy, 0, dh, dh ? a.dbg_nhits + r : (u32 *)0, dcap, cnt, a.A + base,
-                           a.task_nhits + ti);
-        if (rc && w.lane == 0) a.task_nhits[ti] = 0xffffffffu;   // scratch exhausted
+                           a.task_nhits + ti, big_pass != 0);
+        if (rc && w.lane == 0)
+        {
+            a.task_nhits[ti] = 0xffffffffu;                 // unresolved (big pass pending) or failed for good
+            if (rc == 2) a.big_list[atomicAdd(a.n_big, 1u)] = ti;   // untouched: re-run with the big arena
+        }
         if (!remap_pass) cnt.t[12]++;
-        if (!remap_pass && q == 0 && w.lane == 0)   // the longest read: its own stage profile (tail analysis)
+        if (!remap_pass && !big_pass && q == 0 && w.lane == 0)   // the longest read: its own stage profile (tail analysis)
             for (int i = 0; i < 12; i++) a.counters[56 + i] = (unsigned long long)(cnt.t[i] - before.t[i]);
         u64 dt = (u64)(LNR_CLOCK() - t_read);
         cnt.t[14] += dt;
@@ -844,12 +857,15 @@ __global__ void __launch_bounds__(128) k_map_extend(MapArgs a, const u32 * __res
 }
 
 // ---- stage 3: clean / gaps / re-map decision / cord-block chaining, one warp per read
-__global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass)
+__global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int big_pass)
 {
+    // big_pass: tiny second launch over the reads whose chaining scratch did not fit the per-warp arena
     Warp w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
     u32 wid = threadIdx.x >> 5;
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
+    if (big_pass) { ar.base = a.big_arena + (u64)gw * a.big_arena_per_warp; ar.cap = a.big_arena_per_warp; }
+    const u32 n_units = big_pass ? *a.n_big : n_list;
     PipeCounters cnt;
     memset(&cnt, 0, sizeof cnt);
     u64 c_cords = 0;
@@ -858,17 +874,34 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
         u32 q = 0;
         if (w.lane == 0) q = atomicAdd(a.queue, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= n_list) break;
-        u32 r = read_list[q];
+        if (q >= n_units) break;
+        u32 r = big_pass ? a.big_list[q] : read_list[q];
         u64 L = a.read_off[r + 1] - a.read_off[r];
         ReadSlot slot = a.slots[r];
         if (L <= (u64)kMinReadLen) { slot.n_cords = 0; slot.status = 0; slot.task0 = 0; slot.n_tasks = 0; if (w.lane == 0) a.slots[r] = slot; continue; }
         if (slot.status == 2) continue;
         u64 * cords = a.cords + a.cords_base[r];
-        int cap = (int)(a.cords_base[r + 1] - a.cords_base[r]);
         int nc = (int)slot.n_cords;
         int rc = 0;
         long long tl = LNR_CLOCK();
+        // all scratch of this stage is claimed before anything is modified, so that a read that does not fit can be
+        // handed to the big-arena pass untouched
+        arena_reset(ar);
+        YPair * str_ends = arena_alloc<YPair>(ar, (u64)nc + 2);
+        Blk * sep = arena_alloc<Blk>(ar, (u64)nc + 2);
+        int gcap = (int)(L / 1000 + 4);
+        YPair * gaps = arena_alloc<YPair>(ar, (u64)gcap);
+        FinishBufs fb;
+        alloc_finish(ar, fb, nc);
+        if (ar.failed)
+        {
+            if (w.lane == 0)
+            {
+                if (!big_pass) a.big_list[atomicAdd(a.n_big, 1u)] = r;
+                else { slot.n_cords = 0; slot.status = 2; a.slots[r] = slot; }
+            }
+            continue;
+        }
         if (!remap_pass)
         {
             if (a.dbg_c1)
@@ -878,36 +911,27 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
             }
             int remap = 0, n_sep = 0, n_gaps = 0;
             u32 task0 = 0;
-            arena_reset(ar);
-            YPair * str_ends = arena_alloc<YPair>(ar, (u64)nc + 2);
-            Blk * sep = arena_alloc<Blk>(ar, (u64)nc + 2);
-            int gcap = (int)(L / 1000 + 4);
-            YPair * gaps = arena_alloc<YPair>(ar, (u64)gcap);
-            if (ar.failed) rc = 1;
-            else
+            remap = phase_mid_w(w, L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
+            if (w.lane == 0 && remap == 1)
             {
-                remap = phase_mid_w(w, L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
-                if (w.lane == 0 && remap == 1)
-                {
-                    task0 = atomicAdd(a.n_tasks2, (u32)n_gaps);
-                    if (task0 + (u32)n_gaps > a.tasks2_cap) remap = -1;
-                    else
-                        for (int i = 0; i < n_gaps; i++)
-                        {
-                            SeedTask t2;
-                            t2.read = r; t2.str = (u32)(gaps[i].first & kMaskY); t2.end = (u32)gaps[i].second; t2.alpha = 7;
-                            t2.n_samples = seed_task_samples(t2.str, t2.end, 7);
-                            t2.bias = 0; t2.kskip = 0; t2.pad = 0; t2.sample0 = 0;
-                            a.tasks2[task0 + i] = t2;
-                        }
-                }
-                remap = __shfl_sync(0xffffffffu, remap, 0);
-                task0 = __shfl_sync(0xffffffffu, task0, 0);
-                __syncwarp();
-                if (remap < 0) rc = 1;
+                task0 = atomicAdd(a.n_tasks2, (u32)n_gaps);
+                if (task0 + (u32)n_gaps > a.tasks2_cap) remap = -1;
+                else
+                    for (int i = 0; i < n_gaps; i++)
+                    {
+                        SeedTask t2;
+                        t2.read = r; t2.str = (u32)(gaps[i].first & kMaskY); t2.end = (u32)gaps[i].second; t2.alpha = 7;
+                        t2.n_samples = seed_task_samples(t2.str, t2.end, 7);
+                        t2.bias = 0; t2.kskip = 0; t2.pad = 0; t2.sample0 = 0;
+                        a.tasks2[task0 + i] = t2;
+                    }
             }
+            remap = __shfl_sync(0xffffffffu, remap, 0);
+            task0 = __shfl_sync(0xffffffffu, task0, 0);
+            __syncwarp();
+            if (remap < 0) rc = 1;
             LNR_LAP(cnt, 9, tl);
-            if (!rc && remap == 0) rc = finish_read(w, ar, L, cords, nc, cap, sep, n_sep, false);
+            if (!rc && remap == 0) finish_read(w, fb, L, cords, nc, sep, n_sep, false);
             LNR_LAP(cnt, 10, tl);
             slot.n_cords = rc ? 0 : (u32)nc;
             slot.status = rc ? 2u : (remap == 1 ? 1u : 0u);
@@ -916,11 +940,11 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
         }
         else
         {
-            rc = finish_read(w, ar, L, cords, nc, cap, (Blk *)0, 0, true);
+            finish_read(w, fb, L, cords, nc, (Blk *)0, 0, true);
             LNR_LAP(cnt, 10, tl);
-            slot.n_cords = rc ? 0 : (u32)nc;
-            slot.status = rc ? 2u : 0u;
-            if (!rc) c_cords += (u64)nc;
+            slot.n_cords = (u32)nc;
+            slot.status = 0u;
+            c_cords += (u64)nc;
         }
         if (w.lane == 0) a.slots[r] = slot;
     }
@@ -990,7 +1014,9 @@ int lnr_ctx_create(int device, lnr_ctx ** out)
     ctx->n_sm = prop.multiProcessorCount;
     if (const char * e = getenv("LNR_MAP_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->map_ctas_per_sm = v; }
     if (const char * e = getenv("LNR_EXTEND_GROUP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->extend_group = v; }
-    if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }
+    if (const char * e = getenv("LNR_BIG_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 16384) ctx->big_arena_bytes_per_warp = (size_t)v << 20; }
+    if (const char * e = getenv("LNR_ARENA_KB")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) ctx->arena_bytes_per_warp = (size_t)v << 10; }
+    else if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LNR_E_CUDA; }
     *out = ctx;
     return LNR_OK;
@@ -1005,7 +1031,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->big_arena, &ctx->big_list})
         b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1506,18 +1532,34 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(ctx->task_nhits.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
     a.task_nhits = ctx->task_nhits.as<u32>();
     CK(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_reads * sizeof(ReadSlot), ctx->stream));
+    const size_t big_per_warp = ctx->big_arena_bytes_per_warp;
+    CK(ctx->big_arena.reserve(32 * big_per_warp));
+    CK(ctx->big_list.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
+    a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
+    a.big_list = ctx->big_list.as<u32>(); a.n_big = d_queue + 3;
     {
         LaunchScope ls(ctx, "k_map_hits");
-        k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 0);
+        k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 0, 0);
+    }
+    CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_map_hits_big");
+        k_map_hits<<<8, 128, 0, ctx->stream>>>(a, 0, 1);
     }
     {
         LaunchScope ls(ctx, "k_map_extend");
         k_map_extend<<<(u32)(((u64)n_reads * ctx->extend_group + 127) / 128), 128, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0, ctx->extend_group);
     }
     CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+    CK(cudaMemsetAsync(d_queue + 3, 0, sizeof(u32), ctx->stream));
     {
         LaunchScope ls(ctx, "k_map_finish");
-        k_map_finish<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0);
+        k_map_finish<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0, 0);
+    }
+    CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_map_finish_big");
+        k_map_finish<<<8, 128, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0, 1);
     }
     CK(cudaGetLastError());
     // ---- re-map pass
@@ -1548,18 +1590,30 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         a.A = ctx->anchorsA.as<u64>(); a.B = ctx->anchorsB.as<u64>();
         a.dbg_hits = nullptr; a.dbg_c1 = nullptr; a.dbg_nhits = nullptr; a.dbg_nc1 = nullptr;
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        CK(cudaMemsetAsync(d_queue + 3, 0, sizeof(u32), ctx->stream));
         {
             LaunchScope ls(ctx, "k_map_hits_remap");
-            k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 1);
+            k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 1, 0);
+        }
+        CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_map_hits_remap_big");
+            k_map_hits<<<8, 128, 0, ctx->stream>>>(a, 1, 1);
         }
         {
             LaunchScope ls(ctx, "k_map_extend_remap");
             k_map_extend<<<(u32)(((u64)remap_reads.size() * ctx->extend_group + 127) / 128), 128, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size(), 1, ctx->extend_group);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        CK(cudaMemsetAsync(d_queue + 3, 0, sizeof(u32), ctx->stream));
         {
             LaunchScope ls(ctx, "k_map_finish_remap");
-            k_map_finish<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size(), 1);
+            k_map_finish<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size(), 1, 0);
+        }
+        CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_map_finish_remap_big");
+            k_map_finish<<<8, 128, 0, ctx->stream>>>(a, d_remap, (u32)remap_reads.size(), 1, 1);
         }
         CK(cudaGetLastError());
     }

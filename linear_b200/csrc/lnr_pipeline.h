@@ -1138,13 +1138,23 @@ LNR_PIPE int gather_blocks_w(const Warp & w, u64 * cords, int n, YPair * str_end
 // Appends to cords. dbg_hits (optional): hits after getAnchorHitsChains.
 // Return: 0 ok, 1 scratch/cord capacity exhausted.
 // ----------------------------------------------------------------------------------------------------
+// upper bound of the arena bytes phase_map claims for n raw anchors (incl. sentinel): every array is <= n entries
+LNR_HD u64 phase_map_scratch_bound(int n)
+{
+    u64 m = (u64)n + 2;
+    return m * (8 + 4 + 8 + 8 + 4 + 24 + 8 + 8 + 8 + 16 + 8 + 4 + 52 + 1) + 2048;
+}
+
 LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, const PipeIn & in, u64 * A, u64 * B, int n,
                        u64 read_str, u64 read_end, int score_type, u64 * cords, int & n_cords, int cords_cap,
                        u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt,
-                       u64 * hits_out = (u64 *)0, u32 * n_hits_out = (u32 *)0)
+                       u64 * hits_out = (u64 *)0, u32 * n_hits_out = (u32 *)0, bool force_fit = true)
 {
     // hits_out != null: stop after _filterHits and hand the hits over (it may alias A; capacity n) -- the window
     // extension then runs in its own thread-per-read kernel. hits_out == null: run path_dst_2 here.
+    // Return 2 = nothing was touched because even the upper bound of the scratch need (all sizes <= n) does not
+    // fit this arena: the caller re-runs the task with a larger arena (the anchors in A/B are consumed by a run).
+    if (!force_fit && phase_map_scratch_bound(n) > ar.cap) return 2;
     arena_reset(ar);
     long long tl = LNR_CLOCK();
     if (n_hits_out && w.lane == 0) *n_hits_out = 0;

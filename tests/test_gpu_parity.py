@@ -180,3 +180,17 @@ def test_hash_range_sharded_index_build(lb, ctx, n_shards):
     again = lb.Index.from_device(ctx, dt, ht)
     d2, h2 = again.export_dindex()
     assert np.array_equal(d0, d2) and np.array_equal(h0, h2)
+
+
+def test_scratch_overflow_falls_back_to_big_arena(lb, monkeypatch):
+    """reads whose scratch does not fit the per-warp arena are re-run by the big-arena pass; results are unchanged"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    monkeypatch.setenv("LNR_ARENA_KB", "48")
+    small = lb.Context(0)
+    gen = lb.Genome(small, g)
+    feats = lb.create_features(small, gen, 2, T)
+    index = lb.create_index(small, gen, 1, T)
+    cords, coff = lb.apx_map_batch(small, index, feats, bases, offs, preset=preset)
+    kt = small.kernel_times()
+    oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
