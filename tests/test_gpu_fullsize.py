@@ -1,0 +1,79 @@
+"""GPU (-m gpu): BASELINE.json full sizes (3.1-Gbase, 24-contig genome) through size-independent properties -- the CPU
+oracle needs minutes at this size, so here the index is checked by what must hold for ANY correct DIndex, plus one
+cross-check that does not need an oracle: the hash-range sharded build must assemble to the very same arrays."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dindex_3gbase_properties_and_sharded_equivalence():
+    import torch
+    import linear_b200 as lb
+    from linear_b200 import sharding
+    sys.path.insert(0, ROOT)
+    import bench
+    dev = torch.device("cuda", 0)
+    lens = bench.contig_lengths()
+    genome = bench.gen_genome(torch, dev, lens)
+    G = int(sum(lens))
+    assert G > 3_000_000_000 and len(lens) == 24 and max(lens) < 299_000_000
+    ctx = lb.Context(0)
+    gen = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=[int(x) for x in lens])
+    T = 16
+    index = lb.create_index(ctx, gen, 1, T)
+    d, hs = index.export_device(torch, dev)
+    n_hs = hs.numel()
+    cnt = d[1:] - d[:-1]
+    # bucket offsets: exclusive prefix, no bucket above the omission threshold, total = n_hs
+    assert int(d[0]) == 0 and int(d[-1]) == n_hs and int(cnt.min()) >= 0 and int(cnt.max()) <= 400
+    # one record per ~9 bases minus omitted repeats
+    assert 0.09 * G < n_hs < 0.112 * G
+    # ascending inside every bucket: hs[i] < hs[i+1] unless i+1 starts a bucket
+    starts = torch.zeros(n_hs + 1, dtype=torch.bool, device=dev)
+    starts[d.long()] = True
+    asc = hs[1:] > hs[:-1]
+    assert bool((asc | starts[1:n_hs]).all())
+    # every record decodes to (contig, sampled position): id < 24, position inside the contig's sampled range, Y < 256,
+    # and the position lies on its chunk's 9-spaced sampling grid (index_util.cpp:1654-1685)
+    x = (hs >> 20) & ((1 << 30) - 1)
+    cid = (hs >> 50) & 1023
+    y = hs & 0xFFFFF
+    lens_t = torch.tensor(lens, dtype=torch.int64, device=dev)
+    assert int(cid.max()) < 24 and int(y.max()) < 256
+    pos = x - (1 << 20)
+    L = lens_t[cid]
+    assert bool((pos >= 21 + 8).all()) and bool((pos < L - 42).all())
+    chunk = torch.minimum(pos // (L // T), torch.tensor(T - 1, device=dev))
+    # a position may belong to chunk c or (if it is before c's first sample) to c-1; check both candidates
+    ok = torch.zeros_like(pos, dtype=torch.bool)
+    for dc in (0, 1):
+        c = (chunk - dc).clamp_min(0)
+        t_str = (L // T) * c + 21
+        ok |= ((pos - t_str - 8) % 9 == 0) & (pos >= t_str + 8)
+    assert bool(ok.all())
+    del starts, asc, x, cid, y, pos, L, chunk, ok
+    # hash-range sharded build (what N GPUs do) assembles to identical arrays
+    for n_shards in (8,):
+        parts = []
+        for s in range(n_shards):
+            p = lb.Index(ctx, gen, 1, T, shard=s, n_shards=n_shards)
+            parts.append(p.export_device(torch, dev))
+            p.close()
+        d2, h2 = sharding.assemble_dindex(parts, xp=torch)
+        assert torch.equal(d2, d) and torch.equal(h2, hs)
+    # genome features: entry count and field sanity (every 6-bit field <= 48, 47 two-mers minus TT per entry)
+    feats = lb.create_features(ctx, gen, 2, T)
+    f = torch.from_numpy(feats.download(0)).to(dev)
+    assert f.shape[0] == ((lens[0] - 48) >> 4) + 1
+    tot = torch.zeros(f.shape[0], dtype=torch.int64, device=dev)
+    for k in range(3):
+        for sft in range(0, 30, 6):
+            fld = (f[:, k].long() >> sft) & 63
+            assert int(fld.max()) <= 48
+            tot += fld
+    assert int(tot.max()) <= 48 and int(tot.min()) >= 20
