@@ -155,7 +155,7 @@ int64_t ref_hindex_dir_kv(void * h, const uint64_t ** p, uint64_t * table_len)
     XString & x = c->index.hindex.xstr;
     std::vector<std::pair<uint64_t, uint64_t> > v;
     for (uint64_t i = 0; i < length(x.xstring); i++)
-        if (x.xstring[i].val1 != 0 || x.xstring[i].val2 != 0)
+        if (x.xstring[i].val1 != 0)   // val2 of empty slots is uninitialised (XString::_fullSize)
             v.push_back(std::make_pair((uint64_t)x.xstring[i].val1, (uint64_t)x.xstring[i].val2));
     std::sort(v.begin(), v.end());
     c->kv.clear();

@@ -94,3 +94,24 @@ def test_oracle_equals_reference_with_N():
         r = rs.read(i)
         assert np.array_equal(R.stage(r, 1), O.stage(r, 1))
         assert np.array_equal(R.cords(r), O.cords(r))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("threads", [1, 4, 8])
+def test_oracle_hindex_equals_reference(threads):
+    """-i 2: ysa byte-exact (incl. the chunk-tail mislabel), emptyDir, and the open-addressing directory
+    as a sorted (val1, val2) list -- its physical layout is nondeterministic in the reference itself."""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    O = Oracle(g, threads=threads, preset=preset, index_type=2)
+    R = RefImpl(g, threads=threads, preset=preset, index_type=2)
+    y0, e0, kv0, tl0 = R.hindex()
+    y1, e1, kv1, tl1 = O.hindex()
+    assert np.array_equal(y0, y1) and e0 == e1 and tl0 == tl1
+    assert np.array_equal(kv0, kv1)
+    if threads == 4:
+        for r in reads[:25]:
+            if len(r) <= 200:
+                continue
+            assert np.array_equal(R.stage(r, 1), O.stage(r, 1))           # getHIndexMatchAll incl. head words read as bodies
+            assert np.array_equal(R.stage(r, 1, len(r) // 3, len(r) - 100, 1), O.stage(r, 1, len(r) // 3, len(r) - 100, 1))
+            assert np.array_equal(R.cords(r), O.cords(r))
