@@ -65,6 +65,12 @@ int lnr_index_build(lnr_ctx *, const lnr_genome *, int index_type, unsigned thre
 /* DIndex contents: dir = int32[2^26+1], hs = uint64[n_hs] (include/index_util.h:99-120).
  * Pass NULL for dir/hs to query n_hs only. */
 int lnr_index_export_dindex(const lnr_index *, int32_t * dir, uint64_t * hs, uint64_t hs_cap, uint64_t * n_hs);
+/* HIndex contents (index_type 2; include/index_util.h:139-248): ysa words (heads + bodies + two zero terminators),
+ * emptyDir, and the open-addressing directory as (val1, val2) pairs sorted by val1 -- the reference's own physical
+ * table layout differs from run to run, so only the key -> value map is part of the contract.
+ * Any pointer may be NULL (size query). */
+int lnr_index_export_hindex(const lnr_index *, uint64_t * ysa, uint64_t ysa_cap, uint64_t * n_ysa, uint64_t * keyvals /* 2*n_kv */,
+                            uint64_t kv_cap, uint64_t * n_kv, uint64_t * empty_dir, uint64_t * table_len);
 /* Multi-GPU build: shard s of n keeps only the minimizers X in [s*2^26/n, (s+1)*2^26/n). The result is a
  * DIndex whose dir counts only those buckets and whose hs holds only their records; the > 400 omission rule and the
  * order inside a bucket are bucket-local, so concatenating the shards' hs in shard order and rebasing each shard's dir

@@ -29,7 +29,7 @@ EXPORTS = [
     "lnr_ctx_create", "lnr_ctx_destroy", "lnr_last_error", "lnr_ctx_set_profiling", "lnr_ctx_kernel_times",
     "lnr_ctx_reset_kernel_times", "lnr_genome_upload", "lnr_genome_from_device", "lnr_genome_destroy",
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
-    "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_dindex_device",
+    "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
     "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch",
     "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_stage_cycles", "lnr_read_features",
 ]
@@ -82,6 +82,7 @@ def load_library() -> C.CDLL:
     lib.lnr_features_destroy.restype = None
     lib.lnr_index_build.argtypes = [vp, vp, C.c_int, C.c_uint, C.POINTER(vp)]
     lib.lnr_index_export_dindex.argtypes = [vp, i32p, u64p, C.c_uint64, u64p]
+    lib.lnr_index_export_hindex.argtypes = [vp, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p, u64p]
     lib.lnr_index_build_shard.argtypes = [vp, vp, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.POINTER(vp)]
     lib.lnr_index_export_dindex_device.argtypes = [vp, vp, vp, C.c_uint64]
     lib.lnr_index_from_device.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(vp)]
@@ -224,6 +225,16 @@ class Index:
             ctx.check(ctx.lib.lnr_index_build_shard(ctx.h, genome.h, index_type, threads, shard, n_shards, C.byref(h)))
         self.h = h
 
+    def export_hindex(self):
+        """(ysa uint64[], emptyDir, sorted (val1, val2) directory entries, table length) of an HIndex (-i 2)"""
+        n, nk, e, tl = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.lnr_index_export_hindex(self.h, None, 0, C.byref(n), None, 0, C.byref(nk), C.byref(e), C.byref(tl)))
+        ysa = np.zeros(n.value, np.uint64)
+        kv = np.zeros(2 * nk.value, np.uint64)
+        self.ctx.check(self.ctx.lib.lnr_index_export_hindex(self.h, ysa.ctypes.data_as(u64p), n.value, C.byref(n), kv.ctypes.data_as(u64p),
+                                                            nk.value, C.byref(nk), C.byref(e), C.byref(tl)))
+        return ysa, int(e.value), kv.reshape(-1, 2), int(tl.value)
+
     def export_device(self, torch, device):
         """(dir int32[2^26+1], hs int64[n_hs]) as torch device tensors (device-to-device copy)"""
         n = self.n_hs
@@ -240,6 +251,8 @@ class Index:
 
     @property
     def n_hs(self) -> int:
+        if self.index_type == 2:
+            return 0
         n = C.c_uint64()
         self.ctx.check(self.ctx.lib.lnr_index_export_dindex(self.h, None, None, 0, C.byref(n)))
         return int(n.value)

@@ -98,6 +98,12 @@ LNR_HD u32 seed_task_samples(u32 str, u32 end, u32 alpha)
     i64 d = (i64)end - 2 * kSpanD - (i64)str;
     return d > 0 ? (u32)(d / alpha) : 0;
 }
+// getHIndexMatchAll (pmpfinder.cpp:1934): samples k = str + alpha*m - 1, m >= 1, while k < end - 17
+LNR_HD u32 hseed_task_samples(u32 str, u32 end, u32 alpha)
+{
+    i64 d = (i64)end - 17 - (i64)str;
+    return d > 0 ? (u32)(d / alpha) : 0;
+}
 template <class BaseFn>
 LNR_HD void seed_sample(BaseFn base, const SeedTask & t, u32 m /* 1-based */, SeedVal & sv, u32 & k)
 {

@@ -32,8 +32,11 @@ struct SeedVal
 //   n_steps  number of hashNexth calls since hashInit (>= 21: pure window)
 //   init0    position of hashInit's first base (call start + N-skip)
 //   feed0    position of the first base fed by hashNexth (k0 + span - 1)
-template <int SPAN, class BaseFn>
-LNR_HD void eval_sample(BaseFn base, i64 p, i64 n_steps, i64 init0, i64 feed0, int bias, SeedVal & out)
+// FULL_Y = false: Y is the 8-bit flank key of hashNextXY2 (index -i 1, all read seeding).
+// FULL_Y = true : Y is hashNext's key (shape_extend.cpp:132, HIndex build): the bits of v2 outside the minimizer plus
+//                 the minimizer offset code t << (2*span - 2*weight - 1), t = 64 - 2*span + 2*off.
+template <int SPAN, bool FULL_Y, class BaseFn>
+LNR_HD void eval_sample_t(BaseFn base, i64 p, i64 n_steps, i64 init0, i64 feed0, int bias, SeedVal & out)
 {
     const int W = SPAN - 8;
     u64 h = 0, cr = 0;
@@ -75,7 +78,13 @@ LNR_HD void eval_sample(BaseFn base, i64 p, i64 n_steps, i64 init0, i64 feed0, i
         if (X > v1) { X = v1; off = o; }
     }
     u32 Y = 0;
-    if (!strand)
+    if (FULL_Y)
+    {
+        int below = 2 * (8 - off);
+        u64 t = (u64)(64 - 2 * SPAN + 2 * off);
+        Y = (u32)(((v2 >> (below + 2 * W)) << below) + (v2 & ((1ULL << below) - 1)) + (t << (2 * SPAN - 2 * W - 1)));
+    }
+    else if (!strand)
     {
 #pragma unroll
         for (int q = 0; q < 4; q++)
@@ -96,6 +105,12 @@ LNR_HD void eval_sample(BaseFn base, i64 p, i64 n_steps, i64 init0, i64 feed0, i
     out.X = (u32)X;
     out.Y = Y;
     out.strand = strand;
+}
+
+template <int SPAN, class BaseFn>
+LNR_HD void eval_sample(BaseFn base, i64 p, i64 n_steps, i64 init0, i64 feed0, int bias, SeedVal & out)
+{
+    eval_sample_t<SPAN, false>(base, p, n_steps, init0, feed0, bias, out);
 }
 
 // hashInit's N-skip (shape_extend.cpp:96-105): smallest k such that `span` consecutive non-N bases

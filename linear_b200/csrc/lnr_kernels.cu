@@ -108,13 +108,19 @@ struct lnr_feats
     const F96 ** d_ptrs;            // device table of per-contig pointers
     u32 * d_n;                      // device table of counts
 };
+struct HNode;
 struct lnr_index
 {
     lnr_ctx * ctx;
-    int index_type;
+    int index_type;          // 1 = DIndex, 2 = HIndex
     i32 * d_dir;
     u64 * d_hs;
     uint64_t n_hs;
+    // HIndex (include/index_util.h:139-248)
+    u64 * d_ysa = nullptr;
+    uint64_t n_ysa = 0, empty_dir = 0;
+    HNode * d_tab = nullptr;
+    uint64_t tab_len = 0, n_dir_entries = 0;
 };
 
 #define CK(call)                                                                                        \
@@ -630,6 +636,8 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read
     }
 }
 
+#include "lnr_hindex.cuh"
+
 // =====================================================================================================
 // warp-per-read pipeline kernels
 // =====================================================================================================
@@ -653,6 +661,7 @@ struct MapArgs
     u32 * bins; u8 * arena; u64 arena_per_warp;
     u32 * queue;                                       // atomic work counter
     const u32 * order;                                 // reads sorted by length, longest first (tail latency)
+    int index_type;                                    // 1 DIndex, 2 HIndex (sample grid of re-map tasks)
     u32 * task_nhits;                                  // hits per task after stage 1 (0xffffffff = scratch exhausted)
     u32 * big_list; u32 * n_big;                       // tasks whose scratch did not fit the per-warp arena: re-run with the big arena
     u8 * big_arena; u64 big_arena_per_warp;
@@ -921,7 +930,7 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
                     {
                         SeedTask t2;
                         t2.read = r; t2.str = (u32)(gaps[i].first & kMaskY); t2.end = (u32)gaps[i].second; t2.alpha = 7;
-                        t2.n_samples = seed_task_samples(t2.str, t2.end, 7);
+                        t2.n_samples = a.index_type == 2 ? hseed_task_samples(t2.str, t2.end, 7) : seed_task_samples(t2.str, t2.end, 7);
                         t2.bias = 0; t2.kskip = 0; t2.pad = 0; t2.sample0 = 0;
                         a.tasks2[task0 + i] = t2;
                     }
@@ -994,6 +1003,162 @@ static int device_scan(lnr_ctx * ctx, u32 * d_in, u64 n, u32 cap, OutT * d_out, 
     return LNR_OK;
 }
 
+
+// ---- HIndex build (host orchestration) -------------------------------------------------------------------------------
+static int hindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned T, lnr_index ** out)
+{
+    std::vector<HChunk> chunks;
+    u64 n_samples = 0;
+    for (uint32_t ci = 0; ci < g->n_contigs; ci++)
+    {
+        u64 len = g->len[ci];
+        if (len < (u64)kSpanH + T) continue;
+        u64 n = len - kSpanH + 1, q = n / T, r = n - q * T;
+        for (unsigned t = 0; t < T; t++)   // index_util.cpp:742-760
+        {
+            HChunk ch;
+            memset(&ch, 0, sizeof ch);
+            ch.base_off = g->off[ci]; ch.len = (i64)len; ch.contig = ci;
+            if (t < r) { ch.csize = (i64)q + 1; ch.start = (i64)((q + 1) * t); }
+            else { ch.csize = (i64)q; ch.start = (i64)(len + 1 - kSpanH - q * (T - t)); }
+            ch.k_first = (ch.start + kStepH - 1) / kStepH * kStepH;
+            i64 k_end = ch.start + ch.csize;
+            ch.n_samples = ch.k_first < k_end ? (k_end - ch.k_first + kStepH - 1) / kStepH : 0;
+            if (ch.csize <= 0) continue;
+            ch.sample0 = n_samples;
+            n_samples += (u64)ch.n_samples;
+            chunks.push_back(ch);
+        }
+    }
+    if (!n_samples) return fail(ctx, LNR_E_UNSUPPORTED, "genome too small for the HIndex");
+    lnr_index * ix = new lnr_index();
+    ix->ctx = ctx; ix->index_type = 2; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = 0;
+    HChunk * d_chunks = nullptr; u64 * d_body[2] = {nullptr, nullptr}; u32 * d_x[2] = {nullptr, nullptr};
+    u32 * d_hist = nullptr; u64 * d_offs = nullptr; u64 * d_small = nullptr; u32 * d_flag = nullptr; u64 * d_bid = nullptr; u64 * d_starts = nullptr;
+    u64 * d_goff = nullptr; u64 * d_glen = nullptr;
+    auto cleanup = [&]() {
+        for (void * p : {(void *)d_chunks, (void *)d_body[0], (void *)d_body[1], (void *)d_x[0], (void *)d_x[1], (void *)d_hist, (void *)d_offs,
+                         (void *)d_small, (void *)d_flag, (void *)d_bid, (void *)d_starts, (void *)d_goff, (void *)d_glen})
+            if (p) cudaFree(p);
+    };
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); lnr_index_destroy(ix); return LNR_E_CUDA; } } while (0)
+    u32 n_chunks = (u32)chunks.size();
+    CKH(cudaMalloc(&d_small, 64 * sizeof(u64)));
+    CKH(cudaMemsetAsync(d_small, 0, 64 * sizeof(u64), ctx->stream));
+    // ACGT only
+    CKH(cudaMalloc(&d_goff, g->n_contigs * sizeof(u64)));
+    CKH(cudaMalloc(&d_glen, g->n_contigs * sizeof(u64)));
+    CKH(cudaMemcpyAsync(d_goff, g->off.data(), g->n_contigs * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaMemcpyAsync(d_glen, g->len.data(), g->n_contigs * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_check_acgt");
+        k_check_acgt<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(g->d_bases, d_goff, d_glen, g->n_contigs, (u32 *)(d_small + 8));
+    }
+    CKH(cudaMalloc(&d_chunks, chunks.size() * sizeof(HChunk)));
+    CKH(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(HChunk), cudaMemcpyHostToDevice, ctx->stream));
+    for (int i = 0; i < 2; i++) { CKH(cudaMalloc(&d_body[i], (size_t)(n_samples + 8) * sizeof(u64))); CKH(cudaMalloc(&d_x[i], (size_t)(n_samples + 8) * sizeof(u32))); }
+    {
+        LaunchScope ls(ctx, "k_hidx_prep");
+        k_hidx_prep<<<(n_chunks + 63) / 64, 64, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks);
+    }
+    {
+        LaunchScope ls(ctx, "k_hidx_pairs");
+        k_hidx_pairs<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks, n_samples, d_body[0], d_x[0],
+                                                                              (unsigned long long *)d_small);
+    }
+    CKH(cudaGetLastError());
+    u64 h_small[16];
+    CKH(cudaMemcpyAsync(h_small, d_small, sizeof h_small, cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    const u64 n = h_small[0];
+    if (((u32 *)(h_small + 8))[0]) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_UNSUPPORTED, "HIndex (-i 2): genomes containing N are not supported"); }
+    // ---- sort: body descending (LSD over its varying bytes), then X ascending
+    u64 init[4] = {0, ~0ULL, 0, ~0ULL};
+    CKH(cudaMemcpyAsync(d_small + 16, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_rs_masks");
+        k_rs_masks<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(d_body[0], d_x[0], n, d_small + 16);
+    }
+    u64 masks[4];
+    CKH(cudaMemcpyAsync(masks, d_small + 16, sizeof masks, cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    const u64 vary_body = masks[0] ^ masks[1];
+    const u32 vary_x = (u32)(masks[2] ^ masks[3]);
+    const u32 n_tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+    CKH(cudaMalloc(&d_hist, (size_t)256 * n_tiles * sizeof(u32) + 64));
+    CKH(cudaMalloc(&d_offs, ((size_t)256 * n_tiles + STILE) * sizeof(u64)));
+    int cur = 0;
+    for (int pass = 0; pass < 11; pass++)
+    {
+        RsDigit dg;
+        if (pass < 8) { dg.from_aux = 0; dg.shift = 8 * pass; dg.xor_mask = ~0ULL; if (((vary_body >> (8 * pass)) & 255) == 0) continue; }
+        else { dg.from_aux = 1; dg.shift = 8 * (pass - 8); dg.xor_mask = 0; if (((vary_x >> (8 * (pass - 8))) & 255) == 0) continue; }
+        {
+            LaunchScope ls(ctx, "k_rs_hist");
+            k_rs_hist<<<n_tiles, RS_T, 0, ctx->stream>>>(d_body[cur], d_x[cur], n, dg, d_hist, n_tiles);
+        }
+        int rc = device_scan<u64>(ctx, d_hist, (u64)256 * n_tiles, 0, d_offs, d_small + 24, "k_scan_radix");
+        if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
+        {
+            LaunchScope ls(ctx, "k_rs_scatter");
+            k_rs_scatter<<<n_tiles, RS_T, 0, ctx->stream>>>(d_body[cur], d_x[cur], n, dg, d_offs, n_tiles, d_body[cur ^ 1], d_x[cur ^ 1]);
+        }
+        cur ^= 1;
+    }
+    CKH(cudaGetLastError());
+    // ---- blocks
+    CKH(cudaMalloc(&d_flag, (size_t)(n + STILE + 8) * sizeof(u32)));
+    CKH(cudaMalloc(&d_bid, (size_t)(n + STILE + 8) * sizeof(u64)));
+    {
+        LaunchScope ls(ctx, "k_hidx_flags");
+        k_hidx_flags<<<(u32)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_x[cur], n, d_flag);
+    }
+    {
+        int rc = device_scan<u64>(ctx, d_flag, n + 1, 0, d_bid, d_small + 24, "k_scan_blocks");
+        if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
+    }
+    u64 n_blocks = 0;
+    CKH(cudaMemcpyAsync(&n_blocks, d_small + 24, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    if (n - n_blocks <= 2) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_UNSUPPORTED, "genome too small for the HIndex (countMove <= 2, index_util.cpp:1333)"); }
+    CKH(cudaMalloc(&d_starts, (size_t)(n_blocks + 2) * sizeof(u64)));
+    ix->n_ysa = n + n_blocks + 2;
+    ix->empty_dir = n + n_blocks;
+    CKH(cudaMalloc(&ix->d_ysa, (size_t)(ix->n_ysa + 8) * sizeof(u64)));
+    CKH(cudaMemsetAsync(ix->d_ysa + n + n_blocks, 0, 10 * sizeof(u64), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_hidx_starts");
+        k_hidx_starts<<<(u32)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_flag, d_bid, n, d_starts);
+    }
+    {
+        LaunchScope ls(ctx, "k_hidx_write");
+        k_hidx_write<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(d_body[cur], d_x[cur], d_flag, d_bid, d_starts, n, ix->d_ysa);
+    }
+    // ---- directory
+    CKH(cudaMemsetAsync(d_small + 32, 0, sizeof(u64), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_hidx_dir_count");
+        k_hidx_dir<<<(u32)((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, d_starts, n_blocks, 0, (unsigned long long *)(d_small + 32), nullptr, 0);
+    }
+    u64 n_ent = 0;
+    CKH(cudaMemcpyAsync(&n_ent, d_small + 32, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    u64 tl = 1;
+    while ((float)tl < (float)n_ent * 1.6f) tl <<= 1;   // XString::_fullSize index_util.cpp:221, alpha 1.6
+    ix->tab_len = tl; ix->n_dir_entries = n_ent;
+    CKH(cudaMalloc(&ix->d_tab, (size_t)tl * sizeof(HNode)));
+    CKH(cudaMemsetAsync(ix->d_tab, 0, (size_t)tl * sizeof(HNode), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_hidx_dir_insert");
+        k_hidx_dir<<<(u32)((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, d_starts, n_blocks, 1, nullptr, ix->d_tab, tl - 1);
+    }
+    CKH(cudaGetLastError());
+    CKH(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+#undef CKH
+    *out = ix;
+    return LNR_OK;
+}
 
 // =====================================================================================================
 // C ABI
@@ -1209,7 +1374,7 @@ int lnr_index_build_shard(lnr_ctx * ctx, const lnr_genome * g, int index_type, u
 }
 int lnr_index_export_dindex_device(const lnr_index * ix, int32_t * dev_dir, uint64_t * dev_hs, uint64_t hs_cap)
 {
-    if (!ix) return LNR_E_ARG;
+    if (!ix || ix->index_type != 1) return LNR_E_ARG;
     lnr_ctx * ctx = ix->ctx;
     cudaSetDevice(ctx->device);
     if (dev_dir) CK(cudaMemcpyAsync(dev_dir, ix->d_dir, (size_t)kDirSize * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1242,7 +1407,12 @@ int lnr_index_from_device(lnr_ctx * ctx, const int32_t * dev_dir, const uint64_t
 static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_index ** out)
 {
     if (!ctx || !g || !out || threads_sem == 0) return LNR_E_ARG;
-    if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "only index_type 1 (DIndex, -i 1) is implemented");
+    if (index_type == 2)
+    {
+        if (x_lo != 0 || x_hi != (1u << kDirBits)) return fail(ctx, LNR_E_UNSUPPORTED, "sharded build is implemented for index_type 1 only");
+        return hindex_build(ctx, g, threads_sem, out);
+    }
+    if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "index_type must be 1 (DIndex, -i 1) or 2 (HIndex, -i 2)");
     cudaSetDevice(ctx->device);
     // chunk table (createDIndex :1654-1670)
     std::vector<IdxChunk> chunks;
@@ -1321,7 +1491,7 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
 }
 int lnr_index_export_dindex(const lnr_index * ix, int32_t * dir, uint64_t * hs, uint64_t hs_cap, uint64_t * n_hs)
 {
-    if (!ix) return LNR_E_ARG;
+    if (!ix || ix->index_type != 1) return LNR_E_ARG;
     lnr_ctx * ctx = ix->ctx;
     cudaSetDevice(ctx->device);
     if (n_hs) *n_hs = ix->n_hs;
@@ -1339,7 +1509,41 @@ void lnr_index_destroy(lnr_index * ix)
     cudaSetDevice(ix->ctx->device);
     if (ix->d_dir) cudaFree(ix->d_dir);
     if (ix->d_hs) cudaFree(ix->d_hs);
+    if (ix->d_ysa) cudaFree(ix->d_ysa);
+    if (ix->d_tab) cudaFree(ix->d_tab);
     delete ix;
+}
+int lnr_index_export_hindex(const lnr_index * ix, uint64_t * ysa, uint64_t ysa_cap, uint64_t * n_ysa, uint64_t * keyvals, uint64_t kv_cap,
+                            uint64_t * n_kv, uint64_t * empty_dir, uint64_t * table_len)
+{
+    if (!ix || ix->index_type != 2) return LNR_E_ARG;
+    lnr_ctx * ctx = ix->ctx;
+    cudaSetDevice(ctx->device);
+    if (n_ysa) *n_ysa = ix->n_ysa;
+    if (n_kv) *n_kv = ix->n_dir_entries;
+    if (empty_dir) *empty_dir = ix->empty_dir;
+    if (table_len) *table_len = ix->tab_len;
+    if (ysa)
+    {
+        if (ysa_cap < ix->n_ysa) return fail(ctx, LNR_E_CAPACITY, "ysa buffer too small");
+        CK(cudaMemcpy(ysa, ix->d_ysa, (size_t)ix->n_ysa * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    if (keyvals)
+    {
+        if (kv_cap < ix->n_dir_entries) return fail(ctx, LNR_E_CAPACITY, "keyvals buffer too small");
+        u64 * d_kv = nullptr; unsigned long long * d_n = nullptr;
+        CK(cudaMalloc(&d_kv, (size_t)(ix->n_dir_entries + 1) * 16));
+        CK(cudaMalloc(&d_n, 8));
+        CK(cudaMemset(d_n, 0, 8));
+        k_hidx_dir_export<<<(u32)((ix->tab_len + 255) / 256), 256>>>(ix->d_tab, ix->tab_len, d_kv, d_n);
+        std::vector<std::pair<u64, u64> > kv(ix->n_dir_entries);
+        cudaError_t e = cudaMemcpy(kv.data(), d_kv, (size_t)ix->n_dir_entries * 16, cudaMemcpyDeviceToHost);
+        cudaFree(d_kv); cudaFree(d_n);
+        if (e != cudaSuccess) return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e));
+        std::sort(kv.begin(), kv.end());   // the physical layout is not part of the contract
+        for (size_t i = 0; i < kv.size(); i++) { keyvals[2 * i] = kv[i].first; keyvals[2 * i + 1] = kv[i].second; }
+    }
+    return LNR_OK;
 }
 
 // ---- seeding pass (count / scan / fill) -----------------------------------------------------------------------
@@ -1354,15 +1558,22 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     CK(ctx->misc.reserve(1024));
     u64 * d_total = ctx->misc.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
+    const bool hx_mode = ix->index_type == 2;
+    HIndexDev hx = {ix->d_ysa, ix->n_ysa, ix->empty_dir, ix->d_tab, ix->tab_len ? ix->tab_len - 1 : 0};
     {
         LaunchScope ls(ctx, "k_seed_prep");
-        k_seed_prep<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks);
+        if (hx_mode) k_hseed_prep<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks);
+        else k_seed_prep<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks);
     }
     // one extra zero count so that aoff[n_samples] = total
     CK(cudaMemsetAsync(ctx->sample_cnt.as<u32>() + n_samples, 0, sizeof(u32), ctx->stream));
     if (n_samples)
     {
         LaunchScope ls(ctx, tag);
+        if (hx_mode)
+            k_hseed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, hx,
+                                                                                   ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
+        else
         k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dir,
                                                                               ix->d_hs, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
     }
@@ -1379,6 +1590,10 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     if (n_samples)
     {
         LaunchScope ls(ctx, "k_seed_fill");
+        if (hx_mode)
+            k_hseed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, hx,
+                                                                                  ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>());
+        else
         k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs,
                                                                              ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>());
     }
@@ -1406,7 +1621,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         SeedTask & t = tasks[r];
         memset(&t, 0, sizeof t);
         t.read = r; t.str = 0; t.end = (u32)L; t.alpha = 15;
-        t.n_samples = L > (u64)kMinReadLen ? seed_task_samples(0, (u32)L, 15) : 0;
+        t.n_samples = L > (u64)kMinReadLen ? (ix->index_type == 2 ? hseed_task_samples(0, (u32)L, 15) : seed_task_samples(0, (u32)L, 15)) : 0;
         t.sample0 = n_samples;
         n_samples += t.n_samples;
         u32 nf = L > (u64)kMinReadLen ? feat_count_read(L) : 0;
@@ -1520,6 +1735,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     a.tasks2 = ctx->tasks2.as<SeedTask>(); a.tasks2_cap = tasks2_cap; a.n_tasks2 = d_ntasks2;
     a.bins = ctx->bins.as<u32>(); a.arena = ctx->arena.as<u8>(); a.arena_per_warp = ctx->arena_bytes_per_warp;
     a.queue = d_queue;
+    a.index_type = ix->index_type;
     a.order = ctx->order.as<u32>();
     a.stop_ratio = stop_ratio;
     a.counters = d_counters;

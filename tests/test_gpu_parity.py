@@ -194,3 +194,39 @@ def test_scratch_overflow_falls_back_to_big_arena(lb, monkeypatch):
     kt = small.kernel_times()
     oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
     assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+
+
+@pytest.mark.parametrize("threads", [1, 4, 8])
+def test_hindex_build_bit_exact(lb, ctx, threads):
+    """-i 2: ysa byte-exact (heads, descending bodies, zeroed Y of small blocks, chunk-tail mislabel), emptyDir, table
+    length and the directory as a sorted key -> value list"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    O = Oracle(g, threads=threads, preset=preset, index_type=2)
+    y0, e0, kv0, tl0 = O.hindex()
+    gen = lb.Genome(ctx, g)
+    index = lb.create_index(ctx, gen, 2, threads)
+    y1, e1, kv1, tl1 = index.export_hindex()
+    assert len(y0) == len(y1) and e0 == e1 and tl0 == tl1
+    assert np.array_equal(y0, y1)
+    assert np.array_equal(kv0, kv1)
+
+
+def test_hindex_apxmap_bit_exact(lb, ctx):
+    """-i 2 end to end: getHIndexMatchAll anchors (incl. head words consumed as bodies) and final cords"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    O = Oracle(g, threads=T, preset=preset, index_type=2)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 2, T)
+    cords, coff, dbg = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset, debug=True)
+    for i, r in enumerate(reads):
+        if len(r) <= 200:
+            continue
+        ra = dbg["ra"][int(dbg["ra_off"][i]):int(dbg["ra_off"][i + 1])]
+        assert np.array_equal(ra, O.stage(r, 1)[1:]), f"raw anchors, read {i}"
+    oc, oo = O.map_batch(bases, offs, map_threads=4)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+    if have_ref():
+        R = RefImpl(g, threads=T, preset=preset, index_type=2)
+        rc, ro = R.map_batch(bases, offs, map_threads=4)
+        assert np.array_equal(ro, coff) and np.array_equal(rc, cords)
