@@ -20,8 +20,9 @@ CLI = os.path.join(ROOT, "linear_b200", "csrc", "host", "linear_b200_filter")
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/linear did not travel")
-@pytest.mark.parametrize("name,threads,preset,bal", [("clean_hifi", 1, 0, 0), ("clean_hifi", 4, 1, 1), ("repeat_ont", 4, 1, 1)])
-def test_cli_apf_identical_to_reference_binary(tmp_path, name, threads, preset, bal):
+@pytest.mark.parametrize("name,threads,preset,bal,index_t", [("clean_hifi", 1, 0, 0, 1), ("clean_hifi", 4, 1, 1, 1), ("repeat_ont", 4, 1, 1, 1),
+                                                             ("clean_hifi", 1, 1, 0, 2), ("repeat_ont", 4, 1, 1, 2)])
+def test_cli_apf_identical_to_reference_binary(tmp_path, name, threads, preset, bal, index_t):
     assert os.path.exists(CLI), "run __graft_entry__.build()"
     g, reads, bases, offs, T, _ = make_case(name)
     gfa, rfa = str(tmp_path / "genome.fa"), str(tmp_path / "reads.fa")
@@ -29,7 +30,7 @@ def test_cli_apf_identical_to_reference_binary(tmp_path, name, threads, preset, 
     datagen.write_fasta(rfa, [f"read{i}" for i in range(len(reads))], reads)
     d_ref, d_new = tmp_path / "ref", tmp_path / "new"
     d_ref.mkdir(); d_new.mkdir()
-    common = ["filter", rfa, gfa, "-ot", "1", "-t", str(threads), "-p", str(preset), "-g", "0", "-b", str(bal)]
+    common = ["filter", rfa, gfa, "-ot", "1", "-t", str(threads), "-p", str(preset), "-g", "0", "-b", str(bal), "-i", str(index_t)]
     subprocess.run([REF_BIN] + common, cwd=d_ref, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
     subprocess.run([CLI] + common, cwd=d_new, check=True, timeout=900)
     a = open(d_ref / "reads.apf", "rb").read()
