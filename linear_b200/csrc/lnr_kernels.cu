@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -81,7 +82,7 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order, task_nhits, big_arena, big_list;
+    DevBuf remap_list, order, task_nhits, big_arena, big_list, seed_masks, seed_mask_off;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -565,11 +566,18 @@ __device__ __forceinline__ u32 find_task(const SeedTask * tasks, u32 n_tasks, u6
 __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
                                                     const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
                                                     const i32 * __restrict__ dir, const u64 * __restrict__ hs,
-                                                    u64 * __restrict__ info, u32 * __restrict__ count, unsigned long long * counters)
+                                                    u64 * __restrict__ info, u32 * __restrict__ count, unsigned long long * counters,
+                                                    u64 * __restrict__ masks, u32 * __restrict__ mask_off, u32 mask_cap,
+                                                    unsigned int * mask_used)
 {
+    // masks: one bit per scanned bucket record (1 = passes the Y-key rule), 64 records per word, so that the fill pass
+    // touches only the matching records instead of scanning every bucket a second time. Words are claimed from one
+    // pool with a warp-aggregated atomic; a sample that does not get words (pool exhausted) is re-scanned by the fill.
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     u32 c = 0, scanned = 0;
+    i32 bkt_b = 0, bkt_e = 0; u32 qY = 0;
+    bool active = false;
     u32 X = 0xffffffffu, ti = 0xffffffffu, m = 0;
     SeedTask t;
     memset(&t, 0, sizeof t);
@@ -599,14 +607,38 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         u64 inf = 0;
         if (sv.X != xprev)
         {
-            i32 b = __ldg(dir + sv.X), e = __ldg(dir + sv.X + 1);
-            for (i32 i = b; i < e; i++) c += ykey_match((u32)(__ldg(hs + i) & kMaskY), sv.Y) ? 1u : 0u;
-            scanned = (u32)(e - b);
-            inf = (u64)(u32)b | ((u64)(u32)(e - b) << 32) | ((u64)sv.Y << 48) | ((u64)sv.strand << 56);
+            bkt_b = __ldg(dir + sv.X); bkt_e = __ldg(dir + sv.X + 1);
+            qY = sv.Y;
+            scanned = (u32)(bkt_e - bkt_b);
+            active = scanned != 0;
+            inf = (u64)(u32)bkt_b | ((u64)scanned << 32) | ((u64)sv.Y << 48) | ((u64)sv.strand << 56);
         }
         info[s] = inf;
-        count[s] = c;
     }
+    // claim mask words: exclusive prefix of the per-lane word counts, one atomic per warp
+    u32 words = active ? (scanned + 63) >> 6 : 0;
+    u32 incl = words;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t2; }
+    u32 wtot = __shfl_sync(0xffffffffu, incl, 31);
+    u32 wbase = 0;
+    if (lane == 0 && wtot) wbase = atomicAdd(mask_used, wtot);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    u32 moff = wbase + incl - words;
+    bool have_mask = active && (u64)moff + words <= (u64)mask_cap;
+    if (active)
+    {
+        u64 m = 0; u32 wi = 0;
+        for (i32 i = bkt_b; i < bkt_e; i++)
+        {
+            bool hit = ykey_match((u32)(__ldg(hs + i) & kMaskY), qY);
+            c += hit ? 1u : 0u;
+            u32 bit = (u32)(i - bkt_b) & 63;
+            m |= (u64)hit << bit;
+            if (bit == 63 || i == bkt_e - 1) { if (have_mask) masks[moff + wi] = m; wi++; m = 0; }
+        }
+    }
+    if (s < n_samples) { count[s] = c; mask_off[s] = have_mask ? moff : 0xffffffffu; }
     // counters: H (records scanned), A (anchors)
     u32 tot_c = c, tot_s = scanned;
     for (int o = 16; o; o >>= 1) { tot_c += __shfl_xor_sync(0xffffffffu, tot_c, o); tot_s += __shfl_xor_sync(0xffffffffu, tot_s, o); }
@@ -615,13 +647,15 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
 // anchors of task ti start at aoff[sample0] + ti (slot 0 of the region is the sentinel)
 __global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read_off, const SeedTask * __restrict__ tasks, u32 n_tasks,
                                                    u64 n_samples, const u64 * __restrict__ hs, const u64 * __restrict__ info,
-                                                   const u64 * __restrict__ aoff, u64 * __restrict__ anchors)
+                                                   const u64 * __restrict__ aoff, u64 * __restrict__ anchors,
+                                                   const u32 * __restrict__ count, const u64 * __restrict__ masks,
+                                                   const u32 * __restrict__ mask_off)
 {
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_samples) return;
+    if (!count[s]) return;
     u64 inf = info[s];
     u32 nrec = (u32)(inf >> 32) & 0xffff;
-    if (!nrec) return;
     u32 ti = find_task(tasks, n_tasks, s);
     SeedTask t = tasks[ti];
     u32 m = (u32)(s - t.sample0) + 1;
@@ -629,11 +663,27 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read
     u64 L = read_off[t.read + 1] - read_off[t.read];
     u32 b = (u32)inf, Y = (u32)(inf >> 48) & 0xff, strand = (u32)(inf >> 56) & 1;
     u64 * out = anchors + aoff[s] + ti + 1;
-    for (u32 i = 0; i < nrec; i++)
+    u32 mo = mask_off[s];
+    if (mo != 0xffffffffu)
     {
-        u64 h = __ldg(hs + b + i);
-        if (ykey_match((u32)(h & kMaskY), Y)) *out++ = val2anchor(h, k, L, strand);
+        // only the records that matched in the count pass are read again (in bucket order)
+        for (u32 w = 0; w < (nrec + 63) >> 6; w++)
+        {
+            u64 mm = masks[mo + w];
+            while (mm)
+            {
+                int bit = __ffsll((long long)mm) - 1;
+                mm &= mm - 1;
+                *out++ = val2anchor(__ldg(hs + b + 64 * w + bit), k, L, strand);
+            }
+        }
     }
+    else
+        for (u32 i = 0; i < nrec; i++)
+        {
+            u64 h = __ldg(hs + b + i);
+            if (ykey_match((u32)(h & kMaskY), Y)) *out++ = val2anchor(h, k, L, strand);
+        }
 }
 
 #include "lnr_hindex.cuh"
@@ -1196,7 +1246,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->big_arena, &ctx->big_list})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off})
         b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1556,6 +1606,11 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     CK(ctx->sample_cnt.reserve((size_t)(n_samples + STILE + 1) * sizeof(u32)));
     CK(aoff_buf.reserve((size_t)(n_samples + STILE + 1) * sizeof(u64)));
     CK(ctx->misc.reserve(1024));
+    const u32 mask_cap = (u32)std::min<u64>(2 * n_samples + (1u << 20), 0xfffffff0ull);
+    CK(ctx->seed_masks.reserve((size_t)mask_cap * sizeof(u64)));
+    CK(ctx->seed_mask_off.reserve((size_t)(n_samples + 1) * sizeof(u32)));
+    unsigned int * d_mask_used = (unsigned int *)(ctx->misc.as<u64>() + 22);
+    CK(cudaMemsetAsync(d_mask_used, 0, sizeof(unsigned int), ctx->stream));
     u64 * d_total = ctx->misc.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
     const bool hx_mode = ix->index_type == 2;
@@ -1575,7 +1630,8 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
                                                                                    ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
         else
         k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dir,
-                                                                              ix->d_hs, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
+                                                                              ix->d_hs, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters,
+                                                                              ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>(), mask_cap, d_mask_used);
     }
     CK(cudaGetLastError());
     int rc = device_scan<u64>(ctx, ctx->sample_cnt.as<u32>(), n_samples + 1, 0, aoff_buf.as<u64>(), d_total, "k_scan_seeds");
@@ -1589,23 +1645,41 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     CK(ctx->anchorsB.reserve(need));
     if (n_samples)
     {
-        LaunchScope ls(ctx, "k_seed_fill");
+        LaunchScope ls(ctx, std::string(tag) == "k_seed_count" ? "k_seed_fill" : "k_seed_fill_remap");
         if (hx_mode)
             k_hseed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, hx,
                                                                                   ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>());
         else
         k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs,
-                                                                             ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>());
+                                                                             ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>(),
+                                                                             ctx->sample_cnt.as<u32>(), ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>());
     }
     CK(cudaGetLastError());
     return LNR_OK;
 }
 
 // ---- the batch ---------------------------------------------------------------------------------------------------
+struct HostTrace   // LNR_TRACE=1: host wall-clock of the phases of one batch (stderr)
+{
+    bool on; std::chrono::steady_clock::time_point t0; cudaStream_t st; std::string log;
+    HostTrace(cudaStream_t s) : on(getenv("LNR_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), st(s) {}
+    void lap(const char * what, bool sync = false)
+    {
+        if (!on) return;
+        if (sync) cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof b, " %s=%.3f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        log += b; t0 = t1;
+    }
+    ~HostTrace() { if (on) fprintf(stderr, "[lnr trace]%s\n", log.c_str()); }
+};
+
 static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, const lnr_params * prm, uint32_t n_reads,
                        const u8 * d_bases, const uint64_t * h_read_off, u64 * d_out, u64 * d_out_off, uint64_t out_cap,
                        uint64_t * n_cords_total, lnr_debug_out * dbg)
 {
+    HostTrace tr(ctx->stream);
     if (n_reads == 0) { if (n_cords_total) *n_cords_total = 0; return LNR_OK; }
     const float stop_ratio = prm && prm->preset == 0 ? 0.7f : 0.0f;
     // ---- host-side layout from the read lengths
@@ -1635,6 +1709,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     foff[n_reads] = nf_tot; ftile[n_reads] = n_ftiles; cbase[n_reads] = c_tot;
 
     const u64 total_bases = h_read_off[n_reads];
+    tr.lap("layout");
     // ---- uploads
     CK(ctx->read_off.reserve((n_reads + 1) * sizeof(u64)));
     CK(ctx->tasks.reserve(n_reads * sizeof(SeedTask)));
@@ -1660,6 +1735,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     u32 * d_queue = (u32 *)(ctx->misc.as<u64>() + 20);
     u32 * d_ntasks2 = d_queue + 1;
     u32 * d_nfail = d_queue + 2;
+    tr.lap("uploads");
     // ---- read features (both strands)
     if (n_ftiles)
     {
@@ -1672,6 +1748,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     u64 total_anchors = 0;
     int rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks.as<SeedTask>(), n_reads, n_samples, aoff, &total_anchors, "k_seed_count");
     if (rc) return rc;
+    tr.lap("feat+seed(sync)");
     if (dbg && dbg->raw_anchors_off)
     {
         // per-read raw anchors without the sentinel: copy region by region (debug path, not timed)
@@ -1741,6 +1818,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     a.counters = d_counters;
     if (dbg && dbg->hits_off) { a.dbg_hits = ctx->dbg_hits.as<u64>(); a.dbg_hoff = ctx->dbg_hoff.as<u64>(); a.dbg_nhits = ctx->dbg_nhits.as<u32>(); }
     if (dbg && dbg->cords1_off) { a.dbg_c1 = ctx->dbg_c1.as<u64>(); a.dbg_nc1 = ctx->dbg_nc1.as<u32>(); }
+    tr.lap("seed_fill", true);
     {
         LaunchScope ls(ctx, "k_order_tasks");
         k_order_tasks<<<1, 1024, 0, ctx->stream>>>(ctx->tasks.as<SeedTask>(), n_reads, aoff.as<u64>(), ctx->order.as<u32>());
@@ -1757,15 +1835,18 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         LaunchScope ls(ctx, "k_map_hits");
         k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 0, 0);
     }
+    tr.lap("hits", true);
     CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
     {
         LaunchScope ls(ctx, "k_map_hits_big");
         k_map_hits<<<8, 128, 0, ctx->stream>>>(a, 0, 1);
     }
+    tr.lap("hits_big", true);
     {
         LaunchScope ls(ctx, "k_map_extend");
         k_map_extend<<<(u32)(((u64)n_reads * ctx->extend_group + 127) / 128), 128, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0, ctx->extend_group);
     }
+    tr.lap("extend", true);
     CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
     CK(cudaMemsetAsync(d_queue + 3, 0, sizeof(u32), ctx->stream));
     {
@@ -1778,10 +1859,12 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         k_map_finish<<<8, 128, 0, ctx->stream>>>(a, ctx->order.as<u32>(), n_reads, 0, 1);
     }
     CK(cudaGetLastError());
+    tr.lap("launch_map");
     // ---- re-map pass
     u32 n_tasks2 = 0;
     CK(cudaMemcpyAsync(&n_tasks2, d_ntasks2, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    tr.lap("map(sync)");
     if (n_tasks2 > tasks2_cap) return fail(ctx, LNR_E_CAPACITY, "re-map task buffer exhausted");
     if (n_tasks2)
     {
@@ -1833,6 +1916,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         }
         CK(cudaGetLastError());
     }
+    tr.lap("remap", true);
     // ---- compaction into the caller's layout
     {
         LaunchScope ls(ctx, "k_slot_counts");
@@ -1852,6 +1936,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     u64 h_misc[128];
     CK(cudaMemcpyAsync(h_misc, ctx->misc.p, sizeof h_misc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    tr.lap("gather(sync)");
     u64 total_cords = h_misc[0];
     u32 n_fail = ((u32 *)(h_misc + 20))[2];
     ctx->counters[0] = n_samples;                 // S
