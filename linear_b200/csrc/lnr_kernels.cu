@@ -117,6 +117,7 @@ struct lnr_index
     i32 * d_dir;
     u64 * d_hs;
     uint64_t n_hs;
+    u8 * d_hsy = nullptr;    // low byte (the 8-bit Y key) of every hs record, split out for the seeding count pass
     // HIndex (include/index_util.h:139-248)
     u64 * d_ysa = nullptr;
     uint64_t n_ysa = 0, empty_dir = 0;
@@ -521,6 +522,14 @@ __global__ void __launch_bounds__(ST) k_scan_apply(const u32 * __restrict__ in, 
     for (int i = 0; i < SI; i++) { u64 idx = base + i; if (idx < n) out[idx] = (OutT)run; run += v[i]; }
 }
 
+// SoA split for the seeding count pass: the Y-key rule only looks at the low byte of a record (Y is 8 bits,
+// shape_extend.cpp:282), so buckets are scanned as bytes (1/8 of the traffic) and hs itself is read only for matches
+__global__ void k_idx_split_y(const u64 * __restrict__ hs, u64 n, u8 * __restrict__ hsy)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hsy[i] = (u8)(hs[i] & 0xff);
+}
+
 // ascending order inside each bucket (index_util.cpp:1788-1796); one thread per bucket, buckets <= 400
 __global__ void k_idx_sort_buckets(const i32 * __restrict__ dir, u64 * __restrict__ hs, u32 n_buckets)
 {
@@ -565,7 +574,7 @@ __device__ __forceinline__ u32 find_task(const SeedTask * tasks, u32 n_tasks, u6
 }
 __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
                                                     const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
-                                                    const i32 * __restrict__ dir, const u64 * __restrict__ hs,
+                                                    const i32 * __restrict__ dir, const u8 * __restrict__ hsy,
                                                     u64 * __restrict__ info, u32 * __restrict__ count, unsigned long long * counters,
                                                     u64 * __restrict__ masks, u32 * __restrict__ mask_off, u32 mask_cap,
                                                     unsigned int * mask_used)
@@ -631,7 +640,7 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         u64 m = 0; u32 wi = 0;
         for (i32 i = bkt_b; i < bkt_e; i++)
         {
-            bool hit = ykey_match((u32)(__ldg(hs + i) & kMaskY), qY);
+            bool hit = ykey_match((u32)__ldg(hsy + i), qY);
             c += hit ? 1u : 0u;
             u32 bit = (u32)(i - bkt_b) & 63;
             m |= (u64)hit << bit;
@@ -1449,6 +1458,8 @@ int lnr_index_from_device(lnr_ctx * ctx, const int32_t * dev_dir, const uint64_t
     }
     cudaMemcpyAsync(ix->d_dir, dev_dir, (size_t)kDirSize * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream);
     if (n_hs) cudaMemcpyAsync(ix->d_hs, dev_hs, (size_t)n_hs * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (cudaMalloc(&ix->d_hsy, (size_t)n_hs + 64) != cudaSuccess) { lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "cudaMalloc failed in lnr_index_from_device"); }
+    if (n_hs) k_idx_split_y<<<(u32)((n_hs + 255) / 256), 256, 0, ctx->stream>>>(ix->d_hs, n_hs, ix->d_hsy);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)); }
     *out = ix;
@@ -1533,6 +1544,12 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
         }
         CKI(cudaGetLastError());
     }
+    CKI(cudaMalloc(&ix->d_hsy, (size_t)total + 64));
+    if (total)
+    {
+        LaunchScope ls(ctx, "k_idx_split_y");
+        k_idx_split_y<<<(u32)((total + 255) / 256), 256, 0, ctx->stream>>>(ix->d_hs, total, ix->d_hsy);
+    }
     CKI(cudaStreamSynchronize(ctx->stream));
     cleanup();
 #undef CKI
@@ -1559,6 +1576,7 @@ void lnr_index_destroy(lnr_index * ix)
     cudaSetDevice(ix->ctx->device);
     if (ix->d_dir) cudaFree(ix->d_dir);
     if (ix->d_hs) cudaFree(ix->d_hs);
+    if (ix->d_hsy) cudaFree(ix->d_hsy);
     if (ix->d_ysa) cudaFree(ix->d_ysa);
     if (ix->d_tab) cudaFree(ix->d_tab);
     delete ix;
@@ -1630,7 +1648,7 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
                                                                                    ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
         else
         k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dir,
-                                                                              ix->d_hs, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters,
+                                                                              ix->d_hsy, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters,
                                                                               ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>(), mask_cap, d_mask_used);
     }
     CK(cudaGetLastError());
