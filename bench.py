@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 32768)))
+    ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 65536)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("LNR_BENCH_CPU_SAMPLE", 2048)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("LNR_BENCH_STREAMS", 2)),
@@ -445,11 +445,22 @@ def main():
         ms = kt[dom][0] / max(kt[dom][1], 1)
         ab = alg.get(dom, 0)
         ach = ab / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:   # dram__bytes_read+write of one `ncu --set full` capture (profiles/), scaled from its 32768-read batch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            if dom in tj:
+                traffic = tj[dom]["dram_bytes_per_read"] * n_reads
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab, "ms_per_launch": ms,
                 "share_of_step": (kt[dom][0] / args.steps) / step_ms_kernels if step_ms_kernels else None,
                 "whole_step": {"algorithmic_bytes": sum(alg.values()),
                                "achieved_GBps": sum(alg.values()) / (dt / args.steps) / 1e9}}
+    if roof is not None:
+        roof["per_kernel"] = {k: {"algorithmic_GBps": round(alg[k] / (kt[k][0] / max(kt[k][1], 1) * 1e-3) / 1e9, 1),
+                                  "frac": round(alg[k] / (kt[k][0] / max(kt[k][1], 1) * 1e-3) / 1e9 / peak, 4)}
+                              for k in alg if k in kt and kt[k][0] > 0}
     idx_alg = GENOME_BASES + 8 * n_hs + 4 * ((1 << 26) + 1) + GENOME_BASES + 12 * (GENOME_BASES // 16)
     index_info = {"seconds": round(t_index, 4), "seconds_e2e_from_host": None if t_index_e2e is None else round(t_index_e2e, 4),
                   "n_hs": n_hs, "algorithmic_bytes": idx_alg, "achieved_GBps": idx_alg / t_index / 1e9,

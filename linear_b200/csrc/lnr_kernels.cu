@@ -82,7 +82,7 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order, task_nhits, big_arena, big_list, seed_masks, seed_mask_off;
+    DevBuf remap_list, order, task_nhits, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -724,6 +724,7 @@ struct MapArgs
     u32 * task_nhits;                                  // hits per task after stage 1 (0xffffffff = scratch exhausted)
     u32 * big_list; u32 * n_big;                       // tasks whose scratch did not fit the per-warp arena: re-run with the big arena
     u8 * big_arena; u64 big_arena_per_warp;
+    u64 * warp_rec;                                    // optional: 16 u64 per warp, profile of its slowest task
     float stop_ratio;
     unsigned long long * counters;
     // optional debug
@@ -850,11 +851,18 @@ __global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass, int
             if (rc == 2) a.big_list[atomicAdd(a.n_big, 1u)] = ti;   // untouched: re-run with the big arena
         }
         if (!remap_pass) cnt.t[12]++;
-        if (!remap_pass && !big_pass && q == 0 && w.lane == 0)   // the longest read: its own stage profile (tail analysis)
-            for (int i = 0; i < 12; i++) a.counters[56 + i] = (unsigned long long)(cnt.t[i] - before.t[i]);
         u64 dt = (u64)(LNR_CLOCK() - t_read);
         cnt.t[14] += dt;
-        if (dt > cnt.t[13]) cnt.t[13] = dt;
+        if (dt > cnt.t[13])
+        {
+            cnt.t[13] = dt;
+            if (a.warp_rec && !remap_pass && !big_pass && w.lane == 0)   // this warp's slowest task so far (tail analysis)
+            {
+                u64 * rec = a.warp_rec + (u64)gw * 16;
+                for (int i = 0; i < 12; i++) rec[i] = cnt.t[i] - before.t[i];
+                rec[12] = dt; rec[13] = r; rec[14] = L; rec[15] = (u64)n;
+            }
+        }
     }
     if (w.lane == 0)
     {
@@ -1255,7 +1263,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1849,6 +1857,13 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(ctx->big_list.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
     a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
     a.big_list = ctx->big_list.as<u32>(); a.n_big = d_queue + 3;
+    const bool want_rec = getenv("LNR_LONGEST_PROFILE") != nullptr;
+    if (want_rec)
+    {
+        CK(ctx->warp_rec.reserve((size_t)n_warps * 16 * sizeof(u64)));
+        CK(cudaMemsetAsync(ctx->warp_rec.p, 0, (size_t)n_warps * 16 * sizeof(u64), ctx->stream));
+        a.warp_rec = ctx->warp_rec.as<u64>();
+    }
     {
         LaunchScope ls(ctx, "k_map_hits");
         k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 0, 0);
@@ -1966,7 +1981,14 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     ctx->counters[6] = total_bases;
     ctx->counters[7] = n_tasks2;
     for (int i = 0; i < 16; i++) ctx->stage_cycles[i] = h_misc[8 + 24 + i];
-    for (int i = 0; i < 12; i++) ctx->longest_cycles[i] = h_misc[8 + 56 + i];
+    if (want_rec)
+    {
+        std::vector<u64> rec((size_t)n_warps * 16);
+        CK(cudaMemcpy(rec.data(), ctx->warp_rec.p, rec.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+        size_t best = 0;
+        for (size_t wq = 0; wq < (size_t)n_warps; wq++) if (rec[wq * 16 + 12] > rec[best * 16 + 12]) best = wq;
+        for (int i = 0; i < 16; i++) ctx->longest_cycles[i] = rec[best * 16 + i];
+    }
     if (n_cords_total) *n_cords_total = total_cords;
     if (dbg && dbg->hits_off)
     {
@@ -2047,7 +2069,7 @@ int lnr_last_batch_stage_cycles(lnr_ctx * ctx, uint64_t cycles[16])
 {
     if (!ctx || !cycles) return LNR_E_ARG;
     for (int i = 0; i < 16; i++) cycles[i] = ctx->stage_cycles[i];
-    if (getenv("LNR_LONGEST_PROFILE")) for (int i = 0; i < 12; i++) cycles[i] = ctx->longest_cycles[i];
+    if (getenv("LNR_LONGEST_PROFILE")) for (int i = 0; i < 16; i++) cycles[i] = ctx->longest_cycles[i];
     return LNR_OK;
 }
 
