@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -60,9 +61,36 @@ struct DevBuf
     template <class T> T * as() const { return (T *)p; }
 };
 
+// Pinned host staging for the small per-batch tables (offsets, task descriptors). They reach the device through a copy
+// KERNEL that reads the pinned pages over PCIe, not through the copy engine: a small cudaMemcpyAsync queues behind any bulk
+// upload another host thread has in flight on the same engine and would stall this thread's batch for the whole upload.
+struct HostStage
+{
+    u8 * p = nullptr; size_t cap = 0, used = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        used = 0;
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc((void **)&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void * take(size_t bytes)
+    {
+        size_t b = (bytes + 15) & ~(size_t)15;
+        if (used + b > cap) return nullptr;
+        void * r = p + used; used += b; return r;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; used = 0; }
+};
+
 struct lnr_ctx
 {
     int device = 0;
+    HostStage stage;
     int n_sm = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -1265,6 +1293,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
                        &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
+    ctx->stage.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1685,6 +1714,32 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
 }
 
 // ---- the batch ---------------------------------------------------------------------------------------------------
+// One bulk host->device upload at a time per process: concurrent callers (the reference calls p_calRecords from -t
+// threads, each with its own lnr_ctx) would otherwise upload simultaneously at half the PCIe rate each and then all
+// compute simultaneously -- lockstep, copy engine and SMs idle in turn. Serialising the uploads staggers the callers so
+// that one thread's upload overlaps the others' kernels.
+static std::mutex g_upload_mutex;
+
+__global__ void k_stage_copy(const u8 * __restrict__ src, u8 * __restrict__ dst, size_t bytes)
+{
+    size_t n16 = bytes / 16;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = i; k < n16; k += step) ((uint4 *)dst)[k] = ((const uint4 *)src)[k];
+    for (size_t k = n16 * 16 + i; k < bytes; k += step) dst[k] = src[k];
+}
+// host table -> device through the pinned staging area (see HostStage); falls back to the copy engine when the staging
+// area is full
+static cudaError_t upload_small(lnr_ctx * ctx, void * dst, const void * src, size_t bytes)
+{
+    if (!bytes) return cudaSuccess;
+    void * st = ctx->stage.take(bytes);
+    if (!st) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    memcpy(st, src, bytes);
+    unsigned blocks = (unsigned)std::min<size_t>((bytes / 16 + 255) / 256 + 1, 296);
+    k_stage_copy<<<blocks, 256, 0, ctx->stream>>>((const u8 *)st, (u8 *)dst, bytes);
+    return cudaGetLastError();
+}
+
 struct HostTrace   // LNR_TRACE=1: host wall-clock of the phases of one batch (stderr)
 {
     bool on; std::chrono::steady_clock::time_point t0; cudaStream_t st; std::string log;
@@ -1749,11 +1804,12 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(ctx->ncords.reserve((size_t)(n_reads + STILE + 1) * sizeof(u32)));
     CK(ctx->out_off.reserve((size_t)(n_reads + STILE + 1) * sizeof(u64)));
     CK(ctx->misc.reserve(1024));
-    CK(cudaMemcpyAsync(ctx->read_off.p, h_read_off, (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), n_reads * sizeof(SeedTask), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->foff.p, foff.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->ftile.p, ftile.data(), (n_reads + 1) * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->cords_base.p, cbase.data(), (n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->stage.reserve(((size_t)n_reads + 1) * (3 * sizeof(u64) + 2 * sizeof(u32)) + ((size_t)n_reads * 5 + 1024) * sizeof(SeedTask) + 1024));
+    CK(upload_small(ctx, ctx->read_off.p, h_read_off, (n_reads + 1) * sizeof(u64)));
+    CK(upload_small(ctx, ctx->tasks.p, tasks.data(), n_reads * sizeof(SeedTask)));
+    CK(upload_small(ctx, ctx->foff.p, foff.data(), (n_reads + 1) * sizeof(u64)));
+    CK(upload_small(ctx, ctx->ftile.p, ftile.data(), (n_reads + 1) * sizeof(u32)));
+    CK(upload_small(ctx, ctx->cords_base.p, cbase.data(), (n_reads + 1) * sizeof(u64)));
     CK(cudaMemsetAsync(ctx->misc.p, 0, 1024, ctx->stream));
 
     const u64 * d_read_off = ctx->read_off.as<u64>();
@@ -1910,10 +1966,10 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         for (u32 i = 0; i < n_tasks2; i++) { t2[i].sample0 = ns2; ns2 += t2[i].n_samples; }
         std::vector<u32> remap_reads;
         for (uint32_t r = 0; r < n_reads; r++) if (slots[r].status == 1) remap_reads.push_back(r);
-        CK(cudaMemcpyAsync(ctx->tasks2.p, t2.data(), n_tasks2 * sizeof(SeedTask), cudaMemcpyHostToDevice, ctx->stream));
+        CK(upload_small(ctx, ctx->tasks2.p, t2.data(), n_tasks2 * sizeof(SeedTask)));
         CK(ctx->remap_list.reserve(std::max<size_t>(remap_reads.size(), 1) * sizeof(u32)));
         u32 * d_remap = ctx->remap_list.as<u32>();
-        CK(cudaMemcpyAsync(d_remap, remap_reads.data(), remap_reads.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        CK(upload_small(ctx, d_remap, remap_reads.data(), remap_reads.size() * sizeof(u32)));
         u64 total2 = 0;
         rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_remap");
         if (rc) return rc;
@@ -2045,8 +2101,12 @@ int lnr_apxmap_batch(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, 
     if (n_reads == 0) { cords_off[0] = 0; return LNR_OK; }
     u64 total_bases = read_off[n_reads];
     CK(ctx->bases.reserve((size_t)total_bases + 256));
-    CK(cudaMemcpyAsync(ctx->bases.p, bases, total_bases, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->bases.as<u8>() + total_bases, 0, 256, ctx->stream));
+    {
+        std::lock_guard<std::mutex> lk(g_upload_mutex);
+        CK(cudaMemcpyAsync(ctx->bases.p, bases, total_bases, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->bases.as<u8>() + total_bases, 0, 256, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     CK(ctx->out_cords.reserve((size_t)(cords_capacity + 8) * sizeof(u64)));
     u64 total = 0;
     int rc = apxmap_core(ctx, ix, f2, prm, n_reads, ctx->bases.as<u8>(), read_off, ctx->out_cords.as<u64>(), nullptr, cords_capacity, &total, dbg);
