@@ -600,6 +600,61 @@ __device__ __forceinline__ u32 find_task(const SeedTask * tasks, u32 n_tasks, u6
     while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tasks[mid].sample0 <= s) lo = mid; else hi = mid; }
     return lo;
 }
+
+// Fast path of seed_sample (lnr_core.h) for the common sample: a pure 21-base window (>= span steps after hashInit)
+// whose 4 bases of context on either side lie inside the read, and no N among those 29 bases. The bases are fetched as
+// 8 aligned words, packed to 2 bits each (one multiply per 4 bases), and the forward hash, the reverse-complement
+// hash (bit reversal), the selector sum (popcounts), the leftmost minimal 13-mer (min over offset-tagged keys) and
+// both flank keys are derived from that 58-bit value. Returns false when the sample needs the general evaluation.
+__device__ __forceinline__ bool seed_sample_fast(const u8 * __restrict__ rd, i64 L, const SeedTask & t, u32 m, SeedVal & sv)
+{
+    const i64 k0 = (i64)t.str + kSpanD;
+    const i64 p = k0 + (i64)t.alpha * m - 1;
+    if (p - k0 + 1 < kSpanD || p < 8 || p + 28 > L) return false;
+    const u8 * q = rd + p - 4;
+    const unsigned sh = ((unsigned)(uintptr_t)q & 3u) * 8u;
+    const u32 * pw = (const u32 *)((uintptr_t)q & ~(uintptr_t)3);
+    u32 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = __ldg(pw + i);
+    u32 A[8], any = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) A[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    A[7] = (w[7] >> sh) & 0xffu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) any |= A[i];
+    if (any & 0xfcfcfcfcu) return false;
+    u32 qb[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) qb[i] = (A[i] * 0x40100401u) >> 24;   // bases 4i..4i+3 -> 8 bits, first base on top
+    const u32 Phi = (qb[0] << 24) | (qb[1] << 16) | (qb[2] << 8) | qb[3];
+    const u32 Plo = (qb[4] << 24) | (qb[5] << 16) | (qb[6] << 8) | qb[7];
+    const u64 P = ((u64)Phi << 32) | Plo;              // base j (position p-4+j) at bits 2(31-j)
+    const u64 M42 = (1ULL << 42) - 1;
+    const u64 h = (P >> 14) & M42;                      // window = j 4..24
+    // complement + reverse the pairs: base j at bits 2j
+    u64 y = __brevll(~P);
+    const u64 Pc = ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
+    const u64 cr = (Pc >> 8) & M42;
+    const int sum = __popcll(h & 0x5555555555555555ULL) + 2 * __popcll(h & 0xAAAAAAAAAAAAAAAAULL);
+    const int x = 2 * sum - 3 * kSpanD + t.bias;
+    const u32 strand = x > 0 ? 0u : 1u;
+    const u64 v2 = strand ? cr : h;
+    u32 best = 0xffffffffu;
+#pragma unroll
+    for (int o = 0; o <= 8; o++)
+    {
+        const int s2 = 2 * (8 - o) - 4;                 // minimizer candidate into bits 4..29, offset tag below it
+        u32 key = s2 >= 0 ? (u32)(v2 >> s2) : (u32)(v2 << (-s2));
+        key = (key & 0x3ffffff0u) | (u32)o;
+        best = min(best, key);
+    }
+    const u32 off = best & 15u;
+    sv.X = best >> 4;
+    sv.strand = strand;
+    sv.Y = strand ? (u32)(Pc >> (2 * (8 - off))) & 0xffu : (u32)(P >> (2 * (11 - off))) & 0xffu;
+    return true;
+}
 __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
                                                     const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
                                                     const i32 * __restrict__ dir, const u8 * __restrict__ hsy,
@@ -628,7 +683,7 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         u64 L = read_off[t.read + 1] - read_off[t.read];
         acc.s = bases + read_off[t.read]; acc.len = (i64)L;
         u32 k;
-        seed_sample(acc, t, m, sv, k);
+        if (!seed_sample_fast(acc.s, acc.len, t, m, sv)) seed_sample(acc, t, m, sv, k);
         X = sv.X;
     }
     // X of the previous sample of the same task: the lane below usually holds it, otherwise it is recomputed
@@ -639,7 +694,7 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         if (m > 1)
         {
             if (lane > 0 && til == ti && ml == m - 1) xprev = xl;
-            else { SeedVal pv; u32 kp; seed_sample(acc, t, m - 1, pv, kp); xprev = pv.X; }
+            else { SeedVal pv; u32 kp; if (!seed_sample_fast(acc.s, acc.len, t, m - 1, pv)) seed_sample(acc, t, m - 1, pv, kp); xprev = pv.X; }
         }
         u64 inf = 0;
         if (sv.X != xprev)
@@ -658,28 +713,67 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t2; }
     u32 wtot = __shfl_sync(0xffffffffu, incl, 31);
-    u32 wbase = 0;
-    if (lane == 0 && wtot) wbase = atomicAdd(mask_used, wtot);
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    u32 moff = wbase + incl - words;
+    // one atomic per CTA (a same-address atomic per warp serialises in L2)
+    __shared__ u32 s_w[8], s_base;
+    const unsigned wid = threadIdx.x >> 5;
+    if (lane == 0) s_w[wid] = wtot;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        u32 tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { u32 v = s_w[i]; s_w[i] = tot; tot += v; }
+        s_base = tot ? atomicAdd(mask_used, tot) : 0u;
+    }
+    __syncthreads();
+    u32 moff = s_base + s_w[wid] + incl - words;
     bool have_mask = active && (u64)moff + words <= (u64)mask_cap;
     if (active)
     {
-        u64 m = 0; u32 wi = 0;
-        for (i32 i = bkt_b; i < bkt_e; i++)
+        // 4 Y bytes per step from aligned words; ykey_match(b, Y) with v = b ^ Y, l = lowest set bit of v:
+        // v == 0 or v >> ctz(v) < 4  <=>  v <= 3 l
+        const u8 * pb = hsy + bkt_b;
+        const unsigned sh = ((unsigned)(uintptr_t)pb & 3u) * 8u;
+        const u32 * pw = (const u32 *)((uintptr_t)pb & ~(uintptr_t)3);
+        const u32 Y4 = qY * 0x01010101u;
+        u32 w0 = __ldg(pw);
+        u64 mb = 0; u32 wi = 0;
+        for (u32 i = 0; i < scanned; i += 4)
         {
-            bool hit = ykey_match((u32)__ldg(hsy + i), qY);
-            c += hit ? 1u : 0u;
-            u32 bit = (u32)(i - bkt_b) & 63;
-            m |= (u64)hit << bit;
-            if (bit == 63 || i == bkt_e - 1) { if (have_mask) masks[moff + wi] = m; wi++; m = 0; }
+            u32 w1 = __ldg(pw + (i >> 2) + 1);
+            u32 v4 = __funnelshift_r(w0, w1, sh) ^ Y4;
+            w0 = w1;
+            u32 h4 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                u32 v = (v4 >> (8 * j)) & 0xffu;
+                u32 l = v & (0u - v);
+                h4 |= v <= 3u * l ? (1u << j) : 0u;
+            }
+            u32 rem = scanned - i;
+            if (rem < 4) h4 &= (1u << rem) - 1u;
+            c += __popc(h4);
+            u32 bit = i & 63u;
+            mb |= (u64)h4 << bit;
+            if (bit == 60 || rem <= 4) { if (have_mask) masks[moff + wi] = mb; wi++; mb = 0; }
         }
     }
     if (s < n_samples) { count[s] = c; mask_off[s] = have_mask ? moff : 0xffffffffu; }
     // counters: H (records scanned), A (anchors)
     u32 tot_c = c, tot_s = scanned;
     for (int o = 16; o; o >>= 1) { tot_c += __shfl_xor_sync(0xffffffffu, tot_c, o); tot_s += __shfl_xor_sync(0xffffffffu, tot_s, o); }
-    if ((threadIdx.x & 31) == 0 && (tot_c | tot_s)) { atomicAdd(&counters[1], (unsigned long long)tot_s); atomicAdd(&counters[2], (unsigned long long)tot_c); }
+    __shared__ u32 s_c[8], s_s[8];
+    if (lane == 0) { s_c[wid] = tot_c; s_s[wid] = tot_s; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long bc = 0, bs = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { bc += s_c[i]; bs += s_s[i]; }
+        if (bs) atomicAdd(&counters[1], bs);
+        if (bc) atomicAdd(&counters[2], bc);
+    }
 }
 // anchors of task ti start at aoff[sample0] + ti (slot 0 of the region is the sentinel)
 __global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read_off, const SeedTask * __restrict__ tasks, u32 n_tasks,
@@ -834,7 +928,10 @@ __global__ void __launch_bounds__(1024) k_order_tasks(const SeedTask * __restric
 
 // ---- stage 1: hits. One warp per seeding task (primary pass: task r = read r; re-map pass: one task per gap).
 // Everything of apxMap_ up to and including _filterHits; the hits replace the task's anchors in A.
-__global__ void __launch_bounds__(128) k_map_hits(MapArgs a, int remap_pass, int big_pass)
+#ifndef LNR_HITS_MIN_CTAS
+#define LNR_HITS_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, int remap_pass, int big_pass)
 {
     // big_pass: second, tiny launch over the tasks that exhausted the 2 MB per-warp arena (reads with very many
     // anchors), a few warps with a large arena each
