@@ -130,6 +130,11 @@ int lnr_last_batch_stage_cycles(lnr_ctx *, uint64_t cycles[16]);
 int lnr_read_features(lnr_ctx *, const uint8_t * dna5, uint64_t len, int feature_type,
                       void * dst_fwd, void * dst_rev, uint64_t cap_entries, uint64_t * n_entries);
 
+/* self-test of the warp-cooperative std::sort emulation used by chainAnchorsHits (pmpfinder.cpp:2465 sorts by
+ * AnchorX only, so tied anchors end up in libstdc++'s introsort order): sorts n 64-bit records in place, ascending by
+ * their high 32 bits (30 significant), with one warp. Parity tests compare the result with std::sort on the host. */
+int lnr_selftest_sort(lnr_ctx *, uint64_t * records, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,4 +5,4 @@ api.py (ctypes mirror of the reference's operator interface for the path) and da
 """
 from . import datagen  # noqa: F401
 from .api import (Context, Features, Genome, Index, LnrError, apx_map_batch, cords_end, create_features,  # noqa: F401
-                  create_index, load_library, read_features)
+                  create_index, load_library, read_features, selftest_sort)

@@ -31,7 +31,7 @@ EXPORTS = [
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
     "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch",
-    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_stage_cycles", "lnr_read_features",
+    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
 ]
 
 
@@ -295,6 +295,13 @@ def read_features(ctx: Context, read: np.ndarray, feature_type: int = 2):
         ctx.check(ctx.lib.lnr_read_features(ctx.h, read.ctypes.data_as(u8p), len(read), feature_type,
                                             f.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
     return f, r
+
+
+def selftest_sort(ctx: Context, records: np.ndarray) -> np.ndarray:
+    """std::sort-order sort of uint64 records by their high 32 bits with one warp (lnr_selftest_sort)"""
+    a = np.ascontiguousarray(records, dtype=np.uint64).copy()
+    ctx.check(ctx.lib.lnr_selftest_sort(ctx.h, a.ctypes.data_as(u64p), len(a)))
+    return a
 
 
 def apx_map_batch(ctx: Context, index: Index, feats: Features, bases, offsets, preset: int = 1, debug: bool = False,

@@ -110,10 +110,11 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order, task_nhits, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
+    DevBuf remap_list, order, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
+    int sort_ctas_per_sm = 8, chain_ctas_per_sm = 6, blocks_ctas_per_sm = 6;   // residency of the three hit-section kernels (their launch bounds)
     int extend_group = 32;
     size_t arena_bytes_per_warp = 4u << 20;
 };
@@ -209,6 +210,7 @@ static void harvest_stats(lnr_ctx * ctx)
 // =====================================================================================================
 // device helpers
 // =====================================================================================================
+__device__ __forceinline__ u64 globaltimer_ns() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 struct GAcc   // bounds-checked byte view of one sequence in global memory; out of range reads as 0
 {
     const u8 * s; i64 len;
@@ -231,12 +233,72 @@ struct GRcAcc   // reverse-complement view (_compltRvseStr base.cpp:335)
 static const int FT = 256;           // threads per CTA = cells per CTA
 static const int FE = FT - 2;        // entries per CTA
 
-template <class Acc>
-__device__ __forceinline__ void feat_tile(Acc acc, u32 e0, u32 n_entries, F96 * out, u64 * s_lo, u32 * s_hi)
+// ---- table-driven cell for N-free interior cells ----------------------------------------------------------------
+// The 17 bases of a cell are fetched as 5 aligned words and packed to 2 bits each (Q: base i at bits 2(16-i)); the
+// reverse strand's cell is the pair-reversed complement of the forward 17 bases. A 256-entry shared table holds the
+// field increments of the three 2-mers inside every 4-base window, so a cell is 5 table adds + one 2-mer add.
+struct FeatTab { u64 lo3[256]; u32 hi3[256]; u64 lo2[16]; u32 hi2[16]; };
+__device__ __forceinline__ void feat_add(u32 id, u64 & lo, u32 & hi)
 {
-    u32 c = e0 + threadIdx.x;        // cell index
+    if (id < 10) lo += 1ULL << (6 * id);
+    else if (id < 15) hi += 1u << (6 * (id - 10));
+}
+__device__ __forceinline__ void feat_tab_init(FeatTab & T)   // blockDim.x == 256, caller syncs
+{
+    u32 t = threadIdx.x, a = t >> 6, b = (t >> 4) & 3, c = (t >> 2) & 3, d = t & 3;
     u64 lo = 0; u32 hi = 0;
-    if (c < n_entries + 2) feat_cell(acc, 16 * (i64)c, lo, hi);
+    feat_add(4 * a + b, lo, hi); feat_add(4 * b + c, lo, hi); feat_add(4 * c + d, lo, hi);
+    T.lo3[t] = lo; T.hi3[t] = hi;
+    if (t < 16) { lo = 0; hi = 0; feat_add(t, lo, hi); T.lo2[t] = lo; T.hi2[t] = hi; }
+}
+__device__ __forceinline__ bool load17_packed(const u8 * q, u64 & Q)   // needs [q & ~3, q + 20) readable; false on N
+{
+    const unsigned sh = ((unsigned)(uintptr_t)q & 3u) * 8u;
+    const u32 * pw = (const u32 *)((uintptr_t)q & ~(uintptr_t)3);
+    u32 w[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = __ldg(pw + i);
+    u32 A[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) A[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    const u32 b16 = (w[4] >> sh) & 0xffu;
+    if ((A[0] | A[1] | A[2] | A[3] | b16) & 0xfcfcfcfcu) return false;
+    u32 hi32 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) hi32 = (hi32 << 8) | ((A[i] * 0x40100401u) >> 24);
+    Q = ((u64)hi32 << 2) | b16;
+    return true;
+}
+__device__ __forceinline__ u64 rc34(u64 Q)
+{
+    u64 y = __brevll(~Q) >> 30;
+    return (((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1)) & ((1ULL << 34) - 1);
+}
+__device__ __forceinline__ void feat_cell_tab(const FeatTab & T, u64 Q, u64 & lo, u32 & hi)
+{
+    lo = T.lo2[Q & 15]; hi = T.hi2[Q & 15];
+#pragma unroll
+    for (int g = 0; g < 5; g++)
+    {
+        u32 idx = (u32)(Q >> (2 * (13 - 3 * g))) & 0xffu;
+        lo += T.lo3[idx]; hi += T.hi3[idx];
+    }
+}
+template <bool RC>
+__device__ __forceinline__ void feat_tile_reads(const u8 * buf0, const u8 * s, i64 L, u32 e0, u32 n_entries, F96 * out, u64 * s_lo,
+                                                u32 * s_hi, const FeatTab & T)
+{
+    u32 c = e0 + threadIdx.x;
+    u64 lo = 0; u32 hi = 0;
+    if (c < n_entries + 2)
+    {
+        const i64 f0 = RC ? L - 17 - 16 * (i64)c : 16 * (i64)c;   // forward position of the cell's lowest base
+        u64 Q;
+        if (f0 >= 0 && f0 + 20 <= L && (const u8 *)((uintptr_t)(s + f0) & ~(uintptr_t)3) >= buf0 && load17_packed(s + f0, Q))
+            feat_cell_tab(T, RC ? rc34(Q) : Q, lo, hi);
+        else if (RC) { GRcAcc acc = {s, L}; feat_cell(acc, 16 * (i64)c, lo, hi); }
+        else { GAcc acc = {s, L}; feat_cell(acc, 16 * (i64)c, lo, hi); }
+    }
     s_lo[threadIdx.x] = lo;
     s_hi[threadIdx.x] = hi;
     __syncthreads();
@@ -308,6 +370,9 @@ __global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases
 {
     __shared__ u64 s_lo[FT];
     __shared__ u32 s_hi[FT];
+    __shared__ FeatTab T;
+    feat_tab_init(T);
+    __syncthreads();
     u32 tile = blockIdx.x;
     u32 lo_i = 0, hi_i = n_reads;   // largest r with ftile[r] <= tile
     while (hi_i - lo_i > 1) { u32 mid = (lo_i + hi_i) >> 1; if (ftile[mid] <= tile) lo_i = mid; else hi_i = mid; }
@@ -320,8 +385,8 @@ __global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases
     u32 e0 = (t - strand * tps) * FE;
     F96 * o = out + foff[r] + (u64)strand * nf;
     const u8 * s = bases + read_off[r];
-    if (!strand) { GAcc acc = {s, (i64)L}; feat_tile(acc, e0, nf, o, s_lo, s_hi); }
-    else { GRcAcc acc = {s, (i64)L}; feat_tile(acc, e0, nf, o, s_lo, s_hi); }
+    if (!strand) feat_tile_reads<false>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
+    else feat_tile_reads<true>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
 }
 
 // =====================================================================================================
@@ -844,9 +909,12 @@ struct MapArgs
     const u32 * order;                                 // reads sorted by length, longest first (tail latency)
     int index_type;                                    // 1 DIndex, 2 HIndex (sample grid of re-map tasks)
     u32 * task_nhits;                                  // hits per task after stage 1 (0xffffffff = scratch exhausted)
+    u32 * task_state;                                  // primary pass, between the hit sections: n2 after k_hits_sort, hits after
+                                                       // k_hits_chain; 0 = the task is finished, 0xffffffff = left to the big-arena pass
     u32 * big_list; u32 * n_big;                       // tasks whose scratch did not fit the per-warp arena: re-run with the big arena
     u8 * big_arena; u64 big_arena_per_warp;
     u64 * warp_rec;                                    // optional: 16 u64 per warp, profile of its slowest task
+    u64 warp_rec_stage_off;                            // u64 offset of the section kernels' records (8 per warp and section)
     float stop_ratio;
     unsigned long long * counters;
     // optional debug
@@ -929,7 +997,7 @@ __global__ void __launch_bounds__(1024) k_order_tasks(const SeedTask * __restric
 // ---- stage 1: hits. One warp per seeding task (primary pass: task r = read r; re-map pass: one task per gap).
 // Everything of apxMap_ up to and including _filterHits; the hits replace the task's anchors in A.
 #ifndef LNR_HITS_MIN_CTAS
-#define LNR_HITS_MIN_CTAS 1
+#define LNR_HITS_MIN_CTAS 6
 #endif
 __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, int remap_pass, int big_pass)
 {
@@ -945,12 +1013,16 @@ __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, 
     u32 * bins = a.bins + (u64)gw * kNumBins;
     PipeCounters cnt;
     memset(&cnt, 0, sizeof cnt);
+    const bool want_rec = a.warp_rec && !remap_pass && !big_pass;
+    u64 g_start = 0, g_task = 0, n_done = 0, g_busy = 0;
+    if (want_rec) g_start = globaltimer_ns();
     while (true)
     {
         u32 q = 0;
         if (w.lane == 0) q = atomicAdd(a.queue, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= n_units) break;
+        if (want_rec) { g_task = globaltimer_ns(); n_done++; }
         u32 ti = big_pass ? a.big_list[q] : (remap_pass ? q : a.order[q]);   // primary: heaviest reads first
         const SeedTask t = a.tasks[ti];
         u32 r = t.read;
@@ -978,16 +1050,22 @@ __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, 
         if (!remap_pass) cnt.t[12]++;
         u64 dt = (u64)(LNR_CLOCK() - t_read);
         cnt.t[14] += dt;
+        if (want_rec) g_busy += globaltimer_ns() - g_task;
         if (dt > cnt.t[13])
         {
             cnt.t[13] = dt;
             if (a.warp_rec && !remap_pass && !big_pass && w.lane == 0)   // this warp's slowest task so far (tail analysis)
             {
-                u64 * rec = a.warp_rec + (u64)gw * 16;
+                u64 * rec = a.warp_rec + (u64)gw * 24;
                 for (int i = 0; i < 12; i++) rec[i] = cnt.t[i] - before.t[i];
-                rec[12] = dt; rec[13] = r; rec[14] = L; rec[15] = (u64)n;
+                rec[12] = dt; rec[13] = r; rec[14] = L; rec[15] = (u64)n; rec[18] = g_task; rec[20] = q;
             }
         }
+    }
+    if (want_rec && w.lane == 0)
+    {
+        u64 * rec = a.warp_rec + (u64)gw * 24;
+        rec[16] = g_start; rec[17] = globaltimer_ns(); rec[19] = n_done; rec[21] = g_busy; rec[22] = cnt.t[14];
     }
     if (w.lane == 0)
     {
@@ -999,6 +1077,200 @@ __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, 
                 else atomicAdd(&a.counters[24 + i], (unsigned long long)cnt.t[i]);
             }
     }
+}
+
+// ---- primary pass of stage 1 as three kernels, one per section of the hit stage (lnr_pipeline.h hits_sec_*). Per-task
+// state between them lives in the task's own anchor regions: k_hits_sort leaves the x-sorted anchors in A[0..n2),
+// k_hits_chain the chained hits in B[0..n_hits) and their scores (int32) in A, k_hits_blocks the final hits in A.
+struct StageCommon
+{
+    Warp w; u32 gw; Arena ar; PipeCounters cnt;
+    // LNR_LONGEST_PROFILE: when this warp started / retired and its slowest task
+    u64 * rec; u64 g_start; long long t_task; u64 max_dur, max_ti, max_size, max_q, q, n_done;
+};
+__device__ __forceinline__ void stage_begin(const MapArgs & a, StageCommon & c)
+{
+    c.w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
+    c.gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    c.ar = {a.arena + (u64)c.gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
+    memset(&c.cnt, 0, sizeof c.cnt);
+    c.rec = nullptr;
+}
+__device__ __forceinline__ void stage_rec_begin(const MapArgs & a, StageCommon & c, int stage)
+{
+    if (!a.warp_rec) return;
+    c.rec = a.warp_rec + ((u64)stage * gridDim.x * (blockDim.x >> 5) + c.gw) * 8 + (u64)a.warp_rec_stage_off;
+    c.g_start = globaltimer_ns(); c.max_dur = 0; c.max_ti = 0; c.max_size = 0; c.max_q = 0; c.n_done = 0; c.t_task = 0;
+}
+__device__ __forceinline__ void stage_task_done(StageCommon & c, u32 ti, u64 size)
+{
+    if (!c.rec) return;
+    u64 d = (u64)(clock64() - c.t_task);
+    c.n_done++;
+    if (d > c.max_dur) { c.max_dur = d; c.max_ti = ti; c.max_size = size; c.max_q = c.q; }
+}
+__device__ __forceinline__ bool stage_next(const MapArgs & a, StageCommon & c, u32 & ti)
+{
+    u32 q = 0;
+    if (c.w.lane == 0) q = atomicAdd(a.queue, 1u);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= a.n_tasks) return false;
+    ti = a.order[q];                     // heaviest reads first
+    if (c.rec) { c.q = q; c.t_task = clock64(); }
+    return true;
+}
+__device__ __forceinline__ void stage_end(const MapArgs & a, const StageCommon & c)
+{
+    if (c.rec && c.w.lane == 0)
+    {
+        c.rec[0] = c.g_start; c.rec[1] = globaltimer_ns(); c.rec[2] = c.max_dur; c.rec[3] = c.max_ti; c.rec[4] = c.max_size;
+        c.rec[5] = c.max_q; c.rec[6] = c.n_done;
+    }
+    if (c.w.lane == 0)
+    {
+        if (c.cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)c.cnt.hits);
+        for (int i = 0; i < 16; i++)
+            if (c.cnt.t[i])
+            {
+                if (i == 13) atomicMax(&a.counters[24 + i], (unsigned long long)c.cnt.t[i]);
+                else atomicAdd(&a.counters[24 + i], (unsigned long long)c.cnt.t[i]);
+            }
+    }
+}
+__device__ __forceinline__ void task_region(const MapArgs & a, u32 ti, const SeedTask & t, u64 & base, int & n)
+{
+    u64 s0 = t.sample0, s1 = s0 + t.n_samples;
+    base = a.aoff[s0] + ti;
+    n = (int)(a.aoff[s1] - a.aoff[s0]) + 1;
+}
+
+__global__ void __launch_bounds__(128, 8) k_hits_sort(MapArgs a)
+{
+    __shared__ u32 s_hist[4][256];
+    StageCommon c;
+    stage_begin(a, c);
+    const Warp w = c.w;
+    u32 * bins = a.bins + (u64)c.gw * kNumBins;
+    stage_rec_begin(a, c, 0);
+    u32 ti;
+    while (stage_next(a, c, ti))
+    {
+        const SeedTask t = a.tasks[ti];
+        u32 r = t.read;
+        u64 L = a.read_off[r + 1] - a.read_off[r];
+        if (w.lane == 0) { a.task_nhits[ti] = 0; a.task_state[ti] = 0; }
+        if (L <= (u64)kMinReadLen) continue;            // mapper.cpp:440
+        long long tl = LNR_CLOCK();
+        u64 base; int n;
+        task_region(a, ti, t, base, n);
+        if (w.lane == 0 && a.dbg_hits)
+        {
+            a.dbg_nhits[r] = 1;
+            if (a.dbg_hoff[r + 1] > a.dbg_hoff[r]) a.dbg_hits[a.dbg_hoff[r]] = kFlagEnd;
+        }
+        c.cnt.t[12]++;
+        if (phase_map_scratch_bound(n) > c.ar.cap)
+        {
+            // does not fit the per-warp arena: the whole task is left, untouched, to the big-arena pass
+            if (w.lane == 0) { a.task_nhits[ti] = 0xffffffffu; a.task_state[ti] = 0xffffffffu; a.big_list[atomicAdd(a.n_big, 1u)] = ti; }
+            continue;
+        }
+        arena_reset(c.ar);
+        u64 * A = a.A + base;
+        u64 * X; int n2;
+        int rc = hits_sec_sort(w, c.ar, s_hist[threadIdx.x >> 5], bins, A, a.B + base, n, c.cnt, tl, X, n2);
+        if (rc == 0)
+        {
+            if (X != A)
+            {
+                for (int i = w.lane; i < n2; i += 32) A[i] = X[i];
+            }
+            if (w.lane == 0) a.task_state[ti] = (u32)n2;
+        }
+        else if (rc == 1 && w.lane == 0) { a.task_nhits[ti] = 0xffffffffu; a.task_state[ti] = 0; }
+        __syncwarp();
+        stage_task_done(c, ti, (u64)n);
+    }
+    stage_end(a, c);
+}
+
+__global__ void __launch_bounds__(128, 6) k_hits_chain(MapArgs a)
+{
+    StageCommon c;
+    stage_begin(a, c);
+    const Warp w = c.w;
+    stage_rec_begin(a, c, 1);
+    u32 ti;
+    while (stage_next(a, c, ti))
+    {
+        const u32 n2 = a.task_state[ti];
+        if (n2 == 0 || n2 == 0xffffffffu) continue;
+        const SeedTask t = a.tasks[ti];
+        long long tl = LNR_CLOCK();
+        PipeIn in;
+        fill_pipe_in(a, t.read, in);
+        u64 base; int n;
+        task_region(a, ti, t, base, n);
+        arena_reset(c.ar);
+        i32 * score = arena_alloc<i32>(c.ar, (u64)n2 + 2);
+        int n_hits = 1;
+        int rc = c.ar.failed ? 1 : hits_sec_chain(w, c.ar, in, a.A + base, (int)n2, 0, a.B + base, score, n_hits, c.cnt, tl);
+        if (rc == 0)
+        {
+            i32 * dst = (i32 *)(a.A + base);             // the anchors are consumed: A now carries the hit scores
+            for (int i = w.lane; i < n_hits; i += 32) dst[i] = score[i];
+            if (w.lane == 0) a.task_state[ti] = (u32)n_hits;
+        }
+        else if (w.lane == 0) { a.task_nhits[ti] = 0xffffffffu; a.task_state[ti] = 0; }
+        __syncwarp();
+        stage_task_done(c, ti, (u64)n2);
+    }
+    stage_end(a, c);
+}
+
+__global__ void __launch_bounds__(128, 6) k_hits_blocks(MapArgs a)
+{
+    StageCommon c;
+    stage_begin(a, c);
+    const Warp w = c.w;
+    stage_rec_begin(a, c, 2);
+    u32 ti;
+    while (stage_next(a, c, ti))
+    {
+        const u32 nh = a.task_state[ti];
+        if (nh == 0 || nh == 0xffffffffu) continue;
+        const SeedTask t = a.tasks[ti];
+        const u32 r = t.read;
+        long long tl = LNR_CLOCK();
+        PipeIn in;
+        fill_pipe_in(a, r, in);
+        u64 base; int n;
+        task_region(a, ti, t, base, n);
+        arena_reset(c.ar);
+        int n_hits = (int)nh;
+        i32 * score = arena_alloc<i32>(c.ar, (u64)n_hits + 2);
+        int rc = 1;
+        if (!c.ar.failed)
+        {
+            const i32 * src = (const i32 *)(a.A + base);
+            for (int i = w.lane; i < n_hits; i += 32) score[i] = src[i];
+            __syncwarp();
+            u64 * dh = a.dbg_hits ? a.dbg_hits + a.dbg_hoff[r] : (u64 *)0;
+            u32 dcap = dh ? (u32)(a.dbg_hoff[r + 1] - a.dbg_hoff[r]) : 0;
+            u64 * H;
+            rc = hits_sec_blocks(w, c.ar, in, a.B + base, score, n_hits, H, dh, dh ? a.dbg_nhits + r : (u32 *)0, dcap, c.cnt, tl);
+            if (rc == 0)
+            {
+                u64 * out = a.A + base;
+                for (int i = w.lane; i < n_hits; i += 32) out[i] = H[i];
+                if (w.lane == 0) a.task_nhits[ti] = (u32)n_hits;
+            }
+        }
+        if (rc == 1 && w.lane == 0) a.task_nhits[ti] = 0xffffffffu;
+        __syncwarp();
+        stage_task_done(c, ti, (u64)nh);
+    }
+    stage_end(a, c);
 }
 
 // ---- stage 2: window extension (path_dst_2 + extendWindow), ONE THREAD PER READ. The per-step work (3 candidate
@@ -1355,6 +1627,15 @@ static int hindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned T, lnr_ind
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
+struct SelfKeyHi { __device__ u64 operator()(u64 v) const { return v >> 32; } };
+__global__ void k_selftest_sort(u64 * a, u64 * s0, u64 * s1, int n, u64 * out)
+{
+    __shared__ u32 hist[256];
+    Warp w = {(int)threadIdx.x, 32, 0xffffffffu};
+    u64 * r = gnu_sort_w(w, hist, a, s0, s1, n, 32, SelfKeyHi());
+    for (int i = threadIdx.x; i < n; i += 32) out[i] = r[i];
+}
+
 extern "C" {
 
 int lnr_ctx_create(int device, lnr_ctx ** out)
@@ -1370,11 +1651,28 @@ int lnr_ctx_create(int device, lnr_ctx ** out)
     cudaGetDeviceProperties(&prop, device);
     ctx->n_sm = prop.multiProcessorCount;
     if (const char * e = getenv("LNR_MAP_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->map_ctas_per_sm = v; }
+    if (const char * e = getenv("LNR_SORT_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->sort_ctas_per_sm = v; }
+    if (const char * e = getenv("LNR_CHAIN_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 6) ctx->chain_ctas_per_sm = v; }
+    if (const char * e = getenv("LNR_BLOCKS_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 6) ctx->blocks_ctas_per_sm = v; }
     if (const char * e = getenv("LNR_EXTEND_GROUP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->extend_group = v; }
     if (const char * e = getenv("LNR_BIG_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 16384) ctx->big_arena_bytes_per_warp = (size_t)v << 20; }
     if (const char * e = getenv("LNR_ARENA_KB")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) ctx->arena_bytes_per_warp = (size_t)v << 10; }
     else if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LNR_E_CUDA; }
+    {
+        if (getenv("LNR_TRACE"))
+        {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_map_hits, 128, 0);
+            fprintf(stderr, "[lnr trace] occupancy API: k_map_hits %d CTAs/SM", nb);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_map_finish, 128, 0);
+            fprintf(stderr, ", k_map_finish %d", nb);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_map_extend, 128, 0);
+            fprintf(stderr, ", k_map_extend %d", nb);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_feat_reads, FT, 0);
+            fprintf(stderr, ", k_feat_reads %d\n", nb);
+        }
+    }
     *out = ctx;
     return LNR_OK;
 }
@@ -1388,7 +1686,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
     ctx->stage.release();
     cudaStreamDestroy(ctx->stream);
@@ -1950,7 +2248,8 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     // ---- workspace of the pipeline kernels
     const int wpc = 4;
     const int n_ctas = ctx->n_sm * ctx->map_ctas_per_sm;
-    const u64 n_warps = (u64)n_ctas * wpc;
+    const int max_cps = std::max(std::max(ctx->map_ctas_per_sm, ctx->sort_ctas_per_sm), std::max(ctx->chain_ctas_per_sm, ctx->blocks_ctas_per_sm));
+    const u64 n_warps = (u64)ctx->n_sm * max_cps * wpc;    // every warp of the widest kernel owns a histogram and an arena
     CK(ctx->bins.reserve((size_t)n_warps * kNumBins * sizeof(u32)));
     CK(ctx->arena.reserve((size_t)n_warps * ctx->arena_bytes_per_warp));
     if (ctx->bins_zeroed != ctx->bins.p || ctx->bins_zeroed_cap != ctx->bins.cap)   // the kernels return the histograms zeroed
@@ -2004,6 +2303,8 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     }
     CK(ctx->task_nhits.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
     a.task_nhits = ctx->task_nhits.as<u32>();
+    CK(ctx->task_state.reserve((size_t)n_reads * sizeof(u32)));
+    a.task_state = ctx->task_state.as<u32>();
     CK(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_reads * sizeof(ReadSlot), ctx->stream));
     const size_t big_per_warp = ctx->big_arena_bytes_per_warp;
     CK(ctx->big_arena.reserve(32 * big_per_warp));
@@ -2013,14 +2314,35 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     const bool want_rec = getenv("LNR_LONGEST_PROFILE") != nullptr;
     if (want_rec)
     {
-        CK(ctx->warp_rec.reserve((size_t)n_warps * 16 * sizeof(u64)));
-        CK(cudaMemsetAsync(ctx->warp_rec.p, 0, (size_t)n_warps * 16 * sizeof(u64), ctx->stream));
+        CK(ctx->warp_rec.reserve((size_t)n_warps * 48 * sizeof(u64)));
+        CK(cudaMemsetAsync(ctx->warp_rec.p, 0, (size_t)n_warps * 48 * sizeof(u64), ctx->stream));
         a.warp_rec = ctx->warp_rec.as<u64>();
+        a.warp_rec_stage_off = n_warps * 24;
     }
+    if (getenv("LNR_MONOLITHIC_HITS"))
     {
         LaunchScope ls(ctx, "k_map_hits");
         k_map_hits<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, 0, 0);
     }
+    else
+    {
+        // the three sections of the hit stage, one kernel each (see k_hits_sort)
+        {
+            LaunchScope ls(ctx, "k_hits_sort");
+            k_hits_sort<<<ctx->n_sm * ctx->sort_ctas_per_sm, 128, 0, ctx->stream>>>(a);
+        }
+        CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_hits_chain");
+            k_hits_chain<<<ctx->n_sm * ctx->chain_ctas_per_sm, 128, 0, ctx->stream>>>(a);
+        }
+        CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_hits_blocks");
+            k_hits_blocks<<<ctx->n_sm * ctx->blocks_ctas_per_sm, 128, 0, ctx->stream>>>(a);
+        }
+    }
+    CK(cudaGetLastError());
     tr.lap("hits", true);
     CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
     {
@@ -2136,11 +2458,36 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     for (int i = 0; i < 16; i++) ctx->stage_cycles[i] = h_misc[8 + 24 + i];
     if (want_rec)
     {
-        std::vector<u64> rec((size_t)n_warps * 16);
+        std::vector<u64> rec((size_t)n_warps * 48);
         CK(cudaMemcpy(rec.data(), ctx->warp_rec.p, rec.size() * sizeof(u64), cudaMemcpyDeviceToHost));
         size_t best = 0;
-        for (size_t wq = 0; wq < (size_t)n_warps; wq++) if (rec[wq * 16 + 12] > rec[best * 16 + 12]) best = wq;
-        for (int i = 0; i < 16; i++) ctx->longest_cycles[i] = rec[best * 16 + i];
+        for (size_t wq = 0; wq < (size_t)n_warps; wq++) if (rec[wq * 24 + 12] > rec[best * 24 + 12]) best = wq;
+        for (int i = 0; i < 16; i++) ctx->longest_cycles[i] = rec[best * 24 + i];
+        // tail analysis of the three hit-section kernels on stderr: when warps retire, and the slowest tasks
+        const char * names[3] = {"k_hits_sort", "k_hits_chain", "k_hits_blocks"};
+        const int cps[3] = {ctx->sort_ctas_per_sm, ctx->chain_ctas_per_sm, ctx->blocks_ctas_per_sm};
+        for (int st = 0; st < 3; st++)
+        {
+            const size_t nw = (size_t)ctx->n_sm * cps[st] * 4;
+            const u64 * R = rec.data() + n_warps * 24 + (size_t)st * nw * 8;
+            u64 t0 = ~0ULL, t1 = 0;
+            std::vector<double> ends;
+            for (size_t wq = 0; wq < nw; wq++) if (R[wq * 8]) { t0 = std::min(t0, R[wq * 8]); t1 = std::max(t1, R[wq * 8 + 1]); }
+            for (size_t wq = 0; wq < nw; wq++) if (R[wq * 8]) ends.push_back((R[wq * 8 + 1] - t0) * 1e-6);
+            if (ends.empty()) continue;
+            std::sort(ends.begin(), ends.end());
+            fprintf(stderr, "[lnr tail] %s span %.3f ms; warp retire ms: p10 %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f\n", names[st], (t1 - t0) * 1e-6,
+                    ends[ends.size() / 10], ends[ends.size() / 2], ends[ends.size() * 9 / 10], ends[ends.size() * 99 / 100], ends.back());
+            std::vector<size_t> idx(nw);
+            for (size_t i = 0; i < nw; i++) idx[i] = i;
+            std::sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return R[x * 8 + 2] > R[y * 8 + 2]; });
+            for (size_t k = 0; k < std::min<size_t>(6, nw); k++)
+            {
+                const u64 * r = R + idx[k] * 8;
+                fprintf(stderr, "[lnr tail]   task q=%llu dur %.3f ms task %llu size %llu (warp did %llu tasks, retired %.2f ms)\n", (unsigned long long)r[5], r[2] / 1.965e6,
+                        (unsigned long long)r[3], (unsigned long long)r[4], (unsigned long long)r[6], (r[1] - t0) * 1e-6);
+            }
+        }
     }
     if (n_cords_total) *n_cords_total = total_cords;
     if (dbg && dbg->hits_off)
@@ -2227,6 +2574,26 @@ int lnr_last_batch_stage_cycles(lnr_ctx * ctx, uint64_t cycles[16])
     if (!ctx || !cycles) return LNR_E_ARG;
     for (int i = 0; i < 16; i++) cycles[i] = ctx->stage_cycles[i];
     if (getenv("LNR_LONGEST_PROFILE")) for (int i = 0; i < 16; i++) cycles[i] = ctx->longest_cycles[i];
+    return LNR_OK;
+}
+
+int lnr_selftest_sort(lnr_ctx * ctx, uint64_t * records, uint32_t n)
+{
+    if (!ctx || (!records && n)) return LNR_E_ARG;
+    if (n == 0) return LNR_OK;
+    cudaSetDevice(ctx->device);
+    u64 * d = nullptr;
+    CK(cudaMalloc(&d, (size_t)(4 * (size_t)n + 8) * sizeof(u64)));
+    cudaError_t e = cudaMemcpyAsync(d, records, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+    {
+        k_selftest_sort<<<1, 32, 0, ctx->stream>>>(d, d + n, d + 2 * (size_t)n, (int)n, d + 3 * (size_t)n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(records, d + 3 * (size_t)n, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e));
     return LNR_OK;
 }
 

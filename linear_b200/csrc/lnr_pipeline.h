@@ -145,6 +145,112 @@ LNR_PIPE u64 * radix_sort(const Warp & w, u32 * hist, u64 * src, u64 * t0, u64 *
 }
 
 // ----------------------------------------------------------------------------------------------------
+// std::sort's permutation, warp-cooperative (lnr_sortlib.h is the one-lane statement of the same algorithm).
+//
+// less(x, y) = key(x) < key(y). libstdc++'s introsort is (1) a tree of Hoare partitions down to ranges of <= 16
+// elements and (2) one final insertion sort. Both parts have a data-parallel equivalent that yields the same array:
+//
+// (1) __unguarded_partition(lo, hi, pivot) stops its left scan at elements >= pivot and its right scan at elements
+//     <= pivot and swaps the k-th left stop with the k-th right stop until the scans cross. Every stop before the
+//     crossing is an element of the ORIGINAL range (swapped elements are always stepped over), so with l_1 < l_2 < ..
+//     the positions of the elements >= pivot and r_1 > r_2 > .. those of the elements <= pivot, the swaps are exactly
+//     (l_k, r_k) for k = 1..K, K = #{k : l_k < r_k}, and the returned cut is l_1 when K = 0, else min(l_{K+1}, r_K)
+//     (the left scan cannot pass r_K, which now holds an element >= pivot).
+// (2) insertion sort moves an element left only past strictly greater ones: the result is the STABLE sort of the
+//     array the partitions left behind, which the LSD radix sort above computes.
+// The depth-limit heap sort (rare) stays on one lane.
+// ----------------------------------------------------------------------------------------------------
+template <class KeyFn>
+LNR_PIPE int gs_partition_w(const Warp & w, u64 * a, int lo, int hi, int pivot, int * Lidx, int * Ridx, KeyFn key)
+{
+    const u64 pv = key(a[pivot]);
+    const int m = hi - lo;
+    int nL = 0, nR = 0;
+    for (int c = 0; c < m; c += w.nl)
+    {
+        int i = lo + c + w.lane, j = hi - 1 - c - w.lane;
+        bool vi = i < hi, vj = j >= lo;
+        u64 ki = vi ? key(a[i]) : 0, kj = vj ? key(a[j]) : 0;
+        bool isL = vi && !(ki < pv);
+        bool isR = vj && !(pv < kj);
+        u32 bl = wballot(w, isL), br = wballot(w, isR);
+        if (isL) Lidx[nL + popc_below(w, bl)] = i;
+        if (isR) Ridx[nR + popc_below(w, br)] = j;
+        nL += popc32(bl);
+        nR += popc32(br);
+    }
+    wsync(w);
+    const int mn = nL < nR ? nL : nR;
+    int K = 0;
+    for (int c = 0; c < mn; c += w.nl)
+    {
+        int k = c + w.lane;
+        bool p = k < mn && Lidx[k] < Ridx[k];
+        int cnt = popc32(wballot(w, p));
+        K += cnt;
+        if (cnt < w.nl) break;
+    }
+    int cut;
+    if (K == 0) cut = Lidx[0];
+    else
+    {
+        int rK = Ridx[K - 1];
+        cut = (K < nL && Lidx[K] < rK) ? Lidx[K] : rK;
+    }
+    for (int k = w.lane; k < K; k += w.nl)
+    {
+        int x = Lidx[k], y = Ridx[k];
+        u64 t = a[x]; a[x] = a[y]; a[y] = t;
+    }
+    wsync(w);
+    return cut;
+}
+
+// sorts a[0..n) like std::sort(a, a + n, less); s0 / s1: scratch of n u64 each. Returns the buffer holding the result
+// (a, s0 or s1).
+template <class KeyFn>
+LNR_PIPE u64 * gnu_sort_w(const Warp & w, u32 * hist, u64 * a, u64 * s0, u64 * s1, int n, int key_bits, KeyFn key)
+{
+    if (n <= 1) return a;
+    auto less = [key](const u64 & x, const u64 & y) { return key(x) < key(y); };
+    if (n <= 16)
+    {
+        if (w.lane == 0) gs_insertion_sort(a, 0, n, less);
+        wsync(w);
+        return a;
+    }
+    int lg = 0;
+    for (unsigned v = (unsigned)n; v > 1; v >>= 1) lg++;
+    int * Lidx = (int *)s0;
+    int * Ridx = (int *)s1;
+    int st_first[72], st_last[72], st_depth[72];
+    int sp = 1;
+    st_first[0] = 0; st_last[0] = n; st_depth[0] = lg * 2;
+    while (sp > 0)
+    {
+        --sp;
+        int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+        while (last - first > 16)
+        {
+            if (depth == 0)
+            {
+                if (w.lane == 0) gs_heap_sort(a, first, last, less);
+                wsync(w);
+                break;
+            }
+            --depth;
+            int mid = first + (last - first) / 2;
+            if (w.lane == 0) gs_move_median_to_first(a, first, first + 1, mid, last - 1, less);
+            wsync(w);
+            int cut = gs_partition_w(w, a, first + 1, last, first, Lidx, Ridx, key);
+            st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; sp++;
+            last = cut;
+        }
+    }
+    return radix_sort(w, hist, a, s0, s1, n, key_bits, key);
+}
+
+// ----------------------------------------------------------------------------------------------------
 // anchor filters (pmpfinder.cpp:1979-2183)
 // ----------------------------------------------------------------------------------------------------
 LNR_HD u32 anchor_bin(u64 a) { return (u32)(cord_x(a) / 30000); }
@@ -154,28 +260,55 @@ LNR_HD u32 anchor_bin(u64 a) { return (u32)(cord_x(a) / 30000); }
 // returned zeroed.
 LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u64 * A, u64 * B, int n, int & n_out)
 {
-    for (int i = w.lane; i < n; i += w.nl)
+    // Every access to `bins` is a dependent, uncached-latency access (the histogram of a warp spans 140 KB), so each
+    // pass keeps four independent elements per lane in flight.
+    const int U = 4, step = U * w.nl;
+    for (int c = 0; c < n; c += step)
     {
+        u64 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+        {
+            int i = c + k * w.nl + w.lane;
+            if (i < n)
+            {
 #ifdef __CUDA_ARCH__
-        atomicAdd(&bins[anchor_bin(A[i])], 1u);
+                atomicAdd(&bins[anchor_bin(v[k])], 1u);
 #else
-        bins[anchor_bin(A[i])]++;
+                bins[anchor_bin(v[k])]++;
 #endif
+            }
+        }
     }
     wsync(w);
     int ii = 0;
-    for (int c = 0; c < n; c += w.nl)
+    for (int c = 0; c < n; c += step)
     {
-        int i = c + w.lane;
-        u64 a = i < n ? A[i] : 0;
-        bool keep = i < n && bins[anchor_bin(a)] > 10;
-        int total;
-        int pos = wscan_excl(w, keep ? 1 : 0, total);
-        if (keep) B[ii + pos] = a;
-        ii += total;
+        u64 v[U]; u32 cnt[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
+#pragma unroll
+        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; cnt[k] = i < n ? bins[anchor_bin(v[k])] : 0; }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+        {
+            bool keep = cnt[k] > 10;
+            u32 bal = wballot(w, keep);
+            if (keep) B[ii + popc_below(w, bal)] = v[k];
+            ii += popc32(bal);
+        }
     }
     wsync(w);
-    for (int i = w.lane; i < n; i += w.nl) bins[anchor_bin(A[i])] = 0;
+    for (int c = 0; c < n; c += step)
+    {
+        u64 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
+#pragma unroll
+        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; if (i < n) bins[anchor_bin(v[k])] = 0; }
+    }
     wsync(w);
     if (ii != 0) { n_out = ii; return B; }
     n_out = n;
@@ -218,35 +351,47 @@ LNR_HD int filter_anchor_runs(const u64 * a, int n, Blk * ranges)
 // ----------------------------------------------------------------------------------------------------
 // chain scores (cluster_util.cpp:337-443, :586-860)
 // ----------------------------------------------------------------------------------------------------
+// The reference computes these in int64. y is a 20-bit and x a 30-bit coordinate, so dy, dx and da = |dx - dy| fit an
+// int32 and only 100 * da can leave 32 bits (da >= 2^25): the 64-bit division (a long subroutine on the GPU, and the
+// chaining DP evaluates a score per candidate) is kept for that rare case only.
+LNR_HD u32 chain_derr(i32 da, i32 dy, i32 dx, i32 floor_)
+{
+    i32 ady = dy < 0 ? -dy : dy, adx = dx < 0 ? -dx : dx;
+    i32 den = ady > adx ? ady : adx;
+    if (den < floor_) den = floor_;
+    if (da < (1 << 25)) return (100u * (u32)da) / (u32)den;
+    return (u32)((100ULL * (u64)da) / (u64)den);
+}
 LNR_HD int score_anchor(u64 a1, u64 a2)   // getApxChainScore :387
 {
-    i64 dy = (i64)(cord_y(a1) - cord_y(a2));
+    i32 dy = (i32)(u32)(cord_y(a1) - cord_y(a2));
     if (dy < 10) return -10000;
-    i64 dx = (i64)(anchor_x(a1) - anchor_x(a2));
-    i64 da = iabs64(dx - dy);
-    i64 derr = (100 * da) / imax64(imax64(iabs64(dy), iabs64(dx)), 50);
+    i32 dx = (i32)(u32)(anchor_x(a1) - anchor_x(a2));
+    i32 da = dx - dy;
+    if (da < 0) da = -da;
+    i32 derr = (i32)chain_derr(da, dy, dx, 50);
     int sderr;
-    if (derr < 5) sderr = (int)(4 * derr);
-    else if (derr < 10) sderr = (int)(6 * derr - 10);
-    else if (derr < 100) sderr = (int)(derr * derr - 5 * derr);
+    if (derr < 5) sderr = 4 * derr;
+    else if (derr < 10) sderr = 6 * derr - 10;
+    else if (derr < 100) sderr = derr * derr - 5 * derr;
     else return -1000;
     int sdy;
     dy /= 15;
-    if (dy < 150) sdy = (int)(dy / 5);
-    else if (dy < 100) sdy = (int)(dy - 30);
-    else if (dy < 10000) sdy = (int)(dy * dy / 200 + 20);
+    if (dy < 150) sdy = dy / 5;
+    else if (dy < 100) sdy = dy - 30;
+    else if (dy < 10000) sdy = dy * dy / 200 + 20;
     else sdy = 10000;
     return da < 10 ? 100 - sdy : 100 - sdy - sderr;
 }
 LNR_HD int score_anchor0(u64 a1, u64 a2)   // getApxChainScore0 :337
 {
-    i64 dy = (i64)(cord_y(a1) - cord_y(a2));
+    i32 dy = (i32)(u32)(cord_y(a1) - cord_y(a2));
     if (dy < 5) return -10000;
-    i64 dx = (i64)(anchor_x(a1) - anchor_x(a2));
-    i64 da = iabs64(dx - dy);
-    i64 derr = (100 * da) / imax64(imax64(iabs64(dy), iabs64(dx)), 50);
-    if (derr >= 100) return -1000;
-    int sdy = (int)dy, sderr = (int)da;
+    i32 dx = (i32)(u32)(anchor_x(a1) - anchor_x(a2));
+    i32 da = dx - dy;
+    if (da < 0) da = -da;
+    if (chain_derr(da, dy, dx, 50) >= 100) return -1000;
+    int sdy = dy, sderr = da;
     return da < 30 ? 100 - sdy : 100 - sdy - sderr;
 }
 LNR_HD int score_blocks_hits(u64 c11, u64 c22)   // getApxChainScore2 :586
@@ -1145,28 +1290,25 @@ LNR_HD u64 phase_map_scratch_bound(int n)
     return m * (8 + 4 + 8 + 8 + 4 + 24 + 8 + 8 + 8 + 16 + 8 + 4 + 52 + 1) + 2048;
 }
 
-LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, const PipeIn & in, u64 * A, u64 * B, int n,
-                       u64 read_str, u64 read_end, int score_type, u64 * cords, int & n_cords, int cords_cap,
-                       u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt,
-                       u64 * hits_out = (u64 *)0, u32 * n_hits_out = (u32 *)0, bool force_fit = true)
+// The hit stage of apxMap_ in three sections. phase_map runs them back to back inside one warp (re-map pass, big-arena
+// pass, host emulation); the primary pass runs each section as its own kernel (k_hits_sort / k_hits_chain /
+// k_hits_blocks) so that every warp of an SM executes the same few KB of code and each kernel gets its own register
+// budget -- as one 250 KB kernel the warps of an SM sat in different sections and starved on instruction fetch.
+
+// Section 1: filterAnchors (:2159: binningFilter + filterAnchors1) and the AnchorX sort of chainAnchorsHits (:2465).
+// A, B: the task's two n-entry regions (A = raw anchors, A[0] the sentinel slot). On return X[0..n2) are the anchors in
+// chaining order; X is A, B or arena memory. rc: 0 = continue with section 2 (n2 >= 2), 3 = the read has no hits,
+// 1 = arena exhausted.
+LNR_PIPE int hits_sec_sort(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, u64 * A, u64 * B, int n, PipeCounters & cnt,
+                           long long & tl, u64 *& X, int & n2)
 {
-    // hits_out != null: stop after _filterHits and hand the hits over (it may alias A; capacity n) -- the window
-    // extension then runs in its own thread-per-read kernel. hits_out == null: run path_dst_2 here.
-    // Return 2 = nothing was touched because even the upper bound of the scratch need (all sizes <= n) does not
-    // fit this arena: the caller re-runs the task with a larger arena (the anchors in A/B are consumed by a run).
-    if (!force_fit && phase_map_scratch_bound(n) > ar.cap) return 2;
-    arena_reset(ar);
-    long long tl = LNR_CLOCK();
-    if (n_hits_out && w.lane == 0) *n_hits_out = 0;
-    if (dbg_nhits && w.lane == 0) *dbg_nhits = 1;
-    if (dbg_hits && w.lane == 0 && dbg_hits_cap > 0) dbg_hits[0] = kFlagEnd;
+    X = A; n2 = 0;
     if (w.lane == 0) A[0] = 0;               // Anchors::init(1) base.cpp:272
     wsync(w);
-    // ---- filterAnchors (:2159): binningFilter + filterAnchors1
     int m;
     u64 * S = binning_filter(w, bins, A, B, n, m);
     LNR_LAP(cnt, 0, tl);
-    if (m <= 1) return 0;                    // no chains, hits stay empty (path_dst :1457)
+    if (m <= 1) return 3;                    // no chains, hits stay empty (path_dst :1457)
     u64 * O = (S == A) ? B : A;              // the other buffer
     if (w.lane == 0) S[0] = 0;               // filterAnchorsList :2030 overwrites whatever is first
     wsync(w);
@@ -1182,7 +1324,6 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     // compact the accepted runs (anchors[0] is dropped, filterAnchors1 :2073)
     u64 * F = (sorted == O) ? C : O;         // a buffer that is neither `sorted` nor S
     if (F == S) F = (sorted == C) ? O : C;
-    int n2 = 0;
     for (int r = 0; r < nr; r++)
     {
         int b = (int)ranges[r].first, e = (int)ranges[r].second;
@@ -1191,67 +1332,73 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     }
     wsync(w);
     LNR_LAP(cnt, 2, tl);
+    X = F;
+    // a single anchor is sorted trivially and chainAnchorsBase returns without chains (cluster_util.cpp:450): with
+    // fewer than two anchors the hit list stays [sentinel] and path_dst returns at :1457
+    if (n2 < 2) return 3;
     // ---- chainAnchorsHits (:2448): sort by AnchorX descending with std::sort's tie order
-    u64 * hits = arena_alloc<u64>(ar, (u64)n2 + 2);
-    u64 * hits2 = arena_alloc<u64>(ar, (u64)n2 + 2);
-    i32 * hits_score = arena_alloc<i32>(ar, (u64)n2 + 2);
+    u64 * T0 = (F == A) ? B : A;             // free buffers: the two of {A,B,C} that are not F
+    u64 * T1 = (F == C) ? B : C;
+    if (T1 == T0) T1 = C;
+    X = radix_sort(w, hist256, F, T0, T1, n2, 30, KeyXDesc());
+    int tie = 0;
+    for (int i = 1 + w.lane; i < n2; i += w.nl) tie |= anchor_x(X[i]) == anchor_x(X[i - 1]);
+    tie = wballot(w, tie != 0) != 0;
+    if (tie)
+    {
+        // comparator ties: only libstdc++'s own permutation is right
+        X = gnu_sort_w(w, hist256, F, T0, T1, n2, 30, KeyXDesc());
+        cnt.t[11]++;
+    }
+    LNR_LAP(cnt, 3, tl);
+    return 0;
+}
+
+// Section 2: chainAnchorsBase DP + traceback (getBestChains / traceBackChains, cluster_util.cpp:450-560) over
+// X[0..n2), n2 >= 2. Writes hits[0..n_hits) (hits[0] the sentinel) and their scores. hits / hits_score: n2 + 2 entries.
+LNR_PIPE int hits_sec_chain(const Warp & w, Arena & ar, const PipeIn & in, const u64 * X, int n2, int score_type, u64 * hits,
+                            i32 * hits_score, int & n_hits, PipeCounters & cnt, long long & tl)
+{
+    ChainRec * rec = arena_alloc<ChainRec>(ar, (u64)n2);
+    u64 * ch_el = arena_alloc<u64>(ar, (u64)n2);
     int * chain_off = arena_alloc<int>(ar, 64);
     if (ar.failed) return 1;
-    int n_hits = 1;
+    n_hits = 1;
     if (w.lane == 0) { hits[0] = kFlagEnd; hits_score[0] = 0; }
-    if (n2 >= 2)
+    best_chains(w, X, rec, n2, score_type);
+    LNR_LAP(cnt, 4, tl);
+    if (w.lane == 0)
     {
-        // free buffers: the two of {A,B,C} that are not F
-        u64 * T0 = (F == A) ? B : A;
-        u64 * T1 = (F == C) ? B : C;
-        if (T1 == T0) T1 = C;
-        u64 * X = radix_sort(w, hist256, F, T0, T1, n2, 30, KeyXDesc());
-        int tie = 0;
-        for (int i = 1 + w.lane; i < n2; i += w.nl) tie |= anchor_x(X[i]) == anchor_x(X[i - 1]);
-        tie = wballot(w, tie != 0) != 0;
-        if (tie)
+        int nch = traceback<u64>(X, rec, n2, ch_el, hits_score + 1, chain_off, 60, 1, 45, 50, in.stop_ratio);
+        for (int c = 0; c < nch; c++)
         {
-            // comparator ties: only libstdc++'s own permutation is right
-            if (w.lane == 0) gnu_sort(F, n2, [](const u64 & a, const u64 & b) { return anchor_x(a) > anchor_x(b); });
-            wsync(w);
-            X = F;
-            cnt.t[11]++;
+            for (int j = chain_off[c]; j < chain_off[c + 1]; j++) hits[1 + j] = hit2cord_dstr(ch_el[j]);
+            hits[chain_off[c + 1]] |= kFlagEnd;
         }
-        LNR_LAP(cnt, 3, tl);
-        ChainRec * rec = arena_alloc<ChainRec>(ar, (u64)n2);
-        u64 * ch_el = arena_alloc<u64>(ar, (u64)n2);
-        if (ar.failed) return 1;
-        best_chains(w, X, rec, n2, score_type);
-        LNR_LAP(cnt, 4, tl);
-        if (w.lane == 0)
-        {
-            int nch = traceback<u64>(X, rec, n2, ch_el, hits_score + 1, chain_off, 60, 1, 45, 50, in.stop_ratio);
-            for (int c = 0; c < nch; c++)
-            {
-                for (int j = chain_off[c]; j < chain_off[c + 1]; j++) hits[1 + j] = hit2cord_dstr(ch_el[j]);
-                hits[chain_off[c + 1]] |= kFlagEnd;
-            }
-            n_hits = 1 + chain_off[nch];
-        }
-    }
-    else if (w.lane == 0 && n2 == 1)
-    {
-        // a single anchor: sorted trivially, chainAnchorsBase returns without chains (cluster_util.cpp:450)
+        n_hits = 1 + chain_off[nch];
     }
     n_hits = wbcast(w, n_hits, 0);
     wsync(w);
     LNR_LAP(cnt, 5, tl);
-    // ---- blocks of hits: gather_blocks_ (:1484) -> preFilterChains2 (:2366) -> chainBlocksHits
+    return 0;
+}
+
+// Section 3: blocks of hits -- gather_blocks_ (:1484) -> preFilterChains2 (:2366) -> chainBlocksHits -> _filterHits
+// (:1417). hits[0..n_hits) with scores; H returns the surviving hits (hits itself or arena memory), n_hits their number.
+LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, const PipeIn & in, u64 * hits, const i32 * hits_score, int & n_hits,
+                             u64 *& H, u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt, long long & tl)
+{
+    H = hits;
     Blk * sep = arena_alloc<Blk>(ar, (u64)n_hits + 1);
     Blk * sep_tmp = arena_alloc<Blk>(ar, (u64)n_hits + 1);
     u64 * cuts = arena_alloc<u64>(ar, 2 * (u64)n_hits + 2);
     u64 * strs = arena_alloc<u64>(ar, (u64)n_hits + 1);
     i32 * sep_score = arena_alloc<i32>(ar, (u64)n_hits + 1);
+    u64 * hits2 = arena_alloc<u64>(ar, (u64)n_hits + 2);
     BlockScratch bs;
     block_scratch_alloc(ar, bs, n_hits + 1);
     u8 * keep = arena_alloc<u8>(ar, (u64)n_hits + 1);
     if (ar.failed) return 1;
-    u64 * H = hits;
     int err = 0;
     int nb0;
     {
@@ -1289,7 +1436,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     }
     wsync(w);
     LNR_LAP(cnt, 6, tl);
-    if (n_hits < 2) return 0;                // path_dst :1457
+    if (n_hits < 2) return 3;                // path_dst :1457
     // ---- _filterHits (:1417): drop hits whose own window distance >= reject (50)
     for (int it = 1 + w.lane; it < n_hits; it += w.nl)
     {
@@ -1316,6 +1463,36 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     }
     n_hits = wbcast(w, n_hits, 0);
     wsync(w);
+    return 0;
+}
+
+LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, const PipeIn & in, u64 * A, u64 * B, int n,
+                       u64 read_str, u64 read_end, int score_type, u64 * cords, int & n_cords, int cords_cap,
+                       u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt,
+                       u64 * hits_out = (u64 *)0, u32 * n_hits_out = (u32 *)0, bool force_fit = true)
+{
+    // hits_out != null: stop after _filterHits and hand the hits over (it may alias A; capacity n) -- the window
+    // extension then runs in its own thread-per-read kernel. hits_out == null: run path_dst_2 here.
+    // Return 2 = nothing was touched because even the upper bound of the scratch need (all sizes <= n) does not
+    // fit this arena: the caller re-runs the task with a larger arena (the anchors in A/B are consumed by a run).
+    if (!force_fit && phase_map_scratch_bound(n) > ar.cap) return 2;
+    arena_reset(ar);
+    long long tl = LNR_CLOCK();
+    if (n_hits_out && w.lane == 0) *n_hits_out = 0;
+    if (dbg_nhits && w.lane == 0) *dbg_nhits = 1;
+    if (dbg_hits && w.lane == 0 && dbg_hits_cap > 0) dbg_hits[0] = kFlagEnd;
+    u64 * X; int n2;
+    int rc = hits_sec_sort(w, ar, hist256, bins, A, B, n, cnt, tl, X, n2);
+    if (rc) return rc == 3 ? 0 : rc;
+    u64 * hits = arena_alloc<u64>(ar, (u64)n2 + 2);
+    i32 * hits_score = arena_alloc<i32>(ar, (u64)n2 + 2);
+    if (ar.failed) return 1;
+    int n_hits = 1;
+    rc = hits_sec_chain(w, ar, in, X, n2, score_type, hits, hits_score, n_hits, cnt, tl);
+    if (rc) return rc;
+    u64 * H;
+    rc = hits_sec_blocks(w, ar, in, hits, hits_score, n_hits, H, dbg_hits, dbg_nhits, dbg_hits_cap, cnt, tl);
+    if (rc) return rc == 3 ? 0 : rc;
     if (hits_out)
     {
         for (int i = w.lane; i < n_hits; i += w.nl) hits_out[i] = H[i];

@@ -1,5 +1,5 @@
 # occupancy experiment for k_map_hits: rebuild with a min-CTAs launch bound, then time at matching CTAs/SM
-for c in 8 10; do
+for c in 3 4 5 6; do
   rm -f linear_b200/csrc/liblnr_b200.so
   LNR_NVCC_EXTRA="-DLNR_HITS_MIN_CTAS=$c" python -c "import __graft_entry__ as g; g.build()" >/dev/null 2>&1
   echo "min_ctas=$c"

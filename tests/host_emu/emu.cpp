@@ -314,3 +314,24 @@ extern "C" int emu_gnu_sort_check(uint64_t * keys_payload, int n, int descending
     for (int i = 0; i < n; i++) bad += a[i] != b[i];
     return bad;
 }
+
+// gnu_sort_w (the warp-cooperative statement: parallel Hoare partitions + stable radix pass) run with a one-lane warp
+// must give std::sort's permutation too. Key = high 32 bits (30 significant), ascending in the transformed key.
+struct EmuKeyHi { uint64_t operator()(uint64_t v) const { return v >> 32; } };
+extern "C" int emu_gnu_sort_w_check(uint64_t * keys_payload, int n)
+{
+    std::vector<uint64_t> a(keys_payload, keys_payload + n), b(a), s0(n + 1), s1(n + 1);
+    std::sort(a.begin(), a.end(), [](uint64_t & x, uint64_t & y) { return (x >> 32) < (y >> 32); });
+    lnr::Warp w = {0, 1, 1u};
+    uint32_t hist[256];
+    uint64_t * r = lnr::gnu_sort_w(w, hist, b.data(), s0.data(), s1.data(), n, 32, EmuKeyHi());
+    int bad = 0;
+    for (int i = 0; i < n; i++) bad += a[i] != r[i];
+    return bad;
+}
+
+// std::sort itself (ascending by the high 32 bits), for the GPU self-test of gnu_sort_w
+extern "C" void emu_std_sort_hi(uint64_t * a, int n)
+{
+    std::sort(a, a + n, [](uint64_t & x, uint64_t & y) { return (x >> 32) < (y >> 32); });
+}

@@ -230,3 +230,26 @@ def test_hindex_apxmap_bit_exact(lb, ctx):
         R = RefImpl(g, threads=T, preset=preset, index_type=2)
         rc, ro = R.map_batch(bases, offs, map_threads=4)
         assert np.array_equal(ro, coff) and np.array_equal(rc, cords)
+
+
+def test_warp_sort_reproduces_std_sort_tie_order(lb, ctx):
+    """chainAnchorsHits sorts with a key-only comparator (pmpfinder.cpp:2465); tied anchors must come out in libstdc++'s
+    introsort order. The 32-lane gnu_sort_w is checked against std::sort itself on tie-heavy and adversarial inputs."""
+    import ctypes as C
+    from cpu_checkers import build_emu
+    emu = C.CDLL(build_emu())
+    emu.emu_std_sort_hi.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    rng = np.random.default_rng(7)
+    inputs = []
+    for n in (1, 2, 16, 17, 31, 32, 33, 64, 65, 100, 1000, 5000, 40000):
+        for nkeys in (1, 2, 5, 50, 1000, 2 ** 30):
+            inputs.append(rng.integers(0, nkeys, size=n, dtype=np.uint64))
+    for n in (1000, 20000):
+        inputs += [np.arange(n, dtype=np.uint64) // 3, np.arange(n, dtype=np.uint64)[::-1] // 3,
+                   np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]]).astype(np.uint64) // 3]
+    for keys in inputs:
+        a = (keys << np.uint64(32)) | np.arange(len(keys), dtype=np.uint64)
+        want = a.copy()
+        emu.emu_std_sort_hi(want.ctypes.data_as(C.POINTER(C.c_uint64)), len(want))
+        got = lb.selftest_sort(ctx, a)
+        assert np.array_equal(got, want), (len(keys), int(keys.max()))

@@ -78,3 +78,19 @@ def test_gnu_sort_matches_std_sort_with_ties():
         for arr in (np.arange(n), np.arange(n)[::-1], np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]])):
             a = (arr.astype(np.uint64) // np.uint64(3) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
             assert lib.emu_gnu_sort_check(a.ctypes.data_as(C.POINTER(C.c_uint64)), n, 0) == 0
+
+
+def test_warp_cooperative_gnu_sort_matches_std_sort_with_ties():
+    """gnu_sort_w (parallel partitions + stable radix pass, lnr_pipeline.h) == std::sort, one-lane emulation"""
+    lib = C.CDLL(build_emu())
+    lib.emu_gnu_sort_w_check.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 2, 15, 16, 17, 18, 33, 64, 100, 1000, 5000, 40000):
+        for nkeys in (1, 2, 5, 50, 1000, 2 ** 30):
+            keys = rng.integers(0, nkeys, size=n, dtype=np.uint64)
+            a = (keys << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+            assert lib.emu_gnu_sort_w_check(a.ctypes.data_as(C.POINTER(C.c_uint64)), n) == 0, (n, nkeys)
+    for n in (1000, 20000):
+        for arr in (np.arange(n), np.arange(n)[::-1], np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]])):
+            a = (arr.astype(np.uint64) // np.uint64(3) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+            assert lib.emu_gnu_sort_w_check(a.ctypes.data_as(C.POINTER(C.c_uint64)), n) == 0
