@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 65536)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("LNR_BENCH_CPU_SAMPLE", 2048)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("LNR_BENCH_STREAMS", 2)),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("LNR_BENCH_STREAMS", 4)),
                     help="concurrent host threads, each with its own lnr_ctx (the reference calls p_calRecords from -t threads)")
     return ap.parse_args()
 
@@ -368,9 +368,14 @@ def main():
         """k steps in total, dealt round-robin to the host threads; returns wall seconds (barrier + sync both sides)"""
         per = [k // n_str + (1 if i < k % n_str else 0) for i in range(n_str)]
 
+        errors = []
+
         def work(st, n):
-            for _ in range(n):
-                getattr(st, kind)()
+            try:
+                for _ in range(n):
+                    getattr(st, kind)()
+            except BaseException as e:  # noqa: BLE001  -- a failed host thread must fail the run, not shorten it
+                errors.append(e)
         barrier()
         t0 = time.time()
         if n_str == 1:
@@ -382,6 +387,8 @@ def main():
             for t in th:
                 t.join()
         torch.cuda.synchronize()
+        if errors:
+            raise errors[0]
         barrier()
         return time.time() - t0
 
@@ -433,7 +440,9 @@ def main():
         "k_feat_reads": total_bases + nf_bytes,
         "k_seed_count": total_bases + 8 * S + 8 * H,
         "k_seed_fill": 8 * S + 8 * H + 8 * A,
-        "k_map_hits": 8 * A + 48 * Hits,
+        "k_hits_sort": 8 * A,
+        "k_hits_chain": 24 * Hits,
+        "k_hits_blocks": 24 * Hits,
         "k_map_extend": 144 * W + 8 * Cc,
         "k_map_finish": 16 * Cc,
     }

@@ -905,6 +905,7 @@ struct MapArgs
     ReadSlot * slots;
     SeedTask * tasks2; u32 tasks2_cap; u32 * n_tasks2; // re-map tasks produced by the primary pass
     u32 * bins; u8 * arena; u64 arena_per_warp;
+    u64 fit_cap;                                       // k_hits_sort: the smallest per-warp arena of the three section kernels
     u32 * queue;                                       // atomic work counter
     const u32 * order;                                 // reads sorted by length, longest first (tail latency)
     int index_type;                                    // 1 DIndex, 2 HIndex (sample grid of re-map tasks)
@@ -1169,7 +1170,7 @@ __global__ void __launch_bounds__(128, 8) k_hits_sort(MapArgs a)
             if (a.dbg_hoff[r + 1] > a.dbg_hoff[r]) a.dbg_hits[a.dbg_hoff[r]] = kFlagEnd;
         }
         c.cnt.t[12]++;
-        if (phase_map_scratch_bound(n) > c.ar.cap)
+        if (phase_map_scratch_bound(n) > a.fit_cap || (u64)n * 16 + 4096 > c.ar.cap)
         {
             // does not fit the per-warp arena: the whole task is left, untouched, to the big-arena pass
             if (w.lane == 0) { a.task_nhits[ti] = 0xffffffffu; a.task_state[ti] = 0xffffffffu; a.big_list[atomicAdd(a.n_big, 1u)] = ti; }
@@ -2249,9 +2250,13 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     const int wpc = 4;
     const int n_ctas = ctx->n_sm * ctx->map_ctas_per_sm;
     const int max_cps = std::max(std::max(ctx->map_ctas_per_sm, ctx->sort_ctas_per_sm), std::max(ctx->chain_ctas_per_sm, ctx->blocks_ctas_per_sm));
-    const u64 n_warps = (u64)ctx->n_sm * max_cps * wpc;    // every warp of the widest kernel owns a histogram and an arena
+    const u64 n_warps = (u64)ctx->n_sm * max_cps * wpc;    // every warp of the widest kernel owns a histogram
+    // one scratch arena, divided evenly among the warps of whichever kernel is running: arena_bytes_per_warp is what a warp
+    // of the map_ctas_per_sm-wide kernels gets, wider kernels (k_hits_sort needs 12 B per anchor) get proportionally less
+    const size_t arena_total = (size_t)n_ctas * wpc * ctx->arena_bytes_per_warp;
+    auto arena_share = [&](int ctas_per_sm) { return (u64)((arena_total / ((size_t)ctx->n_sm * ctas_per_sm * wpc)) & ~(size_t)255); };
     CK(ctx->bins.reserve((size_t)n_warps * kNumBins * sizeof(u32)));
-    CK(ctx->arena.reserve((size_t)n_warps * ctx->arena_bytes_per_warp));
+    CK(ctx->arena.reserve(arena_total));
     if (ctx->bins_zeroed != ctx->bins.p || ctx->bins_zeroed_cap != ctx->bins.cap)   // the kernels return the histograms zeroed
     {
         ctx->bins_zeroed_cap = ctx->bins.cap;
@@ -2327,19 +2332,25 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     else
     {
         // the three sections of the hit stage, one kernel each (see k_hits_sort)
+        MapArgs as = a;
+        as.arena_per_warp = arena_share(ctx->sort_ctas_per_sm);
+        const u64 cap_chain = arena_share(ctx->chain_ctas_per_sm), cap_blocks = arena_share(ctx->blocks_ctas_per_sm);
+        as.fit_cap = std::min(cap_chain, cap_blocks);   // a task must fit every section's arena (this section: 12 B per anchor)
         {
             LaunchScope ls(ctx, "k_hits_sort");
-            k_hits_sort<<<ctx->n_sm * ctx->sort_ctas_per_sm, 128, 0, ctx->stream>>>(a);
+            k_hits_sort<<<ctx->n_sm * ctx->sort_ctas_per_sm, 128, 0, ctx->stream>>>(as);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        as.arena_per_warp = cap_chain;
         {
             LaunchScope ls(ctx, "k_hits_chain");
-            k_hits_chain<<<ctx->n_sm * ctx->chain_ctas_per_sm, 128, 0, ctx->stream>>>(a);
+            k_hits_chain<<<ctx->n_sm * ctx->chain_ctas_per_sm, 128, 0, ctx->stream>>>(as);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        as.arena_per_warp = cap_blocks;
         {
             LaunchScope ls(ctx, "k_hits_blocks");
-            k_hits_blocks<<<ctx->n_sm * ctx->blocks_ctas_per_sm, 128, 0, ctx->stream>>>(a);
+            k_hits_blocks<<<ctx->n_sm * ctx->blocks_ctas_per_sm, 128, 0, ctx->stream>>>(as);
         }
     }
     CK(cudaGetLastError());
