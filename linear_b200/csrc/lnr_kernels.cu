@@ -110,7 +110,7 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
+    DevBuf remap_list, order, order2, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -995,6 +995,30 @@ __global__ void __launch_bounds__(1024) k_order_tasks(const SeedTask * __restric
     for (u32 t = threadIdx.x; t < n_tasks; t += blockDim.x) order[atomicAdd(&s_cnt[bucket(t)], 1u)] = t;
 }
 
+// the same ordering by an explicit per-task key (the hit-section kernels: anchors after the filters, chained hits)
+__global__ void __launch_bounds__(1024) k_order_by_key(const u32 * __restrict__ key, u32 n_tasks, u32 * __restrict__ order)
+{
+    __shared__ u32 s_cnt[136];
+    for (int i = threadIdx.x; i < 136; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    auto bucket = [&](u32 t) -> int {
+        u32 n = key[t];
+        if (n == 0 || n == 0xffffffffu) return 0;
+        int lg = 31 - __clz((int)n);
+        int frac = lg >= 2 ? (int)((n >> (lg - 2)) & 3) : 0;
+        return lg * 4 + frac + 1;
+    };
+    for (u32 t = threadIdx.x; t < n_tasks; t += blockDim.x) atomicAdd(&s_cnt[bucket(t)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        u32 run = 0;
+        for (int b = 135; b >= 0; b--) { u32 c = s_cnt[b]; s_cnt[b] = run; run += c; }
+    }
+    __syncthreads();
+    for (u32 t = threadIdx.x; t < n_tasks; t += blockDim.x) order[atomicAdd(&s_cnt[bucket(t)], 1u)] = t;
+}
+
 // ---- stage 1: hits. One warp per seeding task (primary pass: task r = read r; re-map pass: one task per gap).
 // Everything of apxMap_ up to and including _filterHits; the hits replace the task's anchors in A.
 #ifndef LNR_HITS_MIN_CTAS
@@ -1258,14 +1282,8 @@ __global__ void __launch_bounds__(128, 6) k_hits_blocks(MapArgs a)
             __syncwarp();
             u64 * dh = a.dbg_hits ? a.dbg_hits + a.dbg_hoff[r] : (u64 *)0;
             u32 dcap = dh ? (u32)(a.dbg_hoff[r + 1] - a.dbg_hoff[r]) : 0;
-            u64 * H;
-            rc = hits_sec_blocks(w, c.ar, in, a.B + base, score, n_hits, H, dh, dh ? a.dbg_nhits + r : (u32 *)0, dcap, c.cnt, tl);
-            if (rc == 0)
-            {
-                u64 * out = a.A + base;
-                for (int i = w.lane; i < n_hits; i += 32) out[i] = H[i];
-                if (w.lane == 0) a.task_nhits[ti] = (u32)n_hits;
-            }
+            rc = hits_sec_blocks(w, c.ar, in, a.B + base, score, n_hits, a.A + base, dh, dh ? a.dbg_nhits + r : (u32 *)0, dcap, c.cnt, tl);
+            if (rc == 0 && w.lane == 0) a.task_nhits[ti] = (u32)n_hits;
         }
         if (rc == 1 && w.lane == 0) a.task_nhits[ti] = 0xffffffffu;
         __syncwarp();
@@ -1687,7 +1705,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->order2, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
     ctx->stage.release();
     cudaStreamDestroy(ctx->stream);
@@ -2342,12 +2360,22 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
         as.arena_per_warp = cap_chain;
+        CK(ctx->order2.reserve((size_t)n_reads * sizeof(u32)));
+        as.order = ctx->order2.as<u32>();
+        {
+            LaunchScope ls(ctx, "k_order_by_key");
+            k_order_by_key<<<1, 1024, 0, ctx->stream>>>(a.task_state, n_reads, ctx->order2.as<u32>());
+        }
         {
             LaunchScope ls(ctx, "k_hits_chain");
             k_hits_chain<<<ctx->n_sm * ctx->chain_ctas_per_sm, 128, 0, ctx->stream>>>(as);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
         as.arena_per_warp = cap_blocks;
+        {
+            LaunchScope ls(ctx, "k_order_by_key");
+            k_order_by_key<<<1, 1024, 0, ctx->stream>>>(a.task_state, n_reads, ctx->order2.as<u32>());
+        }
         {
             LaunchScope ls(ctx, "k_hits_blocks");
             k_hits_blocks<<<ctx->n_sm * ctx->blocks_ctas_per_sm, 128, 0, ctx->stream>>>(as);

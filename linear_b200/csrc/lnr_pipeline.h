@@ -806,6 +806,144 @@ LNR_HD int chain_blocks_base(const u64 * recs, const Blk * sep, const i32 * sep_
     return traceback<Blk>(s.sep_tmp, s.rec, nb, s.out_el, s.out_score, s.chain_off, 6, 1, 0, 3, 0.7f);
 }
 
+// ---- warp-cooperative statements of preFilterChains2 / getBestChains2 / chainBlocksBase for the hit blocks.
+// The sequential ones above stay the reference statement (and serve the cord-block stage); these give the same
+// results with the inner loops spread over the lanes: a read with several hundred blocks spent milliseconds in the
+// blocks x cuts scan on one lane and set the kernel's tail.
+LNR_PIPE int prefilter_chains2_w(const Warp & w, u64 * hits, int n_hits, Blk * sep, int nb, Blk * tmp, int cap, u64 * cuts, u64 * strs)
+{
+    const u64 mask = 1ULL << 62;
+    for (int i = w.lane; i < nb; i += w.nl)
+    {
+        cuts[2 * i] = sep[i].first;
+        cuts[2 * i + 1] = (u64)(sep[i].second - 1) | mask;
+        strs[i] = sep[i].first;
+    }
+    wsync(w);
+    if (w.lane == 0)
+        gnu_sort(cuts, 2 * nb, [hits, mask](const u64 & a, const u64 & b) { return cord_y(hits[a & ~mask]) < cord_y(hits[b & ~mask]); });
+    wsync(w);
+    int nt = 0;
+    for (int i = 0; i < 2 * nb; i++)
+    {
+        const u64 cut = cuts[i];
+        const bool is_last = (cut & mask) != 0;
+        const u64 cuty = cord_y(hits[cut & ~mask]);
+        bool stop = false;
+        for (int c = 0; c < nb && !stop; c += w.nl)
+        {
+            const int j = c + w.lane;
+            bool valid = j < nb;
+            const u64 sj = valid ? strs[j] : 0;
+            // the reference's block loop ends at the first block whose start pointer ran to the end of the hits
+            const u32 bb = wballot(w, valid && sj >= (u64)n_hits);
+            if (bb) { valid = valid && w.lane < ffs32(bb); stop = true; }
+            u64 up = 0;
+            bool emit = false;
+            if (valid)
+            {
+                const u64 e = sep[j].second;
+                if (sj < e && !(cuty < cord_y(hits[sj])) && !(cord_y(hits[e - 1]) < cuty))
+                {
+                    u64 lo = sj, hi = e - 1;                              // first k in [lo, hi] with y >= cuty
+                    while (lo < hi)
+                    {
+                        u64 mid = (lo + hi) >> 1;
+                        if (cord_y(hits[mid]) >= cuty) hi = mid; else lo = mid + 1;
+                    }
+                    up = (is_last && cord_y(hits[lo]) == cuty) ? lo + 1 : lo;
+                    emit = sj != up;
+                }
+            }
+            const u32 be = wballot(w, emit);
+            const int cnt = popc32(be);
+            if (nt + cnt > cap) return -1;
+            if (emit)
+            {
+                const int pos = nt + popc_below(w, be);
+                tmp[pos].first = (u32)sj; tmp[pos].second = (u32)up;
+                strs[j] = up;
+            }
+            nt += cnt;
+        }
+        wsync(w);
+    }
+    for (int i = w.lane; i < nt; i += w.nl) sep[i] = tmp[i];
+    wsync(w);
+    if (w.lane == 0) gnu_sort(sep, nt, [](const Blk & a, const Blk & b) { return a.second < b.second; });
+    wsync(w);
+    for (int i = w.lane; i < nt; i += w.nl) wor_flag64(&hits[sep[i].second - 1], kFlagEnd);
+    wsync(w);
+    return nt;
+}
+
+// getBestChains2, mode 0. The sequential scan keeps the LAST j among equal sums (>=), so the lanes take j from
+// i-1 downwards and a later chunk only wins with a strictly larger sum.
+LNR_PIPE void best_chains2_hits_w(const Warp & w, const u64 * recs, const Blk * sep, const i32 * sep_score, ChainRec * ch, int nb)
+{
+    const int depth = 20;
+    for (int i = 0; i < nb; i++)
+    {
+        const int j_str = i - depth > 0 ? i - depth : 0;
+        const u64 ri = recs[sep[i].second - 1];
+        const i32 si = sep_score[i];
+        int max_j = i, new_max = -1;
+        bool found = false;
+        for (int c = 0; i - 1 - c >= j_str; c += w.nl)
+        {
+            const int j = i - 1 - c - w.lane;
+            i32 val = (i32)0x80000000;
+            if (j >= j_str)
+            {
+                int s = score_blocks_hits(recs[sep[j].first], ri);
+                if (s > 0) val = s + ch[j].score + si;
+            }
+            const i32 vmax = wmax_i32(w, val);
+            if (vmax >= -1 && (!found || vmax > new_max))
+            {
+                const u32 b = wballot(w, val == vmax);
+                max_j = i - 1 - c - ffs32(b);
+                new_max = vmax;
+                found = true;
+            }
+        }
+        if (w.lane == 0)
+        {
+            if (new_max > 0)
+            {
+                ch[i].p2anchor = max_j; ch[i].score = new_max;
+                ch[i].len = (i32)(sep[i].second - sep[i].first) + ch[max_j].len;
+                ch[i].score2 = ch[i].score; ch[i].root_ptr = ch[max_j].root_ptr; ch[i].f_leaf = 1; ch[max_j].f_leaf = 0;
+            }
+            else
+            {
+                ch[i].p2anchor = -1; ch[i].score = si; ch[i].len = (i32)(sep[i].second - sep[i].first);
+                ch[i].score2 = ch[i].score; ch[i].root_ptr = i; ch[i].f_leaf = 1;
+            }
+        }
+        wsync(w);
+    }
+}
+
+// chainBlocksBase for the hit blocks (mode 0, sorted by x); the number of chains is returned on every lane
+LNR_PIPE int chain_blocks_hits_w(const Warp & w, const u64 * recs, const Blk * sep, const i32 * sep_score, int nb, BlockScratch & s)
+{
+    if (nb < 2) return 0;
+    for (int i = w.lane; i < nb; i += w.nl) s.ptr[i] = (u32)i;
+    wsync(w);
+    if (w.lane == 0)
+        gnu_sort(s.ptr, nb, [recs, sep](const u32 & a, const u32 & b) { return cord_x40(recs[sep[a].first]) > cord_x40(recs[sep[b].first]); });
+    wsync(w);
+    for (int i = w.lane; i < nb; i += w.nl) { s.sep_tmp[i] = sep[s.ptr[i]]; s.score_tmp[i] = sep_score[s.ptr[i]]; }
+    wsync(w);
+    best_chains2_hits_w(w, recs, s.sep_tmp, s.score_tmp, s.rec, nb);
+    int nch = 0;
+    if (w.lane == 0) nch = traceback<Blk>(s.sep_tmp, s.rec, nb, s.out_el, s.out_score, s.chain_off, 6, 1, 0, 3, 0.7f);
+    nch = wbcast(w, nch, 0);
+    wsync(w);
+    return nch;
+}
+
 // _filterBlocksHits (cluster_util.cpp:633): major chain + up to 4 optional chains > 0.8 * len.
 // Plans the new hit list (without header): which chains survive. keep_chain[c] = 1 for the chains copied, in order.
 // Returns the number of hits that will be written.
@@ -1384,11 +1522,12 @@ LNR_PIPE int hits_sec_chain(const Warp & w, Arena & ar, const PipeIn & in, const
 }
 
 // Section 3: blocks of hits -- gather_blocks_ (:1484) -> preFilterChains2 (:2366) -> chainBlocksHits -> _filterHits
-// (:1417). hits[0..n_hits) with scores; H returns the surviving hits (hits itself or arena memory), n_hits their number.
+// (:1417). hits[0..n_hits) with scores in; the surviving hits are written to out[0..n_hits) (out must not alias hits;
+// capacity: the incoming n_hits). rc 0 = hits in out, 3 = fewer than two hits (the read has none), 1 = arena exhausted.
 LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, const PipeIn & in, u64 * hits, const i32 * hits_score, int & n_hits,
-                             u64 *& H, u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt, long long & tl)
+                             u64 * out, u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt, long long & tl)
 {
-    H = hits;
+    u64 * H = hits;
     Blk * sep = arena_alloc<Blk>(ar, (u64)n_hits + 1);
     Blk * sep_tmp = arena_alloc<Blk>(ar, (u64)n_hits + 1);
     u64 * cuts = arena_alloc<u64>(ar, 2 * (u64)n_hits + 2);
@@ -1397,34 +1536,23 @@ LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, const PipeIn & in, u64 
     u64 * hits2 = arena_alloc<u64>(ar, (u64)n_hits + 2);
     BlockScratch bs;
     block_scratch_alloc(ar, bs, n_hits + 1);
-    u8 * keep = arena_alloc<u8>(ar, (u64)n_hits + 1);
+    u8 * keep_chain = arena_alloc<u8>(ar, 16);
     if (ar.failed) return 1;
-    int err = 0;
     int nb0;
     {
         int dummy = 0;
         nb0 = gather_blocks_w(w, hits, n_hits, (YPair *)0, dummy, sep, in.L, 600, 0, 0);
     }
-    u8 * keep_chain = keep;            // reuse: `keep` is only needed later by the hit window filter
-    int nch = 0;
-    if (w.lane == 0)
-    {
-        int nb = prefilter_chains2(hits, n_hits, sep, nb0, sep_tmp, n_hits + 1, cuts, strs);
-        if (nb < 0) err = 1;
-        else
-        {
-            for (int i = 0; i < nb; i++) sep_score[i] = hits_score[sep[i].first] - hits_score[sep[i].second - 1];
-            nch = chain_blocks_base(hits, sep, sep_score, nb, bs, in.L, 0, 0, 1);
-            if (nch > 0) n_hits = filter_blocks_hits_plan(bs.out_el, bs.chain_off, nch, keep_chain);
-        }
-    }
-    err = wbcast(w, err, 0);
-    if (err) return 1;
-    nch = wbcast(w, nch, 0);
-    n_hits = wbcast(w, n_hits, 0);
+    int nb = prefilter_chains2_w(w, hits, n_hits, sep, nb0, sep_tmp, n_hits + 1, cuts, strs);
+    if (nb < 0) return 1;
+    for (int i = w.lane; i < nb; i += w.nl) sep_score[i] = hits_score[sep[i].first] - hits_score[sep[i].second - 1];
     wsync(w);
+    int nch = chain_blocks_hits_w(w, hits, sep, sep_score, nb, bs);
     if (nch > 0)
     {
+        if (w.lane == 0) n_hits = filter_blocks_hits_plan(bs.out_el, bs.chain_off, nch, keep_chain);
+        n_hits = wbcast(w, n_hits, 0);
+        wsync(w);
         filter_blocks_hits_copy(w, bs.out_el, bs.chain_off, nch, keep_chain, hits, hits2);
         H = hits2;
     }
@@ -1437,32 +1565,36 @@ LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, const PipeIn & in, u64 
     wsync(w);
     LNR_LAP(cnt, 6, tl);
     if (n_hits < 2) return 3;                // path_dst :1457
-    // ---- _filterHits (:1417): drop hits whose own window distance >= reject (50)
-    for (int it = 1 + w.lane; it < n_hits; it += w.nl)
-    {
-        u64 h = H[it];
-        u32 strand = (u32)cord_strand(h), id = (u32)cord_id(h);
-        u64 x1 = cord_y(h) >> 4, x2 = cord_x(h) >> 4;
-        u32 dist = (x1 + 4 < in.nf1 && x2 + 4 < in.nf2[id]) ? window_dist48(in.f1[strand] + x1, in.f2[id] + x2) : 1000u;   // _windowDist :676
-        keep[it] = dist < (u32)kWinReject;
-    }
+    // ---- _filterHits (:1417): drop hits whose own window distance >= reject (50). The reference compacts in place
+    // and re-attaches the end flag of a dropped chain end to the hit kept before it (the sentinel if there is none):
+    // here 32 hits at a time, kept hits to out[1 + number kept before], dropped ends OR their flag into out[number kept
+    // before].
+    if (w.lane == 0) { out[0] = H[0]; cnt.hits += (u64)(n_hits - 1); }
     wsync(w);
-    LNR_LAP(cnt, 7, tl);
-    if (w.lane == 0)
+    int kept = 0;
+    for (int c = 1; c < n_hits; c += w.nl)
     {
-        cnt.hits += (u64)(n_hits - 1);
-        int mv = 0;
-        for (int it = 1; it < n_hits; it++)
+        const int it = c + w.lane;
+        const bool valid = it < n_hits;
+        u64 h = valid ? H[it] : 0;
+        bool keep = false;
+        if (valid)
         {
-            u64 h = H[it];
-            if (keep[it]) H[it - mv] = h;
-            else mv++;
-            if (is_end(h)) H[it - mv] |= kFlagEnd;
+            u32 strand = (u32)cord_strand(h), id = (u32)cord_id(h);
+            u64 x1 = cord_y(h) >> 4, x2 = cord_x(h) >> 4;
+            u32 dist = (x1 + 4 < in.nf1 && x2 + 4 < in.nf2[id]) ? window_dist48(in.f1[strand] + x1, in.f2[id] + x2) : 1000u;   // _windowDist :676
+            keep = dist < (u32)kWinReject;
         }
-        n_hits -= mv;
+        const u32 bk = wballot(w, keep);
+        const int before = kept + popc_below(w, bk);
+        if (keep) out[1 + before] = h;
+        wsync(w);
+        if (valid && !keep && is_end(h)) wor_flag64(&out[before], kFlagEnd);
+        kept += popc32(bk);
+        wsync(w);
     }
-    n_hits = wbcast(w, n_hits, 0);
-    wsync(w);
+    n_hits = 1 + kept;
+    LNR_LAP(cnt, 7, tl);
     return 0;
 }
 
@@ -1490,15 +1622,14 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     int n_hits = 1;
     rc = hits_sec_chain(w, ar, in, X, n2, score_type, hits, hits_score, n_hits, cnt, tl);
     if (rc) return rc;
-    u64 * H;
+    u64 * H = hits_out ? hits_out : arena_alloc<u64>(ar, (u64)n_hits + 2);
+    if (ar.failed) return 1;
     rc = hits_sec_blocks(w, ar, in, hits, hits_score, n_hits, H, dbg_hits, dbg_nhits, dbg_hits_cap, cnt, tl);
     if (rc) return rc == 3 ? 0 : rc;
     if (hits_out)
     {
-        for (int i = w.lane; i < n_hits; i += w.nl) hits_out[i] = H[i];
         if (w.lane == 0) *n_hits_out = (u32)n_hits;
         wsync(w);
-        LNR_LAP(cnt, 7, tl);
         return 0;
     }
     int ok = path_dst_2(w, in, H, n_hits, cords, n_cords, cords_cap, read_str, read_end, cnt) ? 1 : 0;

@@ -71,6 +71,8 @@ LNR_PIPE_INL int wscan_excl(const Warp & w, int v, int & total)
     return s - v;
 }
 LNR_PIPE_INL u32 wmax_u32(const Warp &, u32 v) { return __reduce_max_sync(kFull, v); }
+LNR_PIPE_INL i32 wmax_i32(const Warp &, i32 v) { return __reduce_max_sync(kFull, v); }
+LNR_PIPE_INL void wor_flag64(u64 * p, u64 f) { atomicOr((unsigned long long *)p, (unsigned long long)f); }
 LNR_PIPE_INL u32 wmatch(const Warp &, u32 key) { return __match_any_sync(kFull, key); }
 LNR_PIPE_INL u32 wshift_up32(const Warp &, u32 v) { return __shfl_up_sync(kFull, v, 1); }   // lane l gets lane l-1 (lane 0 keeps its own)
 LNR_PIPE_INL u64 wshift_up64(const Warp &, u64 v)
@@ -92,6 +94,8 @@ LNR_PIPE_INL u64 wor64(const Warp &, u64 v) { return v; }
 LNR_PIPE_INL i64 wmax_i64(const Warp &, i64 v) { return v; }
 LNR_PIPE_INL int wscan_excl(const Warp &, int v, int & total) { total = v; return 0; }
 LNR_PIPE_INL u32 wmax_u32(const Warp &, u32 v) { return v; }
+LNR_PIPE_INL i32 wmax_i32(const Warp &, i32 v) { return v; }
+LNR_PIPE_INL void wor_flag64(u64 * p, u64 f) { *p |= f; }
 LNR_PIPE_INL u32 wmatch(const Warp &, u32) { return 1u; }
 LNR_PIPE_INL u32 wshift_up32(const Warp &, u32 v) { return v; }
 LNR_PIPE_INL u64 wshift_up64(const Warp &, u64 v) { return v; }
