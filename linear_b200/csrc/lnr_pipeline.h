@@ -996,19 +996,51 @@ LNR_PIPE void filter_blocks_hits_copy(const Warp & w, const Blk * el, const int 
 // ----------------------------------------------------------------------------------------------------
 // distances of the read window at feature row y against genome windows x0, x0+1, x0+2 (__windowDist :655;
 // the reference does not bounds-check, the guard only protects the device on out-of-spec data)
-LNR_PIPE_INL void wdist3(const Warp & w, const PipeIn & in, u32 strand, u32 id, u64 y, u64 x0, u32 d[3], PipeCounters & cnt)
+// What stays fixed along one walk (contig, strand), fetched once: the walk itself is a serial chain of window steps, so
+// everything a step re-reads from the tables lengthens the chain.
+struct WinCtx
 {
-    cnt.windows += 3;
-    const u32 nf2 = in.nf2[id];
-    const bool yok = y + 3 < in.nf1;
-    const F96 * fa = in.f1[strand] + y;
-    const F96 * fb = in.f2[id] + x0;
+    const F96 * fa;     // read features of the strand
+    const F96 * fb;     // genome features of the contig
+    u32 nf1, nf2;
+    u64 id, strand;
+    // lane constants of the 18-way split of a step (full warp only): int offsets into the two rows and the sum slot
+    int off_a, off_b, cand, shift;
+    u32 windows;        // candidates evaluated, added to the counters by the caller
+};
+LNR_PIPE_INL WinCtx win_ctx(const Warp & w, const PipeIn & in, u64 cord)
+{
+    WinCtx c;
+    c.id = cord_id(cord); c.strand = cord_strand(cord);
+    c.fa = in.f1[c.strand]; c.fb = in.f2[c.id];
+    c.nf1 = in.nf1; c.nf2 = in.nf2[c.id];
+    int t = w.lane < 18 ? w.lane : 0;
+    int cd = t / 6, part = t - 6 * cd, i = part >= 3 ? 3 : 0, k = part - i;
+    c.cand = cd; c.off_a = 3 * i + k; c.off_b = 3 * (cd + i) + k; c.shift = 10 * cd;
+    c.windows = 0;
+    return c;
+}
+LNR_PIPE_INL void wdist3(const Warp & w, WinCtx & c, u64 y, u64 x0, u32 d[3])
+{
+    c.windows += 3;
+    const u32 nf2 = c.nf2;
+    const bool yok = y + 3 < c.nf1;
+    const F96 * fa = c.fa + y;
+    const F96 * fb = c.fb + x0;
     // every script distance is <= 5*32, a window sums 6 of them: 10 bits per candidate, one warp add
     int packed = 0;
-    for (int t = w.lane; t < 18; t += w.nl)
+    if (w.nl == 32)
     {
-        int c = t / 6, part = t - 6 * c, i = part >= 3 ? 3 : 0, k = part - i;
-        if (yok && x0 + c + 3 < nf2) packed += script_dist(fa[i].v[k], fb[c + i].v[k]) << (10 * c);
+        if (w.lane < 18 && yok && x0 + c.cand + 3 < nf2)
+            packed = script_dist(((const i32 *)fa)[c.off_a], ((const i32 *)fb)[c.off_b]) << c.shift;
+    }
+    else
+    {
+        for (int t = w.lane; t < 18; t += w.nl)
+        {
+            int cd = t / 6, part = t - 6 * cd, i = part >= 3 ? 3 : 0, k = part - i;
+            if (yok && x0 + cd + 3 < nf2) packed += script_dist(fa[i].v[k], fb[cd + i].v[k]) << (10 * cd);
+        }
     }
     packed = wsum(w, packed);
     int s0 = packed & 1023, s1 = (packed >> 10) & 1023, s2 = (packed >> 20) & 1023;
@@ -1016,13 +1048,14 @@ LNR_PIPE_INL void wdist3(const Warp & w, const PipeIn & in, u32 strand, u32 id, 
     d[1] = (yok && x0 + 4 < nf2) ? (u32)s1 : 1000u;
     d[2] = (yok && x0 + 5 < nf2) ? (u32)s2 : 1000u;
 }
-LNR_PIPE_INL u64 previous_window(const Warp & w, const PipeIn & in, u64 cord, PipeCounters & cnt)   // previousWindow :883
+LNR_PIPE_INL u64 previous_window(const Warp & w, WinCtx & c, u64 cord)   // previousWindow :883
 {
-    u64 id = cord_id(cord), strand = cord_strand(cord), x_suf = cord_x(cord) >> 4, y_suf = cord_y(cord) >> 4;
+    const u64 id = c.id, strand = c.strand;
+    u64 x_suf = cord_x(cord) >> 4, y_suf = cord_y(cord) >> 4;
     if (y_suf < (u64)kMed || x_suf < (u64)kSup) return 0;
     u64 y = y_suf - kMed, x0 = x_suf - kSup;       // candidates x_suf-6 .. x_suf-4
     u32 d[3];
-    wdist3(w, in, (u32)strand, (u32)id, y, x0, d, cnt);
+    wdist3(w, c, y, x0, d);
     u32 mn = d[0]; u64 x_min = x0;                  // first strict minimum in ascending x
     if (d[1] < mn) { mn = d[1]; x_min = x0 + 1; }
     if (d[2] < mn) { mn = d[2]; x_min = x0 + 2; }
@@ -1031,13 +1064,14 @@ LNR_PIPE_INL u64 previous_window(const Warp & w, const PipeIn & in, u64 cord, Pi
         return (((id << 30) + ((x_suf - kMed) << 4)) << 20) + ((x_suf - x_min - kMed + y) << 4) + (strand << 61);
     return (((id << 30) + (x_min << 4)) << 20) + (y << 4) + (strand << 61);
 }
-LNR_PIPE_INL u64 next_window(const Warp & w, const PipeIn & in, u64 cord, PipeCounters & cnt)   // nextWindow :1079
+LNR_PIPE_INL u64 next_window(const Warp & w, WinCtx & c, u64 cord)   // nextWindow :1079
 {
-    u64 id = cord_id(cord), strand = cord_strand(cord), x_pre = cord_x(cord) >> 4, y_pre = cord_y(cord) >> 4;
-    if (y_pre + 2 * kSup > (u64)in.nf1 || x_pre + 2 * kSup > (u64)in.nf2[id]) return 0;
+    const u64 id = c.id, strand = c.strand;
+    u64 x_pre = cord_x(cord) >> 4, y_pre = cord_y(cord) >> 4;
+    if (y_pre + 2 * kSup > (u64)c.nf1 || x_pre + 2 * kSup > (u64)c.nf2) return 0;
     u64 y = y_pre + kMed, x0 = x_pre + kInf;        // candidates x_pre+3 .. x_pre+5
     u32 d[3];
-    wdist3(w, in, (u32)strand, (u32)id, y, x0, d, cnt);
+    wdist3(w, c, y, x0, d);
     u32 mn = d[0]; u64 x_min = x0;
     if (d[1] < mn) { mn = d[1]; x_min = x0 + 1; }
     if (d[2] < mn) { mn = d[2]; x_min = x0 + 2; }
@@ -1053,9 +1087,11 @@ LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, 
     int p_str = n - 1;
     const u64 first = last;
     u64 nc;
-    while ((nc = previous_window(w, in, last, cnt)) && cord_y(nc) >= ystr)
+    // every cord of the walk carries the contig and strand of its seeding cord (the windows only move x and y)
+    WinCtx wc = win_ctx(w, in, last);
+    while ((nc = previous_window(w, wc, last)) && cord_y(nc) >= ystr)
     {
-        if (n >= cap) return false;
+        if (n >= cap) { cnt.windows += wc.windows; return false; }
         if (w.lane == 0) cords[n] = nc;
         n++;
         last = nc;
@@ -1070,13 +1106,14 @@ LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, 
         wsync(w);
     }
     last = first;                                   // after the reversal the seeding cord is last again
-    while ((nc = next_window(w, in, last, cnt)) && cord_y(nc) + kWin < yend)
+    while ((nc = next_window(w, wc, last)) && cord_y(nc) + kWin < yend)
     {
-        if (n >= cap) return false;
+        if (n >= cap) { cnt.windows += wc.windows; return false; }
         if (w.lane == 0) cords[n] = nc;
         n++;
         last = nc;
     }
+    cnt.windows += wc.windows;
     return true;
 }
 
