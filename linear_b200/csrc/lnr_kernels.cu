@@ -1028,7 +1028,9 @@ __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, 
 {
     // big_pass: second, tiny launch over the tasks that exhausted the 2 MB per-warp arena (reads with very many
     // anchors), a few warps with a large arena each
-    __shared__ u32 s_hist[4][256];
+    __shared__ u32 s_hist[4][kWarpSmemWords];
+    for (int i = threadIdx.x; i < 4 * kWarpSmemWords; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
     Warp w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
     u32 wid = threadIdx.x >> 5;
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
@@ -1171,7 +1173,9 @@ __device__ __forceinline__ void task_region(const MapArgs & a, u32 ti, const See
 
 __global__ void __launch_bounds__(128, 8) k_hits_sort(MapArgs a)
 {
-    __shared__ u32 s_hist[4][256];
+    __shared__ u32 s_hist[4][kWarpSmemWords];
+    for (int i = threadIdx.x; i < 4 * kWarpSmemWords; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
     StageCommon c;
     stage_begin(a, c);
     const Warp w = c.w;

@@ -255,13 +255,23 @@ LNR_PIPE u64 * gnu_sort_w(const Warp & w, u32 * hist, u64 * a, u64 * s0, u64 * s
 // ----------------------------------------------------------------------------------------------------
 LNR_HD u32 anchor_bin(u64 a) { return (u32)(cord_x(a) / 30000); }
 
+// Per-warp scratch in shared memory: the radix histogram (256) followed by the bin sketch of binning_filter.
+static const int kSketchBits = 10;
+static const int kSketch = 1 << kSketchBits;
+static const int kWarpSmemWords = 256 + kSketch;
+LNR_HD u32 sketch_slot(u32 bin) { return (bin * 2654435761u) >> (32 - kSketchBits); }
+
 // binningFilter (:1979). A[0..n) -> survivors in B (or A unchanged when nothing survives). Returns the
-// buffer that holds the result and its length through n_out. `bins` is the warp's zeroed histogram and is
-// returned zeroed.
-LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u64 * A, u64 * B, int n, int & n_out)
+// buffer that holds the result and its length through n_out. `bins` is the warp's zeroed histogram (one counter per
+// 30-kb bin of the 30-bit x axis, 140 KB) and is returned zeroed; `sketch` (kSketch zeroed counters in shared memory)
+// likewise.
+//
+// The histogram of a warp is far larger than its share of L2, so every access to it is a DRAM round trip, while nearly
+// all anchors of a read are chance hits alone in their bin. The sketch counts hashed bins in shared memory first: a
+// sketch counter is >= the true count of each bin that maps to it, so an anchor whose counter is <= 10 can be dropped
+// without looking at the histogram at all, and only the few candidates take the exact, global path.
+LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u32 * sketch, u64 * A, u64 * B, int n, int & n_out)
 {
-    // Every access to `bins` is a dependent, uncached-latency access (the histogram of a warp spans 140 KB), so each
-    // pass keeps four independent elements per lane in flight.
     const int U = 4, step = U * w.nl;
     for (int c = 0; c < n; c += step)
     {
@@ -275,10 +285,34 @@ LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u64 * A, u64 * B, int 
             if (i < n)
             {
 #ifdef __CUDA_ARCH__
-                atomicAdd(&bins[anchor_bin(v[k])], 1u);
+                atomicAdd(&sketch[sketch_slot(anchor_bin(v[k]))], 1u);
 #else
-                bins[anchor_bin(v[k])]++;
+                sketch[sketch_slot(anchor_bin(v[k]))]++;
 #endif
+            }
+        }
+    }
+    wsync(w);
+    for (int c = 0; c < n; c += step)
+    {
+        u64 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+        {
+            int i = c + k * w.nl + w.lane;
+            if (i < n)
+            {
+                u32 bin = anchor_bin(v[k]);
+                if (sketch[sketch_slot(bin)] > 10)
+                {
+#ifdef __CUDA_ARCH__
+                    atomicAdd(&bins[bin], 1u);
+#else
+                    bins[bin]++;
+#endif
+                }
             }
         }
     }
@@ -290,7 +324,16 @@ LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u64 * A, u64 * B, int 
 #pragma unroll
         for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
 #pragma unroll
-        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; cnt[k] = i < n ? bins[anchor_bin(v[k])] : 0; }
+        for (int k = 0; k < U; k++)
+        {
+            int i = c + k * w.nl + w.lane;
+            cnt[k] = 0;
+            if (i < n)
+            {
+                u32 bin = anchor_bin(v[k]);
+                if (sketch[sketch_slot(bin)] > 10) cnt[k] = bins[bin];
+            }
+        }
 #pragma unroll
         for (int k = 0; k < U; k++)
         {
@@ -307,8 +350,18 @@ LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u64 * A, u64 * B, int 
 #pragma unroll
         for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
 #pragma unroll
-        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; if (i < n) bins[anchor_bin(v[k])] = 0; }
+        for (int k = 0; k < U; k++)
+        {
+            int i = c + k * w.nl + w.lane;
+            if (i < n)
+            {
+                u32 bin = anchor_bin(v[k]);
+                if (sketch[sketch_slot(bin)] > 10) bins[bin] = 0;
+            }
+        }
     }
+    wsync(w);
+    for (int j = w.lane; j < kSketch; j += w.nl) sketch[j] = 0;
     wsync(w);
     if (ii != 0) { n_out = ii; return B; }
     n_out = n;
@@ -1471,6 +1524,7 @@ LNR_HD u64 phase_map_scratch_bound(int n)
 // budget -- as one 250 KB kernel the warps of an SM sat in different sections and starved on instruction fetch.
 
 // Section 1: filterAnchors (:2159: binningFilter + filterAnchors1) and the AnchorX sort of chainAnchorsHits (:2465).
+// hist256: the warp's kWarpSmemWords words of shared memory (radix histogram + zeroed bin sketch).
 // A, B: the task's two n-entry regions (A = raw anchors, A[0] the sentinel slot). On return X[0..n2) are the anchors in
 // chaining order; X is A, B or arena memory. rc: 0 = continue with section 2 (n2 >= 2), 3 = the read has no hits,
 // 1 = arena exhausted.
@@ -1481,7 +1535,7 @@ LNR_PIPE int hits_sec_sort(const Warp & w, Arena & ar, u32 * hist256, u32 * bins
     if (w.lane == 0) A[0] = 0;               // Anchors::init(1) base.cpp:272
     wsync(w);
     int m;
-    u64 * S = binning_filter(w, bins, A, B, n, m);
+    u64 * S = binning_filter(w, bins, hist256 + 256, A, B, n, m);
     LNR_LAP(cnt, 0, tl);
     if (m <= 1) return 3;                    // no chains, hits stay empty (path_dst :1457)
     u64 * O = (S == A) ? B : A;              // the other buffer

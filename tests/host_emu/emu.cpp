@@ -131,7 +131,7 @@ struct ReadRun
     std::vector<u8> arena, a2;
     std::vector<u64> A, B, cords, dbg_hits;
     std::vector<F96> f1[2];
-    u32 hist[256];
+    u32 hist[lnr::kWarpSmemWords] = {0};
 };
 
 // the per-read orchestration of kernels A and B (apxMap, pmpfinder.cpp:2709)
