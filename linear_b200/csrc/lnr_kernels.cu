@@ -110,7 +110,7 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order, order2, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
+    DevBuf remap_list, order, order2, mask_ctr, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -147,6 +147,7 @@ struct lnr_index
     u64 * d_hs;
     uint64_t n_hs;
     u8 * d_hsy = nullptr;    // low byte (the 8-bit Y key) of every hs record, split out for the seeding count pass
+    uint4 * d_dirx = nullptr; // per bucket 32 B: start, size and the first 24 Y keys -- one DRAM access per seed for most buckets
     // HIndex (include/index_util.h:139-248)
     u64 * d_ysa = nullptr;
     uint64_t n_ysa = 0, empty_dir = 0;
@@ -230,6 +231,7 @@ struct GRcAcc   // reverse-complement view (_compltRvseStr base.cpp:335)
 // =====================================================================================================
 // features
 // =====================================================================================================
+static const u32 kMaskPools = 256;    // pools of the seeding match-mask allocator (k_seed_count)
 static const int FT = 256;           // threads per CTA = cells per CTA
 static const int FE = FT - 2;        // entries per CTA
 
@@ -623,6 +625,27 @@ __global__ void k_idx_split_y(const u64 * __restrict__ hs, u64 n, u8 * __restric
     if (i < n) hsy[i] = (u8)(hs[i] & 0xff);
 }
 
+// Lookup entry of the seeding count pass: dir[X], the bucket size and the bucket's first 24 Y keys in one 32-byte
+// sector. A seed whose bucket has <= 24 records (most) then costs one random DRAM access instead of two (dir, hsy).
+__global__ void k_idx_dirx(const i32 * __restrict__ dir, const u8 * __restrict__ hsy, u32 n_buckets, uint4 * __restrict__ out)
+{
+    u32 X = blockIdx.x * blockDim.x + threadIdx.x;
+    if (X >= n_buckets) return;
+    const i32 b = dir[X], e = dir[X + 1];
+    const u32 n = (u32)(e - b);
+    u32 wds[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+    {
+        u32 v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { u32 idx = 4 * q + k; if (idx < n) v |= (u32)hsy[(size_t)b + idx] << (8 * k); }
+        wds[q] = v;
+    }
+    out[2 * (size_t)X] = make_uint4((u32)b, n, wds[0], wds[1]);
+    out[2 * (size_t)X + 1] = make_uint4(wds[2], wds[3], wds[4], wds[5]);
+}
+
 // ascending order inside each bucket (index_util.cpp:1788-1796); one thread per bucket, buckets <= 400
 __global__ void k_idx_sort_buckets(const i32 * __restrict__ dir, u64 * __restrict__ hs, u32 n_buckets)
 {
@@ -722,27 +745,34 @@ __device__ __forceinline__ bool seed_sample_fast(const u8 * __restrict__ rd, i64
 }
 __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
                                                     const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
-                                                    const i32 * __restrict__ dir, const u8 * __restrict__ hsy,
+                                                    const uint4 * __restrict__ dirx, const u8 * __restrict__ hsy,
                                                     u64 * __restrict__ info, u32 * __restrict__ count, unsigned long long * counters,
-                                                    u64 * __restrict__ masks, u32 * __restrict__ mask_off, u32 mask_cap,
-                                                    unsigned int * mask_used)
+                                                    u64 * __restrict__ masks, u32 * __restrict__ mask_off, u32 pool_cap,
+                                                    unsigned int * mask_ctr)
 {
     // masks: one bit per scanned bucket record (1 = passes the Y-key rule), 64 records per word, so that the fill pass
-    // touches only the matching records instead of scanning every bucket a second time. Words are claimed from one
-    // pool with a warp-aggregated atomic; a sample that does not get words (pool exhausted) is re-scanned by the fill.
+    // touches only the matching records instead of scanning every bucket a second time. Words are claimed with one
+    // atomic per warp from one of kMaskPools pools (a single counter serialises 1.4 M atomics in L2; a per-CTA claim
+    // parks the whole CTA on the round trip); a sample that does not get words (pool exhausted) is re-scanned by the fill.
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     u32 c = 0, scanned = 0;
-    i32 bkt_b = 0, bkt_e = 0; u32 qY = 0;
+    i32 bkt_b = 0; u32 qY = 0;
+    uint4 e0 = make_uint4(0, 0, 0, 0), e1 = make_uint4(0, 0, 0, 0);   // the bucket's lookup entry (k_idx_dirx)
     bool active = false;
     u32 X = 0xffffffffu, ti = 0xffffffffu, m = 0;
     SeedTask t;
     memset(&t, 0, sizeof t);
     GAcc acc = {nullptr, 0};
     SeedVal sv = {0, 0, 0};
+    // the 32 samples of a warp are consecutive and a task has ~1300: one search per warp, the lanes walk on from it
+    u32 t_first = 0;
+    if (lane == 0) t_first = find_task(tasks, n_tasks, min(s, n_samples - 1));
+    t_first = __shfl_sync(0xffffffffu, t_first, 0);
     if (s < n_samples)
     {
-        ti = find_task(tasks, n_tasks, s);
+        ti = t_first;
+        while (ti + 1 < n_tasks && tasks[ti + 1].sample0 <= s) ti++;
         t = tasks[ti];
         m = (u32)(s - t.sample0) + 1;
         u64 L = read_off[t.read + 1] - read_off[t.read];
@@ -764,9 +794,10 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         u64 inf = 0;
         if (sv.X != xprev)
         {
-            bkt_b = __ldg(dir + sv.X); bkt_e = __ldg(dir + sv.X + 1);
+            e0 = __ldg(dirx + 2 * (size_t)sv.X); e1 = __ldg(dirx + 2 * (size_t)sv.X + 1);
+            bkt_b = (i32)e0.x;
             qY = sv.Y;
-            scanned = (u32)(bkt_e - bkt_b);
+            scanned = e0.y;
             active = scanned != 0;
             inf = (u64)(u32)bkt_b | ((u64)scanned << 32) | ((u64)sv.Y << 48) | ((u64)sv.strand << 56);
         }
@@ -778,36 +809,22 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t2; }
     u32 wtot = __shfl_sync(0xffffffffu, incl, 31);
-    // one atomic per CTA (a same-address atomic per warp serialises in L2)
-    __shared__ u32 s_w[8], s_base;
     const unsigned wid = threadIdx.x >> 5;
-    if (lane == 0) s_w[wid] = wtot;
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        u32 tot = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { u32 v = s_w[i]; s_w[i] = tot; tot += v; }
-        s_base = tot ? atomicAdd(mask_used, tot) : 0u;
-    }
-    __syncthreads();
-    u32 moff = s_base + s_w[wid] + incl - words;
-    bool have_mask = active && (u64)moff + words <= (u64)mask_cap;
+    const u32 pool = (blockIdx.x * 8u + wid) & (kMaskPools - 1);
+    u32 wbase = 0;
+    if (lane == 0 && wtot) wbase = atomicAdd(mask_ctr + pool, wtot);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    const u32 local = wbase + incl - words;
+    const u32 moff = pool * pool_cap + local;
+    bool have_mask = active && (u64)local + words <= (u64)pool_cap;
     if (active)
     {
-        // 4 Y bytes per step from aligned words; ykey_match(b, Y) with v = b ^ Y, l = lowest set bit of v:
+        // 4 Y bytes per step; ykey_match(b, Y) with v = b ^ Y, l = lowest set bit of v:
         // v == 0 or v >> ctz(v) < 4  <=>  v <= 3 l
-        const u8 * pb = hsy + bkt_b;
-        const unsigned sh = ((unsigned)(uintptr_t)pb & 3u) * 8u;
-        const u32 * pw = (const u32 *)((uintptr_t)pb & ~(uintptr_t)3);
         const u32 Y4 = qY * 0x01010101u;
-        u32 w0 = __ldg(pw);
         u64 mb = 0; u32 wi = 0;
-        for (u32 i = 0; i < scanned; i += 4)
-        {
-            u32 w1 = __ldg(pw + (i >> 2) + 1);
-            u32 v4 = __funnelshift_r(w0, w1, sh) ^ Y4;
-            w0 = w1;
+        auto step4 = [&](u32 w4, u32 i) {
+            u32 v4 = w4 ^ Y4;
             u32 h4 = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -822,22 +839,48 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
             u32 bit = i & 63u;
             mb |= (u64)h4 << bit;
             if (bit == 60 || rem <= 4) { if (have_mask) masks[moff + wi] = mb; wi++; mb = 0; }
+        };
+        // records 0..23 come with the lookup entry
+        const u32 ew[6] = {e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            if (4u * q < scanned) step4(ew[q], 4u * q);
+        if (scanned > 24)
+        {
+            const u8 * pb = hsy + bkt_b + 24;
+            const unsigned sh = ((unsigned)(uintptr_t)pb & 3u) * 8u;
+            const u32 * pw = (const u32 *)((uintptr_t)pb & ~(uintptr_t)3);
+            u32 w0 = __ldg(pw);
+            for (u32 i = 24; i < scanned; i += 4)
+            {
+                u32 w1 = __ldg(pw + ((i - 24) >> 2) + 1);
+                step4(__funnelshift_r(w0, w1, sh), i);
+                w0 = w1;
+            }
         }
     }
     if (s < n_samples) { count[s] = c; mask_off[s] = have_mask ? moff : 0xffffffffu; }
-    // counters: H (records scanned), A (anchors)
-    u32 tot_c = c, tot_s = scanned;
-    for (int o = 16; o; o >>= 1) { tot_c += __shfl_xor_sync(0xffffffffu, tot_c, o); tot_s += __shfl_xor_sync(0xffffffffu, tot_s, o); }
-    __shared__ u32 s_c[8], s_s[8];
-    if (lane == 0) { s_c[wid] = tot_c; s_s[wid] = tot_s; }
+}
+// H (bucket records scanned) and A (anchors) of a seeding pass for lnr_last_batch_counters: summed from the per-sample
+// records by a pass of its own, so that the count kernel neither synchronises its CTA nor funnels atomics into one line
+__global__ void __launch_bounds__(256) k_seed_stats(const u64 * __restrict__ info, const u32 * __restrict__ count, u64 n_samples,
+                                                    unsigned long long * counters)
+{
+    unsigned long long hs = 0, as = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += (u64)gridDim.x * blockDim.x)
+    {
+        hs += (info[i] >> 32) & 0xffff;
+        as += count[i];
+    }
+    for (int o = 16; o; o >>= 1) { hs += __shfl_xor_sync(0xffffffffu, hs, o); as += __shfl_xor_sync(0xffffffffu, as, o); }
+    __shared__ unsigned long long s_h[8], s_a[8];
+    if ((threadIdx.x & 31) == 0) { s_h[threadIdx.x >> 5] = hs; s_a[threadIdx.x >> 5] = as; }
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        unsigned long long bc = 0, bs = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { bc += s_c[i]; bs += s_s[i]; }
-        if (bs) atomicAdd(&counters[1], bs);
-        if (bc) atomicAdd(&counters[2], bc);
+        for (int i = 1; i < 8; i++) { hs += s_h[i]; as += s_a[i]; }
+        if (hs) atomicAdd(&counters[1], hs);
+        if (as) atomicAdd(&counters[2], as);
     }
 }
 // anchors of task ti start at aoff[sample0] + ti (slot 0 of the region is the sentinel)
@@ -1709,7 +1752,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->order2, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
     ctx->stage.release();
     cudaStreamDestroy(ctx->stream);
@@ -1900,6 +1943,16 @@ int lnr_index_export_dindex_device(const lnr_index * ix, int32_t * dev_dir, uint
     CK(cudaStreamSynchronize(ctx->stream));
     return LNR_OK;
 }
+static cudaError_t index_build_dirx(lnr_ctx * ctx, lnr_index * ix)
+{
+    if (ix->d_dirx || ix->index_type != 1) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&ix->d_dirx, (size_t)(kDirSize - 1) * 32);
+    if (e != cudaSuccess) return e;
+    LaunchScope ls(ctx, "k_idx_dirx");
+    k_idx_dirx<<<((kDirSize - 1) + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, ix->d_hsy, kDirSize - 1, ix->d_dirx);
+    return cudaGetLastError();
+}
+
 int lnr_index_from_device(lnr_ctx * ctx, const int32_t * dev_dir, const uint64_t * dev_hs, uint64_t n_hs, lnr_index ** out)
 {
     if (!ctx || !dev_dir || !out || (n_hs && !dev_hs)) return LNR_E_ARG;
@@ -1915,6 +1968,7 @@ int lnr_index_from_device(lnr_ctx * ctx, const int32_t * dev_dir, const uint64_t
     if (n_hs) cudaMemcpyAsync(ix->d_hs, dev_hs, (size_t)n_hs * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream);
     if (cudaMalloc(&ix->d_hsy, (size_t)n_hs + 64) != cudaSuccess) { lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "cudaMalloc failed in lnr_index_from_device"); }
     if (n_hs) k_idx_split_y<<<(u32)((n_hs + 255) / 256), 256, 0, ctx->stream>>>(ix->d_hs, n_hs, ix->d_hsy);
+    if (index_build_dirx(ctx, ix) != cudaSuccess) { lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "cudaMalloc failed in lnr_index_from_device"); }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)); }
     *out = ix;
@@ -2005,6 +2059,7 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
         LaunchScope ls(ctx, "k_idx_split_y");
         k_idx_split_y<<<(u32)((total + 255) / 256), 256, 0, ctx->stream>>>(ix->d_hs, total, ix->d_hsy);
     }
+    if (x_lo == 0 && x_hi >= (u32)(kDirSize - 1)) CKI(index_build_dirx(ctx, ix));   // a shard is never seeded from
     CKI(cudaStreamSynchronize(ctx->stream));
     cleanup();
 #undef CKI
@@ -2032,6 +2087,7 @@ void lnr_index_destroy(lnr_index * ix)
     if (ix->d_dir) cudaFree(ix->d_dir);
     if (ix->d_hs) cudaFree(ix->d_hs);
     if (ix->d_hsy) cudaFree(ix->d_hsy);
+    if (ix->d_dirx) cudaFree(ix->d_dirx);
     if (ix->d_ysa) cudaFree(ix->d_ysa);
     if (ix->d_tab) cudaFree(ix->d_tab);
     delete ix;
@@ -2075,6 +2131,14 @@ int lnr_index_export_hindex(const lnr_index * ix, uint64_t * ysa, uint64_t ysa_c
 static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases, const u64 * d_read_off, SeedTask * d_tasks,
                         u32 n_tasks, u64 n_samples, DevBuf & aoff_buf, u64 * total_out, const char * tag)
 {
+    if (ix->index_type == 1 && !ix->d_dirx)
+    {
+        // an index built as one shard of a sharded build and used on its own: finish its lookup table now
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        CK(index_build_dirx(ctx, const_cast<lnr_index *>(ix)));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     CK(ctx->sample_info.reserve((size_t)(n_samples + 1) * sizeof(u64)));
     CK(ctx->sample_cnt.reserve((size_t)(n_samples + STILE + 1) * sizeof(u32)));
     CK(aoff_buf.reserve((size_t)(n_samples + STILE + 1) * sizeof(u64)));
@@ -2082,8 +2146,10 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     const u32 mask_cap = (u32)std::min<u64>(2 * n_samples + (1u << 20), 0xfffffff0ull);
     CK(ctx->seed_masks.reserve((size_t)mask_cap * sizeof(u64)));
     CK(ctx->seed_mask_off.reserve((size_t)(n_samples + 1) * sizeof(u32)));
-    unsigned int * d_mask_used = (unsigned int *)(ctx->misc.as<u64>() + 22);
-    CK(cudaMemsetAsync(d_mask_used, 0, sizeof(unsigned int), ctx->stream));
+    CK(ctx->mask_ctr.reserve(kMaskPools * sizeof(unsigned int)));
+    unsigned int * d_mask_ctr = ctx->mask_ctr.as<unsigned int>();
+    CK(cudaMemsetAsync(d_mask_ctr, 0, kMaskPools * sizeof(unsigned int), ctx->stream));
+    const u32 pool_cap = mask_cap / kMaskPools;
     u64 * d_total = ctx->misc.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
     const bool hx_mode = ix->index_type == 2;
@@ -2102,9 +2168,9 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
             k_hseed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, hx,
                                                                                    ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
         else
-        k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dir,
+        k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dirx,
                                                                               ix->d_hsy, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters,
-                                                                              ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>(), mask_cap, d_mask_used);
+                                                                              ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>(), pool_cap, d_mask_ctr);
     }
     CK(cudaGetLastError());
     int rc = device_scan<u64>(ctx, ctx->sample_cnt.as<u32>(), n_samples + 1, 0, aoff_buf.as<u64>(), d_total, "k_scan_seeds");
@@ -2126,6 +2192,11 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
         k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs,
                                                                              ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>(),
                                                                              ctx->sample_cnt.as<u32>(), ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>());
+    }
+    if (n_samples && !hx_mode)
+    {
+        LaunchScope ls(ctx, "k_seed_stats");
+        k_seed_stats<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), n_samples, d_counters);
     }
     CK(cudaGetLastError());
     return LNR_OK;
