@@ -110,7 +110,7 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
-    DevBuf remap_list, order, order2, mask_ctr, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
+    DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -365,30 +365,38 @@ __global__ void __launch_bounds__(FT) k_feat_genome(const u8 * __restrict__ g, i
     }
 }
 
-// reads: tile table gives (read, strand, first entry); ftile[i] = first tile of read i (2 strands per read)
+// reads: ftile[i] = first tile of read i (2 strands per read); tile_read[t] = the read tile t belongs to
+__global__ void k_feat_tile_reads(const u32 * __restrict__ ftile, u32 n_reads, u32 * __restrict__ tile_read)
+{
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    for (u32 t = ftile[r]; t < ftile[r + 1]; t++) tile_read[t] = r;
+}
+// persistent CTAs over the tiles: the 2-mer table is built once per CTA, not once per 256 cells
 __global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
-                                                   const u64 * __restrict__ foff, const u32 * __restrict__ ftile, u32 n_reads,
-                                                   F96 * __restrict__ out)
+                                                   const u64 * __restrict__ foff, const u32 * __restrict__ ftile,
+                                                   const u32 * __restrict__ tile_read, u32 n_tiles, F96 * __restrict__ out)
 {
     __shared__ u64 s_lo[FT];
     __shared__ u32 s_hi[FT];
     __shared__ FeatTab T;
     feat_tab_init(T);
     __syncthreads();
-    u32 tile = blockIdx.x;
-    u32 lo_i = 0, hi_i = n_reads;   // largest r with ftile[r] <= tile
-    while (hi_i - lo_i > 1) { u32 mid = (lo_i + hi_i) >> 1; if (ftile[mid] <= tile) lo_i = mid; else hi_i = mid; }
-    u32 r = lo_i;
-    u64 L = read_off[r + 1] - read_off[r];
-    u32 nf = feat_count_read(L);
-    u32 tps = (nf + FE - 1) / FE;               // tiles per strand
-    u32 t = tile - ftile[r];
-    u32 strand = t >= tps ? 1u : 0u;
-    u32 e0 = (t - strand * tps) * FE;
-    F96 * o = out + foff[r] + (u64)strand * nf;
-    const u8 * s = bases + read_off[r];
-    if (!strand) feat_tile_reads<false>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
-    else feat_tile_reads<true>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
+    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        u32 r = tile_read[tile];
+        u64 L = read_off[r + 1] - read_off[r];
+        u32 nf = feat_count_read(L);
+        u32 tps = (nf + FE - 1) / FE;               // tiles per strand
+        u32 t = tile - ftile[r];
+        u32 strand = t >= tps ? 1u : 0u;
+        u32 e0 = (t - strand * tps) * FE;
+        F96 * o = out + foff[r] + (u64)strand * nf;
+        const u8 * s = bases + read_off[r];
+        if (!strand) feat_tile_reads<false>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
+        else feat_tile_reads<true>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
+        __syncthreads();                            // s_lo / s_hi are reused by the next tile
+    }
 }
 
 // =====================================================================================================
@@ -1752,7 +1760,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
     ctx->stage.release();
     cudaStreamDestroy(ctx->stream);
@@ -2310,8 +2318,11 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     // ---- read features (both strands)
     if (n_ftiles)
     {
+        CK(ctx->tile_read.reserve((size_t)n_ftiles * sizeof(u32)));
         LaunchScope ls(ctx, "k_feat_reads");
-        k_feat_reads<<<n_ftiles, FT, 0, ctx->stream>>>(d_bases, d_read_off, ctx->foff.as<u64>(), ctx->ftile.as<u32>(), n_reads, ctx->feats.as<F96>());
+        k_feat_tile_reads<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(ctx->ftile.as<u32>(), n_reads, ctx->tile_read.as<u32>());
+        k_feat_reads<<<std::min<u32>(n_ftiles, (u32)ctx->n_sm * 16), FT, 0, ctx->stream>>>(d_bases, d_read_off, ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
+                                                                                       ctx->tile_read.as<u32>(), n_ftiles, ctx->feats.as<F96>());
     }
     CK(cudaGetLastError());
     // ---- primary seeding
@@ -2732,7 +2743,10 @@ int lnr_read_features(lnr_ctx * ctx, const uint8_t * dna5, uint64_t len, int fea
     CK(cudaMemcpyAsync(ctx->read_off.p, ro, sizeof ro, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->foff.p, fo, sizeof fo, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->ftile.p, ft, sizeof ft, cudaMemcpyHostToDevice, ctx->stream));
-    k_feat_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(), 1, ctx->feats.as<F96>());
+    CK(ctx->tile_read.reserve((size_t)(ft[1] + 1) * sizeof(u32)));
+    CK(cudaMemsetAsync(ctx->tile_read.p, 0, (size_t)(ft[1] + 1) * sizeof(u32), ctx->stream));   // one read: every tile is read 0
+    if (ft[1]) k_feat_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
+                                                ctx->tile_read.as<u32>(), ft[1], ctx->feats.as<F96>());
     CK(cudaGetLastError());
     if (dst_fwd) CK(cudaMemcpyAsync(dst_fwd, ctx->feats.p, (size_t)nf * sizeof(F96), cudaMemcpyDeviceToHost, ctx->stream));
     if (dst_rev) CK(cudaMemcpyAsync(dst_rev, ctx->feats.as<F96>() + nf, (size_t)nf * sizeof(F96), cudaMemcpyDeviceToHost, ctx->stream));
