@@ -40,7 +40,7 @@ METRIC = "reads/sec apx-map+chain (3.1-Gbase synth); index build sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("LNR_BENCH_BATCH", 65536)))
@@ -290,18 +290,29 @@ def main():
     ctx = lb.Context(local_rank)
     lens64 = [int(x) for x in lens]
     # ---- index build, inputs resident in HBM (genome features + DIndex = createFeatures + createIndexDynamic)
+    def build_device_resident():
+        g_ = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=lens64)
+        f_ = lb.create_features(ctx, g_, 2, THREADS_SEM)
+        if world == 1:
+            i_ = lb.create_index(ctx, g_, 1, THREADS_SEM)
+        else:
+            # hash-range sharded build: every rank builds 2^26/N buckets, one all-gather step over NVLink assembles them
+            from linear_b200 import sharding
+            i_ = sharding.build_index_sharded(lb, ctx, g_, THREADS_SEM, rank, world, torch, dist, dev)
+        torch.cuda.synchronize()
+        return g_, f_, i_
+
+    # the first call also pays the process's one-time costs (kernel images, first multi-GB cudaMalloc); it is reported
+    # as seconds_first_call and the build is timed on the second call
+    barrier()
+    t0 = time.time()
+    gen, feats, index = build_device_resident()
+    t_index_first = max_over_ranks(time.time() - t0)
+    index.close(); feats.close(); gen.close()
     ctx.set_profiling(True)
     barrier()
     t0 = time.time()
-    gen = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=lens64)
-    feats = lb.create_features(ctx, gen, 2, THREADS_SEM)
-    if world == 1:
-        index = lb.create_index(ctx, gen, 1, THREADS_SEM)
-    else:
-        # hash-range sharded build: every rank builds 2^26/N buckets, one all-gather step over NVLink assembles them
-        from linear_b200 import sharding
-        index = sharding.build_index_sharded(lb, ctx, gen, THREADS_SEM, rank, world, torch, dist, dev)
-    torch.cuda.synchronize()
+    gen, feats, index = build_device_resident()
     t_index = max_over_ranks(time.time() - t0)
     idx_kernels = ctx.kernel_times()
     n_hs = index.n_hs
@@ -471,7 +482,7 @@ def main():
                                   "frac": round(alg[k] / (kt[k][0] / max(kt[k][1], 1) * 1e-3) / 1e9 / peak, 4)}
                               for k in alg if k in kt and kt[k][0] > 0}
     idx_alg = GENOME_BASES + 8 * n_hs + 4 * ((1 << 26) + 1) + GENOME_BASES + 12 * (GENOME_BASES // 16)
-    index_info = {"seconds": round(t_index, 4), "seconds_e2e_from_host": None if t_index_e2e is None else round(t_index_e2e, 4),
+    index_info = {"seconds": round(t_index, 4), "seconds_first_call": round(t_index_first, 4), "seconds_e2e_from_host": None if t_index_e2e is None else round(t_index_e2e, 4),
                   "n_hs": n_hs, "algorithmic_bytes": idx_alg, "achieved_GBps": idx_alg / t_index / 1e9,
                   "frac_of_hbm_peak": idx_alg / t_index / 1e9 / peak,
                   "kernels_ms": {k: round(v[0], 3) for k, v in idx_kernels.items()}}
