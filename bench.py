@@ -269,6 +269,11 @@ def main():
     import torch.distributed as dist
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+    # version banner and NCCL_DEBUG output to stdout from C) and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import linear_b200 as lb
@@ -433,9 +438,11 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # every rank leaves the process group at the same point; rank 0 alone goes on to the report
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (SURVEY 8d per-unit bytes x units of one launch)
     peaks = {}
@@ -501,9 +508,8 @@ def main():
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "index_build": index_info,
             "clocks": sampler.summary(), "kernels": per_kernel, "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
             "bases_per_step": total_bases}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
