@@ -1082,7 +1082,7 @@ __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, 
     __shared__ u32 s_hist[4][kWarpSmemWords];
     for (int i = threadIdx.x; i < 4 * kWarpSmemWords; i += blockDim.x) (&s_hist[0][0])[i] = 0;
     __syncthreads();
-    Warp w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
+    Warp w = {(int)(threadIdx.x & 31), 0xffffffffu};
     u32 wid = threadIdx.x >> 5;
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
@@ -1168,7 +1168,7 @@ struct StageCommon
 };
 __device__ __forceinline__ void stage_begin(const MapArgs & a, StageCommon & c)
 {
-    c.w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
+    c.w = {(int)(threadIdx.x & 31), 0xffffffffu};
     c.gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     c.ar = {a.arena + (u64)c.gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
     memset(&c.cnt, 0, sizeof c.cnt);
@@ -1347,17 +1347,16 @@ __global__ void __launch_bounds__(128, 6) k_hits_blocks(MapArgs a)
     stage_end(a, c);
 }
 
-// ---- stage 2: window extension (path_dst_2 + extendWindow), ONE THREAD PER READ. The per-step work (3 candidate
-// windows x 2 scripts x 3 ints) and the control flow are the same for every read, so 32 reads advance in lockstep
-// in one warp; reads are taken in length order so that the lanes of a warp have similar trip counts.
+// ---- stage 2: window extension (path_dst_2 + extendWindow), one warp per read on a regular grid; reads are taken in
+// size order so that neighbouring warps have similar trip counts.
 __global__ void __launch_bounds__(128) k_map_extend(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int group)
 {
-    // `group` lanes (power of two <= 32) cooperate on one read: they share the 18 script distances of a window step
+    // the lanes of a warp cooperate on one read: they share the 18 script distances of a window step (sub-warp groups
+    // and one thread per read were measured slower; `group` is kept in the signature and must be 32)
     u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 q = tid / (u32)group;
-    int gl = (int)(tid % (u32)group);
-    unsigned lane32 = threadIdx.x & 31;
-    unsigned gmask = group == 32 ? 0xffffffffu : (((1u << group) - 1u) << (lane32 - (unsigned)gl));
+    u32 q = tid / 32u;
+    int gl = (int)(tid & 31u);
+    (void)group;
     PipeCounters cnt;
     memset(&cnt, 0, sizeof cnt);
     long long t0 = LNR_CLOCK();
@@ -1367,7 +1366,7 @@ __global__ void __launch_bounds__(128) k_map_extend(MapArgs a, const u32 * __res
         u64 L = a.read_off[r + 1] - a.read_off[r];
         if (L > (u64)kMinReadLen)
         {
-            Warp w1 = {gl, group, gmask};
+            Warp w1 = {gl, 0xffffffffu};
             PipeIn in;
             fill_pipe_in(a, r, in);
             ReadSlot slot = a.slots[r];
@@ -1407,7 +1406,7 @@ __global__ void __launch_bounds__(128) k_map_extend(MapArgs a, const u32 * __res
 __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int big_pass)
 {
     // big_pass: tiny second launch over the reads whose chaining scratch did not fit the per-warp arena
-    Warp w = {(int)(threadIdx.x & 31), 32, 0xffffffffu};
+    Warp w = {(int)(threadIdx.x & 31), 0xffffffffu};
     u32 wid = threadIdx.x >> 5;
     u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
     Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
@@ -1705,7 +1704,7 @@ struct SelfKeyHi { __device__ u64 operator()(u64 v) const { return v >> 32; } };
 __global__ void k_selftest_sort(u64 * a, u64 * s0, u64 * s1, int n, u64 * out)
 {
     __shared__ u32 hist[256];
-    Warp w = {(int)threadIdx.x, 32, 0xffffffffu};
+    Warp w = {(int)threadIdx.x, 0xffffffffu};
     u64 * r = gnu_sort_w(w, hist, a, s0, s1, n, 32, SelfKeyHi());
     for (int i = threadIdx.x; i < n; i += 32) out[i] = r[i];
 }
@@ -1728,7 +1727,6 @@ int lnr_ctx_create(int device, lnr_ctx ** out)
     if (const char * e = getenv("LNR_SORT_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->sort_ctas_per_sm = v; }
     if (const char * e = getenv("LNR_CHAIN_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 6) ctx->chain_ctas_per_sm = v; }
     if (const char * e = getenv("LNR_BLOCKS_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 6) ctx->blocks_ctas_per_sm = v; }
-    if (const char * e = getenv("LNR_EXTEND_GROUP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->extend_group = v; }
     if (const char * e = getenv("LNR_BIG_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 16384) ctx->big_arena_bytes_per_warp = (size_t)v << 20; }
     if (const char * e = getenv("LNR_ARENA_KB")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) ctx->arena_bytes_per_warp = (size_t)v << 10; }
     else if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }

@@ -18,8 +18,14 @@ namespace lnr {
 struct Warp
 {
     int lane;        // 0..nl-1
-    int nl;          // lanes that cooperate on one read: 32 (a warp), a power-of-two sub-warp group, or 1
-    unsigned mask;   // member mask of the group inside its hardware warp (device only)
+    // lanes that cooperate on one read: the hardware warp on the device, one lane in the host build. A compile-time
+    // constant on purpose: the pipeline strides, unrolls and divides by it in every inner loop.
+#ifdef __CUDACC__
+    static constexpr int nl = 32;
+#else
+    static constexpr int nl = 1;
+#endif
+    unsigned mask;   // member mask (device only)
 };
 
 #ifdef __CUDACC__
@@ -35,9 +41,7 @@ LNR_PIPE_INL u64 wbcast64(const Warp &, u64 v, int src)
 }
 LNR_PIPE_INL int wsum(const Warp & w, int v)
 {
-    if (w.nl == 32) return __reduce_add_sync(kFull, v);
-    for (int o = w.nl >> 1; o; o >>= 1) v += __shfl_xor_sync(w.mask, v, o);   // sub-warp group (xor stays inside an aligned group)
-    return v;
+    return __reduce_add_sync(kFull, v);
 }
 LNR_PIPE_INL u64 wor64(const Warp &, u64 v)
 {

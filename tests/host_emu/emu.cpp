@@ -137,7 +137,7 @@ struct ReadRun
 // the per-read orchestration of kernels A and B (apxMap, pmpfinder.cpp:2709)
 int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std::vector<u64> * hits_out, int stop_after_first)
 {
-    Warp w = {0, 1, 1u};
+    Warp w = {0, 1u};
     SeqAcc acc = {read, (i64)L};
     RcAcc rc = {read, (i64)L};
     ReadRun R;
@@ -322,7 +322,7 @@ extern "C" int emu_gnu_sort_w_check(uint64_t * keys_payload, int n)
 {
     std::vector<uint64_t> a(keys_payload, keys_payload + n), b(a), s0(n + 1), s1(n + 1);
     std::sort(a.begin(), a.end(), [](uint64_t & x, uint64_t & y) { return (x >> 32) < (y >> 32); });
-    lnr::Warp w = {0, 1, 1u};
+    lnr::Warp w = {0, 1u};
     uint32_t hist[256];
     uint64_t * r = lnr::gnu_sort_w(w, hist, b.data(), s0.data(), s1.data(), n, 32, EmuKeyHi());
     int bad = 0;
