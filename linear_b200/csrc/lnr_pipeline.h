@@ -1060,6 +1060,7 @@ struct WinCtx
     // lane constants of the 18-way split of a step (full warp only): int offsets into the two rows and the sum slot
     int off_a, off_b, cand, shift;
     u32 windows;        // candidates evaluated, added to the counters by the caller
+    u64 hi;             // contig and strand bits of every cord of the walk
 };
 LNR_PIPE_INL WinCtx win_ctx(const Warp & w, const PipeIn & in, u64 cord)
 {
@@ -1071,9 +1072,10 @@ LNR_PIPE_INL WinCtx win_ctx(const Warp & w, const PipeIn & in, u64 cord)
     int cd = t / 6, part = t - 6 * cd, i = part >= 3 ? 3 : 0, k = part - i;
     c.cand = cd; c.off_a = 3 * i + k; c.off_b = 3 * (cd + i) + k; c.shift = 10 * cd;
     c.windows = 0;
+    c.hi = (c.id << 50) + (c.strand << 61);
     return c;
 }
-LNR_PIPE_INL void wdist3(const Warp & w, WinCtx & c, u64 y, u64 x0, u32 d[3])
+LNR_PIPE_INL void wdist3(const Warp & w, WinCtx & c, u32 y, u32 x0, u32 d[3])
 {
     c.windows += 3;
     const u32 nf2 = c.nf2;
@@ -1101,53 +1103,56 @@ LNR_PIPE_INL void wdist3(const Warp & w, WinCtx & c, u64 y, u64 x0, u32 d[3])
     d[1] = (yok && x0 + 4 < nf2) ? (u32)s1 : 1000u;
     d[2] = (yok && x0 + 5 < nf2) ? (u32)s2 : 1000u;
 }
-LNR_PIPE_INL u64 previous_window(const Warp & w, WinCtx & c, u64 cord)   // previousWindow :883
+// One window step in feature-row coordinates (x row = cord_x >> 4, y row = cord_y >> 4; every cord a step produces has
+// zero low nibbles, so the rows carry the whole state of a walk): 32-bit arithmetic, the 64-bit cord is assembled from
+// the walk's constant contig/strand bits only when it is stored. Returns false where the reference returns 0.
+LNR_PIPE_INL bool previous_step(const Warp & w, WinCtx & c, u32 & xr, u32 & yr)   // previousWindow :883
 {
-    const u64 id = c.id, strand = c.strand;
-    u64 x_suf = cord_x(cord) >> 4, y_suf = cord_y(cord) >> 4;
-    if (y_suf < (u64)kMed || x_suf < (u64)kSup) return 0;
-    u64 y = y_suf - kMed, x0 = x_suf - kSup;       // candidates x_suf-6 .. x_suf-4
+    const u32 x_suf = xr, y_suf = yr;
+    if (y_suf < (u32)kMed || x_suf < (u32)kSup) return false;
+    const u32 y = y_suf - kMed, x0 = x_suf - kSup;  // candidates x_suf-6 .. x_suf-4
     u32 d[3];
     wdist3(w, c, y, x0, d);
-    u32 mn = d[0]; u64 x_min = x0;                  // first strict minimum in ascending x
+    u32 mn = d[0], x_min = x0;                      // first strict minimum in ascending x
     if (d[1] < mn) { mn = d[1]; x_min = x0 + 1; }
     if (d[2] < mn) { mn = d[2]; x_min = x0 + 2; }
-    if (mn > (u32)kWinThr) return 0;
-    if (x_suf - x_min > (u64)kMed)
-        return (((id << 30) + ((x_suf - kMed) << 4)) << 20) + ((x_suf - x_min - kMed + y) << 4) + (strand << 61);
-    return (((id << 30) + (x_min << 4)) << 20) + (y << 4) + (strand << 61);
+    if (mn > (u32)kWinThr) return false;
+    if (x_suf - x_min > (u32)kMed) { xr = x_suf - kMed; yr = x_suf - x_min - kMed + y; }
+    else { xr = x_min; yr = y; }
+    return c.hi != 0 || xr != 0 || yr != 0;         // a cord that is numerically 0 reads as "no window" (:1158)
 }
-LNR_PIPE_INL u64 next_window(const Warp & w, WinCtx & c, u64 cord)   // nextWindow :1079
+LNR_PIPE_INL bool next_step(const Warp & w, WinCtx & c, u32 & xr, u32 & yr)   // nextWindow :1079
 {
-    const u64 id = c.id, strand = c.strand;
-    u64 x_pre = cord_x(cord) >> 4, y_pre = cord_y(cord) >> 4;
-    if (y_pre + 2 * kSup > (u64)c.nf1 || x_pre + 2 * kSup > (u64)c.nf2) return 0;
-    u64 y = y_pre + kMed, x0 = x_pre + kInf;        // candidates x_pre+3 .. x_pre+5
+    const u32 x_pre = xr, y_pre = yr;
+    if (y_pre + 2 * kSup > c.nf1 || x_pre + 2 * kSup > c.nf2) return false;
+    const u32 y = y_pre + kMed, x0 = x_pre + kInf;  // candidates x_pre+3 .. x_pre+5
     u32 d[3];
     wdist3(w, c, y, x0, d);
-    u32 mn = d[0]; u64 x_min = x0;
+    u32 mn = d[0], x_min = x0;
     if (d[1] < mn) { mn = d[1]; x_min = x0 + 1; }
     if (d[2] < mn) { mn = d[2]; x_min = x0 + 2; }
-    if (mn > (u32)kWinThr) return 0;
-    if (x_min - x_pre > (u64)kMed)
-        return (((id << 30) + ((x_pre + kMed) << 4)) << 20) + ((x_pre + kMed - x_min + y) << 4) + (strand << 61);
-    return (((id << 30) + (x_min << 4)) << 20) + (y << 4) + (strand << 61);
+    if (mn > (u32)kWinThr) return false;
+    if (x_min - x_pre > (u32)kMed) { xr = x_pre + kMed; yr = x_pre + kMed - x_min + y; }
+    else { xr = x_min; yr = y; }
+    return true;                                     // y >= kMed: never the zero cord
 }
+LNR_PIPE_INL u64 win_cord(const WinCtx & c, u32 xr, u32 yr) { return c.hi + ((u64)xr << 24) + ((u64)yr << 4); }
 // extendWindow :1152; returns false when the cord buffer is full. `last` == cords[n-1] on entry and exit.
 LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, int & n, int cap, u64 & last, u64 ystr, u64 yend,
                                 PipeCounters & cnt)
 {
     int p_str = n - 1;
     const u64 first = last;
-    u64 nc;
     // every cord of the walk carries the contig and strand of its seeding cord (the windows only move x and y)
     WinCtx wc = win_ctx(w, in, last);
-    while ((nc = previous_window(w, wc, last)) && cord_y(nc) >= ystr)
+    const u32 x_first = (u32)(cord_x(last) >> 4), y_first = (u32)(cord_y(last) >> 4);
+    u32 xr = x_first, yr = y_first;
+    while (previous_step(w, wc, xr, yr) && ((u64)yr << 4) >= ystr)
     {
         if (n >= cap) { cnt.windows += wc.windows; return false; }
-        if (w.lane == 0) cords[n] = nc;
+        last = win_cord(wc, xr, yr);
+        if (w.lane == 0) cords[n] = last;
         n++;
-        last = nc;
     }
     if (n - p_str > 1)
     {
@@ -1159,12 +1164,13 @@ LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, 
         wsync(w);
     }
     last = first;                                   // after the reversal the seeding cord is last again
-    while ((nc = next_window(w, wc, last)) && cord_y(nc) + kWin < yend)
+    xr = x_first; yr = y_first;
+    while (next_step(w, wc, xr, yr) && ((u64)yr << 4) + kWin < yend)
     {
         if (n >= cap) { cnt.windows += wc.windows; return false; }
-        if (w.lane == 0) cords[n] = nc;
+        last = win_cord(wc, xr, yr);
+        if (w.lane == 0) cords[n] = last;
         n++;
-        last = nc;
     }
     cnt.windows += wc.windows;
     return true;
