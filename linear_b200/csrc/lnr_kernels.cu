@@ -1310,6 +1310,7 @@ __global__ void __launch_bounds__(128, 6) k_hits_chain(MapArgs a)
 
 __global__ void __launch_bounds__(128, 6) k_hits_blocks(MapArgs a)
 {
+    __shared__ u32 s_hist[4][256];
     StageCommon c;
     stage_begin(a, c);
     const Warp w = c.w;
@@ -1337,7 +1338,7 @@ __global__ void __launch_bounds__(128, 6) k_hits_blocks(MapArgs a)
             __syncwarp();
             u64 * dh = a.dbg_hits ? a.dbg_hits + a.dbg_hoff[r] : (u64 *)0;
             u32 dcap = dh ? (u32)(a.dbg_hoff[r + 1] - a.dbg_hoff[r]) : 0;
-            rc = hits_sec_blocks(w, c.ar, in, a.B + base, score, n_hits, a.A + base, dh, dh ? a.dbg_nhits + r : (u32 *)0, dcap, c.cnt, tl);
+            rc = hits_sec_blocks(w, c.ar, s_hist[threadIdx.x >> 5], in, a.B + base, score, n_hits, a.A + base, dh, dh ? a.dbg_nhits + r : (u32 *)0, dcap, c.cnt, tl);
             if (rc == 0 && w.lane == 0) a.task_nhits[ti] = (u32)n_hits;
         }
         if (rc == 1 && w.lane == 0) a.task_nhits[ti] = 0xffffffffu;

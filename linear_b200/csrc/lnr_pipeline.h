@@ -863,7 +863,10 @@ LNR_HD int chain_blocks_base(const u64 * recs, const Blk * sep, const i32 * sep_
 // The sequential ones above stay the reference statement (and serve the cord-block stage); these give the same
 // results with the inner loops spread over the lanes: a read with several hundred blocks spent milliseconds in the
 // blocks x cuts scan on one lane and set the kernel's tail.
-LNR_PIPE int prefilter_chains2_w(const Warp & w, u64 * hits, int n_hits, Blk * sep, int nb, Blk * tmp, int cap, u64 * cuts, u64 * strs)
+struct CutKeyY { const u64 * hits; LNR_HD u64 operator()(u64 c) const { return cord_y(hits[c & ~(1ULL << 62)]); } };
+struct BlkKeySecond { LNR_HD u64 operator()(u64 v) const { return v >> 32; } };   // Blk viewed as u64: first low, second high
+LNR_PIPE int prefilter_chains2_w(const Warp & w, u32 * hist256, u64 * hits, int n_hits, Blk * sep, int nb, Blk * tmp, int cap, u64 * cuts,
+                                 u64 * strs, u64 * s0, u64 * s1)
 {
     const u64 mask = 1ULL << 62;
     for (int i = w.lane; i < nb; i += w.nl)
@@ -873,9 +876,12 @@ LNR_PIPE int prefilter_chains2_w(const Warp & w, u64 * hits, int n_hits, Blk * s
         strs[i] = sep[i].first;
     }
     wsync(w);
-    if (w.lane == 0)
-        gnu_sort(cuts, 2 * nb, [hits, mask](const u64 & a, const u64 & b) { return cord_y(hits[a & ~mask]) < cord_y(hits[b & ~mask]); });
-    wsync(w);
+    // std::sort(cuts, by y of the hit) -- ties are common (block ends share y with the next block's start)
+    {
+        CutKeyY ky = {hits};
+        u64 * r = gnu_sort_w(w, hist256, cuts, s0, s1, 2 * nb, 20, ky);
+        if (r != cuts) { for (int i = w.lane; i < 2 * nb; i += w.nl) cuts[i] = r[i]; wsync(w); }
+    }
     int nt = 0;
     for (int i = 0; i < 2 * nb; i++)
     {
@@ -921,10 +927,11 @@ LNR_PIPE int prefilter_chains2_w(const Warp & w, u64 * hits, int n_hits, Blk * s
         }
         wsync(w);
     }
-    for (int i = w.lane; i < nt; i += w.nl) sep[i] = tmp[i];
-    wsync(w);
-    if (w.lane == 0) gnu_sort(sep, nt, [](const Blk & a, const Blk & b) { return a.second < b.second; });
-    wsync(w);
+    {
+        u64 * r = gnu_sort_w(w, hist256, (u64 *)tmp, s0, s1, nt, 32, BlkKeySecond());
+        for (int i = w.lane; i < nt; i += w.nl) ((u64 *)sep)[i] = r[i];
+        wsync(w);
+    }
     for (int i = w.lane; i < nt; i += w.nl) wor_flag64(&hits[sep[i].second - 1], kFlagEnd);
     wsync(w);
     return nt;
@@ -979,14 +986,23 @@ LNR_PIPE void best_chains2_hits_w(const Warp & w, const u64 * recs, const Blk * 
 }
 
 // chainBlocksBase for the hit blocks (mode 0, sorted by x); the number of chains is returned on every lane
-LNR_PIPE int chain_blocks_hits_w(const Warp & w, const u64 * recs, const Blk * sep, const i32 * sep_score, int nb, BlockScratch & s)
+struct BlkKeyXDesc
+{
+    const u64 * recs; const Blk * sep;
+    LNR_HD u64 operator()(u64 i) const { return ((1ULL << 40) - 1) - cord_x40(recs[sep[(u32)i].first]); }
+};
+LNR_PIPE int chain_blocks_hits_w(const Warp & w, u32 * hist256, const u64 * recs, const Blk * sep, const i32 * sep_score, int nb, BlockScratch & s,
+                                 u64 * s0, u64 * s1, u64 * s2)
 {
     if (nb < 2) return 0;
-    for (int i = w.lane; i < nb; i += w.nl) s.ptr[i] = (u32)i;
+    for (int i = w.lane; i < nb; i += w.nl) s2[i] = (u64)i;
     wsync(w);
-    if (w.lane == 0)
-        gnu_sort(s.ptr, nb, [recs, sep](const u32 & a, const u32 & b) { return cord_x40(recs[sep[a].first]) > cord_x40(recs[sep[b].first]); });
-    wsync(w);
+    {
+        BlkKeyXDesc kx = {recs, sep};
+        u64 * r = gnu_sort_w(w, hist256, s2, s0, s1, nb, 40, kx);
+        for (int i = w.lane; i < nb; i += w.nl) s.ptr[i] = (u32)r[i];
+        wsync(w);
+    }
     for (int i = w.lane; i < nb; i += w.nl) { s.sep_tmp[i] = sep[s.ptr[i]]; s.score_tmp[i] = sep_score[s.ptr[i]]; }
     wsync(w);
     best_chains2_hits_w(w, recs, s.sep_tmp, s.score_tmp, s.rec, nb);
@@ -1521,7 +1537,7 @@ LNR_PIPE int gather_blocks_w(const Warp & w, u64 * cords, int n, YPair * str_end
 LNR_HD u64 phase_map_scratch_bound(int n)
 {
     u64 m = (u64)n + 2;
-    return m * (8 + 4 + 8 + 8 + 4 + 24 + 8 + 8 + 8 + 16 + 8 + 4 + 52 + 1) + 2048;
+    return m * (8 + 4 + 8 + 8 + 4 + 24 + 8 + 8 + 8 + 16 + 8 + 4 + 52 + 1 + 40) + 2048;
 }
 
 // The hit stage of apxMap_ in three sections. phase_map runs them back to back inside one warp (re-map pass, big-arena
@@ -1621,7 +1637,7 @@ LNR_PIPE int hits_sec_chain(const Warp & w, Arena & ar, const PipeIn & in, const
 // Section 3: blocks of hits -- gather_blocks_ (:1484) -> preFilterChains2 (:2366) -> chainBlocksHits -> _filterHits
 // (:1417). hits[0..n_hits) with scores in; the surviving hits are written to out[0..n_hits) (out must not alias hits;
 // capacity: the incoming n_hits). rc 0 = hits in out, 3 = fewer than two hits (the read has none), 1 = arena exhausted.
-LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, const PipeIn & in, u64 * hits, const i32 * hits_score, int & n_hits,
+LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, u32 * hist256, const PipeIn & in, u64 * hits, const i32 * hits_score, int & n_hits,
                              u64 * out, u64 * dbg_hits, u32 * dbg_nhits, u32 dbg_hits_cap, PipeCounters & cnt, long long & tl)
 {
     u64 * H = hits;
@@ -1634,17 +1650,20 @@ LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, const PipeIn & in, u64 
     BlockScratch bs;
     block_scratch_alloc(ar, bs, n_hits + 1);
     u8 * keep_chain = arena_alloc<u8>(ar, 16);
+    u64 * srt0 = arena_alloc<u64>(ar, 2 * (u64)n_hits + 2);     // scratch of the std::sort emulation (cuts: 2 per block)
+    u64 * srt1 = arena_alloc<u64>(ar, 2 * (u64)n_hits + 2);
+    u64 * srt2 = arena_alloc<u64>(ar, (u64)n_hits + 2);
     if (ar.failed) return 1;
     int nb0;
     {
         int dummy = 0;
         nb0 = gather_blocks_w(w, hits, n_hits, (YPair *)0, dummy, sep, in.L, 600, 0, 0);
     }
-    int nb = prefilter_chains2_w(w, hits, n_hits, sep, nb0, sep_tmp, n_hits + 1, cuts, strs);
+    int nb = prefilter_chains2_w(w, hist256, hits, n_hits, sep, nb0, sep_tmp, n_hits + 1, cuts, strs, srt0, srt1);
     if (nb < 0) return 1;
     for (int i = w.lane; i < nb; i += w.nl) sep_score[i] = hits_score[sep[i].first] - hits_score[sep[i].second - 1];
     wsync(w);
-    int nch = chain_blocks_hits_w(w, hits, sep, sep_score, nb, bs);
+    int nch = chain_blocks_hits_w(w, hist256, hits, sep, sep_score, nb, bs, srt0, srt1, srt2);
     if (nch > 0)
     {
         if (w.lane == 0) n_hits = filter_blocks_hits_plan(bs.out_el, bs.chain_off, nch, keep_chain);
@@ -1721,7 +1740,7 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
     if (rc) return rc;
     u64 * H = hits_out ? hits_out : arena_alloc<u64>(ar, (u64)n_hits + 2);
     if (ar.failed) return 1;
-    rc = hits_sec_blocks(w, ar, in, hits, hits_score, n_hits, H, dbg_hits, dbg_nhits, dbg_hits_cap, cnt, tl);
+    rc = hits_sec_blocks(w, ar, hist256, in, hits, hits_score, n_hits, H, dbg_hits, dbg_nhits, dbg_hits_cap, cnt, tl);
     if (rc) return rc == 3 ? 0 : rc;
     if (hits_out)
     {

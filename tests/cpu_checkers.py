@@ -178,7 +178,7 @@ def build_emu() -> str:
             if f.endswith(".h")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < newest:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", src, "-o", EMU_SO])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fno-strict-aliasing", "-Wno-unknown-pragmas", src, "-o", EMU_SO])
     return EMU_SO
 
 
