@@ -967,6 +967,7 @@ struct MapArgs
     u8 * big_arena; u64 big_arena_per_warp;
     u64 * warp_rec;                                    // optional: 16 u64 per warp, profile of its slowest task
     u64 warp_rec_stage_off;                            // u64 offset of the section kernels' records (8 per warp and section)
+    u64 warp_rec_stage_stride;                         // warps per section in that area
     float stop_ratio;
     unsigned long long * counters;
     // optional debug
@@ -1177,7 +1178,7 @@ __device__ __forceinline__ void stage_begin(const MapArgs & a, StageCommon & c)
 __device__ __forceinline__ void stage_rec_begin(const MapArgs & a, StageCommon & c, int stage)
 {
     if (!a.warp_rec) return;
-    c.rec = a.warp_rec + ((u64)stage * gridDim.x * (blockDim.x >> 5) + c.gw) * 8 + (u64)a.warp_rec_stage_off;
+    c.rec = a.warp_rec + ((u64)stage * a.warp_rec_stage_stride + c.gw) * 8 + (u64)a.warp_rec_stage_off;
     c.g_start = globaltimer_ns(); c.max_dur = 0; c.max_ti = 0; c.max_size = 0; c.max_q = 0; c.n_done = 0; c.t_task = 0;
 }
 __device__ __forceinline__ void stage_task_done(StageCommon & c, u32 ti, u64 size)
@@ -2426,6 +2427,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         CK(cudaMemsetAsync(ctx->warp_rec.p, 0, (size_t)n_warps * 48 * sizeof(u64), ctx->stream));
         a.warp_rec = ctx->warp_rec.as<u64>();
         a.warp_rec_stage_off = n_warps * 24;
+        a.warp_rec_stage_stride = n_warps;
     }
     if (getenv("LNR_MONOLITHIC_HITS"))
     {
@@ -2593,7 +2595,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         for (int st = 0; st < 3; st++)
         {
             const size_t nw = (size_t)ctx->n_sm * cps[st] * 4;
-            const u64 * R = rec.data() + n_warps * 24 + (size_t)st * nw * 8;
+            const u64 * R = rec.data() + n_warps * 24 + (size_t)st * n_warps * 8;
             u64 t0 = ~0ULL, t1 = 0;
             std::vector<double> ends;
             for (size_t wq = 0; wq < nw; wq++) if (R[wq * 8]) { t0 = std::min(t0, R[wq * 8]); t1 = std::max(t1, R[wq * 8 + 1]); }

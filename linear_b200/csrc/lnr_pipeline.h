@@ -882,37 +882,40 @@ LNR_PIPE int prefilter_chains2_w(const Warp & w, u32 * hist256, u64 * hits, int 
         u64 * r = gnu_sort_w(w, hist256, cuts, s0, s1, 2 * nb, 20, ky);
         if (r != cuts) { for (int i = w.lane; i < 2 * nb; i += w.nl) cuts[i] = r[i]; wsync(w); }
     }
+    // per block: y of its current start (0xffffffff once it is used up) and y of its last hit, so that the cuts x blocks
+    // scan is two coalesced loads and two compares per pair; only the rare pair that passes touches the hits
+    u32 * ys = (u32 *)s1;
+    u32 * ye = ys + nb;
+    for (int j = w.lane; j < nb; j += w.nl)
+    {
+        ys[j] = sep[j].first < sep[j].second ? (u32)cord_y(hits[sep[j].first]) : 0xffffffffu;
+        ye[j] = (u32)cord_y(hits[sep[j].second - 1]);
+    }
+    wsync(w);
     int nt = 0;
+    int j_end = nb;      // the reference's block loop ends at the first block whose start pointer ran to the end of the hits
     for (int i = 0; i < 2 * nb; i++)
     {
         const u64 cut = cuts[i];
         const bool is_last = (cut & mask) != 0;
-        const u64 cuty = cord_y(hits[cut & ~mask]);
-        bool stop = false;
-        for (int c = 0; c < nb && !stop; c += w.nl)
+        const u32 cuty = (u32)cord_y(hits[cut & ~mask]);
+        int j_end_next = j_end;
+        for (int c = 0; c < j_end; c += w.nl)
         {
             const int j = c + w.lane;
-            bool valid = j < nb;
-            const u64 sj = valid ? strs[j] : 0;
-            // the reference's block loop ends at the first block whose start pointer ran to the end of the hits
-            const u32 bb = wballot(w, valid && sj >= (u64)n_hits);
-            if (bb) { valid = valid && w.lane < ffs32(bb); stop = true; }
-            u64 up = 0;
+            u64 up = 0, sj = 0;
             bool emit = false;
-            if (valid)
+            if (j < j_end && ys[j] <= cuty && ye[j] >= cuty)
             {
-                const u64 e = sep[j].second;
-                if (sj < e && !(cuty < cord_y(hits[sj])) && !(cord_y(hits[e - 1]) < cuty))
+                sj = strs[j];
+                u64 lo = sj, hi = (u64)sep[j].second - 1;                 // first k in [lo, hi] with y >= cuty
+                while (lo < hi)
                 {
-                    u64 lo = sj, hi = e - 1;                              // first k in [lo, hi] with y >= cuty
-                    while (lo < hi)
-                    {
-                        u64 mid = (lo + hi) >> 1;
-                        if (cord_y(hits[mid]) >= cuty) hi = mid; else lo = mid + 1;
-                    }
-                    up = (is_last && cord_y(hits[lo]) == cuty) ? lo + 1 : lo;
-                    emit = sj != up;
+                    u64 mid = (lo + hi) >> 1;
+                    if ((u32)cord_y(hits[mid]) >= cuty) hi = mid; else lo = mid + 1;
                 }
+                up = (is_last && (u32)cord_y(hits[lo]) == cuty) ? lo + 1 : lo;
+                emit = sj != up;
             }
             const u32 be = wballot(w, emit);
             const int cnt = popc32(be);
@@ -922,9 +925,13 @@ LNR_PIPE int prefilter_chains2_w(const Warp & w, u32 * hist256, u64 * hits, int 
                 const int pos = nt + popc_below(w, be);
                 tmp[pos].first = (u32)sj; tmp[pos].second = (u32)up;
                 strs[j] = up;
+                ys[j] = up < (u64)sep[j].second ? (u32)cord_y(hits[up]) : 0xffffffffu;
             }
+            const u32 bend = wballot(w, emit && up >= (u64)n_hits);
+            if (bend) { int je = c + ffs32(bend); if (je < j_end_next) j_end_next = je; }
             nt += cnt;
         }
+        j_end = j_end_next;
         wsync(w);
     }
     {
