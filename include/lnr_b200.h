@@ -130,6 +130,26 @@ int lnr_last_batch_stage_cycles(lnr_ctx *, uint64_t cycles[16]);
 int lnr_read_features(lnr_ctx *, const uint8_t * dna5, uint64_t len, int feature_type,
                       void * dst_fwd, void * dst_rev, uint64_t cap_entries, uint64_t * n_entries);
 
+/* ---- read ingest -------------------------------------------------------------------------------
+ * FASTA / FASTQ text -> Dna5 ordinals back to back + read offsets + the span of every record id inside the text, on the
+ * device. Replaces seqan's readRecords + Dna5 conversion in front of p_calRecords (loadRecords base.cpp:154,
+ * readRecords4FinPool2_ parallel_io.cpp:466; Dna5 table: A/a C/c G/g T/t/U/u -> 0..3, any other byte -> 4).
+ * FASTA: '>' at a line start opens a record, sequence lines may be wrapped, '\r' and ' ' are dropped. FASTQ: four lines
+ * per record. The text must start with '>' or '@'. cut_id_at_space: ids end at their first blank (loadRecords). */
+typedef struct lnr_reads lnr_reads;
+int lnr_reads_parse(lnr_ctx *, const char * text, uint64_t n_bytes, int cut_id_at_space, lnr_reads ** out);
+/* text already in device memory; first_byte = text[0] (decides the format) */
+int lnr_reads_parse_device(lnr_ctx *, const char * dev_text, uint64_t n_bytes, int first_byte, int cut_id_at_space, lnr_reads ** out);
+int lnr_reads_info(const lnr_reads *, uint64_t * n_reads, uint64_t * total_bases);
+/* any destination may be NULL; read_off has n_reads + 1 entries, id_off / id_len index the ORIGINAL text */
+int lnr_reads_download(const lnr_reads *, uint8_t * bases, uint64_t * read_off, uint64_t * id_off, uint32_t * id_len);
+/* device views for lnr_apxmap_batch_device (bases) -- valid until lnr_reads_destroy */
+int lnr_reads_device(const lnr_reads *, const uint8_t ** dev_bases, const uint64_t ** dev_read_off);
+/* lnr_apxmap_batch over reads [first, first + n_reads) of a parsed set: no host copy of the bases at all */
+int lnr_apxmap_reads(lnr_ctx *, const lnr_index *, const lnr_feats *, const lnr_params *, const lnr_reads *, uint32_t first,
+                     uint32_t n_reads, uint64_t * cords, uint64_t * cords_off, uint64_t cords_capacity, lnr_debug_out * dbg);
+void lnr_reads_destroy(lnr_reads *);
+
 /* self-test of the warp-cooperative std::sort emulation used by chainAnchorsHits (pmpfinder.cpp:2465 sorts by
  * AnchorX only, so tied anchors end up in libstdc++'s introsort order): sorts n 64-bit records in place, ascending by
  * their high 32 bits (30 significant), with one warp. Parity tests compare the result with std::sort on the host. */

@@ -32,6 +32,7 @@ EXPORTS = [
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
     "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch",
     "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
+    "lnr_reads_parse", "lnr_reads_parse_device", "lnr_reads_info", "lnr_reads_download", "lnr_reads_device", "lnr_reads_destroy", "lnr_apxmap_reads",
 ]
 
 
@@ -94,6 +95,15 @@ def load_library() -> C.CDLL:
     lib.lnr_last_batch_counters.argtypes = [vp, u64p]
     lib.lnr_last_batch_stage_cycles.argtypes = [vp, u64p]
     lib.lnr_read_features.argtypes = [vp, u8p, C.c_uint64, C.c_int, vp, vp, C.c_uint64, u64p]
+    lib.lnr_selftest_sort.argtypes = [vp, u64p, C.c_uint32]
+    lib.lnr_reads_parse.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(vp)]
+    lib.lnr_reads_parse_device.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.lnr_reads_info.argtypes = [vp, u64p, u64p]
+    lib.lnr_reads_download.argtypes = [vp, u8p, u64p, u64p, C.POINTER(C.c_uint32)]
+    lib.lnr_reads_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.lnr_reads_destroy.argtypes = [vp]
+    lib.lnr_reads_destroy.restype = None
+    lib.lnr_apxmap_reads.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint64, vp]
     _lib = lib
     return lib
 
@@ -295,6 +305,52 @@ def read_features(ctx: Context, read: np.ndarray, feature_type: int = 2):
         ctx.check(ctx.lib.lnr_read_features(ctx.h, read.ctypes.data_as(u8p), len(read), feature_type,
                                             f.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
     return f, r
+
+
+class Reads:
+    """FASTA / FASTQ text parsed on the device (lnr_reads_parse): Dna5 ordinals, read offsets and ids.
+    Mirrors readRecords + the Dna5 conversion in front of p_calRecords (loadRecords base.cpp:154)."""
+
+    def __init__(self, ctx: Context, text: bytes, cut_id_at_space: bool = False):
+        self.ctx, self.text = ctx, bytes(text)
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.lnr_reads_parse(ctx.h, self.text, len(self.text), int(cut_id_at_space), C.byref(self.h)))
+        n, tb = C.c_uint64(), C.c_uint64()
+        ctx.check(ctx.lib.lnr_reads_info(self.h, C.byref(n), C.byref(tb)))
+        self.n_reads, self.total_bases = int(n.value), int(tb.value)
+
+    def download(self):
+        """(bases uint8[total], offsets uint64[n+1], ids list[str])"""
+        bases = np.empty(self.total_bases, np.uint8)
+        off = np.zeros(self.n_reads + 1, np.uint64)
+        io = np.zeros(max(self.n_reads, 1), np.uint64)
+        il = np.zeros(max(self.n_reads, 1), np.uint32)
+        self.ctx.check(self.ctx.lib.lnr_reads_download(self.h, bases.ctypes.data_as(u8p), off.ctypes.data_as(u64p), io.ctypes.data_as(u64p),
+                                                       il.ctypes.data_as(C.POINTER(C.c_uint32))))
+        ids = [self.text[int(io[i]):int(io[i]) + int(il[i])].decode("latin1") for i in range(self.n_reads)]
+        return bases, off, ids
+
+    def apx_map(self, index: "Index", feats: "Features", first: int = 0, n: Optional[int] = None, preset: int = 1, cap: Optional[int] = None):
+        """lnr_apxmap_reads: map reads [first, first + n) straight from the parsed device buffers"""
+        n = self.n_reads - first if n is None else n
+        cap = int(self.total_bases // 16 + 64 * n + 1024) if cap is None else cap
+        cords = np.empty(cap, dtype=np.uint64)
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        prm = Params(preset=preset, feature_type=feats.feature_type)
+        self.ctx.check(self.ctx.lib.lnr_apxmap_reads(self.ctx.h, index.h, feats.h, C.byref(prm), self.h, first, n, cords.ctypes.data_as(u64p),
+                                                     coff.ctypes.data_as(u64p), cap, None))
+        return cords[:int(coff[n])].copy(), coff
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lnr_reads_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def selftest_sort(ctx: Context, records: np.ndarray) -> np.ndarray:

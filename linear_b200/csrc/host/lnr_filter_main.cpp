@@ -18,7 +18,12 @@
 #include <vector>
 #include "../../../include/lnr_b200.h"
 
-struct Rec { std::string id; std::vector<uint8_t> seq; };
+struct Rec
+{
+    std::string id; std::vector<uint8_t> seq;
+    uint64_t n = 0;   // sequence length when the bases live on the device only (GPU ingest)
+    uint64_t length() const { return seq.empty() ? n : (uint64_t)seq.size(); }
+};
 
 static inline uint8_t ord5(char c)   // seqan Dna5: every non-ACGTU byte is N (alphabet_residue_tabs.h:113-140)
 {
@@ -94,8 +99,8 @@ static void write_apf(std::ostream & of, const std::vector<Rec> & reads, const s
                 for (size_t i = j;; i++)
                     if ((c[i] & kEnd) || i == n - 1) { rend = cy(c[i]) + window; gend = cx(c[i]) + window; break; }
                 if (k > 0) st << "\n";
-                st << "@ " << reads[k].id << " " << reads[k].seq.size() << " " << cy(c[j]) << " "
-                   << std::min<uint64_t>(rend, reads[k].seq.size()) << " " << main_icon << " " << genome[cid(c[j])].id << " "
+                st << "@ " << reads[k].id << " " << reads[k].length() << " " << cy(c[j]) << " "
+                   << std::min<uint64_t>(rend, reads[k].length()) << " " << main_icon << " " << genome[cid(c[j])].id << " "
                    << genome[cid(c[j])].seq.size() << " " << cx(c[j]) << " " << gend << "\n";
                 fflag = 1;
             }
@@ -112,7 +117,7 @@ static void write_apf(std::ostream & of, const std::vector<Rec> & reads, const s
 int main(int argc, char ** argv)
 {
     std::vector<std::string> pos;
-    int threads = 16, preset = 1, index_t = 1, feature_t = 2, ot = 2, device = 0;   // defaults: base.cpp:26-54
+    int threads = 16, preset = 1, index_t = 1, feature_t = 2, ot = 2, device = 0, host_ingest = 0;   // defaults: base.cpp:26-54
     for (int i = 1; i < argc; i++)
     {
         std::string a = argv[i];
@@ -123,6 +128,7 @@ int main(int argc, char ** argv)
         else if (a == "-f" || a == "--feature_type") val(feature_t);
         else if (a == "-ot" || a == "--output_type") val(ot);
         else if (a == "--device") val(device);
+        else if (a == "--host-ingest") host_ingest = 1;
         else if (a == "-g" || a == "-b" || a == "-o" || a == "-c" || a == "-s" || a == "-a") { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }
         else if (!a.empty() && a[0] == '-') { /* other reference options do not affect this path */ }
         else pos.push_back(a);
@@ -152,25 +158,68 @@ int main(int argc, char ** argv)
     stem = stem.substr(0, stem.find('.'));
     std::ofstream of;
     if (ot & 1) of.open(stem + ".apf");
-    SeqReader rr;
-    if (!rr.open(rpath)) { fprintf(stderr, "E[07]:Can't open read file %s\n", rpath.c_str()); return 1; }
-    std::vector<Rec> reads;
     lnr_params prm; memset(&prm, 0, sizeof prm); prm.preset = preset; prm.feature_type = feature_t;
     char main_icon = '+';
     uint64_t n_reads_total = 0, n_cords_total = 0;
-    while (rr.read(reads, 50000, false))   // blockSize, mapper.cpp:892
+    std::vector<Rec> reads;
+    // read ingest on the device (lnr_reads_parse): the file's bytes are uploaded once, parsed there, and the batches are
+    // mapped straight from the parsed buffers; --host-ingest (or a file that does not start with '>' / '@') takes the
+    // host reader instead
+    std::string text;
+    if (!host_ingest)
     {
-        std::vector<uint64_t> off(reads.size() + 1, 0);
-        for (size_t j = 0; j < reads.size(); j++) off[j + 1] = off[j] + reads[j].seq.size();
-        std::vector<uint8_t> bases(off.back());
-        for (size_t j = 0; j < reads.size(); j++) if (!reads[j].seq.empty()) memcpy(&bases[off[j]], reads[j].seq.data(), reads[j].seq.size());
-        std::vector<uint64_t> cords(off.back() / 16 + 64 * reads.size() + 1024), coff(reads.size() + 1);
-        if ((rc = lnr_apxmap_batch(ctx, ix, f2, &prm, (uint32_t)reads.size(), bases.data(), off.data(), cords.data(), coff.data(), cords.size(), nullptr)))
-            return die("lnr_apxmap_batch", rc);
-        main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
-        if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, 96);
-        n_reads_total += reads.size();
-        n_cords_total += coff.back();
+        std::ifstream fin(rpath, std::ios::binary);
+        if (!fin.good()) { fprintf(stderr, "E[07]:Can't open read file %s\n", rpath.c_str()); return 1; }
+        text.assign(std::istreambuf_iterator<char>(fin), std::istreambuf_iterator<char>());
+        if (text.empty() || (text[0] != '>' && text[0] != '@')) host_ingest = 1;
+    }
+    if (!host_ingest)
+    {
+        lnr_reads * R = nullptr;
+        if ((rc = lnr_reads_parse(ctx, text.data(), text.size(), 0, &R))) return die("lnr_reads_parse", rc);
+        uint64_t n_all = 0, tb = 0;
+        lnr_reads_info(R, &n_all, &tb);
+        std::vector<uint64_t> off(n_all + 1), id_off(n_all + 1);
+        std::vector<uint32_t> id_len(n_all + 1);
+        if ((rc = lnr_reads_download(R, nullptr, off.data(), id_off.data(), id_len.data()))) return die("lnr_reads_download", rc);
+        for (uint64_t first = 0; first < n_all; first += 50000)   // blockSize, mapper.cpp:892
+        {
+            const uint32_t n = (uint32_t)std::min<uint64_t>(50000, n_all - first);
+            reads.assign(n, Rec());
+            for (uint32_t j = 0; j < n; j++)
+            {
+                reads[j].id.assign(text.data() + id_off[first + j], id_len[first + j]);
+                reads[j].n = off[first + j + 1] - off[first + j];
+            }
+            const uint64_t nb = off[first + n] - off[first];
+            std::vector<uint64_t> cords(nb / 16 + 64 * (uint64_t)n + 1024), coff(n + 1);
+            if ((rc = lnr_apxmap_reads(ctx, ix, f2, &prm, R, (uint32_t)first, n, cords.data(), coff.data(), cords.size(), nullptr)))
+                return die("lnr_apxmap_reads", rc);
+            main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
+            if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, 96);
+            n_reads_total += n;
+            n_cords_total += coff.back();
+        }
+        lnr_reads_destroy(R);
+    }
+    else
+    {
+        SeqReader rr;
+        if (!rr.open(rpath)) { fprintf(stderr, "E[07]:Can't open read file %s\n", rpath.c_str()); return 1; }
+        while (rr.read(reads, 50000, false))   // blockSize, mapper.cpp:892
+        {
+            std::vector<uint64_t> off(reads.size() + 1, 0);
+            for (size_t j = 0; j < reads.size(); j++) off[j + 1] = off[j] + reads[j].seq.size();
+            std::vector<uint8_t> bases(off.back());
+            for (size_t j = 0; j < reads.size(); j++) if (!reads[j].seq.empty()) memcpy(&bases[off[j]], reads[j].seq.data(), reads[j].seq.size());
+            std::vector<uint64_t> cords(off.back() / 16 + 64 * reads.size() + 1024), coff(reads.size() + 1);
+            if ((rc = lnr_apxmap_batch(ctx, ix, f2, &prm, (uint32_t)reads.size(), bases.data(), off.data(), cords.data(), coff.data(), cords.size(), nullptr)))
+                return die("lnr_apxmap_batch", rc);
+            main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
+            if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, 96);
+            n_reads_total += reads.size();
+            n_cords_total += coff.back();
+        }
     }
     fprintf(stderr, "lnr_b200 filter: %llu reads, %llu cords -> %s.apf\n", (unsigned long long)n_reads_total, (unsigned long long)n_cords_total, stem.c_str());
     lnr_index_destroy(ix); lnr_features_destroy(f2); lnr_genome_destroy(g); lnr_ctx_destroy(ctx);

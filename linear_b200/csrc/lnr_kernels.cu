@@ -1711,6 +1711,8 @@ __global__ void k_selftest_sort(u64 * a, u64 * s0, u64 * s1, int n, u64 * out)
     for (int i = threadIdx.x; i < n; i += 32) out[i] = r[i];
 }
 
+#include "lnr_ingest.cuh"
+
 extern "C" {
 
 int lnr_ctx_create(int device, lnr_ctx ** out)
@@ -2701,6 +2703,93 @@ int lnr_last_batch_stage_cycles(lnr_ctx * ctx, uint64_t cycles[16])
     for (int i = 0; i < 16; i++) cycles[i] = ctx->stage_cycles[i];
     if (getenv("LNR_LONGEST_PROFILE")) for (int i = 0; i < 16; i++) cycles[i] = ctx->longest_cycles[i];
     return LNR_OK;
+}
+
+// ---- read ingest (lnr_ingest.cuh) ---------------------------------------------------------------------------------
+int lnr_reads_parse_device(lnr_ctx * ctx, const char * dev_text, uint64_t n_bytes, int first_byte, int cut_id_at_space, lnr_reads ** out)
+{
+    if (!ctx || !out || (!dev_text && n_bytes)) return LNR_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (n_bytes == 0)
+    {
+        lnr_reads * R = new lnr_reads();
+        R->ctx = ctx;
+        R->h_off.assign(1, 0);
+        *out = R;
+        return LNR_OK;
+    }
+    return reads_parse_device(ctx, (const u8 *)dev_text, n_bytes, first_byte, cut_id_at_space, out);
+}
+int lnr_reads_parse(lnr_ctx * ctx, const char * text, uint64_t n_bytes, int cut_id_at_space, lnr_reads ** out)
+{
+    if (!ctx || !out || (!text && n_bytes)) return LNR_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (n_bytes == 0) return lnr_reads_parse_device(ctx, nullptr, 0, 0, cut_id_at_space, out);
+    CK(ctx->bases.reserve((size_t)n_bytes + 256));   // the batch's base buffer doubles as the text staging area
+    {
+        std::lock_guard<std::mutex> lk(g_upload_mutex);
+        CK(cudaMemcpyAsync(ctx->bases.p, text, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return reads_parse_device(ctx, ctx->bases.as<u8>(), n_bytes, (unsigned char)text[0], cut_id_at_space, out);
+}
+int lnr_reads_info(const lnr_reads * R, uint64_t * n_reads, uint64_t * total_bases)
+{
+    if (!R) return LNR_E_ARG;
+    if (n_reads) *n_reads = R->n_reads;
+    if (total_bases) *total_bases = R->total_bases;
+    return LNR_OK;
+}
+int lnr_reads_download(const lnr_reads * R, uint8_t * bases, uint64_t * read_off, uint64_t * id_off, uint32_t * id_len)
+{
+    if (!R) return LNR_E_ARG;
+    lnr_ctx * ctx = R->ctx;
+    cudaSetDevice(ctx->device);
+    if (read_off && R->n_reads == 0) read_off[0] = 0;
+    if (R->n_reads == 0) return LNR_OK;
+    if (bases && R->total_bases) CK(cudaMemcpyAsync(bases, R->d_bases, R->total_bases, cudaMemcpyDeviceToHost, ctx->stream));
+    if (read_off) CK(cudaMemcpyAsync(read_off, R->d_off, (R->n_reads + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    if (id_off) CK(cudaMemcpyAsync(id_off, R->d_id_off, R->n_reads * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    if (id_len) CK(cudaMemcpyAsync(id_len, R->d_id_len, R->n_reads * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LNR_OK;
+}
+int lnr_reads_device(const lnr_reads * R, const uint8_t ** dev_bases, const uint64_t ** dev_read_off)
+{
+    if (!R) return LNR_E_ARG;
+    if (dev_bases) *dev_bases = R->d_bases;
+    if (dev_read_off) *dev_read_off = R->d_off;
+    return LNR_OK;
+}
+int lnr_apxmap_reads(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, const lnr_params * prm, const lnr_reads * R, uint32_t first,
+                     uint32_t n_reads, uint64_t * cords, uint64_t * cords_off, uint64_t cords_capacity, lnr_debug_out * dbg)
+{
+    if (!ctx || !ix || !f2 || !R || !cords || !cords_off || (u64)first + n_reads > R->n_reads) return LNR_E_ARG;
+    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
+    cudaSetDevice(ctx->device);
+    if (n_reads == 0) { cords_off[0] = 0; return LNR_OK; }
+    std::vector<u64> ro(n_reads + 1);
+    const u64 o0 = R->h_off[first];
+    for (uint32_t i = 0; i <= n_reads; i++) ro[i] = R->h_off[first + i] - o0;
+    CK(ctx->out_cords.reserve((size_t)(cords_capacity + 8) * sizeof(u64)));
+    u64 total = 0;
+    int rc = apxmap_core(ctx, ix, f2, prm, n_reads, R->d_bases + o0, ro.data(), ctx->out_cords.as<u64>(), nullptr, cords_capacity, &total, dbg);
+    if (rc && rc != LNR_E_CAPACITY) return rc;
+    if (rc == LNR_E_CAPACITY && total > cords_capacity) return rc;
+    CK(cudaMemcpyAsync(cords_off, ctx->out_off.p, (n_reads + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cords, ctx->out_cords.p, (size_t)total * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+void lnr_reads_destroy(lnr_reads * R)
+{
+    if (!R) return;
+    cudaSetDevice(R->ctx->device);
+    if (R->d_bases) cudaFree(R->d_bases);
+    if (R->d_off) cudaFree(R->d_off);
+    if (R->d_id_off) cudaFree(R->d_id_off);
+    if (R->d_id_len) cudaFree(R->d_id_len);
+    delete R;
 }
 
 int lnr_selftest_sort(lnr_ctx * ctx, uint64_t * records, uint32_t n)

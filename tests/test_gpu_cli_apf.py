@@ -96,3 +96,41 @@ def test_config0_50mbase_10k_hifi_reads(tmp_path):
     a, b = _apf_blocks(d_ref / "reads.apf"), _apf_blocks(d_new / "reads.apf")
     same = sum(1 for k in b if a.get(k) == b[k])
     assert len(b) >= 9900 and same >= 0.99 * len(b), f"{same} of {len(b)} reads identical to the reference binary"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/linear did not travel")
+def test_device_ingest_of_awkward_fasta_matches_reference_binary(tmp_path):
+    """Read ingest on the device (lnr_reads_parse) pinned end to end: a reads file with ragged line
+    wrapping, CRLF line ends, lower case, N and ids with blanks gives the same APF through the reference binary (seqan
+    readRecords), the CLI mirror with device ingest, and the CLI mirror with its host reader. (IUPAC letters are outside
+    the reference's domain: seqan refuses the whole file and the reference writes an empty APF -- measured here; our
+    readers map them to N.)"""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    g, reads, bases, offs, T, _ = make_case("repeat_ont")
+    alpha = np.frombuffer(b"ACGTN", np.uint8)
+    lines = []
+    for k, r in enumerate(reads):
+        s = bytearray(alpha[r].tobytes())
+        for p in rng.integers(0, len(s), size=len(s) // 300 + 1):
+            s[int(p)] = ord("N")
+        s = bytes(c | 0x20 if rng.random() < 0.25 else c for c in s)
+        lines.append(b">read%d some description %d\r\n" % (k, len(r)))
+        i = 0
+        while i < len(s):
+            w = int(rng.integers(1, 150))
+            lines.append(s[i:i + w] + b"\r\n")
+            i += w
+    gfa, rfa = str(tmp_path / "genome.fa"), str(tmp_path / "reads.fa")
+    datagen.write_fasta(gfa, [f"chr{i + 1} synthetic" for i in range(len(g))], g)
+    open(rfa, "wb").write(b"".join(lines))
+    outs = {}
+    common = ["filter", rfa, gfa, "-ot", "1", "-t", "1", "-p", "1", "-g", "0", "-b", "0"]
+    for tag, cmd in (("ref", [REF_BIN] + common), ("device", [CLI] + common), ("host", [CLI] + common + ["--host-ingest"])):
+        d = tmp_path / tag
+        d.mkdir()
+        subprocess.run(cmd, cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        outs[tag] = open(d / "reads.apf", "rb").read()
+    assert len(outs["ref"]) > 1000
+    assert outs["device"] == outs["host"]
+    assert outs["device"] == outs["ref"]
