@@ -201,6 +201,67 @@ def cpu_reference(contigs_host, bases, offs, n_sample, cores):
                       f"genome features + DIndex built by the same code at -t {THREADS_SEM} in {t_index:.1f} s"}
 
 
+def measure_ingest(lb, ctx, torch, dev, bases_np, offs, n=2048, wrap=80):
+    """SURVEY 8(f) row 3, read ingest: FASTA text (80-column lines) of the first n reads of the batch -> Dna5 ordinals +
+    offsets on the device. GB/s of text, with the text resident in HBM and from host memory (upload inside), next to a
+    one-core numpy statement of the same parse (a port; the reference's own seqan reader is quoted at 8358 reads/thread/s
+    in its README, about 0.17 GB/s)."""
+    import ctypes as C
+    n = min(n, len(offs) - 1)
+    alpha = np.frombuffer(b"ACGTN", np.uint8)
+    parts = []
+    for k in range(n):
+        s = alpha[bases_np[int(offs[k]):int(offs[k + 1])]].tobytes()
+        parts.append(b">read%d\n" % k)
+        parts.extend(s[i:i + wrap] + b"\n" for i in range(0, len(s), wrap))
+    text = b"".join(parts)
+    vp = C.c_void_p
+
+    def parse_host():
+        h = vp()
+        ctx.check(ctx.lib.lnr_reads_parse(ctx.h, text, len(text), 0, C.byref(h)))
+        ctx.lib.lnr_reads_destroy(h)
+
+    t_dev = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(dev)
+
+    def parse_dev():
+        h = vp()
+        ctx.check(ctx.lib.lnr_reads_parse_device(ctx.h, vp(t_dev.data_ptr()), len(text), text[0], 0, C.byref(h)))
+        ctx.lib.lnr_reads_destroy(h)
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.time() - t0) / reps
+
+    th, td = timed(parse_host), timed(parse_dev)
+    # one-core numpy port: strip header lines and newlines, table lookup
+    t0 = time.time()
+    a = np.frombuffer(text, np.uint8)
+    nl = np.flatnonzero(a == 10)
+    starts = np.concatenate([[0], nl[:-1] + 1])
+    is_hdr = a[starts] == ord(">")
+    keep = np.ones(len(a), bool)
+    keep[nl] = False
+    hb, he = starts[is_hdr], nl[is_hdr]
+    for b_, e_ in zip(hb, he):
+        keep[b_:e_] = False
+    lut = np.full(256, 4, np.uint8)
+    for ch, v in (("Aa", 0), ("Cc", 1), ("Gg", 2), ("TtUu", 3)):
+        for c in ch:
+            lut[ord(c)] = v
+    out = lut[a[keep]]
+    t_cpu = time.time() - t0
+    assert len(out) == int(offs[n] - offs[0])
+    gb = len(text) / 1e9
+    return {"text_bytes": len(text), "reads": n, "line_width": wrap, "device_resident_GBps": gb / td, "from_host_GBps": gb / th,
+            "cpu_port_GBps": gb / t_cpu, "cpu_port": "numpy, 1 core", "ms_device_resident": 1000 * td}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -499,6 +560,12 @@ def main():
             cpu = cpu_reference(contigs_host, bases_np, offs, args.cpu_sample, cores)
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
+    ingest = None
+    if world == 1:
+        try:
+            ingest = measure_ingest(lb, ctx, torch, dev, bases_np, offs)
+        except Exception as e:  # noqa: BLE001
+            ingest = {"error": repr(e)}
     launches = sum(v[1] for v in kt.values())
     line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -506,7 +573,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": total_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * dt_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "index_build": index_info,
-            "clocks": sampler.summary(), "kernels": per_kernel, "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
+            "clocks": sampler.summary(), "ingest": ingest, "kernels": per_kernel, "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
             "bases_per_step": total_bases}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -25,6 +25,7 @@ struct lnr_reads
     u64 * d_id_off = nullptr;    // n_reads: offset of the id inside the text
     u32 * d_id_len = nullptr;    // n_reads
     std::vector<u64> h_off;      // host copy of d_off (batch layout of lnr_apxmap_reads)
+    u8 * d_block = nullptr;      // the one allocation behind the four device arrays
 };
 
 __device__ __forceinline__ u32 ing_ord5(u32 c)
@@ -128,14 +129,16 @@ static int reads_parse_device(lnr_ctx * ctx, const u8 * d_text, u64 n, int first
     lnr_reads * R = new lnr_reads();
     R->ctx = ctx; R->n_bytes = n; R->format = format;
     *out = nullptr;
+    // temporaries live in the context's reusable buffers (a cudaMalloc costs more than parsing tens of MB)
     u32 * d_cnt = nullptr; u64 * d_coff = nullptr, * d_ls = nullptr, * d_koff = nullptr, * d_rb = nullptr, * d_tot = nullptr;
     u32 * d_kept = nullptr, * d_hdr = nullptr;
-    auto cleanup = [&]() { for (void * p : {(void *)d_cnt, (void *)d_coff, (void *)d_ls, (void *)d_koff, (void *)d_rb, (void *)d_tot, (void *)d_kept, (void *)d_hdr}) if (p) cudaFree(p); };
+    auto cleanup = [&]() {};
 #define CKR(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); lnr_reads_destroy(R); return fail(ctx, LNR_E_CUDA, cudaGetErrorString(e_)); } } while (0)
     const u64 nt = (n + 15) / 16;
-    CKR(cudaMalloc(&d_cnt, (nt + STILE + 1) * sizeof(u32)));
-    CKR(cudaMalloc(&d_coff, (nt + STILE + 1) * sizeof(u64)));
-    CKR(cudaMalloc(&d_tot, 4 * sizeof(u64)));
+    CKR(ctx->ing[0].reserve((nt + STILE + 1) * sizeof(u32)));
+    CKR(ctx->ing[1].reserve((nt + STILE + 1) * sizeof(u64)));
+    CKR(ctx->ing[2].reserve(4 * sizeof(u64)));
+    d_cnt = ctx->ing[0].as<u32>(); d_coff = ctx->ing[1].as<u64>(); d_tot = ctx->ing[2].as<u64>();
     {
         LaunchScope ls(ctx, "k_ing_count_nl");
         k_ing_count_nl<<<(u32)((nt + 255) / 256), 256, 0, ctx->stream>>>(d_text, n, d_cnt, nt);
@@ -146,15 +149,17 @@ static int reads_parse_device(lnr_ctx * ctx, const u8 * d_text, u64 n, int first
     CKR(cudaMemcpyAsync(&n_nl, d_tot, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CKR(cudaStreamSynchronize(ctx->stream));
     const u64 n_lines = n_nl + 1;
-    CKR(cudaMalloc(&d_ls, (n_lines + 1) * sizeof(u64)));
+    CKR(ctx->ing[3].reserve((n_lines + 1) * sizeof(u64)));
+    d_ls = ctx->ing[3].as<u64>();
     {
         LaunchScope ls(ctx, "k_ing_line_starts");
         k_ing_line_starts<<<(u32)((nt + 255) / 256), 256, 0, ctx->stream>>>(d_text, n, d_coff, d_ls, nt, n_lines);
     }
-    CKR(cudaMalloc(&d_kept, (n_lines + STILE + 1) * sizeof(u32)));
-    CKR(cudaMalloc(&d_hdr, (n_lines + STILE + 1) * sizeof(u32)));
-    CKR(cudaMalloc(&d_koff, (n_lines + STILE + 1) * sizeof(u64)));
-    CKR(cudaMalloc(&d_rb, (n_lines + STILE + 1) * sizeof(u64)));
+    CKR(ctx->ing[4].reserve((n_lines + STILE + 1) * sizeof(u32)));
+    CKR(ctx->ing[5].reserve((n_lines + STILE + 1) * sizeof(u32)));
+    CKR(ctx->ing[6].reserve((n_lines + STILE + 1) * sizeof(u64)));
+    CKR(ctx->ing[7].reserve((n_lines + STILE + 1) * sizeof(u64)));
+    d_kept = ctx->ing[4].as<u32>(); d_hdr = ctx->ing[5].as<u32>(); d_koff = ctx->ing[6].as<u64>(); d_rb = ctx->ing[7].as<u64>();
     const u32 line_ctas = (u32)((n_lines * 32 + 255) / 256);
     {
         LaunchScope ls(ctx, "k_ing_line_info");
@@ -167,11 +172,17 @@ static int reads_parse_device(lnr_ctx * ctx, const u8 * d_text, u64 n, int first
     CKR(cudaMemcpyAsync(tot, d_tot + 1, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CKR(cudaStreamSynchronize(ctx->stream));
     R->total_bases = tot[0]; R->n_reads = tot[1];
-    CKR(cudaMalloc(&R->d_bases, R->total_bases + 256));
+    {
+        // one allocation: [read_off | id_off | id_len | bases + 256 zero bytes]
+        const size_t nr = (size_t)R->n_reads + 1;
+        const size_t o_idoff = nr * sizeof(u64), o_idlen = o_idoff + nr * sizeof(u64);
+        const size_t o_bases = (o_idlen + nr * sizeof(u32) + 255) & ~(size_t)255;
+        u8 * blk = nullptr;
+        CKR(cudaMalloc(&blk, o_bases + R->total_bases + 256));
+        R->d_block = blk;
+        R->d_off = (u64 *)blk; R->d_id_off = (u64 *)(blk + o_idoff); R->d_id_len = (u32 *)(blk + o_idlen); R->d_bases = blk + o_bases;
+    }
     CKR(cudaMemsetAsync(R->d_bases + R->total_bases, 0, 256, ctx->stream));
-    CKR(cudaMalloc(&R->d_off, (R->n_reads + 1) * sizeof(u64)));
-    CKR(cudaMalloc(&R->d_id_off, (R->n_reads + 1) * sizeof(u64)));
-    CKR(cudaMalloc(&R->d_id_len, (R->n_reads + 1) * sizeof(u32)));
     {
         LaunchScope ls(ctx, "k_ing_write");
         k_ing_write<<<line_ctas, 256, 0, ctx->stream>>>(d_text, d_ls, n_lines, format, d_koff, d_rb, d_hdr, cut_id_at_space, R->d_bases, R->d_off,

@@ -110,6 +110,7 @@ struct lnr_ctx
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
+    DevBuf ing[8];   // read-ingest temporaries (lnr_ingest.cuh)
     DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
@@ -1762,7 +1763,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
     ctx->stage.release();
     cudaStreamDestroy(ctx->stream);
@@ -2785,10 +2786,7 @@ void lnr_reads_destroy(lnr_reads * R)
 {
     if (!R) return;
     cudaSetDevice(R->ctx->device);
-    if (R->d_bases) cudaFree(R->d_bases);
-    if (R->d_off) cudaFree(R->d_off);
-    if (R->d_id_off) cudaFree(R->d_id_off);
-    if (R->d_id_len) cudaFree(R->d_id_len);
+    if (R->d_block) cudaFree(R->d_block);
     delete R;
 }
 
