@@ -201,7 +201,7 @@ def cpu_reference(contigs_host, bases, offs, n_sample, cores):
                       f"genome features + DIndex built by the same code at -t {THREADS_SEM} in {t_index:.1f} s"}
 
 
-def measure_ingest(lb, ctx, torch, dev, bases_np, offs, n=2048, wrap=80):
+def measure_ingest(lb, ctx, torch, dev, bases_np, offs, n=8192, wrap=80):
     """SURVEY 8(f) row 3, read ingest: FASTA text (80-column lines) of the first n reads of the batch -> Dna5 ordinals +
     offsets on the device. GB/s of text, with the text resident in HBM and from host memory (upload inside), next to a
     one-core numpy statement of the same parse (a port; the reference's own seqan reader is quoted at 8358 reads/thread/s
@@ -217,12 +217,13 @@ def measure_ingest(lb, ctx, torch, dev, bases_np, offs, n=2048, wrap=80):
     text = b"".join(parts)
     vp = C.c_void_p
 
-    def parse_host():
-        h = vp()
-        ctx.check(ctx.lib.lnr_reads_parse(ctx.h, text, len(text), 0, C.byref(h)))
-        ctx.lib.lnr_reads_destroy(h)
+    t_pin = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()
+    t_dev = t_pin.to(dev)
 
-    t_dev = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(dev)
+    def parse_host():   # text in pinned host memory: the upload is inside
+        h = vp()
+        ctx.check(ctx.lib.lnr_reads_parse(ctx.h, C.cast(t_pin.data_ptr(), C.c_char_p), len(text), 0, C.byref(h)))
+        ctx.lib.lnr_reads_destroy(h)
 
     def parse_dev():
         h = vp()

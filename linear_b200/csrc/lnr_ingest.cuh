@@ -26,6 +26,7 @@ struct lnr_reads
     u32 * d_id_len = nullptr;    // n_reads
     std::vector<u64> h_off;      // host copy of d_off (batch layout of lnr_apxmap_reads)
     u8 * d_block = nullptr;      // the one allocation behind the four device arrays
+    size_t block_bytes = 0;
 };
 
 __device__ __forceinline__ u32 ing_ord5(u32 c)
@@ -177,8 +178,20 @@ static int reads_parse_device(lnr_ctx * ctx, const u8 * d_text, u64 n, int first
         const size_t nr = (size_t)R->n_reads + 1;
         const size_t o_idoff = nr * sizeof(u64), o_idlen = o_idoff + nr * sizeof(u64);
         const size_t o_bases = (o_idlen + nr * sizeof(u32) + 255) & ~(size_t)255;
+        // (cudaMalloc + cudaFree of a block this size cost several times the parse itself: the context keeps the last
+        // block a destroyed lnr_reads gave back and hands it out again when it is large enough)
+        const size_t need = o_bases + R->total_bases + 256;
         u8 * blk = nullptr;
-        CKR(cudaMalloc(&blk, o_bases + R->total_bases + 256));
+        if (ctx->reads_cache && ctx->reads_cache_bytes >= need)
+        {
+            blk = (u8 *)ctx->reads_cache; R->block_bytes = ctx->reads_cache_bytes;
+            ctx->reads_cache = nullptr; ctx->reads_cache_bytes = 0;
+        }
+        else
+        {
+            CKR(cudaMalloc(&blk, need));
+            R->block_bytes = need;
+        }
         R->d_block = blk;
         R->d_off = (u64 *)blk; R->d_id_off = (u64 *)(blk + o_idoff); R->d_id_len = (u32 *)(blk + o_idlen); R->d_bases = blk + o_bases;
     }

@@ -111,6 +111,7 @@ struct lnr_ctx
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
     DevBuf ing[8];   // read-ingest temporaries (lnr_ingest.cuh)
+    void * reads_cache = nullptr; size_t reads_cache_bytes = 0;   // last output block given back by lnr_reads_destroy
     DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
@@ -1766,6 +1767,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
                        &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
         b->release();
     ctx->stage.release();
+    if (ctx->reads_cache) cudaFree(ctx->reads_cache);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -2786,7 +2788,16 @@ void lnr_reads_destroy(lnr_reads * R)
 {
     if (!R) return;
     cudaSetDevice(R->ctx->device);
-    if (R->d_block) cudaFree(R->d_block);
+    if (R->d_block)
+    {
+        lnr_ctx * ctx = R->ctx;
+        if (R->block_bytes > ctx->reads_cache_bytes)
+        {
+            if (ctx->reads_cache) cudaFree(ctx->reads_cache);
+            ctx->reads_cache = R->d_block; ctx->reads_cache_bytes = R->block_bytes;
+        }
+        else cudaFree(R->d_block);
+    }
     delete R;
 }
 
