@@ -415,11 +415,12 @@ LNR_HD u32 chain_derr(i32 da, i32 dy, i32 dx, i32 floor_)
     if (da < (1 << 25)) return (100u * (u32)da) / (u32)den;
     return (u32)((100ULL * (u64)da) / (u64)den);
 }
-LNR_HD int score_anchor(u64 a1, u64 a2)   // getApxChainScore :387
+// (x, y) = (anchor_x, cord_y) of the two anchors, decoded once by the caller
+LNR_HD int score_anchor_xy(i32 x1, i32 y1, i32 x2, i32 y2)   // getApxChainScore :387
 {
-    i32 dy = (i32)(u32)(cord_y(a1) - cord_y(a2));
+    i32 dy = y1 - y2;
     if (dy < 10) return -10000;
-    i32 dx = (i32)(u32)(anchor_x(a1) - anchor_x(a2));
+    i32 dx = x1 - x2;
     i32 da = dx - dy;
     if (da < 0) da = -da;
     i32 derr = (i32)chain_derr(da, dy, dx, 50);
@@ -436,17 +437,19 @@ LNR_HD int score_anchor(u64 a1, u64 a2)   // getApxChainScore :387
     else sdy = 10000;
     return da < 10 ? 100 - sdy : 100 - sdy - sderr;
 }
-LNR_HD int score_anchor0(u64 a1, u64 a2)   // getApxChainScore0 :337
+LNR_HD int score_anchor0_xy(i32 x1, i32 y1, i32 x2, i32 y2)   // getApxChainScore0 :337
 {
-    i32 dy = (i32)(u32)(cord_y(a1) - cord_y(a2));
+    i32 dy = y1 - y2;
     if (dy < 5) return -10000;
-    i32 dx = (i32)(u32)(anchor_x(a1) - anchor_x(a2));
+    i32 dx = x1 - x2;
     i32 da = dx - dy;
     if (da < 0) da = -da;
     if (chain_derr(da, dy, dx, 50) >= 100) return -1000;
     int sdy = dy, sderr = da;
     return da < 30 ? 100 - sdy : 100 - sdy - sderr;
 }
+LNR_HD int score_anchor(u64 a1, u64 a2) { return score_anchor_xy((i32)anchor_x(a1), (i32)cord_y(a1), (i32)anchor_x(a2), (i32)cord_y(a2)); }
+LNR_HD int score_anchor0(u64 a1, u64 a2) { return score_anchor0_xy((i32)anchor_x(a1), (i32)cord_y(a1), (i32)anchor_x(a2), (i32)cord_y(a2)); }
 LNR_HD int score_blocks_hits(u64 c11, u64 c22)   // getApxChainScore2 :586
 {
     i64 dy = (i64)(cord_y(c11) - cord_y(c22));
@@ -514,7 +517,7 @@ LNR_PIPE void best_chains(const Warp & w, const u64 * a, ChainRec * ch, int n, i
 {
     const int depth = 20;
     const u64 dx_depth = 300;
-    u64 aj = 0;                       // anchor of predecessor i-1-lane
+    i32 xj = 0, yj = 0;               // anchor_x / cord_y of predecessor i-1-lane (decoded once, when it enters the window)
     i32 sj = 0, lenj = 0, rootj = 0;  // its chain score / length / root
     u64 a_next = n > 0 ? a[0] : 0;
     for (int i = 0; i < n; i++)
@@ -522,15 +525,16 @@ LNR_PIPE void best_chains(const Warp & w, const u64 * a, ChainRec * ch, int n, i
         const u64 ai = a_next;
         if (i + 1 < n) a_next = a[i + 1];
         const u64 xi = anchor_x(ai);
+        const i32 xi32 = (i32)xi, yi32 = (i32)cord_y(ai);
         const int j = i - 1 - w.lane;
-        bool ok = j >= 0 && (w.lane < depth || anchor_x(aj) - xi < dx_depth);
+        bool ok = j >= 0 && (w.lane < depth || (u64)(u32)xj - xi < dx_depth);
         u32 okmask = wballot(w, ok);
         u32 full = w.nl == 32 ? 0xffffffffu : ((1u << w.nl) - 1);
         int first_fail = okmask == full ? w.nl : ffs32(~okmask & full);
         u32 key = 0;                  // (sum << 5) | lane ; 0 = none
         if (ok && w.lane < first_fail)
         {
-            int s = score_pair(aj, ai, score_type);
+            int s = score_type == 0 ? score_anchor_xy(xj, yj, xi32, yi32) : score_anchor0_xy(xj, yj, xi32, yi32);
             if (s > 0) key = ((u32)(s + sj) << 5) | (u32)w.lane;
         }
         key = wmax_u32(w, key);
@@ -583,8 +587,9 @@ LNR_PIPE void best_chains(const Warp & w, const u64 * a, ChainRec * ch, int n, i
             if (max_j >= 0) ch[max_j].f_leaf = 0;
         }
         // slide the window: lane l takes lane l-1, lane 0 takes element i
-        aj = wshift_up64(w, aj); sj = (i32)wshift_up32(w, (u32)sj); lenj = (i32)wshift_up32(w, (u32)lenj); rootj = (i32)wshift_up32(w, (u32)rootj);
-        if (w.lane == 0) { aj = ai; sj = c_score; lenj = c_len; rootj = c_root; }
+        xj = (i32)wshift_up32(w, (u32)xj); yj = (i32)wshift_up32(w, (u32)yj);
+        sj = (i32)wshift_up32(w, (u32)sj); lenj = (i32)wshift_up32(w, (u32)lenj); rootj = (i32)wshift_up32(w, (u32)rootj);
+        if (w.lane == 0) { xj = xi32; yj = yi32; sj = c_score; lenj = c_len; rootj = c_root; }
     }
     wsync(w);
 }
