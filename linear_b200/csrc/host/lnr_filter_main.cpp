@@ -101,7 +101,7 @@ static void write_apf(std::ostream & of, const std::vector<Rec> & reads, const s
                 if (k > 0) st << "\n";
                 st << "@ " << reads[k].id << " " << reads[k].length() << " " << cy(c[j]) << " "
                    << std::min<uint64_t>(rend, reads[k].length()) << " " << main_icon << " " << genome[cid(c[j])].id << " "
-                   << genome[cid(c[j])].seq.size() << " " << cx(c[j]) << " " << gend << "\n";
+                   << genome[cid(c[j])].length() << " " << cx(c[j]) << " " << gend << "\n";
                 fflag = 1;
             }
             char icon = cs(c[j]) ? '-' : '+';
@@ -139,18 +139,50 @@ int main(int argc, char ** argv)
         return 1;
     }
     const std::string rpath = pos[1], gpath = pos[2];
-    SeqReader gr;
-    if (!gr.open(gpath)) { fprintf(stderr, "E[06]:Can't open file %s\n", gpath.c_str()); return 1; }
-    std::vector<Rec> genome;
-    gr.read(genome, 0, true);
-    if (genome.size() >= 1024) { fprintf(stderr, "too many contigs (linear.cpp:107)\n"); return 1; }
     lnr_ctx * ctx = nullptr; lnr_genome * g = nullptr; lnr_feats * f2 = nullptr; lnr_index * ix = nullptr;
     auto die = [&](const char * what, int rc) { fprintf(stderr, "lnr_b200: %s failed (%d): %s\n", what, rc, ctx ? lnr_last_error(ctx) : "no CUDA device"); return 2; };
     int rc;
     if ((rc = lnr_ctx_create(device, &ctx))) return die("lnr_ctx_create", rc);
-    std::vector<const uint8_t *> ptr; std::vector<uint64_t> len;
-    for (auto & r : genome) { ptr.push_back(r.seq.data()); len.push_back(r.seq.size()); }
-    if ((rc = lnr_genome_upload(ctx, (uint32_t)genome.size(), ptr.data(), len.data(), &g))) return die("lnr_genome_upload", rc);
+    std::vector<Rec> genome;
+    {
+        // the genome takes the same road as the reads: bytes -> device parse -> lnr_genome_from_device (ids end at the
+        // first blank, loadRecords base.cpp:154); the host reader is the fallback
+        std::string gtext;
+        std::ifstream gin(gpath, std::ios::binary);
+        if (!gin.good()) { fprintf(stderr, "E[06]:Can't open file %s\n", gpath.c_str()); return 1; }
+        if (!host_ingest) gtext.assign(std::istreambuf_iterator<char>(gin), std::istreambuf_iterator<char>());
+        if (!host_ingest && !gtext.empty() && gtext[0] == '>')
+        {
+            lnr_reads * G = nullptr;
+            if ((rc = lnr_reads_parse(ctx, gtext.data(), gtext.size(), 1, &G))) return die("lnr_reads_parse(genome)", rc);
+            uint64_t nc = 0, tb = 0;
+            lnr_reads_info(G, &nc, &tb);
+            if (nc >= 1024) { fprintf(stderr, "too many contigs (linear.cpp:107)\n"); return 1; }
+            std::vector<uint64_t> off(nc + 1), id_off(nc + 1), len(nc);
+            std::vector<uint32_t> id_len(nc + 1);
+            if ((rc = lnr_reads_download(G, nullptr, off.data(), id_off.data(), id_len.data()))) return die("lnr_reads_download(genome)", rc);
+            genome.assign(nc, Rec());
+            for (uint64_t i = 0; i < nc; i++)
+            {
+                genome[i].id.assign(gtext.data() + id_off[i], id_len[i]);
+                genome[i].n = len[i] = off[i + 1] - off[i];
+            }
+            const uint8_t * dev_bases = nullptr;
+            lnr_reads_device(G, &dev_bases, nullptr);
+            if ((rc = lnr_genome_from_device(ctx, (uint32_t)nc, dev_bases, len.data(), &g))) return die("lnr_genome_from_device", rc);
+            lnr_reads_destroy(G);
+        }
+        else
+        {
+            SeqReader gr;
+            if (!gr.open(gpath)) { fprintf(stderr, "E[06]:Can't open file %s\n", gpath.c_str()); return 1; }
+            gr.read(genome, 0, true);
+            if (genome.size() >= 1024) { fprintf(stderr, "too many contigs (linear.cpp:107)\n"); return 1; }
+            std::vector<const uint8_t *> ptr; std::vector<uint64_t> len;
+            for (auto & r : genome) { ptr.push_back(r.seq.data()); len.push_back(r.seq.size()); }
+            if ((rc = lnr_genome_upload(ctx, (uint32_t)genome.size(), ptr.data(), len.data(), &g))) return die("lnr_genome_upload", rc);
+        }
+    }
     if ((rc = lnr_features_build(ctx, g, feature_t, (unsigned)threads, &f2))) return die("lnr_features_build", rc);
     if ((rc = lnr_index_build(ctx, g, index_t, (unsigned)threads, &ix))) return die("lnr_index_build", rc);
     // output prefix = read file stem (mapper.cpp:904-906)
