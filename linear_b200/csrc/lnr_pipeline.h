@@ -82,6 +82,31 @@ LNR_HD u32 wdist(const PipeIn & in, u32 strand, u32 id, u64 y, u64 x, PipeCounte
 // ----------------------------------------------------------------------------------------------------
 struct KeyAsc { LNR_HD u64 operator()(u64 v) const { return v; } };
 struct KeyXDesc { LNR_HD u64 operator()(u64 v) const { return (u64)0x3fffffffULL - anchor_x(v); } };
+// One key functor for every sort of the pipeline, selected at run time: each functor type would instantiate its own
+// copy of radix_sort / gnu_sort_w, and the section kernels are bound by instruction fetch as much as by anything else.
+struct SortKey
+{
+    int mode;          // 0 anchor value ascending, 1 AnchorX descending, 2 y of the hit a cut points to, 3 Blk.second ascending
+                       // (Blk viewed as u64: first low, second high), 4 x40 of a block's first record descending (elements
+                       // are block indices)
+    const u64 * recs;  // modes 2, 4
+    const Blk * sep;   // mode 4
+    LNR_HD u64 operator()(u64 v) const
+    {
+        switch (mode)
+        {
+        case 0: return v;
+        case 1: return (u64)0x3fffffffULL - anchor_x(v);
+        case 2: return cord_y(recs[v & ~(1ULL << 62)]);
+        case 3: return v >> 32;
+        default: return ((1ULL << 40) - 1) - cord_x40(recs[sep[(u32)v].first]);
+        }
+    }
+};
+LNR_HD SortKey sort_key(int mode, const u64 * recs = (const u64 *)0, const Blk * sep = (const Blk *)0)
+{
+    SortKey k; k.mode = mode; k.recs = recs; k.sep = sep; return k;
+}
 
 template <class KeyFn>
 LNR_PIPE u64 * radix_sort(const Warp & w, u32 * hist, u64 * src, u64 * t0, u64 * t1, int n, int key_bits, KeyFn key)
@@ -868,8 +893,6 @@ LNR_HD int chain_blocks_base(const u64 * recs, const Blk * sep, const i32 * sep_
 // The sequential ones above stay the reference statement (and serve the cord-block stage); these give the same
 // results with the inner loops spread over the lanes: a read with several hundred blocks spent milliseconds in the
 // blocks x cuts scan on one lane and set the kernel's tail.
-struct CutKeyY { const u64 * hits; LNR_HD u64 operator()(u64 c) const { return cord_y(hits[c & ~(1ULL << 62)]); } };
-struct BlkKeySecond { LNR_HD u64 operator()(u64 v) const { return v >> 32; } };   // Blk viewed as u64: first low, second high
 LNR_PIPE int prefilter_chains2_w(const Warp & w, u32 * hist256, u64 * hits, int n_hits, Blk * sep, int nb, Blk * tmp, int cap, u64 * cuts,
                                  u64 * strs, u64 * s0, u64 * s1)
 {
@@ -883,8 +906,7 @@ LNR_PIPE int prefilter_chains2_w(const Warp & w, u32 * hist256, u64 * hits, int 
     wsync(w);
     // std::sort(cuts, by y of the hit) -- ties are common (block ends share y with the next block's start)
     {
-        CutKeyY ky = {hits};
-        u64 * r = gnu_sort_w(w, hist256, cuts, s0, s1, 2 * nb, 20, ky);
+        u64 * r = gnu_sort_w(w, hist256, cuts, s0, s1, 2 * nb, 20, sort_key(2, hits));
         if (r != cuts) { for (int i = w.lane; i < 2 * nb; i += w.nl) cuts[i] = r[i]; wsync(w); }
     }
     // per block: y of its current start (0xffffffff once it is used up) and y of its last hit, so that the cuts x blocks
@@ -940,7 +962,7 @@ LNR_PIPE int prefilter_chains2_w(const Warp & w, u32 * hist256, u64 * hits, int 
         wsync(w);
     }
     {
-        u64 * r = gnu_sort_w(w, hist256, (u64 *)tmp, s0, s1, nt, 32, BlkKeySecond());
+        u64 * r = gnu_sort_w(w, hist256, (u64 *)tmp, s0, s1, nt, 32, sort_key(3));
         for (int i = w.lane; i < nt; i += w.nl) ((u64 *)sep)[i] = r[i];
         wsync(w);
     }
@@ -998,11 +1020,6 @@ LNR_PIPE void best_chains2_hits_w(const Warp & w, const u64 * recs, const Blk * 
 }
 
 // chainBlocksBase for the hit blocks (mode 0, sorted by x); the number of chains is returned on every lane
-struct BlkKeyXDesc
-{
-    const u64 * recs; const Blk * sep;
-    LNR_HD u64 operator()(u64 i) const { return ((1ULL << 40) - 1) - cord_x40(recs[sep[(u32)i].first]); }
-};
 LNR_PIPE int chain_blocks_hits_w(const Warp & w, u32 * hist256, const u64 * recs, const Blk * sep, const i32 * sep_score, int nb, BlockScratch & s,
                                  u64 * s0, u64 * s1, u64 * s2)
 {
@@ -1010,8 +1027,7 @@ LNR_PIPE int chain_blocks_hits_w(const Warp & w, u32 * hist256, const u64 * recs
     for (int i = w.lane; i < nb; i += w.nl) s2[i] = (u64)i;
     wsync(w);
     {
-        BlkKeyXDesc kx = {recs, sep};
-        u64 * r = gnu_sort_w(w, hist256, s2, s0, s1, nb, 40, kx);
+        u64 * r = gnu_sort_w(w, hist256, s2, s0, s1, nb, 40, sort_key(4, recs, sep));
         for (int i = w.lane; i < nb; i += w.nl) s.ptr[i] = (u32)r[i];
         wsync(w);
     }
@@ -1578,7 +1594,7 @@ LNR_PIPE int hits_sec_sort(const Warp & w, Arena & ar, u32 * hist256, u32 * bins
     u64 * C = arena_alloc<u64>(ar, (u64)m);
     Blk * ranges = arena_alloc<Blk>(ar, (u64)m / 2 + 2);
     if (ar.failed) return 1;
-    u64 * sorted = radix_sort(w, hist256, S, O, C, m, 62, KeyAsc());
+    u64 * sorted = radix_sort(w, hist256, S, O, C, m, 62, sort_key(0));
     LNR_LAP(cnt, 1, tl);
     int nr = 0;
     if (w.lane == 0) nr = filter_anchor_runs(sorted, m, ranges);
@@ -1603,14 +1619,14 @@ LNR_PIPE int hits_sec_sort(const Warp & w, Arena & ar, u32 * hist256, u32 * bins
     u64 * T0 = (F == A) ? B : A;             // free buffers: the two of {A,B,C} that are not F
     u64 * T1 = (F == C) ? B : C;
     if (T1 == T0) T1 = C;
-    X = radix_sort(w, hist256, F, T0, T1, n2, 30, KeyXDesc());
+    X = radix_sort(w, hist256, F, T0, T1, n2, 30, sort_key(1));
     int tie = 0;
     for (int i = 1 + w.lane; i < n2; i += w.nl) tie |= anchor_x(X[i]) == anchor_x(X[i - 1]);
     tie = wballot(w, tie != 0) != 0;
     if (tie)
     {
         // comparator ties: only libstdc++'s own permutation is right
-        X = gnu_sort_w(w, hist256, F, T0, T1, n2, 30, KeyXDesc());
+        X = gnu_sort_w(w, hist256, F, T0, T1, n2, 30, sort_key(1));
         cnt.t[11]++;
     }
     LNR_LAP(cnt, 3, tl);
