@@ -6,9 +6,13 @@
 
 #ifdef __CUDACC__
 #define LNR_HD __host__ __device__ __forceinline__
+// long, rarely executed bodies (introsort fallbacks, tracebacks): one out-of-line copy per instantiation instead of one
+// per call site -- the warp-per-read kernels are bound by instruction fetch before anything else
+#define LNR_HD_COLD __host__ __device__ __noinline__
 #define LNR_DEV __device__
 #else
 #define LNR_HD inline
+#define LNR_HD_COLD inline
 #define LNR_DEV
 #endif
 

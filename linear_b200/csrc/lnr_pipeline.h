@@ -624,7 +624,7 @@ LNR_PIPE void best_chains(const Warp & w, const u64 * a, ChainRec * ch, int n, i
 // chain_off[c] .. chain_off[c+1] delimit chain c. Sequential. Returns the number of chains.
 // ----------------------------------------------------------------------------------------------------
 template <class E>
-LNR_HD int traceback0(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
+LNR_HD_COLD int traceback0(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
                       int min_len, int abort_score, int bestn, float stop_ratio)
 {   // traceBackChains0 :122
     const int delete_score = -1000;
@@ -679,7 +679,7 @@ LNR_HD int traceback0(const E * el, ChainRec * rec, int n, E * out_el, i32 * out
 }
 
 template <class E>
-LNR_HD int traceback1(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
+LNR_HD_COLD int traceback1(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
                       int min_len, int abort_score, int bestn, float stop_ratio)
 {   // traceBackChains1 :214 -- called only when there are <= 50 trees
     int root[64], lscore[64], llen[64], lidx[64];

@@ -78,7 +78,7 @@ LNR_HD void gs_adjust_heap(T * a, int first, int hole, int len, T value, Less le
 }
 
 template <class T, class Less>
-LNR_HD void gs_heap_sort(T * a, int first, int last, Less less)   // __partial_sort(first, last, last)
+LNR_HD_COLD void gs_heap_sort(T * a, int first, int last, Less less)   // __partial_sort(first, last, last)
 {
     int len = last - first;
     if (len >= 2)
@@ -133,7 +133,7 @@ LNR_HD int gs_unguarded_partition(T * a, int first, int last, int pivot, Less le
 
 // std::sort(a, a + n, less)
 template <class T, class Less>
-LNR_HD void gnu_sort(T * a, int n, Less less)
+LNR_HD_COLD void gnu_sort(T * a, int n, Less less)
 {
     if (n <= 0) return;
     int lg = 0;
