@@ -8,11 +8,12 @@
 //   FASTQ: records of exactly four lines (id, sequence, '+', quality).
 // The text must start with '>' or '@'.
 //
-// Passes (all bandwidth-bound, the text is read four times):
-//   k_ing_count_nl     thread = 16 bytes: newlines per thread                       -> scan -> line starts
-//   k_ing_line_starts  thread = 16 bytes: position after every newline
-//   k_ing_line_info    warp = one line : header flag, bytes kept                    -> scans -> output offsets, record ids
-//   k_ing_write        warp = one line : ordinals (ballot compaction inside the line) / offset + id span of a record
+// Passes (all bandwidth-bound; every thread owns 16 consecutive bytes of the text, which is read four times):
+//   k_ing_count_nl     newlines per thread                                          -> scan -> line index of every thread
+//   k_ing_line_starts  position after every newline (the line table)
+//   k_ing_chunk_count  sequence bytes kept and records opened per thread            -> scans -> output offsets, record ids
+//   k_ing_chunk_write  ordinals at the thread's output offset; offset + id span of every record it opens
+// (A first version ran one warp per LINE for the last two passes: 80-column FASTA left most lanes idle, 1.06 of 1.4 ms.)
 #pragma once
 
 struct lnr_reads
@@ -68,59 +69,71 @@ __global__ void __launch_bounds__(256) k_ing_line_starts(const u8 * __restrict__
     for (u64 i = b; i < e; i++)
         if (text[i] == '\n') ls[k++] = i + 1;
 }
-// kept[l] = sequence bytes line l contributes; hdr[l] = 1 when it opens a record
-__global__ void __launch_bounds__(256) k_ing_line_info(const u8 * __restrict__ text, const u64 * __restrict__ ls, u64 n_lines, int format,
-                                                       u32 * __restrict__ kept, u32 * __restrict__ hdr)
+// what a thread needs to know about the line its current byte is in
+struct IngLine { bool hdr, seq; };
+__device__ __forceinline__ IngLine ing_line(const u8 * __restrict__ text, const u64 * __restrict__ ls, u64 l, int format)
 {
-    u64 l = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned lane = threadIdx.x & 31;
-    if (l >= n_lines) return;
+    IngLine r;
     const u64 b = ls[l], e = ls[l + 1] - 1;   // [b, e): the line without its newline
-    bool is_hdr, is_seq;
-    if (format == 1) { is_hdr = e > b && text[b] == '>'; is_seq = !is_hdr; }
-    else { is_hdr = (l & 3) == 0 && e > b; is_seq = (l & 3) == 1; }
-    u32 c = 0;
-    if (is_seq)
-        for (u64 i = b + lane; i < e; i += 32) { u8 ch = text[i]; c += (ch != '\r' && (format == 2 || ch != ' ')) ? 1u : 0u; }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0) { kept[l] = c; hdr[l] = is_hdr ? 1u : 0u; }
+    if (format == 1) { r.hdr = e > b && text[b] == '>'; r.seq = !r.hdr; }
+    else { r.hdr = (l & 3) == 0 && e > b; r.seq = (l & 3) == 1; }
+    return r;
 }
-__global__ void __launch_bounds__(256) k_ing_write(const u8 * __restrict__ text, const u64 * __restrict__ ls, u64 n_lines, int format,
-                                                   const u64 * __restrict__ kept_off, const u64 * __restrict__ rec_before,
-                                                   const u32 * __restrict__ hdr, int cut_id_at_space, u8 * __restrict__ bases,
-                                                   u64 * __restrict__ read_off, u64 * __restrict__ id_off, u32 * __restrict__ id_len)
+__device__ __forceinline__ bool ing_keep(u8 ch, int format) { return ch != '\r' && (format == 2 || ch != ' '); }   // the FASTQ reader drops only '\r'
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_ing_chunk(const u8 * __restrict__ text, u64 n, const u64 * __restrict__ ls, const u64 * __restrict__ line_of,
+                                                   int format, u64 n_threads, u32 * __restrict__ kept, u32 * __restrict__ hdrs,
+                                                   const u64 * __restrict__ kept_off, const u64 * __restrict__ rec_off, int cut_id_at_space,
+                                                   u8 * __restrict__ bases, u64 * __restrict__ read_off, u64 * __restrict__ id_off, u32 * __restrict__ id_len)
 {
-    u64 l = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned lane = threadIdx.x & 31;
-    if (l >= n_lines) return;
-    const u64 b = ls[l], e = ls[l + 1] - 1;
-    if (hdr[l])
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    const u64 b = t * 16, e = min(b + 16, n);
+    u8 ch[16];
+    if (e - b == 16 && (((uintptr_t)(text + b)) & 15) == 0)
     {
-        const u64 r = rec_before[l];
-        u64 ib = b + 1, ie = e;
-        if (ie > ib && text[ie - 1] == '\r') ie--;
-        if (cut_id_at_space)
+        uint4 v = __ldg((const uint4 *)(text + b));
+        u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; i++) ch[i] = (u8)(w[i >> 2] >> (8 * (i & 3)));
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 16; i++) ch[i] = b + i < e ? text[b + i] : (u8)'\n';
+    }
+    u64 l = line_of[t];                  // line of the thread's first byte = newlines before it
+    IngLine st = ing_line(text, ls, l, format);
+    u32 c = 0, h = 0;
+    u64 pos = WRITE ? kept_off[t] : 0, rec = WRITE ? rec_off[t] : 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+    {
+        const u64 p = b + i;
+        if (p >= e) break;
+        if (st.hdr && p == ls[l])
         {
-            u64 first = ie;   // first ' ' of the id
-            for (u64 i = ib + lane; i < ie; i += 32) if (text[i] == ' ') { first = i; break; }
-            for (int o = 16; o; o >>= 1) { u64 t2 = __shfl_xor_sync(0xffffffffu, first, o); first = min(first, t2); }
-            ie = first;
+            // this thread owns the first byte of a header line: it opens record `rec`
+            if (WRITE)
+            {
+                u64 ib = p + 1, ie = ls[l + 1] - 1;
+                if (ie > ib && text[ie - 1] == '\r') ie--;
+                if (cut_id_at_space)
+                    for (u64 k = ib; k < ie; k++) if (text[k] == ' ') { ie = k; break; }
+                read_off[rec] = pos; id_off[rec] = ib; id_len[rec] = (u32)(ie - ib);
+                rec++;
+            }
+            h++;
         }
-        if (lane == 0) { read_off[r] = kept_off[l]; id_off[r] = ib; id_len[r] = (u32)(ie - ib); }
-        return;
+        if (ch[i] == '\n') { l++; st = ing_line(text, ls, l, format); }
+        else if (st.seq && ing_keep(ch[i], format))
+        {
+            if (WRITE) bases[pos++] = (u8)ing_ord5(ch[i]);
+            c++;
+        }
     }
-    const bool is_seq = format == 1 ? true : (l & 3) == 1;
-    if (!is_seq) return;
-    u64 pos = kept_off[l];
-    for (u64 c0 = b; c0 < e; c0 += 32)
-    {
-        u64 i = c0 + lane;
-        u8 ch = i < e ? text[i] : (u8)'\r';
-        bool keep = ch != '\r' && (format == 2 || ch != ' ');   // the FASTQ reader drops only the carriage return
-        u32 m = __ballot_sync(0xffffffffu, keep);
-        if (keep) bases[pos + __popc(m & ((1u << lane) - 1))] = (u8)ing_ord5(ch);
-        pos += __popc(m);
-    }
+    if (!WRITE) { kept[t] = c; hdrs[t] = h; }
 }
 
 static int reads_parse_device(lnr_ctx * ctx, const u8 * d_text, u64 n, int first_byte, int cut_id_at_space, lnr_reads ** out)
@@ -156,18 +169,19 @@ static int reads_parse_device(lnr_ctx * ctx, const u8 * d_text, u64 n, int first
         LaunchScope ls(ctx, "k_ing_line_starts");
         k_ing_line_starts<<<(u32)((nt + 255) / 256), 256, 0, ctx->stream>>>(d_text, n, d_coff, d_ls, nt, n_lines);
     }
-    CKR(ctx->ing[4].reserve((n_lines + STILE + 1) * sizeof(u32)));
-    CKR(ctx->ing[5].reserve((n_lines + STILE + 1) * sizeof(u32)));
-    CKR(ctx->ing[6].reserve((n_lines + STILE + 1) * sizeof(u64)));
-    CKR(ctx->ing[7].reserve((n_lines + STILE + 1) * sizeof(u64)));
+    CKR(ctx->ing[4].reserve((nt + STILE + 1) * sizeof(u32)));
+    CKR(ctx->ing[5].reserve((nt + STILE + 1) * sizeof(u32)));
+    CKR(ctx->ing[6].reserve((nt + STILE + 1) * sizeof(u64)));
+    CKR(ctx->ing[7].reserve((nt + STILE + 1) * sizeof(u64)));
     d_kept = ctx->ing[4].as<u32>(); d_hdr = ctx->ing[5].as<u32>(); d_koff = ctx->ing[6].as<u64>(); d_rb = ctx->ing[7].as<u64>();
-    const u32 line_ctas = (u32)((n_lines * 32 + 255) / 256);
+    const u32 chunk_ctas = (u32)((nt + 255) / 256);
     {
-        LaunchScope ls(ctx, "k_ing_line_info");
-        k_ing_line_info<<<line_ctas, 256, 0, ctx->stream>>>(d_text, d_ls, n_lines, format, d_kept, d_hdr);
+        LaunchScope ls(ctx, "k_ing_chunk_count");
+        k_ing_chunk<false><<<chunk_ctas, 256, 0, ctx->stream>>>(d_text, n, d_ls, d_coff, format, nt, d_kept, d_hdr, nullptr, nullptr, 0, nullptr, nullptr,
+                                                                nullptr, nullptr);
     }
-    rc = device_scan<u64>(ctx, d_kept, n_lines, 0, d_koff, d_tot + 1, "k_ing_scan_kept");
-    if (!rc) rc = device_scan<u64>(ctx, d_hdr, n_lines, 0, d_rb, d_tot + 2, "k_ing_scan_hdr");
+    rc = device_scan<u64>(ctx, d_kept, nt, 0, d_koff, d_tot + 1, "k_ing_scan_kept");
+    if (!rc) rc = device_scan<u64>(ctx, d_hdr, nt, 0, d_rb, d_tot + 2, "k_ing_scan_hdr");
     if (rc) { cleanup(); lnr_reads_destroy(R); return rc; }
     u64 tot[2] = {0, 0};
     CKR(cudaMemcpyAsync(tot, d_tot + 1, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
@@ -197,9 +211,9 @@ static int reads_parse_device(lnr_ctx * ctx, const u8 * d_text, u64 n, int first
     }
     CKR(cudaMemsetAsync(R->d_bases + R->total_bases, 0, 256, ctx->stream));
     {
-        LaunchScope ls(ctx, "k_ing_write");
-        k_ing_write<<<line_ctas, 256, 0, ctx->stream>>>(d_text, d_ls, n_lines, format, d_koff, d_rb, d_hdr, cut_id_at_space, R->d_bases, R->d_off,
-                                                        R->d_id_off, R->d_id_len);
+        LaunchScope ls(ctx, "k_ing_chunk_write");
+        k_ing_chunk<true><<<chunk_ctas, 256, 0, ctx->stream>>>(d_text, n, d_ls, d_coff, format, nt, nullptr, nullptr, d_koff, d_rb, cut_id_at_space,
+                                                               R->d_bases, R->d_off, R->d_id_off, R->d_id_len);
     }
     CKR(cudaMemcpyAsync(R->d_off + R->n_reads, &R->total_bases, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     CKR(cudaGetLastError());
