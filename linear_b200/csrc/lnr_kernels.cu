@@ -7,18 +7,23 @@
 //   features  F96 (3 x int32) per 16 bases; per contig for the genome, per (read, strand) for a batch
 //   batch     read bases back to back, anchors / scratch per read, cords per read at host-computed offsets
 //
-// Kernels (all HBM / latency bound integer work, no tensor-core shaped math on this path)
-//   k_feat_genome / k_feat_reads      2-mer/48 features: one thread per 16-base cell, 3-cell sums through smem
+//   lookup    hsy: the Y byte of every hs record; dirx: per bucket one 32-B sector (start, size, first 24 Y keys)
+//
+// Kernels (all HBM / issue / latency bound integer work, no tensor-core shaped math on this path)
+//   k_feat_genome / k_feat_reads      2-mer/48 features: one thread per 16-base cell, 3-cell sums through smem; reads:
+//                                     persistent CTAs, 2-bit packed cells, table of 2-mer increments per 4-base window
 //   k_idx_prep, k_idx_pass<FILL>      DIndex samples: genome tile staged in smem, one thread per 4 samples,
 //                                     emit rule by block max-scan, histogram / scatter with global atomics
 //   k_scan_*                          device-wide exclusive scan (reduce / spine / apply), fused bucket omission
-//   k_idx_sort_buckets                ascending order inside each bucket
-//   k_seed_prep / k_seed_count / k_seed_fill   per-read seeding, one thread per sample, exact-size output
-//   k_map_hits                        warp per seeding task (lnr_pipeline.h: filter, sorts, chaining DP, traceback, hit blocks),
-//                                     persistent warps + atomic queue, longest reads first
-//   k_map_extend                      window extension, one THREAD per read (32 reads in lockstep per warp)
+//   k_idx_sort_buckets, k_idx_split_y, k_idx_dirx   bucket order, Y byte array, lookup sectors
+//   k_seed_prep / k_seed_count / k_seed_fill / k_seed_stats   per-read seeding, one thread per sample, exact-size output
+//   k_hits_sort / k_hits_chain / k_hits_blocks      the hit stage, one kernel per section (lnr_pipeline.h hits_sec_*):
+//                                     persistent warp per read + atomic queue, heaviest tasks first
+//   k_map_hits                        the same three sections in one kernel (re-map and big-arena passes)
+//   k_map_extend                      window extension, one warp per read on a regular grid
 //   k_map_finish                      warp per read: clean / gaps / re-map decision / cord-block chaining
 //   k_gather_cords                    per-read cords -> caller's concatenated layout
+//   lnr_ingest.cuh                    FASTA / FASTQ text -> ordinals, offsets, id spans (16 bytes per thread)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -1080,7 +1085,7 @@ __global__ void __launch_bounds__(1024) k_order_by_key(const u32 * __restrict__ 
 #endif
 __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, int remap_pass, int big_pass)
 {
-    // big_pass: second, tiny launch over the tasks that exhausted the 2 MB per-warp arena (reads with very many
+    // big_pass: second, tiny launch over the tasks whose scratch bound exceeds the per-warp arena (reads with very many
     // anchors), a few warps with a large arena each
     __shared__ u32 s_hist[4][kWarpSmemWords];
     for (int i = threadIdx.x; i < 4 * kWarpSmemWords; i += blockDim.x) (&s_hist[0][0])[i] = 0;
