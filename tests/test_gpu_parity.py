@@ -269,3 +269,32 @@ def test_warp_sort_reproduces_std_sort_tie_order(lb, ctx):
         emu.emu_std_sort_hi(want.ctypes.data_as(C.POINTER(C.c_uint64)), len(want))
         got = lb.selftest_sort(ctx, a)
         assert np.array_equal(got, want), (len(keys), int(keys.max()))
+
+
+def test_concurrent_contexts_share_index_and_features(lb, ctx):
+    """p_calRecords is called from -t host threads: several contexts (own stream + workspace each) map at the same time
+    against ONE genome / feature / index object; every thread must get exactly the single-threaded result."""
+    import threading
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    want_c, want_o = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset)
+    ctxs = [lb.Context(0) for _ in range(4)]
+    out, errs = [None] * 4, []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                out[k] = lb.apx_map_batch(ctxs[k], index, feats, bases, offs, preset=preset)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for k in range(4):
+        assert np.array_equal(out[k][1], want_o) and np.array_equal(out[k][0], want_c), k
