@@ -1282,7 +1282,13 @@ __global__ void __launch_bounds__(128, 8) k_hits_sort(MapArgs a)
     stage_end(a, c);
 }
 
-__global__ void __launch_bounds__(128, 6) k_hits_chain(MapArgs a)
+#ifndef LNR_CHAIN_MIN_CTAS
+#define LNR_CHAIN_MIN_CTAS 6
+#endif
+#ifndef LNR_BLOCKS_MIN_CTAS
+#define LNR_BLOCKS_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(128, LNR_CHAIN_MIN_CTAS) k_hits_chain(MapArgs a)
 {
     StageCommon c;
     stage_begin(a, c);
@@ -1316,7 +1322,7 @@ __global__ void __launch_bounds__(128, 6) k_hits_chain(MapArgs a)
     stage_end(a, c);
 }
 
-__global__ void __launch_bounds__(128, 6) k_hits_blocks(MapArgs a)
+__global__ void __launch_bounds__(128, LNR_BLOCKS_MIN_CTAS) k_hits_blocks(MapArgs a)
 {
     __shared__ u32 s_hist[4][256];
     StageCommon c;
