@@ -34,7 +34,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 GENOME_BASES = int(os.environ.get("LNR_BENCH_GENOME", 3_100_000_000))
 N_CONTIGS = 24
 THREADS_SEM = 16          # the reference's code default -t (base.cpp:26-54); semantic for the index
-METRIC = "reads/sec apx-map+chain (3.1-Gbase synth); index build sec"
+METRIC = "reads/sec apx-map+chain at 1/2/4/8 B200 (3.1-Gbase synth); index build sec"   # BASELINE.json's metric, verbatim
+try:
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+except Exception:  # noqa: BLE001
+    pass
 
 
 def parse():
@@ -271,8 +275,9 @@ def main():
     import torch
     lens = contig_lengths()
     cores = os.cpu_count() or 1
-    config = {"workload": f"{GENOME_BASES / 1e9:.2f}-Gbase synthetic genome ({N_CONTIGS} contigs, planted repeats) + ONT-like reads "
-                          f"(lognormal mean 20 kb, 10% error, 20% planted SV), {args.batch_reads} reads per step per GPU",
+    config = {"workload": f"BASELINE configs[2] (apx map + chaining; index build = configs[1]): {GENOME_BASES / 1e9:.2f}-Gbase synthetic genome "
+                          f"({N_CONTIGS} contigs, planted repeats) + simulated ONT-like reads (lognormal mean 20 kb, 10% error, 20% planted "
+                          f"ins/del/inv/dup SVs), one step = one batch of {args.batch_reads} reads per GPU",
               "index": "DIndex (-i 1)", "features": "2-mer/48 (-f 2)", "threads_sem": THREADS_SEM, "preset": 1,
               "batch_reads_per_gpu": args.batch_reads, "parallelism": f"reads sharded x{world} (no collective); index built by minimizer range x{world} + one NCCL all-gather",
               "l2_policy": "inputs larger than L2 (batch bases + index >> 126 MB)",
