@@ -33,6 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 GENOME_BASES = int(os.environ.get("LNR_BENCH_GENOME", 3_100_000_000))
 N_CONTIGS = 24
+READ_PROFILE = os.environ.get("LNR_BENCH_PROFILE", "ont")   # "hifi": 15 kb reads at 1 % error, a side measurement
 THREADS_SEM = 16          # the reference's code default -t (base.cpp:26-54); semantic for the index
 METRIC = "reads/sec apx-map+chain at 1/2/4/8 B200 (3.1-Gbase synth); index build sec"   # BASELINE.json's metric, verbatim
 try:
@@ -282,6 +283,9 @@ def main():
               "batch_reads_per_gpu": args.batch_reads, "parallelism": f"reads sharded x{world} (no collective); index built by minimizer range x{world} + one NCCL all-gather",
               "l2_policy": "inputs larger than L2 (batch bases + index >> 126 MB)",
               "host_threads": args.streams}
+    if READ_PROFILE == "hifi":
+        config["workload"] = (f"side measurement, not the headline: {GENOME_BASES / 1e9:.2f}-Gbase synthetic genome + HiFi-like reads (mean 15 kb, "
+                              f"1% error, no SVs), one step = one batch of {args.batch_reads} reads per GPU")
 
     if args.impl == "reference":
         if rank != 0:
@@ -408,7 +412,10 @@ def main():
         t_index_e2e = time.time() - t0
         ctx.reset_kernel_times()
     # ---- reads of this rank
-    bases_t, offs = gen_reads(torch, dev, genome, lens, args.batch_reads, seed=1000 + rank)
+    if READ_PROFILE == "hifi":   # side measurement (BASELINE configs[0]/[3] flavour), not the headline workload
+        bases_t, offs = gen_reads(torch, dev, genome, lens, args.batch_reads, seed=1000 + rank, mean=15000, sigma=0.2, err=0.01, mix=(1, 1, 1), sv_frac=0.0)
+    else:
+        bases_t, offs = gen_reads(torch, dev, genome, lens, args.batch_reads, seed=1000 + rank)
     del genome
     torch.cuda.empty_cache()
     n_reads = len(offs) - 1
