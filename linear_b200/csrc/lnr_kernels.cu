@@ -2167,7 +2167,8 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     CK(ctx->sample_cnt.reserve((size_t)(n_samples + STILE + 1) * sizeof(u32)));
     CK(aoff_buf.reserve((size_t)(n_samples + STILE + 1) * sizeof(u64)));
     CK(ctx->misc.reserve(1024));
-    const u32 mask_cap = (u32)std::min<u64>(2 * n_samples + (1u << 20), 0xfffffff0ull);
+    u32 mask_cap = (u32)std::min<u64>(2 * n_samples + (1u << 20), 0xfffffff0ull);
+    if (const char * e = getenv("LNR_MASK_WORDS")) { long v = atol(e); if (v >= (long)kMaskPools && (u64)v < mask_cap) mask_cap = (u32)v; }   // tests: force the re-scan path
     CK(ctx->seed_masks.reserve((size_t)mask_cap * sizeof(u64)));
     CK(ctx->seed_mask_off.reserve((size_t)(n_samples + 1) * sizeof(u32)));
     CK(ctx->mask_ctr.reserve(kMaskPools * sizeof(unsigned int)));

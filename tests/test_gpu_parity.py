@@ -298,3 +298,17 @@ def test_concurrent_contexts_share_index_and_features(lb, ctx):
     assert not errs, errs
     for k in range(4):
         assert np.array_equal(out[k][1], want_o) and np.array_equal(out[k][0], want_c), k
+
+
+def test_exhausted_match_mask_pool_falls_back_to_rescan(lb, monkeypatch):
+    """k_seed_count records matches as bitmasks from a pooled allocator; a sample that gets no words is re-scanned by
+    k_seed_fill with the Y-key rule itself. With one word per pool nearly every sample takes that path."""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    monkeypatch.setenv("LNR_MASK_WORDS", "256")
+    c = lb.Context(0)
+    gen = lb.Genome(c, g)
+    feats = lb.create_features(c, gen, 2, T)
+    index = lb.create_index(c, gen, 1, T)
+    cords, coff = lb.apx_map_batch(c, index, feats, bases, offs, preset=preset)
+    oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
