@@ -158,11 +158,35 @@ def gen_reads(torch, dev, genome, lens, n_reads, seed, mean=20000, sigma=0.5, er
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    def __init__(self, gpu_index):
+    """SM clock and throttle reasons of one GPU while the timed regions run. NVML (the library nvidia-smi reads from) when
+    it is importable -- forking nvidia-smi five times a second from a process with GBs of pinned memory, on every rank,
+    perturbs what it observes -- else nvidia-smi itself."""
+
+    def __init__(self, gpu_index, pci_bus_id=None):
         super().__init__(daemon=True)
-        self.gpu, self.stop_flag, self.rows = gpu_index, False, []
+        self.gpu, self.pci, self.stop_flag, self.rows, self.source = gpu_index, pci_bus_id, False, [], "nvidia-smi"
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByPciBusId(self.pci.encode() if isinstance(self.pci, str) else self.pci) if self.pci else \
+            nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (0x8, 0x40, 0x20, 0x4)   # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        self.source = "nvml"
+        while not self.stop_flag:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            time.sleep(0.05)
 
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:  # noqa: BLE001
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
@@ -182,7 +206,7 @@ class ClockSampler(threading.Thread):
         mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 def cpu_reference(contigs_host, bases, offs, n_sample, cores):
@@ -485,8 +509,15 @@ def main():
     # ---- timed region: device-resident inputs
     for c in ctxs:
         c.set_profiling(False)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    pci = None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        pci = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:  # noqa: BLE001
+        pass
+    sampler = ClockSampler(local_rank, pci)
+    if rank == 0:          # one sampler per job: the line reports rank 0's GPU
+        sampler.start()
     run_steps("step_device", args.warmup * n_str)
     for c in ctxs:
         c.set_profiling(True)
@@ -510,7 +541,8 @@ def main():
     c_host = streams[0].last[0]
     d2h = int(len(c_host) * 8 + (n_reads + 1) * 8)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     # every rank leaves the process group at the same point; rank 0 alone goes on to the report
     if world > 1:
