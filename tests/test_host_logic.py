@@ -94,3 +94,23 @@ def test_warp_cooperative_gnu_sort_matches_std_sort_with_ties():
         for arr in (np.arange(n), np.arange(n)[::-1], np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]])):
             a = (arr.astype(np.uint64) // np.uint64(3) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
             assert lib.emu_gnu_sort_w_check(a.ctypes.data_as(C.POINTER(C.c_uint64)), n) == 0
+
+
+@pytest.mark.parametrize("seed", [0, 3, 5, 9, 12])
+def test_host_emulation_on_random_cases(seed):
+    """the randomised cases of tests/test_gpu_fuzz.py (N runs, repeat density, -t, preset all vary) through the product
+    headers on the host: the same sweep the GPU runs, checkable without one"""
+    from test_gpu_fuzz import make_fuzz_case
+    g, bases, offs, T, preset = make_fuzz_case(seed)
+    O = Oracle(g, threads=T, preset=preset)
+    E = HostEmu(g, threads=T, preset=preset)
+    d0, h0 = O.dindex()
+    d1, h1 = E.dindex()
+    assert np.array_equal(d0, d1) and np.array_equal(h0, h1)
+    for r in range(0, len(offs) - 1, 3):
+        read = bases[int(offs[r]):int(offs[r + 1])]
+        if len(read) <= 200:
+            continue
+        assert np.array_equal(O.stage(read, 1), E.stage(read, 1)), (seed, "anchors", r)
+        assert np.array_equal(O.stage(read, 3), E.stage(read, 3)), (seed, "hits", r)
+        assert np.array_equal(O.cords(read), E.cords(read)), (seed, "cords", r)
