@@ -35,6 +35,9 @@ GENOME_BASES = int(os.environ.get("LNR_BENCH_GENOME", 3_100_000_000))
 N_CONTIGS = 24
 READ_PROFILE = os.environ.get("LNR_BENCH_PROFILE", "ont")   # "hifi": 15 kb reads at 1 % error, a side measurement
 THREADS_SEM = 16          # the reference's code default -t (base.cpp:26-54); semantic for the index
+SEED_COUNT_WRITE = 16     # bytes k_seed_count writes per sample: info 8 + count 4 + list offset 4
+SEED_FILL_READ = 24       # bytes k_seed_fill reads per sample: info 8 + count 4 + list offset 4 + anchor offset 8
+TRAFFIC_FILE = "r1_ncu_traffic.json"   # dram bytes per read of each kernel from the last `ncu --set full` capture
 METRIC = "reads/sec apx-map+chain at 1/2/4/8 B200 (3.1-Gbase synth); index build sec"   # BASELINE.json's metric, verbatim
 try:
     METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
@@ -209,9 +212,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
-def cpu_reference(contigs_host, bases, offs, n_sample, cores):
+def cpu_reference(contigs_host, bases, offs, n_sample, cores, reps=1):
     """The reference's own CPU path on a bounded sample: oracle/_ref (kind 'reference') if it travelled, else the
-    oracle port. Returns dict(value reads/s, index_build_s, kind, cores, sample)."""
+    oracle port. Returns (dict(value reads/s, index_build_s, kind, cores, sample), checker, cords, cords_off): the
+    checker and its cords are what the GPU output is compared with (the `parity` object of the line)."""
     from cpu_checkers import Oracle, RefImpl, have_ref
     kind = "reference" if have_ref() else "port"
     cls = RefImpl if have_ref() else Oracle
@@ -221,13 +225,55 @@ def cpu_reference(contigs_host, bases, offs, n_sample, cores):
     n = min(n_sample, len(offs) - 1)
     sb = bases[: int(offs[n])]
     so = offs[: n + 1].copy()
+    best = None
+    for _ in range(max(reps, 1)):
+        t0 = time.time()
+        cords, coff = chk.map_batch(sb, so, map_threads=cores)
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
     t0 = time.time()
-    chk.map_batch(sb, so, map_threads=cores)
-    dt = time.time() - t0
-    return {"value": n / dt, "unit": "reads/s", "cores": cores, "kind": kind, "index_build_s": round(t_index, 2),
-            "index_threads": THREADS_SEM,
-            "sample": f"first {n} reads of the rank-0 batch ({int(so[-1])} bases) through apxMap with {cores} OpenMP threads; "
-                      f"genome features + DIndex built by the same code at -t {THREADS_SEM} in {t_index:.1f} s"}
+    chk.map_batch(sb, so, map_threads=min(4, cores))
+    dt4 = time.time() - t0
+    info = {"value": n / best, "unit": "reads/s", "cores": cores, "kind": kind, "index_build_s": round(t_index, 2),
+            "index_threads": THREADS_SEM, "value_t4": n / dt4,
+            "sample": f"first {n} reads of the rank-0 batch ({int(so[-1])} bases) through apxMap with {cores} OpenMP threads "
+                      f"(value) and with 4 (value_t4, BASELINE configs[0] says -t 4); genome features + DIndex built by the same "
+                      f"code at -t {THREADS_SEM} in {t_index:.1f} s"}
+    return info, chk, cords, coff
+
+
+def check_parity(torch, dev, chk, index, ref_cords, ref_coff, gpu_cords, gpu_coff):
+    """Bit-exact comparison of the GPU results with the reference on the bench's own 3.1-Gbase inputs: the cords of the
+    sampled reads, and the whole DIndex (dir + hs) against the arrays the reference built on the host."""
+    n = len(ref_coff) - 1
+    g_off = np.asarray(gpu_coff[: n + 1], dtype=np.uint64)
+    cords_equal = bool(np.array_equal(g_off, np.asarray(ref_coff, dtype=np.uint64)) and
+                       np.array_equal(np.asarray(gpu_cords[: int(g_off[-1])], dtype=np.uint64), np.asarray(ref_cords, dtype=np.uint64)))
+    n_diff = 0
+    if not cords_equal:
+        for r in range(n):
+            a = gpu_cords[int(g_off[r]):int(g_off[r + 1])]
+            b = ref_cords[int(ref_coff[r]):int(ref_coff[r + 1])]
+            if len(a) != len(b) or not np.array_equal(a, b):
+                n_diff += 1
+    out = {"reads": n, "cords": int(ref_coff[-1]), "cords_equal": cords_equal, "reads_differing": n_diff}
+    try:
+        rdir, rhs = chk.dindex_views()
+        d_dev, hs_dev = index.export_device(torch, dev)
+        ok = len(rhs) == hs_dev.numel() and len(rdir) == d_dev.numel()
+        if ok:
+            ok = bool(torch.equal(torch.from_numpy(rdir).to(dev), d_dev))
+        step = 1 << 26
+        hs_i64 = rhs.view(np.int64)
+        for a in range(0, len(rhs), step):
+            if not ok:
+                break
+            ok = bool(torch.equal(torch.from_numpy(hs_i64[a:a + step]).to(dev), hs_dev[a:a + step]))
+        out.update({"dindex_equal": ok, "n_hs": int(len(rhs))})
+        del d_dev, hs_dev
+    except Exception as e:  # noqa: BLE001
+        out.update({"dindex_equal": None, "dindex_error": repr(e)})
+    return out
 
 
 def measure_ingest(lb, ctx, torch, dev, bases_np, offs, n=8192, wrap=80):
@@ -324,8 +370,10 @@ def main():
         else:
             dev = torch.device("cuda", local_rank)
             genome = gen_genome(torch, dev, lens)
-            bases_t, offs = gen_reads(torch, dev, genome, lens, max(args.cpu_sample, 64), seed=1000)
-            bases = bases_t.cpu().numpy()
+            # the B200 arm's rank-0 batch, generated the same way (same seed, same size), so that the sample is a prefix of it
+            bases_t, offs = gen_reads(torch, dev, genome, lens, args.batch_reads, seed=1000)
+            keep = int(offs[min(args.cpu_sample, len(offs) - 1)])
+            bases = bases_t[:keep].cpu().numpy()
             gh = genome.cpu().numpy()
             coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
             contigs = [gh[coff[i]:coff[i + 1]] for i in range(len(lens))]
@@ -336,26 +384,31 @@ def main():
         t0 = time.time()
         chk = cls(contigs, threads=THREADS_SEM, preset=1)
         t_index = time.time() - t0
+        # one step = the whole sample (the first --cpu-sample reads of the very batch the B200 arm maps), every step the
+        # same reads -- exactly as the B200 arm re-maps one batch per step
         n = min(args.cpu_sample, len(offs) - 1)
-        per = max(n // max(args.steps + args.warmup, 1), 16)
+        so = offs[: n + 1].copy()
+        sb = bases[: int(offs[n])]
         times = []
         for s in range(args.warmup + args.steps):
-            a = (s * per) % max(n - per, 1)
-            so = (offs[a:a + per + 1] - offs[a]).astype(np.uint64)
-            sb = bases[int(offs[a]):int(offs[a + per])]
             t0 = time.time()
             chk.map_batch(sb, so, map_threads=cores)
             if s >= args.warmup:
                 times.append(time.time() - t0)
         tot = sum(times)
-        val = per * len(times) / tot
+        val = n * len(times) / tot
+        t0 = time.time()
+        chk.map_batch(sb, so, map_threads=min(4, cores))
+        val_t4 = n / (time.time() - t0)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000 * tot / len(times), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": dict(config, reads_per_step=per),
-                "index_build_s": round(t_index, 2),
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+                "index_build_s": round(t_index, 2), "reads_per_step": n, "value_t4": val_t4,
                 "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": "reference" if have_ref() else "port",
-                                 "sample": f"{per} reads per step through the reference's apxMap with {cores} OpenMP threads "
-                                           f"(index + features built at -t {THREADS_SEM} in {t_index:.1f} s)"},
+                                 "value_t4": val_t4,
+                                 "sample": f"the first {n} reads of the B200 arm's rank-0 batch ({int(so[-1])} bases), all of them every step, through "
+                                           f"the reference's apxMap with {cores} OpenMP threads (value_t4: 4 threads; index + features built "
+                                           f"at -t {THREADS_SEM} in {t_index:.1f} s)"},
                 "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
@@ -538,8 +591,23 @@ def main():
     run_steps("step_host", n_str)
     dt_e2e = max_over_ranks(run_steps("step_host", args.steps))
     e2e_value = world * n_reads * args.steps / dt_e2e
-    c_host = streams[0].last[0]
+    c_host, coff_host = streams[0].last
     d2h = int(len(c_host) * 8 + (n_reads + 1) * 8)
+    # ---- per-kernel times for the roofline: ONE host thread, so that an event pair brackets one kernel and not the other
+    # threads' kernels interleaved with it (the 4-thread numbers above stay `value` / `e2e`)
+    ctx.set_profiling(True)
+    ctx.reset_kernel_times()
+    single_steps = max(2, min(4, args.steps))
+    streams[0].step_device()
+    ctx.reset_kernel_times()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(single_steps):
+        streams[0].step_device()
+    torch.cuda.synchronize()
+    dt_single = (time.time() - t0) / single_steps
+    kt1 = ctx.kernel_times()
+    ctx.set_profiling(False)
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
@@ -550,7 +618,7 @@ def main():
         dist.destroy_process_group()
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (SURVEY 8d per-unit bytes x units of one launch)
+    # ---- roofline. Algorithmic bytes per launch, one launch = one batch; DESIGN.md section 4 states every term.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -560,49 +628,61 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     S, H, A, Hits, W, Cc = (counters[k] for k in ("S_seeds", "H_records_scanned", "A_raw_anchors", "Hits", "W_windows", "C_cords"))
     nf_bytes = 2 * 12 * (total_bases // 16)
-    alg = {  # algorithmic bytes per launch of each kernel (one launch = one batch)
-        "k_feat_reads": total_bases + nf_bytes,
-        "k_seed_count": total_bases + 8 * S + 8 * H,
-        "k_seed_fill": 8 * S + 8 * H + 8 * A,
+    alg = {
+        "k_feat_reads": total_bases + nf_bytes,            # bases in, both strands' int96 features out
+        "k_seed_count": total_bases + 32 * S + H + SEED_COUNT_WRITE * S,   # bases, one 32-B lookup sector per seed, 1-byte Y keys, per-sample records out
+        "k_seed_fill": SEED_FILL_READ * S + 8 * A + 8 * A,   # per-sample records in, matched hs records in, anchors out
         "k_hits_sort": 8 * A,
         "k_hits_chain": 24 * Hits,
         "k_hits_blocks": 24 * Hits,
         "k_map_extend": 144 * W + 8 * Cc,
         "k_map_finish": 16 * Cc,
     }
+    # the whole step: SURVEY 8(d)'s per-read sum, every term once
+    step_alg = total_bases + 8 * S + 8 * H + 8 * A + nf_bytes + 48 * Hits + 144 * W + 16 * Cc
     per_kernel = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1]} for k, v in kt.items()}
-    step_ms_kernels = sum(v[0] for v in kt.values()) / args.steps
-    dom = max(kt.items(), key=lambda kv: kv[1][0])[0] if kt else None
+    per_kernel_single = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1]} for k, v in kt1.items()}
+    step_ms_kernels = sum(v[0] for v in kt1.values()) / single_steps
+    cand = {k: v for k, v in kt1.items() if k in alg}
+    dom = max(cand.items(), key=lambda kv: kv[1][0])[0] if cand else None
     roof = None
     if dom:
-        ms = kt[dom][0] / max(kt[dom][1], 1)
-        ab = alg.get(dom, 0)
+        ms = kt1[dom][0] / max(kt1[dom][1], 1)
+        ab = alg[dom]
         ach = ab / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         traffic = None
         try:   # dram__bytes_read+write of one `ncu --set full` capture (profiles/), scaled from its 32768-read batch
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
             if dom in tj:
                 traffic = tj[dom]["dram_bytes_per_read"] * n_reads
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab, "ms_per_launch": ms,
-                "share_of_step": (kt[dom][0] / args.steps) / step_ms_kernels if step_ms_kernels else None,
-                "whole_step": {"algorithmic_bytes": sum(alg.values()),
-                               "achieved_GBps": sum(alg.values()) / (dt / args.steps) / 1e9}}
-    if roof is not None:
-        roof["per_kernel"] = {k: {"algorithmic_GBps": round(alg[k] / (kt[k][0] / max(kt[k][1], 1) * 1e-3) / 1e9, 1),
-                                  "frac": round(alg[k] / (kt[k][0] / max(kt[k][1], 1) * 1e-3) / 1e9 / peak, 4)}
-                              for k in alg if k in kt and kt[k][0] > 0}
+                "timing": f"CUDA events on the launching stream, {single_steps} steps with ONE host thread after the timed region",
+                "ms_per_launch_4_threads": kt[dom][0] / max(kt[dom][1], 1) if dom in kt else None,
+                "share_of_step": (kt1[dom][0] / single_steps) / step_ms_kernels if step_ms_kernels else None,
+                "whole_step": {"algorithmic_bytes": step_alg, "ms_per_step": 1000 * dt / args.steps,
+                               "achieved_GBps": step_alg / (dt / args.steps) / 1e9, "frac": step_alg / (dt / args.steps) / 1e9 / peak,
+                               "ms_per_step_one_thread": 1000 * dt_single},
+                "per_kernel": {k: {"ms_per_launch": round(kt1[k][0] / max(kt1[k][1], 1), 4), "algorithmic_bytes": int(alg[k]),
+                                   "algorithmic_GBps": round(alg[k] / (kt1[k][0] / max(kt1[k][1], 1) * 1e-3) / 1e9, 1),
+                                   "frac": round(alg[k] / (kt1[k][0] / max(kt1[k][1], 1) * 1e-3) / 1e9 / peak, 4)}
+                               for k in alg if k in kt1 and kt1[k][0] > 0}}
     idx_alg = GENOME_BASES + 8 * n_hs + 4 * ((1 << 26) + 1) + GENOME_BASES + 12 * (GENOME_BASES // 16)
     index_info = {"seconds": round(t_index, 4), "seconds_first_call": round(t_index_first, 4), "seconds_e2e_from_host": None if t_index_e2e is None else round(t_index_e2e, 4),
                   "n_hs": n_hs, "algorithmic_bytes": idx_alg, "achieved_GBps": idx_alg / t_index / 1e9,
                   "frac_of_hbm_peak": idx_alg / t_index / 1e9 / peak,
                   "kernels_ms": {k: round(v[0], 3) for k, v in idx_kernels.items()}}
+    if roof is not None:
+        roof["index"] = index_info     # index-build seconds live inside a key the driver keeps
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline and contigs_host is not None:
         try:
-            cpu = cpu_reference(contigs_host, bases_np, offs, args.cpu_sample, cores)
+            cpu, chk, r_cords, r_coff = cpu_reference(contigs_host, bases_np, offs, args.cpu_sample, cores)
+            parity = check_parity(torch, dev, chk, index, r_cords, r_coff, c_host, coff_host)
+            chk.close()
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
     ingest = None
@@ -617,11 +697,15 @@ def main():
             "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": total_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * dt_e2e / args.steps},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "index_build": index_info,
-            "clocks": sampler.summary(), "ingest": ingest, "kernels": per_kernel, "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "index_build": index_info,
+            "clocks": sampler.summary(), "ingest": ingest, "kernels": per_kernel, "kernels_one_thread": per_kernel_single,
+            "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
             "bases_per_step": total_bases}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if parity is not None and (parity.get("cords_equal") is False or parity.get("dindex_equal") is False):
+        sys.stderr.write("PARITY FAILURE vs the reference: %r\n" % (parity,))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

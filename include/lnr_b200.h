@@ -120,6 +120,10 @@ int lnr_apxmap_batch_device(lnr_ctx *, const lnr_index *, const lnr_feats * f2, 
 /* algorithmic-byte counters of the last batch: S seeds, H bucket records scanned, A raw anchors,
  * Hits, W window candidates evaluated, C cords */
 int lnr_last_batch_counters(lnr_ctx *, uint64_t counters[8]);
+/* fallback-path diagnostics of the last batch (tests assert that the rare paths really ran): 0 tasks taken by the big-arena
+ * hit pass, 1 reads finished by the big-arena finish pass, 2 seeding samples re-scanned because their match list did not
+ * fit the pool, 3..7 reserved */
+int lnr_last_batch_diag(lnr_ctx *, uint64_t diag[8]);
 /* profiling aid: SM cycles spent per stage of the warp-per-read pipeline in the last batch (lane 0, summed over warps):
  * 0 binning, 1 ascending sort, 2 run filter, 3 x sort, 4 chaining DP, 5 traceback, 6 hit blocks, 7 hit window filter,
  * 8 window extension, 9 clean/gaps, 10 cord block chaining, 11 reads needing the sequential tie-order sort, 12 reads */

@@ -31,7 +31,7 @@ EXPORTS = [
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
     "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch",
-    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
+    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_diag", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
     "lnr_reads_parse", "lnr_reads_parse_device", "lnr_reads_info", "lnr_reads_download", "lnr_reads_device", "lnr_reads_destroy", "lnr_apxmap_reads",
 ]
 
@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
     lib.lnr_apxmap_batch_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, vp, C.c_uint64, u64p]
     lib.lnr_last_batch_counters.argtypes = [vp, u64p]
     lib.lnr_last_batch_stage_cycles.argtypes = [vp, u64p]
+    lib.lnr_last_batch_diag.argtypes = [vp, u64p]
     lib.lnr_read_features.argtypes = [vp, u8p, C.c_uint64, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.lnr_selftest_sort.argtypes = [vp, u64p, C.c_uint32]
     lib.lnr_reads_parse.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(vp)]
@@ -145,6 +146,11 @@ class Context:
         c = (C.c_uint64 * 8)()
         self.check(self.lib.lnr_last_batch_counters(self.h, c))
         return dict(zip(COUNTER_NAMES, [int(v) for v in c]))
+
+    def diag(self):
+        c = (C.c_uint64 * 8)()
+        self.check(self.lib.lnr_last_batch_diag(self.h, c))
+        return {"hits_big_tasks": int(c[0]), "finish_big_reads": int(c[1]), "seed_rescans": int(c[2])}
 
     def stage_cycles(self):
         c = (C.c_uint64 * 16)()

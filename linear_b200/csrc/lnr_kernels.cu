@@ -111,6 +111,7 @@ struct lnr_ctx
         cords, cords_base, ncords, slots, bins, arena, tasks2, misc, out_cords, out_off, dbg_hits, dbg_hoff, dbg_nhits,
         dbg_c1, dbg_nc1, read_meta;
     uint64_t counters[8] = {0};
+    uint64_t diag[8] = {0};
     uint64_t stage_cycles[16] = {0};
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read
                                                    u64 n_samples, const u64 * __restrict__ hs, const u64 * __restrict__ info,
                                                    const u64 * __restrict__ aoff, u64 * __restrict__ anchors,
                                                    const u32 * __restrict__ count, const u64 * __restrict__ masks,
-                                                   const u32 * __restrict__ mask_off)
+                                                   const u32 * __restrict__ mask_off, unsigned long long * counters)
 {
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_samples) return;
@@ -933,11 +934,14 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read
         }
     }
     else
+    {
+        atomicAdd(&counters[18], 1ULL);   // diagnostics: samples re-scanned because the mask pool was exhausted
         for (u32 i = 0; i < nrec; i++)
         {
             u64 h = __ldg(hs + b + i);
             if (ykey_match((u32)(h & kMaskY), Y)) *out++ = val2anchor(h, k, L, strand);
         }
+    }
 }
 
 #include "lnr_hindex.cuh"
@@ -1110,6 +1114,7 @@ __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, 
         if (q >= n_units) break;
         if (want_rec) { g_task = globaltimer_ns(); n_done++; }
         u32 ti = big_pass ? a.big_list[q] : (remap_pass ? q : a.order[q]);   // primary: heaviest reads first
+        if (big_pass && w.lane == 0) atomicAdd(&a.counters[16], 1ULL);       // diagnostics: tasks taken by the big-arena pass
         const SeedTask t = a.tasks[ti];
         u32 r = t.read;
         u64 L = a.read_off[r + 1] - a.read_off[r];
@@ -1437,6 +1442,7 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= n_units) break;
         u32 r = big_pass ? a.big_list[q] : read_list[q];
+        if (big_pass && w.lane == 0) atomicAdd(&a.counters[17], 1ULL);       // diagnostics: reads finished by the big-arena pass
         u64 L = a.read_off[r + 1] - a.read_off[r];
         ReadSlot slot = a.slots[r];
         if (L <= (u64)kMinReadLen) { slot.n_cords = 0; slot.status = 0; slot.task0 = 0; slot.n_tasks = 0; if (w.lane == 0) a.slots[r] = slot; continue; }
@@ -1816,7 +1822,7 @@ int lnr_ctx_kernel_times(lnr_ctx * ctx, int cap, const char ** names, float * to
 // ---- genome -------------------------------------------------------------------------------------------
 static int genome_layout(lnr_ctx * ctx, uint32_t n_contigs, const uint64_t * len, lnr_genome * g)
 {
-    if (n_contigs == 0 || n_contigs > 1024) return fail(ctx, LNR_E_LIMIT, "1..1024 contigs (linear.cpp:107)");
+    if (n_contigs == 0 || n_contigs >= 1024) return fail(ctx, LNR_E_LIMIT, "1..1023 contigs (linear.cpp:107)");
     uint64_t off = 0;
     for (uint32_t i = 0; i < n_contigs; i++)
     {
@@ -1980,6 +1986,7 @@ static cudaError_t index_build_dirx(lnr_ctx * ctx, lnr_index * ix)
 int lnr_index_from_device(lnr_ctx * ctx, const int32_t * dev_dir, const uint64_t * dev_hs, uint64_t n_hs, lnr_index ** out)
 {
     if (!ctx || !dev_dir || !out || (n_hs && !dev_hs)) return LNR_E_ARG;
+    if (n_hs >= (1ULL << 31)) return fail(ctx, LNR_E_LIMIT, "hs exceeds int32 bucket offsets (index_util.h:101)");
     cudaSetDevice(ctx->device);
     lnr_index * ix = new lnr_index();
     ix->ctx = ctx; ix->index_type = 1; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = n_hs;
@@ -2216,7 +2223,7 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
         else
         k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs,
                                                                              ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>(),
-                                                                             ctx->sample_cnt.as<u32>(), ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>());
+                                                                             ctx->sample_cnt.as<u32>(), ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>(), d_counters);
     }
     if (n_samples && !hx_mode)
     {
@@ -2384,7 +2391,10 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         CK(cudaMemsetAsync(ctx->bins.p, 0, (size_t)n_warps * kNumBins * sizeof(u32), ctx->stream));
         ctx->bins_zeroed = ctx->bins.p;
     }
-    u32 tasks2_cap = n_reads * 4 + 1024;
+    u64 tasks2_cap64 = 1024;   // a read emits at most L/1000 + 4 gap tasks (k_map_finish: gcap)
+    for (uint32_t r = 0; r < n_reads; r++) tasks2_cap64 += (h_read_off[r + 1] - h_read_off[r]) / 1000 + 4;
+    if (tasks2_cap64 > 0xfffffff0ull) return fail(ctx, LNR_E_LIMIT, "batch too large");
+    u32 tasks2_cap = (u32)tasks2_cap64;
     CK(ctx->tasks2.reserve((size_t)tasks2_cap * sizeof(SeedTask)));
     if (dbg && dbg->hits_off)
     {
@@ -2598,6 +2608,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     ctx->counters[5] = total_cords;               // C
     ctx->counters[6] = total_bases;
     ctx->counters[7] = n_tasks2;
+    for (int i = 0; i < 8; i++) ctx->diag[i] = h_misc[8 + 16 + i];
     for (int i = 0; i < 16; i++) ctx->stage_cycles[i] = h_misc[8 + 24 + i];
     if (want_rec)
     {
@@ -2709,6 +2720,13 @@ int lnr_last_batch_counters(lnr_ctx * ctx, uint64_t counters[8])
 {
     if (!ctx || !counters) return LNR_E_ARG;
     for (int i = 0; i < 8; i++) counters[i] = ctx->counters[i];
+    return LNR_OK;
+}
+
+int lnr_last_batch_diag(lnr_ctx * ctx, uint64_t diag[8])
+{
+    if (!ctx || !diag) return LNR_E_ARG;
+    for (int i = 0; i < 8; i++) diag[i] = ctx->diag[i];
     return LNR_OK;
 }
 

@@ -54,6 +54,8 @@ def assemble_dindex(parts, xp=np):
     counts = [int(p[1].shape[0]) for p in parts]
     base = 0
     slices = []
+    if sum(counts) >= 1 << 31:
+        raise ValueError("assembled hs exceeds int32 bucket offsets (index_util.h:101)")
     for s, (d, _) in enumerate(parts):
         slices.append(d[s * per:(s + 1) * per] + base)
         base += counts[s]
@@ -88,4 +90,8 @@ def build_index_sharded(lb, ctx, genome, threads, rank, world, torch, dist, devi
     dist.all_gather_into_tensor(dir_all[:N_BUCKETS], my_slice)
     dir_all[N_BUCKETS] = sum(counts)
     hs = torch.cat([hs_all[r * n_max: r * n_max + counts[r]] for r in range(world)])
+    if sum(counts) >= 1 << 31:
+        raise ValueError("assembled hs exceeds int32 bucket offsets (index_util.h:101)")
+    # the library copies on its own (non-blocking) stream: the gathers / cat queued on torch's streams must be complete
+    torch.cuda.synchronize(device)
     return lb.Index.from_device(ctx, dir_all, hs)

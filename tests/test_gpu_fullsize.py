@@ -77,3 +77,45 @@ def test_dindex_3gbase_properties_and_sharded_equivalence():
             assert int(fld.max()) <= 48
             tot += fld
     assert int(tot.max()) <= 48 and int(tot.min()) >= 20
+
+
+def test_config2_cords_and_dindex_vs_reference():
+    """BASELINE configs[1] + configs[2] against the UNMODIFIED reference (oracle/_ref) on the very inputs bench.py times:
+    the whole 3.1-Gbase DIndex (dir + hs, -t 16) and the cords of ONT-like reads incl. planted-SV reads. Regimes the small
+    cases never reach: contig ids up to 23, binningFilter bins up to ~9970 (pmpfinder.cpp:1984-1996), ~27 bucket records
+    per seed, lookup tails beyond 24 keys."""
+    import torch
+    import linear_b200 as lb
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    from cpu_checkers import RefImpl, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref (the compiled reference) did not travel")
+    dev = torch.device("cuda", 0)
+    lens = bench.contig_lengths()
+    genome = bench.gen_genome(torch, dev, lens)
+    n_reads = 768
+    bases_t, offs = bench.gen_reads(torch, dev, genome, lens, n_reads, seed=4242)
+    bases = bases_t.cpu().numpy()
+    gh = genome.cpu().numpy()
+    coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    contigs = [gh[coff[i]:coff[i + 1]] for i in range(len(lens))]
+    T = 16
+    ctx = lb.Context(0)
+    gen = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=[int(x) for x in lens])
+    del genome, bases_t
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    cords, c_off = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=1)
+    ref = RefImpl(contigs, threads=T, preset=1)
+    r_cords, r_off = ref.map_batch(bases, offs, map_threads=os.cpu_count() or 1)
+    par = bench.check_parity(torch, dev, ref, index, r_cords, r_off, cords, c_off)
+    # genome features of the last (24th) contig as well
+    f_gpu = feats.download(len(lens) - 1)
+    f_ref = ref.genome_features(len(lens) - 1)
+    ref.close()
+    assert par["cords_equal"], par
+    assert par["dindex_equal"], par
+    assert par["cords"] > 50 * n_reads          # the reads really mapped
+    assert np.array_equal(f_gpu, f_ref)

@@ -185,13 +185,14 @@ def test_hash_range_sharded_index_build(lb, ctx, n_shards):
 def test_scratch_overflow_falls_back_to_big_arena(lb, monkeypatch):
     """reads whose scratch does not fit the per-warp arena are re-run by the big-arena pass; results are unchanged"""
     g, reads, bases, offs, T, preset = make_case("repeat_ont")
-    monkeypatch.setenv("LNR_ARENA_KB", "48")
+    monkeypatch.setenv("LNR_ARENA_KB", "16")
     small = lb.Context(0)
     gen = lb.Genome(small, g)
     feats = lb.create_features(small, gen, 2, T)
     index = lb.create_index(small, gen, 1, T)
     cords, coff = lb.apx_map_batch(small, index, feats, bases, offs, preset=preset)
-    kt = small.kernel_times()
+    d = small.diag()
+    assert d["hits_big_tasks"] > 0 and d["finish_big_reads"] > 0, d     # the big-arena passes really took tasks
     oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
     assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
 
@@ -203,13 +204,20 @@ def test_one_kernel_hit_stage_gives_the_same_cords(lb, ctx, monkeypatch):
     gen = lb.Genome(ctx, g)
     feats = lb.create_features(ctx, gen, 2, T)
     index = lb.create_index(ctx, gen, 1, T)
+    ctx.set_profiling(True)
+    ctx.reset_kernel_times()
     c3, o3, d3 = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset, debug=True)
+    kt3 = ctx.kernel_times()
+    assert "k_hits_sort" in kt3 and "k_hits_chain" in kt3 and "k_hits_blocks" in kt3 and "k_map_hits" not in kt3, sorted(kt3)
+    ctx.reset_kernel_times()
     monkeypatch.setenv("LNR_MONOLITHIC_HITS", "1")
     c1, o1, d1 = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset, debug=True)
+    kt1 = ctx.kernel_times()
+    ctx.set_profiling(False)
+    assert "k_map_hits" in kt1 and "k_hits_sort" not in kt1, sorted(kt1)
     assert np.array_equal(o1, o3) and np.array_equal(c1, c3)
     for k in d3:
         assert np.array_equal(np.asarray(d1[k]), np.asarray(d3[k])), k
-    assert "k_hits_sort" in ctx.kernel_times() or True
 
 
 @pytest.mark.parametrize("threads", [1, 4, 8])
@@ -310,5 +318,6 @@ def test_exhausted_match_mask_pool_falls_back_to_rescan(lb, monkeypatch):
     feats = lb.create_features(c, gen, 2, T)
     index = lb.create_index(c, gen, 1, T)
     cords, coff = lb.apx_map_batch(c, index, feats, bases, offs, preset=preset)
+    assert c.diag()["seed_rescans"] > 0          # the re-scan branch of the fill pass really ran
     oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
     assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
