@@ -111,6 +111,19 @@ int lnr_apxmap_batch(lnr_ctx *, const lnr_index *, const lnr_feats * f2, const l
                      uint32_t n_reads, const uint8_t * dna5_concat, const uint64_t * read_off /* n+1 */,
                      uint64_t * cords_str_concat, uint64_t * cords_off /* n+1 */, uint64_t cords_capacity,
                      lnr_debug_out * dbg /* may be NULL */);
+/* The same call with the reads 2-bit packed (BASELINE north_star: "2-bit-packed"): base i of the batch (reads back to
+ * back, read_off in bases) is bits 2(i&3)..2(i&3)+1 of packed2[i >> 2], A,C,G,T = 0..3. n_mask is NULL for a batch
+ * without N, else a bitmap with bit (i & 7) of n_mask[i >> 3] set where base i is N (its two packed bits are 0). A
+ * quarter of the bytes of the Dna5 form cross PCIe; the device expands them once. Results are identical to
+ * lnr_apxmap_batch on the corresponding Dna5 string. lnr_pack_dna5 is the host-side converter a shim calls once per
+ * read block (String<Dna5> -> packed2 / n_mask; buffers of (n+3)/4 and (n+7)/8 bytes; *has_n tells whether the bitmap is
+ * needed). */
+int lnr_pack_dna5(const uint8_t * dna5, uint64_t n_bases, uint8_t * packed2, uint8_t * n_mask, int * has_n);
+int lnr_apxmap_batch_packed(lnr_ctx *, const lnr_index *, const lnr_feats * f2, const lnr_params *,
+                            uint32_t n_reads, const uint8_t * packed2, const uint8_t * n_mask /* may be NULL */,
+                            const uint64_t * read_off /* n+1, in bases */,
+                            uint64_t * cords_str_concat, uint64_t * cords_off /* n+1 */, uint64_t cords_capacity,
+                            lnr_debug_out * dbg /* may be NULL */);
 /* device buffers in, device buffers out (inputs already resident in HBM; bench "value" leg).
  * n_cords_total (host) receives the number of cords written. */
 int lnr_apxmap_batch_device(lnr_ctx *, const lnr_index *, const lnr_feats * f2, const lnr_params *,

@@ -30,7 +30,7 @@ EXPORTS = [
     "lnr_ctx_reset_kernel_times", "lnr_genome_upload", "lnr_genome_from_device", "lnr_genome_destroy",
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
-    "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch",
+    "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch", "lnr_apxmap_batch_packed", "lnr_pack_dna5",
     "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_diag", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
     "lnr_reads_parse", "lnr_reads_parse_device", "lnr_reads_info", "lnr_reads_download", "lnr_reads_device", "lnr_reads_destroy", "lnr_apxmap_reads",
 ]
@@ -91,6 +91,9 @@ def load_library() -> C.CDLL:
     lib.lnr_index_destroy.restype = None
     lib.lnr_apxmap_batch.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, u64p, C.c_uint64,
                                      C.POINTER(DebugOut)]
+    lib.lnr_apxmap_batch_packed.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, vp, u64p, vp, u64p, C.c_uint64,
+                                            C.POINTER(DebugOut)]
+    lib.lnr_pack_dna5.argtypes = [vp, C.c_uint64, vp, vp, C.POINTER(C.c_int)]
     lib.lnr_apxmap_batch_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, vp, C.c_uint64, u64p]
     lib.lnr_last_batch_counters.argtypes = [vp, u64p]
     lib.lnr_last_batch_stage_cycles.argtypes = [vp, u64p]
@@ -396,6 +399,37 @@ def apx_map_batch(ctx: Context, index: Index, feats: Features, bases, offsets, p
     if debug:
         return res, coff, keep
     return res, coff
+
+
+def pack_dna5(bases: np.ndarray):
+    """Dna5 ordinals -> (packed2 uint8[(n+3)/4], n_mask uint8[(n+7)/8] or None when the batch has no N) -- lnr_pack_dna5"""
+    lib = load_library()
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    n = len(bases)
+    packed = np.zeros((n + 3) // 4, np.uint8)
+    nmask = np.zeros((n + 7) // 8, np.uint8)
+    has_n = C.c_int()
+    rc = lib.lnr_pack_dna5(C.c_void_p(bases.ctypes.data), n, C.c_void_p(packed.ctypes.data), C.c_void_p(nmask.ctypes.data), C.byref(has_n))
+    if rc != 0:
+        raise LnrError(rc, "lnr_pack_dna5")
+    return packed, (nmask if has_n.value else None)
+
+
+def apx_map_batch_packed(ctx: Context, index: Index, feats: Features, packed: np.ndarray, n_mask: Optional[np.ndarray], offsets,
+                         preset: int = 1, cords_out: Optional[np.ndarray] = None, cords_off_out: Optional[np.ndarray] = None):
+    """lnr_apxmap_batch_packed: 2-bit packed reads (pack_dna5) in host memory -> (cords, cords_off)"""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    total = int(offsets[-1])
+    cap = int(total // 16 + 64 * n + 1024) if cords_out is None else len(cords_out)
+    cords = np.empty(cap, dtype=np.uint64) if cords_out is None else cords_out
+    coff = np.zeros(n + 1, dtype=np.uint64) if cords_off_out is None else cords_off_out
+    prm = Params(preset=preset, feature_type=feats.feature_type)
+    rc = ctx.lib.lnr_apxmap_batch_packed(ctx.h, index.h, feats.h, C.byref(prm), n, C.c_void_p(packed.ctypes.data),
+                                         C.c_void_p(n_mask.ctypes.data) if n_mask is not None else None,
+                                         offsets.ctypes.data_as(u64p), cords.ctypes.data_as(C.c_void_p), coff.ctypes.data_as(u64p), cap, None)
+    ctx.check(rc)
+    return cords[: int(coff[-1])], coff
 
 
 def cords_end(cords_str: np.ndarray, window: int = 96) -> np.ndarray:

@@ -23,6 +23,7 @@ typedef int64_t i64;
 typedef uint32_t u32;
 typedef int32_t i32;
 typedef uint8_t u8;
+typedef uint16_t u16;
 
 // ---- encodings -------------------------------------------------------------------------------------
 static const u64 kAnchorZero = 1ULL << 20;            // const_anchor_zero (cords.cpp:8)

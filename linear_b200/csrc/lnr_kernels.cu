@@ -112,12 +112,14 @@ struct lnr_ctx
         dbg_c1, dbg_nc1, read_meta;
     uint64_t counters[8] = {0};
     uint64_t diag[8] = {0};
+    uint64_t anchors_host_total = 0;   // raw anchors of the DIndex seeding passes of the current batch
     uint64_t stage_cycles[16] = {0};
     uint64_t longest_cycles[16] = {0};
     const void * bins_zeroed = nullptr;
     size_t bins_zeroed_cap = 0;
     DevBuf ing[8];   // read-ingest temporaries (lnr_ingest.cuh)
     void * reads_cache = nullptr; size_t reads_cache_bytes = 0;   // last output block given back by lnr_reads_destroy
+    DevBuf packed;   // 2-bit packed batch as uploaded (lnr_apxmap_batch_packed)
     DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
@@ -759,17 +761,19 @@ __device__ __forceinline__ bool seed_sample_fast(const u8 * __restrict__ rd, i64
     sv.Y = strand ? (u32)(Pc >> (2 * (8 - off))) & 0xffu : (u32)(P >> (2 * (11 - off))) & 0xffu;
     return true;
 }
+// One thread per sample; a warp owns 32 consecutive samples. A sample whose X differs from the previous sample's X
+// (xpre rule, :1882) fetches its bucket's lookup sector and scans the Y keys. The matches of the warp are written, in
+// sample order, as one contiguous run of 32-bit entries (hs index | query strand << 31) claimed with ONE atomic per warp
+// from one of kMaskPools pools; the fill pass then spreads those entries evenly over the lanes -- every lane keeps a
+// random hs load in flight -- instead of walking one sample's matches per thread. A warp that gets no room (pool
+// exhausted) is re-scanned by the fill pass. Per sample only the match count is stored (it feeds the device scan).
+struct SeedWarpRec { u32 list_off; u32 scanned; };   // per warp: start of its entries (0xffffffff: none), records scanned (H)
 __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
                                                     const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
                                                     const uint4 * __restrict__ dirx, const u8 * __restrict__ hsy,
-                                                    u64 * __restrict__ info, u32 * __restrict__ count, unsigned long long * counters,
-                                                    u64 * __restrict__ masks, u32 * __restrict__ mask_off, u32 pool_cap,
-                                                    unsigned int * mask_ctr)
+                                                    u32 * __restrict__ count, SeedWarpRec * __restrict__ wrec,
+                                                    u32 * __restrict__ list, u32 pool_cap, unsigned int * pool_ctr)
 {
-    // masks: one bit per scanned bucket record (1 = passes the Y-key rule), 64 records per word, so that the fill pass
-    // touches only the matching records instead of scanning every bucket a second time. Words are claimed with one
-    // atomic per warp from one of kMaskPools pools (a single counter serialises 1.4 M atomics in L2; a per-CTA claim
-    // parks the whole CTA on the round trip); a sample that does not get words (pool exhausted) is re-scanned by the fill.
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     u32 c = 0, scanned = 0;
@@ -807,7 +811,6 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
             if (lane > 0 && til == ti && ml == m - 1) xprev = xl;
             else { SeedVal pv; u32 kp; if (!seed_sample_fast(acc.s, acc.len, t, m - 1, pv)) seed_sample(acc, t, m - 1, pv, kp); xprev = pv.X; }
         }
-        u64 inf = 0;
         if (sv.X != xprev)
         {
             e0 = __ldg(dirx + 2 * (size_t)sv.X); e1 = __ldg(dirx + 2 * (size_t)sv.X + 1);
@@ -815,131 +818,175 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
             qY = sv.Y;
             scanned = e0.y;
             active = scanned != 0;
-            inf = (u64)(u32)bkt_b | ((u64)scanned << 32) | ((u64)sv.Y << 48) | ((u64)sv.strand << 56);
         }
-        info[s] = inf;
     }
-    // claim mask words: exclusive prefix of the per-lane word counts, one atomic per warp
-    u32 words = active ? (scanned + 63) >> 6 : 0;
-    u32 incl = words;
+    // 4 Y bytes per step; ykey_match(b, Y) with v = b ^ Y, l = lowest set bit of v: v == 0 or v >> ctz(v) < 4  <=>  v <= 3 l
+    const u32 Y4 = qY * 0x01010101u;
+    auto match4 = [&](u32 w4, u32 i) -> u32 {
+        u32 v4 = w4 ^ Y4;
+        u32 h4 = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t2; }
-    u32 wtot = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned wid = threadIdx.x >> 5;
-    const u32 pool = (blockIdx.x * 8u + wid) & (kMaskPools - 1);
-    u32 wbase = 0;
-    if (lane == 0 && wtot) wbase = atomicAdd(mask_ctr + pool, wtot);
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    const u32 local = wbase + incl - words;
-    const u32 moff = pool * pool_cap + local;
-    bool have_mask = active && (u64)local + words <= (u64)pool_cap;
+        for (int j = 0; j < 4; j++)
+        {
+            u32 v = (v4 >> (8 * j)) & 0xffu;
+            u32 l = v & (0u - v);
+            h4 |= v <= 3u * l ? (1u << j) : 0u;
+        }
+        u32 rem = scanned - i;
+        if (rem < 4) h4 &= (1u << rem) - 1u;
+        return h4;
+    };
+    u64 m0 = 0;   // matches among the bucket's first 64 records; longer buckets (rare) are scanned again when emitting
+    const u8 * pb = hsy + bkt_b + 24;
+    const unsigned sh = ((unsigned)(uintptr_t)pb & 3u) * 8u;
+    const u32 * pw = (const u32 *)((uintptr_t)pb & ~(uintptr_t)3);
     if (active)
     {
-        // 4 Y bytes per step; ykey_match(b, Y) with v = b ^ Y, l = lowest set bit of v:
-        // v == 0 or v >> ctz(v) < 4  <=>  v <= 3 l
-        const u32 Y4 = qY * 0x01010101u;
-        u64 mb = 0; u32 wi = 0;
-        auto step4 = [&](u32 w4, u32 i) {
-            u32 v4 = w4 ^ Y4;
-            u32 h4 = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-            {
-                u32 v = (v4 >> (8 * j)) & 0xffu;
-                u32 l = v & (0u - v);
-                h4 |= v <= 3u * l ? (1u << j) : 0u;
-            }
-            u32 rem = scanned - i;
-            if (rem < 4) h4 &= (1u << rem) - 1u;
-            c += __popc(h4);
-            u32 bit = i & 63u;
-            mb |= (u64)h4 << bit;
-            if (bit == 60 || rem <= 4) { if (have_mask) masks[moff + wi] = mb; wi++; mb = 0; }
-        };
         // records 0..23 come with the lookup entry
         const u32 ew[6] = {e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
         for (int q = 0; q < 6; q++)
-            if (4u * q < scanned) step4(ew[q], 4u * q);
+            if (4u * q < scanned) { u32 h4 = match4(ew[q], 4u * q); c += __popc(h4); m0 |= (u64)h4 << (4 * q); }
         if (scanned > 24)
         {
-            const u8 * pb = hsy + bkt_b + 24;
-            const unsigned sh = ((unsigned)(uintptr_t)pb & 3u) * 8u;
-            const u32 * pw = (const u32 *)((uintptr_t)pb & ~(uintptr_t)3);
             u32 w0 = __ldg(pw);
             for (u32 i = 24; i < scanned; i += 4)
             {
                 u32 w1 = __ldg(pw + ((i - 24) >> 2) + 1);
-                step4(__funnelshift_r(w0, w1, sh), i);
+                u32 h4 = match4(__funnelshift_r(w0, w1, sh), i);
+                c += __popc(h4);
+                if (i < 64) m0 |= (u64)h4 << i;
                 w0 = w1;
             }
         }
     }
-    if (s < n_samples) { count[s] = c; mask_off[s] = have_mask ? moff : 0xffffffffu; }
-}
-// H (bucket records scanned) and A (anchors) of a seeding pass for lnr_last_batch_counters: summed from the per-sample
-// records by a pass of its own, so that the count kernel neither synchronises its CTA nor funnels atomics into one line
-__global__ void __launch_bounds__(256) k_seed_stats(const u64 * __restrict__ info, const u32 * __restrict__ count, u64 n_samples,
-                                                    unsigned long long * counters)
-{
-    unsigned long long hs = 0, as = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += (u64)gridDim.x * blockDim.x)
+    // claim the warp's run of entries: exclusive prefix of the per-lane counts, one atomic per warp
+    u32 incl = c, hsum = scanned;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t2; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+    const u32 wtot = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned wid = threadIdx.x >> 5;
+    const u32 pool = (blockIdx.x * 8u + wid) & (kMaskPools - 1);
+    u32 wbase = 0;
+    if (lane == 0 && wtot) wbase = atomicAdd(pool_ctr + pool, wtot);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    const bool have = (u64)wbase + wtot <= (u64)pool_cap;
+    if (lane == 0 && s < n_samples)
     {
-        hs += (info[i] >> 32) & 0xffff;
-        as += count[i];
+        SeedWarpRec r; r.list_off = wtot == 0 ? 0u : (have ? pool * pool_cap + wbase : 0xffffffffu); r.scanned = hsum;
+        wrec[s >> 5] = r;
     }
-    for (int o = 16; o; o >>= 1) { hs += __shfl_xor_sync(0xffffffffu, hs, o); as += __shfl_xor_sync(0xffffffffu, as, o); }
-    __shared__ unsigned long long s_h[8], s_a[8];
-    if ((threadIdx.x & 31) == 0) { s_h[threadIdx.x >> 5] = hs; s_a[threadIdx.x >> 5] = as; }
-    __syncthreads();
-    if (threadIdx.x == 0)
+    if (s < n_samples) count[s] = c;
+    if (c && have)
     {
-        for (int i = 1; i < 8; i++) { hs += s_h[i]; as += s_a[i]; }
-        if (hs) atomicAdd(&counters[1], hs);
-        if (as) atomicAdd(&counters[2], as);
-    }
-}
-// anchors of task ti start at aoff[sample0] + ti (slot 0 of the region is the sentinel)
-__global__ void __launch_bounds__(256) k_seed_fill(const u64 * __restrict__ read_off, const SeedTask * __restrict__ tasks, u32 n_tasks,
-                                                   u64 n_samples, const u64 * __restrict__ hs, const u64 * __restrict__ info,
-                                                   const u64 * __restrict__ aoff, u64 * __restrict__ anchors,
-                                                   const u32 * __restrict__ count, const u64 * __restrict__ masks,
-                                                   const u32 * __restrict__ mask_off, unsigned long long * counters)
-{
-    u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_samples) return;
-    if (!count[s]) return;
-    u64 inf = info[s];
-    u32 nrec = (u32)(inf >> 32) & 0xffff;
-    u32 ti = find_task(tasks, n_tasks, s);
-    SeedTask t = tasks[ti];
-    u32 m = (u32)(s - t.sample0) + 1;
-    u64 k = (u64)t.str + kSpanD + (u64)t.alpha * m - 1;
-    u64 L = read_off[t.read + 1] - read_off[t.read];
-    u32 b = (u32)inf, Y = (u32)(inf >> 48) & 0xff, strand = (u32)(inf >> 56) & 1;
-    u64 * out = anchors + aoff[s] + ti + 1;
-    u32 mo = mask_off[s];
-    if (mo != 0xffffffffu)
-    {
-        // only the records that matched in the count pass are read again (in bucket order)
-        for (u32 w = 0; w < (nrec + 63) >> 6; w++)
+        u32 * o = list + (size_t)pool * pool_cap + wbase + (incl - c);
+        const u32 tag = (u32)bkt_b | (sv.strand << 31);
+        while (m0) { int bit = __ffsll((long long)m0) - 1; m0 &= m0 - 1; *o++ = tag + (u32)bit; }
+        if (scanned > 64)
         {
-            u64 mm = masks[mo + w];
-            while (mm)
+            u32 w0 = __ldg(pw + 10);
+            for (u32 i = 64; i < scanned; i += 4)
             {
-                int bit = __ffsll((long long)mm) - 1;
-                mm &= mm - 1;
-                *out++ = val2anchor(__ldg(hs + b + 64 * w + bit), k, L, strand);
+                u32 w1 = __ldg(pw + ((i - 24) >> 2) + 1);
+                u32 h4 = match4(__funnelshift_r(w0, w1, sh), i);
+                while (h4) { int bit = __ffs((int)h4) - 1; h4 &= h4 - 1; *o++ = tag + i + (u32)bit; }
+                w0 = w1;
             }
         }
     }
-    else
+}
+// H (bucket records scanned) of a seeding pass for lnr_last_batch_counters: summed from the per-warp records by a pass of
+// its own, so that the count kernel neither synchronises its CTA nor funnels atomics into one line
+__global__ void __launch_bounds__(256) k_seed_stats(const SeedWarpRec * __restrict__ wrec, u64 n_warps, unsigned long long * counters)
+{
+    unsigned long long hs = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_warps; i += (u64)gridDim.x * blockDim.x) hs += wrec[i].scanned;
+    for (int o = 16; o; o >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o);
+    __shared__ unsigned long long s_h[8];
+    if ((threadIdx.x & 31) == 0) s_h[threadIdx.x >> 5] = hs;
+    __syncthreads();
+    if (threadIdx.x == 0)
     {
-        atomicAdd(&counters[18], 1ULL);   // diagnostics: samples re-scanned because the mask pool was exhausted
-        for (u32 i = 0; i < nrec; i++)
+        for (int i = 1; i < 8; i++) hs += s_h[i];
+        if (hs) atomicAdd(&counters[1], hs);
+    }
+}
+// anchors of task ti start at aoff[sample0] + ti (slot 0 of the region is the sentinel). A warp owns the same 32 samples
+// as in the count pass; its matches are dealt round-robin to the lanes: entry j of the warp's run belongs to the sample
+// whose exclusive count prefix is the largest one <= j (found with 5 shuffles), that sample's k / L / task come by shuffle.
+__global__ void __launch_bounds__(256) k_seed_fill(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
+                                                   const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
+                                                   const u64 * __restrict__ hs, const uint4 * __restrict__ dirx,
+                                                   const u64 * __restrict__ aoff, u64 * __restrict__ anchors,
+                                                   const u32 * __restrict__ count, const SeedWarpRec * __restrict__ wrec,
+                                                   const u32 * __restrict__ list, unsigned long long * counters)
+{
+    const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    const u64 s0 = s - lane;
+    if (s0 >= n_samples) return;
+    const u32 c = s < n_samples ? count[s] : 0u;
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t2; }
+    const u32 T = __shfl_sync(0xffffffffu, incl, 31);
+    if (T == 0) return;
+    const u32 e = incl - c;
+    u32 t_first = 0;
+    if (lane == 0) t_first = find_task(tasks, n_tasks, s0);
+    t_first = __shfl_sync(0xffffffffu, t_first, 0);
+    u32 ti = t_first, k = 0, L = 0;
+    SeedTask t;
+    memset(&t, 0, sizeof t);
+    if (c)
+    {
+        while (ti + 1 < n_tasks && tasks[ti + 1].sample0 <= s) ti++;
+        t = tasks[ti];
+        const u32 m = (u32)(s - t.sample0) + 1;
+        k = t.str + kSpanD + t.alpha * m - 1;
+        L = (u32)(read_off[t.read + 1] - read_off[t.read]);
+    }
+    const SeedWarpRec wr = wrec[s0 >> 5];
+    const u64 a0 = aoff[s0];
+    if (wr.list_off != 0xffffffffu)
+    {
+        const u32 * lst = list + wr.list_off;
+        for (u32 base = 0; base < T; base += 32)
         {
-            u64 h = __ldg(hs + b + i);
-            if (ykey_match((u32)(h & kMaskY), Y)) *out++ = val2anchor(h, k, L, strand);
+            const u32 j = base + lane;
+            u32 lo = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1)
+            {
+                const u32 cand = lo + step;
+                const u32 ec = __shfl_sync(0xffffffffu, e, cand & 31);
+                if (ec <= j) lo = cand;          // e is non-decreasing over the lanes and cand < 32
+            }
+            const u32 ko = __shfl_sync(0xffffffffu, k, lo), Lo = __shfl_sync(0xffffffffu, L, lo), tio = __shfl_sync(0xffffffffu, ti, lo);
+            if (j < T)
+            {
+                const u32 ent = __ldg(lst + j);
+                const u64 h = __ldg(hs + (ent & 0x7fffffffu));
+                anchors[a0 + j + tio + 1] = val2anchor(h, (u64)ko, (u64)Lo, ent >> 31);
+            }
+        }
+    }
+    else if (c)
+    {
+        // the warp got no room for its entries in the count pass: evaluate the sample again and scan its bucket in hs
+        atomicAdd(&counters[18], 1ULL);   // diagnostics: samples re-scanned
+        GAcc acc = {bases + read_off[t.read], (i64)L};
+        SeedVal sv; u32 kk;
+        const u32 m = (u32)(s - t.sample0) + 1;
+        if (!seed_sample_fast(acc.s, acc.len, t, m, sv)) seed_sample(acc, t, m, sv, kk);
+        const uint4 d0 = __ldg(dirx + 2 * (size_t)sv.X);
+        u64 * out = anchors + a0 + e + ti + 1;
+        for (u32 i = 0; i < d0.y; i++)
+        {
+            u64 h = __ldg(hs + d0.x + i);
+            if (ykey_match((u32)(h & kMaskY), sv.Y)) *out++ = val2anchor(h, (u64)k, (u64)L, sv.strand);
         }
     }
 }
@@ -1753,6 +1800,7 @@ int lnr_ctx_create(int device, lnr_ctx ** out)
     if (const char * e = getenv("LNR_BIG_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 16384) ctx->big_arena_bytes_per_warp = (size_t)v << 20; }
     if (const char * e = getenv("LNR_ARENA_KB")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) ctx->arena_bytes_per_warp = (size_t)v << 10; }
     else if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }
+    if (const char * e = getenv("LNR_L2_FETCH")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LNR_E_CUDA; }
     {
         if (getenv("LNR_TRACE"))
@@ -1781,7 +1829,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec, &ctx->packed})
         b->release();
     ctx->stage.release();
     if (ctx->reads_cache) cudaFree(ctx->reads_cache);
@@ -2170,21 +2218,27 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
         CK(index_build_dirx(ctx, const_cast<lnr_index *>(ix)));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    CK(ctx->sample_info.reserve((size_t)(n_samples + 1) * sizeof(u64)));
+    const bool hx_mode = ix->index_type == 2;
+    if (hx_mode) CK(ctx->sample_info.reserve((size_t)(n_samples + 1) * sizeof(u64)));
     CK(ctx->sample_cnt.reserve((size_t)(n_samples + STILE + 1) * sizeof(u32)));
     CK(aoff_buf.reserve((size_t)(n_samples + STILE + 1) * sizeof(u64)));
     CK(ctx->misc.reserve(1024));
-    u32 mask_cap = (u32)std::min<u64>(2 * n_samples + (1u << 20), 0xfffffff0ull);
-    if (const char * e = getenv("LNR_MASK_WORDS")) { long v = atol(e); if (v >= (long)kMaskPools && (u64)v < mask_cap) mask_cap = (u32)v; }   // tests: force the re-scan path
-    CK(ctx->seed_masks.reserve((size_t)mask_cap * sizeof(u64)));
-    CK(ctx->seed_mask_off.reserve((size_t)(n_samples + 1) * sizeof(u32)));
+    // match entries of the count pass (k_seed_count): 4 per sample on average is twice what this workload produces; a warp
+    // that finds its pool full is re-scanned by the fill pass
+    u32 list_cap = (u32)std::min<u64>(4 * n_samples + (1u << 20), 0xfffffff0ull);
+    if (const char * e = getenv("LNR_MASK_WORDS")) { long v = atol(e); if (v >= (long)kMaskPools && (u64)v < list_cap) list_cap = (u32)v; }   // tests: force the re-scan path
+    const u64 n_swarps = (n_samples + 31) / 32;
+    if (!hx_mode)
+    {
+        CK(ctx->seed_masks.reserve((size_t)list_cap * sizeof(u32)));
+        CK(ctx->seed_mask_off.reserve((size_t)(n_swarps + 1) * sizeof(SeedWarpRec)));
+    }
     CK(ctx->mask_ctr.reserve(kMaskPools * sizeof(unsigned int)));
-    unsigned int * d_mask_ctr = ctx->mask_ctr.as<unsigned int>();
-    CK(cudaMemsetAsync(d_mask_ctr, 0, kMaskPools * sizeof(unsigned int), ctx->stream));
-    const u32 pool_cap = mask_cap / kMaskPools;
+    unsigned int * d_pool_ctr = ctx->mask_ctr.as<unsigned int>();
+    CK(cudaMemsetAsync(d_pool_ctr, 0, kMaskPools * sizeof(unsigned int), ctx->stream));
+    const u32 pool_cap = list_cap / kMaskPools;
     u64 * d_total = ctx->misc.as<u64>();
     unsigned long long * d_counters = (unsigned long long *)(ctx->misc.as<u64>() + 8);
-    const bool hx_mode = ix->index_type == 2;
     HIndexDev hx = {ix->d_ysa, ix->n_ysa, ix->empty_dir, ix->d_tab, ix->tab_len ? ix->tab_len - 1 : 0};
     {
         LaunchScope ls(ctx, "k_seed_prep");
@@ -2200,9 +2254,9 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
             k_hseed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, hx,
                                                                                    ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
         else
-        k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dirx,
-                                                                              ix->d_hsy, ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters,
-                                                                              ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>(), pool_cap, d_mask_ctr);
+            k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dirx,
+                                                                                  ix->d_hsy, ctx->sample_cnt.as<u32>(), ctx->seed_mask_off.as<SeedWarpRec>(),
+                                                                                  ctx->seed_masks.as<u32>(), pool_cap, d_pool_ctr);
     }
     CK(cudaGetLastError());
     int rc = device_scan<u64>(ctx, ctx->sample_cnt.as<u32>(), n_samples + 1, 0, aoff_buf.as<u64>(), d_total, "k_scan_seeds");
@@ -2221,14 +2275,15 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
             k_hseed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, hx,
                                                                                   ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>());
         else
-        k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs,
-                                                                             ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>(),
-                                                                             ctx->sample_cnt.as<u32>(), ctx->seed_masks.as<u64>(), ctx->seed_mask_off.as<u32>(), d_counters);
+            k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs, ix->d_dirx,
+                                                                                 aoff_buf.as<u64>(), ctx->anchorsA.as<u64>(), ctx->sample_cnt.as<u32>(),
+                                                                                 ctx->seed_mask_off.as<SeedWarpRec>(), ctx->seed_masks.as<u32>(), d_counters);
     }
     if (n_samples && !hx_mode)
     {
         LaunchScope ls(ctx, "k_seed_stats");
-        k_seed_stats<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), n_samples, d_counters);
+        k_seed_stats<<<ctx->n_sm * 2, 256, 0, ctx->stream>>>(ctx->seed_mask_off.as<SeedWarpRec>(), n_swarps, d_counters);
+        ctx->anchors_host_total += total;     // A: the scan's total (no device pass needed)
     }
     CK(cudaGetLastError());
     return LNR_OK;
@@ -2282,6 +2337,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
                        uint64_t * n_cords_total, lnr_debug_out * dbg)
 {
     HostTrace tr(ctx->stream);
+    ctx->anchors_host_total = 0;
     if (n_reads == 0) { if (n_cords_total) *n_cords_total = 0; return LNR_OK; }
     const float stop_ratio = prm && prm->preset == 0 ? 0.7f : 0.0f;
     // ---- host-side layout from the read lengths
@@ -2602,7 +2658,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     u32 n_fail = ((u32 *)(h_misc + 20))[2];
     ctx->counters[0] = n_samples;                 // S
     ctx->counters[1] = h_misc[8 + 1];             // H
-    ctx->counters[2] = h_misc[8 + 2];             // A
+    ctx->counters[2] = h_misc[8 + 2] + ctx->anchors_host_total;   // A (HIndex: device counter; DIndex: the scans' totals)
     ctx->counters[3] = h_misc[8 + 3];             // Hits
     ctx->counters[4] = h_misc[8 + 4];             // W
     ctx->counters[5] = total_cords;               // C
@@ -2705,6 +2761,88 @@ int lnr_apxmap_batch(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, 
         CK(cudaMemsetAsync(ctx->bases.as<u8>() + total_bases, 0, 256, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    CK(ctx->out_cords.reserve((size_t)(cords_capacity + 8) * sizeof(u64)));
+    u64 total = 0;
+    int rc = apxmap_core(ctx, ix, f2, prm, n_reads, ctx->bases.as<u8>(), read_off, ctx->out_cords.as<u64>(), nullptr, cords_capacity, &total, dbg);
+    if (rc && rc != LNR_E_CAPACITY) return rc;
+    if (rc == LNR_E_CAPACITY && total > cords_capacity) return rc;
+    CK(cudaMemcpyAsync(cords_off, ctx->out_off.p, (n_reads + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cords, ctx->out_cords.p, (size_t)total * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// ---- 2-bit packed reads -------------------------------------------------------------------------------------------
+// Wire format of lnr_apxmap_batch_packed: base i of the batch (reads back to back) is bits 2(i&3)..2(i&3)+1 of
+// packed2[i >> 2]; n_mask (optional) has bit (i & 7) of n_mask[i >> 3] set where base i is N (its 2 bits are then 0).
+// One quarter (three eighths with the N bitmap) of the bytes of the 1-byte Dna5 form cross PCIe; the device expands them
+// to ordinals once (16 bases per thread: one 4-byte load, one 16-byte store), every kernel downstream is unchanged.
+__global__ void __launch_bounds__(256) k_unpack2(const u32 * __restrict__ packed, const u16 * __restrict__ nmask, u64 n_bases, uint4 * __restrict__ out)
+{
+    const u64 n16 = (n_bases + 15) / 16;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (u64)gridDim.x * blockDim.x)
+    {
+        const u32 w = __ldg(packed + i);
+        const u32 nm = nmask ? (u32)__ldg(nmask + i) : 0u;
+        u32 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const u32 b = (w >> (8 * q)) & 0xffu;          // 4 bases
+            u32 v = (b & 3u) | ((b & 12u) << 6) | ((b & 48u) << 12) | ((b & 192u) << 18);
+            const u32 n4 = (nm >> (4 * q)) & 15u;
+            if (n4) v = (v & ~(((n4 & 1u) * 0xffu) | ((n4 >> 1 & 1u) * 0xff00u) | ((n4 >> 2 & 1u) * 0xff0000u) | ((n4 >> 3 & 1u) * 0xff000000u))) |
+                        ((n4 & 1u) * 4u) | ((n4 >> 1 & 1u) * 0x400u) | ((n4 >> 2 & 1u) * 0x40000u) | ((n4 >> 3 & 1u) * 0x4000000u);
+            o[q] = v;
+        }
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+int lnr_pack_dna5(const uint8_t * dna5, uint64_t n_bases, uint8_t * packed2, uint8_t * n_mask, int * has_n)
+{
+    if ((!dna5 && n_bases) || !packed2) return LNR_E_ARG;
+    const uint64_t nb = (n_bases + 3) / 4, nm = (n_bases + 7) / 8;
+    memset(packed2, 0, (size_t)nb);
+    if (n_mask) memset(n_mask, 0, (size_t)nm);
+    int any = 0;
+    for (uint64_t i = 0; i < n_bases; i++)
+    {
+        const unsigned c = dna5[i];
+        if (c < 4) packed2[i >> 2] |= (uint8_t)(c << (2 * (i & 3)));
+        else { any = 1; if (n_mask) n_mask[i >> 3] |= (uint8_t)(1u << (i & 7)); }
+    }
+    if (has_n) *has_n = any;
+    if (any && !n_mask) return LNR_E_ARG;     // an N needs the bitmap
+    return LNR_OK;
+}
+
+int lnr_apxmap_batch_packed(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, const lnr_params * prm, uint32_t n_reads,
+                            const uint8_t * packed2, const uint8_t * n_mask, const uint64_t * read_off, uint64_t * cords,
+                            uint64_t * cords_off, uint64_t cords_capacity, lnr_debug_out * dbg)
+{
+    if (!ctx || !ix || !f2 || !read_off || (!packed2 && n_reads) || !cords || !cords_off) return LNR_E_ARG;
+    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
+    cudaSetDevice(ctx->device);
+    if (n_reads == 0) { cords_off[0] = 0; return LNR_OK; }
+    const u64 total_bases = read_off[n_reads];
+    const size_t n16 = (size_t)((total_bases + 15) / 16);
+    CK(ctx->bases.reserve(n16 * 16 + 256));
+    CK(ctx->packed.reserve(n16 * 4 + (n_mask ? n16 * 2 : 0) + 64));
+    u8 * d_packed = ctx->packed.as<u8>();
+    u8 * d_nmask = n_mask ? d_packed + n16 * 4 : nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_upload_mutex);
+        CK(cudaMemsetAsync(d_packed, 0, n16 * 4 + (n_mask ? n16 * 2 : 0), ctx->stream));   // the tail words of the last 16-base group
+        CK(cudaMemcpyAsync(d_packed, packed2, (size_t)((total_bases + 3) / 4), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_mask) CK(cudaMemcpyAsync(d_nmask, n_mask, (size_t)((total_bases + 7) / 8), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        LaunchScope ls(ctx, "k_unpack2");
+        k_unpack2<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>((const u32 *)d_packed, (const u16 *)d_nmask, total_bases, (uint4 *)ctx->bases.p);
+    }
+    CK(cudaMemsetAsync(ctx->bases.as<u8>() + total_bases, 0, n16 * 16 + 256 - total_bases, ctx->stream));   // zero slack behind the batch
     CK(ctx->out_cords.reserve((size_t)(cords_capacity + 8) * sizeof(u64)));
     u64 total = 0;
     int rc = apxmap_core(ctx, ix, f2, prm, n_reads, ctx->bases.as<u8>(), read_off, ctx->out_cords.as<u64>(), nullptr, cords_capacity, &total, dbg);

@@ -321,3 +321,33 @@ def test_exhausted_match_mask_pool_falls_back_to_rescan(lb, monkeypatch):
     assert c.diag()["seed_rescans"] > 0          # the re-scan branch of the fill pass really ran
     oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
     assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+
+
+@pytest.mark.parametrize("with_n", [False, True])
+def test_packed_reads_give_identical_cords(lb, ctx, with_n):
+    """lnr_apxmap_batch_packed (2-bit bases + optional N bitmap, a quarter of the PCIe bytes) == lnr_apxmap_batch on the
+    Dna5 string == the oracle; with N runs inside reads, at read edges and at positions that are not multiples of 4/16"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    bases = bases.copy()
+    if with_n:
+        rng = np.random.default_rng(5)
+        for r in range(0, len(offs) - 1, 3):
+            a, b = int(offs[r]), int(offs[r + 1])
+            if b - a < 400:
+                continue
+            for _ in range(3):
+                p = int(rng.integers(a, b - 40))
+                bases[p:p + int(rng.integers(1, 37))] = 4
+        bases[int(offs[1]) - 1] = 4          # last base of a read
+        bases[int(offs[2])] = 4              # first base of a read
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    packed, nmask = lb.pack_dna5(bases)
+    assert (nmask is not None) == with_n
+    assert len(packed) == (len(bases) + 3) // 4
+    c1, o1 = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset)
+    c2, o2 = lb.apx_map_batch_packed(ctx, index, feats, packed, nmask, offs, preset=preset)
+    assert np.array_equal(o1, o2) and np.array_equal(c1, c2)
+    oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
+    assert np.array_equal(oo, o2) and np.array_equal(oc, c2)
