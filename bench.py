@@ -212,6 +212,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
+def bind_to_gpu_numa(pci_bus_id):
+    """Run this rank (and so first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU hangs off: with N
+    ranks on one box, uploads from a remote socket's memory cross the inter-socket link and stop scaling at 4-8 GPUs.
+    Returns the node, or None when sysfs does not tell (numa_node -1: single-node box or a container that hides it)."""
+    try:
+        dom_bus = pci_bus_id.lower()
+        node = int(open(f"/sys/bus/pci/devices/{dom_bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def cpu_reference(contigs_host, bases, offs, n_sample, cores, reps=1):
     """The reference's own CPU path on a bounded sample: oracle/_ref (kind 'reference') if it travelled, else the
     oracle port. Returns (dict(value reads/s, index_build_s, kind, cores, sample), checker, cords, cords_off): the
@@ -426,6 +449,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import linear_b200 as lb
     lb.load_library()
+    pci = None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        pci = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:  # noqa: BLE001
+        pass
+    numa_node = bind_to_gpu_numa(pci) if (pci and world > 1 and not os.environ.get("LNR_BENCH_NO_NUMA")) else None
 
     def barrier():
         if world > 1:
@@ -442,6 +472,15 @@ def main():
     genome = gen_genome(torch, dev, lens)
     ctx = lb.Context(local_rank)
     lens64 = [int(x) for x in lens]
+    comm = None
+    if world > 1:
+        def exchange_id(idb):   # rank 0's NCCL unique id to everybody (the library's communicator is its own)
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if idb is not None:
+                t.copy_(torch.frombuffer(bytearray(idb), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().numpy().tobytes())
+        comm = lb.Comm(ctx, rank, world, exchange_id)
     # ---- index build, inputs resident in HBM (genome features + DIndex = createFeatures + createIndexDynamic)
     def build_device_resident():
         g_ = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=lens64)
@@ -449,9 +488,9 @@ def main():
         if world == 1:
             i_ = lb.create_index(ctx, g_, 1, THREADS_SEM)
         else:
-            # hash-range sharded build: every rank builds 2^26/N buckets, one all-gather step over NVLink assembles them
-            from linear_b200 import sharding
-            i_ = sharding.build_index_sharded(lb, ctx, g_, THREADS_SEM, rank, world, torch, dist, dev)
+            # hash-range sharded build inside the C ABI: every rank builds 2^26/N buckets straight into its slice of the final
+            # arrays, one grouped NCCL exchange over NVLink completes them (lnr_index_build_sharded)
+            i_ = lb.create_index_sharded(ctx, g_, comm, 1, THREADS_SEM)
         torch.cuda.synchronize()
         return g_, f_, i_
 
@@ -505,6 +544,14 @@ def main():
     bases_pin = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)
     bases_pin.copy_(bases_t)
     bases_np = bases_pin.numpy()
+    # the same batch 2-bit packed (lnr_pack_dna5, the converter a shim calls once per read block), in pinned memory
+    packed_pin = torch.empty((total_bases + 3) // 4, dtype=torch.uint8, pin_memory=True)
+    packed_np = packed_pin.numpy()
+    has_n = C.c_int()
+    t0 = time.time()
+    lb.load_library().lnr_pack_dna5(C.c_void_p(bases_np.ctypes.data), total_bases, C.c_void_p(packed_np.ctypes.data), None, C.byref(has_n))
+    t_pack = time.time() - t0
+    assert not has_n.value
     n_str = max(1, args.streams)
     ctxs = [ctx] + [lb.Context(local_rank) for _ in range(n_str - 1)]
 
@@ -528,6 +575,10 @@ def main():
 
         def step_host(self):
             self.last = lb.apx_map_batch(self.ctx, index, feats, bases_np, offs, preset=1, cords_out=self.cords_np, cords_off_out=self.coff_np)
+
+        def step_packed(self):
+            self.last_packed = lb.apx_map_batch_packed(self.ctx, index, feats, packed_np, None, offs, preset=1, cords_out=self.cords_np,
+                                                       cords_off_out=self.coff_np)
 
     streams = [Stream(c) for c in ctxs]
 
@@ -562,13 +613,7 @@ def main():
     # ---- timed region: device-resident inputs
     for c in ctxs:
         c.set_profiling(False)
-    pci = None
-    try:
-        pr = torch.cuda.get_device_properties(local_rank)
-        pci = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-    except Exception:  # noqa: BLE001
-        pass
-    sampler = ClockSampler(local_rank, pci)
+    sampler = ClockSampler(local_rank, ("0000" + pci) if pci else None)
     if rank == 0:          # one sampler per job: the line reports rank 0's GPU
         sampler.start()
     run_steps("step_device", args.warmup * n_str)
@@ -582,6 +627,7 @@ def main():
             a = kt.get(k, (0.0, 0))
             kt[k] = (a[0] + v[0], a[1] + v[1])
     counters = ctx.counters()
+    diag = ctx.diag()
     stage_cycles = ctx.stage_cycles()
     n_cords = int(streams[0].ntot.value)
     value = world * n_reads * args.steps / dt
@@ -592,7 +638,28 @@ def main():
     dt_e2e = max_over_ranks(run_steps("step_host", args.steps))
     e2e_value = world * n_reads * args.steps / dt_e2e
     c_host, coff_host = streams[0].last
+    c_host = c_host.copy()
+    coff_host = coff_host.copy()
     d2h = int(len(c_host) * 8 + (n_reads + 1) * 8)
+    # ---- the same through the 2-bit packed call (a quarter of the upload)
+    run_steps("step_packed", n_str)
+    dt_packed = max_over_ranks(run_steps("step_packed", args.steps))
+    packed_value = world * n_reads * args.steps / dt_packed
+    packed_equal = bool(np.array_equal(streams[0].last_packed[1], coff_host) and np.array_equal(streams[0].last_packed[0], c_host))
+    # ---- host-side ceiling: what this box delivers when every rank only uploads its batch (pinned host -> HBM), all ranks at once
+    up = torch.empty(total_bases, dtype=torch.uint8, device=dev)
+    up.copy_(bases_pin, non_blocking=True)
+    barrier()
+    t0 = time.time()
+    for _ in range(4):
+        up.copy_(bases_pin, non_blocking=True)
+    torch.cuda.synchronize()
+    dt_up = max_over_ranks((time.time() - t0) / 4)
+    barrier()
+    del up
+    h2d_ceiling = {"GBps_per_rank": total_bases / dt_up / 1e9, "GBps_all_ranks": world * total_bases / dt_up / 1e9,
+                   "reads_per_s_if_upload_only": world * n_reads / dt_up, "numa_node_bound": numa_node,
+                   "what": "every rank uploads its batch (1 B/base, pinned) at the same time, nothing else running"}
     # ---- per-kernel times for the roofline: ONE host thread, so that an event pair brackets one kernel and not the other
     # threads' kernels interleaved with it (the 4-thread numbers above stay `value` / `e2e`)
     ctx.set_profiling(True)
@@ -696,10 +763,15 @@ def main():
             "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": total_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1000 * dt_e2e / args.steps},
+                    "ms_per_step": 1000 * dt_e2e / args.steps, "input": "Dna5, 1 byte/base (lnr_apxmap_batch)",
+                    "h2d_GBps_per_rank": total_bases / (dt_e2e / args.steps) / 1e9, "h2d_ceiling": h2d_ceiling},
+            "e2e_packed": {"value": packed_value, "unit": "reads/s", "h2d_bytes_per_step": (total_bases + 3) // 4 + (n_reads + 1) * 8,
+                           "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * dt_packed / args.steps,
+                           "input": "2-bit packed bases (lnr_apxmap_batch_packed)", "cords_equal_to_dna5_call": packed_equal,
+                           "host_pack_seconds_one_core": round(t_pack, 3)},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "index_build": index_info,
             "clocks": sampler.summary(), "ingest": ingest, "kernels": per_kernel, "kernels_one_thread": per_kernel_single,
-            "counters": counters, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
+            "counters": counters, "fallback_paths_last_batch": diag, "stage_cycles_last_batch": stage_cycles, "cords_per_step": n_cords,
             "bases_per_step": total_bases}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -52,10 +52,12 @@ int lnr_genome_from_device(lnr_ctx *, uint32_t n_contigs, const uint8_t * dev_co
 void lnr_genome_destroy(lnr_genome *);
 
 /* ---- genome features: createFeatures(StringSet<String<Dna5>>&, StringSet<FeaturesDynamic>&, int, unsigned)
- *      pmpfinder.cpp:775 -> createFeatures2_48 (parallel builder) :589.  feature_type 2 = 2-mer/48 (-f 2) */
+ *      pmpfinder.cpp:775 -> createFeatures2_48 (parallel builder) :589 for feature_type 2 = 2-mer/48 (-f 2), createFeatures1_32
+ *      :393 for feature_type 1 = 1-mer/32 (-f 1, one short per 16 bases). With -f 1 the reference leaves the last entries of
+ *      a string unwritten and reads up to 10 entries past its end; here both are defined as 0. */
 int lnr_features_build(lnr_ctx *, const lnr_genome *, int feature_type, unsigned threads_sem, lnr_feats ** out);
 int lnr_features_count(const lnr_feats *, uint32_t contig, uint64_t * n_entries);
-/* dst: int32[3*n] (int96 entries) for feature_type 2 */
+/* dst: int32[3*n] (int96 entries) for feature_type 2, int16[n] for feature_type 1 */
 int lnr_features_download(const lnr_feats *, uint32_t contig, void * dst, uint64_t cap_entries, uint64_t * n_entries);
 void lnr_features_destroy(lnr_feats *);
 
@@ -78,6 +80,21 @@ int lnr_index_export_hindex(const lnr_index *, uint64_t * ysa, uint64_t ysa_cap,
  * (one all-gather of counts, hs slices and dir slices) is done by the caller over NCCL on the device buffers below. */
 int lnr_index_build_shard(lnr_ctx *, const lnr_genome *, int index_type, unsigned threads_sem, unsigned shard, unsigned n_shards,
                           lnr_index ** out);
+/* The same build with the exchange inside the library (lnr_index_build_sharded). One lnr_comm per rank wraps
+ * an NCCL communicator: either created here from a unique id the caller distributes (lnr_nccl_unique_id on one rank,
+ * lnr_comm_create on all), or an existing ncclComm_t of the host program (lnr_comm_from_nccl; not destroyed by
+ * lnr_comm_destroy). NCCL is bound at run time (dlopen libnccl.so.2); LNR_E_UNSUPPORTED when it is not installed.
+ * lnr_index_build_sharded is collective: every rank calls it with the same genome and threads_sem. Rank r hashes the
+ * genome, keeps the minimizers of [r*2^26/n, (r+1)*2^26/n), learns all ranks' record counts (one 8-byte all-gather),
+ * builds its buckets directly inside its slice of the final hs / dir arrays, and one grouped exchange (in-place
+ * ncclBroadcast of every rank's hs slice and dir slice at their displacements -- no padding, no staging copy) completes
+ * the identical DIndex on every rank. index_type 1 only. */
+typedef struct lnr_comm lnr_comm;
+int lnr_nccl_unique_id(uint8_t id[128]);
+int lnr_comm_create(lnr_ctx *, const uint8_t id[128], int rank, int n_ranks, lnr_comm ** out);
+int lnr_comm_from_nccl(lnr_ctx *, void * nccl_comm /* ncclComm_t */, int rank, int n_ranks, lnr_comm ** out);
+void lnr_comm_destroy(lnr_comm *);
+int lnr_index_build_sharded(lnr_ctx *, const lnr_genome *, int index_type, unsigned threads_sem, lnr_comm *, lnr_index ** out);
 /* device-to-device copies of the index arrays (dev_dir: int32[2^26+1], dev_hs: uint64[>= n_hs]; either may be NULL) */
 int lnr_index_export_dindex_device(const lnr_index *, int32_t * dev_dir, uint64_t * dev_hs, uint64_t hs_cap);
 /* wraps assembled device arrays into an index (copies them) */
@@ -90,11 +107,11 @@ void lnr_index_destroy(lnr_index *);
  *     apxMap(index, read, anchors, crhit, f1, f2, apx_gaps, cords_str, cords_end, cords_info,
  *            f_chain=1, pm_g, pm_pmp);                                                   pmpfinder.cpp:2709
  * Reads with length <= 200 get an empty cord list (mapper.cpp:440). cords_end[i] = cords_str[i] +
- * ((W<<20)|W), W = lnr_params.window (96 for -f 2), is reconstructed by the caller (pmpfinder.cpp:2801). */
+ * ((W<<20)|W), W = 96 for -f 2 and 192 for -f 1, is reconstructed by the caller (pmpfinder.cpp:2801). */
 typedef struct lnr_params
 {
     int preset;       /* -p: 0 => thd_stop_chain_len_ratio 0.7, 1/2 => 0 (mapper.cpp:174-197); code default 1 */
-    int feature_type; /* -f: 2 */
+    int feature_type; /* -f: 2 or 1; 0 = whatever the genome features were built with */
     int reserved[6];
 } lnr_params;
 

@@ -30,7 +30,8 @@ EXPORTS = [
     "lnr_ctx_reset_kernel_times", "lnr_genome_upload", "lnr_genome_from_device", "lnr_genome_destroy",
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
-    "lnr_index_from_device", "lnr_index_destroy", "lnr_apxmap_batch", "lnr_apxmap_batch_packed", "lnr_pack_dna5",
+    "lnr_index_from_device", "lnr_index_destroy", "lnr_nccl_unique_id", "lnr_comm_create", "lnr_comm_from_nccl", "lnr_comm_destroy",
+    "lnr_index_build_sharded", "lnr_apxmap_batch", "lnr_apxmap_batch_packed", "lnr_pack_dna5",
     "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_diag", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
     "lnr_reads_parse", "lnr_reads_parse_device", "lnr_reads_info", "lnr_reads_download", "lnr_reads_device", "lnr_reads_destroy", "lnr_apxmap_reads",
 ]
@@ -89,6 +90,12 @@ def load_library() -> C.CDLL:
     lib.lnr_index_from_device.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(vp)]
     lib.lnr_index_destroy.argtypes = [vp]
     lib.lnr_index_destroy.restype = None
+    lib.lnr_nccl_unique_id.argtypes = [vp]
+    lib.lnr_comm_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.lnr_comm_from_nccl.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.lnr_comm_destroy.argtypes = [vp]
+    lib.lnr_comm_destroy.restype = None
+    lib.lnr_index_build_sharded.argtypes = [vp, vp, C.c_int, C.c_uint, vp, C.POINTER(vp)]
     lib.lnr_apxmap_batch.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, u64p, C.c_uint64,
                                      C.POINTER(DebugOut)]
     lib.lnr_apxmap_batch_packed.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, vp, u64p, vp, u64p, C.c_uint64,
@@ -214,7 +221,7 @@ class Features:
     def download(self, contig: int) -> np.ndarray:
         n = C.c_uint64()
         self.ctx.check(self.ctx.lib.lnr_features_count(self.h, contig, C.byref(n)))
-        out = np.zeros((n.value, 3), dtype=np.int32)
+        out = np.zeros((n.value, 1), dtype=np.int16) if self.feature_type == 1 else np.zeros((n.value, 3), dtype=np.int32)
         self.ctx.check(self.ctx.lib.lnr_features_download(self.h, contig, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
         return out
 
@@ -296,6 +303,43 @@ class Index:
             pass
 
 
+class Comm:
+    """One rank's NCCL communicator for lnr_index_build_sharded. `exchange_id(id_bytes or None) -> id_bytes` distributes
+    rank 0's 128-byte unique id to the other ranks (e.g. a torch.distributed broadcast); the library itself only needs NCCL."""
+
+    def __init__(self, ctx: Context, rank: int, n_ranks: int, exchange_id):
+        self.ctx = ctx
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            rc = ctx.lib.lnr_nccl_unique_id(buf)
+            if rc != 0:
+                raise LnrError(rc, "lnr_nccl_unique_id (libnccl.so.2 missing?)")
+        raw = exchange_id(bytes(buf) if rank == 0 else None)
+        idb = (C.c_uint8 * 128).from_buffer_copy(raw)
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.lnr_comm_create(ctx.h, idb, rank, n_ranks, C.byref(self.h)))
+        self.rank, self.n_ranks = rank, n_ranks
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.lnr_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def create_index_sharded(ctx, genome, comm: "Comm", index_type=1, threads=4) -> Index:
+    """createIndexDynamic across the ranks of `comm`: minimizer-range shards + one NCCL exchange (lnr_index_build_sharded)"""
+    h = C.c_void_p()
+    ctx.check(ctx.lib.lnr_index_build_sharded(ctx.h, genome.h, index_type, threads, comm.h, C.byref(h)))
+    ix = Index(ctx, genome, index_type, handle=h)
+    return ix
+
+
 def create_features(ctx, genome, feature_type=2, threads=4) -> Features:
     return Features(ctx, genome, feature_type, threads)
 
@@ -308,8 +352,9 @@ def read_features(ctx: Context, read: np.ndarray, feature_type: int = 2):
     read = np.ascontiguousarray(read, dtype=np.uint8)
     n = C.c_uint64()
     ctx.check(ctx.lib.lnr_read_features(ctx.h, read.ctypes.data_as(u8p), len(read), feature_type, None, None, 0, C.byref(n)))
-    f = np.zeros((n.value, 3), np.int32)
-    r = np.zeros((n.value, 3), np.int32)
+    shape, dt = ((n.value, 1), np.int16) if feature_type == 1 else ((n.value, 3), np.int32)
+    f = np.zeros(shape, dt)
+    r = np.zeros(shape, dt)
     if n.value:
         ctx.check(ctx.lib.lnr_read_features(ctx.h, read.ctypes.data_as(u8p), len(read), feature_type,
                                             f.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
@@ -433,5 +478,5 @@ def apx_map_batch_packed(ctx: Context, index: Index, feats: Features, packed: np
 
 
 def cords_end(cords_str: np.ndarray, window: int = 96) -> np.ndarray:
-    """cords_end[i] = cords_str[i] + ((W << 20) | W) (pmpfinder.cpp:2790-2801)."""
+    """cords_end[i] = cords_str[i] + ((W << 20) | W) (pmpfinder.cpp:2790-2801); W = 96 for -f 2, 192 for -f 1."""
     return cords_str + np.uint64((window << 20) | window)

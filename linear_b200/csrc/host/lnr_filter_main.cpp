@@ -135,7 +135,7 @@ int main(int argc, char ** argv)
     }
     if (pos.size() < 3 || pos[0] != "filter")
     {
-        fprintf(stderr, "usage: %s filter reads.fa genome.fa [-t N] [-p N] [-i 1] [-f 2] [-ot 1]\n", argv[0]);
+        fprintf(stderr, "usage: %s filter reads.fa genome.fa [-t N] [-p N] [-i 1|2] [-f 2|1] [-ot 1]\n", argv[0]);
         return 1;
     }
     const std::string rpath = pos[1], gpath = pos[2];
@@ -228,7 +228,7 @@ int main(int argc, char ** argv)
             if ((rc = lnr_apxmap_reads(ctx, ix, f2, &prm, R, (uint32_t)first, n, cords.data(), coff.data(), cords.size(), nullptr)))
                 return die("lnr_apxmap_reads", rc);
             main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
-            if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, 96);
+            if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, feature_t == 1 ? 192 : 96);
             n_reads_total += n;
             n_cords_total += coff.back();
         }
@@ -248,7 +248,7 @@ int main(int argc, char ** argv)
             if ((rc = lnr_apxmap_batch(ctx, ix, f2, &prm, (uint32_t)reads.size(), bases.data(), off.data(), cords.data(), coff.data(), cords.size(), nullptr)))
                 return die("lnr_apxmap_batch", rc);
             main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
-            if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, 96);
+            if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, feature_t == 1 ? 192 : 96);
             n_reads_total += reads.size();
             n_cords_total += coff.back();
         }

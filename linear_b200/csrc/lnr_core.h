@@ -81,6 +81,20 @@ LNR_HD u32 feat_count_genome(u64 len, unsigned T)                               
     return (u32)(((len - 48) >> 4) + 1);
 }
 
+// ---- 1-mer / 32-base features (-f 1, createFeatures1_32 pmpfinder.cpp:354 serial / :393 parallel) ------------------
+// one short per 16 bases: A + 32 C + 1024 G counts over the 32 bases from 16 i on. `written` = the entries the reference's
+// builder writes; the entries behind them, and everything past the end of a string, read as 0 (canonical rule).
+LNR_HD u32 feat32_count(u64 L) { return L >= 32 ? (u32)(((L - 32) >> 4) + 1) : 0; }
+LNR_HD u32 feat32_written_serial(u64 L) { if (L < 32) return 0; u64 lim = L - 32; return (u32)(1 + (lim > 16 ? (lim - 16 + 15) / 16 : 0)); }
+LNR_HD u32 feat32_written_parallel(u64 L) { return L >= 48 ? (u32)((L - 48) / 16) : 0; }
+template <class BaseFn>
+LNR_HD i16 feat32_entry(BaseFn base, i64 p0)
+{
+    int v = 0;
+    for (int k = 0; k < 32; k++) { int b = base(p0 + k); v += b == 0 ? 1 : (b == 1 ? 32 : (b == 2 ? 1024 : 0)); }
+    return (i16)v;
+}
+
 // ---- seeding task (getDIndexMatchAll, pmpfinder.cpp:1856): samples k = str + span + alpha*m - 1, m >= 1 ----
 struct SeedTask
 {

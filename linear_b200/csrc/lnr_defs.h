@@ -24,6 +24,7 @@ typedef uint32_t u32;
 typedef int32_t i32;
 typedef uint8_t u8;
 typedef uint16_t u16;
+typedef int16_t i16;
 
 // ---- encodings -------------------------------------------------------------------------------------
 static const u64 kAnchorZero = 1ULL << 20;            // const_anchor_zero (cords.cpp:8)
@@ -72,6 +73,8 @@ static const u32 kDirSize = (1u << 26) + 1;           // DIndex::fullSize index_
 static const int kIdxMinStep = 8, kIdxMaxStep = 10, kIdxOmit = 400;   // index_util.cpp:2551-2553
 static const int kMinReadLen = 200;                   // mapper.cpp:430
 static const int kWin = 96, kSup = 6, kMed = 5, kInf = 3, kWinThr = 36, kWinReject = 50;   // ApxMapParm2_48
+// ApxMapParm1_32 (-f 1, pmpfinder.cpp:199): cell 16 x 12 => window 192, sup 12, med ceil(.75 * 12), inf ceil(.5 * 12); same thresholds
+static const int kWin32 = 192, kSup32 = 12, kMed32 = 9, kInf32 = 6;
 
 // one int96 feature entry (std::array<int,3>, pmpfinder.h:71)
 struct F96 { i32 v[3]; };

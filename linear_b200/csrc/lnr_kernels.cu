@@ -25,6 +25,8 @@
 //   k_gather_cords                    per-read cords -> caller's concatenated layout
 //   lnr_ingest.cuh                    FASTA / FASTQ text -> ordinals, offsets, id spans (16 bytes per thread)
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -144,8 +146,8 @@ struct lnr_feats
     uint32_t n_contigs;
     std::vector<uint32_t> n;        // entries per contig
     std::vector<uint64_t> off;      // entry offset per contig
-    F96 * d_f;                      // owned, all contigs back to back
-    const F96 ** d_ptrs;            // device table of per-contig pointers
+    F96 * d_f;                      // owned, all contigs back to back (feature_type 1: the same buffer holds shorts)
+    const F96 ** d_ptrs;            // device table of per-contig pointers (feature_type 1: const i16 * behind the cast)
     u32 * d_n;                      // device table of counts
 };
 struct HNode;
@@ -406,6 +408,58 @@ __global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases
         if (!strand) feat_tile_reads<false>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
         else feat_tile_reads<true>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
         __syncthreads();                            // s_lo / s_hi are reused by the next tile
+    }
+}
+
+// ---- -f 1: 1-mer / 32-base features (createFeatures1_32 pmpfinder.cpp:354 serial / :393 parallel) --------------------
+// entry i = A + 32 C + 1024 G counts over the 32 bases from 16 i on, as a short (a count of 32 carries, the sum wraps:
+// part of the spec). One thread per 16-base cell, an entry is the sum of two neighbouring cells (through shared memory).
+// `written` = entries the reference's builder writes; the rest of the string is 0 (canonical rule, oracle/ref_harness.cpp).
+template <bool RC>
+__device__ __forceinline__ int feat32_cell(const u8 * __restrict__ s, i64 L, i64 c)   // cell c of the (reverse-complemented) sequence
+{
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+    {
+        const i64 p = 16 * c + k;
+        int b = 4;
+        if (p < L) { b = (int)__ldg(s + (RC ? L - 1 - p : p)); if (RC && b < 4) b = 3 - b; }
+        v += b == 0 ? 1 : (b == 1 ? 32 : (b == 2 ? 1024 : 0));
+    }
+    return v;
+}
+__global__ void __launch_bounds__(FT) k_feat32_genome(const u8 * __restrict__ g, i64 len, u32 n_written, i16 * __restrict__ out)
+{
+    __shared__ int s_c[FT];
+    const u32 e0 = blockIdx.x * (FT - 1);
+    const u32 c = e0 + threadIdx.x;
+    s_c[threadIdx.x] = c < n_written + 1 ? feat32_cell<false>(g, len, (i64)c) : 0;
+    __syncthreads();
+    if (threadIdx.x < FT - 1 && c < n_written) out[c] = (i16)(s_c[threadIdx.x] + s_c[threadIdx.x + 1]);
+}
+// reads: grid.x = tiles of (FT - 1) entries, grid.y = (read, strand); both strands' strings back to back at foff[r]
+__global__ void __launch_bounds__(FT) k_feat32_reads(const u8 * __restrict__ bases, const u64 * __restrict__ read_off, const u64 * __restrict__ foff,
+                                                    const u32 * __restrict__ ftile, const u32 * __restrict__ tile_read, u32 n_tiles, i16 * __restrict__ out)
+{
+    __shared__ int s_c[FT];
+    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        const u32 r = tile_read[tile];
+        const u64 L = read_off[r + 1] - read_off[r];
+        const u32 nf = feat32_count(L), nw = feat32_written_serial(L);
+        const u32 tps = (nf + (FT - 1) - 1) / (FT - 1);
+        const u32 t = tile - ftile[r];
+        const u32 strand = t >= tps ? 1u : 0u;
+        const u32 c = (t - strand * tps) * (FT - 1) + threadIdx.x;
+        const u8 * s = bases + read_off[r];
+        int v = 0;
+        if (c < nw + 1) v = strand ? feat32_cell<true>(s, (i64)L, (i64)c) : feat32_cell<false>(s, (i64)L, (i64)c);
+        s_c[threadIdx.x] = v;
+        __syncthreads();
+        i16 * o = out + foff[r] + (u64)strand * nf;
+        if (threadIdx.x < FT - 1 && c < nf) o[c] = c < nw ? (i16)(s_c[threadIdx.x] + s_c[threadIdx.x + 1]) : (i16)0;
+        __syncthreads();
     }
 }
 
@@ -707,22 +761,20 @@ __device__ __forceinline__ u32 find_task(const SeedTask * tasks, u32 n_tasks, u6
     return lo;
 }
 
-// Fast path of seed_sample (lnr_core.h) for the common sample: a pure 21-base window (>= span steps after hashInit)
-// whose 4 bases of context on either side lie inside the read, and no N among those 29 bases. The bases are fetched as
-// 8 aligned words, packed to 2 bits each (one multiply per 4 bases), and the forward hash, the reverse-complement
-// hash (bit reversal), the selector sum (popcounts), the leftmost minimal 13-mer (min over offset-tagged keys) and
-// both flank keys are derived from that 58-bit value. Returns false when the sample needs the general evaluation.
-__device__ __forceinline__ bool seed_sample_fast(const u8 * __restrict__ rd, i64 L, const SeedTask & t, u32 m, SeedVal & sv)
+// Fast evaluation of one pure 21-base window (>= span steps after hashInit) whose 4 bases of context on either side are
+// readable and free of N: the 32 bytes around it are fetched as 8 aligned words (global memory or a staged shared-memory
+// tile), packed to 2 bits each (one multiply per 4 bases), and the forward hash, the reverse-complement hash (bit
+// reversal), the selector sum (popcounts), the leftmost minimal 13-mer (min over offset-tagged keys) and both flank
+// keys are derived from that 58-bit value -- ~120 instead of ~500 instructions. q points at window start - 4; the words
+// [q & ~3, (q & ~3) + 32) must be readable. Returns false when one of the 29 bases is an N.
+template <bool SMEM>
+__device__ __forceinline__ bool window_fast(const u8 * q, int bias, SeedVal & sv)
 {
-    const i64 k0 = (i64)t.str + kSpanD;
-    const i64 p = k0 + (i64)t.alpha * m - 1;
-    if (p - k0 + 1 < kSpanD || p < 8 || p + 28 > L) return false;
-    const u8 * q = rd + p - 4;
     const unsigned sh = ((unsigned)(uintptr_t)q & 3u) * 8u;
     const u32 * pw = (const u32 *)((uintptr_t)q & ~(uintptr_t)3);
     u32 w[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) w[i] = __ldg(pw + i);
+    for (int i = 0; i < 8; i++) w[i] = SMEM ? pw[i] : __ldg(pw + i);
     u32 A[8], any = 0;
 #pragma unroll
     for (int i = 0; i < 7; i++) A[i] = __funnelshift_r(w[i], w[i + 1], sh);
@@ -743,7 +795,7 @@ __device__ __forceinline__ bool seed_sample_fast(const u8 * __restrict__ rd, i64
     const u64 Pc = ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
     const u64 cr = (Pc >> 8) & M42;
     const int sum = __popcll(h & 0x5555555555555555ULL) + 2 * __popcll(h & 0xAAAAAAAAAAAAAAAAULL);
-    const int x = 2 * sum - 3 * kSpanD + t.bias;
+    const int x = 2 * sum - 3 * kSpanD + bias;
     const u32 strand = x > 0 ? 0u : 1u;
     const u64 v2 = strand ? cr : h;
     u32 best = 0xffffffffu;
@@ -761,6 +813,334 @@ __device__ __forceinline__ bool seed_sample_fast(const u8 * __restrict__ rd, i64
     sv.Y = strand ? (u32)(Pc >> (2 * (8 - off))) & 0xffu : (u32)(P >> (2 * (11 - off))) & 0xffu;
     return true;
 }
+// read seeding: sample m of a task (seed_sample, lnr_core.h); false = the sample needs the general evaluation
+__device__ __forceinline__ bool seed_sample_fast(const u8 * __restrict__ rd, i64 L, const SeedTask & t, u32 m, SeedVal & sv)
+{
+    const i64 k0 = (i64)t.str + kSpanD;
+    const i64 p = k0 + (i64)t.alpha * m - 1;
+    if (p - k0 + 1 < kSpanD || p < 8 || p + 28 > L) return false;
+    return window_fast<false>(rd + p - 4, t.bias, sv);
+}
+// =====================================================================================================
+// DIndex build, second design (round 2): hash ONCE, partition, then count / place / sort inside L2.
+//   k_idx_emit       CTA = 1024 consecutive samples of a chunk; the 9.3 KB genome tile arrives in shared memory as one
+//                    TMA bulk copy (cp.async.bulk + mbarrier); samples take the packed fast path from the tile; emit rule
+//                    by block max-scan; every sample slot gets (X | invalid, record) -- dense, 16/32-byte stores. Every
+//                    32nd tile also feeds a 4096-bin histogram of X >> 14, from which the host picks 64 splitters of
+//                    ~equal record count (the minimizer distribution is skewed towards small X and genome dependent)
+//   k_idx_partcount  exact number of pairs per partition
+//   k_idx_part       pairs -> the 64 partitions, staged per CTA in shared memory so that every partition receives
+//                    contiguous runs
+//   k_idx_count      cnt[X]++ over the partitioned pairs: one launch, CTAs walk the partitions in order, so the atomics
+//                    of the CTAs in flight fall into a window of cnt that L2 holds (the first design's histogram pass
+//                    dirtied one 32-byte sector per sample: 11 GB of write-backs)
+//   k_scan_*         bucket omission + exclusive scan -> dir (unchanged)
+//   k_idx_place      per partition: record -> staging[dir[X] + slot]; the partition's range (~43 MB) stays in L2, so the
+//                    random 8-byte stores combine there instead of each costing a DRAM read-modify-write
+//   k_idx_rank       per partition, right behind its place kernel (L2-hot): every record counts the smaller records of
+//                    its bucket and moves to that rank of hs (ascending order inside a bucket), its Y byte into hsy
+//   k_idx_dirx       the lookup sectors of the seeding pass, one streaming pass at the end
+// The first design (two hashing passes + atomic scatter + one thread-per-bucket sort from DRAM) moved 70 GB of DRAM traffic
+// in its scatter alone (profiles/r2_ncu_idx_full_summary.txt).
+// =====================================================================================================
+static const int IPARTS = 64;
+static const int ICOARSE_SHIFT = 14, ICOARSE = 1 << (kDirBits - ICOARSE_SHIFT);   // 4096 coarse bins for the splitters
+struct IdxParts { u32 split[IPARTS + 1]; };   // partition p holds X in [split[p], split[p+1])
+
+__device__ __forceinline__ u32 smem_u32(const void * p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 * bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void * dst_smem, const void * src_gmem, u32 bytes, u64 * bar)
+{
+    // one thread: arm the barrier with the byte count, then one bulk async copy global -> shared (TMA, UBLKCP)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 * bar, u32 parity)
+{
+    asm volatile("{\n .reg .pred p;\n LNR_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra LNR_DONE;\n bra LNR_WAIT;\n LNR_DONE:\n}" ::"r"(
+                     smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ u32 idx_part_of(const u32 * split, u32 X)
+{
+    u32 lo = 0;
+#pragma unroll
+    for (int step = IPARTS / 2; step; step >>= 1)
+        if (split[lo + step] <= X) lo += step;
+    return lo;
+}
+
+// the general evaluation (chunk starts, N, contig ends) is rare: one out-of-line copy keeps the kernel's hot code small
+__device__ __noinline__ void idx_sample_slow(const u8 * gs, const IdxChunk & ch, i64 m, u32 & X, u64 & rec)
+{
+    GAcc ga = {gs, ch.len};
+    idx_sample(ga, ch, m, X, rec);
+}
+// sample m of a chunk from the staged tile (fast path) or through the bounds-checked accessor
+__device__ __forceinline__ void idx_sample_tile(const u8 * s_b, i64 p0, i64 p1, const TileAcc & acc, const IdxChunk & ch, i64 m, u32 & X, u64 & rec)
+{
+    const i64 j = ch.t_str + kIdxMinStep + 9 * m;
+    SeedVal sv;
+    if (j - ch.t_str + 1 >= kSpanD && j - 4 >= p0 && j + 28 <= p1 && window_fast<true>(s_b + (j - 4 - p0), ch.bias, sv))
+    {
+        X = sv.X;
+        rec = create_cord(ch.contig, (u64)j + kAnchorZero, sv.Y, sv.strand);
+        return;
+    }
+    idx_sample_slow(acc.g, ch, m, X, rec);
+}
+__device__ __forceinline__ u32 idx_sample_x_global(const u8 * gs, const IdxChunk & ch, i64 m)
+{
+    const i64 j = ch.t_str + kIdxMinStep + 9 * m;
+    SeedVal sv;
+    if (j - ch.t_str + 1 >= kSpanD && j >= 8 && j + 28 <= ch.len && window_fast<false>(gs + j - 4, ch.bias, sv)) return sv.X;
+    u32 X; u64 r;
+    idx_sample_slow(gs, ch, m, X, r);
+    return X;
+}
+
+__global__ void __launch_bounds__(IT) k_idx_emit(const u8 * __restrict__ g, const IdxChunk * __restrict__ chunks,
+                                                 const u32 * __restrict__ tile0, u32 n_chunks, u32 * __restrict__ pairX,
+                                                 u64 * __restrict__ pairRec, u32 x_lo, u32 x_hi, u32 * __restrict__ coarse)
+{
+    // [x_lo, x_hi): minimizer range owned by this shard (multi-GPU build partitions the 2^26 buckets)
+    __shared__ __align__(128) u8 s_b[(ISM + 15 + 16) & ~15];
+    __shared__ __align__(8) u64 s_bar;
+    __shared__ i32 s_warp[IT / 32];
+    __shared__ u32 s_last[IT / 32];
+    __shared__ i32 s_back;
+    const u32 tile = blockIdx.x;
+    u32 lo = 0, hi = n_chunks;
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tile0[mid] <= tile) lo = mid; else hi = mid; }
+    const IdxChunk ch = chunks[lo];
+    const u8 * gs = g + ch.base_off;
+    const i64 m0 = (i64)(tile - tile0[lo]) * ITILE;
+    const i64 nm = ch.n_samples - m0 < ITILE ? ch.n_samples - m0 : ITILE;
+    // stage bases [p0, p1): p0 16-byte aligned (contigs start at 256-byte aligned offsets), the copy length rounded up to
+    // 16 -- at most 15 bytes into the >= 256 zero bytes behind the contig
+    const i64 j0 = ch.t_str + kIdxMinStep + 9 * m0;
+    i64 p0 = (j0 - 8) & ~15LL;
+    if (p0 < 0) p0 = 0;
+    i64 p1 = j0 + 9 * nm + 32;
+    if (p1 > ch.len) p1 = ch.len;
+    const u32 nbytes = (u32)((p1 - p0 + 15) & ~15LL);
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) tma_load_1d(s_b, gs + p0, nbytes, &s_bar);
+    // while the tile is in flight: look-back of the tile's first sample (consecutive earlier samples with the same X);
+    // it needs X of sample m0, which lane 0 takes from global memory like the earlier ones
+    if (threadIdx.x < 32)
+    {
+        i32 back = 0;
+        if (m0 > 0)
+        {
+            u32 X0 = 0;
+            if (threadIdx.x == 0) X0 = idx_sample_x_global(gs, ch, m0);
+            X0 = __shfl_sync(0xffffffffu, X0, 0);
+            i64 m = m0 - 1;
+            while (true)
+            {
+                i64 mm = m - threadIdx.x;
+                bool same = false;
+                if (mm >= 0) same = idx_sample_x_global(gs, ch, mm) == X0;
+                u32 neq = __ballot_sync(0xffffffffu, !same);
+                if (neq) { back += __ffs((int)neq) - 1; break; }
+                back += 32; m -= 32;
+            }
+        }
+        if (threadIdx.x == 0) s_back = back;
+    }
+    mbar_wait(&s_bar, 0);
+    TileAcc acc = {s_b, p0, p1, gs, ch.len};
+    // each thread: IS consecutive samples
+    u32 X[IS]; u64 rec[IS];
+    const i64 mt = m0 + (i64)threadIdx.x * IS;
+#pragma unroll
+    for (int q = 0; q < IS; q++)
+    {
+        X[q] = 0xffffffffu; rec[q] = 0;
+        if ((i64)threadIdx.x * IS + q < nm) idx_sample_tile(s_b, p0, p1, acc, ch, mt + q, X[q], rec[q]);
+    }
+    // X of the sample just before this thread's first one
+    u32 xprev = __shfl_up_sync(0xffffffffu, X[IS - 1], 1);
+    if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = X[IS - 1];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) xprev = threadIdx.x == 0 ? 0xfffffffeu : s_last[(threadIdx.x >> 5) - 1];
+    // run start (tile-relative sample index; negative = before the tile) by max-scan
+    const i32 local_i = (i32)threadIdx.x * IS;
+    i32 rs[IS];
+    i32 run = -0x40000000;   // "unknown, inherited"
+    {
+        u32 xp = xprev;
+#pragma unroll
+        for (int q = 0; q < IS; q++)
+        {
+            bool brk = X[q] != xp;
+            if (threadIdx.x == 0 && q == 0) brk = false;   // resolved through s_back
+            if (brk) run = local_i + q;
+            rs[q] = run;
+            xp = X[q];
+        }
+    }
+    i32 v = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { i32 t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v = max(v, t); }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    i32 carry = -0x40000000;
+    for (int wq = 0; wq < (int)(threadIdx.x >> 5); wq++) carry = max(carry, s_warp[wq]);
+    i32 excl = __shfl_up_sync(0xffffffffu, v, 1);
+    if ((threadIdx.x & 31) == 0) excl = -0x40000000;
+    excl = max(excl, carry);
+    const i32 tile_start_run = -s_back;   // run start of sample 0 (<= 0)
+    u32 ox[IS];
+#pragma unroll
+    for (int q = 0; q < IS; q++)
+    {
+        const i32 r = rs[q] > -0x40000000 ? rs[q] : (excl > -0x40000000 ? excl : tile_start_run);
+        const i32 idx = local_i + q;
+        const bool emit = idx < nm && (((idx - r) & 1) == 0) && X[q] >= x_lo && X[q] < x_hi;
+        ox[q] = emit ? X[q] : 0xffffffffu;
+        if (emit && (tile & 31u) == 0) atomicAdd(&coarse[X[q] >> ICOARSE_SHIFT], 1u);   // a 1/32 sample is plenty for the splitters
+    }
+    // the tile's slots: 16 bytes of X and 32 bytes of records per thread
+    const u64 slot = (u64)tile * ITILE + (u64)local_i;
+    *(uint4 *)(pairX + slot) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
+    *(ulonglong2 *)(pairRec + slot) = make_ulonglong2(rec[0], rec[1]);
+    *(ulonglong2 *)(pairRec + slot + 2) = make_ulonglong2(rec[2], rec[3]);
+}
+
+// exact number of pairs per partition (one pass over the X column)
+__global__ void __launch_bounds__(256) k_idx_partcount(const u32 * __restrict__ pairX, u64 n_slots, IdxParts parts, unsigned long long * __restrict__ part_cnt)
+{
+    __shared__ u32 s_split[IPARTS + 1];
+    __shared__ u32 s_pc[IPARTS];
+    if (threadIdx.x < IPARTS + 1) s_split[threadIdx.x] = parts.split[threadIdx.x];
+    if (threadIdx.x < IPARTS) s_pc[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 n4 = n_slots / 4;     // n_slots is a multiple of the tile size
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (u64)gridDim.x * blockDim.x)
+    {
+        const uint4 v = __ldg((const uint4 *)pairX + i);
+        const u32 xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (xs[q] != 0xffffffffu) atomicAdd(&s_pc[idx_part_of(s_split, xs[q])], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < IPARTS && s_pc[threadIdx.x]) atomicAdd(&part_cnt[threadIdx.x], (unsigned long long)s_pc[threadIdx.x]);
+}
+// histogram of the partitioned pairs (see the header comment)
+__global__ void __launch_bounds__(256) k_idx_count(const u32 * __restrict__ X, u64 n, u32 * __restrict__ cnt)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[__ldg(X + i)], 1u);
+}
+
+static const int PT = 256, PI = 8, PTILE = PT * PI;
+__global__ void __launch_bounds__(PT) k_idx_part(const u32 * __restrict__ pairX, const u64 * __restrict__ pairRec, u64 n_slots, IdxParts parts,
+                                                 const u64 * __restrict__ part_off, unsigned long long * __restrict__ part_fill,
+                                                 u32 * __restrict__ outX, u64 * __restrict__ outRec)
+{
+    __shared__ u32 s_split[IPARTS + 1];
+    __shared__ u32 s_cnt[IPARTS], s_start[IPARTS + 1];
+    __shared__ u64 s_gbase[IPARTS];
+    __shared__ u32 sX[PTILE];
+    __shared__ u64 sRec[PTILE];
+    __shared__ u8 sP[PTILE];
+    if (threadIdx.x < IPARTS + 1) s_split[threadIdx.x] = parts.split[threadIdx.x];
+    if (threadIdx.x < IPARTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * PTILE;
+    u32 x[PI], rk[PI], pp[PI]; u64 rc[PI];
+#pragma unroll
+    for (int i = 0; i < PI; i++)
+    {
+        const u64 idx = base + (u64)i * PT + threadIdx.x;
+        x[i] = idx < n_slots ? __ldg(pairX + idx) : 0xffffffffu;
+        pp[i] = 0xffu; rk[i] = 0; rc[i] = 0;
+        if (x[i] != 0xffffffffu)
+        {
+            rc[i] = __ldg(pairRec + idx);
+            pp[i] = idx_part_of(s_split, x[i]);
+            rk[i] = atomicAdd(&s_cnt[pp[i]], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        // exclusive scan of the 64 counts (2 per lane), then one global claim per non-empty partition
+        const u32 c0 = s_cnt[2 * threadIdx.x], c1 = s_cnt[2 * threadIdx.x + 1];
+        u32 incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (threadIdx.x >= (unsigned)o) incl += t; }
+        const u32 ex = incl - c0 - c1;
+        s_start[2 * threadIdx.x] = ex; s_start[2 * threadIdx.x + 1] = ex + c0;
+        if (threadIdx.x == 31) s_start[IPARTS] = incl;
+        if (c0) s_gbase[2 * threadIdx.x] = part_off[2 * threadIdx.x] + atomicAdd(&part_fill[2 * threadIdx.x], (unsigned long long)c0);
+        if (c1) s_gbase[2 * threadIdx.x + 1] = part_off[2 * threadIdx.x + 1] + atomicAdd(&part_fill[2 * threadIdx.x + 1], (unsigned long long)c1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PI; i++)
+        if (pp[i] != 0xffu)
+        {
+            const u32 o = s_start[pp[i]] + rk[i];
+            sX[o] = x[i]; sRec[o] = rc[i]; sP[o] = (u8)pp[i];
+        }
+    __syncthreads();
+    const u32 total = s_start[IPARTS];
+    for (u32 i = threadIdx.x; i < total; i += PT)
+    {
+        const u32 q = sP[i];
+        const u64 d = s_gbase[q] + (i - s_start[q]);
+        outX[d] = sX[i];
+        outRec[d] = sRec[i];
+    }
+}
+
+// records of one partition -> their buckets, in arrival order, into a staging copy of hs (tmp) together with their X
+__global__ void __launch_bounds__(256) k_idx_place(const u32 * __restrict__ X, const u64 * __restrict__ rec, u64 n, const i32 * __restrict__ dir,
+                                                   u32 * __restrict__ fill, u64 * __restrict__ tmp, u32 * __restrict__ tmpx)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 x = __ldg(X + i);
+    const i32 b = __ldg(dir + x), e = __ldg(dir + x + 1);
+    if (e > b)
+    {
+        const u64 o = (u64)b + atomicAdd(&fill[x], 1u);
+        tmp[o] = __ldg(rec + i);
+        tmpx[o] = x;
+    }
+}
+// ascending order inside each bucket (index_util.cpp:1788-1796) by rank: one thread per staged record counts the records
+// of its bucket that are smaller (records are distinct) and stores itself at that rank of the final hs, its Y byte next to
+// it. Neighbouring threads mostly share a bucket, so the bucket is read once per warp, from L2 (the partition was staged a
+// moment ago); the work per bucket is n^2 compares, but uniform and parallel -- a thread-per-bucket insertion sort spent
+// 10 ms of the build diverging.
+__global__ void __launch_bounds__(256) k_idx_rank(const u64 * __restrict__ tmp, const u32 * __restrict__ tmpx, u64 p0, u64 n, const i32 * __restrict__ dir,
+                                                  u64 * __restrict__ hs, u8 * __restrict__ hsy)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 o = p0 + i;
+    const u64 r = tmp[o];
+    const u32 x = tmpx[o];
+    const i32 b = __ldg(dir + x), e = __ldg(dir + x + 1);
+    u32 rank = 0;
+    for (i32 k = b; k < e; k++) rank += tmp[k] < r ? 1u : 0u;
+    hs[(u64)b + rank] = r;
+    if (hsy) hsy[(u64)b + rank] = (u8)(r & 0xff);
+}
+
 // One thread per sample; a warp owns 32 consecutive samples. A sample whose X differs from the previous sample's X
 // (xpre rule, :1882) fetches its bucket's lookup sector and scans the Y keys. The matches of the warp are written, in
 // sample order, as one contiguous run of 32-bit entries (hs index | query strand << 31) claimed with ONE atomic per warp
@@ -1005,8 +1385,9 @@ struct ReadSlot
 struct MapArgs
 {
     const u64 * read_off; const u8 * bases; u32 n_reads;
-    const F96 * feats; const u64 * foff;               // read features
+    const F96 * feats; const u64 * foff;               // read features (feature_type 1: shorts behind the cast)
     const F96 * const * f2; const u32 * nf2;           // genome features
+    int ft; u32 win;                                   // feature type (2 = 2_48, 1 = 1_32) and its window size
     const SeedTask * tasks; u32 n_tasks;               // seeding tasks of this pass
     const u64 * aoff;                                  // anchor offsets per sample (+ n_samples sentinel entry)
     u64 * A; u64 * B;
@@ -1037,10 +1418,21 @@ __device__ __forceinline__ void fill_pipe_in(const MapArgs & a, u32 r, PipeIn & 
     u64 L = a.read_off[r + 1] - a.read_off[r];
     in.read = a.bases + a.read_off[r];
     in.L = (u32)L;
-    in.nf1 = feat_count_read(L);
-    in.f1[0] = a.feats + a.foff[r];
-    in.f1[1] = in.f1[0] + in.nf1;
-    in.f2 = a.f2; in.nf2 = a.nf2;
+    in.ft = a.ft; in.win = a.win;
+    in.f1[0] = in.f1[1] = nullptr; in.s1[0] = in.s1[1] = nullptr;
+    if (a.ft == 1)
+    {
+        in.nf1 = feat32_count(L);
+        in.s1[0] = (const i16 *)a.feats + a.foff[r];
+        in.s1[1] = in.s1[0] + in.nf1;
+    }
+    else
+    {
+        in.nf1 = feat_count_read(L);
+        in.f1[0] = a.feats + a.foff[r];
+        in.f1[1] = in.f1[0] + in.nf1;
+    }
+    in.f2 = a.f2; in.s2 = (const i16 * const *)a.f2; in.nf2 = a.nf2;
     in.stop_ratio = a.stop_ratio;
 }
 
@@ -1059,13 +1451,13 @@ __device__ __forceinline__ bool alloc_finish(Arena & ar, FinishBufs & f, int n)
     return !ar.failed;
 }
 // finish a read (all lanes): gather blocks again if it was re-mapped, then chainBlocksCords + flags
-__device__ __noinline__ void finish_read(const Warp & w, FinishBufs & f, u64 L, u64 * cords, int & nc, Blk * sep_in, int n_sep_in, bool regather)
+__device__ __noinline__ void finish_read(const Warp & w, FinishBufs & f, u64 L, u64 * cords, int & nc, Blk * sep_in, int n_sep_in, bool regather, u32 win)
 {
     int n_sep;
     if (regather)
     {
         int dummy = 0;
-        n_sep = gather_blocks_w(w, cords, nc, (YPair *)0, dummy, f.sp1, L, 1000, kWin, 1);
+        n_sep = gather_blocks_w(w, cords, nc, (YPair *)0, dummy, f.sp1, L, 1000, win, 1);
     }
     else
     {
@@ -1073,7 +1465,7 @@ __device__ __noinline__ void finish_read(const Warp & w, FinishBufs & f, u64 L, 
         for (int i = w.lane; i < n_sep; i += 32) f.sp1[i] = sep_in[i];
         __syncwarp();
     }
-    phase_finish_w(w, L, cords, nc, f.sp1, n_sep, f.sp2, f.sc1, f.sc2, f.s1, f.s2, f.tmp);
+    phase_finish_w(w, L, cords, nc, f.sp1, n_sep, f.sp2, f.sc1, f.sc2, f.s1, f.s2, f.tmp, win);
     nc = __shfl_sync(0xffffffffu, nc, 0);
     __syncwarp();
 }
@@ -1525,7 +1917,7 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
             }
             int remap = 0, n_sep = 0, n_gaps = 0;
             u32 task0 = 0;
-            remap = phase_mid_w(w, L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap);
+            remap = phase_mid_w(w, L, cords, nc, str_ends, sep, n_sep, gaps, n_gaps, gcap, a.win);
             if (w.lane == 0 && remap == 1)
             {
                 task0 = atomicAdd(a.n_tasks2, (u32)n_gaps);
@@ -1545,7 +1937,7 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
             __syncwarp();
             if (remap < 0) rc = 1;
             LNR_LAP(cnt, 9, tl);
-            if (!rc && remap == 0) finish_read(w, fb, L, cords, nc, sep, n_sep, false);
+            if (!rc && remap == 0) finish_read(w, fb, L, cords, nc, sep, n_sep, false, a.win);
             LNR_LAP(cnt, 10, tl);
             slot.n_cords = rc ? 0 : (u32)nc;
             slot.status = rc ? 2u : (remap == 1 ? 1u : 0u);
@@ -1554,7 +1946,7 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
         }
         else
         {
-            finish_read(w, fb, L, cords, nc, (Blk *)0, 0, true);
+            finish_read(w, fb, L, cords, nc, (Blk *)0, 0, true, a.win);
             LNR_LAP(cnt, 10, tl);
             slot.n_cords = (u32)nc;
             slot.status = 0u;
@@ -1934,30 +2326,37 @@ void lnr_genome_destroy(lnr_genome * g)
 int lnr_features_build(lnr_ctx * ctx, const lnr_genome * g, int feature_type, unsigned threads_sem, lnr_feats ** out)
 {
     if (!ctx || !g || !out || threads_sem == 0) return LNR_E_ARG;
-    if (feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "only feature_type 2 (2-mer/48, -f 2) is implemented");
+    if (feature_type != 2 && feature_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type must be 2 (2-mer/48, -f 2) or 1 (1-mer/32, -f 1)");
     cudaSetDevice(ctx->device);
+    const size_t esz = feature_type == 1 ? sizeof(i16) : sizeof(F96);
     lnr_feats * f = new lnr_feats();
     f->ctx = ctx; f->feature_type = feature_type; f->n_contigs = g->n_contigs; f->d_f = nullptr; f->d_ptrs = nullptr; f->d_n = nullptr;
     uint64_t tot = 0;
     for (uint32_t i = 0; i < g->n_contigs; i++)
     {
-        uint32_t n = feat_count_genome(g->len[i], threads_sem);
+        uint32_t n = feature_type == 1 ? feat32_count(g->len[i]) : feat_count_genome(g->len[i], threads_sem);
         f->n.push_back(n);
         f->off.push_back(tot);
-        tot += n + 8;   // a little slack between contigs
+        tot += (n + 8 + 7) & ~7ull;   // a little slack between contigs; strings stay 16-byte aligned for either entry size
     }
-    CK(cudaMalloc(&f->d_f, (tot + 8) * sizeof(F96)));
-    CK(cudaMemsetAsync(f->d_f, 0, (tot + 8) * sizeof(F96), ctx->stream));
+    CK(cudaMalloc(&f->d_f, (tot + 8) * esz));
+    CK(cudaMemsetAsync(f->d_f, 0, (tot + 8) * esz, ctx->stream));
     CK(cudaMalloc(&f->d_ptrs, g->n_contigs * sizeof(F96 *)));
     CK(cudaMalloc(&f->d_n, g->n_contigs * sizeof(u32)));
     std::vector<const F96 *> ptrs;
-    for (uint32_t i = 0; i < g->n_contigs; i++) ptrs.push_back(f->d_f + f->off[i]);
+    for (uint32_t i = 0; i < g->n_contigs; i++) ptrs.push_back((const F96 *)((const u8 *)f->d_f + f->off[i] * esz));
     CK(cudaMemcpyAsync(f->d_ptrs, ptrs.data(), ptrs.size() * sizeof(F96 *), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f->d_n, f->n.data(), f->n.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     for (uint32_t i = 0; i < g->n_contigs; i++)
     {
         if (!f->n[i]) continue;
         LaunchScope ls(ctx, "k_feat_genome");
+        if (feature_type == 1)
+        {
+            const u32 nw = feat32_written_parallel(g->len[i]);   // the entries behind stay 0 (canonical rule)
+            if (nw) k_feat32_genome<<<(nw + (FT - 1) - 1) / (FT - 1), FT, 0, ctx->stream>>>(g->d_bases + g->off[i], (i64)g->len[i], nw, (i16 *)f->d_f + f->off[i]);
+            continue;
+        }
         u32 grid = (f->n[i] + FE - 1) / FE;
         k_feat_genome<<<grid, FT, 0, ctx->stream>>>(g->d_bases + g->off[i], (i64)g->len[i], f->n[i], f->d_f + f->off[i]);
     }
@@ -1980,7 +2379,8 @@ int lnr_features_download(const lnr_feats * f, uint32_t contig, void * dst, uint
     if (n_entries) *n_entries = f->n[contig];
     if (!dst) return LNR_OK;
     if (cap_entries < f->n[contig]) return fail(ctx, LNR_E_CAPACITY, "feature buffer too small");
-    CK(cudaMemcpy(dst, f->d_f + f->off[contig], (size_t)f->n[contig] * sizeof(F96), cudaMemcpyDeviceToHost));
+    const size_t esz = f->feature_type == 1 ? sizeof(i16) : sizeof(F96);
+    CK(cudaMemcpy(dst, (const u8 *)f->d_f + f->off[contig] * esz, (size_t)f->n[contig] * esz, cudaMemcpyDeviceToHost));
     return LNR_OK;
 }
 void lnr_features_destroy(lnr_feats * f)
@@ -1991,6 +2391,119 @@ void lnr_features_destroy(lnr_feats * f)
     if (f->d_ptrs) cudaFree((void *)f->d_ptrs);
     if (f->d_n) cudaFree(f->d_n);
     delete f;
+}
+
+// ---- multi-GPU index build over NCCL ---------------------------------------------------------------------
+// NCCL is bound at run time (dlopen of libnccl.so.2: in a torch.distributed process that is the library already loaded,
+// in a plain C++ host the system one), so liblnr_b200.so has no link-time dependency on it.
+namespace {
+typedef struct ncclComm * nccl_comm_t;
+struct NcclUid { char internal[128]; };
+struct NcclApi
+{
+    void * lib = nullptr;
+    int (*GetUniqueId)(NcclUid *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char * (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi & nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char * name : {"libnccl.so.2", "libnccl.so"})
+        {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+#define LNR_NCCL_SYM(field, sym) *(void **)(&api.field) = dlsym(api.lib, sym)
+        LNR_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); LNR_NCCL_SYM(CommInitRank, "ncclCommInitRank"); LNR_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+        LNR_NCCL_SYM(AllGather, "ncclAllGather"); LNR_NCCL_SYM(Broadcast, "ncclBroadcast"); LNR_NCCL_SYM(GroupStart, "ncclGroupStart");
+        LNR_NCCL_SYM(GroupEnd, "ncclGroupEnd"); LNR_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef LNR_NCCL_SYM
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GroupStart && api.GroupEnd;
+    });
+    return api;
+}
+const int kNcclInt32 = 2, kNcclUint64 = 5;   // ncclDataType_t values (nccl.h)
+}  // namespace
+
+struct lnr_comm { lnr_ctx * ctx; nccl_comm_t comm; int rank, n_ranks; bool owned; };
+
+#define CKN(call)                                                                                                  \
+    do {                                                                                                           \
+        int r_ = (call);                                                                                           \
+        if (r_ != 0) {                                                                                             \
+            ctx->err = std::string(#call) + ": " + (nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "NCCL error"); \
+            return LNR_E_CUDA;                                                                                     \
+        }                                                                                                          \
+    } while (0)
+
+int lnr_nccl_unique_id(uint8_t id[128])
+{
+    if (!id) return LNR_E_ARG;
+    NcclApi & api = nccl_api();
+    if (!api.ok) return LNR_E_UNSUPPORTED;
+    NcclUid u;
+    if (api.GetUniqueId(&u) != 0) return LNR_E_CUDA;
+    memcpy(id, u.internal, 128);
+    return LNR_OK;
+}
+int lnr_comm_create(lnr_ctx * ctx, const uint8_t id[128], int rank, int n_ranks, lnr_comm ** out)
+{
+    if (!ctx || !id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return LNR_E_ARG;
+    NcclApi & api = nccl_api();
+    if (!api.ok) return fail(ctx, LNR_E_UNSUPPORTED, "libnccl.so.2 not found");
+    cudaSetDevice(ctx->device);
+    NcclUid u;
+    memcpy(u.internal, id, 128);
+    nccl_comm_t c = nullptr;
+    CKN(api.CommInitRank(&c, n_ranks, u, rank));
+    *out = new lnr_comm{ctx, c, rank, n_ranks, true};
+    return LNR_OK;
+}
+int lnr_comm_from_nccl(lnr_ctx * ctx, void * nccl_comm, int rank, int n_ranks, lnr_comm ** out)
+{
+    if (!ctx || !nccl_comm || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return LNR_E_ARG;
+    if (!nccl_api().ok) return fail(ctx, LNR_E_UNSUPPORTED, "libnccl.so.2 not found");
+    *out = new lnr_comm{ctx, (nccl_comm_t)nccl_comm, rank, n_ranks, false};
+    return LNR_OK;
+}
+void lnr_comm_destroy(lnr_comm * c)
+{
+    if (!c) return;
+    if (c->owned && c->comm) { cudaSetDevice(c->ctx->device); nccl_api().CommDestroy(c->comm); }
+    delete c;
+}
+
+__global__ void k_gather_i32(const i32 * __restrict__ src, const u32 * __restrict__ idx, u32 n, i32 * __restrict__ out)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+__global__ void k_idx_rebase(i32 * __restrict__ dir, u32 x0, u32 n, i32 base)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dir[x0 + i] += base;
+}
+
+struct ShardPlan { lnr_comm * comm; };   // non-null: build one minimizer range and assemble over NCCL
+static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_comm * comm, lnr_index ** out);
+
+int lnr_index_build_sharded(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, lnr_comm * comm, lnr_index ** out)
+{
+    if (!ctx || !g || !comm || !out || threads_sem == 0) return LNR_E_ARG;
+    if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "the sharded build is implemented for index_type 1 (DIndex)");
+    if (((1u << kDirBits) % (u32)comm->n_ranks) != 0) return fail(ctx, LNR_E_ARG, "the number of ranks must divide 2^26");
+    const u32 per = (1u << kDirBits) / (u32)comm->n_ranks;
+    return dindex_build(ctx, g, threads_sem, (u32)comm->rank * per, ((u32)comm->rank + 1) * per, comm, out);
 }
 
 // ---- index ---------------------------------------------------------------------------------------------------
@@ -2062,6 +2575,13 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
         return hindex_build(ctx, g, threads_sem, out);
     }
     if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "index_type must be 1 (DIndex, -i 1) or 2 (HIndex, -i 2)");
+    return dindex_build(ctx, g, threads_sem, x_lo, x_hi, nullptr, out);
+}
+// comm == nullptr: the buckets [x_lo, x_hi) only (whole index, or one shard for a caller-side exchange).
+// comm != nullptr: this rank builds [x_lo, x_hi) straight into its slice of the final arrays, then one grouped exchange
+// (every rank broadcasts its hs slice and its dir slice in place, at their displacements) completes them on every rank.
+static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_comm * comm, lnr_index ** out)
+{
     cudaSetDevice(ctx->device);
     // chunk table (createDIndex :1654-1670)
     std::vector<IdxChunk> chunks;
@@ -2084,18 +2604,47 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
         }
     lnr_index * ix = new lnr_index();
     ix->ctx = ctx; ix->index_type = 1; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = 0;
-    u32 * d_cnt = nullptr; IdxChunk * d_chunks = nullptr; u32 * d_tile0 = nullptr; u64 * d_total = nullptr;
-    auto cleanup = [&]() { if (d_cnt) cudaFree(d_cnt); if (d_chunks) cudaFree(d_chunks); if (d_tile0) cudaFree(d_tile0); if (d_total) cudaFree(d_total); };
+    auto cleanup = [&]() {};
 #define CKI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); lnr_index_destroy(ix); return LNR_E_CUDA; } } while (0)
+    const bool full_range = x_lo == 0 && x_hi >= (u32)(kDirSize - 1);
+    const u32 n_chunks = (u32)chunks.size();
+    const u64 n_slots = (u64)n_tiles * ITILE;
+    // every temporary of the build is carved out of the context's scratch arena (the per-warp arenas of the mapping
+    // kernels use the same allocation later): a second build, or a build after a batch, pays no cudaMalloc / cudaFree
+    size_t off_t = 0;
+    auto carve = [&](size_t bytes) { size_t o = off_t; off_t += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_cnt = carve(((size_t)kDirSize + 16) * sizeof(u32));
+    const size_t o_small = carve(4 * IPARTS * sizeof(u64) + ICOARSE * sizeof(u32) + 4 * (IPARTS + 1) * sizeof(u32));
+    const size_t o_chunks = carve(std::max<size_t>(chunks.size(), 1) * sizeof(IdxChunk));
+    const size_t o_tile0 = carve(std::max<size_t>(tile0.size(), 1) * sizeof(u32));
+    const size_t o_px0 = carve((size_t)(n_slots + 16) * sizeof(u32)), o_pr0 = carve((size_t)(n_slots + 16) * sizeof(u64));
+    const size_t o_px1 = carve((size_t)(n_slots + 16) * sizeof(u32)), o_pr1 = carve((size_t)(n_slots + 16) * sizeof(u64));
+    CKI(ctx->arena.reserve(off_t));
+    u8 * T0 = ctx->arena.as<u8>();
+    u32 * d_cnt = (u32 *)(T0 + o_cnt);
+    u64 * d_small = (u64 *)(T0 + o_small);
+    IdxChunk * d_chunks = (IdxChunk *)(T0 + o_chunks);
+    u32 * d_tile0 = (u32 *)(T0 + o_tile0);
+    u32 * d_px[2] = {(u32 *)(T0 + o_px0), (u32 *)(T0 + o_px1)};
+    u64 * d_pr[2] = {(u64 *)(T0 + o_pr0), (u64 *)(T0 + o_pr1)};
     CKI(cudaMalloc(&ix->d_dir, (size_t)kDirSize * sizeof(i32)));
-    CKI(cudaMalloc(&d_cnt, ((size_t)kDirSize + 16) * sizeof(u32)));
-    CKI(cudaMalloc(&d_total, sizeof(u64)));
+    // d_small: [0] scan total, [IPARTS..) partition counts, [2 IPARTS..) offsets, [3 IPARTS..) fill, the coarse histogram, then
+    // the split points and dir at the split points
     CKI(cudaMemsetAsync(d_cnt, 0, ((size_t)kDirSize + 16) * sizeof(u32), ctx->stream));
-    u32 n_chunks = (u32)chunks.size();
+    CKI(cudaMemsetAsync(d_small, 0, 4 * IPARTS * sizeof(u64) + ICOARSE * sizeof(u32), ctx->stream));
+    u64 * d_total = d_small;
+    unsigned long long * d_part_cnt = (unsigned long long *)(d_small + IPARTS);
+    u64 * d_part_off = d_small + 2 * IPARTS;
+    unsigned long long * d_part_fill = (unsigned long long *)(d_small + 3 * IPARTS);
+    u32 * d_coarse = (u32 *)(d_small + 4 * IPARTS);
+    u32 * d_splitx = d_coarse + ICOARSE;                 // 2 (IPARTS + 1) bucket indices: xa, xb of every partition
+    i32 * d_splitdir = (i32 *)(d_splitx + 2 * (IPARTS + 1));
+    IdxParts parts;
+    u64 part_off[IPARTS + 1];
+    for (int q = 0; q <= IPARTS; q++) { parts.split[q] = q == IPARTS ? (1u << kDirBits) : 0; part_off[q] = 0; }
+    u64 n_pairs = 0;
     if (n_chunks)
     {
-        CKI(cudaMalloc(&d_chunks, chunks.size() * sizeof(IdxChunk)));
-        CKI(cudaMalloc(&d_tile0, tile0.size() * sizeof(u32)));
         CKI(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(IdxChunk), cudaMemcpyHostToDevice, ctx->stream));
         CKI(cudaMemcpyAsync(d_tile0, tile0.data(), tile0.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
         {
@@ -2103,42 +2652,153 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
             k_idx_prep<<<(n_chunks + 127) / 128, 128, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks);
         }
         {
-            LaunchScope ls(ctx, "k_idx_count");
-            k_idx_pass<false><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, d_cnt, nullptr, nullptr, nullptr, x_lo, x_hi);
+            LaunchScope ls(ctx, "k_idx_emit");
+            k_idx_emit<<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, d_px[0], d_pr[0], x_lo, x_hi, d_coarse);
         }
         CKI(cudaGetLastError());
+        // splitters of ~equal record count from the sampled coarse histogram (at least one coarse bin per partition)
+        std::vector<u32> coarse(ICOARSE);
+        CKI(cudaMemcpyAsync(coarse.data(), d_coarse, ICOARSE * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaStreamSynchronize(ctx->stream));
+        u64 csum = 0;
+        for (u32 v : coarse) csum += v;
+        {
+            u64 run = 0; int q = 1;
+            for (int bin = 0; bin < ICOARSE && q < IPARTS; bin++)
+            {
+                run += coarse[(size_t)bin];
+                while (q < IPARTS && run * IPARTS >= csum * (u64)q && csum) { parts.split[q++] = (u32)(bin + 1) << ICOARSE_SHIFT; }
+            }
+            for (; q < IPARTS; q++) parts.split[q] = 1u << kDirBits;   // nothing sampled beyond: empty partitions
+            for (q = 1; q <= IPARTS; q++) if (parts.split[q] < parts.split[q - 1]) parts.split[q] = parts.split[q - 1];
+        }
+        {
+            LaunchScope ls(ctx, "k_idx_partcount");
+            k_idx_partcount<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(d_px[0], n_slots, parts, d_part_cnt);
+        }
+        u64 h_cnt[IPARTS];
+        CKI(cudaMemcpyAsync(h_cnt, d_part_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaStreamSynchronize(ctx->stream));
+        for (int q = 0; q < IPARTS; q++) part_off[q + 1] = part_off[q] + h_cnt[q];
+        n_pairs = part_off[IPARTS];      // emitted samples, including those of buckets that will turn out to be omitted
+        if (n_pairs)
+        {
+            CKI(cudaMemcpyAsync(d_part_off, part_off, IPARTS * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+            {
+                LaunchScope ls(ctx, "k_idx_part");
+                k_idx_part<<<(u32)((n_slots + PTILE - 1) / PTILE), PT, 0, ctx->stream>>>(d_px[0], d_pr[0], n_slots, parts, d_part_off, d_part_fill, d_px[1], d_pr[1]);
+            }
+            {
+                LaunchScope ls(ctx, "k_idx_count");
+                k_idx_count<<<(u32)((n_pairs + 255) / 256), 256, 0, ctx->stream>>>(d_px[1], n_pairs, d_cnt);
+            }
+            CKI(cudaGetLastError());
+        }
     }
     // omit buckets > 400, exclusive prefix sum over 2^26+1 entries (:1702-1721)
     {
         int rc = device_scan<i32>(ctx, d_cnt, kDirSize, kIdxOmit, ix->d_dir, d_total, "k_scan_dir");
         if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
     }
-    u64 total = 0;
-    CKI(cudaMemcpyAsync(&total, d_total, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CKI(cudaMemsetAsync(d_cnt, 0, ((size_t)kDirSize + 16) * sizeof(u32), ctx->stream));   // from here on: the fill counters of k_idx_place
+    // where every partition's buckets start and end in hs (this build's own coordinates)
+    u32 h_splitx[2 * (IPARTS + 1)];
+    i32 h_splitdir[2 * (IPARTS + 1)];
+    for (int q = 0; q < IPARTS; q++)
+    {
+        const u32 xa = std::max(parts.split[q], x_lo), xb = std::min(parts.split[q + 1], std::min(x_hi, (u32)(kDirSize - 1)));
+        h_splitx[2 * q] = xa; h_splitx[2 * q + 1] = xb > xa ? xb : xa;
+    }
+    h_splitx[2 * IPARTS] = h_splitx[2 * IPARTS + 1] = 0;
+    CKI(cudaMemcpyAsync(d_splitx, h_splitx, sizeof h_splitx, cudaMemcpyHostToDevice, ctx->stream));
+    k_gather_i32<<<1, 2 * (IPARTS + 1), 0, ctx->stream>>>(ix->d_dir, d_splitx, 2 * (IPARTS + 1), d_splitdir);
+    u64 h_small[1];
+    CKI(cudaMemcpyAsync(h_small, d_small, sizeof h_small, cudaMemcpyDeviceToHost, ctx->stream));
+    CKI(cudaMemcpyAsync(h_splitdir, d_splitdir, sizeof h_splitdir, cudaMemcpyDeviceToHost, ctx->stream));
     CKI(cudaStreamSynchronize(ctx->stream));
+    const u64 local_total = h_small[0];
+    u64 total = local_total, hs_base = 0;            // this build's records start at hs_base of the (final) hs
+    std::vector<u64> rank_cnt;
+    if (comm)
+    {
+        // record counts of all ranks -> displacements of the slices in the final hs
+        NcclApi & api = nccl_api();
+        rank_cnt.assign((size_t)comm->n_ranks, 0);
+        u64 * d_cnts = (u64 *)d_part_fill;            // 64 free words by now
+        if (comm->n_ranks > IPARTS) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_ARG, "more than 64 ranks"); }
+        int nrc = api.AllGather(d_total, d_cnts, 1, kNcclUint64, comm->comm, ctx->stream);
+        cudaError_t ce = cudaMemcpyAsync(rank_cnt.data(), d_cnts, (size_t)comm->n_ranks * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (nrc != 0 || ce != cudaSuccess) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "all-gather of the shard sizes failed"); }
+        total = 0;
+        for (int r = 0; r < comm->n_ranks; r++) { if (r == comm->rank) hs_base = total; total += rank_cnt[(size_t)r]; }
+    }
     if (total >= (1ULL << 31)) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_LIMIT, "hs exceeds int32 bucket offsets (index_util.h:101)"); }
     ix->n_hs = total;
     CKI(cudaMalloc(&ix->d_hs, (size_t)(total + 8) * sizeof(u64)));
-    if (n_chunks && total)
+    const bool derive_here = !comm;                  // sharded: Y bytes and lookup sectors are derived after the exchange
+    CKI(cudaMalloc(&ix->d_hsy, (size_t)total + 64));
+    if (full_range || comm) CKI(cudaMalloc(&ix->d_dirx, (size_t)(kDirSize - 1) * 32));
     {
-        CKI(cudaMemsetAsync(d_cnt, 0, ((size_t)kDirSize + 16) * sizeof(u32), ctx->stream));
+        // partition by partition: stage the records in their buckets, then move every record to its rank -- while the
+        // partition's range is still in L2. The pair buffers of the emit pass are free by now and serve as the staging area.
+        LaunchScope ls(ctx, "k_idx_place_rank", 2 * IPARTS);
+        u64 * d_tmp = d_pr[0]; u32 * d_tmpx = d_px[0];
+        for (int q = 0; q < IPARTS; q++)
         {
-            LaunchScope ls(ctx, "k_idx_fill");
-            k_idx_pass<true><<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, nullptr, ix->d_dir, d_cnt, ix->d_hs, x_lo, x_hi);
+            const u64 np = part_off[q + 1] - part_off[q];
+            if (!np) continue;
+            k_idx_place<<<(u32)((np + 255) / 256), 256, 0, ctx->stream>>>(d_px[1] + part_off[q], d_pr[1] + part_off[q], np, ix->d_dir, d_cnt, d_tmp, d_tmpx);
+            const u64 p0 = (u64)h_splitdir[2 * q], p1 = (u64)h_splitdir[2 * q + 1];
+            if (p1 > p0)
+                k_idx_rank<<<(u32)((p1 - p0 + 255) / 256), 256, 0, ctx->stream>>>(d_tmp, d_tmpx, p0, p1 - p0, ix->d_dir, ix->d_hs + hs_base,
+                                                                                  derive_here ? ix->d_hsy : nullptr);
+        }
+    }
+    CKI(cudaGetLastError());
+    if (derive_here && full_range)
+    {
+        LaunchScope ls(ctx, "k_idx_dirx");
+        k_idx_dirx<<<((kDirSize - 1) + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, ix->d_hsy, kDirSize - 1, ix->d_dirx);
+    }
+    if (comm)
+    {
+        if (hs_base)
+        {
+            // dir of this rank's buckets, and the one entry behind them, in final coordinates
+            LaunchScope ls(ctx, "k_idx_rebase");
+            const u32 n = x_hi - x_lo + 1;
+            k_idx_rebase<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, x_lo, n, (i32)hs_base);
+        }
+        // the one exchange step: every rank's hs slice and dir slice, in place at their displacements (no padding, no copy)
+        NcclApi & api = nccl_api();
+        const u32 per = x_hi - x_lo;
+        int nrc = 0;
+        {
+            LaunchScope ls(ctx, "nccl_exchange", 0);
+            nrc |= api.GroupStart();
+            u64 disp = 0;
+            for (int r = 0; r < comm->n_ranks; r++)
+            {
+                if (rank_cnt[(size_t)r]) nrc |= api.Broadcast(ix->d_hs + disp, ix->d_hs + disp, (size_t)rank_cnt[(size_t)r], kNcclUint64, r, comm->comm, ctx->stream);
+                nrc |= api.Broadcast(ix->d_dir + (size_t)r * per, ix->d_dir + (size_t)r * per, (size_t)per + (r == comm->n_ranks - 1 ? 1 : 0), kNcclInt32, r,
+                                     comm->comm, ctx->stream);
+                disp += rank_cnt[(size_t)r];
+            }
+            nrc |= api.GroupEnd();
+        }
+        if (nrc != 0) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "NCCL exchange of the index slices failed"); }
+        if (total)
+        {
+            LaunchScope ls(ctx, "k_idx_split_y");
+            k_idx_split_y<<<(u32)((total + 255) / 256), 256, 0, ctx->stream>>>(ix->d_hs, total, ix->d_hsy);
         }
         {
-            LaunchScope ls(ctx, "k_idx_sort_buckets");
-            k_idx_sort_buckets<<<((kDirSize - 1) + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, ix->d_hs, kDirSize - 1);
+            LaunchScope ls(ctx, "k_idx_dirx");
+            k_idx_dirx<<<((kDirSize - 1) + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, ix->d_hsy, kDirSize - 1, ix->d_dirx);
         }
         CKI(cudaGetLastError());
     }
-    CKI(cudaMalloc(&ix->d_hsy, (size_t)total + 64));
-    if (total)
-    {
-        LaunchScope ls(ctx, "k_idx_split_y");
-        k_idx_split_y<<<(u32)((total + 255) / 256), 256, 0, ctx->stream>>>(ix->d_hs, total, ix->d_hsy);
-    }
-    if (x_lo == 0 && x_hi >= (u32)(kDirSize - 1)) CKI(index_build_dirx(ctx, ix));   // a shard is never seeded from
     CKI(cudaStreamSynchronize(ctx->stream));
     cleanup();
 #undef CKI
@@ -2340,6 +3000,10 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     ctx->anchors_host_total = 0;
     if (n_reads == 0) { if (n_cords_total) *n_cords_total = 0; return LNR_OK; }
     const float stop_ratio = prm && prm->preset == 0 ? 0.7f : 0.0f;
+    const int ft = f2->feature_type;
+    if (prm && prm->feature_type != 0 && prm->feature_type != ft) return fail(ctx, LNR_E_ARG, "lnr_params.feature_type differs from the genome features' type");
+    const u32 fe_tile = ft == 1 ? (u32)(FT - 1) : (u32)FE;      // entries per feature tile
+    const size_t fesz = ft == 1 ? sizeof(i16) : sizeof(F96);
     // ---- host-side layout from the read lengths
     std::vector<SeedTask> tasks(n_reads);
     std::vector<u64> foff(n_reads + 1), cbase(n_reads + 1), hoff(n_reads + 1);
@@ -2356,11 +3020,11 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         t.n_samples = L > (u64)kMinReadLen ? (ix->index_type == 2 ? hseed_task_samples(0, (u32)L, 15) : seed_task_samples(0, (u32)L, 15)) : 0;
         t.sample0 = n_samples;
         n_samples += t.n_samples;
-        u32 nf = L > (u64)kMinReadLen ? feat_count_read(L) : 0;
+        u32 nf = L > (u64)kMinReadLen ? (ft == 1 ? feat32_count(L) : feat_count_read(L)) : 0;
         foff[r] = nf_tot;
         nf_tot += 2ull * nf;
         ftile[r] = n_ftiles;
-        n_ftiles += 2 * ((nf + FE - 1) / FE);
+        n_ftiles += 2 * ((nf + fe_tile - 1) / fe_tile);
         cbase[r] = c_tot;
         c_tot += L > (u64)kMinReadLen ? 16 + L / 4 : 0;
     }
@@ -2375,7 +3039,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(ctx->ftile.reserve((n_reads + 1) * sizeof(u32)));
     CK(ctx->cords_base.reserve((n_reads + 1) * sizeof(u64)));
     CK(ctx->order.reserve((size_t)n_reads * sizeof(u32)));
-    CK(ctx->feats.reserve((size_t)(nf_tot + 8) * sizeof(F96)));
+    CK(ctx->feats.reserve((size_t)(nf_tot + 8) * fesz));
     CK(ctx->cords.reserve((size_t)(c_tot + 8) * sizeof(u64)));
     CK(ctx->slots.reserve((size_t)n_reads * sizeof(ReadSlot)));
     CK(ctx->ncords.reserve((size_t)(n_reads + STILE + 1) * sizeof(u32)));
@@ -2401,6 +3065,10 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         CK(ctx->tile_read.reserve((size_t)n_ftiles * sizeof(u32)));
         LaunchScope ls(ctx, "k_feat_reads");
         k_feat_tile_reads<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(ctx->ftile.as<u32>(), n_reads, ctx->tile_read.as<u32>());
+        if (ft == 1)
+            k_feat32_reads<<<std::min<u32>(n_ftiles, (u32)ctx->n_sm * 16), FT, 0, ctx->stream>>>(d_bases, d_read_off, ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
+                                                                                             ctx->tile_read.as<u32>(), n_ftiles, ctx->feats.as<i16>());
+        else
         k_feat_reads<<<std::min<u32>(n_ftiles, (u32)ctx->n_sm * 16), FT, 0, ctx->stream>>>(d_bases, d_read_off, ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
                                                                                        ctx->tile_read.as<u32>(), n_ftiles, ctx->feats.as<F96>());
     }
@@ -2474,6 +3142,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     a.read_off = d_read_off; a.bases = d_bases; a.n_reads = n_reads;
     a.feats = ctx->feats.as<F96>(); a.foff = ctx->foff.as<u64>();
     a.f2 = f2->d_ptrs; a.nf2 = f2->d_n;
+    a.ft = ft; a.win = ft == 1 ? (u32)kWin32 : (u32)kWin;
     a.tasks = ctx->tasks.as<SeedTask>(); a.n_tasks = n_reads;
     a.aoff = aoff.as<u64>();
     a.A = ctx->anchorsA.as<u64>(); a.B = ctx->anchorsB.as<u64>();
@@ -2740,7 +3409,6 @@ int lnr_apxmap_batch_device(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats
                             uint64_t cords_capacity, uint64_t * n_cords_total)
 {
     if (!ctx || !ix || !f2 || !host_read_off || !dev_bases || !dev_cords) return LNR_E_ARG;
-    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
     cudaSetDevice(ctx->device);
     return apxmap_core(ctx, ix, f2, prm, n_reads, dev_bases, host_read_off, dev_cords, dev_cords_off, cords_capacity, n_cords_total, nullptr);
 }
@@ -2750,7 +3418,6 @@ int lnr_apxmap_batch(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, 
                      lnr_debug_out * dbg)
 {
     if (!ctx || !ix || !f2 || !read_off || (!bases && n_reads) || !cords || !cords_off) return LNR_E_ARG;
-    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
     cudaSetDevice(ctx->device);
     if (n_reads == 0) { cords_off[0] = 0; return LNR_OK; }
     u64 total_bases = read_off[n_reads];
@@ -2822,7 +3489,6 @@ int lnr_apxmap_batch_packed(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats
                             uint64_t * cords_off, uint64_t cords_capacity, lnr_debug_out * dbg)
 {
     if (!ctx || !ix || !f2 || !read_off || (!packed2 && n_reads) || !cords || !cords_off) return LNR_E_ARG;
-    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
     cudaSetDevice(ctx->device);
     if (n_reads == 0) { cords_off[0] = 0; return LNR_OK; }
     const u64 total_bases = read_off[n_reads];
@@ -2936,7 +3602,6 @@ int lnr_apxmap_reads(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2, 
                      uint32_t n_reads, uint64_t * cords, uint64_t * cords_off, uint64_t cords_capacity, lnr_debug_out * dbg)
 {
     if (!ctx || !ix || !f2 || !R || !cords || !cords_off || (u64)first + n_reads > R->n_reads) return LNR_E_ARG;
-    if (prm && prm->feature_type != 0 && prm->feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
     cudaSetDevice(ctx->device);
     if (n_reads == 0) { cords_off[0] = 0; return LNR_OK; }
     std::vector<u64> ro(n_reads + 1);
@@ -2993,9 +3658,11 @@ int lnr_read_features(lnr_ctx * ctx, const uint8_t * dna5, uint64_t len, int fea
                       uint64_t cap_entries, uint64_t * n_entries)
 {
     if (!ctx || !dna5) return LNR_E_ARG;
-    if (feature_type != 2) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type 2 only");
+    if (feature_type != 2 && feature_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "feature_type must be 1 or 2");
     cudaSetDevice(ctx->device);
-    u32 nf = feat_count_read(len);
+    const size_t esz = feature_type == 1 ? sizeof(i16) : sizeof(F96);
+    const u32 fe_tile = feature_type == 1 ? (u32)(FT - 1) : (u32)FE;
+    u32 nf = feature_type == 1 ? feat32_count(len) : feat_count_read(len);
     if (n_entries) *n_entries = nf;
     if (!nf || (!dst_fwd && !dst_rev)) return LNR_OK;   // count query
     if (cap_entries < nf) return fail(ctx, LNR_E_CAPACITY, "feature buffer too small");
@@ -3005,18 +3672,22 @@ int lnr_read_features(lnr_ctx * ctx, const uint8_t * dna5, uint64_t len, int fea
     CK(ctx->foff.reserve(2 * sizeof(u64)));
     CK(ctx->ftile.reserve(2 * sizeof(u32)));
     u64 ro[2] = {0, len}, fo[2] = {0, 2ull * nf};
-    u32 ft[2] = {0, 2 * ((nf + FE - 1) / FE)};
+    u32 ft[2] = {0, 2 * ((nf + fe_tile - 1) / fe_tile)};
     CK(cudaMemcpyAsync(ctx->bases.p, dna5, len, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->read_off.p, ro, sizeof ro, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->foff.p, fo, sizeof fo, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->ftile.p, ft, sizeof ft, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->tile_read.reserve((size_t)(ft[1] + 1) * sizeof(u32)));
     CK(cudaMemsetAsync(ctx->tile_read.p, 0, (size_t)(ft[1] + 1) * sizeof(u32), ctx->stream));   // one read: every tile is read 0
-    if (ft[1]) k_feat_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
+    if (ft[1] && feature_type == 1)
+        k_feat32_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
+                                                  ctx->tile_read.as<u32>(), ft[1], ctx->feats.as<i16>());
+    else if (ft[1])
+        k_feat_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
                                                 ctx->tile_read.as<u32>(), ft[1], ctx->feats.as<F96>());
     CK(cudaGetLastError());
-    if (dst_fwd) CK(cudaMemcpyAsync(dst_fwd, ctx->feats.p, (size_t)nf * sizeof(F96), cudaMemcpyDeviceToHost, ctx->stream));
-    if (dst_rev) CK(cudaMemcpyAsync(dst_rev, ctx->feats.as<F96>() + nf, (size_t)nf * sizeof(F96), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst_fwd) CK(cudaMemcpyAsync(dst_fwd, ctx->feats.p, (size_t)nf * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst_rev) CK(cudaMemcpyAsync(dst_rev, ctx->feats.as<u8>() + (size_t)nf * esz, (size_t)nf * esz, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return LNR_OK;
 }

@@ -30,6 +30,11 @@ struct PipeIn
     u32 nf1;                    // entries per strand
     const F96 * const * f2;     // genome features per contig            (createFeatures2_48 parallel)
     const u32 * nf2;            // entries per contig
+    // -f 1 (1-mer / 32-base features, one short per 16 bases): the same strings as shorts; ft selects the set
+    const i16 * s1[2];
+    const i16 * const * s2;
+    int ft;                     // feature type: 2 = 2_48 (default), 1 = 1_32
+    u32 win;                    // window size of the feature type: 96 / 192 (getFeatureWindowSize pmpfinder.cpp:244)
     float stop_ratio;           // ChainAnchorsHitsParms::thd_stop_chain_len_ratio (0.7 or 0, mapper.cpp:184)
 };
 
@@ -65,6 +70,22 @@ LNR_HD u32 window_dist48(const F96 * a, const F96 * b)   // _windowDist2_48: scr
     for (int i = 0; i < 6; i += 3)
         s += script_dist(a[i].v[0], b[i].v[0]) + script_dist(a[i].v[1], b[i].v[1]) + script_dist(a[i].v[2], b[i].v[2]);
     return (u32)s;
+}
+// -f 1: __scriptDist16_3 (pmpfinder.cpp:332): three 5-bit counters in a short, the top one by arithmetic shift
+LNR_HD u32 script_dist16(i16 s1, i16 s2)
+{
+    int a = (s1 & 31) - (s2 & 31), b = ((s1 >> 5) & 31) - ((s2 >> 5) & 31), c = (s1 >> 10) - (s2 >> 10);
+    return (u32)((a < 0 ? -a : a) + (b < 0 ? -b : b) + (c < 0 ? -c : c));
+}
+// _windowDist1_32 (:342): 6 scripts, every 2nd entry. Canonical rule for what the reference leaves undefined (it reads
+// up to 10 entries past the end of a string, :693-703 / :924): an entry outside the string is 0 (oracle/ref_harness.cpp)
+LNR_HD u32 window_dist32(const i16 * a, u32 na, u64 y, const i16 * b, u32 nb, u64 x)
+{
+    u32 d = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i += 2)
+        d += script_dist16(y + i < na ? a[y + i] : (i16)0, x + i < nb ? b[x + i] : (i16)0);
+    return d;
 }
 // __windowDist (pmpfinder.cpp:655). The reference does not bounds-check here; for in-spec inputs the
 // indices are in range, the guard only keeps the device from faulting on out-of-spec data.
@@ -1099,6 +1120,9 @@ struct WinCtx
 {
     const F96 * fa;     // read features of the strand
     const F96 * fb;     // genome features of the contig
+    const i16 * sa;     // -f 1: the same two strings as shorts
+    const i16 * sb;
+    int ft; u32 win;
     u32 nf1, nf2;
     u64 id, strand;
     // lane constants of the 18-way split of a step (full warp only): int offsets into the two rows and the sum slot
@@ -1110,7 +1134,10 @@ LNR_PIPE_INL WinCtx win_ctx(const Warp & w, const PipeIn & in, u64 cord)
 {
     WinCtx c;
     c.id = cord_id(cord); c.strand = cord_strand(cord);
-    c.fa = in.f1[c.strand]; c.fb = in.f2[c.id];
+    c.ft = in.ft; c.win = in.win;
+    c.fa = nullptr; c.fb = nullptr; c.sa = nullptr; c.sb = nullptr;
+    if (in.ft == 1) { c.sa = in.s1[c.strand]; c.sb = in.s2[c.id]; }
+    else { c.fa = in.f1[c.strand]; c.fb = in.f2[c.id]; }
     c.nf1 = in.nf1; c.nf2 = in.nf2[c.id];
     int t = w.lane < 18 ? w.lane : 0;
     int cd = t / 6, part = t - 6 * cd, i = part >= 3 ? 3 : 0, k = part - i;
@@ -1147,11 +1174,57 @@ LNR_PIPE_INL void wdist3(const Warp & w, WinCtx & c, u32 y, u32 x0, u32 d[3])
     d[1] = (yok && x0 + 4 < nf2) ? (u32)s1 : 1000u;
     d[2] = (yok && x0 + 5 < nf2) ? (u32)s2 : 1000u;
 }
+// -f 1: minimum over the 6 candidate genome windows x0 .. x0+5 (first strict minimum in ascending x); one candidate per lane
+LNR_PIPE_INL void wmin6_32(const Warp & w, WinCtx & c, u32 y, u32 x0, u32 & mn, u32 & x_min)
+{
+    c.windows += 6;
+    if (w.nl == 32)
+    {
+        u32 key = 0xffffffffu;
+        if (w.lane < 6) key = (window_dist32(c.sa, c.nf1, y, c.sb, c.nf2, x0 + (u32)w.lane) << 3) | (u32)w.lane;   // distance < 2^10
+        key = ~wmax_u32(w, ~key);
+        mn = key >> 3; x_min = x0 + (key & 7u);
+    }
+    else
+    {
+        mn = 0xffffffffu; x_min = x0;
+        for (u32 q = 0; q < 6; q++)
+        {
+            u32 d = window_dist32(c.sa, c.nf1, y, c.sb, c.nf2, x0 + q);
+            if (d < mn) { mn = d; x_min = x0 + q; }
+        }
+    }
+}
+LNR_PIPE_INL bool previous_step32(const Warp & w, WinCtx & c, u32 & xr, u32 & yr)   // previousWindow :883 with ApxMapParm1_32
+{
+    const u32 x_suf = xr, y_suf = yr;
+    if (y_suf < (u32)kMed32 || x_suf < (u32)kSup32) return false;
+    const u32 y = y_suf - kMed32;
+    u32 mn, x_min;
+    wmin6_32(w, c, y, x_suf - kSup32, mn, x_min);
+    if (mn > (u32)kWinThr) return false;
+    if (x_suf - x_min > (u32)kMed32) { xr = x_suf - kMed32; yr = x_suf - x_min - kMed32 + y; }
+    else { xr = x_min; yr = y; }
+    return c.hi != 0 || xr != 0 || yr != 0;
+}
+LNR_PIPE_INL bool next_step32(const Warp & w, WinCtx & c, u32 & xr, u32 & yr)       // nextWindow :1079 with ApxMapParm1_32
+{
+    const u32 x_pre = xr, y_pre = yr;
+    if (y_pre + 2 * kSup32 > c.nf1 || x_pre + 2 * kSup32 > c.nf2) return false;
+    const u32 y = y_pre + kMed32;
+    u32 mn, x_min;
+    wmin6_32(w, c, y, x_pre + kInf32, mn, x_min);
+    if (mn > (u32)kWinThr) return false;
+    if (x_min - x_pre > (u32)kMed32) { xr = x_pre + kMed32; yr = x_pre + kMed32 - x_min + y; }
+    else { xr = x_min; yr = y; }
+    return true;
+}
 // One window step in feature-row coordinates (x row = cord_x >> 4, y row = cord_y >> 4; every cord a step produces has
 // zero low nibbles, so the rows carry the whole state of a walk): 32-bit arithmetic, the 64-bit cord is assembled from
 // the walk's constant contig/strand bits only when it is stored. Returns false where the reference returns 0.
 LNR_PIPE_INL bool previous_step(const Warp & w, WinCtx & c, u32 & xr, u32 & yr)   // previousWindow :883
 {
+    if (c.ft == 1) return previous_step32(w, c, xr, yr);
     const u32 x_suf = xr, y_suf = yr;
     if (y_suf < (u32)kMed || x_suf < (u32)kSup) return false;
     const u32 y = y_suf - kMed, x0 = x_suf - kSup;  // candidates x_suf-6 .. x_suf-4
@@ -1167,6 +1240,7 @@ LNR_PIPE_INL bool previous_step(const Warp & w, WinCtx & c, u32 & xr, u32 & yr) 
 }
 LNR_PIPE_INL bool next_step(const Warp & w, WinCtx & c, u32 & xr, u32 & yr)   // nextWindow :1079
 {
+    if (c.ft == 1) return next_step32(w, c, xr, yr);
     const u32 x_pre = xr, y_pre = yr;
     if (y_pre + 2 * kSup > c.nf1 || x_pre + 2 * kSup > c.nf2) return false;
     const u32 y = y_pre + kMed, x0 = x_pre + kInf;  // candidates x_pre+3 .. x_pre+5
@@ -1209,7 +1283,7 @@ LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, 
     }
     last = first;                                   // after the reversal the seeding cord is last again
     xr = x_first; yr = y_first;
-    while (next_step(w, wc, xr, yr) && ((u64)yr << 4) + kWin < yend)
+    while (next_step(w, wc, xr, yr) && ((u64)yr << 4) + wc.win < yend)
     {
         if (n >= cap) { cnt.windows += wc.windows; return false; }
         last = win_cord(wc, xr, yr);
@@ -1225,7 +1299,7 @@ LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, 
 LNR_PIPE bool path_dst_2(const Warp & w, const PipeIn & in, const u64 * H, int nh, u64 * cords, int & nc, int cap, u64 read_str,
                          u64 read_end, PipeCounters & cnt)
 {
-    const u64 L = in.L, cs = kWin;
+    const u64 L = in.L, cs = in.win;
     int hb = 1, he = nh;
     if (hb + 1 >= he) return true;
     u64 last;
@@ -1726,7 +1800,9 @@ LNR_PIPE int hits_sec_blocks(const Warp & w, Arena & ar, u32 * hist256, const Pi
         {
             u32 strand = (u32)cord_strand(h), id = (u32)cord_id(h);
             u64 x1 = cord_y(h) >> 4, x2 = cord_x(h) >> 4;
-            u32 dist = (x1 + 4 < in.nf1 && x2 + 4 < in.nf2[id]) ? window_dist48(in.f1[strand] + x1, in.f2[id] + x2) : 1000u;   // _windowDist :676
+            u32 dist;   // _windowDist :676 (the bounds-checked wrapper; -f 1 checks the first index only, :693)
+            if (in.ft == 1) dist = (x1 < in.nf1 && x2 < in.nf2[id]) ? window_dist32(in.s1[strand], in.nf1, x1, in.s2[id], in.nf2[id], x2) : 1000u;
+            else dist = (x1 + 4 < in.nf1 && x2 + 4 < in.nf2[id]) ? window_dist48(in.f1[strand] + x1, in.f2[id] + x2) : 1000u;
             keep = dist < (u32)kWinReject;
         }
         const u32 bk = wballot(w, keep);
@@ -1786,12 +1862,13 @@ LNR_PIPE int phase_map(const Warp & w, Arena & ar, u32 * hist256, u32 * bins, co
 // (pmpfinder.cpp:2744-2749). gaps: forward-strand [y1, y2) intervals to re-map. Returns 1 if re-map is
 // needed, 0 if not, -1 on capacity failure.
 // ----------------------------------------------------------------------------------------------------
-LNR_HD int phase_mid(u64 L, u64 * cords, int & n_cords, YPair * str_ends, Blk * sep, int & n_sep, YPair * gaps, int & n_gaps, int gaps_cap)
+LNR_HD int phase_mid(u64 L, u64 * cords, int & n_cords, YPair * str_ends, Blk * sep, int & n_sep, YPair * gaps, int & n_gaps, int gaps_cap,
+                     u32 win = kWin)
 {
-    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)win));
     n_cords = clean_blocks(cords, n_cords, (u64)drop_len, 50);
     int ns = 0;
-    n_sep = gather_blocks(cords, n_cords, str_ends, ns, sep, 0, 1, (u32)n_cords, L, 1000, kWin, 1);
+    n_sep = gather_blocks(cords, n_cords, str_ends, ns, sep, 0, 1, (u32)n_cords, L, 1000, win, 1);
     if (n_cords < 2) ns = 0;
     int gap_sum = gather_gaps_y(str_ends, ns, gaps, n_gaps, gaps_cap, L, 1000);
     if (n_gaps >= gaps_cap) return -1;
@@ -1809,7 +1886,7 @@ LNR_HD int phase_mid(u64 L, u64 * cords, int & n_cords, YPair * str_ends, Blk * 
 // final flags (:2788-2801). sep/n_sep: blocks from the last gather_blocks_. tmp: cord scratch of cords_cap.
 // ----------------------------------------------------------------------------------------------------
 LNR_HD int phase_finish(u64 L, u64 * cords, int & n_cords, Blk * sep, int n_sep, Blk * sep2, i32 * score1, i32 * score2,
-                        BlockScratch & s1, BlockScratch & s2, u64 * tmp)
+                        BlockScratch & s1, BlockScratch & s2, u64 * tmp, u32 win = kWin)
 {
     for (int i = 0; i < n_sep; i++) sep2[i] = sep[i];
     int n1 = chain_blocks_single_strand(cords, sep, n_sep, s1, score1, 0, L, 16);
@@ -1824,7 +1901,7 @@ LNR_HD int phase_finish(u64 L, u64 * cords, int & n_cords, Blk * sep, int n_sep,
         for (int i = 0; i < no; i++) cords[i] = tmp[i];
         n_cords = no;
     }
-    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)win));
     n_cords = clean_blocks(cords, n_cords, (u64)drop_len, 50);
     int seg = 0;
     for (int i = 0; i < n_cords; i++)
@@ -1840,12 +1917,12 @@ LNR_HD int phase_finish(u64 L, u64 * cords, int & n_cords, Blk * sep, int n_sep,
 
 // warp versions of phase 2 / phase 3: the linear passes run on all lanes, the small block-chaining logic on lane 0
 LNR_PIPE int phase_mid_w(const Warp & w, u64 L, u64 * cords, int & n_cords, YPair * str_ends, Blk * sep, int & n_sep, YPair * gaps,
-                         int & n_gaps, int gaps_cap)
+                         int & n_gaps, int gaps_cap, u32 win = kWin)
 {
-    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)win));
     n_cords = clean_blocks_w(w, cords, n_cords, (u64)drop_len, 50);
     int ns = 0;
-    n_sep = gather_blocks_w(w, cords, n_cords, str_ends, ns, sep, L, 1000, kWin, 1);
+    n_sep = gather_blocks_w(w, cords, n_cords, str_ends, ns, sep, L, 1000, win, 1);
     int res = 0;
     if (w.lane == 0)
     {
@@ -1869,7 +1946,7 @@ LNR_PIPE int phase_mid_w(const Warp & w, u64 L, u64 * cords, int & n_cords, YPai
 }
 
 LNR_PIPE void phase_finish_w(const Warp & w, u64 L, u64 * cords, int & n_cords, Blk * sep, int n_sep, Blk * sep2, i32 * score1, i32 * score2,
-                             BlockScratch & s1, BlockScratch & s2, u64 * tmp)
+                             BlockScratch & s1, BlockScratch & s2, u64 * tmp, u32 win = kWin)
 {
     if (w.lane == 0)
     {
@@ -1889,7 +1966,7 @@ LNR_PIPE void phase_finish_w(const Warp & w, u64 L, u64 * cords, int & n_cords, 
     }
     n_cords = wbcast(w, n_cords, 0);
     wsync(w);
-    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)kWin));
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)win));
     n_cords = clean_blocks_w(w, cords, n_cords, (u64)drop_len, 50);
     // main / record flags (pmpfinder.cpp:2788-2801): the record bit alternates after every block end
     int ends_before = 0;

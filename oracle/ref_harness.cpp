@@ -12,6 +12,13 @@
 //     (the reference over-reads the forward Y flank by up to 3 bytes, shape_extend.cpp:292-297),
 //   * `threads` is the reference's -t: it is a semantic parameter of the index
 //     (index_util.cpp:1654-1670) and of the genome feature builder (pmpfinder.cpp:603-650).
+//   * -f 1 (1-mer/32 features): the reference leaves the last 1-2 entries of a feature string unwritten
+//     (createFeatures1_32 pmpfinder.cpp:354-373 serial, :393-423 parallel) and reads up to 10 entries past its end
+//     (_windowDist checks the first index only :693-703; previousWindow has no upper bound :924). The canonical
+//     definition adopted here -- the same way out-of-range flank bases read as 0 -- is: unwritten and out-of-range
+//     feature entries are 0. The harness makes the reference follow it by giving every String<short> >= 64 entries of
+//     capacity beyond its length BEFORE the reference resizes it (no reallocation), and zeroing everything from the
+//     first unwritten entry on afterwards.
 #include <omp.h>
 #include <cstring>
 #include <vector>
@@ -62,6 +69,31 @@ void fill_read(String<Dna5> & s, const uint8_t * p, uint64_t n)
     std::memset(((char *)&s[0]) + n, 0, 32);
 }
 
+// -f 1: first entry the reference's builders leave unwritten (serial: reads; parallel: genome contigs)
+uint64_t f32_written_serial(uint64_t len)    // pmpfinder.cpp:354-373: f[0] + one entry per k = 16, 32, .. < len - 32
+{
+    if (len < 32) return 0;
+    uint64_t lim = len - 32;
+    return 1 + (lim > 16 ? (lim - 16 + 15) / 16 : 0);
+}
+uint64_t f32_written_parallel(uint64_t len)  // pmpfinder.cpp:393-423: entries [0, (len - 32 - 16) / 16)
+{
+    return len >= 48 ? (len - 48) / 16 : 0;
+}
+void f32_reserve(String<short> & f, uint64_t seq_len)
+{
+    uint64_t n = seq_len >= 32 ? ((seq_len - 32) >> 4) + 1 : 1;
+    clear(f);
+    reserve(f, n + 64, Exact());
+}
+void f32_zero_tail(String<short> & f, uint64_t written)
+{
+    uint64_t n = length(f);
+    if (written > n) written = n;
+    short * p = &f[0];
+    std::memset(p + written, 0, (n + 64 - written) * sizeof(short));
+}
+
 struct Worker
 {
     Anchors anchors;
@@ -84,8 +116,10 @@ struct Worker
         _compltRvseStr(read, comStr);
         reserve(comStr, n + 64, Exact());
         std::memset(((char *)&comStr[0]) + n, 0, 32);
+        if (f1[0].isFs1_32()) { f32_reserve(f1[0].fs1_32, n); f32_reserve(f1[1].fs1_32, n); }
         createFeatures(begin(read), end(read), f1[0]);
         createFeatures(begin(comStr), end(comStr), f1[1]);
+        if (f1[0].isFs1_32()) { f32_zero_tail(f1[0].fs1_32, f32_written_serial(n)); f32_zero_tail(f1[1].fs1_32, f32_written_serial(n)); }
     }
 };
 
@@ -117,7 +151,14 @@ void * ref_create(int n_contigs, const uint8_t * const * dna5, const uint64_t * 
         std::memset(((char *)&c->genomes[i][0]) + lens[i], 0, 32);
     }
     omp_set_num_threads(threads);
+    if (feature_type == 1)
+    {
+        resize(c->f2, n_contigs);
+        for (int i = 0; i < n_contigs; i++) f32_reserve(c->f2[i].fs1_32, lens[i]);
+    }
     createFeatures(c->genomes, c->f2, feature_type, (unsigned)threads);   // linear.cpp:14
+    if (feature_type == 1)
+        for (int i = 0; i < n_contigs; i++) f32_zero_tail(c->f2[i].fs1_32, f32_written_parallel(lens[i]));
     c->index.setIndexType(index_type);                                    // mapper.cpp:200
     if (build_index)
         createIndexDynamic(c->genomes, c->index, 0, n_contigs, threads, false);  // mapper.cpp:325

@@ -13,6 +13,7 @@ import subprocess
 import sys
 
 rep, n_reads, prefix = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+traffic_name = sys.argv[4] if len(sys.argv) > 4 else "r1_ncu_traffic.json"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 open(prefix + "_raw.csv", "w").write(raw)
 rows = list(csv.reader(raw.splitlines()))
@@ -44,5 +45,5 @@ for r in rows[2:]:
     if name not in traffic or ms > traffic[name]["ms_under_ncu"]:
         traffic[name] = {"dram_bytes_per_launch": rd + wr, "dram_bytes_per_read": (rd + wr) / n_reads, "ms_under_ncu": ms}
 open(prefix + "_summary.txt", "w").write("\n".join(lines) + "\n")
-json.dump(traffic, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r1_ncu_traffic.json"), "w"), indent=1)
+json.dump(traffic, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), traffic_name), "w"), indent=1)
 print("\n".join(lines))

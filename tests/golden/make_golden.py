@@ -38,3 +38,21 @@ for name in CASES:
     out[name] = e
     print(name, "reads", len(reads), "unstable", stable.count(False), "cords", sum(e["n_cords"]))
 json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=0)
+
+# -f 1 (1-mer / 32-base features): the reference under the canonical rule of oracle/ref_harness.cpp (unwritten and
+# out-of-range feature entries are 0); reads whose cords differ between two passes would be excluded and counted
+out1 = {}
+for name in CASES:
+    g, reads, bases, offs, T, preset = make_case(name)
+    R = RefImpl(g, threads=T, preset=preset, feature_type=1)
+    e = {"threads": T, "preset": preset, "genome_features": [digest(R.genome_features(i)) for i in range(len(g))]}
+    empty = np.zeros(0, np.uint64)
+    cords_a = [R.cords(r) if len(r) > 200 else empty for r in reads]
+    cords_b = [R.cords(r) if len(r) > 200 else empty for r in reads]
+    e["stable"] = [bool(np.array_equal(a, b)) for a, b in zip(cords_a, cords_b)]
+    e["n_cords"] = [int(len(c)) for c in cords_a]
+    e["cords"] = [digest(c) for c in cords_a]
+    e["read_features"] = [digest(np.concatenate([R.read_features(r, 0), R.read_features(r, 1)])) if len(r) > 200 else "" for r in reads[:16]]
+    out1[name] = e
+    print("-f 1", name, "reads", len(reads), "unstable", e["stable"].count(False), "cords", sum(e["n_cords"]))
+json.dump(out1, open(os.path.join(HERE, "golden_f1.json"), "w"), indent=0)

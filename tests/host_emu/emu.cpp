@@ -24,6 +24,9 @@ struct Emu
     std::vector<u64> hs;
     std::vector<std::vector<F96> > f2;
     std::vector<const F96 *> f2p;
+    int ft = 2;                              // feature type: 2 = 2_48, 1 = 1_32
+    std::vector<std::vector<i16> > s2;
+    std::vector<const i16 *> s2p;
     std::vector<u32> nf2;
     std::vector<u64> out;
     std::vector<i32> outf;
@@ -131,8 +134,14 @@ struct ReadRun
     std::vector<u8> arena, a2;
     std::vector<u64> A, B, cords, dbg_hits;
     std::vector<F96> f1[2];
+    std::vector<i16> s1[2];
     u32 hist[lnr::kWarpSmemWords] = {0};
 };
+template <class Acc> void build_feats32(const Acc & acc, u32 n, u32 written, std::vector<i16> & f)
+{
+    f.assign(n, 0);
+    for (u32 i = 0; i < written && i < n; i++) f[i] = feat32_entry(acc, 16 * (i64)i);
+}
 
 // the per-read orchestration of kernels A and B (apxMap, pmpfinder.cpp:2709)
 int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std::vector<u64> * hits_out, int stop_after_first)
@@ -141,12 +150,27 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
     SeqAcc acc = {read, (i64)L};
     RcAcc rc = {read, (i64)L};
     ReadRun R;
-    u32 nf = feat_count_read(L);
-    build_feats(acc, nf, R.f1[0]);
-    build_feats(rc, nf, R.f1[1]);
     PipeIn in;
-    in.read = read; in.L = (u32)L; in.f1[0] = R.f1[0].data(); in.f1[1] = R.f1[1].data(); in.nf1 = nf;
-    in.f2 = E.f2p.data(); in.nf2 = E.nf2.data(); in.stop_ratio = E.stop_ratio;
+    in.read = read; in.L = (u32)L;
+    in.ft = E.ft; in.win = E.ft == 1 ? (u32)kWin32 : (u32)kWin;
+    in.f1[0] = in.f1[1] = nullptr; in.s1[0] = in.s1[1] = nullptr; in.f2 = nullptr; in.s2 = nullptr;
+    if (E.ft == 1)
+    {
+        u32 nf = feat32_count(L);
+        build_feats32(acc, nf, feat32_written_serial(L), R.s1[0]);
+        build_feats32(rc, nf, feat32_written_serial(L), R.s1[1]);
+        in.s1[0] = R.s1[0].data(); in.s1[1] = R.s1[1].data(); in.nf1 = nf;
+        in.s2 = E.s2p.data();
+    }
+    else
+    {
+        u32 nf = feat_count_read(L);
+        build_feats(acc, nf, R.f1[0]);
+        build_feats(rc, nf, R.f1[1]);
+        in.f1[0] = R.f1[0].data(); in.f1[1] = R.f1[1].data(); in.nf1 = nf;
+        in.f2 = E.f2p.data();
+    }
+    in.nf2 = E.nf2.data(); in.stop_ratio = E.stop_ratio;
     R.arena.resize(64 << 20);
     Arena ar = {R.arena.data(), R.arena.size(), 0, 0};
     int cap = 16 + (int)(L / 4);
@@ -172,7 +196,7 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
     Blk * sep = arena_alloc<Blk>(ar, nc + 2);
     YPair * gaps = arena_alloc<YPair>(ar, L / 1000 + 4);
     int n_sep = 0, n_gaps = 0;
-    int remap = phase_mid_w(w, L, R.cords.data(), nc, str_ends, sep, n_sep, gaps, n_gaps, (int)(L / 1000 + 4));
+    int remap = phase_mid_w(w, L, R.cords.data(), nc, str_ends, sep, n_sep, gaps, n_gaps, (int)(L / 1000 + 4), in.win);
     if (remap < 0) return 1;
     std::vector<YPair> gv(gaps, gaps + n_gaps);
     std::vector<Blk> sepv(sep, sep + n_sep);
@@ -190,7 +214,7 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
         }
         sepv.assign(nc + 2, Blk());
         int dummy = 0;
-        n_sep = gather_blocks_w(w, R.cords.data(), nc, (YPair *)0, dummy, sepv.data(), L, 1000, kWin, 1);
+        n_sep = gather_blocks_w(w, R.cords.data(), nc, (YPair *)0, dummy, sepv.data(), L, 1000, in.win, 1);
     }
     arena_reset(ar);
     Blk * sp1 = arena_alloc<Blk>(ar, n_sep + 1);
@@ -203,7 +227,7 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
     u64 * tmp = arena_alloc<u64>(ar, cap);
     if (ar.failed) return 1;
     for (int i = 0; i < n_sep; i++) sp1[i] = sepv[i];
-    phase_finish_w(w, L, R.cords.data(), nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp);
+    phase_finish_w(w, L, R.cords.data(), nc, sp1, n_sep, sp2, sc1, sc2, s1, s2, tmp, in.win);
     cords_out.assign(R.cords.begin(), R.cords.begin() + nc);
     return 0;
 }
@@ -215,8 +239,9 @@ extern "C" {
 void * emu_create(int n_contigs, const uint8_t * const * dna5, const uint64_t * lens, int index_type, int feature_type,
                   int threads, int preset, int build_index)
 {
-    (void)index_type; (void)feature_type;
+    (void)index_type;
     Emu * E = new Emu();
+    E->ft = feature_type == 1 ? 1 : 2;
     E->T = (unsigned)threads;
     E->stop_ratio = preset == 0 ? 0.7f : 0.0f;
     E->f2.resize(n_contigs);
@@ -225,9 +250,14 @@ void * emu_create(int n_contigs, const uint8_t * const * dna5, const uint64_t * 
         E->g.push_back(std::vector<u8>(dna5[i], dna5[i] + lens[i]));
         E->glen.push_back(lens[i]);
         SeqAcc acc = {E->g[i].data(), (i64)lens[i]};
-        build_feats(acc, feat_count_genome(lens[i], E->T), E->f2[i]);
+        if (E->ft == 1) { E->s2.resize(n_contigs); build_feats32(acc, feat32_count(lens[i]), feat32_written_parallel(lens[i]), E->s2[i]); }
+        else build_feats(acc, feat_count_genome(lens[i], E->T), E->f2[i]);
     }
-    for (int i = 0; i < n_contigs; i++) { E->f2p.push_back(E->f2[i].data()); E->nf2.push_back((u32)E->f2[i].size()); }
+    for (int i = 0; i < n_contigs; i++)
+    {
+        if (E->ft == 1) { E->s2p.push_back(E->s2[i].data()); E->nf2.push_back((u32)E->s2[i].size()); }
+        else { E->f2p.push_back(E->f2[i].data()); E->nf2.push_back((u32)E->f2[i].size()); }
+    }
     if (build_index) build_dindex(*E);
     return E;
 }
@@ -239,12 +269,27 @@ int64_t emu_hindex_dir_kv(void *, const uint64_t ** p, uint64_t * t) { *p = 0; *
 int64_t emu_genome_features(void * h, int contig, const int32_t ** p)
 {
     Emu * E = (Emu *)h;
+    if (E->ft == 1)
+    {
+        E->outf.assign(E->s2[contig].begin(), E->s2[contig].end());
+        *p = E->outf.data();
+        return (int64_t)E->s2[contig].size();
+    }
     *p = (const int32_t *)E->f2[contig].data();
     return (int64_t)E->f2[contig].size();
 }
 int64_t emu_read_features(void * h, const uint8_t * read, uint64_t len, int strand, const int32_t ** p)
 {
     Emu * E = (Emu *)h;
+    if (E->ft == 1)
+    {
+        std::vector<i16> f;
+        if (strand) { RcAcc a = {read, (i64)len}; build_feats32(a, feat32_count(len), feat32_written_serial(len), f); }
+        else { SeqAcc a = {read, (i64)len}; build_feats32(a, feat32_count(len), feat32_written_serial(len), f); }
+        E->outf.assign(f.begin(), f.end());
+        *p = E->outf.data();
+        return (int64_t)f.size();
+    }
     std::vector<F96> f;
     if (strand) { RcAcc a = {read, (i64)len}; build_feats(a, feat_count_read(len), f); }
     else { SeqAcc a = {read, (i64)len}; build_feats(a, feat_count_read(len), f); }

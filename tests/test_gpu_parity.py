@@ -351,3 +351,63 @@ def test_packed_reads_give_identical_cords(lb, ctx, with_n):
     assert np.array_equal(o1, o2) and np.array_equal(c1, c2)
     oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
     assert np.array_equal(oo, o2) and np.array_equal(oc, c2)
+
+
+# ---- -f 1: 1-mer / 32-base features, window 192 (createFeatures1_32, __scriptDist16_3; BASELINE configs[3]) -----------
+GOLDEN_F1 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_f1.json")))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_f1_features_and_cords_bit_exact(lb, ctx, name):
+    """-f 1 under the canonical rule (unwritten / out-of-range feature entries are 0): genome features, read features and
+    final cords equal to the oracle, to the golden digests made from the reference, and to the reference itself"""
+    g, reads, bases, offs, T, preset = make_case(name)
+    gd = GOLDEN_F1[name]
+    O = Oracle(g, threads=T, preset=preset, feature_type=1)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 1, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    for i in range(len(g)):
+        f = feats.download(i)
+        assert f.dtype == np.int16
+        assert np.array_equal(f.astype(np.int32), O.genome_features(i))
+        assert digest(f.astype(np.int32)) == gd["genome_features"][i]
+    for k, r in enumerate(reads[:16]):
+        if len(r) <= 200:
+            continue
+        f, rc = lb.read_features(ctx, r, 1)
+        assert np.array_equal(f.astype(np.int32), O.read_features(r, 0)) and np.array_equal(rc.astype(np.int32), O.read_features(r, 1))
+        assert digest(np.concatenate([f.astype(np.int32), rc.astype(np.int32)])) == gd["read_features"][k]
+    cords, coff = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset)
+    oc, oo = O.map_batch(bases, offs, map_threads=4)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+    n_checked = 0
+    for i, r in enumerate(reads):
+        if not gd["stable"][i]:
+            continue
+        c = cords[int(coff[i]):int(coff[i + 1])]
+        assert len(c) == (gd["n_cords"][i] if len(r) > 200 else 0) and (len(r) <= 200 or digest(c) == gd["cords"][i]), f"read {i}"
+        n_checked += 1
+    assert n_checked == len(reads)            # no read had to be excluded as oracle-unstable
+    if have_ref():
+        rc_, ro_ = RefImpl(g, threads=T, preset=preset, feature_type=1).map_batch(bases, offs, map_threads=4)
+        assert np.array_equal(ro_, coff) and np.array_equal(rc_, cords)
+
+
+def test_f1_with_hindex_and_mismatched_params(lb, ctx):
+    """-f 1 together with -i 2, and the argument check: lnr_params.feature_type must agree with the genome features"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 1, T)
+    index = lb.create_index(ctx, gen, 2, T)
+    cords, coff = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset)
+    oc, oo = Oracle(g, threads=T, preset=preset, feature_type=1, index_type=2).map_batch(bases, offs, map_threads=4)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+    import ctypes as C
+    from linear_b200.api import Params, u64p
+    prm = Params(preset=preset, feature_type=2)
+    out = np.zeros(1 << 16, np.uint64)
+    co = np.zeros(len(offs), np.uint64)
+    rc = ctx.lib.lnr_apxmap_batch(ctx.h, index.h, feats.h, C.byref(prm), len(offs) - 1, bases.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(u64p),
+                                  out.ctypes.data_as(C.c_void_p), co.ctypes.data_as(u64p), len(out), None)
+    assert rc == lb.api.LNR_E_ARG

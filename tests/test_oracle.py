@@ -115,3 +115,49 @@ def test_oracle_hindex_equals_reference(threads):
             assert np.array_equal(R.stage(r, 1), O.stage(r, 1))           # getHIndexMatchAll incl. head words read as bodies
             assert np.array_equal(R.stage(r, 1, len(r) // 3, len(r) - 100, 1), O.stage(r, 1, len(r) // 3, len(r) - 100, 1))
             assert np.array_equal(R.cords(r), O.cords(r))
+
+
+# ---- -f 1 (1-mer / 32-base features): canonical rule of oracle/ref_harness.cpp ------------------------------------------
+GOLDEN_F1 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_f1.json")))
+
+
+@pytest.mark.parametrize("name", ["clean_hifi", "repeat_ont", "repeat_t1_p0"])
+def test_oracle_f1_matches_golden(name):
+    g, reads, bases, offs, T, preset = make_case(name)
+    gd = GOLDEN_F1[name]
+    O = Oracle(g, threads=T, preset=preset, feature_type=1)
+    for i in range(len(g)):
+        assert digest(O.genome_features(i)) == gd["genome_features"][i]
+    for k, r in enumerate(reads[:16]):
+        if len(r) > 200:
+            assert digest(np.concatenate([O.read_features(r, 0), O.read_features(r, 1)])) == gd["read_features"][k]
+    cords, coff = O.map_batch(bases, offs, map_threads=2)
+    assert all(gd["stable"])
+    for i, r in enumerate(reads):
+        c = cords[int(coff[i]):int(coff[i + 1])]
+        assert len(c) == (gd["n_cords"][i] if len(r) > 200 else 0)
+        if len(r) > 200:
+            assert digest(c) == gd["cords"][i], f"read {i}"
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_f1_equals_reference_and_reference_is_stable():
+    """with zeroed feature slack the reference's -f 1 output is a function of its input (two passes agree) and the
+    oracle restates it: features incl. the zeroed tail entries, hits, cords after the first apxMap_, final cords"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    O = Oracle(g, threads=T, preset=preset, feature_type=1)
+    R = RefImpl(g, threads=T, preset=preset, feature_type=1)
+    for i in range(len(g)):
+        assert np.array_equal(R.genome_features(i), O.genome_features(i))
+    for r in reads[:30]:
+        if len(r) <= 200:
+            continue
+        for st in (0, 1):
+            assert np.array_equal(R.read_features(r, st), O.read_features(r, st))
+        for stage in (3, 4, 0):
+            assert np.array_equal(R.stage(r, stage), O.stage(r, stage)), f"stage {stage}"
+    a = R.map_batch(bases, offs, map_threads=2)
+    b = R.map_batch(bases, offs, map_threads=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    oc, oo = O.map_batch(bases, offs, map_threads=2)
+    assert np.array_equal(a[1], oo) and np.array_equal(a[0], oc)
