@@ -646,6 +646,30 @@ def main():
     dt_packed = max_over_ranks(run_steps("step_packed", args.steps))
     packed_value = world * n_reads * args.steps / dt_packed
     packed_equal = bool(np.array_equal(streams[0].last_packed[1], coff_host) and np.array_equal(streams[0].last_packed[0], c_host))
+    # ---- the reference's own call pattern (Mapper::p_calRecords, mapper.cpp:404-473): every host thread maps blocks of 64
+    # reads, one lnr_apxmap_batch per block, concurrently on its own context -- no large batches
+    small = None
+    if world == 1 and not os.environ.get("LNR_BENCH_NO_SMALL"):
+        blk, n_blk = 64, 24
+        def small_work(st, t_id, out):
+            for b in range(n_blk):
+                i0 = (t_id * n_blk + b) * blk
+                so = (offs[i0:i0 + blk + 1] - offs[i0]).astype(np.uint64)
+                out.append(lb.apx_map_batch(st.ctx, index, feats, bases_np[int(offs[i0]):int(offs[i0 + blk])], so, preset=1)[1][-1])
+        for rep in range(2):                      # first round warms the contexts' buffers for this shape
+            outs = [[] for _ in range(n_str)]
+            th = [threading.Thread(target=small_work, args=(streams[i], i, outs[i])) for i in range(n_str)]
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            dt_small = time.time() - t0
+        small = {"reads_per_s": n_blk * n_str * blk / dt_small, "block_reads": blk, "blocks": n_blk * n_str, "host_threads": n_str,
+                 "ms_per_block": 1000 * dt_small / n_blk,
+                 "what": "each host thread calls lnr_apxmap_batch on blocks of 64 reads (host buffers in and out), the way "
+                         "Mapper::p_calRecords is driven with -b 1"}
     # ---- host-side ceiling: what this box delivers when every rank only uploads its batch (pinned host -> HBM), all ranks at once
     up = torch.empty(total_bases, dtype=torch.uint8, device=dev)
     up.copy_(bases_pin, non_blocking=True)
@@ -765,6 +789,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": total_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * dt_e2e / args.steps, "input": "Dna5, 1 byte/base (lnr_apxmap_batch)",
                     "h2d_GBps_per_rank": total_bases / (dt_e2e / args.steps) / 1e9, "h2d_ceiling": h2d_ceiling},
+            "e2e_small_blocks": small,
             "e2e_packed": {"value": packed_value, "unit": "reads/s", "h2d_bytes_per_step": (total_bases + 3) // 4 + (n_reads + 1) * 8,
                            "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * dt_packed / args.steps,
                            "input": "2-bit packed bases (lnr_apxmap_batch_packed)", "cords_equal_to_dna5_call": packed_equal,

@@ -1037,13 +1037,16 @@ __global__ void __launch_bounds__(256) k_idx_partcount(const u32 * __restrict__ 
     __syncthreads();
     if (threadIdx.x < IPARTS && s_pc[threadIdx.x]) atomicAdd(&part_cnt[threadIdx.x], (unsigned long long)s_pc[threadIdx.x]);
 }
-// histogram of the partitioned pairs (see the header comment)
+// histogram of the partitioned pairs (see the header comment); 4 independent atomics per thread: the kernel is latency bound
 __global__ void __launch_bounds__(256) k_idx_count(const u32 * __restrict__ X, u64 n, u32 * __restrict__ cnt)
 {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[__ldg(X + i)], 1u);
+    const u64 i0 = (u64)blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+    u32 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const u64 i = i0 + (u64)q * blockDim.x; x[q] = i < n ? __ldg(X + i) : 0xffffffffu; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) if (x[q] != 0xffffffffu) atomicAdd(&cnt[x[q]], 1u);
 }
-
 static const int PT = 256, PI = 8, PTILE = PT * PI;
 __global__ void __launch_bounds__(PT) k_idx_part(const u32 * __restrict__ pairX, const u64 * __restrict__ pairRec, u64 n_slots, IdxParts parts,
                                                  const u64 * __restrict__ part_off, unsigned long long * __restrict__ part_fill,
@@ -1106,20 +1109,33 @@ __global__ void __launch_bounds__(PT) k_idx_part(const u32 * __restrict__ pairX,
     }
 }
 
-// records of one partition -> their buckets, in arrival order, into a staging copy of hs (tmp) together with their X
+// records of one partition -> their buckets, in arrival order, into a staging copy of hs (tmp) together with their X.
+// Every thread carries 4 records: the chain load X -> load dir -> atomic -> store is pure latency, the 4 chains overlap.
 __global__ void __launch_bounds__(256) k_idx_place(const u32 * __restrict__ X, const u64 * __restrict__ rec, u64 n, const i32 * __restrict__ dir,
                                                    u32 * __restrict__ fill, u64 * __restrict__ tmp, u32 * __restrict__ tmpx)
 {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u32 x = __ldg(X + i);
-    const i32 b = __ldg(dir + x), e = __ldg(dir + x + 1);
-    if (e > b)
+    const u64 i0 = (u64)blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+    u32 x[4]; i32 b[4], e[4]; u64 r[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
     {
-        const u64 o = (u64)b + atomicAdd(&fill[x], 1u);
-        tmp[o] = __ldg(rec + i);
-        tmpx[o] = x;
+        const u64 i = i0 + (u64)q * blockDim.x;
+        x[q] = i < n ? __ldg(X + i) : 0xffffffffu;
+        r[q] = i < n ? __ldg(rec + i) : 0;
     }
+#pragma unroll
+    for (int q = 0; q < 4; q++) { b[q] = 0; e[q] = 0; if (x[q] != 0xffffffffu) { b[q] = __ldg(dir + x[q]); e[q] = __ldg(dir + x[q] + 1); } }
+    u32 slot[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) slot[q] = e[q] > b[q] ? atomicAdd(&fill[x[q]], 1u) : 0u;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (e[q] > b[q])
+        {
+            const u64 o = (u64)b[q] + slot[q];
+            tmp[o] = r[q];
+            tmpx[o] = x[q];
+        }
 }
 // ascending order inside each bucket (index_util.cpp:1788-1796) by rank: one thread per staged record counts the records
 // of its bucket that are smaller (records are distinct) and stores itself at that rank of the final hs, its Y byte next to
@@ -2690,7 +2706,7 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
             }
             {
                 LaunchScope ls(ctx, "k_idx_count");
-                k_idx_count<<<(u32)((n_pairs + 255) / 256), 256, 0, ctx->stream>>>(d_px[1], n_pairs, d_cnt);
+                k_idx_count<<<(u32)((n_pairs + 1023) / 1024), 256, 0, ctx->stream>>>(d_px[1], n_pairs, d_cnt);
             }
             CKI(cudaGetLastError());
         }
@@ -2748,7 +2764,7 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
         {
             const u64 np = part_off[q + 1] - part_off[q];
             if (!np) continue;
-            k_idx_place<<<(u32)((np + 255) / 256), 256, 0, ctx->stream>>>(d_px[1] + part_off[q], d_pr[1] + part_off[q], np, ix->d_dir, d_cnt, d_tmp, d_tmpx);
+            k_idx_place<<<(u32)((np + 1023) / 1024), 256, 0, ctx->stream>>>(d_px[1] + part_off[q], d_pr[1] + part_off[q], np, ix->d_dir, d_cnt, d_tmp, d_tmpx);
             const u64 p0 = (u64)h_splitdir[2 * q], p1 = (u64)h_splitdir[2 * q + 1];
             if (p1 > p0)
                 k_idx_rank<<<(u32)((p1 - p0 + 255) / 256), 256, 0, ctx->stream>>>(d_tmp, d_tmpx, p0, p1 - p0, ix->d_dir, ix->d_hs + hs_base,

@@ -31,4 +31,20 @@ if [ -f "$HERE/ref_harness.cpp" ]; then
   g++ -shared -fopenmp "$B/ref_harness.o" $(for s in $SRCS; do [ $s != linear ] && echo "$B/$s.o"; done) \
       -lz -lpthread -lrt -o "$B/libref_harness.so"
 fi
+# hybrid program for the drop-in test (tests/test_gpu_hybrid.py): the reference's own main, scheduler, mapGaps and
+# writers, with createIndexDynamic + apxMap resolved to integration/lnr_seqan_shim.cpp (our code over liblnr_b200.so).
+# The reference objects are used as built above; only copies of two of them get the two symbols weakened, so that the
+# shim's strong definitions win at link time. No reference source is modified or copied.
+SHIM=$HERE/../integration/lnr_seqan_shim.cpp
+LIBDIR=$HERE/../linear_b200/csrc
+if [ -f "$SHIM" ] && [ -f "$LIBDIR/liblnr_b200.so" ]; then
+  APX=$(nm "$B/pmpfinder.o" | awk '$2=="T" && $3 ~ /^_Z6apxMapR12IndexDynamic/ {print $3}')
+  CID=$(nm "$B/index_util.o" | awk '$2=="T" && $3 ~ /^_Z18createIndexDynamic/ {print $3}')
+  objcopy --weaken-symbol="$APX" "$B/pmpfinder.o" "$B/pmpfinder_weak.o"
+  objcopy --weaken-symbol="$CID" "$B/index_util.o" "$B/index_util_weak.o"
+  g++ $FLAGS -I$HERE/../include -c "$SHIM" -o "$B/lnr_seqan_shim.o"
+  g++ -fopenmp $(for s in $SRCS; do case $s in pmpfinder) echo "$B/pmpfinder_weak.o";; index_util) echo "$B/index_util_weak.o";; *) echo "$B/$s.o";; esac; done) \
+      "$B/lnr_seqan_shim.o" -L"$LIBDIR" -llnr_b200 -Wl,-rpath,'$ORIGIN/../../linear_b200/csrc' -lz -lpthread -lrt -o "$B/linear_hybrid"
+  echo "built $B/linear_hybrid"
+fi
 echo "built $B/linear"
