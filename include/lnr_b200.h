@@ -84,8 +84,10 @@ int lnr_index_build_shard(lnr_ctx *, const lnr_genome *, int index_type, unsigne
  * an NCCL communicator: either created here from a unique id the caller distributes (lnr_nccl_unique_id on one rank,
  * lnr_comm_create on all), or an existing ncclComm_t of the host program (lnr_comm_from_nccl; not destroyed by
  * lnr_comm_destroy). NCCL is bound at run time (dlopen libnccl.so.2); LNR_E_UNSUPPORTED when it is not installed.
- * lnr_index_build_sharded is collective: every rank calls it with the same genome and threads_sem. Rank r hashes the
- * genome, keeps the minimizers of [r*2^26/n, (r+1)*2^26/n), learns all ranks' record counts (one 8-byte all-gather),
+ * lnr_index_build_sharded is collective: every rank calls it with the same genome and threads_sem. Every rank hashes the
+ * genome and derives, from the same sampled minimizer histogram, the same n bucket ranges of ~equal record count (equal-
+ * width ranges would leave 99.6 % of a random genome's records on the first of two ranks); rank r keeps the minimizers of
+ * range r, learns all ranks' record counts (one 8-byte all-gather),
  * builds its buckets directly inside its slice of the final hs / dir arrays, and one grouped exchange (in-place
  * ncclBroadcast of every rank's hs slice and dir slice at their displacements -- no padding, no staging copy) completes
  * the identical DIndex on every rank. index_type 1 only. */

@@ -1018,7 +1018,8 @@ __global__ void __launch_bounds__(IT) k_idx_emit(const u8 * __restrict__ g, cons
 }
 
 // exact number of pairs per partition (one pass over the X column)
-__global__ void __launch_bounds__(256) k_idx_partcount(const u32 * __restrict__ pairX, u64 n_slots, IdxParts parts, unsigned long long * __restrict__ part_cnt)
+__global__ void __launch_bounds__(256) k_idx_partcount(const u32 * __restrict__ pairX, u64 n_slots, IdxParts parts, unsigned long long * __restrict__ part_cnt,
+                                                       u32 x_lo, u32 x_hi)
 {
     __shared__ u32 s_split[IPARTS + 1];
     __shared__ u32 s_pc[IPARTS];
@@ -1032,7 +1033,7 @@ __global__ void __launch_bounds__(256) k_idx_partcount(const u32 * __restrict__ 
         const u32 xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            if (xs[q] != 0xffffffffu) atomicAdd(&s_pc[idx_part_of(s_split, xs[q])], 1u);
+            if (xs[q] >= x_lo && xs[q] < x_hi) atomicAdd(&s_pc[idx_part_of(s_split, xs[q])], 1u);   // 0xffffffff (no record) is never < x_hi
     }
     __syncthreads();
     if (threadIdx.x < IPARTS && s_pc[threadIdx.x]) atomicAdd(&part_cnt[threadIdx.x], (unsigned long long)s_pc[threadIdx.x]);
@@ -1050,7 +1051,7 @@ __global__ void __launch_bounds__(256) k_idx_count(const u32 * __restrict__ X, u
 static const int PT = 256, PI = 8, PTILE = PT * PI;
 __global__ void __launch_bounds__(PT) k_idx_part(const u32 * __restrict__ pairX, const u64 * __restrict__ pairRec, u64 n_slots, IdxParts parts,
                                                  const u64 * __restrict__ part_off, unsigned long long * __restrict__ part_fill,
-                                                 u32 * __restrict__ outX, u64 * __restrict__ outRec)
+                                                 u32 * __restrict__ outX, u64 * __restrict__ outRec, u32 x_lo, u32 x_hi)
 {
     __shared__ u32 s_split[IPARTS + 1];
     __shared__ u32 s_cnt[IPARTS], s_start[IPARTS + 1];
@@ -1069,7 +1070,7 @@ __global__ void __launch_bounds__(PT) k_idx_part(const u32 * __restrict__ pairX,
         const u64 idx = base + (u64)i * PT + threadIdx.x;
         x[i] = idx < n_slots ? __ldg(pairX + idx) : 0xffffffffu;
         pp[i] = 0xffu; rk[i] = 0; rc[i] = 0;
-        if (x[i] != 0xffffffffu)
+        if (x[i] >= x_lo && x[i] < x_hi)
         {
             rc[i] = __ldg(pairRec + idx);
             pp[i] = idx_part_of(s_split, x[i]);
@@ -2598,6 +2599,12 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
 // (every rank broadcasts its hs slice and its dir slice in place, at their displacements) completes them on every rank.
 static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_comm * comm, lnr_index ** out)
 {
+    // with a communicator the rank's bucket range is decided below, from the minimizer histogram every rank computes
+    // identically: equal-width ranges are badly unbalanced (minimizers crowd towards small X: the lower half of the range
+    // holds 99.6 % of the records of a random genome)
+    std::vector<u32> rank_lo;   // comm: first bucket of every rank's range, n_ranks + 1 entries
+    if (comm)
+        for (int r = 0; r <= comm->n_ranks; r++) rank_lo.push_back((u32)(((u64)r << kDirBits) / (u64)comm->n_ranks));   // empty genome: any split does
     cudaSetDevice(ctx->device);
     // chunk table (createDIndex :1654-1670)
     std::vector<IdxChunk> chunks;
@@ -2669,28 +2676,44 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
         }
         {
             LaunchScope ls(ctx, "k_idx_emit");
-            k_idx_emit<<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, d_px[0], d_pr[0], x_lo, x_hi, d_coarse);
+            k_idx_emit<<<n_tiles, IT, 0, ctx->stream>>>(g->d_bases, d_chunks, d_tile0, n_chunks, d_px[0], d_pr[0], comm ? 0u : x_lo,
+                                                        comm ? (1u << kDirBits) : x_hi, d_coarse);
         }
         CKI(cudaGetLastError());
         // splitters of ~equal record count from the sampled coarse histogram (at least one coarse bin per partition)
         std::vector<u32> coarse(ICOARSE);
         CKI(cudaMemcpyAsync(coarse.data(), d_coarse, ICOARSE * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CKI(cudaStreamSynchronize(ctx->stream));
-        u64 csum = 0;
-        for (u32 v : coarse) csum += v;
-        {
+        // equal-count cut points of [bin_lo, bin_hi) at coarse-bin granularity: out[0] = first bucket, out[n] = last + 1
+        auto equal_cuts = [&](int bin_lo, int bin_hi, int n, u32 * cut) {
+            u64 csum = 0;
+            for (int b = bin_lo; b < bin_hi; b++) csum += coarse[(size_t)b];
+            cut[0] = (u32)bin_lo << ICOARSE_SHIFT;
             u64 run = 0; int q = 1;
-            for (int bin = 0; bin < ICOARSE && q < IPARTS; bin++)
+            for (int bin = bin_lo; bin < bin_hi && q < n; bin++)
             {
                 run += coarse[(size_t)bin];
-                while (q < IPARTS && run * IPARTS >= csum * (u64)q && csum) { parts.split[q++] = (u32)(bin + 1) << ICOARSE_SHIFT; }
+                while (q < n && csum && run * (u64)n >= csum * (u64)q) cut[q++] = (u32)(bin + 1) << ICOARSE_SHIFT;
             }
-            for (; q < IPARTS; q++) parts.split[q] = 1u << kDirBits;   // nothing sampled beyond: empty partitions
-            for (q = 1; q <= IPARTS; q++) if (parts.split[q] < parts.split[q - 1]) parts.split[q] = parts.split[q - 1];
+            for (; q <= n; q++) cut[q] = (u32)bin_hi << ICOARSE_SHIFT;   // nothing sampled beyond: empty ranges
+            cut[n] = (u32)bin_hi << ICOARSE_SHIFT;
+            for (q = 1; q <= n; q++) if (cut[q] < cut[q - 1]) cut[q] = cut[q - 1];
+        };
+        if (comm)
+        {
+            rank_lo.assign((size_t)comm->n_ranks + 1, 0);
+            equal_cuts(0, ICOARSE, comm->n_ranks, rank_lo.data());
+            x_lo = rank_lo[(size_t)comm->rank]; x_hi = rank_lo[(size_t)comm->rank + 1];
+        }
+        // the 64 partitions of this build's own range
+        {
+            const int bin_lo = (int)(x_lo >> ICOARSE_SHIFT), bin_hi = (int)(((u64)x_hi + (1u << ICOARSE_SHIFT) - 1) >> ICOARSE_SHIFT);
+            equal_cuts(bin_lo, std::max(bin_hi, bin_lo), IPARTS, parts.split);
+            parts.split[0] = 0; parts.split[IPARTS] = 1u << kDirBits;   // the outer partitions absorb whatever lies outside (nothing does)
         }
         {
             LaunchScope ls(ctx, "k_idx_partcount");
-            k_idx_partcount<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(d_px[0], n_slots, parts, d_part_cnt);
+            k_idx_partcount<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(d_px[0], n_slots, parts, d_part_cnt, x_lo, x_hi);
         }
         u64 h_cnt[IPARTS];
         CKI(cudaMemcpyAsync(h_cnt, d_part_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2702,7 +2725,8 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
             CKI(cudaMemcpyAsync(d_part_off, part_off, IPARTS * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
             {
                 LaunchScope ls(ctx, "k_idx_part");
-                k_idx_part<<<(u32)((n_slots + PTILE - 1) / PTILE), PT, 0, ctx->stream>>>(d_px[0], d_pr[0], n_slots, parts, d_part_off, d_part_fill, d_px[1], d_pr[1]);
+                k_idx_part<<<(u32)((n_slots + PTILE - 1) / PTILE), PT, 0, ctx->stream>>>(d_px[0], d_pr[0], n_slots, parts, d_part_off, d_part_fill, d_px[1], d_pr[1],
+                                                                                         x_lo, x_hi);
             }
             {
                 LaunchScope ls(ctx, "k_idx_count");
@@ -2788,7 +2812,6 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
         }
         // the one exchange step: every rank's hs slice and dir slice, in place at their displacements (no padding, no copy)
         NcclApi & api = nccl_api();
-        const u32 per = x_hi - x_lo;
         int nrc = 0;
         {
             LaunchScope ls(ctx, "nccl_exchange", 0);
@@ -2796,9 +2819,10 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
             u64 disp = 0;
             for (int r = 0; r < comm->n_ranks; r++)
             {
+                const u32 lo = rank_lo[(size_t)r], hi = rank_lo[(size_t)r + 1];
+                const size_t n_dir = (size_t)(hi - lo) + (r == comm->n_ranks - 1 ? 1 : 0);
                 if (rank_cnt[(size_t)r]) nrc |= api.Broadcast(ix->d_hs + disp, ix->d_hs + disp, (size_t)rank_cnt[(size_t)r], kNcclUint64, r, comm->comm, ctx->stream);
-                nrc |= api.Broadcast(ix->d_dir + (size_t)r * per, ix->d_dir + (size_t)r * per, (size_t)per + (r == comm->n_ranks - 1 ? 1 : 0), kNcclInt32, r,
-                                     comm->comm, ctx->stream);
+                if (n_dir) nrc |= api.Broadcast(ix->d_dir + lo, ix->d_dir + lo, n_dir, kNcclInt32, r, comm->comm, ctx->stream);
                 disp += rank_cnt[(size_t)r];
             }
             nrc |= api.GroupEnd();

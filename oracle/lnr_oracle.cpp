@@ -215,6 +215,8 @@ struct orc_ctx
     // outputs
     std::vector<u64> out;
     std::vector<int32_t> outf;
+    std::vector<int64_t> recs;   // cords2BamLink records, 8 values each
+    std::vector<u64> cigs;       // cigar elements (operation << 32) | count
 };
 
 namespace {
@@ -527,6 +529,142 @@ int64_t orc_read_features(orc_ctx * c, const uint8_t * read, uint64_t len, int s
     }
     *p = c->outf.data();
     return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SAM* / BAM* record construction: cords2BamLink f_io.cpp:883, cord2cigar_ :758, ifCreateNew_ :673,
+// createRectangleCigarPair :697, socreCigarPair :720, insertNewBamRecord align_util.cpp:301
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Cig { char op; uint32_t count; };
+struct BamRec { int32_t rid, begin_pos; uint32_t flag; int s1, s2, s3; std::vector<Cig> cigar; };
+void append_shrink(std::vector<Cig> & c, const Cig & e)   // appendCigarShrink :658
+{
+    if (!c.empty() && c.back().op == e.op) c.back().count += e.count;
+    else c.push_back(e);
+}
+void rect_pair(u64 cord1, u64 cord2, Cig & c1, Cig & c2, int f_m)   // createRectangleCigarPair :697 (uint64 differences, 32-bit counts)
+{
+    u64 dx = cord_x(cord2) - cord_x(cord1), dy = cord_y(cord2) - cord_y(cord1);
+    c1.op = !f_m ? '=' : 'X';
+    if (dx >= dy) { c2.op = 'D'; c1.count = (uint32_t)dy; c2.count = (uint32_t)(dx - dy); }
+    else { c2.op = 'I'; c1.count = (uint32_t)dx; c2.count = (uint32_t)(dy - dx); }
+}
+void put_pair(std::vector<Cig> & cig, const Cig & c1, const Cig & c2)
+{
+    if (c1.count) append_shrink(cig, c1);
+    if (c2.count) append_shrink(cig, c2);
+}
+u64 cord2cigar(u64 cigar_str, u64 c1s, u64 c1e, u64 c2s, BamRec & r, i64 thd_DI, i64 thd_X)   // cord2cigar_ :758
+{
+    Cig g1 = {0, 0}, g2 = {0, 0};
+    u64 x0 = cord_x(cigar_str), y0 = cord_y(cigar_str), x11 = cord_x(c1s), y11 = cord_y(c1s);
+    u64 x12 = cord_x(c1e), y12 = cord_y(c1e), x21 = cord_x(c2s), y21 = cord_y(c2s);
+    if (x0 - y0 != x11 - y11) return ~0ULL;
+    if (x12 < x21 && y12 < y21)
+    {
+        rect_pair(c1s, c1e, g1, g2, 0);
+        put_pair(r.cigar, g1, g2);
+        i64 DI = (i64)(x21 - x12 - y21 + y12);
+        i64 X = (i64)std::min(x21 - x12, y21 - y12);
+        if (std::abs(DI) > thd_DI && X > thd_X)
+        {
+            i64 split_n = std::min((i64)std::ceil(float(std::abs(DI)) / thd_DI), X);
+            i64 split_DI = thd_DI, split_X = X / split_n;
+            u64 str = c1e;
+            rect_pair(c1e, c2s, g1, g2, 1);   // computed, not appended (:806)
+            for (i64 i = 0; i < split_n - 1; i++)
+            {
+                u64 end = DI < 0 ? shift_cord(str, split_X, split_X + split_DI) : shift_cord(str, split_X + split_DI, split_X);
+                rect_pair(str, end, g1, g2, 0);
+                put_pair(r.cigar, g1, g2);
+                str = end;
+            }
+            rect_pair(str, c2s, g1, g2, 1);
+            put_pair(r.cigar, g1, g2);
+        }
+        else
+        {
+            rect_pair(c1e, c2s, g1, g2, 1);
+            put_pair(r.cigar, g1, g2);
+        }
+    }
+    else   // the three other quadrants (:777, :850, :857) all emit the rectangle cord1_str -> cord2_str
+    {
+        rect_pair(c1s, c2s, g1, g2, 0);
+        put_pair(r.cigar, g1, g2);
+    }
+    // socreCigarPair :720 on the LAST pair built
+    if ((g1.op == '=' || g1.op == 'X') && (g2.op == 'I' || g2.op == 'D'))
+    {
+        if (g1.op == '=') { r.s1 += g1.count; r.s3 += g1.count; }
+        else r.s2 += g1.count;
+        r.s2 += g2.count < 100 ? g2.count : 0;
+        if (g2.op == 'I') r.s3 += g2.count;
+    }
+    return c2s;
+}
+void cords2bam(const u64 * cs, u64 n, u64 read_len, u64 window, u64 thd_large_X, i64 thd_DI, i64 thd_X, std::vector<BamRec> & out)
+{
+    const u64 d = (window << 20) | window;
+    std::vector<int> rec_ptr, end_ptr;
+    u64 cigar_str = 0;
+    int f_new = 1; uint32_t flag = 0;
+    for (u64 i = 1; i < n; i++)
+    {
+        if (f_new)
+        {
+            if (i != 1) { rec_ptr.push_back((int)out.size() - 1); end_ptr.push_back((int)i - 1); }
+            f_new = 0;
+            BamRec r;
+            r.rid = (int32_t)cord_id(cs[i]); r.begin_pos = (int32_t)cord_x(cs[i]);
+            r.flag = flag | (cord_strand(cs[i]) ? 16u : 0u);       // bam_flag_rvcmp align_util.cpp:5
+            r.s1 = r.s2 = r.s3 = 0;
+            int r_begin = (int)cord_y(cs[i]);
+            if (r_begin != 0) r.cigar.push_back(Cig{'S', (uint32_t)r_begin});   // insertNewBamRecord :324 (f_soft = 1)
+            out.push_back(r);
+            cigar_str = cs[i];
+            flag = 0;
+        }
+        u64 c1s = cs[i], c1e = cs[i] + d, c2s;
+        bool last = i == n - 1;
+        if (!last)
+        {   // ifCreateNew_ :673
+            u64 x11 = cord_x(cs[i]), y11 = cord_y(cs[i]), x12 = cord_x(c1e), y12 = cord_y(c1e), x21 = cord_x(cs[i + 1]), y21 = cord_y(cs[i + 1]);
+            last = is_end(cs[i]) || x11 > x21 || y11 > y21 || ((i64)(x21 - x12) > (i64)thd_large_X && (i64)(y21 - y12) > (i64)thd_large_X) ||
+                   cord_strand(cs[i] ^ cs[i + 1]);
+        }
+        if (last) { c2s = c1e; f_new = 1; flag = 2048; }         // bam_flag_suppl
+        else c2s = cs[i + 1];
+        cigar_str = cord2cigar(cigar_str, c1s, c1e, c2s, out.back(), thd_DI, thd_X);
+        if (cigar_str == ~0ULL) break;
+        if (i == n - 1) { rec_ptr.push_back((int)out.size() - 1); end_ptr.push_back((int)n - 1); }
+    }
+    for (size_t k = 0; k < end_ptr.size(); k++)
+    {
+        int clipped = (int)read_len - (int)cord_y(cs[end_ptr[k]] + d);
+        if (clipped > 0) out[rec_ptr[k]].cigar.push_back(Cig{'S', (uint32_t)clipped});
+    }
+}
+}  // namespace
+
+int64_t orc_cords2bam(orc_ctx * c, uint64_t read_len, const uint64_t * cords, uint64_t n_cords, int window, uint64_t thd_large_X,
+                      int64_t thd_DI, int64_t thd_X, const int64_t ** recs, const uint64_t ** cigars, uint64_t * n_cigars)
+{
+    std::vector<BamRec> out;
+    cords2bam(cords, n_cords, read_len, (u64)window, thd_large_X, thd_DI, thd_X, out);
+    c->recs.clear(); c->cigs.clear();
+    for (size_t k = 0; k < out.size(); k++)
+    {
+        const BamRec & r = out[k];
+        c->recs.push_back(r.rid); c->recs.push_back(r.begin_pos); c->recs.push_back(r.flag);
+        c->recs.push_back(r.s1); c->recs.push_back(r.s2); c->recs.push_back(r.s3);
+        c->recs.push_back((int64_t)c->cigs.size());
+        for (size_t j = 0; j < r.cigar.size(); j++) c->cigs.push_back(((u64)(unsigned char)r.cigar[j].op << 32) | r.cigar[j].count);
+        c->recs.push_back((int64_t)c->cigs.size());
+    }
+    *recs = c->recs.data(); *cigars = c->cigs.data(); *n_cigars = c->cigs.size();
+    return (int64_t)out.size();
 }
 
 int64_t orc_read_stage(orc_ctx * c, const uint8_t * read, uint64_t len, int stage,

@@ -28,6 +28,7 @@
 #include "index_util.h"
 #include "cluster_util.h"
 #include "pmpfinder.h"
+#include "align_util.h"
 
 using namespace seqan;
 
@@ -42,6 +43,8 @@ uint64_t apxMap_(IndexDynamic &, String<Dna5> &, Anchors &, String<uint64_t> &, 
                  StringSet<FeaturesDynamic> &, String<uint64_t> &, String<CordInfo> &, uint64_t, uint64_t, int,
                  GlobalParms &, PMPParms &);
 void _compltRvseStr(String<Dna5> & str, String<Dna5> & res);
+int cords2BamLink(String<uint64_t> &, String<uint64_t> &, String<CordInfo> &, String<BamAlignmentRecordLink> &, String<Dna5> &, uint64_t,
+                  int64_t, int64_t);   // f_io.cpp:883 (single read)
 
 namespace {
 
@@ -56,6 +59,8 @@ struct RefCtx
     std::vector<uint64_t> out;   // last stage output
     std::vector<int32_t> outf;   // last feature output
     std::vector<uint64_t> kv;    // HIndex directory as sorted (key,val2) pairs
+    std::vector<int64_t> recs;   // cords2BamLink records of the last call, 8 values each
+    std::vector<uint64_t> cigs;  // their cigar elements, (operation << 32) | count
     RefCtx() : index(genomes) {}
 };
 
@@ -316,6 +321,37 @@ int64_t ref_read_stage(void * h, const uint8_t * read, uint64_t len, int stage,
     }
     *p = c->out.data();
     return (int64_t)c->out.size();
+}
+
+// SAM* / BAM* record construction: cords2BamLink (f_io.cpp:883) for one read. cords_end[i] =
+// cords_str[i] + ((window << 20) | window) as apxMap leaves them. Returns the number of records; *recs holds 8 values per
+// record (rID, beginPos, flag, score.s1, s2, s3, first cigar element, one past the last), *cigars the elements.
+int64_t ref_cords2bam(void * h, uint64_t read_len, const uint64_t * cords, uint64_t n_cords, int window, uint64_t thd_large_X,
+                      int64_t thd_DI, int64_t thd_X, const int64_t ** recs, const uint64_t ** cigars, uint64_t * n_cigars)
+{
+    RefCtx * c = (RefCtx *)h;
+    String<uint64_t> cs, ce;
+    String<CordInfo> ci;
+    String<BamAlignmentRecordLink> recs_;
+    String<Dna5> read;
+    resize(read, read_len);                       // only its length is read (f_io.cpp:989)
+    resize(cs, n_cords); resize(ce, n_cords);
+    const uint64_t d = ((uint64_t)window << 20) | (uint64_t)window;
+    for (uint64_t i = 0; i < n_cords; i++) { cs[i] = cords[i]; ce[i] = cords[i] + d; }
+    cords2BamLink(cs, ce, ci, recs_, read, thd_large_X, thd_DI, thd_X);
+    c->recs.clear(); c->cigs.clear();
+    for (unsigned k = 0; k < length(recs_); k++)
+    {
+        BamAlignmentRecordLink & r = recs_[k];
+        c->recs.push_back(r.rID); c->recs.push_back(r.beginPos); c->recs.push_back(r.flag);
+        c->recs.push_back(r.score.s1); c->recs.push_back(r.score.s2); c->recs.push_back(r.score.s3);
+        c->recs.push_back((int64_t)c->cigs.size());
+        for (unsigned j = 0; j < length(r.cigar); j++)
+            c->cigs.push_back(((uint64_t)(unsigned char)r.cigar[j].operation << 32) | (uint64_t)r.cigar[j].count);
+        c->recs.push_back((int64_t)c->cigs.size());
+    }
+    *recs = c->recs.data(); *cigars = c->cigs.data(); *n_cigars = c->cigs.size();
+    return (int64_t)length(recs_);
 }
 
 // Batch apx-map (the reference's own per-read body, mapper.cpp:438-447 without mapGaps), `map_threads`

@@ -55,6 +55,11 @@ class _Checker:
             fn.restype = C.c_int64
             fn.argtypes = [C.c_void_p] + extra
             setattr(self, "_" + name, fn)
+        self._cords2bam = getattr(L, p + "cords2bam", None)
+        if self._cords2bam is not None:
+            self._cords2bam.restype = C.c_int64
+            self._cords2bam.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_uint64, C.c_int64, C.c_int64,
+                                        C.POINTER(C.POINTER(C.c_int64)), C.POINTER(u64p), u64p]
         self._map_batch = getattr(L, p + "map_batch")
         self._map_batch.restype = C.c_int
         self._map_batch.argtypes = [C.c_void_p, C.c_uint32, u8p, u64p, C.c_int, u64p, u64p, C.c_uint64]
@@ -133,6 +138,20 @@ class _Checker:
 
     def cords(self, read: np.ndarray) -> np.ndarray:
         return self.stage(read, 0)
+
+    def cords2bam(self, read_len: int, cords: np.ndarray, window: int = 96, thd_large_x: int = 8000, thd_di: int = (1 << 60) - 1,
+                  thd_x: int = (1 << 60) - 1):
+        """cords2BamLink (f_io.cpp:883) of one read: (records int64[n, 8] = rID, beginPos, flag, s1, s2, s3, cigar begin, cigar end;
+        cigar elements uint64[] = (operation << 32) | count)"""
+        cords = np.ascontiguousarray(cords, dtype=np.uint64)
+        pr = C.POINTER(C.c_int64)()
+        pc = u64p()
+        nc = C.c_uint64()
+        n = self._cords2bam(self.h, read_len, cords.ctypes.data_as(u64p), len(cords), window, thd_large_x, thd_di, thd_x,
+                            C.byref(pr), C.byref(pc), C.byref(nc))
+        recs = np.ctypeslib.as_array(pr, shape=(n * 8,)).copy().reshape(n, 8) if n else np.zeros((0, 8), np.int64)
+        cig = np.ctypeslib.as_array(pc, shape=(nc.value,)).copy() if nc.value else np.zeros(0, np.uint64)
+        return recs, cig
 
     def map_batch(self, bases: np.ndarray, offsets: np.ndarray, map_threads: int = 1, cap_per_base: float = 0.25):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
