@@ -186,6 +186,33 @@ int lnr_apxmap_reads(lnr_ctx *, const lnr_index *, const lnr_feats *, const lnr_
                      uint32_t n_reads, uint64_t * cords, uint64_t * cords_off, uint64_t cords_capacity, lnr_debug_out * dbg);
 void lnr_reads_destroy(lnr_reads *);
 
+/* ---- SAM* / BAM* record construction ---------------------------------------------------------------
+ * Replaces cords2BamLink (f_io.cpp:883; cord2cigar_ :758, ifCreateNew_ :673, insertNewBamRecord align_util.cpp:301) for a block
+ * of reads, the step Mapper::p_calRecords runs on the cords when no alignment is requested (mapper.cpp:463-468): the cords
+ * of a read become its records -- contig, leftmost position, flag (16 reverse strand, 2048 supplementary), the reference's
+ * cigar* (operations = I D X S, adjacent equal operations merged) and its three score counters. cords may be what
+ * lnr_apxmap_batch returned or what the host's mapGaps made of them; cords_end = cords + ((window << 20) | window).
+ * Outputs: rec_off / cigar_off (n_reads + 1 entries each), recs[rec_off[r] .. rec_off[r+1]) the records of read r, their
+ * cigar_begin / cigar_end relative to cigar_off[r]; a cigar element is (operation << 32) | count. LNR_E_CAPACITY leaves the
+ * needed sizes in rec_off[n_reads] and cigar_off[n_reads]. fillBamRecords (names, SEQ, SA:Z text) stays host code. */
+typedef struct lnr_bam_parms
+{
+    uint32_t window;      /* 96 (-f 2) or 192 (-f 1); 0 = 96 */
+    uint32_t reserved;
+    uint64_t thd_large_x; /* 8000, mapper.cpp:466 */
+    int64_t thd_di, thd_x;/* FIOParms: (1 << 60) - 1 each by default, 80 / 200 with -p 0 (f_io.cpp:16, mapper.cpp:185) */
+} lnr_bam_parms;
+typedef struct lnr_bam_rec
+{
+    int32_t rid, begin_pos;
+    uint32_t flag;
+    int32_t s1, s2, s3;             /* BamAlignmentRecordLinkScore */
+    uint32_t cigar_begin, cigar_end;
+} lnr_bam_rec;
+int lnr_cords_to_records(lnr_ctx *, uint32_t n_reads, const uint64_t * cords, const uint64_t * cords_off /* n+1 */,
+                         const uint64_t * read_len /* n */, const lnr_bam_parms *, lnr_bam_rec * recs, uint64_t rec_cap,
+                         uint64_t * rec_off /* n+1 */, uint64_t * cigars, uint64_t cigar_cap, uint64_t * cigar_off /* n+1 */);
+
 /* self-test of the warp-cooperative std::sort emulation used by chainAnchorsHits (pmpfinder.cpp:2465 sorts by
  * AnchorX only, so tied anchors end up in libstdc++'s introsort order): sorts n 64-bit records in place, ascending by
  * their high 32 bits (30 significant), with one warp. Parity tests compare the result with std::sort on the host. */

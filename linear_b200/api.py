@@ -32,7 +32,7 @@ EXPORTS = [
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
     "lnr_index_from_device", "lnr_index_destroy", "lnr_nccl_unique_id", "lnr_comm_create", "lnr_comm_from_nccl", "lnr_comm_destroy",
     "lnr_index_build_sharded", "lnr_apxmap_batch", "lnr_apxmap_batch_packed", "lnr_pack_dna5",
-    "lnr_apxmap_batch_device", "lnr_last_batch_counters", "lnr_last_batch_diag", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
+    "lnr_apxmap_batch_device", "lnr_cords_to_records", "lnr_last_batch_counters", "lnr_last_batch_diag", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
     "lnr_reads_parse", "lnr_reads_parse_device", "lnr_reads_info", "lnr_reads_download", "lnr_reads_device", "lnr_reads_destroy", "lnr_apxmap_reads",
 ]
 
@@ -45,6 +45,14 @@ class LnrError(RuntimeError):
 
 class Params(C.Structure):
     _fields_ = [("preset", C.c_int), ("feature_type", C.c_int), ("reserved", C.c_int * 6)]
+
+
+class BamParms(C.Structure):
+    _fields_ = [("window", C.c_uint32), ("reserved", C.c_uint32), ("thd_large_x", C.c_uint64), ("thd_di", C.c_int64), ("thd_x", C.c_int64)]
+
+
+BAM_REC_DTYPE = np.dtype([("rid", np.int32), ("begin_pos", np.int32), ("flag", np.uint32), ("s1", np.int32), ("s2", np.int32), ("s3", np.int32),
+                          ("cigar_begin", np.uint32), ("cigar_end", np.uint32)])
 
 
 class DebugOut(C.Structure):
@@ -102,6 +110,7 @@ def load_library() -> C.CDLL:
                                             C.POINTER(DebugOut)]
     lib.lnr_pack_dna5.argtypes = [vp, C.c_uint64, vp, vp, C.POINTER(C.c_int)]
     lib.lnr_apxmap_batch_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, vp, C.c_uint64, u64p]
+    lib.lnr_cords_to_records.argtypes = [vp, C.c_uint32, vp, u64p, u64p, C.POINTER(BamParms), vp, C.c_uint64, u64p, vp, C.c_uint64, u64p]
     lib.lnr_last_batch_counters.argtypes = [vp, u64p]
     lib.lnr_last_batch_stage_cycles.argtypes = [vp, u64p]
     lib.lnr_last_batch_diag.argtypes = [vp, u64p]
@@ -475,6 +484,29 @@ def apx_map_batch_packed(ctx: Context, index: Index, feats: Features, packed: np
                                          offsets.ctypes.data_as(u64p), cords.ctypes.data_as(C.c_void_p), coff.ctypes.data_as(u64p), cap, None)
     ctx.check(rc)
     return cords[: int(coff[-1])], coff
+
+
+def cords_to_records(ctx: Context, cords: np.ndarray, cords_off: np.ndarray, read_len: np.ndarray, window: int = 96, thd_large_x: int = 8000,
+                     thd_di: int = (1 << 60) - 1, thd_x: int = (1 << 60) - 1):
+    """cords2BamLink (f_io.cpp:883) of a block of reads on the GPU: (records structured array, rec_off, cigar elements, cigar_off)"""
+    cords = np.ascontiguousarray(cords, dtype=np.uint64)
+    cords_off = np.ascontiguousarray(cords_off, dtype=np.uint64)
+    read_len = np.ascontiguousarray(read_len, dtype=np.uint64)
+    n = len(cords_off) - 1
+    prm = BamParms(window=window, thd_large_x=thd_large_x, thd_di=thd_di, thd_x=thd_x)
+    rec_off = np.zeros(n + 1, np.uint64)
+    cig_off = np.zeros(n + 1, np.uint64)
+    rc = ctx.lib.lnr_cords_to_records(ctx.h, n, C.c_void_p(cords.ctypes.data), cords_off.ctypes.data_as(u64p), read_len.ctypes.data_as(u64p), C.byref(prm),
+                                      None, 0, rec_off.ctypes.data_as(u64p), None, 0, cig_off.ctypes.data_as(u64p))
+    if rc not in (0, LNR_E_CAPACITY):
+        ctx.check(rc)
+    recs = np.zeros(int(rec_off[n]), BAM_REC_DTYPE)
+    cig = np.zeros(int(cig_off[n]), np.uint64)
+    if len(recs):
+        ctx.check(ctx.lib.lnr_cords_to_records(ctx.h, n, C.c_void_p(cords.ctypes.data), cords_off.ctypes.data_as(u64p), read_len.ctypes.data_as(u64p),
+                                               C.byref(prm), C.c_void_p(recs.ctypes.data), len(recs), rec_off.ctypes.data_as(u64p),
+                                               C.c_void_p(cig.ctypes.data), len(cig), cig_off.ctypes.data_as(u64p)))
+    return recs, rec_off, cig, cig_off
 
 
 def cords_end(cords_str: np.ndarray, window: int = 96) -> np.ndarray:

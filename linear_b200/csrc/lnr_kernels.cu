@@ -41,6 +41,7 @@
 #include "../../include/lnr_b200.h"
 #include "lnr_core.h"
 #include "lnr_pipeline.h"
+#include "lnr_bamrec.h"
 
 using namespace lnr;
 
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases
 // ---- -f 1: 1-mer / 32-base features (createFeatures1_32 pmpfinder.cpp:354 serial / :393 parallel) --------------------
 // entry i = A + 32 C + 1024 G counts over the 32 bases from 16 i on, as a short (a count of 32 carries, the sum wraps:
 // part of the spec). One thread per 16-base cell, an entry is the sum of two neighbouring cells (through shared memory).
-// `written` = entries the reference's builder writes; the rest of the string is 0 (canonical rule, oracle/ref_harness.cpp).
+// `written` = entries the reference's builder writes; the rest of the string is 0 (canonical rule).
 template <bool RC>
 __device__ __forceinline__ int feat32_cell(const u8 * __restrict__ s, i64 L, i64 c)   // cell c of the (reverse-complemented) sequence
 {
@@ -2186,6 +2187,31 @@ __global__ void k_selftest_sort(u64 * a, u64 * s0, u64 * s1, int n, u64 * out)
     for (int i = threadIdx.x; i < n; i += 32) out[i] = r[i];
 }
 
+// ---- SAM* / BAM* records from cords (lnr_bamrec.h): one thread per read, count -> scan -> fill -------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_bam_records(const u64 * __restrict__ cords, const u64 * __restrict__ cords_off, const u64 * __restrict__ read_len,
+                                                     u32 n_reads, BamParms P, u32 * __restrict__ n_rec, u32 * __restrict__ n_cig,
+                                                     const u64 * __restrict__ rec_off, const u64 * __restrict__ cig_off, BamRec * __restrict__ recs,
+                                                     u64 * __restrict__ cigs)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const u64 * cs = cords + cords_off[r];
+    const u32 n = (u32)(cords_off[r + 1] - cords_off[r]);
+    if (!FILL)
+    {
+        BamCountSink sink;
+        bam_walk(cs, n, read_len[r], P, sink);
+        n_rec[r] = sink.n_rec; n_cig[r] = sink.n_cig;
+    }
+    else
+    {
+        BamFillSink sink;
+        sink.recs = recs + rec_off[r]; sink.cig = cigs + cig_off[r];
+        bam_walk(cs, n, read_len[r], P, sink);
+    }
+}
+
 #include "lnr_ingest.cuh"
 
 extern "C" {
@@ -3558,6 +3584,67 @@ int lnr_apxmap_batch_packed(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats
     CK(cudaMemcpyAsync(cords, ctx->out_cords.p, (size_t)total * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return rc;
+}
+
+int lnr_cords_to_records(lnr_ctx * ctx, uint32_t n_reads, const uint64_t * cords, const uint64_t * cords_off, const uint64_t * read_len,
+                         const lnr_bam_parms * prm, lnr_bam_rec * recs, uint64_t rec_cap, uint64_t * rec_off, uint64_t * cigars,
+                         uint64_t cigar_cap, uint64_t * cigar_off)
+{
+    if (!ctx || !cords_off || !read_len || !prm || !rec_off || !cigar_off || (n_reads && cords_off[n_reads] && !cords)) return LNR_E_ARG;
+    static_assert(sizeof(lnr_bam_rec) == sizeof(BamRec), "lnr_bam_rec layout");
+    cudaSetDevice(ctx->device);
+    rec_off[0] = 0; cigar_off[0] = 0;
+    if (n_reads == 0) return LNR_OK;
+    const u64 n_cords = cords_off[n_reads];
+    BamParms P;
+    P.window = prm->window ? prm->window : 96u; P.thd_large_x = prm->thd_large_x; P.thd_di = prm->thd_di; P.thd_x = prm->thd_x;
+    if (P.thd_di <= 0 || P.thd_x < 0) return fail(ctx, LNR_E_ARG, "thd_di must be positive");
+    // workspace: inputs, the two count arrays and their scans
+    size_t off_t = 0;
+    auto carve = [&](size_t bytes) { size_t o = off_t; off_t += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_cords = carve((size_t)(n_cords + 1) * 8), o_coff = carve((size_t)(n_reads + 1) * 8), o_len = carve((size_t)n_reads * 8);
+    const size_t o_nrec = carve((size_t)(n_reads + STILE + 1) * 4), o_ncig = carve((size_t)(n_reads + STILE + 1) * 4);
+    const size_t o_roff = carve((size_t)(n_reads + STILE + 1) * 8), o_goff = carve((size_t)(n_reads + STILE + 1) * 8), o_tot = carve(64);
+    CK(ctx->out_cords.reserve(off_t));
+    u8 * W = ctx->out_cords.as<u8>();
+    u64 * d_cords = (u64 *)(W + o_cords); u64 * d_coff = (u64 *)(W + o_coff); u64 * d_len = (u64 *)(W + o_len);
+    u32 * d_nrec = (u32 *)(W + o_nrec); u32 * d_ncig = (u32 *)(W + o_ncig);
+    u64 * d_roff = (u64 *)(W + o_roff); u64 * d_goff = (u64 *)(W + o_goff); u64 * d_tot = (u64 *)(W + o_tot);
+    if (n_cords) CK(cudaMemcpyAsync(d_cords, cords, (size_t)n_cords * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_coff, cords_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_len, read_len, (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_nrec + n_reads, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(d_ncig + n_reads, 0, 4, ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_bam_count");
+        k_bam_records<false><<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(d_cords, d_coff, d_len, n_reads, P, d_nrec, d_ncig, nullptr, nullptr, nullptr, nullptr);
+    }
+    int rc = device_scan<u64>(ctx, d_nrec, (u64)n_reads + 1, 0, d_roff, d_tot, "k_scan_bam");
+    if (rc) return rc;
+    rc = device_scan<u64>(ctx, d_ncig, (u64)n_reads + 1, 0, d_goff, d_tot + 1, "k_scan_bam");
+    if (rc) return rc;
+    u64 tot[2];
+    CK(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(rec_off, d_roff, (size_t)(n_reads + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cigar_off, d_goff, (size_t)(n_reads + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (tot[0] > rec_cap || tot[1] > cigar_cap || (tot[0] && !recs) || (tot[1] && !cigars))
+        return fail(ctx, LNR_E_CAPACITY, "record / cigar buffer too small (needed sizes are in rec_off[n_reads] and cigar_off[n_reads])");
+    if (tot[0])
+    {
+        CK(ctx->cords.reserve((size_t)tot[0] * sizeof(BamRec) + (size_t)(tot[1] + 1) * 8 + 512));
+        BamRec * d_recs = ctx->cords.as<BamRec>();
+        u64 * d_cigs = (u64 *)(ctx->cords.as<u8>() + (((size_t)tot[0] * sizeof(BamRec) + 255) & ~(size_t)255));
+        {
+            LaunchScope ls(ctx, "k_bam_fill");
+            k_bam_records<true><<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(d_cords, d_coff, d_len, n_reads, P, nullptr, nullptr, d_roff, d_goff, d_recs, d_cigs);
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(recs, d_recs, (size_t)tot[0] * sizeof(BamRec), cudaMemcpyDeviceToHost, ctx->stream));
+        if (tot[1]) CK(cudaMemcpyAsync(cigars, d_cigs, (size_t)tot[1] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return LNR_OK;
 }
 
 int lnr_last_batch_counters(lnr_ctx * ctx, uint64_t counters[8])

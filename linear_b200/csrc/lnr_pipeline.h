@@ -78,7 +78,7 @@ LNR_HD u32 script_dist16(i16 s1, i16 s2)
     return (u32)((a < 0 ? -a : a) + (b < 0 ? -b : b) + (c < 0 ? -c : c));
 }
 // _windowDist1_32 (:342): 6 scripts, every 2nd entry. Canonical rule for what the reference leaves undefined (it reads
-// up to 10 entries past the end of a string, :693-703 / :924): an entry outside the string is 0 (oracle/ref_harness.cpp)
+// up to 10 entries past the end of a string, :693-703 / :924): an entry outside the string is 0
 LNR_HD u32 window_dist32(const i16 * a, u32 na, u64 y, const i16 * b, u32 nb, u64 x)
 {
     u32 d = 0;

@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../linear_b200/csrc/lnr_core.h"
 #include "../../linear_b200/csrc/lnr_pipeline.h"
+#include "../../linear_b200/csrc/lnr_bamrec.h"
 
 using namespace lnr;
 
@@ -31,6 +32,8 @@ struct Emu
     std::vector<u64> out;
     std::vector<i32> outf;
     std::vector<u32> bins;
+    std::vector<int64_t> recs;
+    std::vector<u64> cigs;
 };
 
 struct SeqAcc
@@ -339,6 +342,30 @@ int emu_map_batch(void * h, uint32_t n_reads, const uint8_t * bases, const uint6
 }
 
 }  // extern "C"
+
+// cords2BamLink through the product's walk (lnr_bamrec.h), count pass then fill pass, same output form as the checkers
+extern "C" int64_t emu_cords2bam(void * h, uint64_t read_len, const uint64_t * cords, uint64_t n_cords, int window, uint64_t thd_large_X,
+                                 int64_t thd_DI, int64_t thd_X, const int64_t ** recs, const uint64_t ** cigars, uint64_t * n_cigars)
+{
+    Emu * E = (Emu *)h;
+    lnr::BamParms P = {(u32)window, thd_large_X, thd_DI, thd_X};
+    lnr::BamCountSink cs;
+    lnr::bam_walk(cords, (u32)n_cords, read_len, P, cs);
+    std::vector<lnr::BamRec> r(cs.n_rec + 1);
+    E->cigs.assign(cs.n_cig + 1, 0);
+    lnr::BamFillSink fs;
+    fs.recs = r.data(); fs.cig = E->cigs.data();
+    lnr::bam_walk(cords, (u32)n_cords, read_len, P, fs);
+    if (fs.n_rec != cs.n_rec || fs.n_cig != cs.n_cig) return -1;
+    E->recs.clear();
+    for (u32 k = 0; k < fs.n_rec; k++)
+        for (int64_t v : {(int64_t)r[k].rid, (int64_t)r[k].begin_pos, (int64_t)r[k].flag, (int64_t)r[k].s1, (int64_t)r[k].s2, (int64_t)r[k].s3,
+                          (int64_t)r[k].cigar_begin, (int64_t)r[k].cigar_end})
+            E->recs.push_back(v);
+    E->cigs.resize(fs.n_cig);
+    *recs = E->recs.data(); *cigars = E->cigs.data(); *n_cigars = fs.n_cig;
+    return (int64_t)fs.n_rec;
+}
 
 // gnu_sort must reproduce std::sort's permutation, ties included. Sorts `n` (key, payload) records with a
 // key-only comparator by both and returns the number of positions that differ.

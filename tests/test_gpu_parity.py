@@ -411,3 +411,39 @@ def test_f1_with_hindex_and_mismatched_params(lb, ctx):
     rc = ctx.lib.lnr_apxmap_batch(ctx.h, index.h, feats.h, C.byref(prm), len(offs) - 1, bases.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(u64p),
                                   out.ctypes.data_as(C.c_void_p), co.ctypes.data_as(u64p), len(out), None)
     assert rc == lb.api.LNR_E_ARG
+
+
+# ---- SAM* / BAM* records from cords (lnr_cords_to_records; cords2BamLink f_io.cpp:883) ---------------------------------
+@pytest.mark.parametrize("name", ["clean_hifi", "repeat_ont"])
+def test_cords_to_records_bit_exact(lb, ctx, name):
+    g, reads, bases, offs, T, preset = make_case(name)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    cords, coff = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset)
+    read_len = np.diff(offs).astype(np.uint64)
+    O = Oracle(g, threads=T, preset=preset, build_index=False)
+    R = RefImpl(g, threads=T, preset=preset, build_index=False) if have_ref() else None
+    for di, x, w in [((1 << 60) - 1, (1 << 60) - 1, 96), (80, 200, 96), (5, 3, 96), (7, 1, 192)]:
+        recs, roff, cig, goff = lb.cords_to_records(ctx, cords, coff, read_len, window=w, thd_di=di, thd_x=x)
+        assert len(recs) == int(roff[-1]) and len(cig) == int(goff[-1]) and len(recs) > 40
+        for i, r in enumerate(reads):
+            c = cords[int(coff[i]):int(coff[i + 1])]
+            want = O.cords2bam(len(r), c, w, 8000, di, x)
+            if R is not None:
+                wr = R.cords2bam(len(r), c, w, 8000, di, x)
+                assert np.array_equal(want[0], wr[0]) and np.array_equal(want[1], wr[1])
+            got = recs[int(roff[i]):int(roff[i + 1])]
+            assert len(got) == len(want[0]), (i, di)
+            for k in range(len(got)):
+                assert [int(got[k][f]) for f in ("rid", "begin_pos", "flag", "s1", "s2", "s3", "cigar_begin", "cigar_end")] == [int(v) for v in want[0][k]], (i, k)
+            assert np.array_equal(cig[int(goff[i]):int(goff[i + 1])], want[1]), (i, di)
+    # a buffer that is too small is refused and the needed sizes are reported
+    import ctypes as C
+    from linear_b200.api import BamParms, u64p
+    prm = BamParms(window=96, thd_large_x=8000, thd_di=(1 << 60) - 1, thd_x=(1 << 60) - 1)
+    ro, go = np.zeros(len(coff), np.uint64), np.zeros(len(coff), np.uint64)
+    small = np.zeros(4, lb.api.BAM_REC_DTYPE)
+    rc = ctx.lib.lnr_cords_to_records(ctx.h, len(coff) - 1, C.c_void_p(cords.ctypes.data), coff.ctypes.data_as(u64p), read_len.ctypes.data_as(u64p), C.byref(prm),
+                                      C.c_void_p(small.ctypes.data), 4, ro.ctypes.data_as(u64p), None, 0, go.ctypes.data_as(u64p))
+    assert rc == lb.api.LNR_E_CAPACITY and int(ro[-1]) > 40 and int(go[-1]) > 1000

@@ -161,3 +161,41 @@ def test_oracle_f1_equals_reference_and_reference_is_stable():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     oc, oo = O.map_batch(bases, offs, map_threads=2)
     assert np.array_equal(a[1], oo) and np.array_equal(a[0], oc)
+
+
+# ---- SAM* / BAM* record construction: cords2BamLink f_io.cpp:883 ----------------------------------------
+BAM_PARMS = [((1 << 60) - 1, (1 << 60) - 1, 96), (80, 200, 96), (5, 3, 96), (7, 1, 192)]   # defaults; -p 0; two that force the split path
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["clean_hifi", "repeat_ont"])
+def test_oracle_cords2bam_equals_reference(name):
+    """records (contig, position, flag, score) and cigar* elements of every read, for the default thresholds, the -p 0
+    thresholds (thd_DI 80 / thd_X 200, mapper.cpp:185) and small ones that drive cord2cigar_'s split branch (:795-824)"""
+    g, reads, bases, offs, T, preset = make_case(name)
+    O = Oracle(g, threads=T, preset=preset)
+    R = RefImpl(g, threads=T, preset=preset, build_index=False)
+    cords, coff = O.map_batch(bases, offs, map_threads=2)
+    n_rec = n_split = 0
+    for di, x, w in BAM_PARMS:
+        for i, r in enumerate(reads):
+            c = cords[int(coff[i]):int(coff[i + 1])]
+            a, b = O.cords2bam(len(r), c, w, 8000, di, x), R.cords2bam(len(r), c, w, 8000, di, x)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (i, di, x, w)
+            n_rec += len(a[0])
+            n_split += int(np.count_nonzero((a[1] >> np.uint64(32)) == ord("X")))
+    assert n_rec > 100 and n_split > 0
+
+
+def test_product_record_walk_equals_oracle():
+    """lnr_bamrec.h (the walk the CUDA kernels instantiate) compiled for the host: count pass + fill pass == oracle"""
+    from cpu_checkers import HostEmu
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    O = Oracle(g, threads=T, preset=preset)
+    E = HostEmu(g, threads=T, preset=preset, build_index=False)
+    cords, coff = O.map_batch(bases, offs, map_threads=2)
+    for di, x, w in BAM_PARMS:
+        for i, r in enumerate(reads):
+            c = cords[int(coff[i]):int(coff[i + 1])]
+            a, b = O.cords2bam(len(r), c, w, 8000, di, x), E.cords2bam(len(r), c, w, 8000, di, x)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (i, di, x, w)
