@@ -2450,6 +2450,8 @@ struct NcclApi
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char * (*GetErrorString)(int) = nullptr;
@@ -2470,8 +2472,9 @@ NcclApi & nccl_api()
         LNR_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); LNR_NCCL_SYM(CommInitRank, "ncclCommInitRank"); LNR_NCCL_SYM(CommDestroy, "ncclCommDestroy");
         LNR_NCCL_SYM(AllGather, "ncclAllGather"); LNR_NCCL_SYM(Broadcast, "ncclBroadcast"); LNR_NCCL_SYM(GroupStart, "ncclGroupStart");
         LNR_NCCL_SYM(GroupEnd, "ncclGroupEnd"); LNR_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+        LNR_NCCL_SYM(Send, "ncclSend"); LNR_NCCL_SYM(Recv, "ncclRecv");
 #undef LNR_NCCL_SYM
-        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GroupStart && api.GroupEnd;
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
     });
     return api;
 }
@@ -2836,19 +2839,28 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
             const u32 n = x_hi - x_lo + 1;
             k_idx_rebase<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, x_lo, n, (i32)hs_base);
         }
-        // the one exchange step: every rank's hs slice and dir slice, in place at their displacements (no padding, no copy)
+        // the one exchange step: every rank's hs slice and dir slice, in place at their displacements (no padding, no staging
+        // copy). One group of point-to-point transfers -- every rank sends its two slices to every peer and receives theirs --
+        // so all pairs move at once over NVSwitch (a group of broadcasts with different roots runs them one after the other)
         NcclApi & api = nccl_api();
         int nrc = 0;
         {
             LaunchScope ls(ctx, "nccl_exchange", 0);
             nrc |= api.GroupStart();
+            const u32 my_lo = rank_lo[(size_t)comm->rank], my_hi = rank_lo[(size_t)comm->rank + 1];
+            const size_t my_dir = (size_t)(my_hi - my_lo) + (comm->rank == comm->n_ranks - 1 ? 1 : 0);
             u64 disp = 0;
             for (int r = 0; r < comm->n_ranks; r++)
             {
                 const u32 lo = rank_lo[(size_t)r], hi = rank_lo[(size_t)r + 1];
                 const size_t n_dir = (size_t)(hi - lo) + (r == comm->n_ranks - 1 ? 1 : 0);
-                if (rank_cnt[(size_t)r]) nrc |= api.Broadcast(ix->d_hs + disp, ix->d_hs + disp, (size_t)rank_cnt[(size_t)r], kNcclUint64, r, comm->comm, ctx->stream);
-                if (n_dir) nrc |= api.Broadcast(ix->d_dir + lo, ix->d_dir + lo, n_dir, kNcclInt32, r, comm->comm, ctx->stream);
+                if (r != comm->rank)
+                {
+                    if (rank_cnt[(size_t)r]) nrc |= api.Recv(ix->d_hs + disp, (size_t)rank_cnt[(size_t)r], kNcclUint64, r, comm->comm, ctx->stream);
+                    if (n_dir) nrc |= api.Recv(ix->d_dir + lo, n_dir, kNcclInt32, r, comm->comm, ctx->stream);
+                    if (local_total) nrc |= api.Send(ix->d_hs + hs_base, (size_t)local_total, kNcclUint64, r, comm->comm, ctx->stream);
+                    if (my_dir) nrc |= api.Send(ix->d_dir + my_lo, my_dir, kNcclInt32, r, comm->comm, ctx->stream);
+                }
                 disp += rank_cnt[(size_t)r];
             }
             nrc |= api.GroupEnd();
@@ -3165,21 +3177,31 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         CK(cudaStreamSynchronize(ctx->stream));
     }
     // ---- workspace of the pipeline kernels
+    // A warp owns one task at a time, so a batch of n reads never keeps more than n warps busy: grids, per-warp arenas and
+    // histograms are sized by min(what the device holds, the batch). A 64-read block (the reference's p_calRecords pattern)
+    // then costs a context ~0.3 GB of scratch instead of the 19 GB a 65 536-read batch uses.
     const int wpc = 4;
-    const int n_ctas = ctx->n_sm * ctx->map_ctas_per_sm;
+    const u64 batch_warps = ((u64)n_reads + wpc - 1) / wpc * wpc;
+    auto warps_of = [&](int ctas_per_sm) { return std::min<u64>((u64)ctx->n_sm * ctas_per_sm * wpc, batch_warps); };
+    auto grid_of = [&](int ctas_per_sm) { return (unsigned)(warps_of(ctas_per_sm) / wpc); };
+    const int n_ctas = (int)grid_of(ctx->map_ctas_per_sm);
     const int max_cps = std::max(std::max(ctx->map_ctas_per_sm, ctx->sort_ctas_per_sm), std::max(ctx->chain_ctas_per_sm, ctx->blocks_ctas_per_sm));
-    const u64 n_warps = (u64)ctx->n_sm * max_cps * wpc;    // every warp of the widest kernel owns a histogram
+    const u64 n_warps = warps_of(max_cps);    // every warp of the widest kernel owns a histogram
     // one scratch arena, divided evenly among the warps of whichever kernel is running: arena_bytes_per_warp is what a warp
     // of the map_ctas_per_sm-wide kernels gets, wider kernels (k_hits_sort needs 12 B per anchor) get proportionally less
-    const size_t arena_total = (size_t)n_ctas * wpc * ctx->arena_bytes_per_warp;
-    auto arena_share = [&](int ctas_per_sm) { return (u64)((arena_total / ((size_t)ctx->n_sm * ctas_per_sm * wpc)) & ~(size_t)255); };
+    const size_t arena_total = (size_t)warps_of(ctx->map_ctas_per_sm) * ctx->arena_bytes_per_warp;
+    auto arena_share = [&](int ctas_per_sm) { return (u64)((arena_total / (size_t)warps_of(ctas_per_sm)) & ~(size_t)255); };
     CK(ctx->bins.reserve((size_t)n_warps * kNumBins * sizeof(u32)));
     CK(ctx->arena.reserve(arena_total));
-    if (ctx->bins_zeroed != ctx->bins.p || ctx->bins_zeroed_cap != ctx->bins.cap)   // the kernels return the histograms zeroed
     {
-        ctx->bins_zeroed_cap = ctx->bins.cap;
-        CK(cudaMemsetAsync(ctx->bins.p, 0, (size_t)n_warps * kNumBins * sizeof(u32), ctx->stream));
-        ctx->bins_zeroed = ctx->bins.p;
+        // the kernels return the histograms zeroed; only memory they have not seen yet needs the memset
+        const size_t need = (size_t)n_warps * kNumBins * sizeof(u32);
+        if (ctx->bins_zeroed != ctx->bins.p || ctx->bins_zeroed_cap < need)
+        {
+            CK(cudaMemsetAsync(ctx->bins.p, 0, need, ctx->stream));
+            ctx->bins_zeroed = ctx->bins.p;
+            ctx->bins_zeroed_cap = need;
+        }
     }
     u64 tasks2_cap64 = 1024;   // a read emits at most L/1000 + 4 gap tasks (k_map_finish: gcap)
     for (uint32_t r = 0; r < n_reads; r++) tasks2_cap64 += (h_read_off[r + 1] - h_read_off[r]) / 1000 + 4;
@@ -3215,7 +3237,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     a.cords = ctx->cords.as<u64>(); a.cords_base = ctx->cords_base.as<u64>();
     a.slots = ctx->slots.as<ReadSlot>();
     a.tasks2 = ctx->tasks2.as<SeedTask>(); a.tasks2_cap = tasks2_cap; a.n_tasks2 = d_ntasks2;
-    a.bins = ctx->bins.as<u32>(); a.arena = ctx->arena.as<u8>(); a.arena_per_warp = ctx->arena_bytes_per_warp;
+    a.bins = ctx->bins.as<u32>(); a.arena = ctx->arena.as<u8>(); a.arena_per_warp = arena_share(ctx->map_ctas_per_sm);
     a.queue = d_queue;
     a.index_type = ix->index_type;
     a.order = ctx->order.as<u32>();
@@ -3233,7 +3255,16 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(ctx->task_state.reserve((size_t)n_reads * sizeof(u32)));
     a.task_state = ctx->task_state.as<u32>();
     CK(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_reads * sizeof(ReadSlot), ctx->stream));
-    const size_t big_per_warp = ctx->big_arena_bytes_per_warp;
+    // big-arena pass: 32 warps; no task of this batch can need more than the bound for all of the batch's anchors, no read
+    // more than ~200 B per cord slot in the finish stage
+    u64 max_len = 0;
+    for (uint32_t r = 0; r < n_reads; r++) max_len = std::max<u64>(max_len, h_read_off[r + 1] - h_read_off[r]);
+    auto big_need = [&](u64 anchors) {
+        u64 need = std::max<u64>(phase_map_scratch_bound((int)std::min<u64>(anchors + 2, 0x7ffffff0ull)), 256 * (16 + max_len / 4) + 65536);
+        need = (need + (1u << 20) - 1) & ~(u64)((1u << 20) - 1);
+        return (size_t)std::min<u64>(need, ctx->big_arena_bytes_per_warp);
+    };
+    size_t big_per_warp = big_need(total_anchors);
     CK(ctx->big_arena.reserve(32 * big_per_warp));
     CK(ctx->big_list.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
     a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
@@ -3261,7 +3292,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         as.fit_cap = std::min(cap_chain, cap_blocks);   // a task must fit every section's arena (this section: 12 B per anchor)
         {
             LaunchScope ls(ctx, "k_hits_sort");
-            k_hits_sort<<<ctx->n_sm * ctx->sort_ctas_per_sm, 128, 0, ctx->stream>>>(as);
+            k_hits_sort<<<grid_of(ctx->sort_ctas_per_sm), 128, 0, ctx->stream>>>(as);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
         as.arena_per_warp = cap_chain;
@@ -3273,7 +3304,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         }
         {
             LaunchScope ls(ctx, "k_hits_chain");
-            k_hits_chain<<<ctx->n_sm * ctx->chain_ctas_per_sm, 128, 0, ctx->stream>>>(as);
+            k_hits_chain<<<grid_of(ctx->chain_ctas_per_sm), 128, 0, ctx->stream>>>(as);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
         as.arena_per_warp = cap_blocks;
@@ -3283,7 +3314,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         }
         {
             LaunchScope ls(ctx, "k_hits_blocks");
-            k_hits_blocks<<<ctx->n_sm * ctx->blocks_ctas_per_sm, 128, 0, ctx->stream>>>(as);
+            k_hits_blocks<<<grid_of(ctx->blocks_ctas_per_sm), 128, 0, ctx->stream>>>(as);
         }
     }
     CK(cudaGetLastError());
@@ -3336,6 +3367,12 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         u64 total2 = 0;
         rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_remap");
         if (rc) return rc;
+        if (big_need(total2) > big_per_warp)
+        {
+            big_per_warp = big_need(total2);
+            CK(ctx->big_arena.reserve(32 * big_per_warp));
+            a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
+        }
         a.tasks = ctx->tasks2.as<SeedTask>(); a.n_tasks = n_tasks2;
         a.aoff = aoff.as<u64>();
         a.A = ctx->anchorsA.as<u64>(); a.B = ctx->anchorsB.as<u64>();
