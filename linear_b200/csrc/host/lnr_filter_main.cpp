@@ -197,42 +197,70 @@ int main(int argc, char ** argv)
     // read ingest on the device (lnr_reads_parse): the file's bytes are uploaded once, parsed there, and the batches are
     // mapped straight from the parsed buffers; --host-ingest (or a file that does not start with '>' / '@') takes the
     // host reader instead
+    // The read file is streamed in chunks (default 2 GiB; a real read set is tens to hundreds of GB): a chunk's bytes are
+    // uploaded once and parsed on the device, the complete blocks of `block_reads` reads (blockSize 50 000,
+    // mapper.cpp:892) are mapped straight from the parsed buffers, and the next chunk starts at the first read that was
+    // not mapped -- so the blocks, and with them the blank lines of the APF, are the same for every chunk size.
+    uint64_t chunk_bytes = 2048ull << 20, block_reads = 50000;
+    if (const char * e = getenv("LNR_CLI_CHUNK_MB")) { long v = atol(e); if (v >= 1) chunk_bytes = (uint64_t)v << 20; }
+    if (const char * e = getenv("LNR_CLI_CHUNK_KB")) { long v = atol(e); if (v >= 1) chunk_bytes = (uint64_t)v << 10; }
+    if (const char * e = getenv("LNR_CLI_BLOCK_READS")) { long v = atol(e); if (v >= 1) block_reads = (uint64_t)v; }
     std::string text;
+    std::ifstream fin;
+    uint64_t file_size = 0;
     if (!host_ingest)
     {
-        std::ifstream fin(rpath, std::ios::binary);
+        fin.open(rpath, std::ios::binary);
         if (!fin.good()) { fprintf(stderr, "E[07]:Can't open read file %s\n", rpath.c_str()); return 1; }
-        text.assign(std::istreambuf_iterator<char>(fin), std::istreambuf_iterator<char>());
-        if (text.empty() || (text[0] != '>' && text[0] != '@')) host_ingest = 1;
+        fin.seekg(0, std::ios::end);
+        file_size = (uint64_t)fin.tellg();
+        fin.seekg(0);
+        const int c0 = fin.peek();
+        if (file_size == 0 || (c0 != '>' && c0 != '@')) host_ingest = 1;
     }
     if (!host_ingest)
     {
-        lnr_reads * R = nullptr;
-        if ((rc = lnr_reads_parse(ctx, text.data(), text.size(), 0, &R))) return die("lnr_reads_parse", rc);
-        uint64_t n_all = 0, tb = 0;
-        lnr_reads_info(R, &n_all, &tb);
-        std::vector<uint64_t> off(n_all + 1), id_off(n_all + 1);
-        std::vector<uint32_t> id_len(n_all + 1);
-        if ((rc = lnr_reads_download(R, nullptr, off.data(), id_off.data(), id_len.data()))) return die("lnr_reads_download", rc);
-        for (uint64_t first = 0; first < n_all; first += 50000)   // blockSize, mapper.cpp:892
+        uint64_t pos = 0;
+        while (pos < file_size)
         {
-            const uint32_t n = (uint32_t)std::min<uint64_t>(50000, n_all - first);
-            reads.assign(n, Rec());
-            for (uint32_t j = 0; j < n; j++)
+            const uint64_t want = std::min<uint64_t>(chunk_bytes, file_size - pos);
+            text.resize(want);
+            fin.clear();
+            fin.seekg((std::streamoff)pos);
+            fin.read(&text[0], (std::streamsize)want);
+            const bool eof = pos + want >= file_size;
+            lnr_reads * R = nullptr;
+            if ((rc = lnr_reads_parse(ctx, text.data(), text.size(), 0, &R))) return die("lnr_reads_parse", rc);
+            uint64_t n_all = 0, tb = 0;
+            lnr_reads_info(R, &n_all, &tb);
+            // the last record of a chunk may be cut off: it is never mapped from this chunk
+            const uint64_t n_use = eof ? n_all : (n_all ? (n_all - 1) / block_reads * block_reads : 0);
+            if (!eof && n_use == 0) { lnr_reads_destroy(R); chunk_bytes *= 2; continue; }   // not one whole block in the chunk
+            std::vector<uint64_t> off(n_all + 1), id_off(n_all + 1);
+            std::vector<uint32_t> id_len(n_all + 1);
+            if ((rc = lnr_reads_download(R, nullptr, off.data(), id_off.data(), id_len.data()))) return die("lnr_reads_download", rc);
+            for (uint64_t first = 0; first < n_use; first += block_reads)
             {
-                reads[j].id.assign(text.data() + id_off[first + j], id_len[first + j]);
-                reads[j].n = off[first + j + 1] - off[first + j];
+                const uint32_t n = (uint32_t)std::min<uint64_t>(block_reads, n_use - first);
+                reads.assign(n, Rec());
+                for (uint32_t j = 0; j < n; j++)
+                {
+                    reads[j].id.assign(text.data() + id_off[first + j], id_len[first + j]);
+                    reads[j].n = off[first + j + 1] - off[first + j];
+                }
+                const uint64_t nb = off[first + n] - off[first];
+                std::vector<uint64_t> cords(nb / 16 + 64 * (uint64_t)n + 1024), coff(n + 1);
+                if ((rc = lnr_apxmap_reads(ctx, ix, f2, &prm, R, (uint32_t)first, n, cords.data(), coff.data(), cords.size(), nullptr)))
+                    return die("lnr_apxmap_reads", rc);
+                main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
+                if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, feature_t == 1 ? 192 : 96);
+                n_reads_total += n;
+                n_cords_total += coff.back();
             }
-            const uint64_t nb = off[first + n] - off[first];
-            std::vector<uint64_t> cords(nb / 16 + 64 * (uint64_t)n + 1024), coff(n + 1);
-            if ((rc = lnr_apxmap_reads(ctx, ix, f2, &prm, R, (uint32_t)first, n, cords.data(), coff.data(), cords.size(), nullptr)))
-                return die("lnr_apxmap_reads", rc);
-            main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
-            if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, feature_t == 1 ? 192 : 96);
-            n_reads_total += n;
-            n_cords_total += coff.back();
+            const uint64_t next = eof ? file_size : pos + id_off[n_use] - 1;   // the '>' / '@' in front of the first unmapped id
+            lnr_reads_destroy(R);
+            pos = next;
         }
-        lnr_reads_destroy(R);
     }
     else
     {

@@ -163,3 +163,21 @@ def test_cli_f1_against_reference_binary(tmp_path):
         tot += len(ca | cb)
         same += len(ca & cb)
     assert same >= 0.9 * tot, (same, tot)
+
+
+def test_cli_streams_the_read_file_in_chunks(tmp_path):
+    """the CLI mirror reads the read file chunk by chunk (a real read set does not fit in memory): the output does not depend
+    on the chunk size -- records cut by a chunk end are re-read with the next chunk, blocks stay aligned"""
+    g, reads, bases, offs, T, _ = make_case("repeat_ont")
+    gfa, rfa = str(tmp_path / "genome.fa"), str(tmp_path / "reads.fa")
+    datagen.write_fasta(gfa, [f"chr{i + 1} synthetic" for i in range(len(g))], g)
+    datagen.write_fasta(rfa, [f"read{i} some description" for i in range(len(reads))], reads)
+    outs = []
+    for k, env_extra in enumerate(({"LNR_CLI_BLOCK_READS": "7"}, {"LNR_CLI_BLOCK_READS": "7", "LNR_CLI_CHUNK_KB": "96"},
+                                   {"LNR_CLI_BLOCK_READS": "7", "LNR_CLI_CHUNK_KB": "700"})):
+        d = tmp_path / f"run{k}"
+        d.mkdir()
+        subprocess.run([CLI, "filter", rfa, gfa, "-ot", "1", "-t", "4", "-p", "1"], cwd=d, check=True, timeout=900, env=dict(os.environ, **env_extra))
+        outs.append(open(d / "reads.apf", "rb").read())
+    assert len(outs[0]) > 1000 and outs[0].count(b"\n@") > 40
+    assert outs[1] == outs[0] and outs[2] == outs[0]
