@@ -35,9 +35,9 @@ GENOME_BASES = int(os.environ.get("LNR_BENCH_GENOME", 3_100_000_000))
 N_CONTIGS = 24
 READ_PROFILE = os.environ.get("LNR_BENCH_PROFILE", "ont")   # "hifi": 15 kb reads at 1 % error, a side measurement
 THREADS_SEM = 16          # the reference's code default -t (base.cpp:26-54); semantic for the index
-SEED_COUNT_WRITE = 16     # bytes k_seed_count writes per sample: info 8 + count 4 + list offset 4
-SEED_FILL_READ = 24       # bytes k_seed_fill reads per sample: info 8 + count 4 + list offset 4 + anchor offset 8
-TRAFFIC_FILE = "r1_ncu_traffic.json"   # dram bytes per read of each kernel from the last `ncu --set full` capture
+SEED_COUNT_WRITE = 4      # bytes k_seed_count writes per sample: its match count (+ 4 B per match entry, below)
+SEED_FILL_READ = 4        # bytes k_seed_fill reads per sample: the count (+ 4 B per match entry, below)
+TRAFFIC_FILE = "r2_ncu_traffic.json"   # dram bytes per read of each kernel from the last `ncu --set full` capture
 METRIC = "reads/sec apx-map+chain at 1/2/4/8 B200 (3.1-Gbase synth); index build sec"   # BASELINE.json's metric, verbatim
 try:
     METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
@@ -737,8 +737,8 @@ def main():
     nf_bytes = 2 * 12 * (total_bases // 16)
     alg = {
         "k_feat_reads": total_bases + nf_bytes,            # bases in, both strands' int96 features out
-        "k_seed_count": total_bases + 32 * S + H + SEED_COUNT_WRITE * S,   # bases, one 32-B lookup sector per seed, 1-byte Y keys, per-sample records out
-        "k_seed_fill": SEED_FILL_READ * S + 8 * A + 8 * A,   # per-sample records in, matched hs records in, anchors out
+        "k_seed_count": total_bases + 32 * S + H + SEED_COUNT_WRITE * S + 4 * A,   # bases, one 32-B lookup sector per seed, 1-byte Y keys, counts + match entries out
+        "k_seed_fill": SEED_FILL_READ * S + 4 * A + 8 * A + 8 * A,   # counts in, match entries in, matched hs records in, anchors out
         "k_hits_sort": 8 * A,
         "k_hits_chain": 24 * Hits,
         "k_hits_blocks": 24 * Hits,

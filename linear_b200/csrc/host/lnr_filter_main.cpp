@@ -31,38 +31,57 @@ static inline uint8_t ord5(char c)   // seqan Dna5: every non-ACGTU byte is N (a
                  case 'T': case 't': case 'U': case 'u': return 3; default: return 4; }
 }
 
-// FASTA / FASTQ reader; `n` records at most (0 = all). Returns false at end of file.
+// FASTA / FASTQ reader (--host-ingest); `n` records at most (0 = all). Returns false at end of file.
+// Same record model as the device parser (lnr_ingest.cuh), which the APF tests pin against the reference binary: the
+// first byte of the file decides the format. FASTA: only a line starting with '>' opens a record; every other line adds
+// its bytes except '\r' and ' ' to the sequence. FASTQ: records of exactly four lines (a header line that is empty is
+// skipped, with its three lines); '\r' is stripped from ids and sequences.
 struct SeqReader
 {
-    std::ifstream in; std::string line; bool have = false;
-    bool open(const std::string & p) { in.open(p); return in.good(); }
-    bool next_line() { if (have) { have = false; return true; } return (bool)std::getline(in, line); }
+    std::ifstream in; std::string line; int format = 0; bool have = false;
+    bool open(const std::string & p)
+    {
+        in.open(p);
+        if (!in.good()) return false;
+        const int c = in.peek();
+        format = c == '>' ? 1 : (c == '@' ? 2 : 0);
+        return true;
+    }
+    static void strip_cr(std::string & s) { if (!s.empty() && s.back() == '\r') s.pop_back(); }
     bool read(std::vector<Rec> & out, size_t n, bool cut_id_at_space)
     {
         out.clear();
-        while (n == 0 || out.size() < n)
+        if (format == 1)
         {
-            if (!next_line()) break;
-            if (line.empty()) continue;
-            if (line[0] == '>')
+            while (n == 0 || out.size() < n)
             {
+                if (have) have = false;
+                else if (!std::getline(in, line)) break;
+                if (line.empty() || line[0] != '>') continue;       // bytes in front of the first record belong to nobody
                 Rec r; r.id = line.substr(1);
-                if (!r.id.empty() && r.id.back() == '\r') r.id.pop_back();
+                strip_cr(r.id);
                 if (cut_id_at_space) r.id = r.id.substr(0, r.id.find(' '));   // loadRecords base.cpp:154
                 while (std::getline(in, line))
                 {
-                    if (!line.empty() && (line[0] == '>' || line[0] == '@')) { have = true; break; }
+                    if (!line.empty() && line[0] == '>') { have = true; break; }
                     for (char c : line) if (c != '\r' && c != ' ') r.seq.push_back(ord5(c));
                 }
                 out.push_back(std::move(r));
             }
-            else if (line[0] == '@')
+        }
+        else if (format == 2)
+        {
+            std::string s, plus, q;
+            while (n == 0 || out.size() < n)
             {
+                if (!std::getline(in, line)) break;
+                const bool more = (bool)std::getline(in, s);
+                std::getline(in, plus); std::getline(in, q);
+                if (line.empty()) continue;
                 Rec r; r.id = line.substr(1);
+                strip_cr(r.id);
                 if (cut_id_at_space) r.id = r.id.substr(0, r.id.find(' '));
-                std::string s, plus, q;
-                std::getline(in, s); std::getline(in, plus); std::getline(in, q);
-                for (char c : s) if (c != '\r') r.seq.push_back(ord5(c));
+                if (more) for (char c : s) if (c != '\r') r.seq.push_back(ord5(c));
                 out.push_back(std::move(r));
             }
         }

@@ -1826,7 +1826,10 @@ __global__ void __launch_bounds__(128, LNR_BLOCKS_MIN_CTAS) k_hits_blocks(MapArg
 
 // ---- stage 2: window extension (path_dst_2 + extendWindow), one warp per read on a regular grid; reads are taken in
 // size order so that neighbouring warps have similar trip counts.
-__global__ void __launch_bounds__(128) k_map_extend(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int group)
+#ifndef LNR_EXTEND_MIN_CTAS
+#define LNR_EXTEND_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, LNR_EXTEND_MIN_CTAS) k_map_extend(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int group)
 {
     // the lanes of a warp cooperate on one read: they share the 18 script distances of a window step (sub-warp groups
     // and one thread per read were measured slower; `group` is kept in the signature and must be 32)
@@ -2230,8 +2233,8 @@ int lnr_ctx_create(int device, lnr_ctx ** out)
     ctx->n_sm = prop.multiProcessorCount;
     if (const char * e = getenv("LNR_MAP_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->map_ctas_per_sm = v; }
     if (const char * e = getenv("LNR_SORT_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->sort_ctas_per_sm = v; }
-    if (const char * e = getenv("LNR_CHAIN_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 6) ctx->chain_ctas_per_sm = v; }
-    if (const char * e = getenv("LNR_BLOCKS_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 6) ctx->blocks_ctas_per_sm = v; }
+    if (const char * e = getenv("LNR_CHAIN_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 12) ctx->chain_ctas_per_sm = v; }
+    if (const char * e = getenv("LNR_BLOCKS_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 12) ctx->blocks_ctas_per_sm = v; }
     if (const char * e = getenv("LNR_BIG_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 16384) ctx->big_arena_bytes_per_warp = (size_t)v << 20; }
     if (const char * e = getenv("LNR_ARENA_KB")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) ctx->arena_bytes_per_warp = (size_t)v << 10; }
     else if (const char * e = getenv("LNR_ARENA_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) ctx->arena_bytes_per_warp = (size_t)v << 20; }
@@ -3572,12 +3575,36 @@ __global__ void __launch_bounds__(256) k_unpack2(const u32 * __restrict__ packed
 int lnr_pack_dna5(const uint8_t * dna5, uint64_t n_bases, uint8_t * packed2, uint8_t * n_mask, int * has_n)
 {
     if ((!dna5 && n_bases) || !packed2) return LNR_E_ARG;
-    const uint64_t nb = (n_bases + 3) / 4, nm = (n_bases + 7) / 8;
-    memset(packed2, 0, (size_t)nb);
+    const uint64_t nm = (n_bases + 7) / 8;
     if (n_mask) memset(n_mask, 0, (size_t)nm);
     int any = 0;
-    for (uint64_t i = 0; i < n_bases; i++)
+    // 8 bases per step: two 32-bit multiplies gather the low 2 bits of 4 bytes each into one byte (base i at bits 2i);
+    // a group with an N (any byte > 3) takes the per-base path
+    uint64_t i = 0;
+    const uint64_t n8 = n_bases & ~7ull;
+    for (; i < n8; i += 8)
     {
+        uint64_t x;
+        memcpy(&x, dna5 + i, 8);
+        if ((x & 0xfcfcfcfcfcfcfcfcull) == 0)
+        {
+            const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+            packed2[i >> 2] = (uint8_t)((lo * 0x01041040u) >> 24);
+            packed2[(i >> 2) + 1] = (uint8_t)((hi * 0x01041040u) >> 24);
+            continue;
+        }
+        uint8_t b0 = 0, b1 = 0;
+        for (int k = 0; k < 8; k++)
+        {
+            const unsigned c = dna5[i + k];
+            if (c < 4) { if (k < 4) b0 |= (uint8_t)(c << (2 * k)); else b1 |= (uint8_t)(c << (2 * (k - 4))); }
+            else { any = 1; if (n_mask) n_mask[i >> 3] |= (uint8_t)(1u << k); }
+        }
+        packed2[i >> 2] = b0; packed2[(i >> 2) + 1] = b1;
+    }
+    for (; i < n_bases; i++)
+    {
+        if ((i & 3) == 0) packed2[i >> 2] = 0;
         const unsigned c = dna5[i];
         if (c < 4) packed2[i >> 2] |= (uint8_t)(c << (2 * (i & 3)));
         else { any = 1; if (n_mask) n_mask[i >> 3] |= (uint8_t)(1u << (i & 7)); }

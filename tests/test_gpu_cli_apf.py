@@ -8,6 +8,7 @@ straight from apxMap).
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 from cases import make_case
@@ -181,3 +182,24 @@ def test_cli_streams_the_read_file_in_chunks(tmp_path):
         outs.append(open(d / "reads.apf", "rb").read())
     assert len(outs[0]) > 1000 and outs[0].count(b"\n@") > 40
     assert outs[1] == outs[0] and outs[2] == outs[0]
+
+
+def test_cli_fastq_host_and_device_ingest_agree(tmp_path):
+    """4-line FASTQ with CRLF line ends and blanks in the ids: the device parser and the host reader (--host-ingest) follow
+    the same record model (ids without '\\r', sequence bytes without '\\r'), so the APF files are identical"""
+    g, reads, bases, offs, T, _ = make_case("clean_hifi")
+    gfa, rq = str(tmp_path / "genome.fa"), str(tmp_path / "reads.fq")
+    datagen.write_fasta(gfa, [f"chr{i + 1} synthetic" for i in range(len(g))], g)
+    alpha = np.frombuffer(b"ACGTN", np.uint8)
+    with open(rq, "wb") as f:
+        for i, r in enumerate(reads[:30]):
+            s = alpha[r].tobytes()
+            f.write(b"@read%d extra words\r\n" % i + s + b"\r\n+\r\n" + b"I" * len(s) + b"\r\n")
+    outs = []
+    for k, extra in enumerate(([], ["--host-ingest"])):
+        d = tmp_path / f"run{k}"
+        d.mkdir()
+        subprocess.run([CLI, "filter", rq, gfa, "-ot", "1", "-t", "4", "-p", "1"] + extra, cwd=d, check=True, timeout=900)
+        outs.append(open(d / "reads.apf", "rb").read())
+    assert outs[0].count(b"\n@") >= 20 and b"\r" not in outs[0]
+    assert outs[0] == outs[1]
