@@ -133,6 +133,66 @@ static void write_apf(std::ostream & of, const std::vector<Rec> & reads, const s
     of << st.str();
 }
 
+// ---- SAM* text (-ot 2): header (Mapper::setMapperBamHeaders mapper.cpp:288-321), then per read one line per record
+// (printAlignSamRecord f_io.cpp:525 -> writeSam :313). The records come from lnr_cords_to_records; every record is its
+// own line (cords2BamLink links nothing), a read with several records gets an SA:Z tag that lists the others
+// (createSAZTagOneLine align_util.cpp:719, createSAZTagCigar :452 -- the trailing soft clip never reaches the
+// simplified cigar there, :494, and zero-length elements are kept).
+static void write_sam_header(std::ostream & of, const std::vector<Rec> & genome)
+{
+    for (auto & gnm : genome) of << "@SQ\tSN:" << gnm.id << "\tLN:" << gnm.length() << "\n";
+    of << "@RG\tID:\tSM:\n" << "@PG\tID:M1-3\tPN:Linear\tCL:\n";
+}
+static void write_sam(std::ostream & of, const std::vector<Rec> & reads, const std::vector<Rec> & genome, const lnr_bam_rec * recs,
+                      const uint64_t * rec_off, const uint64_t * cig, const uint64_t * cig_off)
+{
+    std::ostringstream st;
+    for (size_t k = 0; k < reads.size(); k++)
+    {
+        const lnr_bam_rec * r = recs + rec_off[k];
+        const size_t nr = (size_t)(rec_off[k + 1] - rec_off[k]);
+        const uint64_t * c = cig + cig_off[k];
+        // the chimeric entry of every record, used by the other records' tags. Its NM field is the record's edit count only
+        // the first time the entry is produced, 0 afterwards: createSAZTagCigarOneChimeric (align_util.cpp:642) recomputes
+        // nm_i only while the simplified cigar is not cached yet and overwrites record.nm_i with 0 on every later call
+        std::vector<std::string> saz(nr), saz0(nr);
+        if (nr > 1)
+            for (size_t i = 0; i < nr; i++)
+            {
+                long cm = 0, ci = 0, nm = 0; uint32_t s0 = 0;
+                for (uint32_t j = r[i].cigar_begin; j < r[i].cigar_end; j++)
+                {
+                    const char op = (char)(c[j] >> 32); const uint32_t cnt = (uint32_t)c[j];
+                    if (j == r[i].cigar_begin && op == 'S') s0 = cnt;
+                    else if (op == '=') cm += cnt;
+                    else if (op == 'X') { cm += cnt; nm += cnt; }
+                    else if (op == 'I') { ci -= cnt; nm += cnt; }
+                    else if (op == 'D') { ci += cnt; nm += cnt; }
+                }
+                std::ostringstream e;
+                e << genome[r[i].rid].id << "," << (r[i].begin_pos + 1) << "," << ((r[i].flag & 16) ? '-' : '+') << "," << s0 << "S" << (uint32_t)cm << "M"
+                  << (uint32_t)(ci < 0 ? -ci : ci) << (ci < 0 ? 'I' : 'D') << "0S," << 255 << ",";
+                saz[i] = e.str() + std::to_string(nm) + ";";
+                saz0[i] = e.str() + "0;";
+            }
+        for (size_t i = 0; i < nr; i++)
+        {
+            st << reads[k].id << "\t" << r[i].flag << "\t" << genome[r[i].rid].id << "\t" << (r[i].begin_pos + 1) << "\t255\t";
+            if (r[i].cigar_end == r[i].cigar_begin) st << "*";
+            for (uint32_t j = r[i].cigar_begin; j < r[i].cigar_end; j++) st << (uint32_t)c[j] << (char)(c[j] >> 32);
+            st << "\t*\t0\t0\t*\t*";
+            if (nr > 1)
+            {
+                st << "\tSA:Z:";
+                for (size_t j = 0; j < nr; j++)
+                    if (j != i) st << (((j != 0 && i == 0) || (j == 0 && i == 1)) ? saz[j] : saz0[j]);
+            }
+            st << "\n";
+        }
+    }
+    of << st.str();
+}
+
 int main(int argc, char ** argv)
 {
     std::vector<std::string> pos;
@@ -207,8 +267,24 @@ int main(int argc, char ** argv)
     // output prefix = read file stem (mapper.cpp:904-906)
     std::string stem = rpath.substr(rpath.find_last_of('/') == std::string::npos ? 0 : rpath.find_last_of('/') + 1);
     stem = stem.substr(0, stem.find('.'));
-    std::ofstream of;
+    std::ofstream of, osam;
     if (ot & 1) of.open(stem + ".apf");
+    if (ot & 2) { osam.open(stem + ".sam"); write_sam_header(osam, genome); }
+    lnr_bam_parms bprm; memset(&bprm, 0, sizeof bprm);
+    bprm.window = feature_t == 1 ? 192 : 96; bprm.thd_large_x = 8000;                           // mapper.cpp:466
+    bprm.thd_di = preset == 1 ? 80 : (int64_t(1) << 60) - 1; bprm.thd_x = preset == 1 ? 200 : (int64_t(1) << 60) - 1;   // mapper.cpp:185, f_io.cpp:16
+    auto emit_sam = [&](const std::vector<Rec> & rd, const uint64_t * cords, const uint64_t * coff) -> int {
+        const uint32_t n = (uint32_t)rd.size();
+        std::vector<uint64_t> len(n), roff(n + 1), goff(n + 1);
+        for (uint32_t j = 0; j < n; j++) len[j] = rd[j].length();
+        int rc2 = lnr_cords_to_records(ctx, n, cords, coff, len.data(), &bprm, nullptr, 0, roff.data(), nullptr, 0, goff.data());
+        if (rc2 && rc2 != LNR_E_CAPACITY) return rc2;
+        std::vector<lnr_bam_rec> recs(roff[n] + 1);
+        std::vector<uint64_t> cig(goff[n] + 1);
+        if (roff[n] && (rc2 = lnr_cords_to_records(ctx, n, cords, coff, len.data(), &bprm, recs.data(), roff[n], roff.data(), cig.data(), goff[n], goff.data()))) return rc2;
+        write_sam(osam, rd, genome, recs.data(), roff.data(), cig.data(), goff.data());
+        return 0;
+    };
     lnr_params prm; memset(&prm, 0, sizeof prm); prm.preset = preset; prm.feature_type = feature_t;
     char main_icon = '+';
     uint64_t n_reads_total = 0, n_cords_total = 0;
@@ -273,6 +349,7 @@ int main(int argc, char ** argv)
                     return die("lnr_apxmap_reads", rc);
                 main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
                 if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, feature_t == 1 ? 192 : 96);
+                if ((ot & 2) && (rc = emit_sam(reads, cords.data(), coff.data()))) return die("lnr_cords_to_records", rc);
                 n_reads_total += n;
                 n_cords_total += coff.back();
             }
@@ -296,6 +373,7 @@ int main(int argc, char ** argv)
                 return die("lnr_apxmap_batch", rc);
             main_icon = '+';   // print_cords_apf re-initialises it per call (f_io.cpp:110)
             if (ot & 1) write_apf(of, reads, genome, cords.data(), coff.data(), main_icon, feature_t == 1 ? 192 : 96);
+            if ((ot & 2) && (rc = emit_sam(reads, cords.data(), coff.data()))) return die("lnr_cords_to_records", rc);
             n_reads_total += reads.size();
             n_cords_total += coff.back();
         }

@@ -48,6 +48,14 @@ using namespace lnr;
 // =====================================================================================================
 // host-side context
 // =====================================================================================================
+// 8 CTAs per SM (64 registers): both kernels are latency bound, the two extra CTAs buy more than the spills cost
+// (chain 1.78 -> 1.57 ms, blocks 1.38 -> 1.33 ms per 32 768 reads; 10 CTAs: no further gain)
+#ifndef LNR_CHAIN_MIN_CTAS
+#define LNR_CHAIN_MIN_CTAS 8
+#endif
+#ifndef LNR_BLOCKS_MIN_CTAS
+#define LNR_BLOCKS_MIN_CTAS 8
+#endif
 struct KernelStat { double ms; uint64_t launches; };
 
 struct DevBuf
@@ -127,7 +135,7 @@ struct lnr_ctx
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
-    int sort_ctas_per_sm = 8, chain_ctas_per_sm = 6, blocks_ctas_per_sm = 6;   // residency of the three hit-section kernels (their launch bounds)
+    int sort_ctas_per_sm = 8, chain_ctas_per_sm = LNR_CHAIN_MIN_CTAS, blocks_ctas_per_sm = LNR_BLOCKS_MIN_CTAS;   // residency of the three hit-section kernels (their launch bounds)
     int extend_group = 32;
     size_t arena_bytes_per_warp = 4u << 20;
 };
@@ -1744,12 +1752,7 @@ __global__ void __launch_bounds__(128, 8) k_hits_sort(MapArgs a)
     stage_end(a, c);
 }
 
-#ifndef LNR_CHAIN_MIN_CTAS
-#define LNR_CHAIN_MIN_CTAS 6
-#endif
-#ifndef LNR_BLOCKS_MIN_CTAS
-#define LNR_BLOCKS_MIN_CTAS 6
-#endif
+
 __global__ void __launch_bounds__(128, LNR_CHAIN_MIN_CTAS) k_hits_chain(MapArgs a)
 {
     StageCommon c;
@@ -1826,10 +1829,12 @@ __global__ void __launch_bounds__(128, LNR_BLOCKS_MIN_CTAS) k_hits_blocks(MapArg
 
 // ---- stage 2: window extension (path_dst_2 + extendWindow), one warp per read on a regular grid; reads are taken in
 // size order so that neighbouring warps have similar trip counts.
-#ifndef LNR_EXTEND_MIN_CTAS
-#define LNR_EXTEND_MIN_CTAS 1
+#ifdef LNR_EXTEND_MIN_CTAS
+#define LNR_EXTEND_BOUNDS __launch_bounds__(128, LNR_EXTEND_MIN_CTAS)
+#else
+#define LNR_EXTEND_BOUNDS __launch_bounds__(128)
 #endif
-__global__ void __launch_bounds__(128, LNR_EXTEND_MIN_CTAS) k_map_extend(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int group)
+__global__ void LNR_EXTEND_BOUNDS k_map_extend(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int group)
 {
     // the lanes of a warp cooperate on one read: they share the 18 script distances of a window step (sub-warp groups
     // and one thread per read were measured slower; `group` is kept in the signature and must be 32)
@@ -1862,7 +1867,9 @@ __global__ void __launch_bounds__(128, LNR_EXTEND_MIN_CTAS) k_map_extend(MapArgs
                 u32 nh = a.task_nhits[ti];
                 if (nh == 0xffffffffu) { ok = false; break; }
                 u64 base = a.aoff[t.sample0] + ti;
-                ok = path_dst_2(w1, in, a.A + base, (int)nh, cords, nc, cap, (u64)t.str, remap_pass ? ((u64)t.end & kMaskY) : (L & kMaskY), cnt);
+                const u64 rend = remap_pass ? ((u64)t.end & kMaskY) : (L & kMaskY);
+                ok = a.ft == 1 ? path_dst_2<1>(w1, in, a.A + base, (int)nh, cords, nc, cap, (u64)t.str, rend, cnt)
+                               : path_dst_2<2>(w1, in, a.A + base, (int)nh, cords, nc, cap, (u64)t.str, rend, cnt);
             }
             if (gl == 0)
             {

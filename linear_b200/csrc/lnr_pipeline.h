@@ -1130,13 +1130,14 @@ struct WinCtx
     u32 windows;        // candidates evaluated, added to the counters by the caller
     u64 hi;             // contig and strand bits of every cord of the walk
 };
+template <int FT>
 LNR_PIPE_INL WinCtx win_ctx(const Warp & w, const PipeIn & in, u64 cord)
 {
     WinCtx c;
     c.id = cord_id(cord); c.strand = cord_strand(cord);
-    c.ft = in.ft; c.win = in.win;
+    c.ft = FT ? FT : in.ft; c.win = FT == 1 ? (u32)kWin32 : (FT == 2 ? (u32)kWin : in.win);   // FT: the feature type as a compile-time constant
     c.fa = nullptr; c.fb = nullptr; c.sa = nullptr; c.sb = nullptr;
-    if (in.ft == 1) { c.sa = in.s1[c.strand]; c.sb = in.s2[c.id]; }
+    if (c.ft == 1) { c.sa = in.s1[c.strand]; c.sb = in.s2[c.id]; }
     else { c.fa = in.f1[c.strand]; c.fb = in.f2[c.id]; }
     c.nf1 = in.nf1; c.nf2 = in.nf2[c.id];
     int t = w.lane < 18 ? w.lane : 0;
@@ -1256,13 +1257,14 @@ LNR_PIPE_INL bool next_step(const Warp & w, WinCtx & c, u32 & xr, u32 & yr)   //
 }
 LNR_PIPE_INL u64 win_cord(const WinCtx & c, u32 xr, u32 yr) { return c.hi + ((u64)xr << 24) + ((u64)yr << 4); }
 // extendWindow :1152; returns false when the cord buffer is full. `last` == cords[n-1] on entry and exit.
+template <int FT>
 LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, int & n, int cap, u64 & last, u64 ystr, u64 yend,
                                 PipeCounters & cnt)
 {
     int p_str = n - 1;
     const u64 first = last;
     // every cord of the walk carries the contig and strand of its seeding cord (the windows only move x and y)
-    WinCtx wc = win_ctx(w, in, last);
+    WinCtx wc = win_ctx<FT>(w, in, last);
     const u32 x_first = (u32)(cord_x(last) >> 4), y_first = (u32)(cord_y(last) >> 4);
     u32 xr = x_first, yr = y_first;
     while (previous_step(w, wc, xr, yr) && ((u64)yr << 4) >= ystr)
@@ -1296,10 +1298,13 @@ LNR_PIPE_INL bool extend_window(const Warp & w, const PipeIn & in, u64 * cords, 
 
 // path_dst_2 (pmpfinder.cpp:1309), iterators restated as indices (hitBegin = 1). Warp-uniform.
 // Returns false on overflow.
+// FT = 0: the feature type is read from `in` (re-map / big-arena passes, host build); 1 / 2: compiled for that type alone, so
+// that the 2_48 walk of the extension kernel carries none of the 1_32 code
+template <int FT = 0>
 LNR_PIPE bool path_dst_2(const Warp & w, const PipeIn & in, const u64 * H, int nh, u64 * cords, int & nc, int cap, u64 read_str,
                          u64 read_end, PipeCounters & cnt)
 {
-    const u64 L = in.L, cs = in.win;
+    const u64 L = in.L, cs = FT == 1 ? (u64)kWin32 : (FT == 2 ? (u64)kWin : (u64)in.win);
     int hb = 1, he = nh;
     if (hb + 1 >= he) return true;
     u64 last;
@@ -1361,7 +1366,7 @@ LNR_PIPE bool path_dst_2(const Warp & w, const PipeIn & in, const u64 * H, int n
         }
         if (is_end(Hit) || f_block_end) { f_block_end = true; cordy_end = ready_end; }
         if (f_append)
-            if (!extend_window(w, in, cords, nc, cap, last, cordy_str, cordy_end, cnt)) return false;
+            if (!extend_window<FT>(w, in, cords, nc, cap, last, cordy_str, cordy_end, cnt)) return false;
         if (f_block_end)
         {
             last |= kFlagEnd;

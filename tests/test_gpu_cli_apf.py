@@ -203,3 +203,34 @@ def test_cli_fastq_host_and_device_ingest_agree(tmp_path):
         outs.append(open(d / "reads.apf", "rb").read())
     assert outs[0].count(b"\n@") >= 20 and b"\r" not in outs[0]
     assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/linear did not travel")
+@pytest.mark.parametrize("name,preset", [("clean_hifi", 1), ("repeat_ont", 1), ("repeat_ont", 0)])
+def test_cli_sam_identical_to_reference_binary(tmp_path, name, preset):
+    """-ot 3 (APF + SAM*), -g 0, -b 1: the SAM text written from lnr_cords_to_records' records -- header, flag, position,
+    cigar* (with the -p 1 split thresholds 80 / 200, mapper.cpp:185), SA:Z tags of reads with several records incl. the
+    reference's NM caching quirk -- is byte-identical to what the reference binary writes from its own cords"""
+    g, reads, bases, offs, T, _ = make_case(name)
+    gfa, rfa = str(tmp_path / "genome.fa"), str(tmp_path / "reads.fa")
+    datagen.write_fasta(gfa, [f"chr{i + 1} synthetic" for i in range(len(g))], g)
+    datagen.write_fasta(rfa, [f"read{i}" for i in range(len(reads))], reads)
+    d_ref, d_new = tmp_path / "ref", tmp_path / "new"
+    d_ref.mkdir(); d_new.mkdir()
+    common = ["filter", rfa, gfa, "-ot", "3", "-t", "4", "-p", str(preset), "-g", "0", "-b", "1"]
+    subprocess.run([REF_BIN] + common, cwd=d_ref, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+    subprocess.run([CLI] + common, cwd=d_new, check=True, timeout=900)
+    a = open(d_ref / "reads.sam", "rb").read()
+    b = open(d_new / "reads.sam", "rb").read()
+    assert a.count(b"\n") > 40
+    # the -b 1 scheduler of the reference writes its blocks in completion order: compare as sets of lines per read, in read order
+    def lines(t):
+        hdr = [l for l in t.split(b"\n") if l[:1] == b"@"]
+        rec = [l for l in t.split(b"\n") if l and l[:1] != b"@"]
+        return hdr, sorted(rec, key=lambda l: int(l.split(b"\t")[0][4:]))
+    ha, ra = lines(a)
+    hb, rb = lines(b)
+    assert ha == hb
+    assert ra == rb
+    if name == "repeat_ont":
+        assert any(b"SA:Z:" in l for l in rb)

@@ -39,3 +39,35 @@ def test_reference_host_stages_consume_gpu_cords(tmp_path, extra):
     b = _strip(open(d_new / "reads.apf", "rb").read())
     assert len(a) > 1000 and a.count(b"\n@") + 1 >= 40
     assert a == b
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(HYBRID)), reason="oracle/_ref (compiled reference + hybrid) did not travel")
+def test_samples_stream_against_replicated_index(tmp_path):
+    """BASELINE configs[4] in miniature: several samples are streamed at the same time (`-b 1` scheduler, -ot 3 = APF + SAM,
+    host gap mapping on), one hybrid process per sample, each with its own replica of the index on the GPU it is given
+    (LNR_DEVICE; all of them on GPU 0 when the box has one). Every sample's APF and SAM equal the all-CPU reference's."""
+    import torch
+    n_gpu = max(torch.cuda.device_count(), 1)
+    g, reads, bases, offs, T, _ = make_case("clean_hifi")
+    gfa = str(tmp_path / "genome.fa")
+    datagen.write_fasta(gfa, [f"chr{i + 1} synthetic" for i in range(len(g))], g)
+    n_samples = 3
+    procs = []
+    for s in range(n_samples):
+        sub = reads[s::n_samples]
+        rfa = str(tmp_path / f"sample{s}.fa")
+        datagen.write_fasta(rfa, [f"s{s}_read{i}" for i in range(len(sub))], sub)
+        d_ref, d_new = tmp_path / f"ref{s}", tmp_path / f"new{s}"
+        d_ref.mkdir(); d_new.mkdir()
+        common = ["filter", rfa, gfa, "-ot", "3", "-t", "2", "-b", "1"]
+        subprocess.run([REF_BIN] + common, cwd=d_ref, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        env = dict(os.environ, LNR_ARENA_KB="1024", LNR_DEVICE=str(s % n_gpu))
+        procs.append((s, subprocess.Popen([HYBRID] + common, cwd=d_new, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)))
+    for s, p in procs:
+        out, _ = p.communicate(timeout=900)
+        assert p.returncode == 0, out[-2000:]
+        for ext in ("apf", "sam"):
+            a = _strip(open(tmp_path / f"ref{s}" / f"sample{s}.{ext}", "rb").read())
+            b = _strip(open(tmp_path / f"new{s}" / f"sample{s}.{ext}", "rb").read())
+            assert a == b, (s, ext)
+        assert os.path.getsize(tmp_path / f"new{s}" / f"sample{s}.apf") > 1000
