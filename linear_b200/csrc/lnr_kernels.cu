@@ -7,7 +7,7 @@
 //   features  F96 (3 x int32) per 16 bases; per contig for the genome, per (read, strand) for a batch
 //   batch     read bases back to back, anchors / scratch per read, cords per read at host-computed offsets
 //
-//   lookup    hsy: the Y byte of every hs record; dirx: per bucket one 32-B sector (start, size, first 24 Y keys)
+//   lookup    hsy: the Y byte of every hs record; dirx: per bucket 64 B = one DRAM burst (start, size, first 56 Y keys)
 //
 // Kernels (all HBM / issue / latency bound integer work, no tensor-core shaped math on this path)
 //   k_feat_genome / k_feat_reads      2-mer/48 features: one thread per 16-base cell, 3-cell sums through smem; reads:
@@ -168,7 +168,7 @@ struct lnr_index
     u64 * d_hs;
     uint64_t n_hs;
     u8 * d_hsy = nullptr;    // low byte (the 8-bit Y key) of every hs record, split out for the seeding count pass
-    uint4 * d_dirx = nullptr; // per bucket 32 B: start, size and the first 24 Y keys -- one DRAM access per seed for most buckets
+    uint4 * d_dirx = nullptr; // per bucket 64 B: start, size and the first 56 Y keys -- one DRAM access per seed for most buckets
     // HIndex (include/index_util.h:139-248)
     u64 * d_ysa = nullptr;
     uint64_t n_ysa = 0, empty_dir = 0;
@@ -706,25 +706,31 @@ __global__ void k_idx_split_y(const u64 * __restrict__ hs, u64 n, u8 * __restric
     if (i < n) hsy[i] = (u8)(hs[i] & 0xff);
 }
 
-// Lookup entry of the seeding count pass: dir[X], the bucket size and the bucket's first 24 Y keys in one 32-byte
-// sector. A seed whose bucket has <= 24 records (most) then costs one random DRAM access instead of two (dir, hsy).
+// Lookup entry of the seeding count pass: dir[X], the bucket size and the bucket's first 56 Y keys in 64 bytes = the two
+// sectors one DRAM access brings in anyway (ncu: every L2 read miss of the random-access kernels fetches 64 B). A seed
+// whose bucket has <= 56 records (95 % of them at 3.1 Gbase) costs one random DRAM access; with 32-byte entries (24 keys)
+// every second seed paid a second, dependent one into hsy.
+static const int kDirxKeys = 56, kDirxQuads = 4;      // keys per entry, uint4 per entry
 __global__ void k_idx_dirx(const i32 * __restrict__ dir, const u8 * __restrict__ hsy, u32 n_buckets, uint4 * __restrict__ out)
 {
     u32 X = blockIdx.x * blockDim.x + threadIdx.x;
     if (X >= n_buckets) return;
     const i32 b = dir[X], e = dir[X + 1];
     const u32 n = (u32)(e - b);
-    u32 wds[6];
+    u32 wds[14];
 #pragma unroll
-    for (int q = 0; q < 6; q++)
+    for (int q = 0; q < 14; q++)
     {
         u32 v = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) { u32 idx = 4 * q + k; if (idx < n) v |= (u32)hsy[(size_t)b + idx] << (8 * k); }
         wds[q] = v;
     }
-    out[2 * (size_t)X] = make_uint4((u32)b, n, wds[0], wds[1]);
-    out[2 * (size_t)X + 1] = make_uint4(wds[2], wds[3], wds[4], wds[5]);
+    uint4 * o = out + (size_t)kDirxQuads * X;
+    o[0] = make_uint4((u32)b, n, wds[0], wds[1]);
+    o[1] = make_uint4(wds[2], wds[3], wds[4], wds[5]);
+    o[2] = make_uint4(wds[6], wds[7], wds[8], wds[9]);
+    o[3] = make_uint4(wds[10], wds[11], wds[12], wds[13]);
 }
 
 // ascending order inside each bucket (index_util.cpp:1788-1796); one thread per bucket, buckets <= 400
@@ -1219,7 +1225,7 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         }
         if (sv.X != xprev)
         {
-            e0 = __ldg(dirx + 2 * (size_t)sv.X); e1 = __ldg(dirx + 2 * (size_t)sv.X + 1);
+            e0 = __ldg(dirx + (size_t)kDirxQuads * sv.X); e1 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 1);
             bkt_b = (i32)e0.x;
             qY = sv.Y;
             scanned = e0.y;
@@ -1243,22 +1249,31 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         return h4;
     };
     u64 m0 = 0;   // matches among the bucket's first 64 records; longer buckets (rare) are scanned again when emitting
-    const u8 * pb = hsy + bkt_b + 24;
+    const u8 * pb = hsy + bkt_b + kDirxKeys;
     const unsigned sh = ((unsigned)(uintptr_t)pb & 3u) * 8u;
     const u32 * pw = (const u32 *)((uintptr_t)pb & ~(uintptr_t)3);
     if (active)
     {
-        // records 0..23 come with the lookup entry
+        // records 0..23 come with the first half of the lookup entry, 24..55 with its second half (the same 64-byte DRAM
+        // burst: an L2 hit), only longer buckets go on in hsy
         const u32 ew[6] = {e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
         for (int q = 0; q < 6; q++)
             if (4u * q < scanned) { u32 h4 = match4(ew[q], 4u * q); c += __popc(h4); m0 |= (u64)h4 << (4 * q); }
         if (scanned > 24)
         {
+            const uint4 e2 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 2), e3 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 3);
+            const u32 fw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (24u + 4u * q < scanned) { u32 h4 = match4(fw[q], 24u + 4u * q); c += __popc(h4); m0 |= (u64)h4 << (24 + 4 * q); }
+        }
+        if (scanned > (u32)kDirxKeys)
+        {
             u32 w0 = __ldg(pw);
-            for (u32 i = 24; i < scanned; i += 4)
+            for (u32 i = kDirxKeys; i < scanned; i += 4)
             {
-                u32 w1 = __ldg(pw + ((i - 24) >> 2) + 1);
+                u32 w1 = __ldg(pw + ((i - kDirxKeys) >> 2) + 1);
                 u32 h4 = match4(__funnelshift_r(w0, w1, sh), i);
                 c += __popc(h4);
                 if (i < 64) m0 |= (u64)h4 << i;
@@ -1292,10 +1307,10 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         while (m0) { int bit = __ffsll((long long)m0) - 1; m0 &= m0 - 1; *o++ = tag + (u32)bit; }
         if (scanned > 64)
         {
-            u32 w0 = __ldg(pw + 10);
+            u32 w0 = __ldg(pw + 2);
             for (u32 i = 64; i < scanned; i += 4)
             {
-                u32 w1 = __ldg(pw + ((i - 24) >> 2) + 1);
+                u32 w1 = __ldg(pw + ((i - kDirxKeys) >> 2) + 1);
                 u32 h4 = match4(__funnelshift_r(w0, w1, sh), i);
                 while (h4) { int bit = __ffs((int)h4) - 1; h4 &= h4 - 1; *o++ = tag + i + (u32)bit; }
                 w0 = w1;
@@ -1387,7 +1402,7 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u8 * __restrict__ bases
         SeedVal sv; u32 kk;
         const u32 m = (u32)(s - t.sample0) + 1;
         if (!seed_sample_fast(acc.s, acc.len, t, m, sv)) seed_sample(acc, t, m, sv, kk);
-        const uint4 d0 = __ldg(dirx + 2 * (size_t)sv.X);
+        const uint4 d0 = __ldg(dirx + (size_t)kDirxQuads * sv.X);
         u64 * out = anchors + a0 + e + ti + 1;
         for (u32 i = 0; i < d0.y; i++)
         {
@@ -2593,7 +2608,7 @@ int lnr_index_export_dindex_device(const lnr_index * ix, int32_t * dev_dir, uint
 static cudaError_t index_build_dirx(lnr_ctx * ctx, lnr_index * ix)
 {
     if (ix->d_dirx || ix->index_type != 1) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&ix->d_dirx, (size_t)(kDirSize - 1) * 32);
+    cudaError_t e = cudaMalloc(&ix->d_dirx, (size_t)(kDirSize - 1) * 16 * kDirxQuads);
     if (e != cudaSuccess) return e;
     LaunchScope ls(ctx, "k_idx_dirx");
     k_idx_dirx<<<((kDirSize - 1) + 255) / 256, 256, 0, ctx->stream>>>(ix->d_dir, ix->d_hsy, kDirSize - 1, ix->d_dirx);
@@ -2817,7 +2832,7 @@ static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_se
     CKI(cudaMalloc(&ix->d_hs, (size_t)(total + 8) * sizeof(u64)));
     const bool derive_here = !comm;                  // sharded: Y bytes and lookup sectors are derived after the exchange
     CKI(cudaMalloc(&ix->d_hsy, (size_t)total + 64));
-    if (full_range || comm) CKI(cudaMalloc(&ix->d_dirx, (size_t)(kDirSize - 1) * 32));
+    if (full_range || comm) CKI(cudaMalloc(&ix->d_dirx, (size_t)(kDirSize - 1) * 16 * kDirxQuads));
     {
         // partition by partition: stage the records in their buckets, then move every record to its rank -- while the
         // partition's range is still in L2. The pair buffers of the emit pass are free by now and serve as the staging area.
