@@ -114,7 +114,13 @@ typedef struct lnr_params
 {
     int preset;       /* -p: 0 => thd_stop_chain_len_ratio 0.7, 1/2 => 0 (mapper.cpp:174-197); code default 1 */
     int feature_type; /* -f: 2 or 1; 0 = whatever the genome features were built with */
-    int reserved[6];
+    int no_chain;     /* 1 = -c 0: apxMap with f_chain = 0 (alg_type 1, pmpfinder.cpp:2773-2787): anchors grouped by sorting
+                       * (getDAnchorList :2185, getDHitList :2246), path_dst_1 :1269, a second attempt at k-mer step 7 when the
+                       * longest block covers < 0.7 of the read; 0 = the default chaining path (f_chain = 1) */
+    int gdl_state;    /* -c 0 only. The reference keeps one PMPParms per thread and this mode changes it for good:
+                       * GetDHitListParms starts as (thd_list_n 20, thd_best_n 1) and is (10, 999) from the first read that
+                       * needed the second attempt on (toggle(0), :2784). 0 = the state as constructed, 1 = the later one. */
+    int reserved[4];
 } lnr_params;
 
 /* optional stage checkpoints; any pointer may be NULL. Offsets arrays hold n_reads+1 entries. */

@@ -44,7 +44,7 @@ class LnrError(RuntimeError):
 
 
 class Params(C.Structure):
-    _fields_ = [("preset", C.c_int), ("feature_type", C.c_int), ("reserved", C.c_int * 6)]
+    _fields_ = [("preset", C.c_int), ("feature_type", C.c_int), ("no_chain", C.c_int), ("gdl_state", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class BamParms(C.Structure):
@@ -424,16 +424,18 @@ def selftest_sort(ctx: Context, records: np.ndarray) -> np.ndarray:
 
 
 def apx_map_batch(ctx: Context, index: Index, feats: Features, bases, offsets, preset: int = 1, debug: bool = False,
-                  cords_out: Optional[np.ndarray] = None, cords_off_out: Optional[np.ndarray] = None):
+                  cords_out: Optional[np.ndarray] = None, cords_off_out: Optional[np.ndarray] = None, no_chain: bool = False,
+                  gdl_state: int = 0):
     """bases: uint8 host buffer (numpy array; pass the numpy view of a pinned torch tensor for full PCIe speed),
-    offsets: uint64[n+1]. Returns (cords uint64[], cords_off uint64[n+1][, debug dict])."""
+    offsets: uint64[n+1]. Returns (cords uint64[], cords_off uint64[n+1][, debug dict]).
+    no_chain = the reference's -c 0 (apxMap with f_chain = 0); gdl_state: see lnr_params in include/lnr_b200.h."""
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     n = len(offsets) - 1
     cap = int(len(bases) // 16 + 64 * n + 1024) if cords_out is None else len(cords_out)
     cords = np.empty(cap, dtype=np.uint64) if cords_out is None else cords_out
     coff = np.zeros(n + 1, dtype=np.uint64) if cords_off_out is None else cords_off_out
-    prm = Params(preset=preset, feature_type=feats.feature_type)
+    prm = Params(preset=preset, feature_type=feats.feature_type, no_chain=int(no_chain), gdl_state=gdl_state)
     dbg = None
     keep = {}
     if debug:

@@ -2004,6 +2004,89 @@ __global__ void __launch_bounds__(128) k_map_finish(MapArgs a, const u32 * __res
     }
 }
 
+// ---- -c 0 (apxMap with f_chain = 0, alg_type 1): one warp per read runs a whole attempt -- sort, run list, hits, path_dst_1
+// (phase_c0). attempt 0 = the primary tasks (k-mer step 15); a read whose longest block stays below 0.7 of its length
+// (c0_attempt_too_short) becomes a task of the second attempt (step 7, GetDHitListParms 20 / 1), which the host seeds and
+// runs through this kernel again; whichever attempt is the read's last also cleans the blocks and sets the flags.
+__global__ void __launch_bounds__(128) k_map_c0(MapArgs a, int attempt, int big_pass, int list_n, int best_n)
+{
+    __shared__ u32 s_hist[4][kWarpSmemWords];
+    for (int i = threadIdx.x; i < 4 * kWarpSmemWords; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    Warp w = {(int)(threadIdx.x & 31), 0xffffffffu};
+    u32 wid = threadIdx.x >> 5;
+    u32 gw = blockIdx.x * (blockDim.x >> 5) + wid;
+    Arena ar = {a.arena + (u64)gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
+    if (big_pass) { ar.base = a.big_arena + (u64)gw * a.big_arena_per_warp; ar.cap = a.big_arena_per_warp; }
+    const u32 n_units = big_pass ? *a.n_big : a.n_tasks;
+    PipeCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    u64 c_cords = 0;
+    while (true)
+    {
+        u32 q = 0;
+        if (w.lane == 0) q = atomicAdd(a.queue, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= n_units) break;
+        u32 ti = big_pass ? a.big_list[q] : (attempt ? q : a.order[q]);
+        if (big_pass && w.lane == 0) atomicAdd(&a.counters[16], 1ULL);
+        const SeedTask t = a.tasks[ti];
+        const u32 r = t.read;
+        const u64 L = a.read_off[r + 1] - a.read_off[r];
+        ReadSlot slot;
+        slot.n_cords = 0; slot.status = 0; slot.task0 = 0; slot.n_tasks = 0;
+        if (L <= (u64)kMinReadLen) { if (w.lane == 0) a.slots[r] = slot; continue; }   // mapper.cpp:440
+        PipeIn in;
+        fill_pipe_in(a, r, in);
+        u64 base; int n;
+        task_region(a, ti, t, base, n);
+        u64 * cords = a.cords + a.cords_base[r];
+        const int cap = (int)(a.cords_base[r + 1] - a.cords_base[r]);
+        int nc = 0;
+        u64 max_len = 0;
+        int rc = a.ft == 1 ? phase_c0<1>(w, ar, s_hist[wid], in, a.A + base, a.B + base, n, list_n, best_n, cords, nc, cap, cnt, max_len, big_pass != 0)
+                           : phase_c0<2>(w, ar, s_hist[wid], in, a.A + base, a.B + base, n, list_n, best_n, cords, nc, cap, cnt, max_len, big_pass != 0);
+        if (rc == 2)
+        {
+            if (w.lane == 0) a.big_list[atomicAdd(a.n_big, 1u)] = ti;      // untouched: re-run with the big arena
+            continue;
+        }
+        if (rc) { slot.status = 2; if (w.lane == 0) a.slots[r] = slot; continue; }
+        if (attempt == 0 && c0_attempt_too_short(max_len, L, a.win))
+        {
+            // clear(cords_str); toggle(1); second attempt (pmpfinder.cpp:2781-2784)
+            u32 t0 = 0;
+            if (w.lane == 0)
+            {
+                t0 = atomicAdd(a.n_tasks2, 1u);
+                if (t0 < a.tasks2_cap)
+                {
+                    SeedTask t2;
+                    t2.read = r; t2.str = 0; t2.end = (u32)L; t2.alpha = 7;
+                    t2.n_samples = a.index_type == 2 ? hseed_task_samples(0, (u32)L, 7) : seed_task_samples(0, (u32)L, 7);
+                    t2.bias = 0; t2.kskip = 0; t2.pad = 0; t2.sample0 = 0;
+                    a.tasks2[t0] = t2;
+                }
+            }
+            t0 = __shfl_sync(0xffffffffu, t0, 0);
+            slot.status = t0 < a.tasks2_cap ? 1u : 2u;
+            slot.task0 = t0; slot.n_tasks = 1;
+            if (w.lane == 0) a.slots[r] = slot;
+            continue;
+        }
+        c0_finish(w, L, cords, nc, a.win);
+        slot.n_cords = (u32)nc;
+        c_cords += (u64)nc;
+        if (w.lane == 0) a.slots[r] = slot;
+    }
+    if (w.lane == 0)
+    {
+        if (cnt.hits) atomicAdd(&a.counters[3], (unsigned long long)cnt.hits);
+        if (cnt.windows) atomicAdd(&a.counters[4], (unsigned long long)cnt.windows);
+        if (c_cords) atomicAdd(&a.counters[5], (unsigned long long)c_cords);
+    }
+}
+
 __global__ void k_slot_counts(const ReadSlot * __restrict__ slots, u32 n, u32 * __restrict__ cnt, u32 * __restrict__ n_fail)
 {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -3103,6 +3186,20 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     ctx->anchors_host_total = 0;
     if (n_reads == 0) { if (n_cords_total) *n_cords_total = 0; return LNR_OK; }
     const float stop_ratio = prm && prm->preset == 0 ? 0.7f : 0.0f;
+    const bool no_chain = prm && prm->no_chain;
+    if (no_chain && ix->index_type == 2)
+    {
+        // -c 0 with -i 2 maps nothing in the reference: getHIndexMatchAll takes its record window from the x fields of
+        // map_str / map_end (pmpfinder.cpp:1932-1933, idx_end = getCordX(map_end)) and this mode passes the bare read length
+        // as map_end (:2778), so idx_end = 0, no record is accepted in either attempt and every read comes back without cords
+        CK(ctx->out_off.reserve((size_t)(n_reads + STILE + 1) * sizeof(u64)));
+        CK(cudaMemsetAsync(d_out_off ? (void *)d_out_off : ctx->out_off.p, 0, ((size_t)n_reads + 1) * sizeof(u64), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memset(ctx->counters, 0, sizeof ctx->counters);
+        ctx->counters[6] = h_read_off[n_reads];
+        if (n_cords_total) *n_cords_total = 0;
+        return LNR_OK;
+    }
     const int ft = f2->feature_type;
     if (prm && prm->feature_type != 0 && prm->feature_type != ft) return fail(ctx, LNR_E_ARG, "lnr_params.feature_type differs from the genome features' type");
     const u32 fe_tile = ft == 1 ? (u32)(FT - 1) : (u32)FE;      // entries per feature tile
@@ -3303,6 +3400,67 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         a.warp_rec_stage_off = n_warps * 24;
         a.warp_rec_stage_stride = n_warps;
     }
+    u32 n_tasks2 = 0;
+    if (no_chain)
+    {
+        // -c 0: one kernel per attempt (k_map_c0) plus its big-arena launch; the second attempt is seeded at step 7 for the
+        // reads the first one left too short
+        if (c0_scratch_bound((int)std::min<u64>(total_anchors + n_reads + 2, 0x7ffffff0ull)) > big_per_warp)
+        {
+            big_per_warp = (size_t)std::min<u64>((c0_scratch_bound((int)std::min<u64>(total_anchors + n_reads + 2, 0x7ffffff0ull)) + (1u << 20) - 1) & ~(u64)((1u << 20) - 1),
+                                                 ctx->big_arena_bytes_per_warp);
+            CK(ctx->big_arena.reserve(32 * big_per_warp));
+            a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
+        }
+        const int gdl = prm->gdl_state ? 1 : 0;
+        auto run_attempt = [&](int attempt, int list_n, int best_n, const char * tag, const char * tag_big) -> int {
+            CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+            CK(cudaMemsetAsync(d_queue + 3, 0, sizeof(u32), ctx->stream));
+            {
+                LaunchScope ls(ctx, tag);
+                k_map_c0<<<n_ctas, wpc * 32, 0, ctx->stream>>>(a, attempt, 0, list_n, best_n);
+            }
+            CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+            {
+                LaunchScope ls(ctx, tag_big);
+                k_map_c0<<<8, 128, 0, ctx->stream>>>(a, attempt, 1, list_n, best_n);
+            }
+            CK(cudaGetLastError());
+            return LNR_OK;
+        };
+        rc = run_attempt(0, gdl ? 10 : 20, gdl ? 999 : 1, "k_map_c0", "k_map_c0_big");
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&n_tasks2, d_ntasks2, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (n_tasks2 > tasks2_cap) return fail(ctx, LNR_E_CAPACITY, "second-attempt task buffer exhausted");
+        if (n_tasks2)
+        {
+            std::vector<SeedTask> t2(n_tasks2);
+            CK(cudaMemcpyAsync(t2.data(), ctx->tasks2.p, n_tasks2 * sizeof(SeedTask), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            std::sort(t2.begin(), t2.end(), [](const SeedTask & x, const SeedTask & y) { return x.read < y.read; });   // deterministic layout
+            u64 ns2 = 0;
+            for (u32 i = 0; i < n_tasks2; i++) { t2[i].sample0 = ns2; ns2 += t2[i].n_samples; }
+            CK(upload_small(ctx, ctx->tasks2.p, t2.data(), n_tasks2 * sizeof(SeedTask)));
+            u64 total2 = 0;
+            rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_c0_retry");
+            if (rc) return rc;
+            const u64 need2 = (c0_scratch_bound((int)std::min<u64>(total2 + n_tasks2 + 2, 0x7ffffff0ull)) + (1u << 20) - 1) & ~(u64)((1u << 20) - 1);
+            if (std::min<u64>(need2, ctx->big_arena_bytes_per_warp) > big_per_warp)
+            {
+                big_per_warp = (size_t)std::min<u64>(need2, ctx->big_arena_bytes_per_warp);
+                CK(ctx->big_arena.reserve(32 * big_per_warp));
+            }
+            a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
+            a.tasks = ctx->tasks2.as<SeedTask>(); a.n_tasks = n_tasks2;
+            a.aoff = aoff.as<u64>();
+            a.A = ctx->anchorsA.as<u64>(); a.B = ctx->anchorsB.as<u64>();
+            rc = run_attempt(1, 20, 1, "k_map_c0_retry", "k_map_c0_retry_big");
+            if (rc) return rc;
+        }
+    }
+    else
+    {
     if (getenv("LNR_MONOLITHIC_HITS"))
     {
         LaunchScope ls(ctx, "k_map_hits");
@@ -3369,7 +3527,6 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(cudaGetLastError());
     tr.lap("launch_map");
     // ---- re-map pass
-    u32 n_tasks2 = 0;
     CK(cudaMemcpyAsync(&n_tasks2, d_ntasks2, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     tr.lap("map(sync)");
@@ -3430,6 +3587,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         }
         CK(cudaGetLastError());
     }
+    }   // f_chain = 1
     tr.lap("remap", true);
     // ---- compaction into the caller's layout
     {

@@ -109,7 +109,7 @@ struct SortKey
 {
     int mode;          // 0 anchor value ascending, 1 AnchorX descending, 2 y of the hit a cut points to, 3 Blk.second ascending
                        // (Blk viewed as u64: first low, second high), 4 x40 of a block's first record descending (elements
-                       // are block indices)
+                       // are block indices), 5 / 6: the two sorts of the -c 0 path
     const u64 * recs;  // modes 2, 4
     const Blk * sep;   // mode 4
     LNR_HD u64 operator()(u64 v) const
@@ -120,6 +120,8 @@ struct SortKey
         case 1: return (u64)0x3fffffffULL - anchor_x(v);
         case 2: return cord_y(recs[v & ~(1ULL << 62)]);
         case 3: return v >> 32;
+        case 5: return v & kMaskY;              // -c 0: Anchors::sortPos2 (base.cpp:303)
+        case 6: return ~v;                      // -c 0: the run list, descending (getDHitList pmpfinder.cpp:2252)
         default: return ((1ULL << 40) - 1) - cord_x40(recs[sep[(u32)v].first]);
         }
     }
@@ -1982,6 +1984,240 @@ LNR_PIPE void phase_finish_w(const Warp & w, u64 L, u64 * cords, int & n_cords, 
         u32 m = wballot(w, i < n_cords && is_end(c));
         int seg = (ends_before + popc_below(w, m)) & 1;
         if (i < n_cords)
+        {
+            if (seg) c |= kFlagRecd; else c &= ~kFlagRecd;
+            cords[i] = c | kFlagMain;
+        }
+        ends_before += popc32(m);
+    }
+    wsync(w);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// -c 0 (apxMap with f_chain = 0, alg_type 1; pmpfinder.cpp:2773-2787): the anchors are grouped by sorting instead of the
+// chaining DP. getDAnchorMatchList :2301 = getDAnchorList :2185 + getDHitList :2246, then path_dst_1 :1269.
+// ----------------------------------------------------------------------------------------------------
+// single IEEE operations, never contracted or approximated: the reference's float compares decide which anchors group
+LNR_HD float c0_fmul(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+LNR_HD float c0_fdiv(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+LNR_HD u64 c0_scratch_bound(int n) { return ((u64)n + 4) * 24 + 1024; }
+
+// getDAnchorList over the ascending anchors S[0..n) (S[0] = 0, the Anchors::init entry): a sequential recurrence -- the
+// running medians ak2 / ak3 depend on every decision before -- that all lanes follow in step (the loads are broadcasts);
+// lane 0 records the accepted runs as (c_b << 40) + (sb << 20) + k. The reference sorts an accepted run by y on the spot
+// (sortPos2); nothing later in the scan reads below k, so here only the runs that become hits are sorted, by the caller.
+// float thresholds exactly as the reference declares them (0.001f, 0.01f, 0.2f).
+LNR_PIPE int c0_anchor_list(const Warp & w, const u64 * S, int n, u64 read_str, u64 read_end, u64 * list)
+{
+    const float dens = 0.001f, lens_rate = 0.01f, err = 0.2f;
+    const i64 shape_len = 21;                                   // GlobalParms::shape_len base.cpp:99
+    const i64 accept_lens = (i64)c0_fmul(lens_rate, (float)(read_end - read_str));
+    int nl = 0;
+    if (n <= 1) return 0;
+    u64 ak2 = S[0], ak3 = S[0];
+    i64 c_b = shape_len, sb = 1;
+    u64 min_y = ~0ULL, max_y = 0;
+    u64 prev = S[0];
+    for (int k = 1; k < n; k++)
+    {
+        const u64 ak = S[k];
+        const i64 anc_y = (i64)cord_y(ak);
+        const i64 dy2 = iabs64(anc_y - (i64)cord_y(ak2)), dy3 = iabs64(anc_y - (i64)cord_y(ak3));
+        const bool f_cont = (float)cord_x(ak - ak2) < c0_fmul(err, (float)dy2) || (float)cord_x(ak - ak3) < c0_fmul(err, (float)dy3);
+        if (f_cont)
+        {
+            i64 dy = iabs64((i64)cord_y(ak) - (i64)cord_y(prev));
+            c_b += imin64(dy, shape_len);
+            ak2 = S[(sb + k) >> 1];
+            ak3 = S[k - ((k - sb) >> 2)];
+            const u64 y = cord_y(ak);
+            min_y = y < min_y ? y : min_y;
+            max_y = y > max_y ? y : max_y;
+        }
+        if (!f_cont || k == n - 1)
+        {
+            if (c_b > accept_lens && (i64)k - sb >= (i64)(u32)c0_fmul((float)(max_y - min_y), dens))
+            {
+                if (w.lane == 0) list[nl] = (u64)((c_b << 40) + (sb << 20) + (i64)k);
+                nl++;
+            }
+            sb = k;
+            ak2 = ak; ak3 = ak;
+            c_b = shape_len;
+            min_y = max_y = cord_y(ak);
+        }
+        prev = ak;
+    }
+    wsync(w);
+    return nl;
+}
+
+// path_dst_1 :1269 with initCord :1178, nextCord :1209, endCord :1200 over the hits H[1..nh) (H[0] the sentinel), into an
+// EMPTY cord list. Warp-uniform; the window extension is the one of path_dst_2. Returns false on overflow. max_len = the
+// low 20 bits of cords[0] (Cord::setMaxLen cords.cpp:122), what apxMap compares with thd_sen.
+template <int FT = 0>
+LNR_PIPE bool path_dst_1(const Warp & w, const PipeIn & in, const u64 * H, int nh, u64 * cords, int & nc, int cap, u64 read_str,
+                         u64 read_end, PipeCounters & cnt, u64 & max_len)
+{
+    const u64 L = in.L, cs = FT == 1 ? (u64)kWin32 : (FT == 2 ? (u64)kWin : (u64)in.win);
+    max_len = 0;
+    nc = 0;
+    if (nh < 2) return true;                                    // path_dst :1457 isHitsEmpty
+    if (cap < 2) return false;
+    u64 c0 = kFlagEnd;                                          // cords[0]; rewritten by setMaxLen at the end
+    int it = 1;
+    u64 last = H[it++];
+    if (w.lane == 0) { cords[0] = c0; cords[1] = last; }
+    nc = 2;
+    int pre = 1;
+    while (true)
+    {
+        wsync(w);
+        const u64 strand = cord_strand(last);
+        u64 cordy_str = strand ? L - read_end : read_str;
+        const u64 cordy_end = strand ? L - read_str - 1 : read_end;
+        const u64 before = cords[nc - 2];
+        const u64 pre_y = is_end(before) ? 0 : cord_y(before) + 1;
+        cordy_str = pre_y > cordy_str ? pre_y : cordy_str;
+        if (!extend_window<FT>(w, in, cords, nc, cap, last, cordy_str, cordy_end, cnt)) return false;
+        // nextCord: the first later hit that starts a new block or lies behind the last cord, passes the window test and
+        // stays inside [read_str, read_end)
+        bool found = false, f_new_block = false;
+        while (it < nh)
+        {
+            if (is_end(H[it - 1]))
+            {
+                last |= kFlagEnd;
+                if (w.lane == 0) cords[nc - 1] = last;
+                pre = nc;
+                f_new_block = true;
+            }
+            const u64 h = H[it++];
+            if (cord_y(h) > cord_y(last) || f_new_block)
+            {
+                const u32 st = (u32)cord_strand(h), id = (u32)cord_id(h);
+                const u64 x1 = cord_y(h) >> 4, x2 = cord_x(h) >> 4;
+                u32 dist;   // _windowDist :676, the bounds-checked wrapper (as in _filterHits)
+                if ((FT ? FT : in.ft) == 1) dist = (x1 < in.nf1 && x2 < in.nf2[id]) ? window_dist32(in.s1[st], in.nf1, x1, in.s2[id], in.nf2[id], x2) : 1000u;
+                else dist = (x1 + 4 < in.nf1 && x2 + 4 < in.nf2[id]) ? window_dist48(in.f1[st] + x1, in.f2[id] + x2) : 1000u;
+                cnt.windows++;
+                const u64 nyf = st ? L - 1 - cord_y(h) : cord_y(h);
+                if (dist < (u32)kWinThr && cord_y(h) + cs < L && nyf >= read_str && nyf + cs < read_end)
+                {
+                    if (nc >= cap) return false;
+                    last = h;
+                    if (w.lane == 0) cords[nc] = h;
+                    nc++;
+                    found = true;
+                    break;
+                }
+            }
+        }
+        if (!found)
+        {
+            if (f_new_block) { last |= kFlagEnd; pre = nc; }
+            break;
+        }
+    }
+    last |= kFlagEnd;                                           // set_cord_end(back(cords)), endCord
+    const u64 len = (u64)(nc - pre);
+    if (len > (c0 & kMaskY)) c0 = len + (c0 & ~kMaskY);
+    if (w.lane == 0) { cords[nc - 1] = last; cords[0] = c0; }
+    wsync(w);
+    max_len = c0 & kMaskY;
+    return true;
+}
+
+// One attempt of apxMap_ with alg_type 1 (:2632) on the raw anchors of a whole-read seeding task: A / B = the task's two
+// n-entry regions (A[0] the sentinel slot). list_n / best_n = GetDHitListParms (thd_list_n, thd_best_n). Leaves the cords
+// of the attempt in cords[0..nc). Return: 0 ok, 1 arena / cord capacity exhausted, 2 = nothing touched, arena too small.
+template <int FT = 0>
+LNR_PIPE int phase_c0(const Warp & w, Arena & ar, u32 * hist256, const PipeIn & in, u64 * A, u64 * B, int n, int list_n, int best_n,
+                      u64 * cords, int & nc, int cap, PipeCounters & cnt, u64 & max_len, bool force_fit)
+{
+    nc = 0; max_len = 0;
+    if (n >= (1 << 20)) return 1;                               // the run list packs anchor indices into 20 bits (:2232, :2264)
+    if (!force_fit && c0_scratch_bound(n) > ar.cap) return 2;
+    arena_reset(ar);
+    if (w.lane == 0) A[0] = 0;                                  // Anchors::init(1) base.cpp:272
+    wsync(w);
+    if (n <= 1) return 0;
+    const u64 read_str = 0, read_end = (u64)in.L & kMaskY;      // apxMap :2778: map_end = length(read), get_cord_y keeps 20 bits
+    u64 * C = arena_alloc<u64>(ar, (u64)n);
+    u64 * list = arena_alloc<u64>(ar, (u64)n);
+    u64 * hits = arena_alloc<u64>(ar, (u64)n + 2);
+    u64 * top = arena_alloc<u64>(ar, 32);
+    if (ar.failed) return 1;
+    u64 * S = radix_sort(w, hist256, A, B, C, n, 62, sort_key(0));          // anchors.sort = ska_sort, ascending
+    u64 * T0 = (S == A) ? B : A;                                // the two buffers of {A, B, C} that are not S
+    u64 * T1 = (S == C) ? B : C;
+    if (T1 == T0) T1 = C;
+    const int nl = c0_anchor_list(w, S, n, read_str, read_end, list);
+    if (nl == 0) return 0;
+    // getDHitList :2246: the runs by descending (c_b, sb, k); at most list_n are looked at, best_n become hits
+    u64 * SL = radix_sort(w, hist256, list, T0, T1, nl, 64, sort_key(6));
+    const int tmp = nl > list_n ? list_n : nl;                  // <= 20
+    for (int i = w.lane; i < tmp; i += w.nl) top[i] = SL[i];
+    wsync(w);
+    int nh = 1, record_num = 1;
+    if (w.lane == 0) hits[0] = kFlagEnd;
+    const i64 l0 = (i64)top[0];
+    for (int k = 0; k < tmp; k++)
+    {
+        if (record_num > best_n) break;
+        const i64 lk = (i64)top[k];
+        if (!((l0 / 10) < lk && lk)) break;
+        const int sb = (int)((lk >> 20) & (i64)kMaskY), sc = (int)(lk & (i64)kMaskY);
+        const int len = sc - sb;
+        if (len > 0)
+        {
+            u64 * R = gnu_sort_w(w, hist256, S + sb, T0, T1, len, 20, sort_key(5));   // sortPos2: std::sort by y, its tie order
+            for (int i = w.lane; i < len; i += w.nl) hits[nh + i] = hit2cord_dstr(R[i]);
+            nh += len;
+        }
+        wsync(w);
+        if (w.lane == 0) hits[nh - 1] |= kFlagEnd;              // back(hits): the sentinel when the run is empty
+        wsync(w);
+        ++record_num;
+    }
+    cnt.hits += (u64)(nh - 1);
+    return path_dst_1<FT>(w, in, hits, nh, cords, nc, cap, read_str, read_end, cnt, max_len) ? 0 : 1;
+}
+
+// apxMap :2779-2786: the attempt is kept when its longest block reaches thd_sen (0.7) of the read, counted in windows
+LNR_HD bool c0_attempt_too_short(u64 max_len, u64 L, u32 win)
+{
+    const float sen_thr = c0_fdiv(0.7f, (float)(i64)win);
+    return (float)max_len < c0_fmul((float)L, sen_thr);
+}
+
+// clean_blocks_ with its default map error (:2787) and the main / record flags (:2788-2801)
+LNR_PIPE void c0_finish(const Warp & w, u64 L, u64 * cords, int & nc, u32 win)
+{
+    i64 drop_len = imin64(2, (i64)((double)L * 0.05 / (double)win));
+    nc = clean_blocks_w(w, cords, nc, (u64)drop_len, 50);
+    int ends_before = 0;
+    for (int c0 = 0; c0 < nc; c0 += w.nl)
+    {
+        int i = c0 + w.lane;
+        u64 c = i < nc ? cords[i] : 0;
+        u32 m = wballot(w, i < nc && is_end(c));
+        int seg = (ends_before + popc_below(w, m)) & 1;
+        if (i < nc)
         {
             if (seg) c |= kFlagRecd; else c &= ~kFlagRecd;
             cords[i] = c | kFlagMain;

@@ -735,4 +735,29 @@ int orc_map_batch(orc_ctx * c, uint32_t n_reads, const uint8_t * bases, const ui
     return 0;
 }
 
+// -c 0 (f_chain = 0): see apx_map_c0; gdl_state 0 = PMPParms as constructed, 1 = as left by an earlier toggle(0)
+int orc_map_batch_c0(orc_ctx * c, uint32_t n_reads, const uint8_t * bases, const uint64_t * read_off, int map_threads, int gdl_state,
+                     uint64_t * cords, uint64_t * cords_off, uint64_t cords_cap)
+{
+    std::vector<std::vector<u64> > res(n_reads);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(map_threads)
+    for (uint32_t j = 0; j < n_reads; j++)
+    {
+        u64 len = read_off[j + 1] - read_off[j];
+        if (len <= 200) continue;   // mapper.cpp:430,440
+        ReadWork w(*c, bases + read_off[j], len);
+        apx_map_c0(*c, w, res[j], gdl_state);
+    }
+    u64 tot = 0;
+    cords_off[0] = 0;
+    for (uint32_t j = 0; j < n_reads; j++)
+    {
+        if (tot + res[j].size() > cords_cap) return -1;
+        if (!res[j].empty()) std::memcpy(cords + tot, res[j].data(), 8 * res[j].size());
+        tot += res[j].size();
+        cords_off[j + 1] = tot;
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -38,6 +38,11 @@ int64_t orc_read_stage(orc_ctx *, const uint8_t * read, uint64_t len, int stage,
 int orc_map_batch(orc_ctx *, uint32_t n_reads, const uint8_t * bases, const uint64_t * read_off, int map_threads,
                   uint64_t * cords, uint64_t * cords_off, uint64_t cords_cap);
 
+/* -c 0 (f_chain = 0, alg_type 1: getDAnchorList / getDHitList / path_dst_1). gdl_state 0 = a PMPParms as constructed
+ * (thd_list_n 20, thd_best_n 1), 1 = as any earlier toggle(0) leaves it (10, 999). */
+int orc_map_batch_c0(orc_ctx *, uint32_t n_reads, const uint8_t * bases, const uint64_t * read_off, int map_threads, int gdl_state,
+                     uint64_t * cords, uint64_t * cords_off, uint64_t cords_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -392,4 +392,46 @@ int ref_map_batch(void * h, uint32_t n_reads, const uint8_t * bases, const uint6
     return 0;
 }
 
+// -c 0 (f_chain = 0, alg_type 1; apxMap pmpfinder.cpp:2773-2787). The reference keeps ONE PMPParms per thread and this
+// mode leaves it changed: GetDHitListParms is constructed in its toggle(1) state (thd_list_n 20, thd_best_n 1, :2290-2297)
+// and the first read that needs the second attempt ends with toggle(0) (10, 999) for every later read of that thread.
+// Canonical convention: a fresh PMPParms per read; gdl_state 1 applies toggle(0) first (the "later reads" state).
+int ref_map_batch_c0(void * h, uint32_t n_reads, const uint8_t * bases, const uint64_t * read_off, int map_threads, int gdl_state,
+                     uint64_t * cords, uint64_t * cords_off, uint64_t cords_cap)
+{
+    RefCtx * c = (RefCtx *)h;
+    std::vector<std::vector<uint64_t> > res(n_reads);
+    omp_set_num_threads(map_threads);
+#pragma omp parallel
+    {
+        Worker w(*c);
+#pragma omp for schedule(dynamic, 4)
+        for (uint32_t j = 0; j < n_reads; j++)
+        {
+            uint64_t len = read_off[j + 1] - read_off[j];
+            if (len <= 200) continue;   // mapper.cpp:430,440
+            w.prepare(bases + read_off[j], len);
+            PMPParms fresh;
+            fresh.pm_cah.thd_stop_chain_len_ratio = c->stop_ratio;
+            if (gdl_state) fresh.toggle(0);
+            String<uint64_t> cords_str, cords_end;
+            String<CordInfo> cords_info;
+            apxMap(c->index, w.read, w.anchors, w.crhit, w.f1, c->f2, w.apx_gaps, cords_str, cords_end,
+                   cords_info, 0, w.pm_g, fresh);
+            copy_u64(res[j], cords_str);
+        }
+    }
+    omp_set_num_threads(c->threads);
+    uint64_t tot = 0;
+    cords_off[0] = 0;
+    for (uint32_t j = 0; j < n_reads; j++)
+    {
+        if (tot + res[j].size() > cords_cap) return -1;
+        if (!res[j].empty()) std::memcpy(cords + tot, res[j].data(), 8 * res[j].size());
+        tot += res[j].size();
+        cords_off[j + 1] = tot;
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -63,6 +63,10 @@ class _Checker:
         self._map_batch = getattr(L, p + "map_batch")
         self._map_batch.restype = C.c_int
         self._map_batch.argtypes = [C.c_void_p, C.c_uint32, u8p, u64p, C.c_int, u64p, u64p, C.c_uint64]
+        self._map_batch_c0 = getattr(L, p + "map_batch_c0", None)
+        if self._map_batch_c0 is not None:
+            self._map_batch_c0.restype = C.c_int
+            self._map_batch_c0.argtypes = [C.c_void_p, C.c_uint32, u8p, u64p, C.c_int, C.c_int, u64p, u64p, C.c_uint64]
         self.contigs = [np.ascontiguousarray(c, dtype=np.uint8) for c in contigs]
         n = len(self.contigs)
         ptrs = (u8p * n)(*[c.ctypes.data_as(u8p) for c in self.contigs])
@@ -153,15 +157,21 @@ class _Checker:
         cig = np.ctypeslib.as_array(pc, shape=(nc.value,)).copy() if nc.value else np.zeros(0, np.uint64)
         return recs, cig
 
-    def map_batch(self, bases: np.ndarray, offsets: np.ndarray, map_threads: int = 1, cap_per_base: float = 0.25):
+    def map_batch(self, bases: np.ndarray, offsets: np.ndarray, map_threads: int = 1, cap_per_base: float = 0.25,
+                  no_chain: bool = False, gdl_state: int = 0):
+        """no_chain: the reference's -c 0 (apxMap with f_chain = 0); gdl_state: see oracle/ref_harness.cpp ref_map_batch_c0"""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
         cap = int(len(bases) * cap_per_base) + 64 * n + 1024
         cords = np.zeros(cap, dtype=np.uint64)
         coff = np.zeros(n + 1, dtype=np.uint64)
-        rc = self._map_batch(self.h, n, bases.ctypes.data_as(u8p), offsets.ctypes.data_as(u64p), map_threads,
-                             cords.ctypes.data_as(u64p), coff.ctypes.data_as(u64p), cap)
+        if no_chain:
+            rc = self._map_batch_c0(self.h, n, bases.ctypes.data_as(u8p), offsets.ctypes.data_as(u64p), map_threads, gdl_state,
+                                    cords.ctypes.data_as(u64p), coff.ctypes.data_as(u64p), cap)
+        else:
+            rc = self._map_batch(self.h, n, bases.ctypes.data_as(u8p), offsets.ctypes.data_as(u64p), map_threads,
+                                 cords.ctypes.data_as(u64p), coff.ctypes.data_as(u64p), cap)
         if rc != 0:
             raise RuntimeError("map_batch capacity too small")
         return cords[: int(coff[-1])].copy(), coff

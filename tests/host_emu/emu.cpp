@@ -235,6 +235,57 @@ int run_read(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, std:
     return 0;
 }
 
+// -c 0 (apxMap with f_chain = 0): the product's phase_c0 / c0_finish driven the way apxmap_core drives k_map_c0
+int run_read_c0(Emu & E, const u8 * read, u64 L, std::vector<u64> & cords_out, int gdl_state)
+{
+    Warp w = {0, 1u};
+    SeqAcc acc = {read, (i64)L};
+    RcAcc rc = {read, (i64)L};
+    ReadRun R;
+    PipeIn in;
+    in.read = read; in.L = (u32)L;
+    in.ft = E.ft; in.win = E.ft == 1 ? (u32)kWin32 : (u32)kWin;
+    in.f1[0] = in.f1[1] = nullptr; in.s1[0] = in.s1[1] = nullptr; in.f2 = nullptr; in.s2 = nullptr;
+    if (E.ft == 1)
+    {
+        u32 nf = feat32_count(L);
+        build_feats32(acc, nf, feat32_written_serial(L), R.s1[0]);
+        build_feats32(rc, nf, feat32_written_serial(L), R.s1[1]);
+        in.s1[0] = R.s1[0].data(); in.s1[1] = R.s1[1].data(); in.nf1 = nf;
+        in.s2 = E.s2p.data();
+    }
+    else
+    {
+        u32 nf = feat_count_read(L);
+        build_feats(acc, nf, R.f1[0]);
+        build_feats(rc, nf, R.f1[1]);
+        in.f1[0] = R.f1[0].data(); in.f1[1] = R.f1[1].data(); in.nf1 = nf;
+        in.f2 = E.f2p.data();
+    }
+    in.nf2 = E.nf2.data(); in.stop_ratio = E.stop_ratio;
+    R.arena.resize(64 << 20);
+    Arena ar = {R.arena.data(), R.arena.size(), 0, 0};
+    int cap = 16 + (int)(L / 4);
+    R.cords.assign(cap, 0);
+    int nc = 0;
+    PipeCounters cnt = {0, 0};
+    u64 max_len = 0;
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        SeedTask t = make_task(acc, 0, 0, (u32)L, attempt ? 7 : 15);
+        seed(E, acc, t, R.A);
+        R.B.assign(R.A.size(), 0);
+        const bool first_state = attempt == 0 && gdl_state;
+        if (phase_c0(w, ar, R.hist, in, R.A.data(), R.B.data(), (int)R.A.size(), first_state ? 10 : 20, first_state ? 999 : 1, R.cords.data(), nc,
+                     cap, cnt, max_len, true))
+            return 1;
+        if (!c0_attempt_too_short(max_len, L, in.win)) break;
+    }
+    c0_finish(w, L, R.cords.data(), nc, in.win);
+    cords_out.assign(R.cords.begin(), R.cords.begin() + nc);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -333,6 +384,26 @@ int emu_map_batch(void * h, uint32_t n_reads, const uint8_t * bases, const uint6
         std::vector<u64> c;
         if (len > (u64)kMinReadLen)
             if (run_read(*E, bases + read_off[j], len, c, 0, 0)) return -2;
+        if (tot + c.size() > cords_cap) return -1;
+        if (!c.empty()) std::memcpy(cords + tot, c.data(), 8 * c.size());
+        tot += c.size();
+        cords_off[j + 1] = tot;
+    }
+    return 0;
+}
+
+int emu_map_batch_c0(void * h, uint32_t n_reads, const uint8_t * bases, const uint64_t * read_off, int, int gdl_state, uint64_t * cords,
+                     uint64_t * cords_off, uint64_t cords_cap)
+{
+    Emu * E = (Emu *)h;
+    u64 tot = 0;
+    cords_off[0] = 0;
+    for (uint32_t j = 0; j < n_reads; j++)
+    {
+        u64 len = read_off[j + 1] - read_off[j];
+        std::vector<u64> c;
+        if (len > (u64)kMinReadLen)
+            if (run_read_c0(*E, bases + read_off[j], len, c, gdl_state)) return -2;
         if (tot + c.size() > cords_cap) return -1;
         if (!c.empty()) std::memcpy(cords + tot, c.data(), 8 * c.size());
         tot += c.size();

@@ -447,3 +447,59 @@ def test_cords_to_records_bit_exact(lb, ctx, name):
     rc = ctx.lib.lnr_cords_to_records(ctx.h, len(coff) - 1, C.c_void_p(cords.ctypes.data), coff.ctypes.data_as(u64p), read_len.ctypes.data_as(u64p), C.byref(prm),
                                       C.c_void_p(small.ctypes.data), 4, ro.ctypes.data_as(u64p), None, 0, go.ctypes.data_as(u64p))
     assert rc == lb.api.LNR_E_CAPACITY and int(ro[-1]) > 40 and int(go[-1]) > 1000
+
+
+# ---- -c 0 (lnr_params.no_chain; apxMap with f_chain = 0, pmpfinder.cpp:2773-2787) ---------------------------
+GOLDEN_C0 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_c0.json")))
+
+
+@pytest.mark.parametrize("name", ["clean_hifi", "repeat_ont", "repeat_t1_p0"])
+@pytest.mark.parametrize("ft", [2, 1])
+def test_c0_cords_bit_exact(lb, ctx, name, ft):
+    """k_map_c0 (sorted anchor runs -> hits -> path_dst_1, second attempt at step 7) against the oracle, the golden digests
+    made from the reference and the reference itself, for both GetDHitListParms states"""
+    g, reads, bases, offs, T, preset = make_case(name)
+    O = Oracle(g, threads=T, preset=preset, feature_type=ft)
+    R = RefImpl(g, threads=T, preset=preset, feature_type=ft) if have_ref() else None
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, ft, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    for st in (0, 1):
+        gd = GOLDEN_C0[name][f"f{ft}_s{st}"]
+        cords, coff = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset, no_chain=True, gdl_state=st)
+        oc, oo = O.map_batch(bases, offs, map_threads=4, no_chain=True, gdl_state=st)
+        bad = [i for i in range(len(reads)) if not np.array_equal(cords[int(coff[i]):int(coff[i + 1])], oc[int(oo[i]):int(oo[i + 1])])]
+        assert not bad, (st, bad[:8])
+        assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+        for i in range(len(reads)):
+            c = cords[int(coff[i]):int(coff[i + 1])]
+            assert len(c) == gd["n_cords"][i] and digest(c) == gd["cords"][i], f"read {i} state {st}"
+        if R is not None:
+            rc_, ro_ = R.map_batch(bases, offs, map_threads=4, no_chain=True, gdl_state=st)
+            assert np.array_equal(ro_, coff) and np.array_equal(rc_, cords)
+
+
+def test_c0_second_attempt_big_arena_and_hindex(lb, monkeypatch):
+    """-c 0: the junk / chimeric reads of the case take the second attempt (step 7); with a 48 KB per-warp arena most reads go
+    through the big-arena launch and the cords stay the same; with -i 2 the mode maps nothing, as in the reference"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4, no_chain=True)
+    ctx = lb.Context(0)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, 1, T)
+    cords, coff = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset, no_chain=True)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
+    assert ctx.counters()["remap_tasks"] > 0               # reads that needed the second attempt
+    hindex = lb.create_index(ctx, gen, 2, T)
+    ch, oh = lb.apx_map_batch(ctx, hindex, feats, bases, offs, preset=preset, no_chain=True)
+    ohc, oho = Oracle(g, threads=T, preset=preset, index_type=2).map_batch(bases, offs, map_threads=4, no_chain=True)
+    assert len(ch) == 0 and len(ohc) == 0 and np.array_equal(oh, oho)
+    monkeypatch.setenv("LNR_ARENA_KB", "48")
+    ctx2 = lb.Context(0)
+    gen2 = lb.Genome(ctx2, g)
+    feats2 = lb.create_features(ctx2, gen2, 2, T)
+    index2 = lb.create_index(ctx2, gen2, 1, T)
+    c2, o2 = lb.apx_map_batch(ctx2, index2, feats2, bases, offs, preset=preset, no_chain=True)
+    assert np.array_equal(oo, o2) and np.array_equal(oc, c2)
+    assert ctx2.diag()["hits_big_tasks"] > 0               # tasks taken by the big-arena launch

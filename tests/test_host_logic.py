@@ -114,3 +114,16 @@ def test_host_emulation_on_random_cases(seed):
         assert np.array_equal(O.stage(read, 1), E.stage(read, 1)), (seed, "anchors", r)
         assert np.array_equal(O.stage(read, 3), E.stage(read, 3)), (seed, "hits", r)
         assert np.array_equal(O.cords(read), E.cords(read)), (seed, "cords", r)
+
+
+@pytest.mark.parametrize("name", ["clean_hifi", "repeat_ont"])
+def test_host_emulation_of_c0_path_matches_oracle(name):
+    """-c 0: the product's phase_c0 / path_dst_1 / c0_finish (lnr_pipeline.h) with a one-lane warp against the oracle"""
+    g, reads, bases, offs, T, preset = make_case(name)
+    for ft in (2, 1):
+        O = Oracle(g, threads=T, preset=preset, feature_type=ft)
+        E = HostEmu(g, threads=T, preset=preset, feature_type=ft)
+        for st in (0, 1):
+            oc, oo = O.map_batch(bases, offs, map_threads=2, no_chain=True, gdl_state=st)
+            ec, eo = E.map_batch(bases, offs, no_chain=True, gdl_state=st)
+            assert np.array_equal(oo, eo) and np.array_equal(oc, ec), (ft, st)

@@ -199,3 +199,41 @@ def test_product_record_walk_equals_oracle():
             c = cords[int(coff[i]):int(coff[i + 1])]
             a, b = O.cords2bam(len(r), c, w, 8000, di, x), E.cords2bam(len(r), c, w, 8000, di, x)
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (i, di, x, w)
+
+
+# ---- -c 0 (apxMap with f_chain = 0, alg_type 1: getDAnchorList / getDHitList / path_dst_1) -----------------
+GOLDEN_C0 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_c0.json")))
+
+
+@pytest.mark.parametrize("name", ["clean_hifi", "repeat_ont", "repeat_t1_p0"])
+@pytest.mark.parametrize("ft", [2, 1])
+def test_oracle_c0_matches_golden(name, ft):
+    g, reads, bases, offs, T, preset = make_case(name)
+    O = Oracle(g, threads=T, preset=preset, feature_type=ft)
+    for st in (0, 1):
+        gd = GOLDEN_C0[name][f"f{ft}_s{st}"]
+        assert all(gd["stable"])
+        cords, coff = O.map_batch(bases, offs, map_threads=2, no_chain=True, gdl_state=st)
+        for i in range(len(reads)):
+            c = cords[int(coff[i]):int(coff[i + 1])]
+            assert len(c) == gd["n_cords"][i] and digest(c) == gd["cords"][i], f"read {i} state {st}"
+    # the mode is a different algorithm, not a variant of the default: most reads get other cords than with f_chain = 1
+    c1, o1 = O.map_batch(bases, offs, map_threads=2)
+    assert not (np.array_equal(o1, coff) and np.array_equal(c1, cords))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_c0_equals_reference():
+    """the unmodified reference's apxMap with f_chain = 0 (fresh PMPParms per read, both GetDHitListParms states) against the
+    restatement, incl. -i 2 seeding"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    for it, ft in ((1, 2), (2, 2), (1, 1)):
+        O = Oracle(g, threads=T, preset=preset, feature_type=ft, index_type=it)
+        R = RefImpl(g, threads=T, preset=preset, feature_type=ft, index_type=it)
+        for st in (0, 1):
+            oc, oo = O.map_batch(bases, offs, map_threads=2, no_chain=True, gdl_state=st)
+            rc, ro = R.map_batch(bases, offs, map_threads=2, no_chain=True, gdl_state=st)
+            assert np.array_equal(oo, ro) and np.array_equal(oc, rc), (it, ft, st)
+            # -i 2 maps nothing in this mode: getHIndexMatchAll reads its record window from map_end's x field, and
+            # apxMap passes the bare read length there (pmpfinder.cpp:1933, :2778)
+            assert int(np.count_nonzero(np.diff(oo.astype(np.int64)))) > len(reads) // 2 if it == 1 else len(oc) == 0
