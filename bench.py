@@ -33,6 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 GENOME_BASES = int(os.environ.get("LNR_BENCH_GENOME", 3_100_000_000))
 N_CONTIGS = 24
+INDEX_TYPE = int(os.environ.get("LNR_BENCH_INDEX", 1))     # 2: HIndex (-i 2), a side measurement (BASELINE configs[3]); N = 1 only
 READ_PROFILE = os.environ.get("LNR_BENCH_PROFILE", "ont")   # "hifi": 15 kb reads at 1 % error, a side measurement
 THREADS_SEM = 16          # the reference's code default -t (base.cpp:26-54); semantic for the index
 SEED_COUNT_WRITE = 4      # bytes k_seed_count writes per sample: its match count (+ 4 B per match entry, below)
@@ -243,7 +244,7 @@ def cpu_reference(contigs_host, bases, offs, n_sample, cores, reps=1):
     kind = "reference" if have_ref() else "port"
     cls = RefImpl if have_ref() else Oracle
     t0 = time.time()
-    chk = cls(contigs_host, threads=THREADS_SEM, preset=1)
+    chk = cls(contigs_host, threads=THREADS_SEM, preset=1, index_type=INDEX_TYPE)
     t_index = time.time() - t0
     n = min(n_sample, len(offs) - 1)
     sb = bases[: int(offs[n])]
@@ -281,6 +282,8 @@ def check_parity(torch, dev, chk, index, ref_cords, ref_coff, gpu_cords, gpu_cof
                 n_diff += 1
     out = {"reads": n, "cords": int(ref_coff[-1]), "cords_equal": cords_equal, "reads_differing": n_diff}
     try:
+        if INDEX_TYPE != 1:
+            raise RuntimeError("HIndex run: only the cords are compared")
         rdir, rhs = chk.dindex_views()
         d_dev, hs_dev = index.export_device(torch, dev)
         ok = len(rhs) == hs_dev.numel() and len(rdir) == d_dev.numel()
@@ -372,7 +375,7 @@ def main():
     config = {"workload": f"BASELINE configs[2] (apx map + chaining; index build = configs[1]): {GENOME_BASES / 1e9:.2f}-Gbase synthetic genome "
                           f"({N_CONTIGS} contigs, planted repeats) + simulated ONT-like reads (lognormal mean 20 kb, 10% error, 20% planted "
                           f"ins/del/inv/dup SVs), one step = one batch of {args.batch_reads} reads per GPU",
-              "index": "DIndex (-i 1)", "features": "2-mer/48 (-f 2)", "threads_sem": THREADS_SEM, "preset": 1,
+              "index": "DIndex (-i 1)" if INDEX_TYPE == 1 else "HIndex (-i 2), side measurement", "features": "2-mer/48 (-f 2)", "threads_sem": THREADS_SEM, "preset": 1,
               "batch_reads_per_gpu": args.batch_reads, "parallelism": f"reads sharded x{world} (no collective); index built by minimizer range x{world} + one NCCL all-gather",
               "l2_policy": "inputs larger than L2 (batch bases + index >> 126 MB)",
               "host_threads": args.streams}
@@ -490,7 +493,7 @@ def main():
         g_ = lb.Genome(ctx, device_ptr=genome.data_ptr(), lens=lens64)
         f_ = lb.create_features(ctx, g_, 2, THREADS_SEM)
         if world == 1:
-            i_ = lb.create_index(ctx, g_, 1, THREADS_SEM)
+            i_ = lb.create_index(ctx, g_, INDEX_TYPE, THREADS_SEM)
         else:
             # hash-range sharded build inside the C ABI: every rank builds 2^26/N buckets straight into its slice of the final
             # arrays, one grouped NCCL exchange over NVLink completes them (lnr_index_build_sharded)
@@ -539,7 +542,7 @@ def main():
         t0 = time.time()
         gen = lb.Genome(ctx, contigs_host)
         feats = lb.create_features(ctx, gen, 2, THREADS_SEM)
-        index = lb.create_index(ctx, gen, 1, THREADS_SEM)
+        index = lb.create_index(ctx, gen, INDEX_TYPE, THREADS_SEM)
         torch.cuda.synchronize()
         t_index_e2e = time.time() - t0
         ctx.reset_kernel_times()

@@ -101,6 +101,14 @@ int lnr_index_build_sharded(lnr_ctx *, const lnr_genome *, int index_type, unsig
 int lnr_index_export_dindex_device(const lnr_index *, int32_t * dev_dir, uint64_t * dev_hs, uint64_t hs_cap);
 /* wraps assembled device arrays into an index (copies them) */
 int lnr_index_from_device(lnr_ctx *, const int32_t * dev_dir, const uint64_t * dev_hs, uint64_t n_hs, lnr_index ** out);
+/* ---- index serialisation. The reference has no on-disk index: `linear` hashes the genome again on every
+ * run (createIndexDynamic, 21 s at 3.1 Gbase). lnr_index_save writes what createIndexDynamic produced -- DIndex: dir + hs;
+ * HIndex: ysa + the directory table + emptyDir -- behind a 64-byte header (magic "LNRIDX1", index type, element counts, one
+ * 64-bit checksum per array); lnr_index_load reads it back onto ctx's device and re-derives the lookup arrays of the
+ * seeding kernels. The file does not name the genome or -t it was built from: that pairing is the caller's (store the
+ * file next to the FASTA). Errors: LNR_E_ARG = cannot open / not an index file / checksum or size mismatch. */
+int lnr_index_save(const lnr_index *, const char * path);
+int lnr_index_load(lnr_ctx *, const char * path, lnr_index ** out);
 void lnr_index_destroy(lnr_index *);
 
 /* ---- per-read approximate mapping -------------------------------------------------------------------

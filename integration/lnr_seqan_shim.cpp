@@ -109,7 +109,6 @@ uint64_t apxMap(IndexDynamic & index, String<Dna5> & read, Anchors & anchors, St
                 String<CordInfo> & cords_info, int f_chain, GlobalParms & pm_g, PMPParms & pm_pmp)
 {
     (void)index; (void)anchors; (void)hit; (void)f1; (void)cords_info; (void)pm_g;
-    if (!f_chain) die("apxMap with f_chain = 0 (-c 0, alg_type 1)", LNR_E_UNSUPPORTED, nullptr);
     if (!G.index) die("apxMap before createIndexDynamic", LNR_E_ARG, nullptr);
     const int fs_type = f2[0].fs_type;
     if (!G.feats || G.feats_type != fs_type) ensure_features(fs_type);
@@ -123,8 +122,21 @@ uint64_t apxMap(IndexDynamic & index, String<Dna5> & read, Anchors & anchors, St
     std::memset(&prm, 0, sizeof prm);
     prm.preset = pm_pmp.pm_cah.thd_stop_chain_len_ratio > 0.0f ? 0 : 1;   // mapper.cpp:181-195: -p 0 => 0.7, -p 1/2 => 0
     prm.feature_type = fs_type;
+    if (!f_chain)
+    {
+        // -c 0 (alg_type 1, pmpfinder.cpp:2773-2787). This mode reads AND changes the caller's per-thread PMPParms:
+        // GetDHitListParms is (20, 1) as constructed and (10, 999) once any read of the thread has needed the second attempt
+        // (toggle(1) ... toggle(0), :2782-2784). The library takes the state as a parameter; the shim keeps the object in step.
+        prm.no_chain = 1;
+        prm.gdl_state = pm_pmp.pm_gdl.thd_list_n == 10 ? 1 : 0;
+    }
     int rc = lnr_apxmap_batch(ctx, G.index, G.feats, &prm, 1, (const uint8_t *)&read[0], off, cords.data(), coff, cords.size(), nullptr);
     if (rc) die("lnr_apxmap_batch", rc, ctx);
+    if (!f_chain)
+    {
+        uint64_t counters[8];
+        if (lnr_last_batch_counters(ctx, counters) == 0 && counters[7] > 0) { pm_pmp.toggle(1); pm_pmp.toggle(0); }   // the second attempt ran
+    }
     const uint64_t n = coff[1];
     const uint64_t w = fs_type == 1 ? 192 : 96;              // getFeatureWindowSize(f1), pmpfinder.cpp:2724
     const uint64_t d = (w << 20) | w;                        // shift_cord(0, w, w), pmpfinder.cpp:2790

@@ -30,7 +30,7 @@ EXPORTS = [
     "lnr_ctx_reset_kernel_times", "lnr_genome_upload", "lnr_genome_from_device", "lnr_genome_destroy",
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
-    "lnr_index_from_device", "lnr_index_destroy", "lnr_nccl_unique_id", "lnr_comm_create", "lnr_comm_from_nccl", "lnr_comm_destroy",
+    "lnr_index_from_device", "lnr_index_save", "lnr_index_load", "lnr_index_destroy", "lnr_nccl_unique_id", "lnr_comm_create", "lnr_comm_from_nccl", "lnr_comm_destroy",
     "lnr_index_build_sharded", "lnr_apxmap_batch", "lnr_apxmap_batch_packed", "lnr_pack_dna5",
     "lnr_apxmap_batch_device", "lnr_cords_to_records", "lnr_last_batch_counters", "lnr_last_batch_diag", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
     "lnr_reads_parse", "lnr_reads_parse_device", "lnr_reads_info", "lnr_reads_download", "lnr_reads_device", "lnr_reads_destroy", "lnr_apxmap_reads",
@@ -98,6 +98,8 @@ def load_library() -> C.CDLL:
     lib.lnr_index_from_device.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(vp)]
     lib.lnr_index_destroy.argtypes = [vp]
     lib.lnr_index_destroy.restype = None
+    lib.lnr_index_save.argtypes = [vp, C.c_char_p]
+    lib.lnr_index_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.lnr_nccl_unique_id.argtypes = [vp]
     lib.lnr_comm_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
     lib.lnr_comm_from_nccl.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
@@ -259,6 +261,17 @@ class Index:
         else:
             ctx.check(ctx.lib.lnr_index_build_shard(ctx.h, genome.h, index_type, threads, shard, n_shards, C.byref(h)))
         self.h = h
+
+    def save(self, path: str):
+        """lnr_index_save: the index arrays behind a 64-byte header (the reference has no on-disk index)"""
+        self.ctx.check(self.ctx.lib.lnr_index_save(self.h, os.fsencode(path)))
+
+    @staticmethod
+    def load(ctx: "Context", path: str) -> "Index":
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lnr_index_load(ctx.h, os.fsencode(path), C.byref(h)))
+        t = 1 if ctx.lib.lnr_index_export_dindex(h, None, None, 0, C.c_uint64()) == 0 else 2
+        return Index(ctx, None, index_type=t, handle=h)
 
     def export_hindex(self):
         """(ysa uint64[], emptyDir, sorted (val1, val2) directory entries, table length) of an HIndex (-i 2)"""

@@ -1,4 +1,4 @@
-// `linear_b200_filter filter reads.fa genome.fa [-t N] [-p N] [-i 1] [-f 2] [-ot 1] [-g 0]`
+// `linear_b200_filter filter reads.fa genome.fa [-t N] [-p N] [-i 1] [-f 2] [-c 1] [-ot 1] [-g 0]`
 //
 // Host-side mirror of the reference's CLI surface for the apx-map path (src/args_parser.cpp:118,
 // src/linear.cpp:8-21 process1, src/mapper.cpp:883 map): load genome -> features + index on the GPU through the
@@ -197,6 +197,7 @@ int main(int argc, char ** argv)
 {
     std::vector<std::string> pos;
     int threads = 16, preset = 1, index_t = 1, feature_t = 2, ot = 2, device = 0, host_ingest = 0;   // defaults: base.cpp:26-54
+    int apx_chain = 1, gdl_state = 0;   // -c (apx_chain_flag, base.cpp:35); --gdl-state: lnr_params.gdl_state for -c 0
     for (int i = 1; i < argc; i++)
     {
         std::string a = argv[i];
@@ -208,13 +209,15 @@ int main(int argc, char ** argv)
         else if (a == "-ot" || a == "--output_type") val(ot);
         else if (a == "--device") val(device);
         else if (a == "--host-ingest") host_ingest = 1;
-        else if (a == "-g" || a == "-b" || a == "-o" || a == "-c" || a == "-s" || a == "-a") { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }
+        else if (a == "-c" || a == "--apx_c_flag") val(apx_chain);
+        else if (a == "--gdl-state") val(gdl_state);
+        else if (a == "-g" || a == "-b" || a == "-o" || a == "-s" || a == "-a") { if (i + 1 < argc && argv[i + 1][0] != '-') i++; }
         else if (!a.empty() && a[0] == '-') { /* other reference options do not affect this path */ }
         else pos.push_back(a);
     }
     if (pos.size() < 3 || pos[0] != "filter")
     {
-        fprintf(stderr, "usage: %s filter reads.fa genome.fa [-t N] [-p N] [-i 1|2] [-f 2|1] [-ot 1]\n", argv[0]);
+        fprintf(stderr, "usage: %s filter reads.fa genome.fa [-t N] [-p N] [-i 1|2] [-f 2|1] [-c 1|0] [-ot 1|2|3]\n", argv[0]);
         return 1;
     }
     const std::string rpath = pos[1], gpath = pos[2];
@@ -286,6 +289,7 @@ int main(int argc, char ** argv)
         return 0;
     };
     lnr_params prm; memset(&prm, 0, sizeof prm); prm.preset = preset; prm.feature_type = feature_t;
+    prm.no_chain = apx_chain == 0; prm.gdl_state = gdl_state;
     char main_icon = '+';
     uint64_t n_reads_total = 0, n_cords_total = 0;
     std::vector<Rec> reads;

@@ -2720,6 +2720,134 @@ int lnr_index_from_device(lnr_ctx * ctx, const int32_t * dev_dir, const uint64_t
     *out = ix;
     return LNR_OK;
 }
+// ---- index serialisation (include/lnr_b200.h: lnr_index_save / lnr_index_load) ----------------------------------------------
+struct IdxFileHeader
+{
+    char magic[8];               // "LNRIDX1"
+    uint32_t index_type, elem_b; // 1 DIndex / 2 HIndex; bytes per element of array B (8 hs record, 16 directory slot)
+    uint64_t n_a, n_b;           // elements of array A (dir int32 / ysa u64) and B (hs u64 / directory table)
+    uint64_t empty_dir, n_dir_entries;
+    uint64_t sum_a, sum_b;       // word-wise checksums
+};
+static_assert(sizeof(IdxFileHeader) == 64, "index file header is 64 bytes");
+static uint64_t idx_file_sum(uint64_t h, const void * p, size_t bytes)
+{
+    const uint64_t * w = (const uint64_t *)p;
+    size_t n = bytes / 8;
+    for (size_t i = 0; i < n; i++) h = (h ^ w[i]) * 0x100000001b3ULL;
+    const unsigned char * t = (const unsigned char *)p + n * 8;
+    for (size_t i = 0; i < bytes - n * 8; i++) h = (h ^ t[i]) * 0x100000001b3ULL;
+    return h;
+}
+static const size_t kIdxFileChunk = (size_t)64 << 20;
+// device array -> file (write = true) or file -> device array, 64 MB at a time through a pinned staging buffer
+static int idx_file_stream(lnr_ctx * ctx, FILE * f, void * dev, size_t bytes, bool write, void * stage, uint64_t * sum)
+{
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (size_t o = 0; o < bytes; o += kIdxFileChunk)
+    {
+        const size_t n = std::min(kIdxFileChunk, bytes - o);
+        if (write)
+        {
+            CK(cudaMemcpyAsync(stage, (const u8 *)dev + o, n, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (fwrite(stage, 1, n, f) != n) return fail(ctx, LNR_E_ARG, "index file: write failed");
+        }
+        else
+        {
+            if (fread(stage, 1, n, f) != n) return fail(ctx, LNR_E_ARG, "index file: truncated");
+            CK(cudaMemcpyAsync((u8 *)dev + o, stage, n, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        h = idx_file_sum(h, stage, n);
+    }
+    *sum = h;
+    return LNR_OK;
+}
+int lnr_index_save(const lnr_index * ix, const char * path)
+{
+    if (!ix || !path) return LNR_E_ARG;
+    lnr_ctx * ctx = ix->ctx;
+    cudaSetDevice(ctx->device);
+    IdxFileHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, "LNRIDX1", 8);
+    hd.index_type = (uint32_t)ix->index_type;
+    void * a; void * b; size_t ba, bb;
+    if (ix->index_type == 1)
+    {
+        hd.n_a = kDirSize; hd.n_b = ix->n_hs; hd.elem_b = 8;
+        a = ix->d_dir; ba = (size_t)kDirSize * sizeof(i32); b = ix->d_hs; bb = (size_t)ix->n_hs * sizeof(u64);
+    }
+    else
+    {
+        hd.n_a = ix->n_ysa; hd.n_b = ix->tab_len; hd.elem_b = (uint32_t)sizeof(HNode);
+        hd.empty_dir = ix->empty_dir; hd.n_dir_entries = ix->n_dir_entries;
+        a = ix->d_ysa; ba = (size_t)ix->n_ysa * sizeof(u64); b = ix->d_tab; bb = (size_t)ix->tab_len * sizeof(HNode);
+    }
+    FILE * f = fopen(path, "wb");
+    if (!f) return fail(ctx, LNR_E_ARG, "index file: cannot open for writing");
+    void * stage = nullptr;
+    if (cudaMallocHost(&stage, kIdxFileChunk) != cudaSuccess) { fclose(f); return fail(ctx, LNR_E_CUDA, "cudaMallocHost failed in lnr_index_save"); }
+    int rc = fwrite(&hd, 1, sizeof hd, f) == sizeof hd ? LNR_OK : fail(ctx, LNR_E_ARG, "index file: write failed");
+    if (!rc) rc = idx_file_stream(ctx, f, a, ba, true, stage, &hd.sum_a);
+    if (!rc) rc = idx_file_stream(ctx, f, b, bb, true, stage, &hd.sum_b);
+    if (!rc && (fseek(f, 0, SEEK_SET) != 0 || fwrite(&hd, 1, sizeof hd, f) != sizeof hd)) rc = fail(ctx, LNR_E_ARG, "index file: write failed");
+    cudaFreeHost(stage);
+    if (fclose(f) != 0 && !rc) rc = fail(ctx, LNR_E_ARG, "index file: write failed");
+    return rc;
+}
+int lnr_index_load(lnr_ctx * ctx, const char * path, lnr_index ** out)
+{
+    if (!ctx || !path || !out) return LNR_E_ARG;
+    cudaSetDevice(ctx->device);
+    FILE * f = fopen(path, "rb");
+    if (!f) return fail(ctx, LNR_E_ARG, "index file: cannot open");
+    IdxFileHeader hd;
+    if (fread(&hd, 1, sizeof hd, f) != sizeof hd || memcmp(hd.magic, "LNRIDX1", 8) != 0) { fclose(f); return fail(ctx, LNR_E_ARG, "not an index file (magic LNRIDX1)"); }
+    const bool dtype = hd.index_type == 1 && hd.n_a == (uint64_t)kDirSize && hd.elem_b == 8 && hd.n_b < (1ULL << 31);
+    const bool htype = hd.index_type == 2 && hd.elem_b == sizeof(HNode) && hd.n_b >= 2 && (hd.n_b & (hd.n_b - 1)) == 0 && hd.n_a >= 2 && hd.n_a < (1ULL << 40);
+    if (!dtype && !htype) { fclose(f); return fail(ctx, LNR_E_ARG, "index file: inconsistent header"); }
+    lnr_index * ix = new lnr_index();
+    ix->ctx = ctx; ix->index_type = (int)hd.index_type; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = 0;
+    void * stage = nullptr;
+    int rc = LNR_OK;
+    auto done = [&](int code) {
+        if (stage) cudaFreeHost(stage);
+        fclose(f);
+        if (code) lnr_index_destroy(ix); else *out = ix;
+        return code;
+    };
+    if (cudaMallocHost(&stage, kIdxFileChunk) != cudaSuccess) return done(fail(ctx, LNR_E_CUDA, "cudaMallocHost failed in lnr_index_load"));
+    uint64_t sa = 0, sb = 0;
+    if (dtype)
+    {
+        ix->n_hs = hd.n_b;
+        if (cudaMalloc(&ix->d_dir, (size_t)kDirSize * sizeof(i32)) != cudaSuccess || cudaMalloc(&ix->d_hs, (size_t)(hd.n_b + 8) * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&ix->d_hsy, (size_t)hd.n_b + 64) != cudaSuccess)
+            return done(fail(ctx, LNR_E_CUDA, "cudaMalloc failed in lnr_index_load"));
+        cudaMemsetAsync(ix->d_hs + hd.n_b, 0, 8 * sizeof(u64), ctx->stream);
+        if ((rc = idx_file_stream(ctx, f, ix->d_dir, (size_t)kDirSize * sizeof(i32), false, stage, &sa))) return done(rc);
+        if ((rc = idx_file_stream(ctx, f, ix->d_hs, (size_t)hd.n_b * sizeof(u64), false, stage, &sb))) return done(rc);
+        if (sa != hd.sum_a || sb != hd.sum_b) return done(fail(ctx, LNR_E_ARG, "index file: checksum mismatch"));
+        if (hd.n_b) k_idx_split_y<<<(u32)((hd.n_b + 255) / 256), 256, 0, ctx->stream>>>(ix->d_hs, hd.n_b, ix->d_hsy);
+        if (index_build_dirx(ctx, ix) != cudaSuccess) return done(fail(ctx, LNR_E_CUDA, "cudaMalloc failed in lnr_index_load"));
+    }
+    else
+    {
+        ix->n_ysa = hd.n_a; ix->tab_len = hd.n_b; ix->empty_dir = hd.empty_dir; ix->n_dir_entries = hd.n_dir_entries;
+        if (hd.empty_dir >= hd.n_a) return done(fail(ctx, LNR_E_ARG, "index file: inconsistent header"));
+        if (cudaMalloc(&ix->d_ysa, (size_t)(hd.n_a + 8) * sizeof(u64)) != cudaSuccess || cudaMalloc(&ix->d_tab, (size_t)hd.n_b * sizeof(HNode)) != cudaSuccess)
+            return done(fail(ctx, LNR_E_CUDA, "cudaMalloc failed in lnr_index_load"));
+        cudaMemsetAsync(ix->d_ysa + hd.n_a, 0, 8 * sizeof(u64), ctx->stream);      // the seeding scan may look past the two terminators
+        if ((rc = idx_file_stream(ctx, f, ix->d_ysa, (size_t)hd.n_a * sizeof(u64), false, stage, &sa))) return done(rc);
+        if ((rc = idx_file_stream(ctx, f, ix->d_tab, (size_t)hd.n_b * sizeof(HNode), false, stage, &sb))) return done(rc);
+        if (sa != hd.sum_a || sb != hd.sum_b) return done(fail(ctx, LNR_E_ARG, "index file: checksum mismatch"));
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return done(fail(ctx, LNR_E_CUDA, cudaGetErrorString(e)));
+    return done(LNR_OK);
+}
 static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_index ** out)
 {
     if (!ctx || !g || !out || threads_sem == 0) return LNR_E_ARG;
@@ -3197,6 +3325,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         CK(cudaStreamSynchronize(ctx->stream));
         memset(ctx->counters, 0, sizeof ctx->counters);
         ctx->counters[6] = h_read_off[n_reads];
+        for (uint32_t r = 0; r < n_reads; r++) ctx->counters[7] += h_read_off[r + 1] - h_read_off[r] > (u64)kMinReadLen;   // second attempts
         if (n_cords_total) *n_cords_total = 0;
         return LNR_OK;
     }

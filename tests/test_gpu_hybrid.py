@@ -42,6 +42,28 @@ def test_reference_host_stages_consume_gpu_cords(tmp_path, extra):
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(HYBRID)), reason="oracle/_ref (compiled reference + hybrid) did not travel")
+def test_hybrid_c0_follows_the_reference_parameter_state(tmp_path):
+    """`-c 0` (apxMap with f_chain = 0) reads and changes the thread's PMPParms: the first read that needs the second attempt
+    leaves GetDHitListParms at (10, 999) for every later read. The shim hands the state to the library per call and keeps the
+    caller's object in step, so with one mapping thread the hybrid writes the reference binary's APF, junk reads included."""
+    g, reads, bases, offs, T, _ = make_case("repeat_ont")
+    gfa, rfa = str(tmp_path / "genome.fa"), str(tmp_path / "reads.fa")
+    datagen.write_fasta(gfa, [f"chr{i + 1} synthetic" for i in range(len(g))], g)
+    datagen.write_fasta(rfa, [f"read{i}" for i in range(len(reads))], reads)
+    d_ref, d_new = tmp_path / "ref", tmp_path / "new"
+    d_ref.mkdir(); d_new.mkdir()
+    common = ["filter", rfa, gfa, "-ot", "1", "-t", "1", "-b", "0", "-g", "0", "-c", "0"]
+    subprocess.run([REF_BIN] + common, cwd=d_ref, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+    env = dict(os.environ, LNR_ARENA_KB="1024")
+    p = subprocess.run([HYBRID] + common, cwd=d_new, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900, env=env)
+    assert p.returncode == 0, p.stdout[-2000:]
+    a = _strip(open(d_ref / "reads.apf", "rb").read())
+    b = _strip(open(d_new / "reads.apf", "rb").read())
+    assert len(a) > 1000 and a.count(b"\n@") + 1 >= 40
+    assert a == b
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(HYBRID)), reason="oracle/_ref (compiled reference + hybrid) did not travel")
 def test_samples_stream_against_replicated_index(tmp_path):
     """BASELINE configs[4] in miniature: several samples are streamed at the same time (`-b 1` scheduler, -ot 3 = APF + SAM,
     host gap mapping on), one hybrid process per sample, each with its own replica of the index on the GPU it is given

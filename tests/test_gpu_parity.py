@@ -503,3 +503,45 @@ def test_c0_second_attempt_big_arena_and_hindex(lb, monkeypatch):
     c2, o2 = lb.apx_map_batch(ctx2, index2, feats2, bases, offs, preset=preset, no_chain=True)
     assert np.array_equal(oo, o2) and np.array_equal(oc, c2)
     assert ctx2.diag()["hits_big_tasks"] > 0               # tasks taken by the big-arena launch
+
+
+# ---- index serialisation (lnr_index_save / lnr_index_load) -------------------------------------------------
+@pytest.mark.parametrize("index_type", [1, 2])
+def test_index_save_load_round_trip(lb, ctx, tmp_path, index_type):
+    """an index written by lnr_index_save and read back by lnr_index_load (into another context) has the same arrays and maps
+    the reads to the same cords; a truncated or altered file is refused"""
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, T)
+    index = lb.create_index(ctx, gen, index_type, T)
+    path = str(tmp_path / "genome.lnridx")
+    index.save(path)
+    ctx2 = lb.Context(0)
+    back = lb.Index.load(ctx2, path)
+    assert back.index_type == index_type
+    if index_type == 1:
+        d0, h0 = index.export_dindex()
+        d1, h1 = back.export_dindex()
+        assert np.array_equal(d0, d1) and np.array_equal(h0, h1)
+        assert os.path.getsize(path) == 64 + d0.nbytes + h0.nbytes
+    else:
+        y0, e0, kv0, t0 = index.export_hindex()
+        y1, e1, kv1, t1 = back.export_hindex()
+        assert np.array_equal(y0, y1) and e0 == e1 and np.array_equal(kv0, kv1) and t0 == t1
+    gen2 = lb.Genome(ctx2, g)
+    feats2 = lb.create_features(ctx2, gen2, 2, T)
+    c0, o0 = lb.apx_map_batch(ctx, index, feats, bases, offs, preset=preset)
+    c1, o1 = lb.apx_map_batch(ctx2, back, feats2, bases, offs, preset=preset)
+    assert np.array_equal(o0, o1) and np.array_equal(c0, c1) and len(c0) > 1000
+    raw = bytearray(open(path, "rb").read())
+    bad = str(tmp_path / "bad.lnridx")
+    open(bad, "wb").write(raw[: len(raw) - 4096])
+    with pytest.raises(lb.api.LnrError):
+        lb.Index.load(ctx2, bad)
+    raw[len(raw) // 2] ^= 0x40
+    open(bad, "wb").write(raw)
+    with pytest.raises(lb.api.LnrError):
+        lb.Index.load(ctx2, bad)
+    open(bad, "wb").write(b">chr1\nACGT\n" * 100)
+    with pytest.raises(lb.api.LnrError):
+        lb.Index.load(ctx2, bad)
