@@ -689,6 +689,31 @@ def main():
                  "ms_per_block": 1000 * dt_small / n_blk,
                  "what": "each host thread calls lnr_apxmap_batch on blocks of 64 reads (host buffers in and out), the way "
                          "Mapper::p_calRecords is driven with -b 1"}
+        # the same pattern from as many calling threads as the reference would run with -t 16: a block keeps 64 warps busy, so
+        # the device has room for many blocks in flight and the throughput follows the number of callers
+        try:
+            n_thr = int(os.environ.get("LNR_BENCH_SMALL_THREADS", 16))
+            class _C:
+                pass
+            extra = []
+            for _ in range(n_thr):
+                o = _C(); o.ctx = lb.Context(local_rank); extra.append(o)
+            for rep in range(2):
+                outs = [[] for _ in range(n_thr)]
+                th = [threading.Thread(target=small_work, args=(extra[i], i, outs[i])) for i in range(n_thr)]
+                torch.cuda.synchronize()
+                t0 = time.time()
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                dt_small = time.time() - t0
+            small["more_threads"] = {"host_threads": n_thr, "reads_per_s": n_blk * n_thr * blk / dt_small, "blocks": n_blk * n_thr,
+                                     "ms_per_block": 1000 * dt_small / n_blk}
+            for o in extra:
+                o.ctx.close()
+        except Exception as e:  # noqa: BLE001
+            small["more_threads"] = {"error": repr(e)}
     # ---- host-side ceiling: what this box delivers when every rank only uploads its batch (pinned host -> HBM), all ranks at once
     up = torch.empty(total_bases, dtype=torch.uint8, device=dev)
     up.copy_(bases_pin, non_blocking=True)

@@ -152,15 +152,25 @@ __device__ __forceinline__ void hdir_insert(HNode * tab, u64 mask, u64 key, u32 
 // getXDir (index_util.cpp:1102): exact-match lookups; returns empty_dir on a miss
 __device__ __forceinline__ u64 hdir_lookup(const HNode * __restrict__ tab, u64 mask, u64 X, u64 Y, u64 empty_dir)
 {
+    // A virtual head (block >= 1024) sends the lookup on to the key (Y, X). For Y == 0 that is the key it started with: the
+    // reference then probes the same slots again, for ever (index_util.cpp:1082-1086 -- `linear -i 2` does not return from
+    // such a read; from ~200 Mbase on every run meets one). The (key -> value) map has no such entry, so the canonical
+    // answer is a miss, which is what the oracle's exact-match map returns.
     u64 val = (X << 2) + 1, delta = 0;
     u64 h = xnode_hash(X) & mask;
+    bool rehashed = false;
     while (true)
     {
         u64 v1 = tab[h].val1;
         if (!v1) return empty_dir;
         u64 c = v1 ^ val;
         if (c == 0) return tab[h].val2;
-        if (c == 2) { val = (Y << 42) + (X << 2) + 1; h = xnode_hash((Y << 40) + X) & mask; delta = 0; continue; }
+        if (c == 2)
+        {
+            if (rehashed || Y == 0) return empty_dir;
+            rehashed = true;
+            val = (Y << 42) + (X << 2) + 1; h = xnode_hash((Y << 40) + X) & mask; delta = 0; continue;
+        }
         h = (h + delta + 1) & mask; delta++;
     }
 }

@@ -210,6 +210,12 @@ struct LaunchScope
         if (!on) return;
         cudaEventRecord(p.b, ctx->stream);
         ctx->pending.push_back(p);
+        if (getenv("LNR_TRACE_SYNC"))      // debugging aid: name every launch as it completes (the last line names the one before a hang)
+        {
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            fprintf(stderr, "[lnr sync] %s %s\n", p.name.c_str(), e == cudaSuccess ? "done" : cudaGetErrorString(e));
+            fflush(stderr);
+        }
     }
 };
 static void harvest_stats(lnr_ctx * ctx)
@@ -3181,8 +3187,17 @@ int lnr_index_export_hindex(const lnr_index * ix, uint64_t * ysa, uint64_t ysa_c
 // ---- seeding pass (count / scan / fill) -----------------------------------------------------------------------
 // tasks: host copy (sample0/n_samples filled); d_tasks: device copy. On return anchorsA holds the anchors,
 // *d_aoff the per-sample offsets (n_samples + 1 entries, in sample_info's tail buffer), total anchors in *total.
+// the most raw anchors any single task of the pass has: what the big-arena launches (one task per warp) must be able to hold
+__global__ void k_task_max_anchors(const SeedTask * __restrict__ tasks, u32 n_tasks, const u64 * __restrict__ aoff, unsigned long long * out)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 m = 0;
+    if (i < n_tasks) { const SeedTask t = tasks[i]; m = aoff[t.sample0 + t.n_samples] - aoff[t.sample0]; }
+    for (int o = 16; o; o >>= 1) { u64 v = __shfl_xor_sync(0xffffffffu, m, o); m = v > m ? v : m; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, (unsigned long long)m);
+}
 static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases, const u64 * d_read_off, SeedTask * d_tasks,
-                        u32 n_tasks, u64 n_samples, DevBuf & aoff_buf, u64 * total_out, const char * tag)
+                        u32 n_tasks, u64 n_samples, DevBuf & aoff_buf, u64 * total_out, const char * tag, u64 * max_task_out = nullptr)
 {
     if (ix->index_type == 1 && !ix->d_dirx)
     {
@@ -3235,10 +3250,14 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     CK(cudaGetLastError());
     int rc = device_scan<u64>(ctx, ctx->sample_cnt.as<u32>(), n_samples + 1, 0, aoff_buf.as<u64>(), d_total, "k_scan_seeds");
     if (rc) return rc;
-    u64 total = 0;
-    CK(cudaMemcpyAsync(&total, d_total, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(d_total + 1, 0, sizeof(u64), ctx->stream));
+    if (n_tasks) k_task_max_anchors<<<(n_tasks + 255) / 256, 256, 0, ctx->stream>>>(d_tasks, n_tasks, aoff_buf.as<u64>(), (unsigned long long *)(d_total + 1));
+    u64 tm[2] = {0, 0};
+    CK(cudaMemcpyAsync(tm, d_total, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    const u64 total = tm[0];
     *total_out = total;
+    if (max_task_out) *max_task_out = tm[1];
     size_t need = (size_t)(total + n_tasks + 8) * sizeof(u64);
     CK(ctx->anchorsA.reserve(need));
     CK(ctx->anchorsB.reserve(need));
@@ -3404,8 +3423,8 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     CK(cudaGetLastError());
     // ---- primary seeding
     DevBuf & aoff = ctx->read_meta;   // reused as the per-sample anchor offset buffer
-    u64 total_anchors = 0;
-    int rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks.as<SeedTask>(), n_reads, n_samples, aoff, &total_anchors, "k_seed_count");
+    u64 total_anchors = 0, max_task_anchors = 0;
+    int rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks.as<SeedTask>(), n_reads, n_samples, aoff, &total_anchors, "k_seed_count", &max_task_anchors);
     if (rc) return rc;
     tr.lap("feat+seed(sync)");
     if (dbg && dbg->raw_anchors_off)
@@ -3515,7 +3534,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         need = (need + (1u << 20) - 1) & ~(u64)((1u << 20) - 1);
         return (size_t)std::min<u64>(need, ctx->big_arena_bytes_per_warp);
     };
-    size_t big_per_warp = big_need(total_anchors);
+    size_t big_per_warp = big_need(max_task_anchors);     // a warp of the big-arena launches runs one task at a time
     CK(ctx->big_arena.reserve(32 * big_per_warp));
     CK(ctx->big_list.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
     a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
@@ -3534,9 +3553,9 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     {
         // -c 0: one kernel per attempt (k_map_c0) plus its big-arena launch; the second attempt is seeded at step 7 for the
         // reads the first one left too short
-        if (c0_scratch_bound((int)std::min<u64>(total_anchors + n_reads + 2, 0x7ffffff0ull)) > big_per_warp)
+        if (c0_scratch_bound((int)std::min<u64>(max_task_anchors + 4, 0x7ffffff0ull)) > big_per_warp)
         {
-            big_per_warp = (size_t)std::min<u64>((c0_scratch_bound((int)std::min<u64>(total_anchors + n_reads + 2, 0x7ffffff0ull)) + (1u << 20) - 1) & ~(u64)((1u << 20) - 1),
+            big_per_warp = (size_t)std::min<u64>((c0_scratch_bound((int)std::min<u64>(max_task_anchors + 4, 0x7ffffff0ull)) + (1u << 20) - 1) & ~(u64)((1u << 20) - 1),
                                                  ctx->big_arena_bytes_per_warp);
             CK(ctx->big_arena.reserve(32 * big_per_warp));
             a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
@@ -3571,10 +3590,10 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
             u64 ns2 = 0;
             for (u32 i = 0; i < n_tasks2; i++) { t2[i].sample0 = ns2; ns2 += t2[i].n_samples; }
             CK(upload_small(ctx, ctx->tasks2.p, t2.data(), n_tasks2 * sizeof(SeedTask)));
-            u64 total2 = 0;
-            rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_c0_retry");
+            u64 total2 = 0, max2 = 0;
+            rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_c0_retry", &max2);
             if (rc) return rc;
-            const u64 need2 = (c0_scratch_bound((int)std::min<u64>(total2 + n_tasks2 + 2, 0x7ffffff0ull)) + (1u << 20) - 1) & ~(u64)((1u << 20) - 1);
+            const u64 need2 = (c0_scratch_bound((int)std::min<u64>(max2 + 4, 0x7ffffff0ull)) + (1u << 20) - 1) & ~(u64)((1u << 20) - 1);
             if (std::min<u64>(need2, ctx->big_arena_bytes_per_warp) > big_per_warp)
             {
                 big_per_warp = (size_t)std::min<u64>(need2, ctx->big_arena_bytes_per_warp);
@@ -3675,12 +3694,12 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         CK(ctx->remap_list.reserve(std::max<size_t>(remap_reads.size(), 1) * sizeof(u32)));
         u32 * d_remap = ctx->remap_list.as<u32>();
         CK(upload_small(ctx, d_remap, remap_reads.data(), remap_reads.size() * sizeof(u32)));
-        u64 total2 = 0;
-        rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_remap");
+        u64 total2 = 0, max2 = 0;
+        rc = seeding_pass(ctx, ix, d_bases, d_read_off, ctx->tasks2.as<SeedTask>(), n_tasks2, ns2, aoff, &total2, "k_seed_count_remap", &max2);
         if (rc) return rc;
-        if (big_need(total2) > big_per_warp)
+        if (big_need(max2) > big_per_warp)
         {
-            big_per_warp = big_need(total2);
+            big_per_warp = big_need(max2);
             CK(ctx->big_arena.reserve(32 * big_per_warp));
             a.big_arena = ctx->big_arena.as<u8>(); a.big_arena_per_warp = big_per_warp;
         }

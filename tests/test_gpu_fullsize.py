@@ -119,3 +119,30 @@ def test_config2_cords_and_dindex_vs_reference():
     assert par["dindex_equal"], par
     assert par["cords"] > 50 * n_reads          # the reads really mapped
     assert np.array_equal(f_gpu, f_ref)
+
+
+def test_hindex_at_200_mbase_returns_and_equals_the_oracle():
+    """-i 2 beyond the small genomes. From ~200 Mbase on HIndex blocks reach the 1024-record limit and get virtual heads; a
+    read seed that meets one with YValue == 0 sends the reference's getXDir (index_util.cpp:1076-1090) round the same probe
+    sequence for ever -- on this very input `ref_read_stage(read 8, stage 1)` did not return within 150 s (round 2 log) --
+    while the (key -> value) map has no such entry. The library answers with a miss, like the oracle's exact-match map:
+    raw anchors and cords of all reads equal the oracle's, and the call returns."""
+    import linear_b200 as lb
+    from linear_b200 import datagen
+    from cpu_checkers import Oracle
+    lens = datagen.contig_lengths(200_000_000, 4, seed=31)
+    rng = np.random.default_rng(5)
+    g = [rng.integers(0, 4, size=int(l), dtype=np.uint8) for l in lens]
+    rs = datagen.simulate_reads(9, g, 16, mean_len=15000, sd_len=3000, err=0.1, sv_frac=0.2)
+    ctx = lb.Context(0)
+    gen = lb.Genome(ctx, g)
+    feats = lb.create_features(ctx, gen, 2, 16)
+    index = lb.create_index(ctx, gen, 2, 16)
+    cords, coff, dbg = lb.apx_map_batch(ctx, index, feats, rs.bases, rs.offsets, preset=1, debug=True)
+    O = Oracle(g, threads=16, preset=1, index_type=2)
+    for i in range(rs.n):
+        a = O.stage(rs.read(i), 1)[1:]
+        got = dbg["ra"][int(dbg["ra_off"][i]):int(dbg["ra_off"][i + 1])]
+        assert np.array_equal(a, got), f"raw anchors of read {i}"
+    oc, oo = O.map_batch(rs.bases, rs.offsets, map_threads=8)
+    assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
