@@ -1240,16 +1240,18 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
     }
     // 4 Y bytes per step; ykey_match(b, Y) with v = b ^ Y, l = lowest set bit of v: v == 0 or v >> ctz(v) < 4  <=>  v <= 3 l
     const u32 Y4 = qY * 0x01010101u;
+    // all four bytes at once: v <= 3 l  <=>  v has no two set bits two or more positions apart. s = every position at least
+    // two below a set bit of v (per byte), d = v & s is zero exactly for the matching bytes; d <= 0x3f, so d + 0x7f sets a
+    // byte's top bit iff the byte is non-zero and never carries into the next one; one multiply gathers the four flags
     auto match4 = [&](u32 w4, u32 i) -> u32 {
-        u32 v4 = w4 ^ Y4;
-        u32 h4 = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-        {
-            u32 v = (v4 >> (8 * j)) & 0xffu;
-            u32 l = v & (0u - v);
-            h4 |= v <= 3u * l ? (1u << j) : 0u;
-        }
+        const u32 v4 = w4 ^ Y4;
+        u32 sm = (v4 >> 2) & 0x3f3f3f3fu;
+        sm |= (sm >> 1) & 0x7f7f7f7fu;
+        sm |= (sm >> 2) & 0x3f3f3f3fu;
+        sm |= (sm >> 4) & 0x0f0f0f0fu;
+        const u32 d = v4 & sm;
+        const u32 z = (((d + 0x7f7f7f7fu) & 0x80808080u) ^ 0x80808080u) >> 7;
+        u32 h4 = (z * 0x01020408u) >> 24;
         u32 rem = scanned - i;
         if (rem < 4) h4 &= (1u << rem) - 1u;
         return h4;
