@@ -168,7 +168,8 @@ int lnr_apxmap_batch_device(lnr_ctx *, const lnr_index *, const lnr_feats * f2, 
 int lnr_last_batch_counters(lnr_ctx *, uint64_t counters[8]);
 /* fallback-path diagnostics of the last batch (tests assert that the rare paths really ran): 0 tasks taken by the big-arena
  * hit pass, 1 reads finished by the big-arena finish pass, 2 seeding samples re-scanned because their match list did not
- * fit the pool, 3..7 reserved */
+ * fit the pool, 3 tasks with more anchors than a warp's share of the scratch holds that the big-arena warps of the hit-section
+ * kernels served (the "heavy lane"), 4..7 reserved */
 int lnr_last_batch_diag(lnr_ctx *, uint64_t diag[8]);
 /* profiling aid: SM cycles spent per stage of the warp-per-read pipeline in the last batch (lane 0, summed over warps):
  * 0 binning, 1 ascending sort, 2 run filter, 3 x sort, 4 chaining DP, 5 traceback, 6 hit blocks, 7 hit window filter,

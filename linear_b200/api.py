@@ -171,7 +171,7 @@ class Context:
     def diag(self):
         c = (C.c_uint64 * 8)()
         self.check(self.lib.lnr_last_batch_diag(self.h, c))
-        return {"hits_big_tasks": int(c[0]), "finish_big_reads": int(c[1]), "seed_rescans": int(c[2])}
+        return {"hits_big_tasks": int(c[0]), "finish_big_reads": int(c[1]), "seed_rescans": int(c[2]), "heavy_lane_tasks": int(c[3])}
 
     def stage_cycles(self):
         c = (C.c_uint64 * 16)()

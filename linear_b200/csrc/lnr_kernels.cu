@@ -131,7 +131,7 @@ struct lnr_ctx
     DevBuf ing[8];   // read-ingest temporaries (lnr_ingest.cuh)
     void * reads_cache = nullptr; size_t reads_cache_bytes = 0;   // last output block given back by lnr_reads_destroy
     DevBuf packed;   // 2-bit packed batch as uploaded (lnr_apxmap_batch_packed)
-    DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, seed_masks, seed_mask_off, warp_rec;
+    DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, heavy_list, seed_masks, seed_mask_off, warp_rec;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -1243,7 +1243,7 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
     // all four bytes at once: v <= 3 l  <=>  v has no two set bits two or more positions apart. s = every position at least
     // two below a set bit of v (per byte), d = v & s is zero exactly for the matching bytes; d <= 0x3f, so d + 0x7f sets a
     // byte's top bit iff the byte is non-zero and never carries into the next one; one multiply gathers the four flags
-    auto match4 = [&](u32 w4, u32 i) -> u32 {
+    auto match4raw = [&](u32 w4) -> u32 {
         const u32 v4 = w4 ^ Y4;
         u32 sm = (v4 >> 2) & 0x3f3f3f3fu;
         sm |= (sm >> 1) & 0x7f7f7f7fu;
@@ -1251,7 +1251,10 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         sm |= (sm >> 4) & 0x0f0f0f0fu;
         const u32 d = v4 & sm;
         const u32 z = (((d + 0x7f7f7f7fu) & 0x80808080u) ^ 0x80808080u) >> 7;
-        u32 h4 = (z * 0x01020408u) >> 24;
+        return (z * 0x01020408u) >> 24;
+    };
+    auto match4 = [&](u32 w4, u32 i) -> u32 {       // the same with the keys behind the bucket's end masked off
+        u32 h4 = match4raw(w4);
         u32 rem = scanned - i;
         if (rem < 4) h4 &= (1u << rem) - 1u;
         return h4;
@@ -1265,16 +1268,17 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
         // records 0..23 come with the first half of the lookup entry, 24..55 with its second half (the same 64-byte DRAM
         // burst: an L2 hit), only longer buckets go on in hsy
         const u32 ew[6] = {e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        // the first 64 records: unmasked flags into m0, the bucket's end is applied once at the end (one popcount)
 #pragma unroll
         for (int q = 0; q < 6; q++)
-            if (4u * q < scanned) { u32 h4 = match4(ew[q], 4u * q); c += __popc(h4); m0 |= (u64)h4 << (4 * q); }
+            if (4u * q < scanned) m0 |= (u64)match4raw(ew[q]) << (4 * q);
         if (scanned > 24)
         {
             const uint4 e2 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 2), e3 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 3);
             const u32 fw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
 #pragma unroll
             for (int q = 0; q < 8; q++)
-                if (24u + 4u * q < scanned) { u32 h4 = match4(fw[q], 24u + 4u * q); c += __popc(h4); m0 |= (u64)h4 << (24 + 4 * q); }
+                if (24u + 4u * q < scanned) m0 |= (u64)match4raw(fw[q]) << (24 + 4 * q);
         }
         if (scanned > (u32)kDirxKeys)
         {
@@ -1282,12 +1286,13 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
             for (u32 i = kDirxKeys; i < scanned; i += 4)
             {
                 u32 w1 = __ldg(pw + ((i - kDirxKeys) >> 2) + 1);
-                u32 h4 = match4(__funnelshift_r(w0, w1, sh), i);
-                c += __popc(h4);
-                if (i < 64) m0 |= (u64)h4 << i;
+                if (i < 64) m0 |= (u64)match4raw(__funnelshift_r(w0, w1, sh)) << i;
+                else c += __popc(match4(__funnelshift_r(w0, w1, sh), i));
                 w0 = w1;
             }
         }
+        if (scanned < 64) m0 &= (1ULL << scanned) - 1ULL;
+        c += __popcll(m0);
     }
     // claim the warp's run of entries: exclusive prefix of the per-lane counts, one atomic per warp
     u32 incl = c, hsum = scanned;
@@ -1445,6 +1450,10 @@ struct MapArgs
     SeedTask * tasks2; u32 tasks2_cap; u32 * n_tasks2; // re-map tasks produced by the primary pass
     u32 * bins; u8 * arena; u64 arena_per_warp;
     u64 fit_cap;                                       // k_hits_sort: the smallest per-warp arena of the three section kernels
+    // Heavy tasks of the primary pass (more raw anchors than fit_n: their scratch bound exceeds a warp's share of the arena).
+    // k_order_tasks lists them; in each of the three section kernels the first kBigWarps warps take them first, each on its
+    // slot of the big arena, so the few reads with the most anchors start at once instead of queueing behind everything else
+    u32 fit_n; const u32 * heavy_list; const u32 * n_heavy; u32 * queue_h;
     u32 * queue;                                       // atomic work counter
     const u32 * order;                                 // reads sorted by length, longest first (tail latency)
     int index_type;                                    // 1 DIndex, 2 HIndex (sample grid of re-map tasks)
@@ -1522,7 +1531,8 @@ __device__ __noinline__ void finish_read(const Warp & w, FinishBufs & f, u64 L, 
 // Processing order of the primary pass: tasks with the most raw anchors first (their hits stage is the longest, so
 // they must not start last). Counting sort into 132 quarter-octave buckets, one CTA.
 __global__ void __launch_bounds__(1024) k_order_tasks(const SeedTask * __restrict__ tasks, u32 n_tasks, const u64 * __restrict__ aoff,
-                                                      u32 * __restrict__ order)
+                                                      u32 * __restrict__ order, u32 fit_n = 0xffffffffu, u32 * heavy_list = nullptr,
+                                                      u32 * n_heavy = nullptr)
 {
     __shared__ u32 s_cnt[136];
     for (int i = threadIdx.x; i < 136; i += blockDim.x) s_cnt[i] = 0;
@@ -1535,7 +1545,15 @@ __global__ void __launch_bounds__(1024) k_order_tasks(const SeedTask * __restric
         int b = lg * 4 + frac + 1;
         return b > 135 ? 135 : b;
     };
-    for (u32 t = threadIdx.x; t < n_tasks; t += blockDim.x) atomicAdd(&s_cnt[bucket(t)], 1u);
+    for (u32 t = threadIdx.x; t < n_tasks; t += blockDim.x)
+    {
+        atomicAdd(&s_cnt[bucket(t)], 1u);
+        if (heavy_list)     // n of phase_map = raw anchors + the sentinel slot
+        {
+            u64 n = aoff[tasks[t].sample0 + tasks[t].n_samples] - aoff[tasks[t].sample0] + 1;
+            if (n > (u64)fit_n) heavy_list[atomicAdd(n_heavy, 1u)] = t;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0)
     {
@@ -1661,9 +1679,11 @@ __global__ void __launch_bounds__(128, LNR_HITS_MIN_CTAS) k_map_hits(MapArgs a, 
 // ---- primary pass of stage 1 as three kernels, one per section of the hit stage (lnr_pipeline.h hits_sec_*). Per-task
 // state between them lives in the task's own anchor regions: k_hits_sort leaves the x-sorted anchors in A[0..n2),
 // k_hits_chain the chained hits in B[0..n_hits) and their scores (int32) in A, k_hits_blocks the final hits in A.
+static const u32 kBigWarps = 32;      // slots of the big arena
 struct StageCommon
 {
     Warp w; u32 gw; Arena ar; PipeCounters cnt;
+    Arena small, big; bool big_warp, heavy_open;
     // LNR_LONGEST_PROFILE: when this warp started / retired and its slowest task
     u64 * rec; u64 g_start; long long t_task; u64 max_dur, max_ti, max_size, max_q, q, n_done;
 };
@@ -1672,6 +1692,10 @@ __device__ __forceinline__ void stage_begin(const MapArgs & a, StageCommon & c)
     c.w = {(int)(threadIdx.x & 31), 0xffffffffu};
     c.gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     c.ar = {a.arena + (u64)c.gw * a.arena_per_warp, a.arena_per_warp, 0, 0};
+    c.small = c.ar;
+    c.big_warp = a.heavy_list != nullptr && c.gw < kBigWarps;
+    c.heavy_open = c.big_warp;
+    c.big = {a.big_arena + (u64)c.gw * a.big_arena_per_warp, a.big_arena_per_warp, 0, 0};
     memset(&c.cnt, 0, sizeof c.cnt);
     c.rec = nullptr;
 }
@@ -1688,8 +1712,27 @@ __device__ __forceinline__ void stage_task_done(StageCommon & c, u32 ti, u64 siz
     c.n_done++;
     if (d > c.max_dur) { c.max_dur = d; c.max_ti = ti; c.max_size = size; c.max_q = c.q; }
 }
-__device__ __forceinline__ bool stage_next(const MapArgs & a, StageCommon & c, u32 & ti)
+// next task of this warp; heavy = it comes from the heavy list and runs on the warp's big-arena slot (c.ar is switched).
+// Heavy tasks that a warp meets in the ordinary queue are skipped by the caller (task_is_heavy): the big warps own them.
+__device__ __forceinline__ bool stage_next(const MapArgs & a, StageCommon & c, u32 & ti, bool & heavy)
 {
+    heavy = false;
+    if (c.heavy_open)
+    {
+        u32 h = 0;
+        if (c.w.lane == 0) h = atomicAdd(a.queue_h, 1u);
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (h < *a.n_heavy)
+        {
+            ti = a.heavy_list[h];
+            heavy = true;
+            c.ar = c.big;
+            if (c.rec) { c.q = h; c.t_task = clock64(); }
+            return true;
+        }
+        c.heavy_open = false;
+        c.ar = c.small;
+    }
     u32 q = 0;
     if (c.w.lane == 0) q = atomicAdd(a.queue, 1u);
     q = __shfl_sync(0xffffffffu, q, 0);
@@ -1698,6 +1741,7 @@ __device__ __forceinline__ bool stage_next(const MapArgs & a, StageCommon & c, u
     if (c.rec) { c.q = q; c.t_task = clock64(); }
     return true;
 }
+__device__ __forceinline__ bool task_is_heavy(const MapArgs & a, int n) { return a.heavy_list != nullptr && (u32)n > a.fit_n; }
 __device__ __forceinline__ void stage_end(const MapArgs & a, const StageCommon & c)
 {
     if (c.rec && c.w.lane == 0)
@@ -1733,24 +1777,26 @@ __global__ void __launch_bounds__(128, 8) k_hits_sort(MapArgs a)
     const Warp w = c.w;
     u32 * bins = a.bins + (u64)c.gw * kNumBins;
     stage_rec_begin(a, c, 0);
-    u32 ti;
-    while (stage_next(a, c, ti))
+    u32 ti; bool heavy;
+    while (stage_next(a, c, ti, heavy))
     {
         const SeedTask t = a.tasks[ti];
         u32 r = t.read;
         u64 L = a.read_off[r + 1] - a.read_off[r];
+        u64 base; int n;
+        task_region(a, ti, t, base, n);
+        if (!heavy && task_is_heavy(a, n)) continue;    // taken from the heavy list by one of the big warps
+        if (heavy && w.lane == 0) atomicAdd(&a.counters[19], 1ULL);    // diagnostics: tasks served by the heavy lane
         if (w.lane == 0) { a.task_nhits[ti] = 0; a.task_state[ti] = 0; }
         if (L <= (u64)kMinReadLen) continue;            // mapper.cpp:440
         long long tl = LNR_CLOCK();
-        u64 base; int n;
-        task_region(a, ti, t, base, n);
         if (w.lane == 0 && a.dbg_hits)
         {
             a.dbg_nhits[r] = 1;
             if (a.dbg_hoff[r + 1] > a.dbg_hoff[r]) a.dbg_hits[a.dbg_hoff[r]] = kFlagEnd;
         }
         c.cnt.t[12]++;
-        if (phase_map_scratch_bound(n) > a.fit_cap || (u64)n * 16 + 4096 > c.ar.cap)
+        if (heavy ? phase_map_scratch_bound(n) > c.ar.cap : (phase_map_scratch_bound(n) > a.fit_cap || (u64)n * 16 + 4096 > c.ar.cap))
         {
             // does not fit the per-warp arena: the whole task is left, untouched, to the big-arena pass
             if (w.lane == 0) { a.task_nhits[ti] = 0xffffffffu; a.task_state[ti] = 0xffffffffu; a.big_list[atomicAdd(a.n_big, 1u)] = ti; }
@@ -1782,17 +1828,18 @@ __global__ void __launch_bounds__(128, LNR_CHAIN_MIN_CTAS) k_hits_chain(MapArgs 
     stage_begin(a, c);
     const Warp w = c.w;
     stage_rec_begin(a, c, 1);
-    u32 ti;
-    while (stage_next(a, c, ti))
+    u32 ti; bool heavy;
+    while (stage_next(a, c, ti, heavy))
     {
+        const SeedTask t = a.tasks[ti];
+        u64 base; int n;
+        task_region(a, ti, t, base, n);
+        if (!heavy && task_is_heavy(a, n)) continue;
         const u32 n2 = a.task_state[ti];
         if (n2 == 0 || n2 == 0xffffffffu) continue;
-        const SeedTask t = a.tasks[ti];
         long long tl = LNR_CLOCK();
         PipeIn in;
         fill_pipe_in(a, t.read, in);
-        u64 base; int n;
-        task_region(a, ti, t, base, n);
         arena_reset(c.ar);
         i32 * score = arena_alloc<i32>(c.ar, (u64)n2 + 2);
         int n_hits = 1;
@@ -1817,18 +1864,19 @@ __global__ void __launch_bounds__(128, LNR_BLOCKS_MIN_CTAS) k_hits_blocks(MapArg
     stage_begin(a, c);
     const Warp w = c.w;
     stage_rec_begin(a, c, 2);
-    u32 ti;
-    while (stage_next(a, c, ti))
+    u32 ti; bool heavy;
+    while (stage_next(a, c, ti, heavy))
     {
+        const SeedTask t = a.tasks[ti];
+        u64 base; int n;
+        task_region(a, ti, t, base, n);
+        if (!heavy && task_is_heavy(a, n)) continue;
         const u32 nh = a.task_state[ti];
         if (nh == 0 || nh == 0xffffffffu) continue;
-        const SeedTask t = a.tasks[ti];
         const u32 r = t.read;
         long long tl = LNR_CLOCK();
         PipeIn in;
         fill_pipe_in(a, r, in);
-        u64 base; int n;
-        task_region(a, ti, t, base, n);
         arena_reset(c.ar);
         int n_hits = (int)nh;
         i32 * score = arena_alloc<i32>(c.ar, (u64)n_hits + 2);
@@ -3518,9 +3566,24 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     if (dbg && dbg->hits_off) { a.dbg_hits = ctx->dbg_hits.as<u64>(); a.dbg_hoff = ctx->dbg_hoff.as<u64>(); a.dbg_nhits = ctx->dbg_nhits.as<u32>(); }
     if (dbg && dbg->cords1_off) { a.dbg_c1 = ctx->dbg_c1.as<u64>(); a.dbg_nc1 = ctx->dbg_nc1.as<u32>(); }
     tr.lap("seed_fill", true);
+    // the most anchors (+ sentinel) a task may have to be served from a warp's share of the arena in all three section
+    // kernels; the tasks above it are listed by k_order_tasks and taken by the big-arena warps of those kernels
+    const u64 sec_fit_cap = std::min(arena_share(ctx->chain_ctas_per_sm), arena_share(ctx->blocks_ctas_per_sm));
+    u32 fit_n = 0;
+    {
+        const u64 per = phase_map_scratch_bound(1) - phase_map_scratch_bound(0);       // the bound is linear in n
+        const u64 n_a = sec_fit_cap > phase_map_scratch_bound(0) ? (sec_fit_cap - phase_map_scratch_bound(0)) / per : 0;
+        const u64 share_sort = arena_share(ctx->sort_ctas_per_sm);
+        const u64 n_b = share_sort > 4096 ? (share_sort - 4096) / 16 : 0;
+        fit_n = (u32)std::min<u64>(std::min(n_a, n_b), 0x7fffffffu);
+    }
+    const bool heavy_lane = !no_chain && !getenv("LNR_MONOLITHIC_HITS") && !getenv("LNR_NO_HEAVY_LANE");
+    CK(ctx->heavy_list.reserve((size_t)n_reads * sizeof(u32)));
+    u32 * d_queue_h = d_queue + 4, * d_n_heavy = d_queue + 5;
     {
         LaunchScope ls(ctx, "k_order_tasks");
-        k_order_tasks<<<1, 1024, 0, ctx->stream>>>(ctx->tasks.as<SeedTask>(), n_reads, aoff.as<u64>(), ctx->order.as<u32>());
+        k_order_tasks<<<1, 1024, 0, ctx->stream>>>(ctx->tasks.as<SeedTask>(), n_reads, aoff.as<u64>(), ctx->order.as<u32>(), fit_n,
+                                                  heavy_lane ? ctx->heavy_list.as<u32>() : nullptr, d_n_heavy);
     }
     CK(ctx->task_nhits.reserve((size_t)std::max<u32>(n_reads, tasks2_cap) * sizeof(u32)));
     a.task_nhits = ctx->task_nhits.as<u32>();
@@ -3623,11 +3686,13 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         as.arena_per_warp = arena_share(ctx->sort_ctas_per_sm);
         const u64 cap_chain = arena_share(ctx->chain_ctas_per_sm), cap_blocks = arena_share(ctx->blocks_ctas_per_sm);
         as.fit_cap = std::min(cap_chain, cap_blocks);   // a task must fit every section's arena (this section: 12 B per anchor)
+        if (heavy_lane) { as.fit_n = fit_n; as.heavy_list = ctx->heavy_list.as<u32>(); as.n_heavy = d_n_heavy; as.queue_h = d_queue_h; }
         {
             LaunchScope ls(ctx, "k_hits_sort");
             k_hits_sort<<<grid_of(ctx->sort_ctas_per_sm), 128, 0, ctx->stream>>>(as);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        CK(cudaMemsetAsync(d_queue_h, 0, sizeof(u32), ctx->stream));
         as.arena_per_warp = cap_chain;
         CK(ctx->order2.reserve((size_t)n_reads * sizeof(u32)));
         as.order = ctx->order2.as<u32>();
@@ -3640,6 +3705,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
             k_hits_chain<<<grid_of(ctx->chain_ctas_per_sm), 128, 0, ctx->stream>>>(as);
         }
         CK(cudaMemsetAsync(d_queue, 0, sizeof(u32), ctx->stream));
+        CK(cudaMemsetAsync(d_queue_h, 0, sizeof(u32), ctx->stream));
         as.arena_per_warp = cap_blocks;
         {
             LaunchScope ls(ctx, "k_order_by_key");

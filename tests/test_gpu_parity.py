@@ -192,7 +192,12 @@ def test_scratch_overflow_falls_back_to_big_arena(lb, monkeypatch):
     index = lb.create_index(small, gen, 1, T)
     cords, coff = lb.apx_map_batch(small, index, feats, bases, offs, preset=preset)
     d = small.diag()
-    assert d["hits_big_tasks"] > 0 and d["finish_big_reads"] > 0, d     # the big-arena passes really took tasks
+    assert d["heavy_lane_tasks"] > 0 and d["finish_big_reads"] > 0, d   # the big-arena warps / passes really took tasks
+    # the same with the heavy lane switched off: the tasks go through the separate big-arena launch instead
+    monkeypatch.setenv("LNR_NO_HEAVY_LANE", "1")
+    c2, o2 = lb.apx_map_batch(small, index, feats, bases, offs, preset=preset)
+    assert small.diag()["hits_big_tasks"] > 0 and small.diag()["heavy_lane_tasks"] == 0
+    assert np.array_equal(o2, coff) and np.array_equal(c2, cords)
     oc, oo = Oracle(g, threads=T, preset=preset).map_batch(bases, offs, map_threads=4)
     assert np.array_equal(oo, coff) and np.array_equal(oc, cords)
 
