@@ -300,6 +300,72 @@ LNR_PIPE u64 * gnu_sort_w(const Warp & w, u32 * hist, u64 * a, u64 * s0, u64 * s
 
 // ----------------------------------------------------------------------------------------------------
 // anchor filters (pmpfinder.cpp:1979-2183)
+// The same filter on all lanes. The recurrence is sequential only through its breaks: inside a run the median the next
+// anchor is tested against is a[(block_str + i - 1) >> 1], known without looking at the decisions before it. So every lane
+// tests one of the next anchors ON THE ASSUMPTION that all anchors between the round's first and its own continue the run;
+// the lanes below the first break (or the last anchor) were right and are folded in at once, the break itself is applied
+// as the reference does, and the next round starts behind it. A clean read advances 32 anchors per round, a noisy stretch
+// one break per round. One lane (host build) degenerates to the sequential loop of filter_anchor_runs below.
+LNR_PIPE int filter_anchor_runs_w(const Warp & w, const u64 * a, int n, Blk * ranges)
+{
+    int nr = 0;
+    if (n < 2) return 0;
+    u64 ak2 = a[1];
+    u64 block_str = 1, count = 0, min_y = ~0ULL, max_y = 0;
+    int i0 = 1;
+    while (i0 < n)
+    {
+        const int i = i0 + w.lane;
+        const bool valid = i < n;
+        u64 ai = 0, ref = ak2;
+        if (valid)
+        {
+            ai = a[i];
+            if (w.lane > 0) ref = a[(block_str + (u64)(i - 1)) >> 1];
+        }
+        const u64 y = cord_y(ai);
+        const u64 dy2 = (u64)iabs64((i64)(y - cord_y(ref)));
+        const bool cont = valid && cord_x40(ai - ref) < (dy2 >> 2);
+        const u32 ev = wballot(w, valid && (!cont || i == n - 1));
+        const int f = ev ? ffs32(ev) : w.nl;       // lanes below f continue the run (the last anchor is always an event)
+        if (f > 0)
+        {
+            const u32 mn = ~wmax_u32(w, w.lane < f ? ~(u32)y : 0u), mx = wmax_u32(w, w.lane < f ? (u32)y : 0u);
+            if (min_y > mn) min_y = mn;
+            if (max_y < mx) max_y = mx;
+            count += (u64)f;
+            ak2 = a[(block_str + (u64)(i0 + f - 1)) >> 1];
+        }
+        if (ev)
+        {
+            const int ix = i0 + f;
+            const u64 yf = (u64)wbcast(w, (u32)y, f);
+            const u64 af = wbcast64(w, ai, f);
+            if ((wballot(w, cont) >> f) & 1u)      // the last anchor, continuing the run
+            {
+                if (min_y > yf) min_y = yf;
+                if (max_y < yf) max_y = yf;
+                ++count;
+            }
+            const u64 thd = umax64((max_y - min_y) >> 10, 2);
+            if (count > thd)
+            {
+                if (w.lane == 0) { ranges[nr].first = (u32)block_str; ranges[nr].second = (u32)ix; }
+                nr++;
+            }
+            block_str = (u64)ix;
+            ak2 = af;
+            min_y = yf;
+            max_y = yf;
+            count = 1;
+            i0 = ix + 1;
+        }
+        else i0 += w.nl;
+    }
+    wsync(w);
+    return nr;
+}
+
 // ----------------------------------------------------------------------------------------------------
 LNR_HD u32 anchor_bin(u64 a) { return (u32)(cord_x(a) / 30000); }
 
@@ -763,6 +829,144 @@ LNR_HD int traceback(const E * el, ChainRec * rec, int n, E * out_el, i32 * out_
     return traceback1(el, rec, n, out_el, out_score, chain_off, max_chains, min_len, abort_score, bestn, stop_ratio);
 }
 
+// Warp versions of the two tracebacks: what is a scan over all n records in the reference -- the arg-max of every peel round
+// (traceBackChains0), the search for the leaves (traceBackChains1), the count of roots -- runs on all lanes; the short,
+// pointer-chasing parts (following one chain, ranking <= 64 trees) stay on lane 0. Same results as traceback<E> on lane 0.
+template <class E>
+LNR_PIPE int traceback0_w(const Warp & w, const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
+                          int min_len, int abort_score, int bestn, float stop_ratio)
+{   // traceBackChains0 :122
+    const int delete_score = -1000;
+    int n_chains = 0, pos = 0;                      // lane 0's
+    if (w.lane == 0) chain_off[0] = 0;
+    const int search_times = bestn < 50 ? bestn : 50;
+    for (int it = 0; it < search_times; it++)
+    {
+        // the sequential scan `if (score > max) { max_2nd = max; max = score; .. }` from max = -1 ends with the FIRST index of
+        // the largest score and with max_2nd = the largest score before that index (or -1)
+        i32 best = -1; int bidx = 0x7fffffff;
+        for (int j = w.lane; j < n; j += w.nl) { const i32 sc = rec[j].score; if (sc > best) { best = sc; bidx = j; } }
+        const i32 max_score = wmax_i32(w, best);
+        if (max_score <= -1) break;                 // f_done: nothing left (the stop-ratio clause cannot revive it: max_len = 0)
+        const int max_str = -wmax_i32(w, best == max_score ? -bidx : (i32)0x80000000);
+        if (max_score == 0) break;
+        i32 pm = -1;
+        for (int j = w.lane; j < max_str; j += w.nl) { const i32 sc = rec[j].score; pm = sc > pm ? sc : pm; }
+        const i32 max_2nd = wmax_i32(w, pm);
+        if (w.lane == 0)
+        {
+            const int max_len = rec[max_str].len;
+            if (max_len > min_len && max_score / (max_len - 1) > abort_score)
+            {
+                int cur = pos;   // tentative chain [pos, cur)
+                for (int j = max_str; j != -1; j = rec[j].p2anchor)
+                {
+                    if (rec[j].score != delete_score)
+                    {
+                        out_el[cur] = el[j];
+                        out_score[cur] = rec[j].score2;
+                        cur++;
+                        rec[j].score = delete_score;
+                    }
+                    else
+                    {
+                        int infix = rec[j].score2;
+                        if (max_score - infix < max_2nd)
+                        {
+                            for (int k = max_str; k != j; k = rec[k].p2anchor) rec[k].score = rec[k].score2 - infix;
+                            cur = pos;
+                        }
+                        break;
+                    }
+                }
+                if (cur != pos && n_chains < max_chains)
+                {
+                    pos = cur;
+                    n_chains++;
+                    chain_off[n_chains] = pos;
+                }
+            }
+            rec[max_str].score = delete_score;
+        }
+        wsync(w);
+    }
+    (void)stop_ratio;
+    return wbcast(w, n_chains, 0);
+}
+template <class E>
+LNR_PIPE int traceback_w(const Warp & w, const E * el, ChainRec * rec, int n, E * out_el, i32 * out_score, int * chain_off, int max_chains,
+                         int min_len, int abort_score, int bestn, float stop_ratio)
+{   // traceBackChains :307
+    int roots = 0;
+    for (int i = w.lane; i < n; i += w.nl) roots += rec[i].p2anchor == -1;
+    roots = wsum(w, roots);
+    if (roots > 50) return traceback0_w(w, el, rec, n, out_el, out_score, chain_off, max_chains, min_len, abort_score, bestn, stop_ratio);
+    // traceBackChains1 :214 -- only the leaves matter: gather them in index order (out_score is free until the chains are
+    // written), then the reference's own loop over that short list
+    int * leaf = (int *)out_score;
+    int n_leaf = 0;
+    for (int c = 0; c < n; c += w.nl)
+    {
+        const int j = c + w.lane;
+        const bool is_leaf = j < n && rec[j].f_leaf != 0;
+        const u32 bal = wballot(w, is_leaf);
+        if (is_leaf) leaf[n_leaf + popc_below(w, bal)] = j;
+        n_leaf += popc32(bal);
+    }
+    wsync(w);
+    int n_chains = 0;
+    if (w.lane == 0)
+    {
+        int root[64], lscore[64], llen[64], lidx[64];
+        int nt = 0;
+        for (int q = 0; q < n_leaf; q++)
+        {
+            const int j = leaf[q];
+            int f_new = 1;
+            for (int k = 0; k < nt; k++)
+                if (root[k] == rec[j].root_ptr)
+                {
+                    if (rec[j].score > lscore[k]) { lscore[k] = rec[j].score; llen[k] = rec[j].len; lidx[k] = j; }
+                    f_new = 0;
+                }
+            if (f_new && nt < 64) { root[nt] = rec[j].root_ptr; lscore[nt] = rec[j].score; llen[nt] = rec[j].len; lidx[nt] = j; nt++; }
+        }
+        struct Rank { int first, second; };
+        Rank ranks[64];
+        for (int i = 0; i < nt; i++) { ranks[i].first = i; ranks[i].second = lscore[i]; }
+        gnu_sort(ranks, nt, [](const Rank & a, const Rank & b) { return a.second > b.second; });
+        int pos = 0, f_stop = 0;
+        int stale = 0;   // the reference keeps appending to an uncleared `chain` once f_stop is set (dead data)
+        chain_off[0] = 0;
+        int lim = bestn < nt ? bestn : nt;
+        for (int i = 0; i < lim; i++)
+        {
+            int t = ranks[i].first;
+            int max_score = lscore[t], max_len = llen[t], max_str = lidx[t];
+            int mean = max_len > 1 ? max_score / (max_len - 1) : abort_score + 1;
+            if (max_len > min_len && mean > abort_score)
+            {
+                int cur = pos;
+                for (int j = max_str; j != -1; j = rec[j].p2anchor) { out_el[cur] = el[j]; out_score[cur] = rec[j].score2; cur++; }
+                if (cur != pos)
+                {
+                    if (n_chains > 0)
+                        if ((float)(u64)(cur - pos + stale) / (float)(u64)(chain_off[1] - chain_off[0]) < stop_ratio) f_stop = 1;
+                    if (!f_stop && n_chains < max_chains)
+                    {
+                        pos = cur;
+                        n_chains++;
+                        chain_off[n_chains] = pos;
+                    }
+                    else if (f_stop) stale += cur - pos;
+                }
+            }
+        }
+    }
+    wsync(w);
+    return wbcast(w, n_chains, 0);
+}
+
 // ----------------------------------------------------------------------------------------------------
 // blocks of hits / cords
 // ----------------------------------------------------------------------------------------------------
@@ -1057,11 +1261,7 @@ LNR_PIPE int chain_blocks_hits_w(const Warp & w, u32 * hist256, const u64 * recs
     for (int i = w.lane; i < nb; i += w.nl) { s.sep_tmp[i] = sep[s.ptr[i]]; s.score_tmp[i] = sep_score[s.ptr[i]]; }
     wsync(w);
     best_chains2_hits_w(w, recs, s.sep_tmp, s.score_tmp, s.rec, nb);
-    int nch = 0;
-    if (w.lane == 0) nch = traceback<Blk>(s.sep_tmp, s.rec, nb, s.out_el, s.out_score, s.chain_off, 6, 1, 0, 3, 0.7f);
-    nch = wbcast(w, nch, 0);
-    wsync(w);
-    return nch;
+    return traceback_w<Blk>(w, s.sep_tmp, s.rec, nb, s.out_el, s.out_score, s.chain_off, 6, 1, 0, 3, 0.7f);
 }
 
 // _filterBlocksHits (cluster_util.cpp:633): major chain + up to 4 optional chains > 0.8 * len.
@@ -1677,10 +1877,7 @@ LNR_PIPE int hits_sec_sort(const Warp & w, Arena & ar, u32 * hist256, u32 * bins
     if (ar.failed) return 1;
     u64 * sorted = radix_sort(w, hist256, S, O, C, m, 62, sort_key(0));
     LNR_LAP(cnt, 1, tl);
-    int nr = 0;
-    if (w.lane == 0) nr = filter_anchor_runs(sorted, m, ranges);
-    nr = wbcast(w, nr, 0);
-    wsync(w);
+    const int nr = filter_anchor_runs_w(w, sorted, m, ranges);
     // compact the accepted runs (anchors[0] is dropped, filterAnchors1 :2073)
     u64 * F = (sorted == O) ? C : O;         // a buffer that is neither `sorted` nor S
     if (F == S) F = (sorted == C) ? O : C;
@@ -1727,17 +1924,15 @@ LNR_PIPE int hits_sec_chain(const Warp & w, Arena & ar, const PipeIn & in, const
     if (w.lane == 0) { hits[0] = kFlagEnd; hits_score[0] = 0; }
     best_chains(w, X, rec, n2, score_type);
     LNR_LAP(cnt, 4, tl);
-    if (w.lane == 0)
     {
-        int nch = traceback<u64>(X, rec, n2, ch_el, hits_score + 1, chain_off, 60, 1, 45, 50, in.stop_ratio);
+        const int nch = traceback_w<u64>(w, X, rec, n2, ch_el, hits_score + 1, chain_off, 60, 1, 45, 50, in.stop_ratio);
         for (int c = 0; c < nch; c++)
         {
-            for (int j = chain_off[c]; j < chain_off[c + 1]; j++) hits[1 + j] = hit2cord_dstr(ch_el[j]);
-            hits[chain_off[c + 1]] |= kFlagEnd;
+            for (int j = chain_off[c] + w.lane; j < chain_off[c + 1]; j += w.nl)
+                hits[1 + j] = hit2cord_dstr(ch_el[j]) | (j == chain_off[c + 1] - 1 ? kFlagEnd : 0ULL);
         }
         n_hits = 1 + chain_off[nch];
     }
-    n_hits = wbcast(w, n_hits, 0);
     wsync(w);
     LNR_LAP(cnt, 5, tl);
     return 0;
