@@ -78,6 +78,7 @@ int lnr_index_export_hindex(const lnr_index *, uint64_t * ysa, uint64_t ysa_cap,
  * order inside a bucket are bucket-local, so concatenating the shards' hs in shard order and rebasing each shard's dir
  * slice by the records of the shards before it gives exactly the index lnr_index_build produces. The exchange
  * (one all-gather of counts, hs slices and dir slices) is done by the caller over NCCL on the device buffers below. */
+/* (index_type 1 only; the HIndex shards through lnr_index_build_sharded below.) */
 int lnr_index_build_shard(lnr_ctx *, const lnr_genome *, int index_type, unsigned threads_sem, unsigned shard, unsigned n_shards,
                           lnr_index ** out);
 /* The same build with the exchange inside the library (lnr_index_build_sharded). One lnr_comm per rank wraps
@@ -90,7 +91,13 @@ int lnr_index_build_shard(lnr_ctx *, const lnr_genome *, int index_type, unsigne
  * range r, learns all ranks' record counts (one 8-byte all-gather),
  * builds its buckets directly inside its slice of the final hs / dir arrays, and one grouped exchange (in-place
  * ncclBroadcast of every rank's hs slice and dir slice at their displacements -- no padding, no staging copy) completes
- * the identical DIndex on every rank. index_type 1 only. */
+ * the identical DIndex on every rank.
+ * index_type 2 (HIndex, createHIndex index_util.cpp:1471): the same scheme on the 18-bit X axis of the 17-base shape --
+ * every rank counts the (head, body) pairs per X over the whole genome, derives the same n X ranges of equal pair count,
+ * sorts and assembles the blocks of its own range straight into its slice of the final ysa (a block is one X, so no
+ * block straddles a cut), one 16-byte all-gather of (pairs, blocks) gives the displacements, one grouped exchange of the
+ * ysa slices completes the array on every rank, and the directory is derived locally from the head words of the assembled
+ * ysa. The result equals lnr_index_build's for any number of ranks. */
 typedef struct lnr_comm lnr_comm;
 int lnr_nccl_unique_id(uint8_t id[128]);
 int lnr_comm_create(lnr_ctx *, const uint8_t id[128], int rank, int n_ranks, lnr_comm ** out);

@@ -64,9 +64,14 @@ __global__ void k_check_acgt(const u8 * __restrict__ g, const u64 * __restrict__
             if (g[off[c] + i] > 3) { atomicAdd(bad, 1u); return; }
 }
 
-// one thread per sample; emitted pairs are appended (any order: the sort fixes it)
+// one thread per sample; emitted pairs are appended (any order: the sort fixes it). Two forms share the evaluation:
+// xhist != null: count the emitted pairs per X (X < 2^18 for the 9-base minimizer of a 17-base shape), nothing is stored --
+// the sharded build cuts the X axis into ranges of equal pair count from it; xhist == null: store the pairs whose X lies in
+// [x_lo, x_hi) (the whole axis for the single-GPU build).
+static const u32 kXRangeH = 1u << 18;
 __global__ void __launch_bounds__(256) k_hidx_pairs(const u8 * __restrict__ g, const HChunk * __restrict__ chunks, u32 n_chunks, u64 n_samples,
-                                                    u64 * __restrict__ body, u32 * __restrict__ xkey, unsigned long long * n_pairs)
+                                                    u64 * __restrict__ body, u32 * __restrict__ xkey, unsigned long long * n_pairs,
+                                                    u32 x_lo, u32 x_hi, u32 * __restrict__ xhist)
 {
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     bool emit = false;
@@ -88,8 +93,11 @@ __global__ void __launch_bounds__(256) k_hidx_pairs(const u8 * __restrict__ g, c
             X = (m == ch.m_last_emit) ? ch.x_last : sv.X;
             b = (1ULL << 63) | (((u64)sv.Y << 41) + ((u64)ch.contig << 30) + (u64)k);
             if (sv.strand) b |= 1ULL << 40;
+            if (xhist) { atomicAdd(&xhist[X < kXRangeH ? X : kXRangeH - 1], 1u); emit = false; }
+            else emit = X >= x_lo && X < x_hi;
         }
     }
+    if (xhist) return;
     u32 m = __ballot_sync(0xffffffffu, emit);
     u64 base = 0;
     if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(n_pairs, (unsigned long long)__popc(m));
@@ -200,6 +208,43 @@ __global__ void __launch_bounds__(256) k_hidx_dir(const u64 * __restrict__ ysa, 
                     cnt++;
                     if (mode) hdir_insert(tab, mask, X + ((ysa[j] & ((1ULL << 61) - (1ULL << 41))) >> 1), (u32)j, 1);
                 }
+        }
+    }
+    if (!mode)
+    {
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_entries, (unsigned long long)cnt);
+    }
+}
+// The same directory entries derived from the assembled ysa alone (sharded build: the block starts of the other ranks'
+// slices are not on this rank): one thread per ysa word; a head word (bit 63 clear -- every body carries bit 63) gives its
+// block's X and length. n_words = pairs + blocks (the two terminators behind them are not looked at).
+__global__ void __launch_bounds__(256) k_hidx_dir_scan(const u64 * __restrict__ ysa, u64 n_words, int mode, unsigned long long * n_entries,
+                                                       HNode * tab, u64 mask)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 cnt = 0;
+    if (i < n_words)
+    {
+        const u64 head = ysa[i];
+        if (!(head >> 63))
+        {
+            const u64 ptr = head >> 40, X = head & ((1ULL << 40) - 1);
+            cnt = 1;
+            if (ptr < kBlockLimitH)
+            {
+                if (mode) hdir_insert(tab, mask, X, (u32)(i + 1), 1);
+            }
+            else
+            {
+                if (mode) hdir_insert(tab, mask, X, ~1u, 3);
+                for (u64 j = i + 1; j < i + ptr; j++)
+                    if (((ysa[j] ^ ysa[j - 1]) >> 41) & 0xfffff)
+                    {
+                        cnt++;
+                        if (mode) hdir_insert(tab, mask, X + ((ysa[j] & ((1ULL << 61) - (1ULL << 41))) >> 1), (u32)j, 1);
+                    }
+            }
         }
     }
     if (!mode)

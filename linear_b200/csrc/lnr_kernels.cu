@@ -263,10 +263,13 @@ static const int FT = 256;           // threads per CTA = cells per CTA
 static const int FE = FT - 2;        // entries per CTA
 
 // ---- table-driven cell for N-free interior cells ----------------------------------------------------------------
-// The 17 bases of a cell are fetched as 5 aligned words and packed to 2 bits each (Q: base i at bits 2(16-i)); the
-// reverse strand's cell is the pair-reversed complement of the forward 17 bases. A 256-entry shared table holds the
-// field increments of the three 2-mers inside every 4-base window, so a cell is 5 table adds + one 2-mer add.
-struct FeatTab { u64 lo3[256]; u32 hi3[256]; u64 lo2[16]; u32 hi2[16]; };
+// The kernel is bound by the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 84 % with 4-byte loads and a 4-base table),
+// so a cell costs as few wavefronts as possible: its 17 bases arrive as the TWO aligned 16-byte blocks that hold them
+// (feat_cell_issue; [q & ~15, +32) must be readable), are packed to 2 bits each (feat_cell_finish; Q: base i at bits
+// 2(16-i); a cell with an N takes the general evaluation), and a 1024-entry shared table holds the field increments of
+// the four 2-mers inside every 5-base window: a cell is 4 table adds. The reverse strand's cell is the pair-reversed
+// complement of the forward 17 bases.
+struct FeatTab { u64 lo[1024]; u32 hi[1024]; };
 __device__ __forceinline__ void feat_add(u32 id, u64 & lo, u32 & hi)
 {
     if (id < 10) lo += 1ULL << (6 * id);
@@ -274,29 +277,13 @@ __device__ __forceinline__ void feat_add(u32 id, u64 & lo, u32 & hi)
 }
 __device__ __forceinline__ void feat_tab_init(FeatTab & T)   // blockDim.x == 256, caller syncs
 {
-    u32 t = threadIdx.x, a = t >> 6, b = (t >> 4) & 3, c = (t >> 2) & 3, d = t & 3;
-    u64 lo = 0; u32 hi = 0;
-    feat_add(4 * a + b, lo, hi); feat_add(4 * b + c, lo, hi); feat_add(4 * c + d, lo, hi);
-    T.lo3[t] = lo; T.hi3[t] = hi;
-    if (t < 16) { lo = 0; hi = 0; feat_add(t, lo, hi); T.lo2[t] = lo; T.hi2[t] = hi; }
-}
-__device__ __forceinline__ bool load17_packed(const u8 * q, u64 & Q)   // needs [q & ~3, q + 20) readable; false on N
-{
-    const unsigned sh = ((unsigned)(uintptr_t)q & 3u) * 8u;
-    const u32 * pw = (const u32 *)((uintptr_t)q & ~(uintptr_t)3);
-    u32 w[5];
+    for (u32 t = threadIdx.x; t < 1024; t += FT)
+    {
+        u64 lo = 0; u32 hi = 0;
 #pragma unroll
-    for (int i = 0; i < 5; i++) w[i] = __ldg(pw + i);
-    u32 A[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) A[i] = __funnelshift_r(w[i], w[i + 1], sh);
-    const u32 b16 = (w[4] >> sh) & 0xffu;
-    if ((A[0] | A[1] | A[2] | A[3] | b16) & 0xfcfcfcfcu) return false;
-    u32 hi32 = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) hi32 = (hi32 << 8) | ((A[i] * 0x40100401u) >> 24);
-    Q = ((u64)hi32 << 2) | b16;
-    return true;
+        for (int k = 0; k < 4; k++) feat_add((t >> (2 * (3 - k))) & 15u, lo, hi);   // bases k, k+1 of the window (base 0 on top)
+        T.lo[t] = lo; T.hi[t] = hi;
+    }
 }
 __device__ __forceinline__ u64 rc34(u64 Q)
 {
@@ -305,38 +292,67 @@ __device__ __forceinline__ u64 rc34(u64 Q)
 }
 __device__ __forceinline__ void feat_cell_tab(const FeatTab & T, u64 Q, u64 & lo, u32 & hi)
 {
-    lo = T.lo2[Q & 15]; hi = T.hi2[Q & 15];
+    lo = 0; hi = 0;
 #pragma unroll
-    for (int g = 0; g < 5; g++)
+    for (int g = 0; g < 4; g++)
     {
-        u32 idx = (u32)(Q >> (2 * (13 - 3 * g))) & 0xffu;
-        lo += T.lo3[idx]; hi += T.hi3[idx];
+        const u32 idx = (u32)(Q >> (24 - 8 * g)) & 0x3ffu;      // bases 4g .. 4g+4
+        lo += T.lo[idx]; hi += T.hi[idx];
     }
 }
+// A cell in two steps, so that a thread can have the loads of several cells in flight before it needs the first word
+// (k_feat_reads: the forward and the reverse cell of the same tile index): issue = decide the path and start the two
+// 16-byte loads of the packed path; finish = pack, table adds -- or the general base-by-base evaluation (read ends, N).
+struct CellLoad { uint4 v0, v1; unsigned a; int mode; };   // a = byte offset of the cell in the 32 bytes; mode 0: no cell, 1: loaded, 2: general evaluation
 template <bool RC>
-__device__ __forceinline__ void feat_tile_reads(const u8 * buf0, const u8 * s, i64 L, u32 e0, u32 n_entries, F96 * out, u64 * s_lo,
-                                                u32 * s_hi, const FeatTab & T)
+__device__ __forceinline__ void feat_cell_issue(const u8 * buf0, const u8 * s, i64 L, u32 c, u32 n_entries, CellLoad & cl)
 {
-    u32 c = e0 + threadIdx.x;
-    u64 lo = 0; u32 hi = 0;
-    if (c < n_entries + 2)
+    cl.mode = 0; cl.a = 0;
+    cl.v0 = make_uint4(0, 0, 0, 0); cl.v1 = make_uint4(0, 0, 0, 0);
+    if (c >= n_entries + 2) return;
+    const i64 f0 = RC ? L - 17 - 16 * (i64)c : 16 * (i64)c;   // forward position of the cell's lowest base
+    const u8 * q = s + f0;
+    const uint4 * pv = (const uint4 *)((uintptr_t)q & ~(uintptr_t)15);
+    if (f0 >= 0 && f0 + 32 <= L && (const u8 *)pv >= buf0)    // the 32 bytes lie inside this read (and inside the caller's buffer)
     {
-        const i64 f0 = RC ? L - 17 - 16 * (i64)c : 16 * (i64)c;   // forward position of the cell's lowest base
-        u64 Q;
-        if (f0 >= 0 && f0 + 20 <= L && (const u8 *)((uintptr_t)(s + f0) & ~(uintptr_t)3) >= buf0 && load17_packed(s + f0, Q))
+        cl.mode = 1;
+        cl.a = (unsigned)(uintptr_t)q & 15u;
+        cl.v0 = __ldg(pv); cl.v1 = __ldg(pv + 1);
+    }
+    else cl.mode = 2;
+}
+template <bool RC>
+__device__ __forceinline__ void feat_cell_finish(const CellLoad & cl, const u8 * s, i64 L, u32 c, const FeatTab & T, u64 & lo, u32 & hi)
+{
+    lo = 0; hi = 0;
+    if (cl.mode == 0) return;
+    if (cl.mode == 1)
+    {
+        // the 5 words that hold bytes a .. a+16: skip a >> 2 whole words (two select levels), then funnel by the byte rest
+        const u32 W[8] = {cl.v0.x, cl.v0.y, cl.v0.z, cl.v0.w, cl.v1.x, cl.v1.y, cl.v1.z, cl.v1.w};
+        const bool s2 = (cl.a & 8u) != 0, s1 = (cl.a & 4u) != 0;
+        u32 V[6], U[5];
+#pragma unroll
+        for (int i = 0; i < 6; i++) V[i] = s2 ? W[i + 2] : W[i];
+#pragma unroll
+        for (int i = 0; i < 5; i++) U[i] = s1 ? V[i + 1] : V[i];
+        const unsigned sh = (cl.a & 3u) * 8u;
+        u32 A[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) A[i] = __funnelshift_r(U[i], U[i + 1], sh);
+        const u32 b16 = (U[4] >> sh) & 0xffu;
+        if (!((A[0] | A[1] | A[2] | A[3] | b16) & 0xfcfcfcfcu))
+        {
+            u32 hi32 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) hi32 = (hi32 << 8) | ((A[i] * 0x40100401u) >> 24);
+            const u64 Q = ((u64)hi32 << 2) | b16;
             feat_cell_tab(T, RC ? rc34(Q) : Q, lo, hi);
-        else if (RC) { GRcAcc acc = {s, L}; feat_cell(acc, 16 * (i64)c, lo, hi); }
-        else { GAcc acc = {s, L}; feat_cell(acc, 16 * (i64)c, lo, hi); }
+            return;
+        }
     }
-    s_lo[threadIdx.x] = lo;
-    s_hi[threadIdx.x] = hi;
-    __syncthreads();
-    if (threadIdx.x < FE && c < n_entries)
-    {
-        F96 f = feat_entry(lo + s_lo[threadIdx.x + 1] + s_lo[threadIdx.x + 2], hi + s_hi[threadIdx.x + 1] + s_hi[threadIdx.x + 2]);
-        i32 * o = (i32 *)(out + c);
-        o[0] = f.v[0]; o[1] = f.v[1]; o[2] = f.v[2];
-    }
+    if (RC) { GRcAcc acc = {s, L}; feat_cell(acc, 16 * (i64)c, lo, hi); }
+    else { GAcc acc = {s, L}; feat_cell(acc, 16 * (i64)c, lo, hi); }
 }
 
 // genome: aligned 16-byte loads for interior cells
@@ -399,30 +415,56 @@ __global__ void k_feat_tile_reads(const u32 * __restrict__ ftile, u32 n_reads, u
     if (r >= n_reads) return;
     for (u32 t = ftile[r]; t < ftile[r + 1]; t++) tile_read[t] = r;
 }
-// persistent CTAs over the tiles: the 2-mer table is built once per CTA, not once per 256 cells
+// persistent CTAs over the tiles: the 2-mer table is built once per CTA, not once per 256 cells. A read's tiles come as
+// tps forward tiles followed by tps reverse tiles (n_tiles is even, every read's range starts at an even tile): one loop
+// iteration takes the forward and the reverse tile of the same index together -- both cells' loads are issued before either
+// is used. LNR_FEAT_BUFS = 2 exchanges the cell sums through two alternating shared buffers, so that an iteration has ONE
+// barrier (a thread can be at most one iteration ahead of the slowest, and then writes the other buffer).
 __global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
                                                    const u64 * __restrict__ foff, const u32 * __restrict__ ftile,
                                                    const u32 * __restrict__ tile_read, u32 n_tiles, F96 * __restrict__ out)
 {
-    __shared__ u64 s_lo[FT];
-    __shared__ u32 s_hi[FT];
+#ifndef LNR_FEAT_BUFS
+#define LNR_FEAT_BUFS 1     // 2: alternating buffers, one barrier per iteration -- measured equal (1.57 vs 1.60 ms, call 29), 6 KB more
+#endif
+    __shared__ u64 s_lo[LNR_FEAT_BUFS][2][FT];
+    __shared__ u32 s_hi[LNR_FEAT_BUFS][2][FT];
     __shared__ FeatTab T;
     feat_tab_init(T);
     __syncthreads();
-    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    const u32 n_pairs = n_tiles >> 1;
+    u32 buf = 0;
+    for (u32 pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, buf ^= (u32)(LNR_FEAT_BUFS - 1))
     {
-        u32 r = tile_read[tile];
-        u64 L = read_off[r + 1] - read_off[r];
-        u32 nf = feat_count_read(L);
-        u32 tps = (nf + FE - 1) / FE;               // tiles per strand
-        u32 t = tile - ftile[r];
-        u32 strand = t >= tps ? 1u : 0u;
-        u32 e0 = (t - strand * tps) * FE;
-        F96 * o = out + foff[r] + (u64)strand * nf;
+        const u32 r = tile_read[2 * pair];
+        const u64 L = read_off[r + 1] - read_off[r];
+        const u32 nf = feat_count_read(L);
+        const u32 e0 = (pair - (ftile[r] >> 1)) * FE;
+        const u32 c = e0 + threadIdx.x;
+        F96 * o = out + foff[r];
         const u8 * s = bases + read_off[r];
-        if (!strand) feat_tile_reads<false>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
-        else feat_tile_reads<true>(bases, s, (i64)L, e0, nf, o, s_lo, s_hi, T);
-        __syncthreads();                            // s_lo / s_hi are reused by the next tile
+        CellLoad cf, cr;
+        feat_cell_issue<false>(bases, s, (i64)L, c, nf, cf);
+        feat_cell_issue<true>(bases, s, (i64)L, c, nf, cr);
+        u64 lo0, lo1; u32 hi0, hi1;
+        feat_cell_finish<false>(cf, s, (i64)L, c, T, lo0, hi0);
+        feat_cell_finish<true>(cr, s, (i64)L, c, T, lo1, hi1);
+        u64 (* bl)[FT] = s_lo[buf]; u32 (* bh)[FT] = s_hi[buf];
+        bl[0][threadIdx.x] = lo0; bh[0][threadIdx.x] = hi0;
+        bl[1][threadIdx.x] = lo1; bh[1][threadIdx.x] = hi1;
+        __syncthreads();
+        if (threadIdx.x < FE && c < nf)
+        {
+            F96 f = feat_entry(lo0 + bl[0][threadIdx.x + 1] + bl[0][threadIdx.x + 2], hi0 + bh[0][threadIdx.x + 1] + bh[0][threadIdx.x + 2]);
+            i32 * w = (i32 *)(o + c);
+            w[0] = f.v[0]; w[1] = f.v[1]; w[2] = f.v[2];
+            f = feat_entry(lo1 + bl[1][threadIdx.x + 1] + bl[1][threadIdx.x + 2], hi1 + bh[1][threadIdx.x + 1] + bh[1][threadIdx.x + 2]);
+            w = (i32 *)(o + nf + c);
+            w[0] = f.v[0]; w[1] = f.v[1]; w[2] = f.v[2];
+        }
+#if LNR_FEAT_BUFS == 1
+        __syncthreads();
+#endif
     }
 }
 
@@ -1900,11 +1942,12 @@ __global__ void __launch_bounds__(128, LNR_BLOCKS_MIN_CTAS) k_hits_blocks(MapArg
 
 // ---- stage 2: window extension (path_dst_2 + extendWindow), one warp per read on a regular grid; reads are taken in
 // size order so that neighbouring warps have similar trip counts.
-#ifdef LNR_EXTEND_MIN_CTAS
-#define LNR_EXTEND_BOUNDS __launch_bounds__(128, LNR_EXTEND_MIN_CTAS)
-#else
-#define LNR_EXTEND_BOUNDS __launch_bounds__(128)
+// 12 CTAs (48 warps) per SM: the walk is a serial chain of window steps, more resident warps hide it better than more
+// registers do (64 regs / 8 CTAs: 5.10 ms per 65 536 reads; 40 regs / 12 CTAs: 4.82; 32 regs / 16 CTAs: 5.01 -- call 28)
+#ifndef LNR_EXTEND_MIN_CTAS
+#define LNR_EXTEND_MIN_CTAS 12
 #endif
+#define LNR_EXTEND_BOUNDS __launch_bounds__(128, LNR_EXTEND_MIN_CTAS)
 __global__ void LNR_EXTEND_BOUNDS k_map_extend(MapArgs a, const u32 * __restrict__ read_list, u32 n_list, int remap_pass, int group)
 {
     // the lanes of a warp cooperate on one read: they share the 18 script distances of a window step (sub-warp groups
@@ -2182,162 +2225,6 @@ static int device_scan(lnr_ctx * ctx, u32 * d_in, u64 n, u32 cap, OutT * d_out, 
     return LNR_OK;
 }
 
-
-// ---- HIndex build (host orchestration) -------------------------------------------------------------------------------
-static int hindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned T, lnr_index ** out)
-{
-    std::vector<HChunk> chunks;
-    u64 n_samples = 0;
-    for (uint32_t ci = 0; ci < g->n_contigs; ci++)
-    {
-        u64 len = g->len[ci];
-        if (len < (u64)kSpanH + T) continue;
-        u64 n = len - kSpanH + 1, q = n / T, r = n - q * T;
-        for (unsigned t = 0; t < T; t++)   // index_util.cpp:742-760
-        {
-            HChunk ch;
-            memset(&ch, 0, sizeof ch);
-            ch.base_off = g->off[ci]; ch.len = (i64)len; ch.contig = ci;
-            if (t < r) { ch.csize = (i64)q + 1; ch.start = (i64)((q + 1) * t); }
-            else { ch.csize = (i64)q; ch.start = (i64)(len + 1 - kSpanH - q * (T - t)); }
-            ch.k_first = (ch.start + kStepH - 1) / kStepH * kStepH;
-            i64 k_end = ch.start + ch.csize;
-            ch.n_samples = ch.k_first < k_end ? (k_end - ch.k_first + kStepH - 1) / kStepH : 0;
-            if (ch.csize <= 0) continue;
-            ch.sample0 = n_samples;
-            n_samples += (u64)ch.n_samples;
-            chunks.push_back(ch);
-        }
-    }
-    if (!n_samples) return fail(ctx, LNR_E_UNSUPPORTED, "genome too small for the HIndex");
-    lnr_index * ix = new lnr_index();
-    ix->ctx = ctx; ix->index_type = 2; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = 0;
-    HChunk * d_chunks = nullptr; u64 * d_body[2] = {nullptr, nullptr}; u32 * d_x[2] = {nullptr, nullptr};
-    u32 * d_hist = nullptr; u64 * d_offs = nullptr; u64 * d_small = nullptr; u32 * d_flag = nullptr; u64 * d_bid = nullptr; u64 * d_starts = nullptr;
-    u64 * d_goff = nullptr; u64 * d_glen = nullptr;
-    auto cleanup = [&]() {
-        for (void * p : {(void *)d_chunks, (void *)d_body[0], (void *)d_body[1], (void *)d_x[0], (void *)d_x[1], (void *)d_hist, (void *)d_offs,
-                         (void *)d_small, (void *)d_flag, (void *)d_bid, (void *)d_starts, (void *)d_goff, (void *)d_glen})
-            if (p) cudaFree(p);
-    };
-#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); lnr_index_destroy(ix); return LNR_E_CUDA; } } while (0)
-    u32 n_chunks = (u32)chunks.size();
-    CKH(cudaMalloc(&d_small, 64 * sizeof(u64)));
-    CKH(cudaMemsetAsync(d_small, 0, 64 * sizeof(u64), ctx->stream));
-    // ACGT only
-    CKH(cudaMalloc(&d_goff, g->n_contigs * sizeof(u64)));
-    CKH(cudaMalloc(&d_glen, g->n_contigs * sizeof(u64)));
-    CKH(cudaMemcpyAsync(d_goff, g->off.data(), g->n_contigs * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    CKH(cudaMemcpyAsync(d_glen, g->len.data(), g->n_contigs * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    {
-        LaunchScope ls(ctx, "k_check_acgt");
-        k_check_acgt<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(g->d_bases, d_goff, d_glen, g->n_contigs, (u32 *)(d_small + 8));
-    }
-    CKH(cudaMalloc(&d_chunks, chunks.size() * sizeof(HChunk)));
-    CKH(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(HChunk), cudaMemcpyHostToDevice, ctx->stream));
-    for (int i = 0; i < 2; i++) { CKH(cudaMalloc(&d_body[i], (size_t)(n_samples + 8) * sizeof(u64))); CKH(cudaMalloc(&d_x[i], (size_t)(n_samples + 8) * sizeof(u32))); }
-    {
-        LaunchScope ls(ctx, "k_hidx_prep");
-        k_hidx_prep<<<(n_chunks + 63) / 64, 64, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks);
-    }
-    {
-        LaunchScope ls(ctx, "k_hidx_pairs");
-        k_hidx_pairs<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks, n_samples, d_body[0], d_x[0],
-                                                                              (unsigned long long *)d_small);
-    }
-    CKH(cudaGetLastError());
-    u64 h_small[16];
-    CKH(cudaMemcpyAsync(h_small, d_small, sizeof h_small, cudaMemcpyDeviceToHost, ctx->stream));
-    CKH(cudaStreamSynchronize(ctx->stream));
-    const u64 n = h_small[0];
-    if (((u32 *)(h_small + 8))[0]) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_UNSUPPORTED, "HIndex (-i 2): genomes containing N are not supported"); }
-    // ---- sort: body descending (LSD over its varying bytes), then X ascending
-    u64 init[4] = {0, ~0ULL, 0, ~0ULL};
-    CKH(cudaMemcpyAsync(d_small + 16, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-    {
-        LaunchScope ls(ctx, "k_rs_masks");
-        k_rs_masks<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(d_body[0], d_x[0], n, d_small + 16);
-    }
-    u64 masks[4];
-    CKH(cudaMemcpyAsync(masks, d_small + 16, sizeof masks, cudaMemcpyDeviceToHost, ctx->stream));
-    CKH(cudaStreamSynchronize(ctx->stream));
-    const u64 vary_body = masks[0] ^ masks[1];
-    const u32 vary_x = (u32)(masks[2] ^ masks[3]);
-    const u32 n_tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
-    CKH(cudaMalloc(&d_hist, (size_t)256 * n_tiles * sizeof(u32) + 64));
-    CKH(cudaMalloc(&d_offs, ((size_t)256 * n_tiles + STILE) * sizeof(u64)));
-    int cur = 0;
-    for (int pass = 0; pass < 11; pass++)
-    {
-        RsDigit dg;
-        if (pass < 8) { dg.from_aux = 0; dg.shift = 8 * pass; dg.xor_mask = ~0ULL; if (((vary_body >> (8 * pass)) & 255) == 0) continue; }
-        else { dg.from_aux = 1; dg.shift = 8 * (pass - 8); dg.xor_mask = 0; if (((vary_x >> (8 * (pass - 8))) & 255) == 0) continue; }
-        {
-            LaunchScope ls(ctx, "k_rs_hist");
-            k_rs_hist<<<n_tiles, RS_T, 0, ctx->stream>>>(d_body[cur], d_x[cur], n, dg, d_hist, n_tiles);
-        }
-        int rc = device_scan<u64>(ctx, d_hist, (u64)256 * n_tiles, 0, d_offs, d_small + 24, "k_scan_radix");
-        if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
-        {
-            LaunchScope ls(ctx, "k_rs_scatter");
-            k_rs_scatter<<<n_tiles, RS_T, 0, ctx->stream>>>(d_body[cur], d_x[cur], n, dg, d_offs, n_tiles, d_body[cur ^ 1], d_x[cur ^ 1]);
-        }
-        cur ^= 1;
-    }
-    CKH(cudaGetLastError());
-    // ---- blocks
-    CKH(cudaMalloc(&d_flag, (size_t)(n + STILE + 8) * sizeof(u32)));
-    CKH(cudaMalloc(&d_bid, (size_t)(n + STILE + 8) * sizeof(u64)));
-    {
-        LaunchScope ls(ctx, "k_hidx_flags");
-        k_hidx_flags<<<(u32)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_x[cur], n, d_flag);
-    }
-    {
-        int rc = device_scan<u64>(ctx, d_flag, n + 1, 0, d_bid, d_small + 24, "k_scan_blocks");
-        if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
-    }
-    u64 n_blocks = 0;
-    CKH(cudaMemcpyAsync(&n_blocks, d_small + 24, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CKH(cudaStreamSynchronize(ctx->stream));
-    if (n - n_blocks <= 2) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_UNSUPPORTED, "genome too small for the HIndex (countMove <= 2, index_util.cpp:1333)"); }
-    CKH(cudaMalloc(&d_starts, (size_t)(n_blocks + 2) * sizeof(u64)));
-    ix->n_ysa = n + n_blocks + 2;
-    ix->empty_dir = n + n_blocks;
-    CKH(cudaMalloc(&ix->d_ysa, (size_t)(ix->n_ysa + 8) * sizeof(u64)));
-    CKH(cudaMemsetAsync(ix->d_ysa + n + n_blocks, 0, 10 * sizeof(u64), ctx->stream));
-    {
-        LaunchScope ls(ctx, "k_hidx_starts");
-        k_hidx_starts<<<(u32)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_flag, d_bid, n, d_starts);
-    }
-    {
-        LaunchScope ls(ctx, "k_hidx_write");
-        k_hidx_write<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(d_body[cur], d_x[cur], d_flag, d_bid, d_starts, n, ix->d_ysa);
-    }
-    // ---- directory
-    CKH(cudaMemsetAsync(d_small + 32, 0, sizeof(u64), ctx->stream));
-    {
-        LaunchScope ls(ctx, "k_hidx_dir_count");
-        k_hidx_dir<<<(u32)((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, d_starts, n_blocks, 0, (unsigned long long *)(d_small + 32), nullptr, 0);
-    }
-    u64 n_ent = 0;
-    CKH(cudaMemcpyAsync(&n_ent, d_small + 32, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CKH(cudaStreamSynchronize(ctx->stream));
-    u64 tl = 1;
-    while ((float)tl < (float)n_ent * 1.6f) tl <<= 1;   // XString::_fullSize index_util.cpp:221, alpha 1.6
-    ix->tab_len = tl; ix->n_dir_entries = n_ent;
-    CKH(cudaMalloc(&ix->d_tab, (size_t)tl * sizeof(HNode)));
-    CKH(cudaMemsetAsync(ix->d_tab, 0, (size_t)tl * sizeof(HNode), ctx->stream));
-    {
-        LaunchScope ls(ctx, "k_hidx_dir_insert");
-        k_hidx_dir<<<(u32)((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, d_starts, n_blocks, 1, nullptr, ix->d_tab, tl - 1);
-    }
-    CKH(cudaGetLastError());
-    CKH(cudaStreamSynchronize(ctx->stream));
-    cleanup();
-#undef CKH
-    *out = ix;
-    return LNR_OK;
-}
 
 // =====================================================================================================
 // C ABI
@@ -2706,11 +2593,13 @@ __global__ void k_idx_rebase(i32 * __restrict__ dir, u32 x0, u32 n, i32 base)
 
 struct ShardPlan { lnr_comm * comm; };   // non-null: build one minimizer range and assemble over NCCL
 static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_comm * comm, lnr_index ** out);
+static int hindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned T, lnr_comm * comm, lnr_index ** out);
 
 int lnr_index_build_sharded(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, lnr_comm * comm, lnr_index ** out)
 {
     if (!ctx || !g || !comm || !out || threads_sem == 0) return LNR_E_ARG;
-    if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "the sharded build is implemented for index_type 1 (DIndex)");
+    if (index_type == 2) return hindex_build(ctx, g, threads_sem, comm, out);
+    if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "index_type must be 1 (DIndex, -i 1) or 2 (HIndex, -i 2)");
     if (((1u << kDirBits) % (u32)comm->n_ranks) != 0) return fail(ctx, LNR_E_ARG, "the number of ranks must divide 2^26");
     const u32 per = (1u << kDirBits) / (u32)comm->n_ranks;
     return dindex_build(ctx, g, threads_sem, (u32)comm->rank * per, ((u32)comm->rank + 1) * per, comm, out);
@@ -2909,12 +2798,265 @@ static int index_build_range(lnr_ctx * ctx, const lnr_genome * g, int index_type
     if (!ctx || !g || !out || threads_sem == 0) return LNR_E_ARG;
     if (index_type == 2)
     {
-        if (x_lo != 0 || x_hi != (1u << kDirBits)) return fail(ctx, LNR_E_UNSUPPORTED, "sharded build is implemented for index_type 1 only");
-        return hindex_build(ctx, g, threads_sem, out);
+        if (x_lo != 0 || x_hi != (1u << kDirBits)) return fail(ctx, LNR_E_UNSUPPORTED, "lnr_index_build_shard (caller-side exchange) is DIndex only; use lnr_index_build_sharded for -i 2");
+        return hindex_build(ctx, g, threads_sem, nullptr, out);
     }
     if (index_type != 1) return fail(ctx, LNR_E_UNSUPPORTED, "index_type must be 1 (DIndex, -i 1) or 2 (HIndex, -i 2)");
     return dindex_build(ctx, g, threads_sem, x_lo, x_hi, nullptr, out);
 }
+// ---- HIndex build (host orchestration) -------------------------------------------------------------------------------
+// comm != nullptr: the X axis (18 bits) is cut into n_ranks ranges of equal pair count -- every rank derives the same cuts from
+// the same per-X histogram of the whole genome --, a rank sorts and assembles only the pairs of its range, straight into its slice
+// of the final ysa (blocks never straddle a cut: a block is one X), one all-gather of (pairs, blocks) tells everybody the
+// displacements, one group of point-to-point transfers completes the ysa on every rank, and the directory is derived locally
+// from the assembled ysa. The result does not depend on the number of ranks.
+static int hindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned T, lnr_comm * comm, lnr_index ** out)
+{
+    cudaSetDevice(ctx->device);
+    std::vector<HChunk> chunks;
+    u64 n_samples = 0;
+    for (uint32_t ci = 0; ci < g->n_contigs; ci++)
+    {
+        u64 len = g->len[ci];
+        if (len < (u64)kSpanH + T) continue;
+        u64 n = len - kSpanH + 1, q = n / T, r = n - q * T;
+        for (unsigned t = 0; t < T; t++)   // index_util.cpp:742-760
+        {
+            HChunk ch;
+            memset(&ch, 0, sizeof ch);
+            ch.base_off = g->off[ci]; ch.len = (i64)len; ch.contig = ci;
+            if (t < r) { ch.csize = (i64)q + 1; ch.start = (i64)((q + 1) * t); }
+            else { ch.csize = (i64)q; ch.start = (i64)(len + 1 - kSpanH - q * (T - t)); }
+            ch.k_first = (ch.start + kStepH - 1) / kStepH * kStepH;
+            i64 k_end = ch.start + ch.csize;
+            ch.n_samples = ch.k_first < k_end ? (k_end - ch.k_first + kStepH - 1) / kStepH : 0;
+            if (ch.csize <= 0) continue;
+            ch.sample0 = n_samples;
+            n_samples += (u64)ch.n_samples;
+            chunks.push_back(ch);
+        }
+    }
+    if (!n_samples) return fail(ctx, LNR_E_UNSUPPORTED, "genome too small for the HIndex");
+    lnr_index * ix = new lnr_index();
+    ix->ctx = ctx; ix->index_type = 2; ix->d_dir = nullptr; ix->d_hs = nullptr; ix->n_hs = 0;
+    HChunk * d_chunks = nullptr; u64 * d_body[2] = {nullptr, nullptr}; u32 * d_x[2] = {nullptr, nullptr};
+    u32 * d_hist = nullptr; u64 * d_offs = nullptr; u64 * d_small = nullptr; u32 * d_flag = nullptr; u64 * d_bid = nullptr; u64 * d_starts = nullptr;
+    u64 * d_goff = nullptr; u64 * d_glen = nullptr; u32 * d_xhist = nullptr;
+    auto cleanup = [&]() {
+        for (void * p : {(void *)d_chunks, (void *)d_body[0], (void *)d_body[1], (void *)d_x[0], (void *)d_x[1], (void *)d_hist, (void *)d_offs,
+                         (void *)d_small, (void *)d_flag, (void *)d_bid, (void *)d_starts, (void *)d_goff, (void *)d_glen, (void *)d_xhist})
+            if (p) cudaFree(p);
+    };
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); lnr_index_destroy(ix); return LNR_E_CUDA; } } while (0)
+    u32 n_chunks = (u32)chunks.size();
+    CKH(cudaMalloc(&d_small, 64 * sizeof(u64)));
+    CKH(cudaMemsetAsync(d_small, 0, 64 * sizeof(u64), ctx->stream));
+    // ACGT only
+    CKH(cudaMalloc(&d_goff, g->n_contigs * sizeof(u64)));
+    CKH(cudaMalloc(&d_glen, g->n_contigs * sizeof(u64)));
+    CKH(cudaMemcpyAsync(d_goff, g->off.data(), g->n_contigs * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaMemcpyAsync(d_glen, g->len.data(), g->n_contigs * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_check_acgt");
+        k_check_acgt<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(g->d_bases, d_goff, d_glen, g->n_contigs, (u32 *)(d_small + 8));
+    }
+    CKH(cudaMalloc(&d_chunks, chunks.size() * sizeof(HChunk)));
+    CKH(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(HChunk), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_hidx_prep");
+        k_hidx_prep<<<(n_chunks + 63) / 64, 64, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks);
+    }
+    u32 x_lo = 0, x_hi = kXRangeH;
+    u64 pair_cap = n_samples;
+    if (comm)
+    {
+        // pairs per X over the whole genome -> this rank's range [x_lo, x_hi) and its pair count (the arrays are sized by it)
+        CKH(cudaMalloc(&d_xhist, (size_t)kXRangeH * sizeof(u32)));
+        CKH(cudaMemsetAsync(d_xhist, 0, (size_t)kXRangeH * sizeof(u32), ctx->stream));
+        {
+            LaunchScope ls(ctx, "k_hidx_xhist");
+            k_hidx_pairs<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks, n_samples, nullptr, nullptr, nullptr,
+                                                                                  0u, kXRangeH, d_xhist);
+        }
+        CKH(cudaGetLastError());
+        std::vector<u32> xh(kXRangeH);
+        CKH(cudaMemcpyAsync(xh.data(), d_xhist, (size_t)kXRangeH * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CKH(cudaStreamSynchronize(ctx->stream));
+        u64 all = 0;
+        for (u32 x = 0; x < kXRangeH; x++) all += xh[x];
+        // cut r = the first X at which the running count reaches r/n_ranks of all pairs
+        std::vector<u32> cut((size_t)comm->n_ranks + 1, kXRangeH);
+        cut[0] = 0;
+        {
+            u64 run = 0; int r = 1;
+            for (u32 x = 0; x < kXRangeH && r < comm->n_ranks; x++)
+            {
+                while (r < comm->n_ranks && run >= (all * (u64)r + (u64)comm->n_ranks - 1) / (u64)comm->n_ranks) cut[(size_t)r++] = x;
+                run += xh[x];
+            }
+        }
+        x_lo = cut[(size_t)comm->rank]; x_hi = cut[(size_t)comm->rank + 1];
+        pair_cap = 0;
+        for (u32 x = x_lo; x < x_hi; x++) pair_cap += xh[x];
+    }
+    for (int i = 0; i < 2; i++) { CKH(cudaMalloc(&d_body[i], (size_t)(pair_cap + 8) * sizeof(u64))); CKH(cudaMalloc(&d_x[i], (size_t)(pair_cap + 8) * sizeof(u32))); }
+    {
+        LaunchScope ls(ctx, "k_hidx_pairs");
+        k_hidx_pairs<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(g->d_bases, d_chunks, n_chunks, n_samples, d_body[0], d_x[0],
+                                                                              (unsigned long long *)d_small, x_lo, x_hi, nullptr);
+    }
+    CKH(cudaGetLastError());
+    u64 h_small[16];
+    CKH(cudaMemcpyAsync(h_small, d_small, sizeof h_small, cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    const u64 n = h_small[0];                  // pairs of this build (of this rank's range)
+    if (((u32 *)(h_small + 8))[0]) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_UNSUPPORTED, "HIndex (-i 2): genomes containing N are not supported"); }
+    if (n > pair_cap) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "HIndex build: pair count exceeds the histogram's"); }
+    // ---- sort: body descending (LSD over its varying bytes), then X ascending
+    u64 init[4] = {0, ~0ULL, 0, ~0ULL};
+    CKH(cudaMemcpyAsync(d_small + 16, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_rs_masks");
+        k_rs_masks<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(d_body[0], d_x[0], n, d_small + 16);
+    }
+    u64 masks[4];
+    CKH(cudaMemcpyAsync(masks, d_small + 16, sizeof masks, cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    const u64 vary_body = masks[0] ^ masks[1];
+    const u32 vary_x = (u32)(masks[2] ^ masks[3]);
+    const u32 n_tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+    CKH(cudaMalloc(&d_hist, (size_t)256 * n_tiles * sizeof(u32) + 64));
+    CKH(cudaMalloc(&d_offs, ((size_t)256 * n_tiles + STILE) * sizeof(u64)));
+    int cur = 0;
+    for (int pass = 0; pass < 11 && n; pass++)     // n == 0: a rank whose range is empty (tiny genome, many ranks)
+    {
+        RsDigit dg;
+        if (pass < 8) { dg.from_aux = 0; dg.shift = 8 * pass; dg.xor_mask = ~0ULL; if (((vary_body >> (8 * pass)) & 255) == 0) continue; }
+        else { dg.from_aux = 1; dg.shift = 8 * (pass - 8); dg.xor_mask = 0; if (((vary_x >> (8 * (pass - 8))) & 255) == 0) continue; }
+        {
+            LaunchScope ls(ctx, "k_rs_hist");
+            k_rs_hist<<<n_tiles, RS_T, 0, ctx->stream>>>(d_body[cur], d_x[cur], n, dg, d_hist, n_tiles);
+        }
+        int rc = device_scan<u64>(ctx, d_hist, (u64)256 * n_tiles, 0, d_offs, d_small + 24, "k_scan_radix");
+        if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
+        {
+            LaunchScope ls(ctx, "k_rs_scatter");
+            k_rs_scatter<<<n_tiles, RS_T, 0, ctx->stream>>>(d_body[cur], d_x[cur], n, dg, d_offs, n_tiles, d_body[cur ^ 1], d_x[cur ^ 1]);
+        }
+        cur ^= 1;
+    }
+    CKH(cudaGetLastError());
+    // ---- blocks
+    CKH(cudaMalloc(&d_flag, (size_t)(n + STILE + 8) * sizeof(u32)));
+    CKH(cudaMalloc(&d_bid, (size_t)(n + STILE + 8) * sizeof(u64)));
+    {
+        LaunchScope ls(ctx, "k_hidx_flags");
+        k_hidx_flags<<<(u32)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_x[cur], n, d_flag);
+    }
+    {
+        int rc = device_scan<u64>(ctx, d_flag, n + 1, 0, d_bid, d_small + 24, "k_scan_blocks");
+        if (rc) { cleanup(); lnr_index_destroy(ix); return rc; }
+    }
+    u64 n_blocks = 0;
+    CKH(cudaMemcpyAsync(&n_blocks, d_small + 24, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    // ---- sharded: (pairs, blocks) of every rank -> totals and the displacement of this rank's slice in the final ysa
+    u64 n_all = n, nb_all = n_blocks, disp = 0;
+    std::vector<u64> rank_words;                   // ysa words (pairs + blocks) of every rank's slice
+    if (comm)
+    {
+        NcclApi & api = nccl_api();
+        if (comm->n_ranks > 64) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_ARG, "more than 64 ranks"); }
+        const u64 mine[2] = {n, n_blocks};
+        std::vector<u64> cnts(2 * (size_t)comm->n_ranks);
+        u64 * d_mine = d_small + 40; u64 * d_cnts = (u64 *)d_hist;        // the radix histogram is free by now (>= 64 bytes; see below)
+        if (2 * (size_t)comm->n_ranks * sizeof(u64) > (size_t)256 * n_tiles * sizeof(u32) + 64)
+        {
+            cudaFree(d_hist); d_hist = nullptr;
+            CKH(cudaMalloc(&d_hist, 2 * (size_t)comm->n_ranks * sizeof(u64)));
+            d_cnts = (u64 *)d_hist;
+        }
+        CKH(cudaMemcpyAsync(d_mine, mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+        int nrc = api.AllGather(d_mine, d_cnts, 2, kNcclUint64, comm->comm, ctx->stream);
+        cudaError_t ce = cudaMemcpyAsync(cnts.data(), d_cnts, cnts.size() * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (nrc != 0 || ce != cudaSuccess) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "all-gather of the shard sizes failed"); }
+        n_all = 0; nb_all = 0;
+        for (int r = 0; r < comm->n_ranks; r++)
+        {
+            if (r == comm->rank) disp = n_all + nb_all;
+            n_all += cnts[2 * (size_t)r]; nb_all += cnts[2 * (size_t)r + 1];
+            rank_words.push_back(cnts[2 * (size_t)r] + cnts[2 * (size_t)r + 1]);
+        }
+    }
+    if (n_all - nb_all <= 2) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_UNSUPPORTED, "genome too small for the HIndex (countMove <= 2, index_util.cpp:1333)"); }
+    if (n_all + nb_all + 2 >= (1ULL << 32)) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_LIMIT, "ysa exceeds the 32-bit directory values (index_util.h: XNode val2)"); }
+    CKH(cudaMalloc(&d_starts, (size_t)(n_blocks + 2) * sizeof(u64)));
+    ix->n_ysa = n_all + nb_all + 2;
+    ix->empty_dir = n_all + nb_all;
+    CKH(cudaMalloc(&ix->d_ysa, (size_t)(ix->n_ysa + 8) * sizeof(u64)));
+    CKH(cudaMemsetAsync(ix->d_ysa + n_all + nb_all, 0, 10 * sizeof(u64), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_hidx_starts");
+        k_hidx_starts<<<(u32)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_flag, d_bid, n, d_starts);
+    }
+    if (n)
+    {
+        LaunchScope ls(ctx, "k_hidx_write");
+        k_hidx_write<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(d_body[cur], d_x[cur], d_flag, d_bid, d_starts, n, ix->d_ysa + disp);
+    }
+    CKH(cudaGetLastError());
+    if (comm && comm->n_ranks > 1)
+    {
+        // the one exchange step: every rank's slice of ysa, in place at its displacement
+        NcclApi & api = nccl_api();
+        int nrc = 0;
+        {
+            LaunchScope ls(ctx, "nccl_exchange", 0);
+            nrc |= api.GroupStart();
+            u64 d = 0;
+            for (int r = 0; r < comm->n_ranks; r++)
+            {
+                if (r != comm->rank)
+                {
+                    if (rank_words[(size_t)r]) nrc |= api.Recv(ix->d_ysa + d, (size_t)rank_words[(size_t)r], kNcclUint64, r, comm->comm, ctx->stream);
+                    if (n + n_blocks) nrc |= api.Send(ix->d_ysa + disp, (size_t)(n + n_blocks), kNcclUint64, r, comm->comm, ctx->stream);
+                }
+                d += rank_words[(size_t)r];
+            }
+            nrc |= api.GroupEnd();
+        }
+        if (nrc != 0) { cleanup(); lnr_index_destroy(ix); return fail(ctx, LNR_E_CUDA, "NCCL exchange of the ysa slices failed"); }
+    }
+    // ---- directory: from this build's block starts, or (sharded) from the head words of the assembled ysa
+    const u64 n_words = n_all + nb_all;
+    CKH(cudaMemsetAsync(d_small + 32, 0, sizeof(u64), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_hidx_dir_count");
+        if (comm) k_hidx_dir_scan<<<(u32)((n_words + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, n_words, 0, (unsigned long long *)(d_small + 32), nullptr, 0);
+        else k_hidx_dir<<<(u32)((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, d_starts, n_blocks, 0, (unsigned long long *)(d_small + 32), nullptr, 0);
+    }
+    u64 n_ent = 0;
+    CKH(cudaMemcpyAsync(&n_ent, d_small + 32, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    u64 tl = 1;
+    while ((float)tl < (float)n_ent * 1.6f) tl <<= 1;   // XString::_fullSize index_util.cpp:221, alpha 1.6
+    ix->tab_len = tl; ix->n_dir_entries = n_ent;
+    CKH(cudaMalloc(&ix->d_tab, (size_t)tl * sizeof(HNode)));
+    CKH(cudaMemsetAsync(ix->d_tab, 0, (size_t)tl * sizeof(HNode), ctx->stream));
+    {
+        LaunchScope ls(ctx, "k_hidx_dir_insert");
+        if (comm) k_hidx_dir_scan<<<(u32)((n_words + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, n_words, 1, nullptr, ix->d_tab, tl - 1);
+        else k_hidx_dir<<<(u32)((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(ix->d_ysa, d_starts, n_blocks, 1, nullptr, ix->d_tab, tl - 1);
+    }
+    CKH(cudaGetLastError());
+    CKH(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+#undef CKH
+    *out = ix;
+    return LNR_OK;
+}
+
 // comm == nullptr: the buckets [x_lo, x_hi) only (whole index, or one shard for a caller-side exchange).
 // comm != nullptr: this rank builds [x_lo, x_hi) straight into its slice of the final arrays, then one grouped exchange
 // (every rank broadcasts its hs slice and its dir slice in place, at their displacements) completes them on every rank.
