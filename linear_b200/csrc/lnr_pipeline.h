@@ -147,14 +147,26 @@ LNR_PIPE u64 * radix_sort(const Warp & w, u32 * hist, u64 * src, u64 * t0, u64 *
         if (((diff >> shift) & 0xff) == 0) continue;
         for (int b = w.lane; b < 256; b += w.nl) hist[b] = 0;
         wsync(w);
-        for (int i = w.lane; i < n; i += w.nl)
+        // four loads in flight per lane: the loop is bound by the round trip of in[i], not by the counting
+        for (int c = 0; c < n; c += 4 * w.nl)
         {
-            u32 d = (u32)(key(in[i]) >> shift) & 0xff;
+            u64 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? in[i] : 0; }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                int i = c + k * w.nl + w.lane;
+                if (i < n)
+                {
+                    u32 d = (u32)(key(v[k]) >> shift) & 0xff;
 #ifdef __CUDA_ARCH__
-            atomicAdd(&hist[d], 1u);
+                    atomicAdd(&hist[d], 1u);
 #else
-            hist[d]++;
+                    hist[d]++;
 #endif
+                }
+            }
         }
         wsync(w);
         // exclusive scan of the 256 bins
@@ -168,11 +180,13 @@ LNR_PIPE u64 * radix_sort(const Warp & w, u32 * hist, u64 * src, u64 * t0, u64 *
         }
         wsync(w);
         // stable scatter, 32 keys at a time in index order
+        u64 v_next = w.lane < n ? in[w.lane] : 0;   // the next 32 keys are fetched while the current ones are ranked
         for (int c = 0; c < n; c += w.nl)
         {
             int i = c + w.lane;
             bool valid = i < n;
-            u64 v = valid ? in[i] : 0;
+            u64 v = v_next;
+            v_next = i + w.nl < n ? in[i + w.nl] : 0;
             u32 d = valid ? ((u32)(key(v) >> shift) & 0xff) : 0x100u + (u32)w.lane;
             u32 peers = wmatch(w, d);
             int rank = popc_below(w, peers);
@@ -384,6 +398,10 @@ LNR_HD u32 sketch_slot(u32 bin) { return (bin * 2654435761u) >> (32 - kSketchBit
 // all anchors of a read are chance hits alone in their bin. The sketch counts hashed bins in shared memory first: a
 // sketch counter is >= the true count of each bin that maps to it, so an anchor whose counter is <= 10 can be dropped
 // without looking at the histogram at all, and only the few candidates take the exact, global path.
+// Two passes over A (sketch; exact counts of the candidates, which are copied to B in order), then two over the short
+// candidate list only: mark the candidates whose bin holds > 10 (bit 63 of the copy: raw anchors never carry it, their
+// contig id ends at bit 59 and only the strand bit 61 lies above), then clear the candidates' bins and compact the marked
+// ones in place. (Four passes over A took 48 % of k_hits_sort.)
 LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u32 * sketch, u64 * A, u64 * B, int n, int & n_out)
 {
     const int U = 4, step = U * w.nl;
@@ -407,6 +425,7 @@ LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u32 * sketch, u64 * A,
         }
     }
     wsync(w);
+    int nc = 0;                                  // candidates, copied to B[0..nc) in the order of A
     for (int c = 0; c < n; c += step)
     {
         u64 v[U];
@@ -416,10 +435,12 @@ LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u32 * sketch, u64 * A,
         for (int k = 0; k < U; k++)
         {
             int i = c + k * w.nl + w.lane;
+            bool cand = false;
             if (i < n)
             {
                 u32 bin = anchor_bin(v[k]);
-                if (sketch[sketch_slot(bin)] > 10)
+                cand = sketch[sketch_slot(bin)] > 10;
+                if (cand)
                 {
 #ifdef __CUDA_ARCH__
                     atomicAdd(&bins[bin], 1u);
@@ -428,53 +449,35 @@ LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u32 * sketch, u64 * A,
 #endif
                 }
             }
+            u32 bal = wballot(w, cand);
+            if (cand) B[nc + popc_below(w, bal)] = v[k];
+            nc += popc32(bal);
+        }
+    }
+    wsync(w);
+    for (int c = 0; c < nc; c += w.nl)             // mark
+    {
+        int i = c + w.lane;
+        if (i < nc)
+        {
+            u64 v = B[i];
+            if (bins[anchor_bin(v)] > 10) B[i] = v | kFlagMain;
         }
     }
     wsync(w);
     int ii = 0;
-    for (int c = 0; c < n; c += step)
+    for (int c = 0; c < nc; c += w.nl)             // clear the bins, keep the marked candidates (ii <= c: in place)
     {
-        u64 v[U]; u32 cnt[U];
-#pragma unroll
-        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
-#pragma unroll
-        for (int k = 0; k < U; k++)
-        {
-            int i = c + k * w.nl + w.lane;
-            cnt[k] = 0;
-            if (i < n)
-            {
-                u32 bin = anchor_bin(v[k]);
-                if (sketch[sketch_slot(bin)] > 10) cnt[k] = bins[bin];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < U; k++)
-        {
-            bool keep = cnt[k] > 10;
-            u32 bal = wballot(w, keep);
-            if (keep) B[ii + popc_below(w, bal)] = v[k];
-            ii += popc32(bal);
-        }
+        int i = c + w.lane;
+        u64 v = i < nc ? B[i] : 0;
+        if (i < nc) bins[anchor_bin(v)] = 0;
+        wsync(w);
+        bool keep = (v & kFlagMain) != 0;
+        u32 bal = wballot(w, keep);
+        if (keep) B[ii + popc_below(w, bal)] = v & ~kFlagMain;
+        ii += popc32(bal);
+        wsync(w);
     }
-    wsync(w);
-    for (int c = 0; c < n; c += step)
-    {
-        u64 v[U];
-#pragma unroll
-        for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
-#pragma unroll
-        for (int k = 0; k < U; k++)
-        {
-            int i = c + k * w.nl + w.lane;
-            if (i < n)
-            {
-                u32 bin = anchor_bin(v[k]);
-                if (sketch[sketch_slot(bin)] > 10) bins[bin] = 0;
-            }
-        }
-    }
-    wsync(w);
     for (int j = w.lane; j < kSketch; j += w.nl) sketch[j] = 0;
     wsync(w);
     if (ii != 0) { n_out = ii; return B; }

@@ -1,0 +1,12 @@
+# round 2, call 33: warp-cooperative bucket tails in k_seed_count: parity (all of test_gpu_parity + fuzz), bench line
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r2_tests33.log
+cat gpurun_out/r2_tests33.log
+export LNR_BENCH_NO_SMALL=1
+timeout 400 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench33.json 2> gpurun_out/r2_bench33.err; echo "rc=$?"
+python - <<PY
+import json
+d=json.load(open('gpurun_out/r2_bench33.json'))
+k=d['kernels_one_thread']
+print(round(d['value']), round(d['e2e']['value']), round(d['ms_per_step'],2), 'count', round(k['k_seed_count']['ms_per_launch'],3), 'fill', round(k['k_seed_fill']['ms_per_launch'],3), 'sort', round(k['k_hits_sort']['ms_per_launch'],3), 'one-thread step', round(d['roofline']['whole_step']['ms_per_step_one_thread'],2), d['fallback_paths_last_batch'])
+PY
