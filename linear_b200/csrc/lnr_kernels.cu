@@ -131,7 +131,7 @@ struct lnr_ctx
     DevBuf ing[8];   // read-ingest temporaries (lnr_ingest.cuh)
     void * reads_cache = nullptr; size_t reads_cache_bytes = 0;   // last output block given back by lnr_reads_destroy
     DevBuf packed;   // 2-bit packed batch as uploaded (lnr_apxmap_batch_packed)
-    DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, heavy_list, seed_masks, seed_mask_off, warp_rec;
+    DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, heavy_list, seed_masks, seed_mask_off, warp_rec, task_info;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -802,7 +802,14 @@ __global__ void k_idx_sort_buckets(const i32 * __restrict__ dir, u64 * __restric
 // =====================================================================================================
 // seeding (getDIndexMatchAll, pmpfinder.cpp:1856)
 // =====================================================================================================
-__global__ void k_seed_prep(const u8 * __restrict__ bases, const u64 * __restrict__ read_off, SeedTask * tasks, u32 n_tasks)
+// Besides the hash constants of a task this pass lays out what the two seeding kernels would otherwise find through
+// chains of dependent loads at the head of every warp: the read's offset and length next to the task (tinfo), and for
+// every warp of 32 samples the task of its first sample (wrec[].task; the count pass rewrites the record with the same
+// value) -- a binary search over 65 536 tasks was 16 round trips before a warp touched its first base.
+struct SeedTaskInfo { u64 base; u64 len; };
+struct SeedWarpRec { u32 list_off; u32 scanned; u32 task; u32 pad; };   // per warp: start of its entries (0xffffffff: none), records scanned (H), task of its first sample
+__global__ void k_seed_prep(const u8 * __restrict__ bases, const u64 * __restrict__ read_off, SeedTask * tasks, u32 n_tasks,
+                            SeedTaskInfo * __restrict__ tinfo, SeedWarpRec * __restrict__ wrec)
 {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_tasks) return;
@@ -812,6 +819,11 @@ __global__ void k_seed_prep(const u8 * __restrict__ bases, const u64 * __restric
     t.kskip = (u32)hash_init_skip<kSpanD>(acc, 0, (i64)L);
     t.bias = selector_bias<kSpanD>(acc, (i64)t.kskip, (i64)t.str + kSpanD);
     tasks[i] = t;
+    SeedTaskInfo inf; inf.base = read_off[t.read]; inf.len = L;
+    tinfo[i] = inf;
+    // warps w whose first sample 32 w lies in [sample0, sample0 + n_samples)
+    const u64 w1 = (t.sample0 + t.n_samples + 31) >> 5;
+    for (u64 w = (t.sample0 + 31) >> 5; w < w1; w++) wrec[w].task = i;
 }
 
 // per sample: packed info = bucket start (32) | bucket size (16) | Y (8) | strand (1) | k (is recomputed) ;
@@ -821,6 +833,23 @@ __device__ __forceinline__ u32 find_task(const SeedTask * tasks, u32 n_tasks, u6
 {
     u32 lo = 0, hi = n_tasks;
     while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tasks[mid].sample0 <= s) lo = mid; else hi = mid; }
+    return lo;
+}
+// the same answer (the last task whose sample0 is <= s) by a 32-ary search of the whole warp: 4 dependent loads for 65 536
+// tasks instead of 16 -- the search sits at the head of every warp's chain of round trips
+__device__ __forceinline__ u32 find_task_warp(const SeedTask * tasks, u32 n_tasks, u64 s, unsigned lane)
+{
+    u32 lo = 0, hi = n_tasks;
+    while (hi - lo > 1)
+    {
+        const u32 step = (hi - lo + 31u) / 32u;
+        const u32 idx = lo + step * lane;
+        const bool le = idx < hi && tasks[idx].sample0 <= s;      // lane 0 probes lo itself; true for a prefix of the lanes
+        const u32 m = __ballot_sync(0xffffffffu, le) | 1u;
+        const u32 top = 31u - (u32)__clz((int)m);
+        lo += step * top;
+        hi = min(hi, lo + step);
+    }
     return lo;
 }
 
@@ -1227,11 +1256,13 @@ __global__ void __launch_bounds__(256) k_idx_rank(const u64 * __restrict__ tmp, 
 // from one of kMaskPools pools; the fill pass then spreads those entries evenly over the lanes -- every lane keeps a
 // random hs load in flight -- instead of walking one sample's matches per thread. A warp that gets no room (pool
 // exhausted) is re-scanned by the fill pass. Per sample only the match count is stored (it feeds the device scan).
-struct SeedWarpRec { u32 list_off; u32 scanned; };   // per warp: start of its entries (0xffffffff: none), records scanned (H)
-__global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
-                                                    const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
-                                                    const uint4 * __restrict__ dirx, const u8 * __restrict__ hsy,
-                                                    u32 * __restrict__ count, SeedWarpRec * __restrict__ wrec,
+#ifndef LNR_COUNT_MIN_CTAS
+#define LNR_COUNT_MIN_CTAS 8     // 32 registers (24 bytes spilled), 64 warps per SM: 4.65 -> 4.46 ms per 65 536 reads (call 35)
+#endif
+__global__ void __launch_bounds__(256, LNR_COUNT_MIN_CTAS) k_seed_count(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
+                                                    const SeedTask * __restrict__ tasks, const SeedTaskInfo * __restrict__ tinfo, u32 n_tasks,
+                                                    u64 n_samples, const uint4 * __restrict__ dirx, const u8 * __restrict__ hsy,
+                                                    u32 * __restrict__ count, SeedWarpRec * wrec,
                                                     u32 * __restrict__ list, u32 pool_cap, unsigned int * pool_ctr)
 {
     u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1246,17 +1277,15 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
     GAcc acc = {nullptr, 0};
     SeedVal sv = {0, 0, 0};
     // the 32 samples of a warp are consecutive and a task has ~1300: one search per warp, the lanes walk on from it
-    u32 t_first = 0;
-    if (lane == 0) t_first = find_task(tasks, n_tasks, min(s, n_samples - 1));
-    t_first = __shfl_sync(0xffffffffu, t_first, 0);
+    const u32 t_first = s - lane < n_samples ? wrec[(s - lane) >> 5].task : 0u;     // laid out by k_seed_prep
     if (s < n_samples)
     {
         ti = t_first;
         while (ti + 1 < n_tasks && tasks[ti + 1].sample0 <= s) ti++;
         t = tasks[ti];
         m = (u32)(s - t.sample0) + 1;
-        u64 L = read_off[t.read + 1] - read_off[t.read];
-        acc.s = bases + read_off[t.read]; acc.len = (i64)L;
+        const SeedTaskInfo inf = tinfo[ti];
+        acc.s = bases + inf.base; acc.len = (i64)inf.len;
         u32 k;
         if (!seed_sample_fast(acc.s, acc.len, t, m, sv)) seed_sample(acc, t, m, sv, k);
         X = sv.X;
@@ -1351,7 +1380,7 @@ __global__ void __launch_bounds__(256) k_seed_count(const u8 * __restrict__ base
     const bool have = (u64)wbase + wtot <= (u64)pool_cap;
     if (lane == 0 && s < n_samples)
     {
-        SeedWarpRec r; r.list_off = wtot == 0 ? 0u : (have ? pool * pool_cap + wbase : 0xffffffffu); r.scanned = hsum;
+        SeedWarpRec r; r.list_off = wtot == 0 ? 0u : (have ? pool * pool_cap + wbase : 0xffffffffu); r.scanned = hsum; r.task = t_first; r.pad = 0;
         wrec[s >> 5] = r;
     }
     if (s < n_samples) count[s] = c;
@@ -1392,9 +1421,12 @@ __global__ void __launch_bounds__(256) k_seed_stats(const SeedWarpRec * __restri
 // anchors of task ti start at aoff[sample0] + ti (slot 0 of the region is the sentinel). A warp owns the same 32 samples
 // as in the count pass; its matches are dealt round-robin to the lanes: entry j of the warp's run belongs to the sample
 // whose exclusive count prefix is the largest one <= j (found with 5 shuffles), that sample's k / L / task come by shuffle.
-__global__ void __launch_bounds__(256) k_seed_fill(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
-                                                   const SeedTask * __restrict__ tasks, u32 n_tasks, u64 n_samples,
-                                                   const u64 * __restrict__ hs, const uint4 * __restrict__ dirx,
+#ifndef LNR_FILL_MIN_CTAS
+#define LNR_FILL_MIN_CTAS 8      // 32 registers, 64 warps per SM: the kernel lives on loads in flight, 3.16 -> 2.91 ms (call 35)
+#endif
+__global__ void __launch_bounds__(256, LNR_FILL_MIN_CTAS) k_seed_fill(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
+                                                   const SeedTask * __restrict__ tasks, const SeedTaskInfo * __restrict__ tinfo, u32 n_tasks,
+                                                   u64 n_samples, const u64 * __restrict__ hs, const uint4 * __restrict__ dirx,
                                                    const u64 * __restrict__ aoff, u64 * __restrict__ anchors,
                                                    const u32 * __restrict__ count, const SeedWarpRec * __restrict__ wrec,
                                                    const u32 * __restrict__ list, unsigned long long * counters)
@@ -1410,10 +1442,17 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u8 * __restrict__ bases
     const u32 T = __shfl_sync(0xffffffffu, incl, 31);
     if (T == 0) return;
     const u32 e = incl - c;
-    u32 t_first = 0;
-    if (lane == 0) t_first = find_task(tasks, n_tasks, s0);
-    t_first = __shfl_sync(0xffffffffu, t_first, 0);
-    u32 ti = t_first, k = 0, L = 0;
+    const SeedWarpRec wr = wrec[s0 >> 5];        // (the task of the warp's first sample is here)
+    const u64 a0 = aoff[s0];
+    // the first 64 entries of the warp's run are on their way before the task of the sample is looked up
+    const u32 * lst = list + (wr.list_off != 0xffffffffu ? wr.list_off : 0u);
+    u32 pe0 = 0, pe1 = 0;
+    if (wr.list_off != 0xffffffffu)
+    {
+        if (lane < T) pe0 = __ldg(lst + lane);
+        if (lane + 32 < T) pe1 = __ldg(lst + lane + 32);
+    }
+    u32 ti = wr.task, k = 0, L = 0;
     SeedTask t;
     memset(&t, 0, sizeof t);
     if (c)
@@ -1422,30 +1461,44 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u8 * __restrict__ bases
         t = tasks[ti];
         const u32 m = (u32)(s - t.sample0) + 1;
         k = t.str + kSpanD + t.alpha * m - 1;
-        L = (u32)(read_off[t.read + 1] - read_off[t.read]);
+        L = (u32)tinfo[ti].len;
     }
-    const SeedWarpRec wr = wrec[s0 >> 5];
-    const u64 a0 = aoff[s0];
     if (wr.list_off != 0xffffffffu)
     {
-        const u32 * lst = list + wr.list_off;
-        for (u32 base = 0; base < T; base += 32)
+        // two entries per lane and iteration (a warp has ~60): both entry loads, then both random record loads, are in flight
+        // together -- the kernel waits on DRAM round trips (long scoreboard 23 cycles per issue), not on anything it computes
+        for (u32 base = 0; base < T; base += 64)
         {
-            const u32 j = base + lane;
-            u32 lo = 0;
+            const u32 j0 = base + lane, j1 = j0 + 32;
+            const bool two = base + 32 < T;                      // warp-uniform
+            const u32 ent0 = base == 0 ? pe0 : (j0 < T ? __ldg(lst + j0) : 0u);
+            const u32 ent1 = base == 0 ? pe1 : (j1 < T ? __ldg(lst + j1) : 0u);
+            u32 lo0 = 0, lo1 = 0;
 #pragma unroll
             for (int step = 16; step; step >>= 1)
             {
-                const u32 cand = lo + step;
-                const u32 ec = __shfl_sync(0xffffffffu, e, cand & 31);
-                if (ec <= j) lo = cand;          // e is non-decreasing over the lanes and cand < 32
+                const u32 c0 = lo0 + step;
+                const u32 ec0 = __shfl_sync(0xffffffffu, e, c0 & 31);
+                if (ec0 <= j0) lo0 = c0;         // e is non-decreasing over the lanes and cand < 32
             }
-            const u32 ko = __shfl_sync(0xffffffffu, k, lo), Lo = __shfl_sync(0xffffffffu, L, lo), tio = __shfl_sync(0xffffffffu, ti, lo);
-            if (j < T)
+            if (two)
             {
-                const u32 ent = __ldg(lst + j);
-                const u64 h = __ldg(hs + (ent & 0x7fffffffu));
-                anchors[a0 + j + tio + 1] = val2anchor(h, (u64)ko, (u64)Lo, ent >> 31);
+#pragma unroll
+                for (int step = 16; step; step >>= 1)
+                {
+                    const u32 c1 = lo1 + step;
+                    const u32 ec1 = __shfl_sync(0xffffffffu, e, c1 & 31);
+                    if (ec1 <= j1) lo1 = c1;
+                }
+            }
+            const u64 h0 = j0 < T ? __ldg(hs + (ent0 & 0x7fffffffu)) : 0ull;
+            const u64 h1 = j1 < T ? __ldg(hs + (ent1 & 0x7fffffffu)) : 0ull;
+            const u32 ko0 = __shfl_sync(0xffffffffu, k, lo0), Lo0 = __shfl_sync(0xffffffffu, L, lo0), tio0 = __shfl_sync(0xffffffffu, ti, lo0);
+            if (j0 < T) anchors[a0 + j0 + tio0 + 1] = val2anchor(h0, (u64)ko0, (u64)Lo0, ent0 >> 31);
+            if (two)
+            {
+                const u32 ko1 = __shfl_sync(0xffffffffu, k, lo1), Lo1 = __shfl_sync(0xffffffffu, L, lo1), tio1 = __shfl_sync(0xffffffffu, ti, lo1);
+                if (j1 < T) anchors[a0 + j1 + tio1 + 1] = val2anchor(h1, (u64)ko1, (u64)Lo1, ent1 >> 31);
             }
         }
     }
@@ -1453,7 +1506,7 @@ __global__ void __launch_bounds__(256) k_seed_fill(const u8 * __restrict__ bases
     {
         // the warp got no room for its entries in the count pass: evaluate the sample again and scan its bucket in hs
         atomicAdd(&counters[18], 1ULL);   // diagnostics: samples re-scanned
-        GAcc acc = {bases + read_off[t.read], (i64)L};
+        GAcc acc = {bases + tinfo[ti].base, (i64)L};
         SeedVal sv; u32 kk;
         const u32 m = (u32)(s - t.sample0) + 1;
         if (!seed_sample_fast(acc.s, acc.len, t, m, sv)) seed_sample(acc, t, m, sv, kk);
@@ -1743,7 +1796,7 @@ __device__ __forceinline__ void stage_begin(const MapArgs & a, StageCommon & c)
 }
 __device__ __forceinline__ void stage_rec_begin(const MapArgs & a, StageCommon & c, int stage)
 {
-    if (!a.warp_rec) return;
+    if (!a.warp_rec || (u64)c.gw >= a.warp_rec_stage_stride) return;     // (a section launched with more warps than the record area has rows)
     c.rec = a.warp_rec + ((u64)stage * a.warp_rec_stage_stride + c.gw) * 8 + (u64)a.warp_rec_stage_off;
     c.g_start = globaltimer_ns(); c.max_dur = 0; c.max_ti = 0; c.max_size = 0; c.max_q = 0; c.n_done = 0; c.t_task = 0;
 }
@@ -2315,7 +2368,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec, &ctx->packed})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec, &ctx->packed, &ctx->task_info})
         b->release();
     ctx->stage.release();
     if (ctx->reads_cache) cudaFree(ctx->reads_cache);
@@ -3413,6 +3466,7 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     {
         CK(ctx->seed_masks.reserve((size_t)list_cap * sizeof(u32)));
         CK(ctx->seed_mask_off.reserve((size_t)(n_swarps + 1) * sizeof(SeedWarpRec)));
+        CK(ctx->task_info.reserve((size_t)(n_tasks + 1) * sizeof(SeedTaskInfo)));
     }
     CK(ctx->mask_ctr.reserve(kMaskPools * sizeof(unsigned int)));
     unsigned int * d_pool_ctr = ctx->mask_ctr.as<unsigned int>();
@@ -3424,7 +3478,8 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
     {
         LaunchScope ls(ctx, "k_seed_prep");
         if (hx_mode) k_hseed_prep<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks);
-        else k_seed_prep<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks);
+        else k_seed_prep<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, ctx->task_info.as<SeedTaskInfo>(),
+                                                                         ctx->seed_mask_off.as<SeedWarpRec>());
     }
     // one extra zero count so that aoff[n_samples] = total
     CK(cudaMemsetAsync(ctx->sample_cnt.as<u32>() + n_samples, 0, sizeof(u32), ctx->stream));
@@ -3435,7 +3490,7 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
             k_hseed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, hx,
                                                                                    ctx->sample_info.as<u64>(), ctx->sample_cnt.as<u32>(), d_counters);
         else
-            k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_dirx,
+            k_seed_count<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, ctx->task_info.as<SeedTaskInfo>(), n_tasks, n_samples, ix->d_dirx,
                                                                                   ix->d_hsy, ctx->sample_cnt.as<u32>(), ctx->seed_mask_off.as<SeedWarpRec>(),
                                                                                   ctx->seed_masks.as<u32>(), pool_cap, d_pool_ctr);
     }
@@ -3460,7 +3515,7 @@ static int seeding_pass(lnr_ctx * ctx, const lnr_index * ix, const u8 * d_bases,
             k_hseed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_read_off, d_tasks, n_tasks, n_samples, hx,
                                                                                   ctx->sample_info.as<u64>(), aoff_buf.as<u64>(), ctx->anchorsA.as<u64>());
         else
-            k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, n_tasks, n_samples, ix->d_hs, ix->d_dirx,
+            k_seed_fill<<<(u32)((n_samples + 255) / 256), 256, 0, ctx->stream>>>(d_bases, d_read_off, d_tasks, ctx->task_info.as<SeedTaskInfo>(), n_tasks, n_samples, ix->d_hs, ix->d_dirx,
                                                                                  aoff_buf.as<u64>(), ctx->anchorsA.as<u64>(), ctx->sample_cnt.as<u32>(),
                                                                                  ctx->seed_mask_off.as<SeedWarpRec>(), ctx->seed_masks.as<u32>(), d_counters);
     }
@@ -3991,7 +4046,7 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
         const int cps[3] = {ctx->sort_ctas_per_sm, ctx->chain_ctas_per_sm, ctx->blocks_ctas_per_sm};
         for (int st = 0; st < 3; st++)
         {
-            const size_t nw = (size_t)ctx->n_sm * cps[st] * 4;
+            const size_t nw = std::min<size_t>((size_t)ctx->n_sm * cps[st] * 4, (size_t)n_warps);
             const u64 * R = rec.data() + n_warps * 24 + (size_t)st * n_warps * 8;
             u64 t0 = ~0ULL, t1 = 0;
             std::vector<double> ends;
