@@ -131,7 +131,7 @@ struct lnr_ctx
     DevBuf ing[8];   // read-ingest temporaries (lnr_ingest.cuh)
     void * reads_cache = nullptr; size_t reads_cache_bytes = 0;   // last output block given back by lnr_reads_destroy
     DevBuf packed;   // 2-bit packed batch as uploaded (lnr_apxmap_batch_packed)
-    DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, heavy_list, seed_masks, seed_mask_off, warp_rec, task_info;
+    DevBuf remap_list, order, order2, mask_ctr, tile_read, task_nhits, task_state, big_arena, big_list, heavy_list, seed_masks, seed_mask_off, warp_rec, task_info, feat_pairs;
     size_t big_arena_bytes_per_warp = 128u << 20;
     int map_warps_per_cta = 4;
     int map_ctas_per_sm = 6;
@@ -415,14 +415,28 @@ __global__ void k_feat_tile_reads(const u32 * __restrict__ ftile, u32 n_reads, u
     if (r >= n_reads) return;
     for (u32 t = ftile[r]; t < ftile[r + 1]; t++) tile_read[t] = r;
 }
+// one descriptor per pair of tiles (forward + reverse tile of the same index), laid out by a thread per read: the feature
+// kernel then starts an iteration with ONE load instead of a chain tile -> read -> offsets
+struct FeatPair { u64 base; u64 out; u32 L; u32 nf; u32 e0; u32 pad; };
+__global__ void k_feat_pairs(const u32 * __restrict__ ftile, const u64 * __restrict__ read_off, const u64 * __restrict__ foff, u32 n_reads,
+                             FeatPair * __restrict__ pairs)
+{
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    FeatPair d;
+    d.base = read_off[r]; d.out = foff[r];
+    const u64 L = read_off[r + 1] - read_off[r];
+    d.L = (u32)L; d.nf = feat_count_read(L); d.pad = 0;
+    const u32 p0 = ftile[r] >> 1, p1 = ftile[r + 1] >> 1;
+    for (u32 p = p0; p < p1; p++) { d.e0 = (p - p0) * FE; pairs[p] = d; }
+}
 // persistent CTAs over the tiles: the 2-mer table is built once per CTA, not once per 256 cells. A read's tiles come as
 // tps forward tiles followed by tps reverse tiles (n_tiles is even, every read's range starts at an even tile): one loop
 // iteration takes the forward and the reverse tile of the same index together -- both cells' loads are issued before either
 // is used. LNR_FEAT_BUFS = 2 exchanges the cell sums through two alternating shared buffers, so that an iteration has ONE
 // barrier (a thread can be at most one iteration ahead of the slowest, and then writes the other buffer).
-__global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases, const u64 * __restrict__ read_off,
-                                                   const u64 * __restrict__ foff, const u32 * __restrict__ ftile,
-                                                   const u32 * __restrict__ tile_read, u32 n_tiles, F96 * __restrict__ out)
+__global__ void __launch_bounds__(FT, 8) k_feat_reads(const u8 * __restrict__ bases, const FeatPair * __restrict__ pairs, u32 n_tiles,
+                                                   F96 * __restrict__ out)
 {
 #ifndef LNR_FEAT_BUFS
 #define LNR_FEAT_BUFS 1     // 2: alternating buffers, one barrier per iteration -- measured equal (1.57 vs 1.60 ms, call 29), 6 KB more
@@ -436,13 +450,12 @@ __global__ void __launch_bounds__(FT) k_feat_reads(const u8 * __restrict__ bases
     u32 buf = 0;
     for (u32 pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, buf ^= (u32)(LNR_FEAT_BUFS - 1))
     {
-        const u32 r = tile_read[2 * pair];
-        const u64 L = read_off[r + 1] - read_off[r];
-        const u32 nf = feat_count_read(L);
-        const u32 e0 = (pair - (ftile[r] >> 1)) * FE;
-        const u32 c = e0 + threadIdx.x;
-        F96 * o = out + foff[r];
-        const u8 * s = bases + read_off[r];
+        const FeatPair d = pairs[pair];
+        const u64 L = d.L;
+        const u32 nf = d.nf;
+        const u32 c = d.e0 + threadIdx.x;
+        F96 * o = out + d.out;
+        const u8 * s = bases + d.base;
         CellLoad cf, cr;
         feat_cell_issue<false>(bases, s, (i64)L, c, nf, cf);
         feat_cell_issue<true>(bases, s, (i64)L, c, nf, cr);
@@ -1280,11 +1293,18 @@ __global__ void __launch_bounds__(256, LNR_COUNT_MIN_CTAS) k_seed_count(const u8
     const u32 t_first = s - lane < n_samples ? wrec[(s - lane) >> 5].task : 0u;     // laid out by k_seed_prep
     if (s < n_samples)
     {
+        // the warp's first task, its read and the start of the next task in one round trip; only the lanes of a warp that
+        // straddles a task boundary (1 warp in ~40) walk on
         ti = t_first;
-        while (ti + 1 < n_tasks && tasks[ti + 1].sample0 <= s) ti++;
+        const u64 nxt = ti + 1 < n_tasks ? tasks[ti + 1].sample0 : ~0ULL;
         t = tasks[ti];
+        SeedTaskInfo inf = tinfo[ti];
+        if (nxt <= s)
+        {
+            do ti++; while (ti + 1 < n_tasks && tasks[ti + 1].sample0 <= s);
+            t = tasks[ti]; inf = tinfo[ti];
+        }
         m = (u32)(s - t.sample0) + 1;
-        const SeedTaskInfo inf = tinfo[ti];
         acc.s = bases + inf.base; acc.len = (i64)inf.len;
         u32 k;
         if (!seed_sample_fast(acc.s, acc.len, t, m, sv)) seed_sample(acc, t, m, sv, k);
@@ -1457,11 +1477,16 @@ __global__ void __launch_bounds__(256, LNR_FILL_MIN_CTAS) k_seed_fill(const u8 *
     memset(&t, 0, sizeof t);
     if (c)
     {
-        while (ti + 1 < n_tasks && tasks[ti + 1].sample0 <= s) ti++;
+        const u64 nxt = ti + 1 < n_tasks ? tasks[ti + 1].sample0 : ~0ULL;
         t = tasks[ti];
+        L = (u32)tinfo[ti].len;
+        if (nxt <= s)
+        {
+            do ti++; while (ti + 1 < n_tasks && tasks[ti + 1].sample0 <= s);
+            t = tasks[ti]; L = (u32)tinfo[ti].len;
+        }
         const u32 m = (u32)(s - t.sample0) + 1;
         k = t.str + kSpanD + t.alpha * m - 1;
-        L = (u32)tinfo[ti].len;
     }
     if (wr.list_off != 0xffffffffu)
     {
@@ -2368,7 +2393,7 @@ void lnr_ctx_destroy(lnr_ctx * ctx)
     for (DevBuf * b : {&ctx->bases, &ctx->read_off, &ctx->tasks, &ctx->sample_info, &ctx->sample_cnt, &ctx->scan_tmp, &ctx->anchorsA,
                        &ctx->anchorsB, &ctx->feats, &ctx->foff, &ctx->ftile, &ctx->cords, &ctx->cords_base, &ctx->ncords, &ctx->slots,
                        &ctx->bins, &ctx->arena, &ctx->tasks2, &ctx->misc, &ctx->out_cords, &ctx->out_off, &ctx->dbg_hits, &ctx->dbg_hoff,
-                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec, &ctx->packed, &ctx->task_info})
+                       &ctx->dbg_nhits, &ctx->dbg_c1, &ctx->dbg_nc1, &ctx->read_meta, &ctx->remap_list, &ctx->ing[0], &ctx->ing[1], &ctx->ing[2], &ctx->ing[3], &ctx->ing[4], &ctx->ing[5], &ctx->ing[6], &ctx->ing[7], &ctx->order, &ctx->order2, &ctx->mask_ctr, &ctx->tile_read, &ctx->task_nhits, &ctx->task_state, &ctx->big_arena, &ctx->big_list, &ctx->seed_masks, &ctx->seed_mask_off, &ctx->warp_rec, &ctx->packed, &ctx->task_info, &ctx->feat_pairs})
         b->release();
     ctx->stage.release();
     if (ctx->reads_cache) cudaFree(ctx->reads_cache);
@@ -3658,14 +3683,17 @@ static int apxmap_core(lnr_ctx * ctx, const lnr_index * ix, const lnr_feats * f2
     if (n_ftiles)
     {
         CK(ctx->tile_read.reserve((size_t)n_ftiles * sizeof(u32)));
-        LaunchScope ls(ctx, "k_feat_reads");
-        k_feat_tile_reads<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(ctx->ftile.as<u32>(), n_reads, ctx->tile_read.as<u32>());
+        CK(ctx->feat_pairs.reserve((size_t)(n_ftiles / 2 + 1) * sizeof(FeatPair)));
+        LaunchScope ls(ctx, "k_feat_reads", 2);
+        if (ft == 1) k_feat_tile_reads<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(ctx->ftile.as<u32>(), n_reads, ctx->tile_read.as<u32>());
         if (ft == 1)
             k_feat32_reads<<<std::min<u32>(n_ftiles, (u32)ctx->n_sm * 16), FT, 0, ctx->stream>>>(d_bases, d_read_off, ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
                                                                                              ctx->tile_read.as<u32>(), n_ftiles, ctx->feats.as<i16>());
         else
-        k_feat_reads<<<std::min<u32>(n_ftiles, (u32)ctx->n_sm * 16), FT, 0, ctx->stream>>>(d_bases, d_read_off, ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
-                                                                                       ctx->tile_read.as<u32>(), n_ftiles, ctx->feats.as<F96>());
+        {
+            k_feat_pairs<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(ctx->ftile.as<u32>(), d_read_off, ctx->foff.as<u64>(), n_reads, ctx->feat_pairs.as<FeatPair>());
+            k_feat_reads<<<std::min<u32>(n_ftiles / 2, (u32)ctx->n_sm * 8), FT, 0, ctx->stream>>>(d_bases, ctx->feat_pairs.as<FeatPair>(), n_ftiles, ctx->feats.as<F96>());
+        }
     }
     CK(cudaGetLastError());
     // ---- primary seeding
@@ -4467,8 +4495,11 @@ int lnr_read_features(lnr_ctx * ctx, const uint8_t * dna5, uint64_t len, int fea
         k_feat32_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
                                                   ctx->tile_read.as<u32>(), ft[1], ctx->feats.as<i16>());
     else if (ft[1])
-        k_feat_reads<<<ft[1], FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), ctx->ftile.as<u32>(),
-                                                ctx->tile_read.as<u32>(), ft[1], ctx->feats.as<F96>());
+    {
+        CK(ctx->feat_pairs.reserve((size_t)(ft[1] / 2 + 1) * sizeof(FeatPair)));
+        k_feat_pairs<<<1, 32, 0, ctx->stream>>>(ctx->ftile.as<u32>(), ctx->read_off.as<u64>(), ctx->foff.as<u64>(), 1u, ctx->feat_pairs.as<FeatPair>());
+        k_feat_reads<<<ft[1] / 2, FT, 0, ctx->stream>>>(ctx->bases.as<u8>(), ctx->feat_pairs.as<FeatPair>(), ft[1], ctx->feats.as<F96>());
+    }
     CK(cudaGetLastError());
     if (dst_fwd) CK(cudaMemcpyAsync(dst_fwd, ctx->feats.p, (size_t)nf * esz, cudaMemcpyDeviceToHost, ctx->stream));
     if (dst_rev) CK(cudaMemcpyAsync(dst_rev, ctx->feats.as<u8>() + (size_t)nf * esz, (size_t)nf * esz, cudaMemcpyDeviceToHost, ctx->stream));
