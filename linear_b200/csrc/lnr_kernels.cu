@@ -821,6 +821,22 @@ __global__ void k_idx_sort_buckets(const i32 * __restrict__ dir, u64 * __restric
 // value) -- a binary search over 65 536 tasks was 16 round trips before a warp touched its first base.
 struct SeedTaskInfo { u64 base; u64 len; };
 struct SeedWarpRec { u32 list_off; u32 scanned; u32 task; u32 pad; };   // per warp: start of its entries (0xffffffff: none), records scanned (H), task of its first sample
+// Random index reads of the seeding kernels. A plain load that misses in L2 brings in 128 bytes (measured: it times exactly
+// like ld.global.nc.L2::128B, and ncu shows 2.8 DRAM sectors per requested sector); the smallest size PTX can ask for is 64
+// bytes -- one lookup entry of dirx, or the sector pair around an 8-byte hs record: k_seed_fill 2.49 -> 2.17 ms per 65 536
+// reads (L2::256B: 2.67 ms; L2-only ld.global.cg loads and a 32-byte cudaLimitMaxL2FetchGranularity change nothing).
+__device__ __forceinline__ u64 ld_hs(const u64 * p)
+{
+    u64 v; asm volatile("ld.global.nc.L2::64B.b64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint4 ld_dirx(const uint4 * p)
+{
+#ifdef LNR_DIRX_PLAIN
+    return __ldg(p);
+#else
+    uint4 v; asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
+#endif
+}
 __global__ void k_seed_prep(const u8 * __restrict__ bases, const u64 * __restrict__ read_off, SeedTask * tasks, u32 n_tasks,
                             SeedTaskInfo * __restrict__ tinfo, SeedWarpRec * __restrict__ wrec)
 {
@@ -1322,7 +1338,7 @@ __global__ void __launch_bounds__(256, LNR_COUNT_MIN_CTAS) k_seed_count(const u8
         }
         if (sv.X != xprev)
         {
-            e0 = __ldg(dirx + (size_t)kDirxQuads * sv.X); e1 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 1);
+            e0 = ld_dirx(dirx + (size_t)kDirxQuads * sv.X); e1 = ld_dirx(dirx + (size_t)kDirxQuads * sv.X + 1);
             bkt_b = (i32)e0.x;
             qY = sv.Y;
             scanned = e0.y;
@@ -1365,7 +1381,7 @@ __global__ void __launch_bounds__(256, LNR_COUNT_MIN_CTAS) k_seed_count(const u8
             if (4u * q < scanned) m0 |= (u64)match4raw(ew[q]) << (4 * q);
         if (scanned > 24)
         {
-            const uint4 e2 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 2), e3 = __ldg(dirx + (size_t)kDirxQuads * sv.X + 3);
+            const uint4 e2 = ld_dirx(dirx + (size_t)kDirxQuads * sv.X + 2), e3 = ld_dirx(dirx + (size_t)kDirxQuads * sv.X + 3);
             const u32 fw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
 #pragma unroll
             for (int q = 0; q < 8; q++)
@@ -1516,8 +1532,8 @@ __global__ void __launch_bounds__(256, LNR_FILL_MIN_CTAS) k_seed_fill(const u8 *
                     if (ec1 <= j1) lo1 = c1;
                 }
             }
-            const u64 h0 = j0 < T ? __ldg(hs + (ent0 & 0x7fffffffu)) : 0ull;
-            const u64 h1 = j1 < T ? __ldg(hs + (ent1 & 0x7fffffffu)) : 0ull;
+            const u64 h0 = j0 < T ? ld_hs(hs + (ent0 & 0x7fffffffu)) : 0ull;
+            const u64 h1 = j1 < T ? ld_hs(hs + (ent1 & 0x7fffffffu)) : 0ull;
             const u32 ko0 = __shfl_sync(0xffffffffu, k, lo0), Lo0 = __shfl_sync(0xffffffffu, L, lo0), tio0 = __shfl_sync(0xffffffffu, ti, lo0);
             if (j0 < T) anchors[a0 + j0 + tio0 + 1] = val2anchor(h0, (u64)ko0, (u64)Lo0, ent0 >> 31);
             if (two)
