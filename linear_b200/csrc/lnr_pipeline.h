@@ -401,7 +401,8 @@ LNR_HD u32 sketch_slot(u32 bin) { return (bin * 2654435761u) >> (32 - kSketchBit
 // Two passes over A (sketch; exact counts of the candidates, which are copied to B in order), then two over the short
 // candidate list only: mark the candidates whose bin holds > 10 (bit 63 of the copy: raw anchors never carry it, their
 // contig id ends at bit 59 and only the strand bit 61 lies above), then clear the candidates' bins and compact the marked
-// ones in place. (Four passes over A took 48 % of k_hits_sort.)
+// ones in place. (Four passes over A took 48 % of k_hits_sort.) When most anchors are candidates the list would only add
+// copies, and the passes walk A itself.
 LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u32 * sketch, u64 * A, u64 * B, int n, int & n_out)
 {
     const int U = 4, step = U * w.nl;
@@ -425,6 +426,88 @@ LNR_PIPE u64 * binning_filter(const Warp & w, u32 * bins, u32 * sketch, u64 * A,
         }
     }
     wsync(w);
+    // the number of candidates is known from the sketch alone: the sum of the counters above 10
+    int n_cand = 0;
+    for (int j = w.lane; j < kSketch; j += w.nl) { u32 v = sketch[j]; if (v > 10) n_cand += (int)v; }
+    n_cand = wsum(w, n_cand);
+    if (2 * n_cand > n)
+    {
+        // dense case (repeat-rich reads, HIndex seeding: most anchors are candidates): a candidate list would only add
+        // copies -- exact counts, compaction and clearing walk A itself
+        for (int c = 0; c < n; c += step)
+        {
+            u64 v[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+            {
+                int i = c + k * w.nl + w.lane;
+                if (i < n)
+                {
+                    u32 bin = anchor_bin(v[k]);
+                    if (sketch[sketch_slot(bin)] > 10)
+                    {
+#ifdef __CUDA_ARCH__
+                        atomicAdd(&bins[bin], 1u);
+#else
+                        bins[bin]++;
+#endif
+                    }
+                }
+            }
+        }
+        wsync(w);
+        int id = 0;
+        for (int c = 0; c < n; c += step)
+        {
+            u64 v[U]; u32 cnt[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+            {
+                int i = c + k * w.nl + w.lane;
+                cnt[k] = 0;
+                if (i < n)
+                {
+                    u32 bin = anchor_bin(v[k]);
+                    if (sketch[sketch_slot(bin)] > 10) cnt[k] = bins[bin];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+            {
+                bool keep = cnt[k] > 10;
+                u32 bal = wballot(w, keep);
+                if (keep) B[id + popc_below(w, bal)] = v[k];
+                id += popc32(bal);
+            }
+        }
+        wsync(w);
+        for (int c = 0; c < n; c += step)
+        {
+            u64 v[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) { int i = c + k * w.nl + w.lane; v[k] = i < n ? A[i] : 0; }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+            {
+                int i = c + k * w.nl + w.lane;
+                if (i < n)
+                {
+                    u32 bin = anchor_bin(v[k]);
+                    if (sketch[sketch_slot(bin)] > 10) bins[bin] = 0;
+                }
+            }
+        }
+        wsync(w);
+        for (int j = w.lane; j < kSketch; j += w.nl) sketch[j] = 0;
+        wsync(w);
+        if (id != 0) { n_out = id; return B; }
+        n_out = n;
+        return A;
+    }
     int nc = 0;                                  // candidates, copied to B[0..nc) in the order of A
     for (int c = 0; c < n; c += step)
     {
