@@ -11,12 +11,15 @@
 //
 // Kernels (all HBM / issue / latency bound integer work, no tensor-core shaped math on this path)
 //   k_feat_genome / k_feat_reads      2-mer/48 features: one thread per 16-base cell, 3-cell sums through smem; reads:
-//                                     persistent CTAs, 2-bit packed cells, table of 2-mer increments per 4-base window
-//   k_idx_prep, k_idx_pass<FILL>      DIndex samples: genome tile staged in smem, one thread per 4 samples,
-//                                     emit rule by block max-scan, histogram / scatter with global atomics
+//                                     persistent CTAs, both strands of a tile per iteration (k_feat_pairs descriptors), a
+//                                     cell = two aligned 16-byte loads, 2-bit packing, 4 lookups in a 5-base window table
+//   k_idx_prep, k_idx_emit            DIndex samples: genome tile by one TMA bulk copy, packed window evaluation, emit rule
+//                                     by block max-scan, dense (X, record) pairs
+//   k_idx_partcount / k_idx_part / k_idx_count / k_idx_place / k_idx_rank   partition by X range, count / place / rank in L2
 //   k_scan_*                          device-wide exclusive scan (reduce / spine / apply), fused bucket omission
-//   k_idx_sort_buckets, k_idx_split_y, k_idx_dirx   bucket order, Y byte array, lookup sectors
-//   k_seed_prep / k_seed_count / k_seed_fill / k_seed_stats   per-read seeding, one thread per sample, exact-size output
+//   k_idx_split_y, k_idx_dirx         Y byte array, 64-byte lookup entries
+//   k_seed_prep / k_seed_count / k_seed_fill / k_seed_stats   per-read seeding, one thread per sample, exact-size output;
+//                                     random index reads with a 64-byte L2 fetch hint (a plain miss brings in 128 bytes)
 //   k_hits_sort / k_hits_chain / k_hits_blocks      the hit stage, one kernel per section (lnr_pipeline.h hits_sec_*):
 //                                     persistent warp per read + atomic queue, heaviest tasks first
 //   k_map_hits                        the same three sections in one kernel (re-map and big-arena passes)
@@ -562,129 +565,6 @@ struct TileAcc   // smem-staged tile with global fallback
     }
 };
 
-// FILL = false: histogram of emitted samples (createDIndex pass 1, index_util.cpp:1661-1699)
-// FILL = true : scatter records of non-omitted buckets (pass 2, :1737-1781)
-template <bool FILL>
-__global__ void __launch_bounds__(IT) k_idx_pass(const u8 * __restrict__ g, const IdxChunk * __restrict__ chunks,
-                                                 const u32 * __restrict__ tile0, u32 n_chunks, u32 * __restrict__ cnt,
-                                                 const i32 * __restrict__ dir, u32 * __restrict__ fillc, u64 * __restrict__ hs,
-                                                 u32 x_lo, u32 x_hi)
-{
-    // [x_lo, x_hi): minimizer range owned by this shard (multi-GPU build partitions the 2^26 buckets)
-    __shared__ __align__(16) u8 s_b[ISM];
-    __shared__ i32 s_warp[IT / 32];
-    __shared__ i32 s_back;
-    // chunk of this tile
-    u32 tile = blockIdx.x;
-    u32 lo = 0, hi = n_chunks;
-    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tile0[mid] <= tile) lo = mid; else hi = mid; }
-    const IdxChunk ch = chunks[lo];
-    const u8 * gs = g + ch.base_off;
-    i64 m0 = (i64)(tile - tile0[lo]) * ITILE;
-    i64 nm = ch.n_samples - m0 < ITILE ? ch.n_samples - m0 : ITILE;
-    // stage bases [j0 - 8, j0 + 9*nm + 32) ; j0 = first sample position of the tile
-    i64 j0 = ch.t_str + kIdxMinStep + 9 * m0;
-    i64 p0 = (j0 - 8) & ~15LL;
-    if (p0 < 0) p0 = 0;
-    i64 p1 = j0 + 9 * nm + 32;
-    if (p1 > ch.len) p1 = ch.len;
-    {
-        i64 nb = p1 - p0;
-        i64 nv = nb >> 4;
-        const uint4 * src = (const uint4 *)(gs + p0);
-        uint4 * dst = (uint4 *)s_b;
-        for (i64 i = threadIdx.x; i < nv; i += IT) dst[i] = __ldg(src + i);
-        for (i64 i = (nv << 4) + threadIdx.x; i < nb; i += IT) s_b[i] = __ldg(gs + p0 + i);
-    }
-    __syncthreads();
-    TileAcc acc = {s_b, p0, p1, gs, ch.len};
-    // each thread: IS consecutive samples
-    u32 X[IS]; u64 rec[IS];
-    i64 mt = m0 + (i64)threadIdx.x * IS;
-#pragma unroll
-    for (int q = 0; q < IS; q++)
-    {
-        X[q] = 0xffffffffu; rec[q] = 0;
-        if (mt + q < ch.n_samples && (i64)threadIdx.x * IS + q < nm) idx_sample(acc, ch, mt + q, X[q], rec[q]);
-    }
-    // X of the sample just before this thread's first one
-    u32 xprev = __shfl_up_sync(0xffffffffu, X[IS - 1], 1);
-    __shared__ u32 s_last[IT / 32];
-    if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = X[IS - 1];
-    // look-back of the tile's first sample: number of consecutive earlier samples with the same X
-    if (threadIdx.x < 32)
-    {
-        i32 back = 0;
-        if (m0 > 0)
-        {
-            u32 X0 = __shfl_sync(0xffffffffu, X[0], 0);
-            GAcc ga = {gs, ch.len};
-            i64 m = m0 - 1;
-            while (true)
-            {
-                i64 mm = m - threadIdx.x;
-                bool same = false;
-                if (mm >= 0) { u32 Xm; u64 r; idx_sample(ga, ch, mm, Xm, r); same = Xm == X0; }
-                u32 neq = __ballot_sync(0xffffffffu, !same);
-                if (neq) { back += __ffs((int)neq) - 1; break; }
-                back += 32; m -= 32;
-            }
-        }
-        if (threadIdx.x == 0) s_back = back;
-    }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) xprev = threadIdx.x == 0 ? 0xfffffffeu : s_last[(threadIdx.x >> 5) - 1];
-    // run start (tile-relative sample index; negative = before the tile) by max-scan
-    i32 local_i = (i32)threadIdx.x * IS;
-    i32 rs[IS];
-    i32 run = -0x40000000;   // "unknown, inherited"
-    {
-        u32 xp = xprev;
-#pragma unroll
-        for (int q = 0; q < IS; q++)
-        {
-            bool brk = X[q] != xp;
-            if (threadIdx.x == 0 && q == 0) brk = false;   // resolved through s_back
-            if (brk) run = local_i + q;
-            rs[q] = run;
-            xp = X[q];
-        }
-    }
-    // inclusive max-scan of `run` across threads
-    i32 v = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { i32 t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v = max(v, t); }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
-    __syncthreads();
-    i32 carry = -0x40000000;
-    for (int wq = 0; wq < (int)(threadIdx.x >> 5); wq++) carry = max(carry, s_warp[wq]);
-    i32 excl = __shfl_up_sync(0xffffffffu, v, 1);
-    if ((threadIdx.x & 31) == 0) excl = -0x40000000;
-    excl = max(excl, carry);
-    i32 tile_start_run = -s_back;   // run start of sample 0 (<= 0)
-#pragma unroll
-    for (int q = 0; q < IS; q++)
-    {
-        i32 r = rs[q] > -0x40000000 ? rs[q] : (excl > -0x40000000 ? excl : tile_start_run);
-        i32 idx = local_i + q;
-        bool valid = idx < nm;
-        bool emit = valid && (((idx - r) & 1) == 0) && X[q] >= x_lo && X[q] < x_hi;
-        if (emit)
-        {
-            if (!FILL) atomicAdd(&cnt[X[q]], 1u);
-            else
-            {
-                i32 b = dir[X[q]], e = dir[X[q] + 1];
-                if (e - b > 0)
-                {
-                    u32 slot = atomicAdd(&fillc[X[q]], 1u);
-                    hs[(u64)b + slot] = rec[q];
-                }
-            }
-        }
-    }
-}
-
 // ---- device-wide exclusive scan of u32 (reduce / spine / apply), 4096 items per CTA --------------------
 static const int ST = 256, SI = 16, STILE = ST * SI;
 // transform applied to the input: cap > 0 -> values > cap become 0 and are written back (bucket omission)
@@ -794,24 +674,6 @@ __global__ void k_idx_dirx(const i32 * __restrict__ dir, const u8 * __restrict__
     o[3] = make_uint4(wds[10], wds[11], wds[12], wds[13]);
 }
 
-// ascending order inside each bucket (index_util.cpp:1788-1796); one thread per bucket, buckets <= 400
-__global__ void k_idx_sort_buckets(const i32 * __restrict__ dir, u64 * __restrict__ hs, u32 n_buckets)
-{
-    u32 X = blockIdx.x * blockDim.x + threadIdx.x;
-    if (X >= n_buckets) return;
-    i32 b = dir[X], e = dir[X + 1];
-    int n = e - b;
-    if (n < 2) return;
-    u64 * a = hs + b;
-    for (int i = 1; i < n; i++)
-    {
-        u64 v = a[i];
-        int j = i - 1;
-        while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
-        a[j + 1] = v;
-    }
-}
-
 // =====================================================================================================
 // seeding (getDIndexMatchAll, pmpfinder.cpp:1856)
 // =====================================================================================================
@@ -862,23 +724,6 @@ __device__ __forceinline__ u32 find_task(const SeedTask * tasks, u32 n_tasks, u6
 {
     u32 lo = 0, hi = n_tasks;
     while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tasks[mid].sample0 <= s) lo = mid; else hi = mid; }
-    return lo;
-}
-// the same answer (the last task whose sample0 is <= s) by a 32-ary search of the whole warp: 4 dependent loads for 65 536
-// tasks instead of 16 -- the search sits at the head of every warp's chain of round trips
-__device__ __forceinline__ u32 find_task_warp(const SeedTask * tasks, u32 n_tasks, u64 s, unsigned lane)
-{
-    u32 lo = 0, hi = n_tasks;
-    while (hi - lo > 1)
-    {
-        const u32 step = (hi - lo + 31u) / 32u;
-        const u32 idx = lo + step * lane;
-        const bool le = idx < hi && tasks[idx].sample0 <= s;      // lane 0 probes lo itself; true for a prefix of the lanes
-        const u32 m = __ballot_sync(0xffffffffu, le) | 1u;
-        const u32 top = 31u - (u32)__clz((int)m);
-        lo += step * top;
-        hi = min(hi, lo + step);
-    }
     return lo;
 }
 
