@@ -619,24 +619,79 @@ __global__ void __launch_bounds__(1024) k_scan_spine(u64 * __restrict__ partial,
     if (threadIdx.x == 0) *total = s_carry;
 }
 // OutT = i32 (dir) or u32 / u64 offsets
+// A warp owns 512 consecutive items as 4 chunks of 128 and a lane 4 consecutive items of every chunk, so that a warp's loads
+// are contiguous 512-byte runs and its stores contiguous 0.5 / 1-KB runs (16 consecutive items per thread -- the first
+// version -- made every request touch 32 sectors: the pass ran at 1.9 TB/s).
 template <class OutT>
 __global__ void __launch_bounds__(ST) k_scan_apply(const u32 * __restrict__ in, u64 n, const u64 * __restrict__ partial, OutT * __restrict__ out)
 {
+    static_assert(STILE == (ST / 32) * 512, "a warp scans 512 items");
     __shared__ u64 s[ST / 32];
-    u64 base = (u64)blockIdx.x * STILE + (u64)threadIdx.x * SI;
-    u32 v[SI];
-    u64 sum = 0;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u64 wb = (u64)blockIdx.x * STILE + (u64)wid * 512;
+    const bool vin = ((uintptr_t)in & 15) == 0, vout = ((uintptr_t)out & 15) == 0;
+    u32 v[4][4];
+    u64 lsum[4], incl[4], ctot[4];
 #pragma unroll
-    for (int i = 0; i < SI; i++) { u64 idx = base + i; v[i] = idx < n ? in[idx] : 0; sum += v[i]; }
-    u64 x = sum;
-    for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += t; }
-    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+    for (int j = 0; j < 4; j++)
+    {
+        const u64 idx = wb + 128u * j + 4u * lane;
+        if (vin && idx + 3 < n)
+        {
+            const uint4 q = *(const uint4 *)(in + idx);
+            v[j][0] = q.x; v[j][1] = q.y; v[j][2] = q.z; v[j][3] = q.w;
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[j][k] = idx + k < n ? in[idx + k] : 0u;
+        }
+        lsum[j] = (u64)v[j][0] + v[j][1] + v[j][2] + v[j][3];
+    }
+    u64 wtot = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        u64 x = lsum[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += t; }
+        incl[j] = x;
+        ctot[j] = __shfl_sync(0xffffffffu, x, 31);
+        wtot += ctot[j];
+    }
+    if (lane == 0) s[wid] = wtot;
     __syncthreads();
-    u64 wbase = 0;
-    for (int i = 0; i < (int)(threadIdx.x >> 5); i++) wbase += s[i];
-    u64 run = partial[blockIdx.x] + wbase + x - sum;
+    u64 carry = partial[blockIdx.x];
+    for (unsigned i = 0; i < wid; i++) carry += s[i];
 #pragma unroll
-    for (int i = 0; i < SI; i++) { u64 idx = base + i; if (idx < n) out[idx] = (OutT)run; run += v[i]; }
+    for (int j = 0; j < 4; j++)
+    {
+        const u64 idx = wb + 128u * j + 4u * lane;
+        const u64 r0 = carry + incl[j] - lsum[j], r1 = r0 + v[j][0], r2 = r1 + v[j][1], r3 = r2 + v[j][2];
+        if (vout && idx + 3 < n)
+        {
+            if (sizeof(OutT) == 8)
+            {
+                ulonglong2 a, b2;
+                a.x = r0; a.y = r1; b2.x = r2; b2.y = r3;
+                ((ulonglong2 *)(out + idx))[0] = a; ((ulonglong2 *)(out + idx))[1] = b2;
+            }
+            else
+            {
+                uint4 q;
+                q.x = (u32)(OutT)r0; q.y = (u32)(OutT)r1; q.z = (u32)(OutT)r2; q.w = (u32)(OutT)r3;
+                *(uint4 *)(out + idx) = q;
+            }
+        }
+        else
+        {
+            if (idx < n) out[idx] = (OutT)r0;
+            if (idx + 1 < n) out[idx + 1] = (OutT)r1;
+            if (idx + 2 < n) out[idx + 2] = (OutT)r2;
+            if (idx + 3 < n) out[idx + 3] = (OutT)r3;
+        }
+        carry += ctot[j];
+    }
 }
 
 // SoA split for the seeding count pass: the Y-key rule only looks at the low byte of a record (Y is 8 bits,
