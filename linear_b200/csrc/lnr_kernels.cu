@@ -702,8 +702,8 @@ __global__ void k_idx_split_y(const u64 * __restrict__ hs, u64 n, u8 * __restric
     if (i < n) hsy[i] = (u8)(hs[i] & 0xff);
 }
 
-// Lookup entry of the seeding count pass: dir[X], the bucket size and the bucket's first 56 Y keys in 64 bytes = the two
-// sectors one DRAM access brings in anyway (ncu: every L2 read miss of the random-access kernels fetches 64 B). A seed
+// Lookup entry of the seeding count pass: dir[X], the bucket size and the bucket's first 56 Y keys in 64 bytes = exactly what
+// one L2 miss brings in when the load carries the 64-byte fetch hint (ld_dirx below; a plain load fetches 128 bytes). A seed
 // whose bucket has <= 56 records (95 % of them at 3.1 Gbase) costs one random DRAM access; with 32-byte entries (24 keys)
 // every second seed paid a second, dependent one into hsy.
 static const int kDirxKeys = 56, kDirxQuads = 4;      // keys per entry, uint4 per entry
