@@ -104,6 +104,10 @@ int lnr_comm_create(lnr_ctx *, const uint8_t id[128], int rank, int n_ranks, lnr
 int lnr_comm_from_nccl(lnr_ctx *, void * nccl_comm /* ncclComm_t */, int rank, int n_ranks, lnr_comm ** out);
 void lnr_comm_destroy(lnr_comm *);
 int lnr_index_build_sharded(lnr_ctx *, const lnr_genome *, int index_type, unsigned threads_sem, lnr_comm *, lnr_index ** out);
+/* The X ranges the sharded HIndex build uses (host arithmetic, no device needed): from the number of (head, body) pairs per
+ * X, cuts[0..n_ranks] with cuts[0] = 0, cuts[n_ranks] = n_x and rank r owning X in [cuts[r], cuts[r+1]); cut r is the first
+ * X at which the running pair count reaches r/n_ranks of all pairs. */
+int lnr_hindex_shard_cuts(const uint32_t * pairs_per_x, uint32_t n_x, int n_ranks, uint32_t * cuts);
 /* device-to-device copies of the index arrays (dev_dir: int32[2^26+1], dev_hs: uint64[>= n_hs]; either may be NULL) */
 int lnr_index_export_dindex_device(const lnr_index *, int32_t * dev_dir, uint64_t * dev_hs, uint64_t hs_cap);
 /* wraps assembled device arrays into an index (copies them) */

@@ -5,4 +5,4 @@ api.py (ctypes mirror of the reference's operator interface for the path) and da
 """
 from . import datagen  # noqa: F401
 from .api import (cords_to_records, Comm, create_index_sharded, Context, Features, Genome, Index, LnrError, Reads, apx_map_batch, apx_map_batch_packed, pack_dna5, cords_end, create_features,  # noqa: F401
-                  create_index, load_library, read_features, selftest_sort)
+                  create_index, hindex_shard_cuts, load_library, read_features, selftest_sort)

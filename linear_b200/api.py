@@ -31,7 +31,7 @@ EXPORTS = [
     "lnr_features_build", "lnr_features_count", "lnr_features_download", "lnr_features_destroy",
     "lnr_index_build", "lnr_index_build_shard", "lnr_index_export_dindex", "lnr_index_export_hindex", "lnr_index_export_dindex_device",
     "lnr_index_from_device", "lnr_index_save", "lnr_index_load", "lnr_index_destroy", "lnr_nccl_unique_id", "lnr_comm_create", "lnr_comm_from_nccl", "lnr_comm_destroy",
-    "lnr_index_build_sharded", "lnr_apxmap_batch", "lnr_apxmap_batch_packed", "lnr_pack_dna5",
+    "lnr_index_build_sharded", "lnr_hindex_shard_cuts", "lnr_apxmap_batch", "lnr_apxmap_batch_packed", "lnr_pack_dna5",
     "lnr_apxmap_batch_device", "lnr_cords_to_records", "lnr_last_batch_counters", "lnr_last_batch_diag", "lnr_last_batch_stage_cycles", "lnr_read_features", "lnr_selftest_sort",
     "lnr_reads_parse", "lnr_reads_parse_device", "lnr_reads_info", "lnr_reads_download", "lnr_reads_device", "lnr_reads_destroy", "lnr_apxmap_reads",
 ]
@@ -106,6 +106,7 @@ def load_library() -> C.CDLL:
     lib.lnr_comm_destroy.argtypes = [vp]
     lib.lnr_comm_destroy.restype = None
     lib.lnr_index_build_sharded.argtypes = [vp, vp, C.c_int, C.c_uint, vp, C.POINTER(vp)]
+    lib.lnr_hindex_shard_cuts.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
     lib.lnr_apxmap_batch.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, u64p, vp, u64p, C.c_uint64,
                                      C.POINTER(DebugOut)]
     lib.lnr_apxmap_batch_packed.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, vp, vp, u64p, vp, u64p, C.c_uint64,
@@ -352,6 +353,17 @@ class Comm:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+def hindex_shard_cuts(pairs_per_x: np.ndarray, n_ranks: int) -> np.ndarray:
+    """X ranges of the sharded HIndex build (lnr_hindex_shard_cuts; host arithmetic, no device needed): cuts[0..n_ranks]"""
+    lib = load_library()
+    h = np.ascontiguousarray(pairs_per_x, dtype=np.uint32)
+    cuts = np.zeros(n_ranks + 1, dtype=np.uint32)
+    rc = lib.lnr_hindex_shard_cuts(h.ctypes.data_as(C.POINTER(C.c_uint32)), len(h), n_ranks, cuts.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if rc != 0:
+        raise LnrError(rc, "lnr_hindex_shard_cuts")
+    return cuts
 
 
 def create_index_sharded(ctx, genome, comm: "Comm", index_type=1, threads=4) -> Index:

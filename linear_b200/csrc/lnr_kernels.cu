@@ -2589,6 +2589,24 @@ struct ShardPlan { lnr_comm * comm; };   // non-null: build one minimizer range 
 static int dindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned threads_sem, u32 x_lo, u32 x_hi, lnr_comm * comm, lnr_index ** out);
 static int hindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned T, lnr_comm * comm, lnr_index ** out);
 
+// X ranges of the sharded HIndex build: cut r = the first X at which the running pair count reaches r/n_ranks of all pairs
+// (pure host arithmetic on the per-X histogram every rank computes identically; exported so that the CPU tests can check it)
+int lnr_hindex_shard_cuts(const uint32_t * pairs_per_x, uint32_t n_x, int n_ranks, uint32_t * cuts)
+{
+    if (!pairs_per_x || !cuts || n_ranks < 1) return LNR_E_ARG;
+    u64 all = 0;
+    for (u32 x = 0; x < n_x; x++) all += pairs_per_x[x];
+    for (int r = 0; r <= n_ranks; r++) cuts[r] = n_x;
+    cuts[0] = 0;
+    u64 run = 0; int r = 1;
+    for (u32 x = 0; x < n_x && r < n_ranks; x++)
+    {
+        while (r < n_ranks && run >= (all * (u64)r + (u64)n_ranks - 1) / (u64)n_ranks) cuts[r++] = x;
+        run += pairs_per_x[x];
+    }
+    return LNR_OK;
+}
+
 int lnr_index_build_sharded(lnr_ctx * ctx, const lnr_genome * g, int index_type, unsigned threads_sem, lnr_comm * comm, lnr_index ** out)
 {
     if (!ctx || !g || !comm || !out || threads_sem == 0) return LNR_E_ARG;
@@ -2876,19 +2894,8 @@ static int hindex_build(lnr_ctx * ctx, const lnr_genome * g, unsigned T, lnr_com
         std::vector<u32> xh(kXRangeH);
         CKH(cudaMemcpyAsync(xh.data(), d_xhist, (size_t)kXRangeH * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CKH(cudaStreamSynchronize(ctx->stream));
-        u64 all = 0;
-        for (u32 x = 0; x < kXRangeH; x++) all += xh[x];
-        // cut r = the first X at which the running count reaches r/n_ranks of all pairs
         std::vector<u32> cut((size_t)comm->n_ranks + 1, kXRangeH);
-        cut[0] = 0;
-        {
-            u64 run = 0; int r = 1;
-            for (u32 x = 0; x < kXRangeH && r < comm->n_ranks; x++)
-            {
-                while (r < comm->n_ranks && run >= (all * (u64)r + (u64)comm->n_ranks - 1) / (u64)comm->n_ranks) cut[(size_t)r++] = x;
-                run += xh[x];
-            }
-        }
+        lnr_hindex_shard_cuts(xh.data(), kXRangeH, comm->n_ranks, cut.data());
         x_lo = cut[(size_t)comm->rank]; x_hi = cut[(size_t)comm->rank + 1];
         pair_cap = 0;
         for (u32 x = x_lo; x < x_hi; x++) pair_cap += xh[x];

@@ -94,3 +94,39 @@ def test_assemble_dindex_from_hash_range_shards():
             parts.append((ds, hs[d[s * per]:d[(s + 1) * per]]))
         d2, h2 = sharding.assemble_dindex(parts)
         assert np.array_equal(d2, d) and np.array_equal(h2, hs)
+
+
+def test_hindex_shard_cuts_balance_and_reassemble():
+    """host logic of the sharded HIndex build (lnr_index_build_sharded, index_type 2): the X ranges every rank derives from the
+    per-X pair histogram are ordered, cover the 18-bit X axis, balance the pairs up to one X's worth, and -- a block being one
+    X -- the ranks' slices of ysa, concatenated in rank order, are ysa itself"""
+    from cases import make_case
+    from cpu_checkers import Oracle
+    import linear_b200 as lb
+    g, reads, bases, offs, T, preset = make_case("repeat_ont")
+    ysa, empty_dir, kv, tl = Oracle(g, threads=T, preset=preset, index_type=2).hindex()
+    words = ysa[:empty_dir]
+    heads = np.flatnonzero((words >> np.uint64(63)) == 0)          # every body carries bit 63
+    X = (words[heads] & np.uint64((1 << 40) - 1)).astype(np.int64)
+    n_body = (words[heads] >> np.uint64(40)).astype(np.int64) - 1  # head = (bodies + 1) << 40 | X
+    assert np.all(np.diff(X) > 0) and int(n_body.sum()) + len(heads) == empty_dir
+    NX = 1 << 18
+    hist = np.zeros(NX, dtype=np.uint32)
+    hist[X] = n_body
+    total = int(hist.sum())
+    for n in (1, 2, 3, 8, 64):
+        cuts = lb.hindex_shard_cuts(hist, n).astype(np.int64)
+        assert cuts[0] == 0 and cuts[n] == NX and np.all(np.diff(cuts) >= 0)
+        per = [int(hist[cuts[r]:cuts[r + 1]].sum()) for r in range(n)]
+        assert sum(per) == total
+        assert max(per) <= -(-total // n) + int(hist.max())
+        pieces = []
+        for r in range(n):
+            blk = np.flatnonzero((X >= cuts[r]) & (X < cuts[r + 1]))
+            if len(blk):
+                pieces.append(words[heads[blk[0]]:heads[blk[-1]] + n_body[blk[-1]] + 1])
+                assert len(pieces[-1]) == per[r] + len(blk)         # pairs + blocks: what the rank reports in the all-gather
+        assert np.array_equal(np.concatenate(pieces), words)
+    # degenerate inputs
+    assert list(lb.hindex_shard_cuts(np.zeros(16, np.uint32), 4)) == [0, 0, 0, 0, 16]
+    assert list(lb.hindex_shard_cuts(np.array([5, 0, 0, 0], np.uint32), 2)) == [0, 1, 4]
